@@ -1,0 +1,573 @@
+"""
+CPU oracle for the alplib Monte-Carlo flux-and-event hot path.
+
+TEST INFRASTRUCTURE ONLY.  This module is a NumPy/SciPy restatement of the reference algorithm
+(athompson-git/alplib).  It may be imported ONLY by `tests/`, by `__graft_entry__.smoke()` and by the
+`cpu_baseline` / `--impl reference` legs of `bench.py` -- always as the checker or as the timed CPU
+baseline, never as part of the product path (`alplib_b200/` never imports it).
+
+Parity status: PINNED.  The reference publishes no golden vectors for this path, so the
+oracle is pinned against outputs of the unmodified reference itself, run in the build container with
+identical replayed uniforms (`tests/golden/make_golden.py` -> `tests/golden/*.npz`) and against the
+known-answer values of SURVEY.md section 8c (`tests/test_oracle_golden.py`).
+
+Every function cites the reference file:line (relative to the reference repository root) it follows.
+Operation order follows the reference expression by expression so that FP64 results agree to the last few
+ulp (the remaining differences are NumPy scalar-vs-array libm paths, SURVEY.md section 7 hard part 6).
+
+Third-party arithmetic used by the reference on this path and reused here: NumPy (`np.interp`, `np.unique`,
+ufuncs), SciPy `integrate.quad` (fmath.py:36) and `special.gamma` (fluxes.py:259); reference pins
+numpy==2.3.3 / scipy==1.16.2 (requirements.txt:2-3).
+"""
+
+import json
+import os
+
+import numpy as np
+from numpy import pi
+from scipy.integrate import quad
+from scipy.special import gamma as _gamma
+
+# ---------------------------------------------------------------------------------------------------------
+# constants.py:14-66 (values restated bit for bit; KAT in tests/test_oracle_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+ALPHA = 1 / 137                       # constants.py:14
+C_LIGHT = 2.99792458e10               # constants.py:20
+HBARC = 1.97236e-11                   # constants.py:22
+AVOGADRO = 6.022e23                   # constants.py:29
+M_E = 0.511                           # constants.py:32
+METER_BY_MEV = 6.58212e-22 * 2.998e8  # constants.py:60
+MEV2_CM2 = (METER_BY_MEV * 100) ** 2  # constants.py:65
+S_PER_DAY = 3600 * 24                 # constants.py:66
+MEV_PER_KG = 5.6095887e29             # constants.py:61
+
+_DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "alplib_b200", "data")
+
+
+class UniformSource:
+    """Source of U[0,1) variates consumed in the reference's draw order.
+
+    Wraps either a legacy `np.random.RandomState` (so `RandomState(s)` replays `np.random.seed(s)` of the
+    reference bit for bit: legacy `uniform(lo,hi,n) = lo + (hi-lo)*random_sample(n)`) or a preset 1-D array.
+    Everything handed out is logged so it can be injected into the CUDA kernels.
+    """
+
+    def __init__(self, src):
+        self._rs = src if isinstance(src, np.random.RandomState) else None
+        self._arr = None if self._rs is not None else np.asarray(src, dtype=np.float64).ravel()
+        self._pos = 0
+        self.log = []
+
+    def take(self, n=None):
+        k = 1 if n is None else int(n)
+        if self._rs is not None:
+            u = self._rs.random_sample(k)
+        else:
+            u = self._arr[self._pos:self._pos + k]
+            if u.shape[0] != k:
+                raise ValueError("UniformSource exhausted")
+            self._pos += k
+        self.log.append(u)
+        return u[0] if n is None else u
+
+    def uniform(self, lo, hi, n=None):
+        # numpy legacy: loc + scale * double  (mtrand legacy_uniform)
+        return lo + (hi - lo) * self.take(n)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# materials.py:12-46  (host-side input container)
+# ---------------------------------------------------------------------------------------------------------
+class Material:
+    def __init__(self, material_name, fiducial_mass=1.0, volume=1.0, density=1.0):
+        with open(os.path.join(_DATA_DIR, "mat_params.json")) as f:
+            mat_file = json.load(f)
+        if material_name not in mat_file:
+            raise Exception("No such detector in mat_params.json.")          # materials.py:46
+        info = mat_file[material_name]
+        self.mat_name = material_name
+        self.iso = info["iso"]
+        self.z = np.array(info["z"])
+        self.n = np.array(info["n"])
+        self.m = np.array(info["m"])
+        self.frac = np.array(info["frac"])
+        self.density = info["density"]
+        self.rad_length = info["rad_length"]
+        self.fid_mass = fiducial_mass
+        self.volume = volume
+        # materials.py:42-43 -- uses the ctor's density argument, not the JSON one
+        self.ntargets = density * volume / (np.dot(self.m, self.iso * self.frac) / MEV_PER_KG / 1e-3)
+        self.ndensity = density / (np.dot(self.m, self.iso * self.frac) / MEV_PER_KG / 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# photon_xs.py:18-52  AbsCrossSection
+# ---------------------------------------------------------------------------------------------------------
+_XS_DIM = {"NaI": 149.89 / AVOGADRO, "CsI": 259.81 / AVOGADRO, "CH2": 14.027 / AVOGADRO,
+           "N2": 28.0 / AVOGADRO, "O2": 32.0 / AVOGADRO, "TeO2": 32.0 / AVOGADRO}   # photon_xs.py:27-38
+
+
+class AbsCrossSection:
+    def __init__(self, material):
+        name = material.mat_name if hasattr(material, "mat_name") else str(material)
+        self.mat_name = name
+        self.xs_dim = _XS_DIM.get(name, 1e-24)                                       # photon_xs.py:20
+        fpath = os.path.join(_DATA_DIR, "photon_absorption", "photon_abs_" + name + ".txt")
+        pe = np.genfromtxt(fpath, skip_header=3)                                     # photon_xs.py:25
+        self.pe_data = pe[np.unique(pe[:, 0], return_index=True)[1]]                 # photon_xs.py:42-43
+        self.log10_e = np.log10(self.pe_data[:, 0])
+        self.log10_xs = np.log10(self.xs_dim * self.pe_data[:, 1])
+
+    def sigma_mev(self, E):                                                          # photon_xs.py:48-49
+        return 10 ** np.interp(np.log10(E), self.log10_e, self.log10_xs, left=0.0, right=0.0) / MEV2_CM2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# decay.py:10-52  widths
+# ---------------------------------------------------------------------------------------------------------
+def W_gg(g_agamma, ma):                                                              # decay.py:10-13
+    return g_agamma ** 2 * ma ** 3 / (64 * pi)
+
+
+def W_ee(g_ae, ma):                                                                  # decay.py:26-29
+    return g_ae ** 2 * ma * np.sqrt(1 - (2 * M_E / ma) ** 2) / (8 * pi) \
+        if 1 - 4 * (M_E / ma) ** 2 > 0 else 0.0
+
+
+def fp2(tau):                                                                        # decay.py:35-37
+    return np.arcsin(1 / np.sqrt(tau)) ** 2 if tau >= 1 \
+        else pi ** 2 / 4 + np.log((1 + np.sqrt(1 - tau)) / (1 - np.sqrt(1 - tau))) ** 2 / 4
+
+
+def b1(tau):                                                                         # decay.py:42-43
+    return 1 - tau * fp2(tau)
+
+
+def W_gg_loop(g_af, ma, mf):                                                         # decay.py:48-52
+    g_agamma_eff = g_af * ALPHA * b1(np.power(2 * mf / ma, 2)) / (4 * pi)
+    return W_gg(g_agamma_eff, ma)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# prod_xs.py  production cross sections
+# ---------------------------------------------------------------------------------------------------------
+def primakoff_sigma(eg, g, ma, z, r0=2.2e-10 / METER_BY_MEV):                        # prod_xs.py:99-104
+    prefactor = (g * z) ** 2 / (2 * 137)
+    eta2 = r0 ** 2 * eg ** 2
+    return np.heaviside(eg - ma, 0.0) * prefactor * (((2 * eta2 + 1) / (4 * eta2)) * np.log(1 + 4 * eta2) - 1)
+
+
+def compton_dsigma_dea(ea, eg, g, ma, z=1):                                          # prod_xs.py:155-169
+    a = 1 / 137
+    aa = g ** 2 / 4 / pi
+    s = 2 * M_E * eg + M_E ** 2
+    x = ((ma ** 2 / (2 * eg * M_E)) - ea / eg + 1)
+    xmin = ((s - M_E ** 2) * (s - M_E ** 2 + ma ** 2)
+            - (s - M_E ** 2) * np.sqrt((s - M_E ** 2 + ma ** 2) ** 2 - 4 * s * ma ** 2)) / (2 * s * (s - M_E ** 2))
+    xmax = ((s - M_E ** 2) * (s - M_E ** 2 + ma ** 2)
+            + (s - M_E ** 2) * np.sqrt((s - M_E ** 2 + ma ** 2) ** 2 - 4 * s * ma ** 2)) / (2 * s * (s - M_E ** 2))
+    thresh = np.heaviside(eg - ma, 0.0) * np.heaviside(x - xmin, 0.0) * np.heaviside(xmax - x, 0.0)
+    return z * thresh * (1 / eg) * pi * a * aa / (s - M_E ** 2) * (
+        x / (1 - x) * (-2 * ma ** 2 / (s - M_E ** 2) ** 2 * (s - M_E ** 2 / (1 - x) - ma ** 2 / x) + x))
+
+
+def brem_dsigma_dea(Ea, Ee, g, ma, z):                                               # prod_xs.py:209-221
+    r0 = ALPHA / M_E
+    x = Ea / Ee
+    f = np.power(ma / (x * M_E), 2) * (1 - x)
+    ln_el = np.log(184 * np.power(z, -1 / 3))
+    ln_inel = np.log(1194 * np.power(z, -2 / 3))
+    prefactor = 2 * r0 ** 2 * g ** 2 / 4 / pi / Ee
+    phase_space = ((x * (1 + f / 1.5) / np.power(1 + f, 2)) * (z ** 2 * ln_el + z * ln_inel)
+                   + x * (z ** 2 + z) * ((1 + f) * np.log(1 + f) / (3 * f ** 2)
+                                         - (1 + 4 * f + 2 * f ** 2) / (3 * f * np.power(1 + f, 2))))
+    return prefactor * phase_space * np.heaviside(phase_space, 0.0)
+
+
+def brem_dsigma_dx_vector(x, coupling, ma, z):                                       # prod_xs.py:313-323
+    ln_el = np.log(184 * np.power(z, -1 / 3))
+    ln_inel = np.log(1194 * np.power(z, -2 / 3))
+    chi = z ** 2 * ln_el + z * ln_inel
+    prefactor = chi * (4 * ALPHA ** 2 * coupling ** 2) / (4 * pi)
+    return prefactor * (1 - x + x ** 2 / 3) / ((ma ** 2 * (1 - x) / x) + x * M_E ** 2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# det_xs.py  detection cross sections
+# ---------------------------------------------------------------------------------------------------------
+def iprimakoff_sigma(ea, g, ma, z, r0=2.2e-10 / METER_BY_MEV):                       # det_xs.py:37-42
+    prefactor = (g * z) ** 2 / (2 * 137)
+    eta2 = r0 ** 2 * (ea ** 2 - ma ** 2)
+    with np.errstate(all="ignore"):
+        return np.heaviside(ea - ma, 0.0) * prefactor * (((2 * eta2 + 1) / (4 * eta2)) * np.log(1 + 4 * eta2) - 1)
+
+
+def icompton_sigma(ea, ma, g, z=1):                                                  # det_xs.py:89-98
+    with np.errstate(all="ignore"):
+        y = 2 * M_E * ea + ma ** 2
+        pa = np.sqrt(np.clip(ea ** 2 - ma ** 2, a_min=0.0, a_max=np.inf))
+        prefactor = np.heaviside(ea - ma, 0.0) \
+            * np.heaviside(ea - ma * np.sqrt(2 * M_E ** 2 + ma ** 2) / (2 * M_E), 0.0) \
+            * z * ALPHA * np.power(g / M_E, 2) / (8 * pa)
+        return np.nan_to_num(prefactor * ((2 * M_E ** 2 * (M_E + ea) * y) / np.power(M_E ** 2 + y, 2)
+                                          + (4 * M_E * (ma ** 4 + 2 * np.power(ma * M_E, 2) - np.power(2 * M_E * ea, 2)))
+                                          / (y * (M_E ** 2 + y))
+                                          + np.log((M_E + ea + pa) / (M_E + ea - pa))
+                                          * (np.power(2 * M_E * pa, 2) + ma ** 4) / (pa * y)))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fmath.py:33-36, fluxes.py:257-266  track-length helpers
+# ---------------------------------------------------------------------------------------------------------
+def nu_integral(x, alpha, T_max=np.inf):                                             # fmath.py:33-36
+    f = lambda t: np.power(x, t + alpha) / _gamma(t + 1 + alpha)
+    return quad(f, 0.0, T_max)[0]
+
+
+def track_length_prob(Ei, Ef, t):                                                    # fluxes.py:257-259
+    b = 4 / 3
+    with np.errstate(all="ignore"):
+        return np.heaviside(Ei - Ef, 1.0) * abs(np.power(np.log(Ei / Ef), b * t - 1) / (Ei * _gamma(b * t)))
+
+
+def track_length_integrated_prob(Ei, Ef, T_max=5.0):                                 # fluxes.py:264-266
+    return (3 / 4) * np.heaviside(Ei - Ef, 1.0) * nu_integral(np.log(Ei / Ef), -1, 4 * T_max / 3) / Ei
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fluxes.py:43-65 + 153-162  propagate (+ isotropic acceptance)
+# ---------------------------------------------------------------------------------------------------------
+def propagate(e_a, wgt, ma, decay_width, rescale_factor, det_dist, det_length,
+              timing_window=None, geom_accept=None, geom_accept_f64=False):
+    """Returns dict with the FP64 pre-cast weights (`decay_w64`, `scatter_w64`, before the acceptance factor)
+    and the reference's float32 attributes (`decay_w`, `scatter_w`, after fluxes.py:159-162).
+
+    `geom_accept` None == `is_isotropic=False`.  The in-place `*=` of fluxes.py:161-162 runs in float32 when
+    `geom_accept` is a Python float (NEP 50 weak scalar) and in float64-then-cast when it is an np.float64
+    (`geom_accept_f64=True`)."""
+    e_a = np.asarray(e_a, dtype=np.float64)
+    wgt = np.array(wgt, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        p_a = np.sqrt(e_a ** 2 - ma ** 2)                                            # fluxes.py:48
+        v_a = p_a / e_a                                                              # :49
+        boost = e_a / ma                                                             # :50
+        tau = boost / decay_width if decay_width > 0.0 else np.inf * np.ones_like(boost)   # :51
+        if timing_window is not None:                                                # :54-58
+            tof = det_dist / (v_a * 1e-2 * C_LIGHT)
+            delta_tof = abs((det_dist / (1e-2 * C_LIGHT)) - tof)
+            wgt = wgt * (delta_tof < timing_window)
+        surv_prob = np.exp(-det_dist / METER_BY_MEV / v_a / tau)                     # :61
+        decay_prob = (1 - np.exp(-det_length / METER_BY_MEV / v_a / tau))            # :62
+        d64 = rescale_factor * wgt * surv_prob * decay_prob                          # :64
+        s64 = rescale_factor * wgt * surv_prob                                       # :65
+    d32 = np.asarray(d64, dtype=np.float32)
+    s32 = np.asarray(s64, dtype=np.float32)
+    if geom_accept is not None:                                                      # fluxes.py:159-162
+        if geom_accept_f64:
+            d32 = (d32.astype(np.float64) * np.float64(geom_accept)).astype(np.float32)
+            s32 = (s32.astype(np.float64) * np.float64(geom_accept)).astype(np.float32)
+        else:
+            d32 = d32 * np.float32(geom_accept)
+            s32 = s32 * np.float32(geom_accept)
+    return {"decay_w64": d64, "scatter_w64": s64, "decay_w": d32, "scatter_w": s32}
+
+
+def geom_acceptance(det_area, det_dist):                                             # fluxes.py:160
+    return det_area / (4 * pi * det_dist ** 2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fluxes.py:133-151  FluxPrimakoffIsotropic.simulate
+# ---------------------------------------------------------------------------------------------------------
+def primakoff_simulate(photon_flux, ma, g, target_z, abs_xs):
+    photon_flux = np.asarray(photon_flux, dtype=np.float64)
+    energy, flux = [], []
+    for el in photon_flux:                                                           # fluxes.py:150-151
+        eg, wgt = el[0], el[1]
+        if eg < ma:                                                                  # :136
+            continue
+        xs = primakoff_sigma(eg, g, ma, target_z)                                    # :139
+        br = xs / abs_xs.sigma_mev(eg)                                               # :140
+        energy.append(eg)
+        flux.append(wgt * br)                                                        # :142
+    return np.array(energy, dtype=np.float64), np.array(flux, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fluxes.py:210-233  FluxComptonIsotropic.simulate
+# ---------------------------------------------------------------------------------------------------------
+def compton_row_valid(photon_flux, ma):                                              # fluxes.py:214-216
+    eg = np.asarray(photon_flux, dtype=np.float64)[:, 0]
+    s = 2 * M_E * eg + M_E ** 2
+    return ~(s < (M_E + ma) ** 2)
+
+
+def compton_simulate(photon_flux, ma, g, target_z, abs_xs, n_samples, usrc):
+    """Draw order: per row passing the s-threshold, `n_samples` uniforms (fluxes.py:218)."""
+    photon_flux = np.asarray(photon_flux, dtype=np.float64)
+    energy, flux = [], []
+    with np.errstate(all="ignore"):
+        for el in photon_flux:
+            eg, wgt = el[0], el[1]
+            s = 2 * M_E * eg + M_E ** 2                                              # :214
+            if s < (M_E + ma) ** 2:
+                continue
+            ea = usrc.uniform(ma, eg, n_samples)                                     # :218
+            mc_xs = (eg - ma) * compton_dsigma_dea(ea, eg, g, ma, target_z) / n_samples   # :219
+            diff_br = mc_xs / abs_xs.sigma_mev(eg)                                   # :220
+            energy.append(ea)
+            flux.append(wgt * diff_br)                                               # :224
+    if not energy:
+        return np.zeros(0), np.zeros(0)
+    return np.concatenate(energy), np.concatenate(flux)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fluxes.py:276-356  FluxBremIsotropic.simulate
+# ---------------------------------------------------------------------------------------------------------
+def brem_simulate(electron_flux, positron_flux, ma, g, target, n_samples, usrc, boson_type="pseudoscalar",
+                  max_t=5.0, use_track_length=True):
+    """Draw order (use_track_length): per e- row with E0 >= max(ma, M_E): 1 scalar (fluxes.py:350), then --
+    only if ea_max > ma -- `n_samples` (fluxes.py:326).  Returns (E, flux, info) where info carries the
+    per-row scalar draws and validity for uniform injection."""
+    electron_flux = np.asarray(electron_flux, dtype=np.float64)
+    positron_flux = np.asarray(positron_flux, dtype=np.float64)
+    z = target.z[0]
+    ntarget_area_density = target.rad_length * AVOGADRO / (2 * z)                    # fluxes.py:290
+    energy, flux = [], []
+    rows, row_u, row_E1, row_W, row_emit = [], [], [], [], []
+
+    def single(el_energy, el_wgt):                                                   # fluxes.py:318-337
+        with np.errstate(all="ignore"):
+            ea_max = el_energy * (1 - np.power(ma / el_energy, 2))
+            if ea_max <= ma:
+                return False
+            ea_rnd = np.power(10, usrc.uniform(np.log10(ma), np.log10(ea_max), n_samples))
+            if boson_type == "pseudoscalar":
+                mc_vol = np.log(10) * ea_rnd * (np.log10(ea_max) - np.log10(ma)) / n_samples
+                diff_br = (ntarget_area_density * HBARC ** 2) * mc_vol \
+                    * brem_dsigma_dea(ea_rnd, el_energy, g, ma, z)
+            elif boson_type == "vector":
+                x_rnd = ea_rnd / el_energy
+                mc_vol = np.log(10) * x_rnd * (np.log10(ea_max / el_energy) - np.log10(ma / el_energy)) / n_samples
+                diff_br = (ntarget_area_density * HBARC ** 2) * mc_vol * brem_dsigma_dx_vector(x_rnd, g, ma, z)
+            else:
+                raise UnboundLocalError("diff_br")   # the reference falls through to an unbound local
+            energy.append(ea_rnd)
+            flux.append(el_wgt * diff_br)
+            return True
+
+    if use_track_length:
+        ep_min = max(ma, M_E)                                                        # fluxes.py:346
+        for i, el in enumerate(electron_flux):
+            if el[0] < ep_min:
+                continue
+            u = usrc.take()
+            new_energy = ep_min + (el[0] - ep_min) * u                               # :350
+            fl = (np.interp(el[0], electron_flux[:, 0], electron_flux[:, 1], left=0.0, right=0.0)
+                  + np.interp(el[0], positron_flux[:, 0], positron_flux[:, 1], left=0.0, right=0.0))
+            flux_weight = (el[0] - ep_min) * (fl * track_length_integrated_prob(el[0], new_energy, max_t))  # :351
+            emitted = single(new_energy, flux_weight)
+            rows.append(i); row_u.append(u); row_E1.append(new_energy); row_W.append(flux_weight)
+            row_emit.append(emitted)
+    else:
+        for i, el in enumerate(electron_flux):                                       # fluxes.py:354-356
+            emitted = single(el[0], el[1])
+            rows.append(i); row_u.append(np.nan); row_E1.append(el[0]); row_W.append(el[1])
+            row_emit.append(emitted)
+    info = {"rows": np.array(rows, dtype=np.int64), "row_u": np.array(row_u), "row_E1": np.array(row_E1),
+            "row_W": np.array(row_W), "row_emit": np.array(row_emit, dtype=bool)}
+    if not energy:
+        return np.zeros(0), np.zeros(0), info
+    return np.concatenate(energy), np.concatenate(flux), info
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fluxes.py:385-445  FluxResonanceIsotropic.simulate
+# ---------------------------------------------------------------------------------------------------------
+def resonance_peak(ge, ma, boson_type="pseudoscalar"):                               # fluxes.py:413-419
+    if boson_type == "pseudoscalar":
+        return 2 * pi * M_E * np.power(ge / ma, 2) / np.sqrt(1 - np.power(2 * M_E / ma, 2))
+    elif boson_type == "vector":
+        return 12 * pi * ge ** 2 * ALPHA / M_E / 6
+
+
+def resonance_simulate(positron_flux, ma, g, target, n_samples, usrc, boson_type="pseudoscalar", max_t=5.0):
+    """Draw order: `n_samples` for E+ (fluxes.py:437) then `n_samples` for t (:438).  One output sample."""
+    positron_flux = np.asarray(positron_flux, dtype=np.float64)
+    z = target.z[0]
+    ntarget_area_density = target.rad_length * AVOGADRO / (target.z[0] + target.n[0])   # fluxes.py:397
+    resonant_energy = -M_E + ma ** 2 / (2 * M_E)                                     # :427
+    emax = max(positron_flux[:, 0])
+    if resonant_energy + M_E < ma or resonant_energy < M_E or resonant_energy > emax:   # :428-435
+        return np.zeros(0), np.zeros(0)
+    e_rnd = usrc.uniform(resonant_energy, emax, n_samples)                           # :437
+    t_rnd = usrc.uniform(0.0, max_t, n_samples)                                      # :438
+    mc_vol = max_t * (emax - resonant_energy)                                        # :439
+    att = np.interp(e_rnd, positron_flux[:, 0], positron_flux[:, 1], left=0.0, right=0.0) \
+        * track_length_prob(e_rnd, resonant_energy, t_rnd)                           # :410-411
+    attenuated_flux = mc_vol * np.sum(att) / n_samples                               # :441
+    wgt = z * (ntarget_area_density * HBARC ** 2) * resonance_peak(g, ma, boson_type) * attenuated_flux   # :442
+    return np.array([ma ** 2 / (2 * M_E)]), np.array([wgt])                          # :444-445
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cross_section_mc.py:669-685  lorentz_boost for a boost along +-z (the only case the in-scope flux classes
+# produce: parents and beams are on the z axis).  Row sums are evaluated in the order NumPy's 4x4 `mat @ pmu`
+# produces for rows with two non-zero terms.
+# ---------------------------------------------------------------------------------------------------------
+def _boost_z(e, px, py, pz, vz):
+    """Boost 4-vectors (arrays) by frame velocity (0,0,vz) -- restates cross_section_mc.py:676-685."""
+    beta = np.sqrt(vz * vz)                                                          # Vector3.mag :60
+    if beta == 0.0:
+        return e, px, py, pz
+    nz = vz / beta                                                                   # unit_vec :49-53
+    gam = 1 / np.sqrt(1 - beta ** 2)                                                 # :680
+    m03 = -gam * beta * nz
+    m33 = 1 + (gam - 1) * nz * nz
+    e_lab = gam * e + m03 * pz
+    pz_lab = m03 * e + m33 * pz
+    return e_lab, px + 0.0, py + 0.0, pz_lab
+
+
+# ---------------------------------------------------------------------------------------------------------
+# matrix_element.py:717-734  M2AssociatedProduction ; cross_section_mc.py:181-240  Scatter2to2MC
+# ---------------------------------------------------------------------------------------------------------
+def m2_associated(s, t, ma):
+    u_prop = (M_E ** 2 + ma ** 2 - s - t)
+    t_prop = (M_E ** 2 - t)
+    Mt2 = -4 * (3 * M_E ** 4 - M_E ** 2 * (ma ** 2 + s) + t * (-ma ** 2 + s + t)) / t_prop ** 2
+    Mu2 = -4 * (7 * M_E ** 4 + M_E ** 2 * (ma ** 2 - 3 * s - 4 * t) + t * (-ma ** 2 + s + t)) / u_prop ** 2
+    MtMu = 8 * (-3 * M_E ** 4 + M_E ** 2 * (s - 2 * t) + t * (-ma ** 2 + s + t)) / (u_prop * t_prop)
+    M2 = Mt2 + Mu2 + 2 * MtMu
+    prefactor = (pi * ALPHA) * 1.0 ** 2
+    p_pos_cm = np.sqrt((np.power(s - 2 * M_E ** 2, 2) - 4 * np.power(M_E, 4)) / (4 * s))
+    e_pos_cm = np.sqrt(p_pos_cm ** 2 + M_E ** 2)
+    tmax = M_E ** 2 - 2 * 0.01 * e_pos_cm * (e_pos_cm)
+    return prefactor * M2 * np.heaviside(tmax - t, 0.0)
+
+
+def pairann_row_valid(positron_flux, ma):                                            # fluxes.py:507
+    ep = np.asarray(positron_flux, dtype=np.float64)[:, 0]
+    return ~(ep < max((ma ** 2 - M_E ** 2) / (2 * M_E), M_E))
+
+
+def pairann_simulate(positron_flux, ma, g, target, n_samples, usrc):
+    """FluxPairAnnihilationIsotropic.simulate (fluxes.py:503-530).  Draw order per row above threshold:
+    `n_samples` phi then `n_samples` theta (cross_section_mc.py:204-205) -- drawn BEFORE the s-threshold
+    return of scatter_sim (:213-214)."""
+    positron_flux = np.asarray(positron_flux, dtype=np.float64)
+    z = target.z[0]
+    ntarget_area_density = target.rad_length * AVOGADRO / (2 * z)                    # fluxes.py:484
+    m1, m2, m3, m4 = M_E, M_E, ma, 0.0                                               # matrix_element.py:714
+    energy, flux = [], []
+    with np.errstate(all="ignore"):
+        for el in positron_flux:
+            ep_lab, pos_wgt = el[0], el[1]
+            if ep_lab < max((ma ** 2 - M_E ** 2) / (2 * M_E), M_E):                  # fluxes.py:507
+                continue
+            p1z = np.sqrt(ep_lab ** 2 - M_E ** 2)                                    # :513
+            phi = 2 * pi * usrc.take(n_samples)                                      # cross_section_mc.py:204
+            theta = np.arccos(1 - 2 * usrc.take(n_samples))                          # :205
+            e_in = ep_lab + M_E                                                      # :208-209
+            vz = (p1z + 0.0) / e_in                                                  # :211
+            # mass2 = dot(pmu**2, [1,-1,-1,-1])  (:110-111)
+            s = float(np.dot(np.array([e_in, 0.0, 0.0, p1z]) ** 2, np.array([1, -1, -1, -1])))
+            # cross_section_mc.py:213-214 (s < (m3+m4)^2 -> early return) is unreachable for rows that passed
+            # the fluxes.py:507 threshold: s = 2 me^2 + 2 me E+ >= ma^2 + me^2 > ma^2.
+            p1_cm = np.sqrt((np.power(s - m1 ** 2 - m2 ** 2, 2) - np.power(2 * m1 * m2, 2)) / (4 * s))
+            p3_cm = np.sqrt((np.power(s - m3 ** 2 - m4 ** 2, 2) - np.power(2 * m3 * m4, 2)) / (4 * s))
+            e1_cm = np.sqrt(p1_cm ** 2 + m1 ** 2)
+            e3_cm = np.sqrt(p3_cm ** 2 + m3 ** 2)
+            t_rnd = m1 ** 2 + m3 ** 2 + 2 * (p1_cm * p3_cm * np.cos(theta) - e1_cm * e3_cm)   # :221
+            mc_volume = 4 * p1_cm * p3_cm / n_samples                                # :227
+            dsdt = m2_associated(s, t_rnd, ma) / (16 * np.pi * (s - (m1 + m2) ** 2) * (s - (m1 - m2) ** 2))
+            wts = mc_volume * dsdt                                                   # :228
+            px = p3_cm * np.cos(phi) * np.sin(theta)                                 # :231-234
+            py = p3_cm * np.sin(phi) * np.sin(theta)
+            pz = p3_cm * np.cos(theta)
+            # lorentz_boost(p3, -v_in) with v_in = (0,0,vz)                             :235
+            ea_lab, _, _, _ = _boost_z(e3_cm * np.ones(n_samples), px, py, pz, -vz)
+            energy.append(ea_lab)
+            flux.append(pos_wgt * z * g ** 2 * ntarget_area_density * HBARC ** 2 * wts)   # fluxes.py:518
+    if not energy:
+        return np.zeros(0), np.zeros(0)
+    return np.concatenate(energy), np.concatenate(flux)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# generators.py:41-46, 80-92  event weights
+# ---------------------------------------------------------------------------------------------------------
+def decays(axion_energy, decay_axion_weight, days_exposure, threshold):              # generators.py:88-92
+    """`days*S_PER_DAY*w` keeps w's dtype (float32 attribute -> float32 product under NEP 50 for a Python
+    `days`), the heaviside factor then promotes to float64."""
+    e = np.asarray(axion_energy, dtype=np.float64)
+    w = days_exposure * S_PER_DAY * decay_axion_weight * np.heaviside(e - threshold, 1.0)
+    return w, np.sum(w)
+
+
+def compton_events(axion_energy, scatter_axion_weight, ge, ma, ntargets, det_area, det_z,
+                   days_exposure, threshold):                                        # generators.py:41-46
+    e = np.asarray(axion_energy, dtype=np.float64)
+    w = days_exposure * S_PER_DAY * (ntargets / det_area) \
+        * icompton_sigma(e, ma, ge, det_z) \
+        * METER_BY_MEV ** 2 * scatter_axion_weight * np.heaviside(e - threshold, 1.0)
+    return w, np.sum(w)
+
+
+def inverse_primakoff_events(axion_energy, scatter_axion_weight, gagamma, ma, ntargets, det_area, det_z,
+                             days_exposure, threshold=0.0):                          # generators.py:80-86
+    e = np.asarray(axion_energy, dtype=np.float64)
+    w = days_exposure * S_PER_DAY * (ntargets / det_area) \
+        * iprimakoff_sigma(e, gagamma, ma, det_z) \
+        * METER_BY_MEV ** 2 * scatter_axion_weight * np.heaviside(e - threshold, 1.0)
+    return w, np.sum(w)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# generators.py:94-128 + cross_section_mc.py:510-544  simulate_decay_4vectors (forward parents, theta = 0)
+# ---------------------------------------------------------------------------------------------------------
+def decay_4vectors(axion_energy, decay_axion_weight, ma, days_exposure, n_samples, usrc):
+    """Draw order: `n_flux` parent phis (generators.py:100, drawn but irrelevant at theta=0), then per parent
+    `n_samples` phi1 and `n_samples` theta1 (cross_section_mc.py:529-530).
+
+    Returns p1[N,4], p2[N,4] (E,px,py,pz), w[N] float32, N = n_flux*n_samples, parent-major order."""
+    e_all = np.asarray(axion_energy, dtype=np.float64)
+    n_flux = e_all.shape[0]
+    event_weight = days_exposure * S_PER_DAY * decay_axion_weight / n_samples        # generators.py:97
+    phis = usrc.uniform(0.0, 2 * pi, n_flux)                                         # :100 (unused at theta=0)
+    p1 = np.empty((n_flux * n_samples, 4))
+    p2 = np.empty((n_flux * n_samples, 4))
+    w = np.empty(n_flux * n_samples, dtype=np.asarray(event_weight).dtype)
+    m1 = m2 = 0.0
+    with np.errstate(all="ignore"):
+        for i in range(n_flux):
+            ea = e_all[i]
+            pa = np.sqrt(ea ** 2 - ma ** 2)                                          # :118
+            # theta=0: px = pa*cos(phi)*sin(0) = +-0, py = +-0, pz = pa*cos(0) = pa  (:120)
+            pz_parent = pa * np.cos(0.0)
+            mp = np.sqrt(ea ** 2 - pz_parent ** 2)                                   # LorentzVector.mass() :113-114
+            p_cm = np.power((mp ** 2 - (m2 - m1) ** 2) * (mp ** 2 - (m2 + m1) ** 2), 0.5) / (2 * mp)   # :524
+            e1_cm = np.sqrt(p_cm ** 2 + m1 ** 2)
+            e2_cm = np.sqrt(p_cm ** 2 + m2 ** 2)
+            phi1 = 2 * pi * usrc.take(n_samples)                                     # :529
+            th1 = np.arccos(1 - 2 * usrc.take(n_samples))                            # :530
+            vz = -(pz_parent / ea)                                                   # :532  v_in = -velocity
+            px = p_cm * np.cos(phi1) * np.sin(th1)
+            py = p_cm * np.sin(phi1) * np.sin(th1)
+            pz = p_cm * np.cos(th1)
+            sl = slice(i * n_samples, (i + 1) * n_samples)
+            a = _boost_z(e1_cm * np.ones(n_samples), px, py, pz, vz)
+            b = _boost_z(e2_cm * np.ones(n_samples), -px, -py, -pz, vz)
+            p1[sl] = np.stack(a, axis=1)
+            p2[sl] = np.stack(b, axis=1)
+            w[sl] = event_weight[i] * np.ones(n_samples)                             # generators.py:126
+    return p1, p2, w
+
+
+# ---------------------------------------------------------------------------------------------------------
+# np.histogram(E, bins=edges, weights=w) semantics used for the binned spectra
+# ---------------------------------------------------------------------------------------------------------
+def histogram(x, w, edges):
+    return np.histogram(np.asarray(x, dtype=np.float64), bins=np.asarray(edges, dtype=np.float64),
+                        weights=np.asarray(w, dtype=np.float64))[0]
