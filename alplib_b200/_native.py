@@ -1,0 +1,141 @@
+"""
+ctypes binding of libalpk.so (include/alpk.h) -- the only route from the Python drop-in classes to the sm_100a
+kernels.  There is no CPU fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libalpk.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_scan.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
+
+SCRATCH_DOUBLES = 16384
+COMPTON_NP = 10
+PARENT_NP = 6
+BREM_NP = 10
+PAIRANN_NP = 12
+
+
+class AlpkError(RuntimeError):
+    pass
+
+
+class PropT(C.Structure):
+    _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("width", C.c_double), ("rescale", C.c_double),
+                ("neg_dist_mbm", C.c_double), ("neg_len_mbm", C.c_double), ("geom", C.c_double),
+                ("geom32", C.c_float), ("apply_geom", C.c_int), ("geom_f64", C.c_int), ("use_tof", C.c_int),
+                ("tof_light", C.c_double), ("det_dist", C.c_double), ("timing_window", C.c_double)]
+
+
+class EventT(C.Structure):
+    _fields_ = [("days_sec", C.c_double), ("days_sec32", C.c_float), ("days_f64", C.c_int),
+                ("threshold", C.c_double)]
+
+
+class ComptonT(C.Structure):
+    _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("aa", C.c_double), ("z", C.c_double),
+                ("n_samples", C.c_double)]
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def build(force=False, verbose=False):
+    """Compile libalpk.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] \
+        + [os.path.join(_HERE, "..", "include", "alpk.h")]
+    if not force and os.path.exists(LIB_PATH):
+        t = os.path.getmtime(LIB_PATH)
+        if all(os.path.getmtime(d) <= t for d in deps):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    if r.returncode != 0:
+        raise AlpkError("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_P = C.c_void_p
+_U64 = C.c_uint64
+_U32 = C.c_uint32
+_D = C.c_double
+_I = C.c_int
+
+_SIGNATURES = {
+    "alpk_version": ([], _I),
+    "alpk_last_error": ([], C.c_char_p),
+    "alpk_device_info": ([_I, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
+    "alpk_propagate": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _P, _P], _I),
+    "alpk_decays": ([_P, _P, _U64, C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_scatter_events": ([_I, _P, _P, _U64, C.POINTER(_D), _D, _D, C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_abs_sigma_mev": ([_P, _P, _I, _P, _U64, _P, _P], _I),
+    "alpk_primakoff": ([_P, _P, _U64, _P, _P, _I, _D, _D, _D, _P, _P, _P], _I),
+    "alpk_compton_rows": ([_P, _P, _U64, _P, _P, _I, C.POINTER(ComptonT), _P, _P], _I),
+    "alpk_compton_samples": ([_P, _U64, _U32, _P, C.POINTER(ComptonT), _P, _U64, _P, _P,
+                              C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_decay_parent_rows": ([_P, _P, _U64, _D, C.POINTER(EventT), _U32, _P, _P], _I),
+    "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _P, _P, _P, _P], _I),
+    "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
+    "alpk_sum": ([_P, _U64, _P, _P, _P], _I),
+}
+
+
+def declared_symbols():
+    """Every entry point declared in include/alpk.h (parsed from the header, used by the CPU-only ABI test)."""
+    import re
+    hdr = open(os.path.join(_HERE, "..", "include", "alpk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(alpk_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def lib():
+    """Load libalpk.so (once).  Raises AlpkError if it has not been built -- never falls back to the CPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AlpkError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a).  alplib_b200 has no CPU fallback.")
+    try:
+        L = C.CDLL(LIB_PATH)
+    except OSError as e:
+        raise AlpkError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError as e:
+            raise AlpkError(f"{LIB_PATH} does not export {name}") from e
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = L
+    return L
+
+
+def call(name, *args):
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise AlpkError(f"{name} failed ({rc}): {L.alpk_last_error().decode(errors='replace')}")
+
+
+def ptr(t):
+    """Device pointer of a torch CUDA tensor (or None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise AlpkError("alplib_b200 kernels need CUDA tensors; there is no CPU path")
+    if not t.is_contiguous():
+        raise AlpkError("non-contiguous tensor passed to a kernel")
+    return C.c_void_p(t.data_ptr())

@@ -1,0 +1,27 @@
+"""Physical constants and unit conversions in MeV / cm / s.
+
+The numerical values are the reference's (constants.py:14-66, cited per line); they must agree bit for bit because
+every weight is proportional to products of them (known-answer test: tests/test_oracle_golden.py).
+Only the constants the Monte-Carlo flux-and-event path uses are defined.
+"""
+import numpy as np
+
+# base units
+GeV = 1.0e3
+MeV = 1.0
+keV = 1e-3
+
+ALPHA = 1 / 137                        # constants.py:14 (fine-structure constant as used by the reference)
+C_LIGHT = 2.99792458e10                # constants.py:20  cm/s
+HBAR = 6.58212e-22                     # constants.py:21  MeV s
+HBARC = 1.97236e-11                    # constants.py:22  MeV cm
+AVOGADRO = 6.022e23                    # constants.py:29
+M_E = 0.511                            # constants.py:32  MeV
+M_P = 938.0                            # constants.py:33
+M_MU = 105.658369                      # constants.py:34
+METER_BY_MEV = 6.58212e-22 * 2.998e8   # constants.py:60  MeV m
+MEV_PER_KG = 5.6095887e29              # constants.py:61
+MEV2_CM2 = (METER_BY_MEV * 100) ** 2   # constants.py:65
+S_PER_DAY = 3600 * 24                  # constants.py:66
+
+pi = np.pi

@@ -1,0 +1,314 @@
+// Per-sample / per-bin arithmetic of the alplib Monte-Carlo hot path, written once and used by every kernel.
+//
+// Everything here is `ALP_HD` (host + device) so that the exact same expressions can be exercised on the CPU by
+// tests/hostcheck (unit tests only -- the product path is the CUDA kernels, there is no CPU fallback).
+//
+// FP64 op order follows the reference expression by expression (file:line cited per function, relative to the
+// reference repository root).  The library is compiled with -fmad=false so that no a*b+c is contracted into an
+// FMA: several expressions are cancellation-dominated (parent mass from the 4-vector, gamma from 1/sqrt(1-b^2),
+// the Compton x variable) and a fused rounding there moves results by far more than the 1e-9 parity tolerance.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ALP_HD __host__ __device__ __forceinline__
+#else
+#define ALP_HD inline
+#endif
+
+namespace alp {
+
+// ---- constants.py:14-66 -------------------------------------------------------------------------------------
+constexpr double kAlpha = 1.0 / 137.0;                     // constants.py:14  ALPHA = 1/137
+constexpr double kME = 0.511;                              // constants.py:32
+constexpr double kMeterByMeV = 6.58212e-22 * 2.998e8;      // constants.py:60
+constexpr double kMeV2Cm2 = (kMeterByMeV * 100) * (kMeterByMeV * 100);   // constants.py:65
+constexpr double kHbarC = 1.97236e-11;                     // constants.py:22
+constexpr double kAvogadro = 6.022e23;                     // constants.py:29
+constexpr double kCLight = 2.99792458e10;                  // constants.py:20
+constexpr double kPi = 3.141592653589793;                  // numpy.pi
+constexpr double kTwoPi = 2 * 3.141592653589793;           // 2*pi as evaluated by Python
+
+// ---- counter-based RNG: Philox4x32-10 (Salmon et al., SC'11) ------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+ALP_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    const uint64_t p = (uint64_t)a * (uint64_t)b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+ALP_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c0, hi0, lo0);
+        mulhilo32(M1, c2, hi1, lo1);
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// 53-bit uniform in [0,1) from two 32-bit words (same construction as MT19937 genrand_res53 / numpy legacy
+// random_sample, so the free-running stream has the reference's granularity).
+ALP_HD double u53(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+// Stream tags: 4th counter word.  A variate is a pure function of (seed, tag, row, sample) -- independent of the
+// launch configuration and of how rows are sharded over GPUs.
+enum StreamTag : uint32_t {
+    kTagComptonEa = 1, kTagBremRow = 2, kTagBremEa = 3, kTagResonance = 4, kTagPairAnn = 5, kTagDecay2 = 6,
+    kTagDecayParentPhi = 7
+};
+
+// One uniform per sample: sample s uses Philox counter s>>1 and word pair s&1.
+ALP_HD double uniform_1(uint64_t seed, uint32_t tag, uint32_t row, uint64_t s) {
+    const uint64_t c = s >> 1;
+    const Philox4 r = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), row, tag, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return (s & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
+}
+
+// Two uniforms per sample: sample s uses Philox counter s; (x,y) -> first variate, (z,w) -> second.
+ALP_HD void uniform_2(uint64_t seed, uint32_t tag, uint32_t row, uint64_t s, double& u1, double& u2) {
+    const Philox4 r = philox4x32_10((uint32_t)s, (uint32_t)(s >> 32), row, tag, (uint32_t)seed, (uint32_t)(seed >> 32));
+    u1 = u53(r.x, r.y);
+    u2 = u53(r.z, r.w);
+}
+
+// ---- np.heaviside ---------------------------------------------------------------------------------------------
+ALP_HD double heaviside(double x, double h0) {
+    if (x != x) return x;            // NaN propagates
+    return x > 0.0 ? 1.0 : (x < 0.0 ? 0.0 : h0);
+}
+
+// ---- np.interp (numpy/_core/src/multiarray/compiled_base.c arr_interp) ------------------------------------------
+// xp strictly increasing, n >= 1.
+ALP_HD double interp(double x, const double* xp, const double* fp, int n, double left, double right) {
+    if (x != x) return x;
+    if (x < xp[0]) return left;
+    if (x > xp[n - 1]) return right;
+    int lo = 0, hi = n - 1;          // invariant xp[lo] <= x <= xp[hi]
+    if (x == xp[n - 1]) return fp[n - 1];
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= xp[mid]) lo = mid; else hi = mid;
+    }
+    if (xp[lo] == x) return fp[lo];
+    const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+    double r = slope * (x - xp[lo]) + fp[lo];
+    if (r != r) {
+        r = slope * (x - xp[lo + 1]) + fp[lo + 1];
+        if (r != r && fp[lo] == fp[lo + 1]) r = fp[lo];
+    }
+    return r;
+}
+
+// photon_xs.py:48-49  AbsCrossSection.sigma_mev: 10**interp(log10 E; log10 E_i, log10(dim*sigma_i), 0, 0)/MEV2_CM2.
+// (Out-of-range energies give 10**0/MEV2_CM2 -- the reference's behaviour)
+ALP_HD double abs_sigma_mev(double e, const double* log10_e, const double* log10_xs, int n) {
+    const double y = interp(log10(e), log10_e, log10_xs, n, 0.0, 0.0);
+    return pow(10.0, y) / kMeV2Cm2;
+}
+
+// ---- prod_xs.py:99-104  primakoff_sigma -------------------------------------------------------------------------
+// pref = (g*z)**2/(2*137) and r02 = r0**2 are evaluated by the host (Python-float arithmetic, like the reference).
+ALP_HD double primakoff_sigma(double eg, double ma, double pref, double r02) {
+    const double eta2 = r02 * (eg * eg);
+    return heaviside(eg - ma, 0.0) * pref * (((2 * eta2 + 1) / (4 * eta2)) * log(1 + 4 * eta2) - 1);
+}
+
+// ---- det_xs.py:37-42  iprimakoff_sigma ----------------------------------------------------------------------------
+ALP_HD double iprimakoff_sigma(double ea, double ma, double ma2, double pref, double r02) {
+    const double eta2 = r02 * (ea * ea - ma2);
+    return heaviside(ea - ma, 0.0) * pref * (((2 * eta2 + 1) / (4 * eta2)) * log(1 + 4 * eta2) - 1);
+}
+
+// ---- det_xs.py:89-98  icompton_sigma --------------------------------------------------------------------------------
+struct IComptonConst {
+    double ma, ma2, ma4;    // ma, ma**2, ma**4
+    double ethr;            // ma*sqrt(2*M_E**2 + ma**2)/(2*M_E)
+    double zfac;            // z*ALPHA*power(g/M_E,2)  (left-to-right product after the two heavisides)
+    double c2;              // ma**4 + 2*power(ma*M_E,2)
+};
+
+ALP_HD double icompton_sigma(double ea, const IComptonConst& c) {
+    const double me = kME, me2 = kME * kME;
+    const double y = (2 * me) * ea + c.ma2;
+    double d = ea * ea - c.ma2;
+    if (d < 0.0) d = 0.0;                                        // np.clip(..., a_min=0)
+    const double pa = sqrt(d);
+    const double pref = ((heaviside(ea - c.ma, 0.0) * heaviside(ea - c.ethr, 0.0)) * c.zfac) / (8 * pa);
+    const double m2y = me2 + y;
+    const double tme = (2 * me) * ea;
+    const double tmp = (2 * me) * pa;
+    const double t1 = (((2 * me2) * (me + ea)) * y) / (m2y * m2y);
+    const double t2 = ((4 * me) * (c.c2 - tme * tme)) / (y * m2y);
+    const double t3 = (log(((me + ea) + pa) / ((me + ea) - pa)) * (tmp * tmp + c.ma4)) / (pa * y);
+    double r = pref * ((t1 + t2) + t3);
+    // np.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX
+    if (r != r) return 0.0;
+    if (isinf(r)) return r > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    return r;
+}
+
+// ---- Compton production: per-bin constants (prod_xs.py:155-169, fluxes.py:210-224) -----------------------------------
+// Layout of one row of the per-bin parameter table (doubles).
+enum ComptonBin { CB_EG = 0, CB_SPAN, CB_C0, CB_XMIN, CB_XMAX, CB_P, CB_K, CB_S, CB_SIGABS, CB_PHI, CB_NP };
+
+struct ComptonGlobals {
+    double ma, ma2;      // ma, ma**2 (Python float pow on the host)
+    double aa;           // g**2/4/pi
+    double z;            // target Z
+    double n_samples;    // as double (divisor)
+};
+
+ALP_HD void compton_bin_params(double eg, double phi, double sigabs, const ComptonGlobals& g, double* out) {
+    const double me2 = kME * kME;
+    const double s = (2 * kME) * eg + me2;                        // :158
+    const double A = s - me2;
+    const double B = A + g.ma2;
+    const double D = sqrt(B * B - (4 * s) * g.ma2);
+    const double den = (2 * s) * A;
+    out[CB_EG] = eg;
+    out[CB_SPAN] = eg - g.ma;
+    out[CB_C0] = g.ma2 / ((2 * eg) * kME);                        // :159
+    out[CB_XMIN] = (A * B - A * D) / den;                         // :161-162
+    out[CB_XMAX] = (A * B + A * D) / den;                         // :163-164
+    // z * thresh * (1/eg) * pi * a * aa / (s - M_E**2), thresh factored out (0 or 1)    :167
+    out[CB_P] = (((((g.z * heaviside(eg - g.ma, 0.0)) * (1 / eg)) * kPi) * (1.0 / 137.0)) * g.aa) / A;
+    out[CB_K] = (-2 * g.ma2) / (A * A);
+    out[CB_S] = s;
+    out[CB_SIGABS] = sigabs;
+    out[CB_PHI] = phi;
+}
+
+// One Compton sample: returns E_a, writes the production weight (fluxes.py:218-224).
+ALP_HD double compton_sample(double u, const double* b, const ComptonGlobals& g, double& flux) {
+    const double me2 = kME * kME;
+    const double eg = b[CB_EG];
+    const double ea = g.ma + b[CB_SPAN] * u;                      // np.random.uniform(ma, eg): lo + (hi-lo)*u
+    const double x = (b[CB_C0] - ea / eg) + 1;                    // prod_xs.py:159
+    const double th = heaviside(x - b[CB_XMIN], 0.0) * heaviside(b[CB_XMAX] - x, 0.0);   // :166
+    const double omx = 1 - x;
+    const double inner = b[CB_K] * ((b[CB_S] - me2 / omx) - g.ma2 / x) + x;              // :167-168
+    const double dsig = (b[CB_P] * th) * ((x / omx) * inner);
+    const double mc_xs = (b[CB_SPAN] * dsig) / g.n_samples;       // fluxes.py:219
+    flux = b[CB_PHI] * (mc_xs / b[CB_SIGABS]);                    // :220, :224
+    return ea;
+}
+
+// ---- fluxes.py:43-65 + 159-162  propagate ----------------------------------------------------------------------------
+struct PropConst {
+    double ma, ma2;           // ma, ma**2
+    double width;             // decay width; <= 0 -> infinite lifetime (fluxes.py:51)
+    double rescale;           // rescale_factor
+    double neg_dist_mbm;      // -det_dist / METER_BY_MEV        (host-evaluated, Python floats)
+    double neg_len_mbm;       // -det_length / METER_BY_MEV
+    double geom;              // det_area/(4*pi*det_dist**2) or unused
+    float  geom32;            // float32(geom)  (NEP 50: Python-float factor multiplies a float32 array in float32)
+    int    apply_geom;        // is_isotropic
+    int    geom_f64;          // factor was an np.float64 -> multiply in f64 then cast
+    int    use_tof;           // time_of_flight_cut is not None
+    double tof_light;         // det_dist / (1e-2*C_LIGHT)
+    double det_dist;          // metres
+    double timing_window;     // seconds
+};
+
+// Returns the FP64 weights before the float32 cast (decay, scatter); the casts + acceptance are prop_cast().
+ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
+    const double pa = sqrt(ea * ea - c.ma2);                      // :48
+    const double va = pa / ea;                                    // :49
+    const double boost = ea / c.ma;                               // :50
+    const double tau = c.width > 0.0 ? boost / c.width : INFINITY;   // :51
+    if (c.use_tof) {                                              // :54-58
+        const double tof = c.det_dist / ((va * 1e-2) * kCLight);
+        const double dt = fabs(c.tof_light - tof);
+        wgt = wgt * ((dt < c.timing_window) ? 1.0 : 0.0);
+    }
+    const double surv = exp((c.neg_dist_mbm / va) / tau);         // :61
+    const double dec = 1 - exp((c.neg_len_mbm / va) / tau);       // :62
+    s64 = (c.rescale * wgt) * surv;                               // :65
+    d64 = s64 * dec;                                              // :64
+}
+
+ALP_HD float prop_cast(double w64, const PropConst& c) {
+    float w = (float)w64;                                         // np.asarray(..., dtype=np.float32)
+    if (c.apply_geom) {                                           // fluxes.py:159-162
+        if (c.geom_f64) w = (float)((double)w * c.geom);
+        else w = w * c.geom32;
+    }
+    return w;
+}
+
+// ---- generators.py:88-92  decays: days*S_PER_DAY*w32*heaviside(E-thr,1) ---------------------------------------------------
+struct EventConst {
+    double days_sec;      // days_exposure*S_PER_DAY
+    float  days_sec32;    // float32 of it (Python-scalar * float32 array stays float32 under NEP 50)
+    int    days_f64;      // exposure was an np.float64 -> product in f64
+    double threshold;
+};
+
+ALP_HD double decay_event_weight(double ea, float w32, const EventConst& c) {
+    const double base = c.days_f64 ? c.days_sec * (double)w32 : (double)(c.days_sec32 * w32);
+    return base * heaviside(ea - c.threshold, 1.0);
+}
+
+// ---- 2-body decay a -> gamma gamma of a forward parent (generators.py:116-126, cross_section_mc.py:510-544,669-685) ----------
+enum ParentRow { PR_ECM = 0, PR_PCM, PR_GAM, PR_M03, PR_M33, PR_W, PR_NP };
+
+// Per-parent constants.  ma2 = ma**2.  Returns false when the boost is the identity (beta == 0).
+ALP_HD void decay_parent_params(double ea, double ma2, double w, double* out) {
+    const double pa = sqrt(ea * ea - ma2);                        // generators.py:118
+    const double pz = pa;                                         // pa*cos(0.0)
+    const double mp = sqrt(ea * ea - pz * pz);                    // LorentzVector.mass(): sqrt(dot(pmu**2, mt))
+    const double mp2 = mp * mp;
+    const double pcm = sqrt((mp2 - 0.0) * (mp2 - 0.0)) / (2 * mp);   // cross_section_mc.py:524 (m1 = m2 = 0)
+    const double ecm = sqrt(pcm * pcm + 0.0);                     // :525
+    const double vz = -(pz / ea);                                 // :532
+    const double beta = sqrt(vz * vz);                            // Vector3.mag
+    double gam = 1.0, m03 = 0.0, m33 = 1.0;
+    if (beta != 0.0) {                                            // lorentz_boost :678-685
+        const double nz = vz / beta;
+        gam = 1 / sqrt(1 - beta * beta);
+        m03 = ((-gam) * beta) * nz;
+        m33 = 1 + ((gam - 1) * nz) * nz;
+    }
+    out[PR_ECM] = ecm; out[PR_PCM] = pcm; out[PR_GAM] = gam; out[PR_M03] = m03; out[PR_M33] = m33; out[PR_W] = w;
+}
+
+// One decay: u1 -> phi, u2 -> theta.  p1/p2 = (E, px, py, pz) lab frame.
+ALP_HD void decay_event(double u1, double u2, const double* p, double* p1, double* p2) {
+    const double phi = kTwoPi * u1;                               // :529
+    const double th = acos(1 - 2 * u2);                           // :530
+    double sphi, cphi, sth, cth;
+#if defined(__CUDA_ARCH__)
+    sincos(phi, &sphi, &cphi);
+    sincos(th, &sth, &cth);
+#else
+    sphi = sin(phi); cphi = cos(phi); sth = sin(th); cth = cos(th);
+#endif
+    const double pcm = p[PR_PCM], ecm = p[PR_ECM], gam = p[PR_GAM], m03 = p[PR_M03], m33 = p[PR_M33];
+    const double px = (pcm * cphi) * sth;                         // :535-537
+    const double py = (pcm * sphi) * sth;
+    const double pz = pcm * cth;
+    p1[0] = gam * ecm + m03 * pz;                                 // mat @ pmu, rows 0 and 3
+    p1[1] = px; p1[2] = py;
+    p1[3] = m03 * ecm + m33 * pz;
+    p2[0] = gam * ecm + m03 * (-pz);
+    p2[1] = -px; p2[2] = -py;
+    p2[3] = m03 * ecm + m33 * (-pz);
+}
+
+}  // namespace alp

@@ -1,0 +1,470 @@
+// libalpk core: error plumbing, propagate / event-weight kernels, table lookups, Primakoff and Compton production.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/alpk.h"
+#include "common.cuh"
+
+using namespace alp;
+
+namespace alpk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+        cached = p.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// deterministic second stage of every reduction: one CTA sums the per-CTA partials in a fixed order
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void finalize_sum_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+    __shared__ double red[32];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) *out = v;
+}
+
+static int finalize_sum(const double* partials, int n, double* out, cudaStream_t st) {
+    finalize_sum_kernel<<<1, 256, 0, st>>>(partials, n, out);
+    return check_launch("finalize_sum");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// propagate  (fluxes.py:43-65, 159-162)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+propagate_kernel(const double* __restrict__ energy, const double* __restrict__ weight, uint64_t n, PropConst c,
+                 float* __restrict__ d32, float* __restrict__ s32, double* __restrict__ d64o, double* __restrict__ s64o) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double d64, s64;
+        propagate_sample(__ldg(energy + i), __ldg(weight + i), c, d64, s64);
+        d32[i] = prop_cast(d64, c);
+        s32[i] = prop_cast(s64, c);
+        if (d64o) d64o[i] = d64;
+        if (s64o) s64o[i] = s64;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decays / scatter event weights + rate  (generators.py:41-46, 80-92)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+decays_kernel(const double* __restrict__ energy, const float* __restrict__ w32, uint64_t n, EventConst c,
+              double* __restrict__ event_w, double* __restrict__ partials) {
+    __shared__ double red[32];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ev = decay_event_weight(__ldg(energy + i), __ldg(w32 + i), c);
+        if (event_w) event_w[i] = ev;
+        acc += ev;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+struct ScatterConst {
+    int kind;
+    IComptonConst ic;
+    double ma, ma2, pref, r02;
+    double targets_per_area, mbm2;
+};
+
+// days*S_PER_DAY * (ntargets/det_area) * sigma(E) * METER_BY_MEV**2 * scatter_w32 * heaviside(E-thr, 1)
+__global__ void __launch_bounds__(kThreads)
+scatter_kernel(const double* __restrict__ energy, const float* __restrict__ w32, uint64_t n, ScatterConst sc,
+               EventConst c, double* __restrict__ event_w, double* __restrict__ partials) {
+    __shared__ double red[32];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const double lead = c.days_sec * sc.targets_per_area;       // Python floats: (days*S_PER_DAY)*(ntargets/area)
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ea = __ldg(energy + i);
+        const double xs = sc.kind == 0 ? icompton_sigma(ea, sc.ic) : iprimakoff_sigma(ea, sc.ma, sc.ma2, sc.pref, sc.r02);
+        const double ev = (((lead * xs) * sc.mbm2) * (double)__ldg(w32 + i)) * heaviside(ea - c.threshold, 1.0);
+        if (event_w) event_w[i] = ev;
+        acc += ev;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads)
+sum_kernel(const double* __restrict__ x, uint64_t n, double* __restrict__ partials) {
+    __shared__ double red[32];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += __ldg(x + i);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// table lookup + Primakoff rows + Compton rows (one thread per flux row; the XCOM table lives in shared memory)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxTable = 512;
+
+__device__ __forceinline__ void stage_table(double* s_e, double* s_xs, const double* __restrict__ log10_e,
+                                            const double* __restrict__ log10_xs, int n_table) {
+    for (int i = threadIdx.x; i < n_table; i += blockDim.x) {
+        s_e[i] = __ldg(log10_e + i);
+        s_xs[i] = __ldg(log10_xs + i);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+abs_sigma_kernel(const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
+                 const double* __restrict__ energy, uint64_t n, double* __restrict__ out) {
+    __shared__ double s_e[kMaxTable], s_xs[kMaxTable];
+    stage_table(s_e, s_xs, log10_e, log10_xs, n_table);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = abs_sigma_mev(__ldg(energy + i), s_e, s_xs, n_table);
+}
+
+__global__ void __launch_bounds__(kThreads)
+primakoff_kernel(const double* __restrict__ eg, const double* __restrict__ phi, uint64_t n,
+                 const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
+                 double ma, double pref, double r02, double* __restrict__ out_e, double* __restrict__ out_f) {
+    __shared__ double s_e[kMaxTable], s_xs[kMaxTable];
+    stage_table(s_e, s_xs, log10_e, log10_xs, n_table);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = __ldg(eg + i);
+        const double xs = primakoff_sigma(e, ma, pref, r02);               // fluxes.py:139
+        const double br = xs / abs_sigma_mev(e, s_e, s_xs, n_table);       // :140
+        out_e[i] = e;                                                      // :141
+        out_f[i] = __ldg(phi + i) * br;                                    // :142
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+compton_rows_kernel(const double* __restrict__ eg, const double* __restrict__ phi, uint64_t n,
+                    const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
+                    ComptonGlobals g, double* __restrict__ table) {
+    __shared__ double s_e[kMaxTable], s_xs[kMaxTable];
+    stage_table(s_e, s_xs, log10_e, log10_xs, n_table);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = __ldg(eg + i);
+        double row[CB_NP];
+        compton_bin_params(e, __ldg(phi + i), abs_sigma_mev(e, s_e, s_xs, n_table), g, row);
+#pragma unroll
+        for (int k = 0; k < CB_NP; ++k) table[i * CB_NP + k] = row[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Compton per-sample kernel: production (+ fused propagate (+ fused decays))
+//   one CTA walks tiles of kThreads*2*kUnroll consecutive samples; each thread handles PAIRS of adjacent samples so
+//   that one Philox4x32 call (2 x 53-bit uniforms) feeds both and stores are 16-byte (f64) / 8-byte (f32) vectors.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kUnroll = 4;
+constexpr int kTile = kThreads * 2 * kUnroll;
+
+struct ComptonArgs {
+    const double* table; uint64_t n_rows; uint32_t n_samples; const uint32_t* row_ids;
+    ComptonGlobals g; const double* uniforms; uint64_t seed;
+    double* out_e; double* out_f;
+    PropConst prop; float* d32; float* s32; double* d64; double* s64;
+    EventConst ev; double* event_w; double* partials;
+};
+
+template <bool INJECT, int STAGE>   // STAGE 0: production; 1: + propagate; 2: + decays
+__global__ void __launch_bounds__(kThreads)
+compton_samples_kernel(const ComptonArgs a) {
+    __shared__ double s_rows[kStageRows * CB_NP];
+    __shared__ double red[32];
+    const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
+    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+    double acc = 0.0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t base = tile * kTile;
+        const uint64_t last = (base + kTile <= n ? base + kTile : n) - 1;
+        const uint64_t r0 = base / a.n_samples;
+        const uint64_t r1 = last / a.n_samples;
+        const int nrows = (int)(r1 - r0 + 1);
+        const double* rows;                          // row r -> rows + (r - r0)*CB_NP
+        __syncthreads();                             // previous tile finished reading s_rows
+        if (nrows <= kStageRows) {
+            stage_rows<CB_NP>(s_rows, a.table, r0, nrows);
+            rows = s_rows;
+        } else {
+            rows = a.table + r0 * CB_NP;             // many tiny rows per tile: read through L1/L2 instead
+        }
+        __syncthreads();
+        const uint64_t row0_first = r0 * (uint64_t)a.n_samples;
+
+#pragma unroll 1
+        for (int k = 0; k < kUnroll; ++k) {
+            const uint64_t i0 = base + 2 * ((uint64_t)k * kThreads + threadIdx.x);
+            if (i0 >= n) break;
+            const bool have2 = (i0 + 1 < n);
+            double e[2], f[2], u[2];
+            float d32v[2], s32v[2];
+            double d64v[2], s64v[2], evv[2];
+            uint32_t rr[2], ss[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t off = (uint32_t)(i0 + j - row0_first);
+                rr[j] = off / a.n_samples;
+                ss[j] = off - rr[j] * a.n_samples;
+            }
+            if (INJECT) {
+                u[0] = __ldg(a.uniforms + i0);
+                u[1] = have2 ? __ldg(a.uniforms + i0 + 1) : 0.5;
+            } else {
+                // sample s uses Philox counter s>>1, word pair s&1: adjacent samples of one row share a call
+                const uint64_t ra = r0 + rr[0];
+                const uint32_t rid0 = a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra;
+                const Philox4 q = philox4x32_10(ss[0] >> 1, 0u, rid0, kTagComptonEa, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                u[0] = (ss[0] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+                if (rr[1] == rr[0] && (ss[1] >> 1) == (ss[0] >> 1)) {
+                    u[1] = u53(q.z, q.w);
+                } else {
+                    const uint64_t rb = r0 + rr[1];
+                    const uint32_t rid1 = (have2 && a.row_ids) ? __ldg(a.row_ids + rb) : (uint32_t)rb;
+                    u[1] = uniform_1(a.seed, kTagComptonEa, rid1, ss[1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                // a lone last sample computes a throw-away duplicate in lane j=1 (keeps the pair loop branch-free)
+                const double* b = rows + (size_t)rr[(j == 1 && !have2) ? 0 : j] * CB_NP;
+                e[j] = compton_sample(u[j], b, a.g, f[j]);
+                if (STAGE >= 1) {
+                    propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                    d32v[j] = prop_cast(d64v[j], a.prop);
+                    s32v[j] = prop_cast(s64v[j], a.prop);
+                }
+                if (STAGE >= 2) {
+                    evv[j] = decay_event_weight(e[j], d32v[j], a.ev);
+                    if (j == 0 || have2) acc += evv[j];
+                }
+            }
+            if (have2) {
+                if (a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
+                if (a.out_f) *reinterpret_cast<double2*>(a.out_f + i0) = make_double2(f[0], f[1]);
+                if (STAGE >= 1) {
+                    if (a.d32) *reinterpret_cast<float2*>(a.d32 + i0) = make_float2(d32v[0], d32v[1]);
+                    if (a.s32) *reinterpret_cast<float2*>(a.s32 + i0) = make_float2(s32v[0], s32v[1]);
+                    if (a.d64) *reinterpret_cast<double2*>(a.d64 + i0) = make_double2(d64v[0], d64v[1]);
+                    if (a.s64) *reinterpret_cast<double2*>(a.s64 + i0) = make_double2(s64v[0], s64v[1]);
+                }
+                if (STAGE >= 2 && a.event_w) *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
+            } else {
+                {
+                    const int j = 0;
+                    if (a.out_e) a.out_e[i0 + j] = e[j];
+                    if (a.out_f) a.out_f[i0 + j] = f[j];
+                    if (STAGE >= 1) {
+                        if (a.d32) a.d32[i0 + j] = d32v[j];
+                        if (a.s32) a.s32[i0 + j] = s32v[j];
+                        if (a.d64) a.d64[i0 + j] = d64v[j];
+                        if (a.s64) a.s64[i0 + j] = s64v[j];
+                    }
+                    if (STAGE >= 2 && a.event_w) a.event_w[i0 + j] = evv[j];
+                }
+            }
+        }
+    }
+    if (STAGE >= 2) {
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) a.partials[blockIdx.x] = acc;
+    }
+}
+
+static PropConst to_prop(const alpk_prop_t* p) {
+    PropConst c;
+    c.ma = p->ma; c.ma2 = p->ma2; c.width = p->width; c.rescale = p->rescale;
+    c.neg_dist_mbm = p->neg_dist_mbm; c.neg_len_mbm = p->neg_len_mbm; c.geom = p->geom; c.geom32 = p->geom32;
+    c.apply_geom = p->apply_geom; c.geom_f64 = p->geom_f64; c.use_tof = p->use_tof; c.tof_light = p->tof_light;
+    c.det_dist = p->det_dist; c.timing_window = p->timing_window;
+    return c;
+}
+
+static EventConst to_event(const alpk_event_t* e) {
+    EventConst c;
+    c.days_sec = e->days_sec; c.days_sec32 = e->days_sec32; c.days_f64 = e->days_f64; c.threshold = e->threshold;
+    return c;
+}
+
+static ComptonGlobals to_compton(const alpk_compton_t* p) {
+    ComptonGlobals g;
+    g.ma = p->ma; g.ma2 = p->ma2; g.aa = p->aa; g.z = p->z; g.n_samples = p->n_samples;
+    return g;
+}
+
+}  // namespace alpk
+
+using namespace alpk;
+
+// ===================================================================================================================
+// C ABI
+// ===================================================================================================================
+ALPK_EXPORT int alpk_version(void) { return ALPK_VERSION; }
+
+ALPK_EXPORT const char* alpk_last_error(void) { return g_err; }
+
+ALPK_EXPORT int alpk_device_info(int device, char* h_name, int name_len, int* h_sm_count, int* h_cc_major, int* h_cc_minor) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e)); return 1; }
+    if (h_name && name_len > 0) { strncpy(h_name, p.name, (size_t)name_len - 1); h_name[name_len - 1] = 0; }
+    if (h_sm_count) *h_sm_count = p.multiProcessorCount;
+    if (h_cc_major) *h_cc_major = p.major;
+    if (h_cc_minor) *h_cc_minor = p.minor;
+    return 0;
+}
+
+ALPK_EXPORT int alpk_propagate(const double* energy, const double* weight, uint64_t n, const alpk_prop_t* h_prop,
+                               float* decay_w32, float* scatter_w32, double* d64, double* s64, void* stream) {
+    if (!h_prop || !decay_w32 || !scatter_w32) { set_error("alpk_propagate: null argument"); return 2; }
+    if (n == 0) return 0;
+    if (!energy || !weight) { set_error("alpk_propagate: null input"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    propagate_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop), decay_w32,
+                                                                   scatter_w32, d64, s64);
+    return check_launch("alpk_propagate");
+}
+
+ALPK_EXPORT int alpk_decays(const double* energy, const float* decay_w32, uint64_t n, const alpk_event_t* h_ev,
+                            double* event_w, double* rate, double* scratch, void* stream) {
+    if (!h_ev || !rate || !scratch) { set_error("alpk_decays: null argument"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(rate, 0, sizeof(double), st); return check_launch("alpk_decays(memset)"); }
+    const int grid = grid_for(n, kThreads * 4, 8);
+    decays_kernel<<<grid, kThreads, 0, st>>>(energy, decay_w32, n, to_event(h_ev), event_w, scratch);
+    if (check_launch("alpk_decays")) return 1;
+    return finalize_sum(scratch, grid, rate, st);
+}
+
+ALPK_EXPORT int alpk_scatter_events(int kind, const double* energy, const float* scatter_w32, uint64_t n,
+                                    const double* h_xs, double prefactor, double mbm2, const alpk_event_t* h_ev,
+                                    double* event_w, double* rate, double* scratch, void* stream) {
+    if (!h_ev || !rate || !scratch || !h_xs) { set_error("alpk_scatter_events: null argument"); return 2; }
+    if (kind != 0 && kind != 1) { set_error("alpk_scatter_events: unknown kind %d", kind); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(rate, 0, sizeof(double), st); return check_launch("alpk_scatter_events(memset)"); }
+    ScatterConst sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.kind = kind;
+    if (kind == 0) {
+        sc.ic.ma = h_xs[0]; sc.ic.ma2 = h_xs[1]; sc.ic.ma4 = h_xs[2]; sc.ic.ethr = h_xs[3]; sc.ic.zfac = h_xs[4]; sc.ic.c2 = h_xs[5];
+    } else {
+        sc.ma = h_xs[0]; sc.ma2 = h_xs[1]; sc.pref = h_xs[2]; sc.r02 = h_xs[3];
+    }
+    sc.targets_per_area = prefactor; sc.mbm2 = mbm2;
+    const int grid = grid_for(n, kThreads * 2, 8);
+    scatter_kernel<<<grid, kThreads, 0, st>>>(energy, scatter_w32, n, sc, to_event(h_ev), event_w, scratch);
+    if (check_launch("alpk_scatter_events")) return 1;
+    return finalize_sum(scratch, grid, rate, st);
+}
+
+ALPK_EXPORT int alpk_sum(const double* x, uint64_t n, double* out, double* scratch, void* stream) {
+    if (!out || !scratch) { set_error("alpk_sum: null argument"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(out, 0, sizeof(double), st); return check_launch("alpk_sum(memset)"); }
+    const int grid = grid_for(n, kThreads * 8, 8);
+    sum_kernel<<<grid, kThreads, 0, st>>>(x, n, scratch);
+    if (check_launch("alpk_sum")) return 1;
+    return finalize_sum(scratch, grid, out, st);
+}
+
+ALPK_EXPORT int alpk_abs_sigma_mev(const double* log10_e, const double* log10_xs, int n_table, const double* energy,
+                                   uint64_t n, double* sigma_mev, void* stream) {
+    if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_abs_sigma_mev: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
+    if (n == 0) return 0;
+    abs_sigma_kernel<<<grid_for(n, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(log10_e, log10_xs, n_table, energy, n, sigma_mev);
+    return check_launch("alpk_abs_sigma_mev");
+}
+
+ALPK_EXPORT int alpk_primakoff(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,
+                               const double* log10_e, const double* log10_xs, int n_table,
+                               double ma, double pref, double r02, double* out_energy, double* out_flux, void* stream) {
+    if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_primakoff: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
+    if (n_rows == 0) return 0;
+    primakoff_kernel<<<grid_for(n_rows, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(
+        e_gamma, phi_gamma, n_rows, log10_e, log10_xs, n_table, ma, pref, r02, out_energy, out_flux);
+    return check_launch("alpk_primakoff");
+}
+
+ALPK_EXPORT int alpk_compton_rows(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,
+                                  const double* log10_e, const double* log10_xs, int n_table,
+                                  const alpk_compton_t* h_par, double* row_table, void* stream) {
+    static_assert(CB_NP == ALPK_COMPTON_NP, "header/table layout mismatch");
+    if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_compton_rows: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
+    if (!h_par) { set_error("alpk_compton_rows: null argument"); return 2; }
+    if (n_rows == 0) return 0;
+    compton_rows_kernel<<<grid_for(n_rows, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(
+        e_gamma, phi_gamma, n_rows, log10_e, log10_xs, n_table, to_compton(h_par), row_table);
+    return check_launch("alpk_compton_rows");
+}
+
+ALPK_EXPORT int alpk_compton_samples(const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
+                                     const alpk_compton_t* h_par, const double* uniforms, uint64_t seed,
+                                     double* out_energy, double* out_flux,
+                                     const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
+                                     double* decay_w64, double* scatter_w64,
+                                     const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream) {
+    if (!h_par || !row_table) { set_error("alpk_compton_samples: null argument"); return 2; }
+    if (h_ev && (!h_prop || !rate || !scratch)) { set_error("alpk_compton_samples: events need prop, rate and scratch"); return 2; }
+    if (n_samples == 0 || n_samples > 0x7fffffffu - kTile) { set_error("alpk_compton_samples: n_samples out of range"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t n = n_rows * (uint64_t)n_samples;
+    if (n == 0) {
+        if (h_ev) { cudaMemsetAsync(rate, 0, sizeof(double), st); return check_launch("alpk_compton_samples(memset)"); }
+        return 0;
+    }
+    ComptonArgs a;
+    memset(&a, 0, sizeof(a));
+    a.table = row_table; a.n_rows = n_rows; a.n_samples = n_samples; a.row_ids = row_ids;
+    a.g = to_compton(h_par); a.uniforms = uniforms; a.seed = seed;
+    a.out_e = out_energy; a.out_f = out_flux;
+    const int stage = h_ev ? 2 : (h_prop ? 1 : 0);
+    if (h_prop) { a.prop = to_prop(h_prop); a.d32 = decay_w32; a.s32 = scatter_w32; a.d64 = decay_w64; a.s64 = scatter_w64; }
+    if (h_ev) { a.ev = to_event(h_ev); a.event_w = event_w; a.partials = scratch; }
+    const int grid = grid_for(n, kTile, 8);
+    const bool inj = uniforms != nullptr;
+    switch (stage * 2 + (inj ? 1 : 0)) {
+        case 0: compton_samples_kernel<false, 0><<<grid, kThreads, 0, st>>>(a); break;
+        case 1: compton_samples_kernel<true, 0><<<grid, kThreads, 0, st>>>(a); break;
+        case 2: compton_samples_kernel<false, 1><<<grid, kThreads, 0, st>>>(a); break;
+        case 3: compton_samples_kernel<true, 1><<<grid, kThreads, 0, st>>>(a); break;
+        case 4: compton_samples_kernel<false, 2><<<grid, kThreads, 0, st>>>(a); break;
+        default: compton_samples_kernel<true, 2><<<grid, kThreads, 0, st>>>(a); break;
+    }
+    if (check_launch("alpk_compton_samples")) return 1;
+    if (stage == 2) return finalize_sum(scratch, grid, rate, st);
+    return 0;
+}

@@ -1,0 +1,141 @@
+/*
+ * alpk.h -- C ABI of libalpk.so, the sm_100a CUDA implementation of alplib's Monte-Carlo flux-and-event path.
+ *
+ * The reference (athompson-git/alplib) is pure Python and has no FFI; its boundary for this path is the Python
+ * class API (fluxes.py / generators.py).  `alplib_b200` keeps that API and binds the entry points below with
+ * ctypes (INTEGRATION.md shows the stub a reference maintainer would add).  Each entry point cites the reference
+ * code it replaces (file:line relative to the reference repository root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (cudaMalloc'd / torch CUDA tensor) unless its name starts with `h_`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it; nothing synchronises;
+ *   - return value 0 = OK, non-zero = error, text from alpk_last_error() (thread local);
+ *   - nothing is allocated or freed across the boundary; `scratch` arguments are caller-owned device buffers of
+ *     at least ALPK_SCRATCH_DOUBLES doubles used for the deterministic two-stage reductions;
+ *   - all arithmetic is IEEE FP64 in the reference's operation order (library built with -fmad=false), weights
+ *     are rounded to float32 exactly where the reference rounds them;
+ *   - `uniforms` arguments: NULL = free-running Philox4x32-10 keyed by (seed, stream tag, row id, sample);
+ *     non-NULL = injected U[0,1) variates in the reference's draw order (parity mode).
+ */
+#ifndef ALPK_H
+#define ALPK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALPK_VERSION 1
+#define ALPK_SCRATCH_DOUBLES 16384
+
+/* number of doubles per row of the per-row parameter tables */
+#define ALPK_COMPTON_NP 10
+#define ALPK_PARENT_NP 6
+#define ALPK_BREM_NP 10
+#define ALPK_PAIRANN_NP 12
+
+int alpk_version(void);
+const char* alpk_last_error(void);
+/* writes name, SM count, compute capability of `device`; used by the loader to refuse non-sm_100 devices */
+int alpk_device_info(int device, char* h_name, int name_len, int* h_sm_count, int* h_cc_major, int* h_cc_minor);
+
+/* ---- propagate: fluxes.py:43-65 (AxionFlux.propagate) + fluxes.py:159-162 (isotropic acceptance) ------------ */
+typedef struct {
+    double ma, ma2;          /* axion mass, ma**2 */
+    double width;            /* decay width [MeV]; <= 0 -> infinite lifetime (fluxes.py:51) */
+    double rescale;          /* rescale_factor, (g'/g)^2 for propagate(new_coupling) */
+    double neg_dist_mbm;     /* -det_dist / METER_BY_MEV */
+    double neg_len_mbm;      /* -det_length / METER_BY_MEV */
+    double geom;             /* det_area / (4 pi det_dist^2) */
+    float  geom32;           /* float32(geom) */
+    int    apply_geom;       /* is_isotropic */
+    int    geom_f64;         /* acceptance factor is an np.float64 (multiply in f64, then cast) */
+    int    use_tof;          /* time_of_flight_cut is not None (fluxes.py:54-58) */
+    double tof_light;        /* det_dist / (1e-2*C_LIGHT) */
+    double det_dist;         /* metres */
+    double timing_window;    /* seconds */
+} alpk_prop_t;
+
+/* event weights: generators.py:88-92 (decays), :41-46 (compton), :80-86 (inverse_primakoff) */
+typedef struct {
+    double days_sec;         /* days_exposure * S_PER_DAY */
+    float  days_sec32;       /* float32(days_sec): Python scalar * float32 array stays float32 */
+    int    days_f64;         /* exposure was an np.float64: product evaluated in f64 */
+    double threshold;        /* MeV */
+} alpk_event_t;
+
+/* E[n], w[n] (f64) -> decay_w32[n], scatter_w32[n] (the reference's float32 attributes); the optional f64 outputs
+ * are the weights before the float32 cast and acceptance factor (what the 1e-9 FP64 criterion is evaluated on). */
+int alpk_propagate(const double* energy, const double* weight, uint64_t n, const alpk_prop_t* h_prop,
+                   float* decay_w32, float* scatter_w32, double* decay_w64_or_null, double* scatter_w64_or_null,
+                   void* stream);
+
+/* decays(): event_w[n] (f64, may be NULL) and *rate = sum(event_w)  -- generators.py:88-92 */
+int alpk_decays(const double* energy, const float* decay_w32, uint64_t n, const alpk_event_t* h_ev,
+                double* event_w_or_null, double* rate, double* scratch, void* stream);
+
+/* scatter channels: kind 0 = inverse Compton (generators.py:41-46, det_xs.py:89-98),
+ *                   kind 1 = inverse Primakoff (generators.py:80-86, det_xs.py:37-42).
+ * h_xs: kind 0 -> {ma, ma**2, ma**4, e_thr, z*ALPHA*(g/M_E)**2, ma**4 + 2 (ma M_E)**2}
+ *       kind 1 -> {ma, ma**2, (g z)**2/(2*137), r0**2, 0, 0}
+ * prefactor = ntargets/det_area (applied after days*S_PER_DAY), mbm2 = METER_BY_MEV**2. */
+int alpk_scatter_events(int kind, const double* energy, const float* scatter_w32, uint64_t n,
+                        const double* h_xs, double prefactor, double mbm2, const alpk_event_t* h_ev,
+                        double* event_w_or_null, double* rate, double* scratch, void* stream);
+
+/* ---- photon absorption table: photon_xs.py:48-49 (AbsCrossSection.sigma_mev) --------------------------------- */
+int alpk_abs_sigma_mev(const double* log10_e, const double* log10_xs, int n_table, const double* energy, uint64_t n,
+                       double* sigma_mev, void* stream);
+
+/* ---- Primakoff production: fluxes.py:133-142, prod_xs.py:99-104 ----------------------------------------------------
+ * rows already filtered by the host (E_gamma >= ma, fluxes.py:136).  pref = (g z)^2/(2*137), r02 = r0^2. */
+int alpk_primakoff(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,
+                   const double* log10_e, const double* log10_xs, int n_table,
+                   double ma, double pref, double r02, double* out_energy, double* out_flux, void* stream);
+
+/* ---- Compton production: fluxes.py:210-224, prod_xs.py:155-169 ------------------------------------------------------ */
+typedef struct {
+    double ma, ma2;          /* ma, ma**2 */
+    double aa;               /* g**2/4/pi */
+    double z;                /* target Z */
+    double n_samples;        /* n_samples as a double */
+} alpk_compton_t;
+
+/* per-row table [n_rows][ALPK_COMPTON_NP]; rows already filtered by the host (s >= (M_E+ma)^2, fluxes.py:214-216) */
+int alpk_compton_rows(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,
+                      const double* log10_e, const double* log10_xs, int n_table,
+                      const alpk_compton_t* h_par, double* row_table, void* stream);
+
+/* Per-sample kernel.  n = n_rows*n_samples samples, row-major (all samples of row 0, then row 1, ...).
+ * Outputs (each may be NULL): out_energy/out_flux f64 (axion_energy/axion_flux), and -- when h_prop != NULL -- the
+ * fused propagate (decay_w32/scatter_w32, optional f64 pre-cast weights) and -- when h_ev != NULL too -- the fused
+ * decays() event weights and total rate.  row_ids: global row index per table row for the Philox key (NULL = 0..). */
+int alpk_compton_samples(const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
+                         const alpk_compton_t* h_par, const double* uniforms, uint64_t seed,
+                         double* out_energy, double* out_flux,
+                         const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
+                         double* decay_w64, double* scatter_w64,
+                         const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream);
+
+/* ---- a -> gamma gamma decay MC: generators.py:94-128, cross_section_mc.py:510-544, 669-685 ------------------------------
+ * parents: energy[n_parents] f64 and decay_w32[n_parents]; n_samples decays each, parent-major order.
+ * outputs SoA: p1[4][N], p2[4][N] (E,px,py,pz planes, N = n_parents*n_samples) and w[N] (f64 holding the float32
+ * event weight days*S_PER_DAY*w32/n_samples, generators.py:97,126).
+ * uniforms (parity mode): [n_parents][2][n_samples] -- per parent n_samples phi then n_samples theta draws. */
+int alpk_decay_parent_rows(const double* energy, const float* decay_w32, uint64_t n_parents, double ma2,
+                           const alpk_event_t* h_ev, uint32_t n_samples, double* row_table, void* stream);
+int alpk_decay2body(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
+                    const double* uniforms, uint64_t seed, double* p1, double* p2, double* w, void* stream);
+
+/* ---- weighted histogram: np.histogram(x, bins=edges, weights=w) (half-open bins, last bin closed) ------------------ */
+int alpk_hist(const double* x, const double* w64_or_null, const float* w32_or_null, uint64_t n,
+              const double* edges, int n_edges, double* hist /* [n_edges-1], accumulated into */, void* stream);
+
+/* sum of a f64 array (deterministic two-stage) */
+int alpk_sum(const double* x, uint64_t n, double* out, double* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALPK_H */

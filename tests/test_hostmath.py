@@ -1,0 +1,177 @@
+"""CPU tier: the kernels' per-sample arithmetic (alplib_b200/csrc/alp_math*.cuh, compiled for the host by
+tests/hostcheck) against the golden fixtures of the reference.  Same header the CUDA kernels include; only libm
+differs (glibc here, libdevice on the GPU).  Tolerance: relative 1e-9 (north star, FP64 mode); observed ~1e-15."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_decay_close, dptr, load_golden, max_rel
+from oracle import alp_oracle as O
+from oracle import philox as PX
+from alplib_b200 import _native as N
+from alplib_b200 import params as P
+
+TOL = 1e-9
+GA = P.geom_acceptance(0.04, 4.0)
+
+
+def table(mat="W"):
+    a = O.AbsCrossSection(O.Material(mat))
+    return np.ascontiguousarray(a.log10_e), np.ascontiguousarray(a.log10_xs)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors: philox4x32-10
+    r = PX.philox4x32_10(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = PX.philox4x32_10(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
+    assert [int(v) for v in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = PX.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
+    assert [int(v) for v in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_device_code_matches_numpy(hostcheck):
+    seed = 0xA1B2C3D4_0000_0007
+    out = np.empty(1001)
+    hostcheck.hc_philox(C.c_uint64(seed), C.c_uint32(PX.TAG_COMPTON_EA), C.c_uint32(12345), C.c_uint64(1001), 0, dptr(out))
+    assert np.array_equal(out, PX.uniform_1(seed, PX.TAG_COMPTON_EA, 12345, 1001))
+    out2 = np.empty(2 * 500)
+    hostcheck.hc_philox(C.c_uint64(seed), C.c_uint32(PX.TAG_DECAY2), C.c_uint32(3), C.c_uint64(500), 1, dptr(out2))
+    u1, u2 = PX.uniform_2(seed, PX.TAG_DECAY2, 3, 500)
+    assert np.array_equal(out2[0::2], u1) and np.array_equal(out2[1::2], u2)
+    assert 0.0 <= out.min() and out.max() < 1.0 and abs(out.mean() - 0.5) < 0.05
+
+
+@pytest.mark.parametrize("mat", ["W", "C"])
+def test_abs_sigma(hostcheck, mat):
+    g = load_golden("abs_table_" + mat)
+    le, lx = table(mat)
+    e = np.ascontiguousarray(g["energy"])
+    out = np.empty_like(e)
+    hostcheck.hc_abs_sigma(dptr(le), dptr(lx), le.shape[0], dptr(e), C.c_uint64(e.shape[0]), dptr(out))
+    assert max_rel(out, g["sigma_mev"]) < 1e-13
+    assert out[e > 1e5 * 1.0000001].max() == pytest.approx(2.5680599121454694e+21)      # out-of-range quirk kept
+
+
+def run_primakoff(hostcheck, pf, ma, g):
+    keep = ~(pf[:, 0] < ma)
+    eg = np.ascontiguousarray(pf[keep, 0]); ph = np.ascontiguousarray(pf[keep, 1])
+    le, lx = table("W")
+    pref, r02 = P.primakoff_consts(g, np.int64(74))
+    oe, of = np.empty_like(eg), np.empty_like(eg)
+    hostcheck.hc_primakoff(dptr(eg), dptr(ph), C.c_uint64(eg.shape[0]), dptr(le), dptr(lx), le.shape[0],
+                           C.c_double(ma), C.c_double(pref), C.c_double(r02), dptr(oe), dptr(of))
+    return oe, of
+
+
+def run_propagate(hostcheck, E, F, prop):
+    n = E.shape[0]
+    d32, s32 = np.empty(n, np.float32), np.empty(n, np.float32)
+    d64, s64 = np.empty(n), np.empty(n)
+    hostcheck.hc_propagate(dptr(np.ascontiguousarray(E)), dptr(np.ascontiguousarray(F)), C.c_uint64(n), C.byref(prop),
+                           dptr(d32), dptr(s32), dptr(d64), dptr(s64))
+    return d32, s32, d64, s64
+
+
+@pytest.mark.parametrize("name", ["c1_primakoff", "primakoff_ragged"])
+def test_primakoff_chain(hostcheck, name):
+    g = load_golden(name)
+    ma, gg = float(g["ma"]), float(g["g"])
+    E, F = run_primakoff(hostcheck, g["photon_flux"], ma, gg)
+    assert np.array_equal(E, g["axion_energy"])
+    assert max_rel(F, g["axion_flux"]) < 1e-13
+    prop = P.prop_params(ma, O.W_gg(gg, ma), 1.0, 4.0, 0.2, geom_accept=GA)
+    d32, s32, d64, s64 = run_propagate(hostcheck, E, F, prop)
+    assert max_rel(s64 * GA, g["scatter_w64"]) < TOL
+    assert_decay_close(d64 * GA, g["decay_w64"], g["scatter_w64"], TOL)
+    assert max_rel(s32, g["scatter_w32"]) <= 1.2e-7
+    assert_decay_close(d32, g["decay_w32"], g["scatter_w32"], TOL, extra_rel=1.2e-7)
+    days, thr, key = (100, 5.0, "decays_100_5") if name == "c1_primakoff" else (30, 1.0, "decays_30_1")
+    ev = P.event_params(days, thr)
+    out = np.empty(E.shape[0])
+    # (the ragged fixture took decays() after propagate(new_coupling): its rate belongs to decay_w32_new)
+    w32 = g["decay_w32" if name == "c1_primakoff" else "decay_w32_new"].astype(np.float32)
+    hostcheck.hc_decays(dptr(E), dptr(w32), C.c_uint64(E.shape[0]), C.byref(ev), dptr(out))
+    assert max_rel(out.sum(), g[key]) < 1e-12
+    if name == "c1_primakoff":
+        assert out.sum() == 284.1535949707031
+        xs = P.iprimakoff_consts(0.1, 1e-5, np.int64(18))
+        hostcheck.hc_scatter(1, dptr(E), dptr(g["scatter_w32"].astype(np.float32)), C.c_uint64(E.shape[0]), xs,
+                             C.c_double(1e27 / 0.04), C.c_double(P.METER_BY_MEV ** 2), C.byref(ev), dptr(out))
+        assert max_rel(out, g["scatter_weights"]) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["katc_compton", "compton_mid", "compton_loop"])
+def test_compton_chain(hostcheck, name):
+    g = load_golden(name)
+    ma, gg, ns = float(g["ma"]), float(g["g"]), int(g["n_samples"])
+    pf = g["photon_flux"]
+    keep = O.compton_row_valid(pf, ma)
+    eg = np.ascontiguousarray(pf[keep, 0]); ph = np.ascontiguousarray(pf[keep, 1])
+    le, lx = table("W")
+    par = P.compton_params(ma, gg, np.int64(74), ns)
+    n = eg.shape[0] * ns
+    u = np.ascontiguousarray(g["uniforms"])
+    assert u.shape[0] == n
+    oe, of = np.empty(n), np.empty(n)
+    hostcheck.hc_compton(dptr(eg), dptr(ph), C.c_uint64(eg.shape[0]), C.c_uint32(ns), dptr(le), dptr(lx), le.shape[0],
+                         C.byref(par), dptr(u), dptr(oe), dptr(of))
+    assert np.array_equal(oe, g["axion_energy"])                  # E_a = ma + (eg-ma)*u is bit exact
+    assert max_rel(of, g["axion_flux"]) < 1e-12
+    loop = bool(g["loop_decay"]) if "loop_decay" in g else False
+    iso = bool(g["is_isotropic"]) if "is_isotropic" in g else True
+    width = O.W_ee(gg, ma) + (O.W_gg_loop(gg, ma, O.M_E) if loop else 0.0)
+    prop = P.prop_params(ma, width, 1.0, 4.0, 0.2, geom_accept=GA if iso else None)
+    d32, s32, d64, s64 = run_propagate(hostcheck, oe, of, prop)
+    ga = GA if iso else 1.0
+    assert max_rel(s64 * ga, g["scatter_w64"]) < TOL
+    assert_decay_close(d64 * ga, g["decay_w64"], g["scatter_w64"], TOL)       # conditioned on 1-exp(-x), see conftest
+    assert max_rel(s32, g["scatter_w32"]) <= 1.2e-7
+    assert_decay_close(d32, g["decay_w32"], g["scatter_w32"], TOL, extra_rel=1.2e-7)
+    if "scatter_weights" in g:
+        ev = P.event_params(100, 5.0)
+        out = np.empty(n)
+        xs = P.icompton_consts(ma, gg, np.int64(18))
+        hostcheck.hc_scatter(0, dptr(oe), dptr(g["scatter_w32"].astype(np.float32)), C.c_uint64(n), xs,
+                             C.c_double(1e27 / 0.04), C.c_double(P.METER_BY_MEV ** 2), C.byref(ev), dptr(out))
+        assert max_rel(out, g["scatter_weights"], floor=1e-300) < 1e-12
+        hostcheck.hc_decays(dptr(oe), dptr(g["decay_w32"].astype(np.float32)), C.c_uint64(n), C.byref(ev), dptr(out))
+        assert np.array_equal(out, g["decay_weights"])
+    if "new_coupling" in g:
+        nc = float(g["new_coupling"])
+        prop = P.prop_params(ma, O.W_ee(nc, ma), np.power(nc / gg, 2), 4.0, 0.2, geom_accept=GA)
+        d32, s32, d64, s64 = run_propagate(hostcheck, oe, of, prop)
+        assert_decay_close(d64 * GA, g["decay_w64_new"], g["scatter_w64_new"], TOL)
+        assert_decay_close(d32, g["decay_w32_new"], g["scatter_w32_new"], TOL, extra_rel=1.2e-7)
+
+
+def test_propagate_misc(hostcheck):
+    g = load_golden("propagate_misc")
+    E, F = g["axion_energy"], g["axion_flux"]
+    d32, s32, d64, s64 = run_propagate(hostcheck, E, F, P.prop_params(0.9, 0.0, 1.0, 4.0, 0.2, geom_accept=GA))
+    assert np.all(d32 == 0) and max_rel(s32, g["zero_scatter_w32"]) <= 1.2e-7
+    prop = P.prop_params(0.9, float(g["tof_width"]), float(g["tof_rescale"]), 4.0, 0.2, timing_window=float(g["tof_window"]))
+    d32, s32, d64, s64 = run_propagate(hostcheck, E, F, prop)
+    assert max_rel(s64, g["tof_scatter_w64"]) < TOL
+    assert_decay_close(d64, g["tof_decay_w64"], g["tof_scatter_w64"], TOL)
+
+
+@pytest.mark.parametrize("name", ["katd_decay4", "decay4_boosted", "decay4_heavy"])
+def test_decay2body(hostcheck, name):
+    g = load_golden(name)
+    ma, ns = float(g["ma"]), int(g["n_samples"])
+    E = np.ascontiguousarray(g["axion_energy"]); w32 = np.ascontiguousarray(g["decay_w32"].astype(np.float32))
+    npar = E.shape[0]
+    u = np.ascontiguousarray(g["uniforms"][npar:])              # the first n_flux draws are the unused parent phis
+    n = npar * ns
+    p1, p2, w = np.empty((4, n)), np.empty((4, n)), np.empty(n)
+    ev = P.event_params(int(g["days"]), 0.0)
+    hostcheck.hc_decay2body(dptr(E), dptr(w32), C.c_uint64(npar), C.c_double(ma ** 2), C.byref(ev), C.c_uint32(ns),
+                            dptr(u), dptr(p1), dptr(p2), dptr(w))
+    scale = np.repeat(E, ns)[None, :]
+    assert np.max(np.abs(p1 - g["p1"].T) / scale) < TOL          # |dp| / E_parent (SURVEY section 7 hard part 1)
+    assert np.max(np.abs(p2 - g["p2"].T) / scale) < TOL
+    assert np.array_equal(w, g["w"])
+    # the host build follows the reference's op order; what is left is glibc-scalar vs NumPy-SIMD sin/cos/acos
+    assert np.max(np.abs(p1 - g["p1"].T) / scale) < 1e-14 and np.max(np.abs(p2 - g["p2"].T) / scale) < 1e-14
