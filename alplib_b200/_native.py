@@ -76,6 +76,7 @@ _I = C.c_int
 _SIGNATURES = {
     "alpk_version": ([], _I),
     "alpk_last_error": ([], C.c_char_p),
+    "alpk_launch_count": ([], C.c_uint64),
     "alpk_device_info": ([_I, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
     "alpk_propagate": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _P, _P], _I),
     "alpk_decays": ([_P, _P, _U64, C.POINTER(EventT), _P, _P, _P, _P], _I),
@@ -89,6 +90,7 @@ _SIGNATURES = {
     "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _P, _P, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),
+    "alpk_fp64_peak": ([_U64, _I, _P, _P], _I),
 }
 
 
@@ -128,6 +130,10 @@ def call(name, *args):
     rc = getattr(L, name)(*args)
     if rc != 0:
         raise AlpkError(f"{name} failed ({rc}): {L.alpk_last_error().decode(errors='replace')}")
+
+
+def launch_count():
+    return int(lib().alpk_launch_count())
 
 
 def ptr(t):

@@ -1,7 +1,7 @@
 """Physical constants and unit conversions in MeV / cm / s.
 
 The numerical values are the reference's (constants.py:14-66, cited per line); they must agree bit for bit because
-every weight is proportional to products of them (known-answer test: tests/test_oracle_golden.py).
+every weight is proportional to products of them (known-answer test in tests/).
 Only the constants the Monte-Carlo flux-and-event path uses are defined.
 """
 import numpy as np

@@ -10,6 +10,7 @@ using namespace alp;
 namespace alpk {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;      // kernels launched through this library (bench.py reports it)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -24,6 +25,7 @@ int check_launch(const char* what) {
         set_error("%s: %s", what, cudaGetErrorString(e));
         return 1;
     }
+    __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
     return 0;
 }
 
@@ -336,6 +338,8 @@ ALPK_EXPORT int alpk_version(void) { return ALPK_VERSION; }
 
 ALPK_EXPORT const char* alpk_last_error(void) { return g_err; }
 
+ALPK_EXPORT uint64_t alpk_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 ALPK_EXPORT int alpk_device_info(int device, char* h_name, int name_len, int* h_sm_count, int* h_cc_major, int* h_cc_minor) {
     cudaDeviceProp p;
     cudaError_t e = cudaGetDeviceProperties(&p, device);
@@ -467,4 +471,27 @@ ALPK_EXPORT int alpk_compton_samples(const double* row_table, uint64_t n_rows, u
     if (check_launch("alpk_compton_samples")) return 1;
     if (stage == 2) return finalize_sum(scratch, grid, rate, st);
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP64 issue-rate microbenchmark (roofline denominator measured on the box; MEASURED_PEAKS.json has no FP64 figure)
+// ---------------------------------------------------------------------------------------------------------------
+namespace alpk {
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(uint64_t iters, double a, double b, double* __restrict__ out) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (uint64_t i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // never true; keeps the chains alive
+}
+}  // namespace alpk
+
+// launches `blocks` CTAs of 256 threads, each thread doing 8*iters dependent-chain DFMAs (16*iters flops)
+ALPK_EXPORT int alpk_fp64_peak(uint64_t iters, int blocks, double* out, void* stream) {
+    if (!out || blocks < 1) { set_error("alpk_fp64_peak: bad argument"); return 2; }
+    fp64_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.999999, 1e-7, out);
+    return check_launch("alpk_fp64_peak");
 }

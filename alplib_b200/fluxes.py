@@ -1,0 +1,437 @@
+"""
+ALP flux generators -- drop-in for the reference's `fluxes.py` classes on the Monte-Carlo hot path.
+
+Same constructor signatures, attributes and method names as the reference (cited per class).  Differences, all
+opt-in or invisible to a script that only uses the documented attributes:
+
+  * samples live on the GPU; `axion_energy`, `axion_flux` (float64) and `decay_axion_weight`, `scatter_axion_weight`
+    (float32, like the reference) are materialised on the host lazily, as NumPy arrays, when read.  Assigning to
+    them uploads the new values.
+  * random variates come from a counter-based Philox4x32-10 stream keyed by (seed, row, sample) instead of the global
+    MT19937 state; `seed=None` draws the seed from `np.random` so `np.random.seed(...)` still makes runs
+    reproducible.  `simulate(uniforms=...)` injects U[0,1) variates in the reference's draw order (parity mode).
+  * `fused=True` defers `simulate()`/`propagate()` and lets `EventGenerator.decays()` run production -> propagate ->
+    decay-rate in ONE kernel without materialising per-sample arrays (they are recomputed on demand, bit-identically,
+    because the variates are a pure function of the seed).
+
+There is no CPU fallback: every array operation below is a CUDA kernel in libalpk.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from numpy import arctan, pi, power, sqrt
+
+from . import _native as N
+from . import params as P
+from .constants import AVOGADRO, HBARC, M_E
+from .decay import W_ee, W_gg, W_gg_loop
+from .materials import Material
+from .photon_xs import AbsCrossSection
+from .runtime import Runtime
+
+_EMPTY64 = np.zeros(0, dtype=np.float64)
+
+__all__ = ["AxionFlux", "FluxPrimakoffIsotropic", "FluxComptonIsotropic"]
+
+
+def _as_flux_table(flux, name):
+    a = np.asarray(flux, dtype=np.float64)
+    if a.ndim != 2 or a.shape[1] < 2:
+        # the reference indexes photon[0], photon[1] of every row (fluxes.py:134-135) and fails on 1-D input
+        raise IndexError(f"{name} must have shape (n, 2): rows of [energy, weight]")
+    return a
+
+
+def _draw_seed():
+    # one draw from the global legacy NumPy RNG, so np.random.seed(s) pins the Philox key like it pins the reference
+    return int(np.random.randint(0, 2**63 - 1, dtype=np.int64))
+
+
+class AxionFlux:
+    """Generic superclass (reference: fluxes.py:20-89)."""
+
+    def __init__(self, axion_mass, target: Material, det_dist, det_length, det_area, n_samples=1000,
+                 off_axis_angle=0.0, timing_window_ns=np.inf, seed=None, device=None, fused=False, keep_f64=False):
+        self.ma = axion_mass
+        self.target_z = target.z[0]
+        self.target_a = target.z[0] + target.n[0]
+        self.target_density = target.density
+        self.det_dist = det_dist  # meters
+        self.det_length = det_length  # meters
+        self.det_area = det_area  # square meters
+        self.axion_angle = []
+        self.n_samples = n_samples
+        self.off_axis_angle = off_axis_angle
+        self.timing_window = 1e-9 * timing_window_ns
+        # --- device state ---
+        self.seed = seed
+        self.fused = fused
+        self.keep_f64 = keep_f64          # also keep the float64 weights before the float32 cast (parity / fp64 mode)
+        self._device = device
+        self._rt_cached = None
+        self._reset_samples()
+
+    # ---- runtime / state -----------------------------------------------------------------------------------------
+    @property
+    def _rt(self) -> Runtime:
+        if self._rt_cached is None:
+            self._rt_cached = Runtime.get(self._device)
+        return self._rt_cached
+
+    def _reset_samples(self):
+        self._E = self._F = None            # device float64: axion_energy / axion_flux
+        self._D32 = self._S32 = None        # device float32: decay / scatter weights
+        self._D64 = self._S64 = None        # device float64 pre-cast weights (keep_f64)
+        self._pending_production = None     # callable materialising _E/_F (fused mode)
+        self._pending_prop = None           # (PropT) recorded by propagate() in fused mode
+        self._host = {}
+
+    def n_flux(self):
+        self._ensure_production()
+        return 0 if self._E is None else int(self._E.shape[0])
+
+    def _ensure_production(self):
+        if self._E is None and self._pending_production is not None:
+            self._pending_production()
+
+    def _ensure_propagated(self):
+        if self._D32 is None and self._pending_prop is not None:
+            self._run_propagate(self._pending_prop)
+
+    def _set_production(self, E, F):
+        self._E, self._F = E, F
+        self._D32 = self._S32 = self._D64 = self._S64 = None
+        self._host = {}
+
+    def _host_get(self, key, tensor, empty):
+        if tensor is None:
+            return empty
+        h = self._host.get(key)
+        if h is None:
+            h = self._host[key] = tensor.cpu().numpy()
+        return h
+
+    # ---- the reference's public attributes ---------------------------------------------------------------------------
+    @property
+    def axion_energy(self):
+        self._ensure_production()
+        return self._host_get("E", self._E, [])
+
+    @axion_energy.setter
+    def axion_energy(self, v):
+        self._pending_production = None
+        self._E = self._rt.upload(np.asarray(v, dtype=np.float64).ravel())
+        self._host.pop("E", None)
+
+    @property
+    def axion_flux(self):
+        self._ensure_production()
+        return self._host_get("F", self._F, [])
+
+    @axion_flux.setter
+    def axion_flux(self, v):
+        self._pending_production = None
+        self._F = self._rt.upload(np.asarray(v, dtype=np.float64).ravel())
+        self._host.pop("F", None)
+
+    @property
+    def decay_axion_weight(self):
+        self._ensure_propagated()
+        return self._host_get("D32", self._D32, [])
+
+    @decay_axion_weight.setter
+    def decay_axion_weight(self, v):
+        self._pending_prop = None
+        self._D32 = self._rt.upload(np.asarray(v, dtype=np.float32).ravel(), np.float32)
+        self._host.pop("D32", None)
+
+    @property
+    def scatter_axion_weight(self):
+        self._ensure_propagated()
+        return self._host_get("S32", self._S32, [])
+
+    @scatter_axion_weight.setter
+    def scatter_axion_weight(self, v):
+        self._pending_prop = None
+        self._S32 = self._rt.upload(np.asarray(v, dtype=np.float32).ravel(), np.float32)
+        self._host.pop("S32", None)
+
+    @property
+    def decay_axion_weight_f64(self):
+        """float64 decay weights before the float32 cast and acceptance factor (needs keep_f64=True)."""
+        self._ensure_propagated()
+        return self._host_get("D64", self._D64, _EMPTY64)
+
+    @property
+    def scatter_axion_weight_f64(self):
+        self._ensure_propagated()
+        return self._host_get("S64", self._S64, _EMPTY64)
+
+    def device_arrays(self):
+        """The sample arrays as torch CUDA tensors (no copy): E, flux (f64), decay_w, scatter_w (f32)."""
+        self._ensure_production()
+        self._ensure_propagated()
+        return {"axion_energy": self._E, "axion_flux": self._F, "decay_axion_weight": self._D32,
+                "scatter_axion_weight": self._S32}
+
+    # ---- reference methods ----------------------------------------------------------------------------------------------
+    def det_sa(self):
+        return arctan(sqrt(self.det_area / pi) / self.det_dist)
+
+    def _prop_params(self, decay_width, rescale_factor, geom_accept, time_of_flight_cut):
+        return P.prop_params(self.ma, decay_width, rescale_factor, self.det_dist, self.det_length,
+                             geom_accept=geom_accept,
+                             timing_window=self.timing_window if time_of_flight_cut is not None else None)
+
+    def _run_propagate(self, prop):
+        self._ensure_production()
+        self._pending_prop = None
+        rt = self._rt
+        n = 0 if self._E is None else int(self._E.shape[0])
+        if self._F is None or int(self._F.shape[0]) != n:
+            raise ValueError("axion_energy and axion_flux have different lengths")
+        with rt.activate():
+            self._D32 = rt.empty(n, torch.float32)
+            self._S32 = rt.empty(n, torch.float32)
+            self._D64 = rt.empty(n) if self.keep_f64 else None
+            self._S64 = rt.empty(n) if self.keep_f64 else None
+            if n:
+                N.call("alpk_propagate", N.ptr(self._E), N.ptr(self._F), n, C.byref(prop), N.ptr(self._D32),
+                       N.ptr(self._S32), N.ptr(self._D64), N.ptr(self._S64), rt.stream())
+        for k in ("D32", "S32", "D64", "S64"):
+            self._host.pop(k, None)
+
+    def _propagate(self, decay_width, rescale_factor=1.0, geom_accept=None, time_of_flight_cut=None):
+        prop = self._prop_params(decay_width, rescale_factor, geom_accept, time_of_flight_cut)
+        self._D32 = self._S32 = self._D64 = self._S64 = None
+        for k in ("D32", "S32", "D64", "S64"):
+            self._host.pop(k, None)
+        if self.fused:
+            self._pending_prop = prop
+        else:
+            self._run_propagate(prop)
+
+    def propagate(self, decay_width, rescale_factor=1.0, time_of_flight_cut=None):
+        """Survival x decay probability weights (reference: AxionFlux.propagate, fluxes.py:43-65)."""
+        self._propagate(decay_width, rescale_factor, None, time_of_flight_cut)
+
+    def _geom_accept(self):
+        return self.det_area / (4*pi*self.det_dist**2)          # fluxes.py:160
+
+    # ---- event-rate hooks used by the generators -------------------------------------------------------------------------
+    def _decay_rate(self, ev, want_event_w):
+        """(rate tensor[1], event_w tensor or None): generators.py:88-92 on the device."""
+        rt = self._rt
+        fused = self._fused_decay_rate(ev) if (self.fused and not want_event_w) else None
+        if fused is not None:
+            return fused, None
+        self._ensure_production()
+        self._ensure_propagated()
+        n = 0 if self._E is None else int(self._E.shape[0])
+        if self._D32 is None or int(self._D32.shape[0]) != n:
+            raise ValueError("propagate() must run before decays(): decay_axion_weight does not match axion_energy")
+        with rt.activate():
+            rate = rt.empty(1)
+            evw = rt.empty(n) if want_event_w else None
+            N.call("alpk_decays", N.ptr(self._E), N.ptr(self._D32), n, C.byref(ev), N.ptr(evw), N.ptr(rate),
+                   N.ptr(rt.scratch), rt.stream())
+        return rate, evw
+
+    def _fused_decay_rate(self, ev):
+        return None      # flux classes with a fused production->propagate->decays kernel override this
+
+
+def _width_e(self, ge, ma):
+    if self.loop_decay:
+        return W_ee(ge, ma) + W_gg_loop(ge, ma, M_E)
+    else:
+        return W_ee(ge, ma)
+
+
+class FluxPrimakoffIsotropic(AxionFlux):
+    """
+    Primakoff-produced ALP flux from a photon flux table [[E_gamma, counts/s], ...] in the target
+    (reference: fluxes.py:111-169).  One ALP sample per photon row with E_gamma >= m_a.
+    """
+    def __init__(self, photon_flux=[[1, 1]], target=None, det_dist=4.0, det_length=0.2,
+                 det_area=0.04, axion_mass=0.1, axion_coupling=1e-3, n_samples=1000, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, **kwargs)
+        self.photon_flux = photon_flux
+        self.gagamma = axion_coupling
+        self.n_samples = n_samples
+        self.target_photon_xs = AbsCrossSection(target)
+
+    def decay_width(self, gagamma, ma):
+        return W_gg(gagamma, ma)
+
+    def photon_flux_dN_dE(self, energy):
+        pf = np.asarray(self.photon_flux, dtype=np.float64)
+        return np.interp(energy, pf[:, 0], pf[:, 1], left=0.0, right=0.0)
+
+    def _stage_inputs(self):
+        """Host-side row filter (fluxes.py:136) + upload of the surviving rows (SoA: energies, weights)."""
+        pf = _as_flux_table(self.photon_flux, "photon_flux")
+        keep = ~(pf[:, 0] < self.ma)
+        rt = self._rt
+        with rt.activate():
+            self._inputs = (rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1]), int(np.count_nonzero(keep)))
+        return self._inputs
+
+    def _produce(self):
+        """Launch the per-row production kernel on the staged inputs (device resident)."""
+        self._pending_production = None
+        d_eg, d_ph, n = self._inputs
+        rt = self._rt
+        with rt.activate():
+            E, F = rt.empty(n), rt.empty(n)
+            if n:
+                le, lx, nt = self.target_photon_xs.device_table(rt)
+                pref, r02 = P.primakoff_consts(self.gagamma, self.target_z)
+                N.call("alpk_primakoff", N.ptr(d_eg), N.ptr(d_ph), n, N.ptr(le), N.ptr(lx), nt,
+                       float(self.ma), pref, r02, N.ptr(E), N.ptr(F), rt.stream())
+        self._set_production(E, F)
+
+    def simulate(self):
+        self._reset_samples()
+        self._stage_inputs()
+        if self.fused:
+            self._pending_production = self._produce
+        else:
+            self._produce()
+
+    def propagate(self, new_coupling=None, is_isotropic=True):
+        geom = self._geom_accept() if is_isotropic else None
+        if new_coupling is not None:
+            rescale = power(new_coupling/self.gagamma, 2)
+            self._propagate(W_gg(new_coupling, self.ma), rescale, geom)
+        else:
+            self._propagate(W_gg(self.gagamma, self.ma), 1.0, geom)
+
+
+class FluxComptonIsotropic(AxionFlux):
+    """
+    ALP flux from Compton-like scattering gamma e- -> a e- (reference: fluxes.py:188-252).  `n_samples` uniform
+    E_a draws per photon row, weighted by dsigma/dE_a / sigma_abs.
+    """
+    def __init__(self, photon_flux=[[1, 1]], target=None, det_dist=4.,
+                 det_length=0.2, det_area=0.04, axion_mass=0.1, axion_coupling=1e-3, n_samples=100,
+                 is_isotropic=True, loop_decay=False, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, **kwargs)
+        self.photon_flux = photon_flux
+        self.ge = axion_coupling
+        self.n_samples = n_samples
+        self.target_photon_xs = AbsCrossSection(target)
+        self.is_isotropic = is_isotropic
+        self.loop_decay = loop_decay
+        self._rows = None
+        self.row_offset = 0      # global index of photon_flux row 0 when the table is one shard of a larger one
+
+    decay_width = _width_e
+
+    def _stage_inputs(self, uniforms=None):
+        """Host-side row filter (fluxes.py:214-216) + upload of the surviving rows, their global row ids (Philox
+        key) and, in parity mode, the injected uniforms."""
+        pf = _as_flux_table(self.photon_flux, "photon_flux")
+        s = 2 * M_E * pf[:, 0] + M_E ** 2
+        keep = ~(s < (M_E + self.ma)**2)
+        row_ids = (np.nonzero(keep)[0] + int(self.row_offset)).astype(np.uint32)
+        ns = int(self.n_samples)
+        n_rows = int(row_ids.shape[0])
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        self._seed_used = seed
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+            if uniforms.shape[0] != n_rows * ns:
+                raise ValueError(f"uniforms must hold n_rows*n_samples = {n_rows * ns} variates, got {uniforms.shape[0]}")
+        rt = self._rt
+        with rt.activate():
+            self._inputs = (rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1]), n_rows, ns, rt.upload(row_ids, np.uint32),
+                            rt.upload(uniforms) if uniforms is not None else None, seed)
+            self._table = rt.empty(n_rows * N.COMPTON_NP)
+        return self._inputs
+
+    def _launch_rows(self):
+        """Per-row constants (threshold window, prefactors, sigma_abs lookup) -> row table, on the device."""
+        d_eg, d_ph, n_rows, ns, d_ids, d_u, seed = self._inputs
+        par = P.compton_params(self.ma, self.ge, self.target_z, ns)
+        rt = self._rt
+        with rt.activate():
+            if n_rows:
+                le, lx, nt = self.target_photon_xs.device_table(rt)
+                N.call("alpk_compton_rows", N.ptr(d_eg), N.ptr(d_ph), n_rows, N.ptr(le), N.ptr(lx), nt,
+                       C.byref(par), N.ptr(self._table), rt.stream())
+        self._rows = (self._table, n_rows, ns, d_ids, par, d_u, seed)
+
+    def _produce(self):
+        self._pending_production = None
+        rt = self._rt
+        n = self._rows[1] * self._rows[2]
+        with rt.activate():
+            E, F = rt.empty(n), rt.empty(n)
+            self._launch_samples(E, F, None, None)
+        self._set_production(E, F)
+
+    def simulate(self, uniforms=None):
+        """uniforms: optional U[0,1) array, n_samples per row passing the threshold, row-major (parity mode)."""
+        self._reset_samples()
+        self._stage_inputs(uniforms)
+        self._launch_rows()
+        if self.fused:
+            self._pending_production = self._produce
+        else:
+            self._produce()
+
+    def _launch_samples(self, E, F, prop, ev, d32=None, s32=None, d64=None, s64=None, evw=None, rate=None):
+        table, n_rows, ns, d_ids, par, d_u, seed = self._rows
+        rt = self._rt
+        N.call("alpk_compton_samples", N.ptr(table), n_rows, ns, N.ptr(d_ids), C.byref(par), N.ptr(d_u),
+               C.c_uint64(seed), N.ptr(E), N.ptr(F),
+               C.byref(prop) if prop is not None else None, N.ptr(d32), N.ptr(s32), N.ptr(d64), N.ptr(s64),
+               C.byref(ev) if ev is not None else None, N.ptr(evw), N.ptr(rate), N.ptr(rt.scratch), rt.stream())
+
+    def _fused_decay_rate(self, ev):
+        """production -> propagate -> decays in one kernel, nothing materialised."""
+        if self._rows is None or self._pending_prop is None or self._E is not None:
+            return None
+        rt = self._rt
+        with rt.activate():
+            rate = rt.empty(1)
+            self._launch_samples(None, None, self._pending_prop, ev, rate=rate)
+        return rate
+
+    def chain(self, days_exposure, threshold, new_coupling=None, materialize=True):
+        """One-kernel production -> propagate -> decays.  With materialize=True also fills axion_energy/axion_flux/
+        decay_axion_weight/scatter_axion_weight (device) and returns (rate tensor, event-weight tensor)."""
+        if self._rows is None:
+            raise RuntimeError("simulate() must be called first")
+        width, rescale = self._width_rescale(new_coupling)
+        prop = self._prop_params(width, rescale, self._geom_accept() if self.is_isotropic else None, None)
+        ev = P.event_params(days_exposure, threshold)
+        rt = self._rt
+        n = self._rows[1] * self._rows[2]
+        with rt.activate():
+            rate = rt.empty(1)
+            if materialize:
+                E, F = rt.empty(n), rt.empty(n)
+                d32, s32 = rt.empty(n, torch.float32), rt.empty(n, torch.float32)
+                evw = rt.empty(n)
+                self._launch_samples(E, F, prop, ev, d32=d32, s32=s32, evw=evw, rate=rate)
+                self._pending_production = None
+                self._pending_prop = None
+                self._set_production(E, F)
+                self._D32, self._S32 = d32, s32
+                return rate, evw
+            self._launch_samples(None, None, prop, ev, rate=rate)
+            return rate, None
+
+    def _width_rescale(self, new_coupling):
+        if new_coupling is not None:
+            return self.decay_width(new_coupling, self.ma), power(new_coupling/self.ge, 2)
+        return self.decay_width(self.ge, self.ma), 1.0
+
+    def propagate(self, new_coupling=None):
+        width, rescale = self._width_rescale(new_coupling)
+        self._propagate(width, rescale, self._geom_accept() if self.is_isotropic else None)

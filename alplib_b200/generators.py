@@ -1,0 +1,172 @@
+"""
+ALP event generators -- drop-in for the reference's `generators.py` classes on the hot path
+(ElectronEventGenerator generators.py:18-52, PhotonEventGenerator generators.py:57-128).
+
+`decays`, `compton`, `inverse_primakoff` return the total event count (np.float64, like `np.sum`); the per-sample
+event weights stay on the GPU and are copied to the host when the `decay_weights` / `scatter_weights` attributes are
+read.  `simulate_decay_4vectors` returns two `LorentzVectorArray`s and a weight array (sequence-compatible with the
+reference's three lists).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import params as P
+from .constants import METER_BY_MEV
+from .fluxes import AxionFlux, _draw_seed
+from .materials import Material
+from .vectors import LorentzVectorArray
+
+
+class _EventGenerator:
+    def __init__(self, flux: AxionFlux, detector: Material):
+        self.flux = flux
+        self.det_z = detector.z[0]
+        self.efficiency = None
+        self.energy_threshold = None
+        self._dev = {}            # name -> device tensor of per-sample event weights
+        self._hostcache = {}
+        self.materialize_weights = True   # keep per-sample event weights (device) so the attributes can be read
+
+    # reference attributes (host views, lazily copied)
+    @property
+    def axion_energy(self):
+        return np.array(self.flux.axion_energy)
+
+    def _weights(self, name, like):
+        t = self._dev.get(name)
+        if t is None:
+            return np.zeros_like(like)
+        h = self._hostcache.get(name)
+        if h is None:
+            h = self._hostcache[name] = t.cpu().numpy()
+        return h
+
+    @property
+    def decay_weights(self):
+        return self._weights("decay", self.flux.decay_axion_weight)
+
+    @property
+    def scatter_weights(self):
+        return self._weights("scatter", self.flux.scatter_axion_weight)
+
+    @property
+    def pair_weights(self):
+        return self._weights("pair", self.flux.scatter_axion_weight)
+
+    def _store(self, name, t):
+        self._dev[name] = t
+        self._hostcache.pop(name, None)
+
+    def decays(self, days_exposure, threshold):
+        """days*S_PER_DAY * decay_axion_weight * heaviside(E - threshold, 1), summed (generators.py:48-52, 88-92)."""
+        ev = P.event_params(days_exposure, threshold)
+        rate, evw = self.flux._decay_rate(ev, self.materialize_weights and not self.flux.fused)
+        self._store("decay", evw)
+        return np.float64(rate.item())
+
+    def decays_device(self, days_exposure, threshold):
+        """Same as decays() but returns the rate as a 1-element CUDA tensor without synchronising."""
+        ev = P.event_params(days_exposure, threshold)
+        rate, evw = self.flux._decay_rate(ev, False)
+        return rate
+
+    def _scatter(self, kind, xs, ntargets, days_exposure, threshold):
+        fl = self.flux
+        fl._ensure_production()
+        fl._ensure_propagated()
+        rt = fl._rt
+        n = 0 if fl._E is None else int(fl._E.shape[0])
+        if fl._S32 is None or int(fl._S32.shape[0]) != n:
+            raise ValueError("propagate() must run first: scatter_axion_weight does not match axion_energy")
+        ev = P.event_params(days_exposure, threshold)
+        with rt.activate():
+            rate = rt.empty(1)
+            evw = rt.empty(n) if self.materialize_weights else None
+            N.call("alpk_scatter_events", kind, N.ptr(fl._E), N.ptr(fl._S32), n, xs, float(ntargets / fl.det_area),
+                   float(METER_BY_MEV**2), C.byref(ev), N.ptr(evw), N.ptr(rate), N.ptr(rt.scratch), rt.stream())
+        self._store("scatter", evw)
+        return np.float64(rate.item())
+
+
+class ElectronEventGenerator(_EventGenerator):
+    """ALP-electron coupling: decay and inverse-Compton scattering rates (generators.py:18-52)."""
+
+    def compton(self, ge, ma, ntargets, days_exposure, threshold):
+        return self._scatter(0, P.icompton_consts(ma, ge, self.det_z), ntargets, days_exposure, threshold)
+
+
+class PhotonEventGenerator(_EventGenerator):
+    """ALP-photon coupling: decay and inverse-Primakoff rates, a -> gamma gamma decay MC (generators.py:57-128)."""
+
+    def propagate_isotropic(self, new_gagamma=1.0):
+        pass
+
+    def inverse_primakoff(self, gagamma, ma, ntargets, days_exposure, threshold=0.0):
+        return self._scatter(1, P.iprimakoff_consts(ma, gagamma, self.det_z), ntargets, days_exposure, threshold)
+
+    def simulate_decay_4vectors(self, days_exposure, n_samples=1, uniforms=None, seed=None):
+        """2-body decay a -> gamma gamma of every flux sample, `n_samples` decays each (generators.py:94-128).
+
+        Returns (photon-1 4-vectors, photon-2 4-vectors, weights): two LorentzVectorArray (sequence of
+        LorentzVector) and a float64 array, length n_flux*n_samples in parent-major order.  Parents are forward
+        (theta = 0) as for every flux class on this path (`axion_angle` empty, generators.py:111-112).
+        `uniforms` (parity mode): array [n_flux, 2, n_samples] -- per parent the phi draws then the theta draws."""
+        fl = self.flux
+        if len(fl.axion_angle) != 0:
+            raise NotImplementedError("parents with a polar angle come from flux classes outside this path")
+        fl._ensure_production()
+        fl._ensure_propagated()
+        rt = fl._rt
+        n_flux = 0 if fl._F is None else int(fl._F.shape[0])        # generators.py:98
+        if fl._D32 is None or int(fl._D32.shape[0]) != n_flux:
+            raise ValueError("propagate() must run before simulate_decay_4vectors()")
+        ns = int(n_samples)
+        n = n_flux * ns
+        ev = P.event_params(days_exposure, 0.0)
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+            if uniforms.shape[0] != 2 * n:
+                raise ValueError(f"uniforms must hold 2*n_flux*n_samples = {2 * n} variates")
+            seed = 0
+        elif seed is None:
+            seed = fl.seed if fl.seed is not None else _draw_seed()
+        with rt.activate():
+            table = rt.empty(n_flux * N.PARENT_NP)
+            p1 = torch.empty((4, n), dtype=torch.float64, device=rt.device)
+            p2 = torch.empty((4, n), dtype=torch.float64, device=rt.device)
+            w = rt.empty(n)
+            if n:
+                d_u = rt.upload(uniforms) if uniforms is not None else None
+                N.call("alpk_decay_parent_rows", N.ptr(fl._E), N.ptr(fl._D32), n_flux, float(fl.ma**2), C.byref(ev), ns,
+                       N.ptr(table), rt.stream())
+                N.call("alpk_decay2body", N.ptr(table), n_flux, ns, None, N.ptr(d_u), C.c_uint64(seed),
+                       N.ptr(p1), N.ptr(p2), N.ptr(w), rt.stream())
+        return LorentzVectorArray(p1), LorentzVectorArray(p2), _DeviceWeights(w)
+
+
+class _DeviceWeights:
+    """Event weights of the decay MC: a lazily-copied float64 host array with the device tensor alongside."""
+
+    def __init__(self, t):
+        self.device = t
+        self._h = None
+
+    def _host(self):
+        if self._h is None:
+            self._h = self.device.cpu().numpy()
+        return self._h
+
+    def __len__(self):
+        return int(self.device.shape[0])
+
+    def __getitem__(self, i):
+        return self._host()[i]
+
+    def __iter__(self):
+        return iter(self._host())
+
+    def __array__(self, dtype=None, copy=None):
+        return self._host() if dtype is None else self._host().astype(dtype)

@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the alplib Monte-Carlo flux-and-event path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # CUDA arm (one process per GPU under torchrun)
+    python bench.py --impl reference [--gpus N --steps K --warmup W]  # CPU arm: the reference algorithm (oracle port)
+
+Workload (BASELINE.json configs[1], "ex2_beam_dump", synthesised per SURVEY.md section 8d because the reference's
+example file is empty): photon spectrum of 1e4 log-spaced bins (0.5 MeV..1 GeV, Phi = 1e16 E^-1.5 exp(-E/150) /s) on a
+W target; Primakoff production (ma = 0.1 MeV, g = 1e-5 /MeV, one sample per bin) and Compton production (ma = 1.5 MeV,
+g = 1e-7, n_samples = 1e4 per bin); propagate to a 4 m / 0.2 m / 0.04 m^2 detector; decays(100 days, 5 MeV).
+A "step" is one pass of that chain; a "sample" is one weighted ALP sample taken through production + propagate +
+decay weighting.  With N GPUs every rank takes its own 1e4-bin shard of an N x 1e4-bin spectrum (weak scaling) and the
+per-step rates are merged with one NCCL all-reduce.
+
+`value`: samples/s with the flux tables resident in HBM, every per-sample output (E, flux, decay_w, scatter_w, event
+weight: 32 B/sample) written to HBM by the fused kernel.  `e2e`: the same chain through the public drop-in classes from
+HOST arrays (H2D of the flux tables and D2H of the rates inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "weighted ALP MC samples/sec (prod+propagate+decay)"
+UNIT = "samples/s"
+N_BINS = 10_000
+N_SAMPLES = 10_000
+MA_P, G_P = 0.1, 1e-5
+MA_C, G_C = 1.5, 1e-7
+GEOM = dict(det_dist=4.0, det_length=0.2, det_area=0.04)
+DAYS, THR = 100, 5.0
+SEED = 0xA1B2C3D4 + 2
+BYTES_PER_SAMPLE = 32          # E f64 + flux f64 + decay_w f32 + scatter_w f32 + event weight f64
+FLOPS_PER_SAMPLE = 180         # expanded FP64 flops of the Compton chain (SURVEY section 8d accounting)
+
+
+def c2_spectrum(n_bins_total, lo=0.5, hi=1e3):
+    e = np.logspace(np.log10(lo), np.log10(hi), n_bins_total)
+    return np.stack([e, 1e16 * e ** -1.5 * np.exp(-e / 150)], axis=1)
+
+
+def workload_config(world, n_samples=N_SAMPLES):
+    return {
+        "workload": "C2 ex2_beam_dump (synthetic): 1e4 photon bins/GPU x 1e4 Compton samples + 1e4 Primakoff samples, "
+                    "W target, propagate 4m/0.2m/0.04m2, decays(100 d, 5 MeV)",
+        "n_bins_per_gpu": N_BINS, "n_samples": n_samples, "ma_compton": MA_C, "g_compton": G_C,
+        "ma_primakoff": MA_P, "g_primakoff": G_P, "sharding": f"flux-bin ranges x{world}",
+        "outputs": "materialised in HBM (32 B/sample)",
+        "l2": "no flush needed: each step writes 3.2 GB of outputs (>> 126 MB L2) and re-reads none of it",
+    }
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# clocks
+# -----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = []
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                rows.append((ts, float(f[1]), float(f[2]), f[4:8]))
+            except ValueError:
+                continue
+        sel = [r for r in rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1 + 0.1)] or rows
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in sel for i in range(4) if r[3][i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median([r[1] for r in sel])), "sm_max_mhz": max(r[2] for r in sel),
+                "reasons": reasons, "samples": len(sel)}
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (NumPy oracle port, per-bin loops with n_samples-long vector ops like the
+# reference's simulate_single), fanned out over host cores by contiguous bin ranges.
+# -----------------------------------------------------------------------------------------------------------------
+def _cpu_chunk(args):
+    pf, n_samples, seed = args
+    from oracle import alp_oracle as O
+    W = O.AbsCrossSection(O.Material("W"))
+    ga = O.geom_acceptance(GEOM["det_area"], GEOM["det_dist"])
+    n = 0
+    # Primakoff: simulate + propagate + decays
+    E, F = O.primakoff_simulate(pf, MA_P, G_P, 74, W)
+    p = O.propagate(E, F, MA_P, O.W_gg(G_P, MA_P), 1.0, GEOM["det_dist"], GEOM["det_length"], geom_accept=ga)
+    _, r1 = O.decays(E, p["decay_w"], DAYS, THR)
+    n += E.shape[0]
+    # Compton: simulate + propagate + decays, in row blocks to bound memory
+    r2 = 0.0
+    us = O.UniformSource(np.random.RandomState(seed))
+    for i in range(0, pf.shape[0], 500):
+        E, F = O.compton_simulate(pf[i:i + 500], MA_C, G_C, 74, W, n_samples, us)
+        us.log.clear()
+        p = O.propagate(E, F, MA_C, O.W_ee(G_C, MA_C), 1.0, GEOM["det_dist"], GEOM["det_length"], geom_accept=ga)
+        _, r = O.decays(E, p["decay_w"], DAYS, THR)
+        r2 += float(r)
+        n += E.shape[0]
+    return n, float(r1), r2
+
+
+def cpu_pass(pf, n_samples, cores, pool=None):
+    """One pass of the chain on the host; returns (samples, seconds, rates)."""
+    chunks = np.array_split(np.arange(pf.shape[0]), cores)
+    jobs = [(pf[c], n_samples, 1000 + k) for k, c in enumerate(chunks) if c.size]
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_chunk, jobs) if pool is not None else [_cpu_chunk(j) for j in jobs]
+    dt = time.perf_counter() - t0
+    return sum(r[0] for r in res), dt, (sum(r[1] for r in res), sum(r[2] for r in res))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_samples = 1000                                # bounded sample: every bin, 1/10 of the samples per bin
+    pf = c2_spectrum(N_BINS)
+    with mp.get_context("fork").Pool(cores) as pool:
+        _, dt, _ = cpu_pass(pf, n_samples, cores, pool)
+        budget = 150.0                              # keep the whole run within a few minutes
+        if dt * (args.steps + args.warmup) > budget:
+            n_samples = int(max(20, n_samples * budget / (dt * (args.steps + args.warmup))))
+        for _ in range(args.warmup):
+            cpu_pass(pf, n_samples, cores, pool)
+        n_tot, t_tot = 0, 0.0
+        for _ in range(args.steps):
+            n, dt, _ = cpu_pass(pf, n_samples, cores, pool)
+            n_tot += n
+            t_tot += dt
+    v = n_tot / t_tot
+    sample = f"C2 with n_samples={n_samples} per bin (all {N_BINS} bins): {n_tot // max(args.steps, 1)} samples/step"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args.gpus, n_samples),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                            "note": "NumPy restatement of the reference algorithm (oracle/alp_oracle.py, pinned "
+                                    "bit-for-bit against the reference); the reference itself is Python and cannot "
+                                    "travel to the GPU box.  The port keeps the reference's per-bin vector loops but "
+                                    "collects arrays instead of per-sample list.append, so it is ~3x FASTER than the "
+                                    "unmodified reference (1.6e6 samples/s/core, BASELINE.md section 2)."},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# -----------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import alplib_b200 as A
+    from alplib_b200 import _native as NV
+    from alplib_b200.runtime import Runtime
+    rt = Runtime.get(local)
+    W, Ar = A.Material("W"), A.Material("Ar")
+
+    pf_all = c2_spectrum(N_BINS * world)
+    pf = np.ascontiguousarray(pf_all[rank * N_BINS:(rank + 1) * N_BINS])
+    prim = A.FluxPrimakoffIsotropic(pf, W, axion_mass=MA_P, axion_coupling=G_P, **GEOM)
+    comp = A.FluxComptonIsotropic(pf, W, axion_mass=MA_C, axion_coupling=G_C, n_samples=N_SAMPLES, seed=SEED, **GEOM)
+    comp.row_offset = rank * N_BINS
+    prim._stage_inputs()
+    comp._stage_inputs()                       # flux tables now resident in HBM
+    genP = A.PhotonEventGenerator(prim, Ar)
+    n_step = prim._inputs[2] + comp._inputs[2] * N_SAMPLES
+    n_compton = comp._inputs[2] * N_SAMPLES
+    rates = torch.zeros(2, dtype=torch.float64, device=rt.device)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
+
+    def step(kpair=None):
+        prim._produce()
+        prim.propagate()
+        r1 = genP.decays_device(DAYS, THR)
+        comp._launch_rows()
+        if kpair is not None:
+            kpair[0].record()
+        r2, _ = comp.chain(DAYS, THR, materialize=True)
+        if kpair is not None:
+            kpair[1].record()
+        rates[0:1].copy_(r1)
+        rates[1:2].copy_(r2)
+        if world > 1:
+            dist.all_reduce(rates)             # the path's only exchange: merged rates (NCCL over NVLink)
+        return rates
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = NV.launch_count()
+    t_host0 = time.perf_counter()
+    ev0.record()
+    for k in range(args.steps):
+        step(kev[k] if k < len(kev) else None)  # per-launch duration of the dominant kernel: CUDA events on its stream
+    ev1.record()
+    barrier()
+    t_host1 = time.perf_counter()
+    kernel_ms = [a.elapsed_time(b) for a, b in kev[:min(args.steps, len(kev))]]
+    launches = NV.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=rt.device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    final_rates = [float(x) for x in rates.cpu()]
+    value = world * n_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public drop-in API, host arrays in, rates out ------------------------------------
+    def e2e_step(fused):
+        p = A.FluxPrimakoffIsotropic(pf, W, axion_mass=MA_P, axion_coupling=G_P, fused=fused, **GEOM)
+        p.simulate(); p.propagate()
+        rp = A.PhotonEventGenerator(p, Ar).decays(DAYS, THR)
+        c = A.FluxComptonIsotropic(pf, W, axion_mass=MA_C, axion_coupling=G_C, n_samples=N_SAMPLES, seed=SEED,
+                                   fused=fused, **GEOM)
+        c.row_offset = rank * N_BINS
+        c.simulate(); c.propagate()
+        rc = A.ElectronEventGenerator(c, Ar).decays(DAYS, THR)
+        return rp, rc, p, c
+
+    e2e = {}
+    e2e_steps = max(3, min(args.steps, 20))
+    for tag, fused in (("e2e", False), ("e2e_fused", True)):
+        for _ in range(2):
+            res = e2e_step(fused)
+        del res
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rp, rc, p, c = e2e_step(fused)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=rt.device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = sum(int(t.numel() * t.element_size()) for t in (p._inputs[0], p._inputs[1], c._inputs[0], c._inputs[1], c._inputs[4]))
+        e2e[tag] = {"value": world * n_step * e2e_steps / float(dt.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "steps": e2e_steps,
+                    "api": "Flux*Isotropic.simulate()/propagate() + EventGenerator.decays()"
+                           + (" with fused=True (deferred, one reduce-only kernel)" if fused else
+                              " (default: every per-sample array materialised in HBM)"),
+                    "rates": [float(rp), float(rc)]}
+        del p, c
+    clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (fused Compton production->propagate->decays, materialising) ------------
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+        kms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
+        achieved = n_compton * BYTES_PER_SAMPLE / (kms * 1e-3) / 1e9
+        # FP64 issue-rate denominator measured here (no FP64 figure in MEASURED_PEAKS.json)
+        iters, blocks = 20000, rt.sm_count * 8
+        scratch = rt.empty(blocks * 256)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        NV.call("alpk_fp64_peak", 2000, blocks, NV.ptr(scratch), rt.stream())
+        torch.cuda.synchronize()
+        f0.record()
+        NV.call("alpk_fp64_peak", iters, blocks, NV.ptr(scratch), rt.stream())
+        f1.record()
+        torch.cuda.synchronize()
+        fp64_peak = blocks * 256 * 16.0 * iters / (f0.elapsed_time(f1) * 1e-3) / 1e12
+        fp64_ach = n_compton * FLOPS_PER_SAMPLE / (kms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("compton_chain_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"kernel": "alpk::compton_samples_kernel<false,2> (production+propagate+decays, materialising)",
+                    "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": n_compton * BYTES_PER_SAMPLE,
+                    "kernel_ms": kms, "kernel_ms_samples": len(kernel_ms),
+                    "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
+                             "flops_per_sample": FLOPS_PER_SAMPLE,
+                             "peak_source": "DFMA loop measured in this run (alpk_fp64_peak)",
+                             "note": "the kernel is FP64-issue bound, not HBM bound; flops use SURVEY section 8d's "
+                                     "expanded accounting (div 8, sqrt 10, exp 25)"}}
+        # ---- CPU baseline beside it (bounded sample, 1 core) -------------------------------------------------------------
+        ns_cpu = 1000
+        n_cpu, dt_cpu, r_cpu = cpu_pass(c2_spectrum(N_BINS), ns_cpu, 1)
+        cpu_baseline = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"C2 with n_samples={ns_cpu} per bin (all {N_BINS} bins): {n_cpu} samples in {dt_cpu:.2f} s",
+                        "rates": list(r_cpu)}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": workload_config(world), "clocks": clocks, "e2e": e2e["e2e"], "e2e_fused": e2e["e2e_fused"],
+               "gpu_launches": int(launches), "samples_per_step": world * n_step, "rates": final_rates,
+               "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

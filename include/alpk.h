@@ -37,6 +37,8 @@ extern "C" {
 
 int alpk_version(void);
 const char* alpk_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t alpk_launch_count(void);
 /* writes name, SM count, compute capability of `device`; used by the loader to refuse non-sm_100 devices */
 int alpk_device_info(int device, char* h_name, int name_len, int* h_sm_count, int* h_cc_major, int* h_cc_minor);
 
@@ -131,6 +133,10 @@ int alpk_decay2body(const double* row_table, uint64_t n_parents, uint32_t n_samp
 /* ---- weighted histogram: np.histogram(x, bins=edges, weights=w) (half-open bins, last bin closed) ------------------ */
 int alpk_hist(const double* x, const double* w64_or_null, const float* w32_or_null, uint64_t n,
               const double* edges, int n_edges, double* hist /* [n_edges-1], accumulated into */, void* stream);
+
+/* FP64 issue-rate microbenchmark: `blocks` CTAs x 256 threads x 8 independent DFMA chains x iters (bench.py uses it
+ * to measure the FP64 roofline denominator on the box).  out: >= blocks*256 doubles (never written in practice). */
+int alpk_fp64_peak(uint64_t iters, int blocks, double* out, void* stream);
 
 /* sum of a f64 array (deterministic two-stage) */
 int alpk_sum(const double* x, uint64_t n, double* out, double* scratch, void* stream);

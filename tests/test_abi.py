@@ -1,0 +1,73 @@
+"""CPU tier: the C-ABI library builds for sm_100a, loads, and exports every symbol include/alpk.h declares (no compute
+calls -- there is no GPU here), and the product path refuses to run without a CUDA device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from alplib_b200 import _native as N
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    if not os.path.exists(N.LIB_PATH):
+        N.build()
+    return N.LIB_PATH
+
+
+def test_header_symbols_exported(libpath):
+    declared = N.declared_symbols()
+    assert len(declared) >= 15
+    L = ctypes.CDLL(libpath)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/alpk.h but not exported by libalpk.so"
+    # the ctypes binding covers the whole header
+    assert sorted(N._SIGNATURES) == declared
+
+
+def test_lib_binds_and_reports_version(libpath):
+    L = N.lib()
+    assert L.alpk_version() == 1
+    assert L.alpk_last_error() is not None
+    hdr = open(os.path.join(ROOT, "include", "alpk.h")).read()
+    assert int(re.search(r"#define ALPK_SCRATCH_DOUBLES (\d+)", hdr).group(1)) == N.SCRATCH_DOUBLES
+    assert int(re.search(r"#define ALPK_COMPTON_NP (\d+)", hdr).group(1)) == N.COMPTON_NP
+    assert int(re.search(r"#define ALPK_PARENT_NP (\d+)", hdr).group(1)) == N.PARENT_NP
+
+
+def test_struct_layouts_match_header():
+    # field order/size of the ctypes mirrors (doubles are 8-aligned, float+3 ints pack into 16 bytes)
+    assert ctypes.sizeof(N.PropT) == 7 * 8 + 16 + 3 * 8
+    assert ctypes.sizeof(N.EventT) == 8 + 8 + 8
+    assert ctypes.sizeof(N.ComptonT) == 5 * 8
+    assert N.PropT.geom32.offset == 56 and N.PropT.tof_light.offset == 72
+    assert N.EventT.threshold.offset == 16
+
+
+def test_library_contains_sm100a_code_only(libpath):
+    out = os.popen(f"cuobjdump -lelf {libpath} 2>/dev/null").read()
+    if out:
+        assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import alplib_b200 as A
+    fl = A.FluxPrimakoffIsotropic(np.array([[100.0, 1e12]]), A.Material("W"))
+    with pytest.raises(N.AlpkError, match="no CPU fallback"):
+        fl.simulate()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "alplib_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"
+                assert "hostcheck" not in src

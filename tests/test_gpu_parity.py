@@ -1,0 +1,288 @@
+"""GPU tier (pytest -m gpu, runs on the B200 box): the CUDA path, called through the reference-shaped Python classes
+and the C ABI of libalpk.so, against (i) the golden fixtures produced by the unmodified reference and (ii) the NumPy
+oracle on the same injected uniforms.  Tolerance: relative 1e-9 on FP64 quantities (north star), 1.2e-7 (one float32
+ulp) on the reference's float32 attributes; decay weights use the conditioned tolerance of conftest.decay_tol."""
+import numpy as np
+import pytest
+
+from conftest import assert_decay_close, load_golden, max_rel
+from oracle import alp_oracle as O
+from oracle import philox as PX
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+F32 = 1.2e-7
+GEOM = dict(det_dist=4.0, det_length=0.2, det_area=0.04)
+GA = O.geom_acceptance(0.04, 4.0)
+
+
+@pytest.fixture(scope="module")
+def A():
+    import torch
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import alplib_b200
+    from alplib_b200 import _native
+    _native.lib()          # fails loudly if libalpk.so is missing
+    return alplib_b200
+
+
+@pytest.mark.parametrize("mat", ["W", "C"])
+def test_abs_sigma(A, mat):
+    g = load_golden("abs_table_" + mat)
+    xs = A.AbsCrossSection(A.Material(mat))
+    assert max_rel(xs.sigma_mev(g["energy"]), g["sigma_mev"]) < 1e-12
+    assert float(xs.sigma_mev(2e5)) == pytest.approx(2.5680599121454694e+21, rel=1e-12)   # out-of-range quirk kept
+
+
+def test_c1_readme_example(A):
+    """BASELINE config 1: README Primakoff example end to end."""
+    g = load_golden("c1_primakoff")
+    fl = A.FluxPrimakoffIsotropic(g["photon_flux"], A.Material("W"), axion_mass=0.1, axion_coupling=1e-5,
+                                  n_samples=1000, keep_f64=True, **GEOM)
+    fl.simulate()
+    assert list(fl.axion_energy) == [100.0]
+    assert max_rel(fl.axion_flux, [327952.3965351194]) < TOL
+    fl.propagate()
+    assert fl.decay_axion_weight.dtype == np.float32 and fl.scatter_axion_weight.dtype == np.float32
+    assert max_rel(fl.decay_axion_weight, g["decay_w32"]) <= F32
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    assert max_rel(fl.decay_axion_weight_f64 * GA, g["decay_w64"]) < TOL
+    gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+    rate = gen.decays(100, 5.0)
+    assert isinstance(rate, np.float64)
+    assert rate == pytest.approx(284.1535949707031, rel=2 * F32)
+    assert max_rel(gen.decay_weights, g["decay_weights"]) <= 2 * F32
+    ipr = gen.inverse_primakoff(1e-5, 0.1, 1e27, 100, 5.0)
+    assert ipr == pytest.approx(float(g["iprimakoff_1e27_100_5"]), rel=2 * F32)
+    # 1-D photon table fails like the reference (README.md:90 quirk)
+    with pytest.raises(IndexError):
+        A.FluxPrimakoffIsotropic(np.array([100.0, 1e12]), A.Material("W")).simulate()
+    with pytest.raises(Exception, match="No such detector"):
+        A.Material("Unobtainium")
+
+
+def test_primakoff_ragged(A):
+    g = load_golden("primakoff_ragged")
+    ma, gg = float(g["ma"]), float(g["g"])
+    fl = A.FluxPrimakoffIsotropic(g["photon_flux"], A.Material("W"), axion_mass=ma, axion_coupling=gg, keep_f64=True, **GEOM)
+    fl.simulate()
+    assert np.array_equal(fl.axion_energy, g["axion_energy"])           # rows below ma dropped, order kept
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < TOL
+    assert len(fl.decay_axion_weight) == 0                                # reset by simulate()
+    fl.propagate()
+    assert max_rel(fl.scatter_axion_weight_f64 * GA, g["scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64 * GA, g["decay_w64"], g["scatter_w64"], TOL)
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    assert_decay_close(fl.decay_axion_weight, g["decay_w32"], g["scatter_w32"], TOL, extra_rel=F32)
+    fl.propagate(new_coupling=float(g["new_coupling"]))
+    assert max_rel(fl.scatter_axion_weight_f64 * GA, g["scatter_w64_new"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64 * GA, g["decay_w64_new"], g["scatter_w64_new"], TOL)
+    rate = A.PhotonEventGenerator(fl, A.Material("Ar")).decays(30, 1.0)
+    assert rate == pytest.approx(float(g["decays_30_1"]), rel=1e-6)
+
+
+@pytest.mark.parametrize("name", ["katc_compton", "compton_mid", "compton_loop"])
+def test_compton_chain_injected(A, name):
+    g = load_golden(name)
+    ma, gg, ns = float(g["ma"]), float(g["g"]), int(g["n_samples"])
+    loop = bool(g["loop_decay"]) if "loop_decay" in g else False
+    iso = bool(g["is_isotropic"]) if "is_isotropic" in g else True
+    fl = A.FluxComptonIsotropic(g["photon_flux"], A.Material("W"), axion_mass=ma, axion_coupling=gg, n_samples=ns,
+                                loop_decay=loop, is_isotropic=iso, keep_f64=True, **GEOM)
+    fl.simulate(uniforms=g["uniforms"])
+    assert np.array_equal(fl.axion_energy, g["axion_energy"])             # ma + (eg-ma)*u: bit exact
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < TOL
+    fl.propagate()
+    ga = GA if iso else 1.0
+    assert max_rel(fl.scatter_axion_weight_f64 * ga, g["scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64 * ga, g["decay_w64"], g["scatter_w64"], TOL)
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    assert_decay_close(fl.decay_axion_weight, g["decay_w32"], g["scatter_w32"], TOL, extra_rel=F32)
+    gen = A.ElectronEventGenerator(fl, A.Material("Ar"))
+    r_dec = gen.decays(100, 5.0)
+    r_com = gen.compton(gg, ma, 1e27, 100, 5.0)
+    assert r_com == pytest.approx(float(g["compton_1e27_100_5"]), rel=1e-6)
+    if float(g["decays_100_5"]) != 0:
+        assert r_dec == pytest.approx(float(g["decays_100_5"]), rel=1e-4 if name == "compton_loop" else 1e-6)
+    if "scatter_weights" in g:
+        assert max_rel(gen.scatter_weights, g["scatter_weights"], floor=1e-300) < 2 * F32
+    if "new_coupling" in g:
+        fl.propagate(new_coupling=float(g["new_coupling"]))
+        assert_decay_close(fl.decay_axion_weight_f64 * GA, g["decay_w64_new"], g["scatter_w64_new"], TOL)
+        assert_decay_close(fl.decay_axion_weight, g["decay_w32_new"], g["scatter_w32_new"], TOL, extra_rel=F32)
+
+
+def _c2_flux(n_bins):
+    e = np.logspace(np.log10(0.5), np.log10(1e3), n_bins)
+    return np.stack([e, 1e16 * e ** -1.5 * np.exp(-e / 150)], axis=1)
+
+
+def test_compton_free_running_matches_oracle_sample_by_sample(A):
+    """Free-running Philox mode: replay the kernel's uniforms with the NumPy Philox and feed them to the oracle."""
+    pf = _c2_flux(37)
+    ma, gg, ns, seed = 1.5, 1e-7, 501, 0xA1B2C3D4 + 2          # odd n_samples: pairs straddle rows
+    fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=gg, n_samples=ns, seed=seed,
+                                keep_f64=True, **GEOM)
+    fl.simulate()
+    fl.propagate()
+    keep = O.compton_row_valid(pf, ma)
+    assert 0 < keep.sum() < pf.shape[0]
+    u = np.concatenate([PX.uniform_1(seed, PX.TAG_COMPTON_EA, int(r), ns) for r in np.nonzero(keep)[0]])
+    oE, oF = O.compton_simulate(pf, ma, gg, 74, O.AbsCrossSection(O.Material("W")), ns, O.UniformSource(u))
+    assert np.array_equal(fl.axion_energy, oE)
+    assert max_rel(fl.axion_flux, oF) < TOL
+    p = O.propagate(oE, oF, ma, O.W_ee(gg, ma), 1.0, 4.0, 0.2, geom_accept=GA)
+    assert max_rel(fl.scatter_axion_weight_f64, p["scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64, p["decay_w64"], p["scatter_w64"], TOL)
+    assert_decay_close(fl.decay_axion_weight, p["decay_w"], p["scatter_w"], TOL, extra_rel=F32)
+    _, orate = O.decays(oE, p["decay_w"], 100, 5.0)
+    rate = A.ElectronEventGenerator(fl, A.Material("Ar")).decays(100, 5.0)
+    assert rate == pytest.approx(orate, rel=1e-6)
+
+
+def test_compton_fused_equals_unfused(A):
+    """One-kernel chain (materialising and reduce-only) vs the three separate launches: identical samples."""
+    pf = _c2_flux(300)
+    kw = dict(axion_mass=1.5, axion_coupling=1e-7, n_samples=1000, seed=77, **GEOM)
+    a = A.FluxComptonIsotropic(pf, A.Material("W"), **kw)
+    a.simulate(); a.propagate(new_coupling=3e-7)
+    gen_a = A.ElectronEventGenerator(a, A.Material("Ar"))
+    ra = gen_a.decays(100, 5.0)
+    b = A.FluxComptonIsotropic(pf, A.Material("W"), **kw)
+    b.simulate()
+    rate_b, evw_b = b.chain(100, 5.0, new_coupling=3e-7, materialize=True)
+    assert np.array_equal(a.axion_energy, b.axion_energy) and np.array_equal(a.axion_flux, b.axion_flux)
+    assert np.array_equal(a.decay_axion_weight, b.decay_axion_weight)
+    assert np.array_equal(a.scatter_axion_weight, b.scatter_axion_weight)
+    assert np.array_equal(gen_a.decay_weights, evw_b.cpu().numpy())
+    assert float(rate_b.item()) == pytest.approx(ra, rel=1e-12)
+    c = A.FluxComptonIsotropic(pf, A.Material("W"), fused=True, **kw)
+    c.simulate(); c.propagate(new_coupling=3e-7)
+    assert c._E is None and c._D32 is None                         # nothing launched yet
+    rc = A.ElectronEventGenerator(c, A.Material("Ar")).decays(100, 5.0)
+    assert c._E is None                                            # reduce-only: still nothing materialised
+    assert rc == pytest.approx(ra, rel=1e-12)
+    assert np.array_equal(c.axion_energy, a.axion_energy)          # recomputed on demand, bit-identical
+    assert np.array_equal(c.decay_axion_weight, a.decay_axion_weight)
+
+
+def test_compton_rates_statistical(A):
+    """Free-running RNG, different seeds: total rate agrees with an independent oracle run within MC error."""
+    pf = _c2_flux(200)
+    ma, gg, ns = 1.5, 1e-7, 2000
+    rates = []
+    for seed in (1, 2, 3, 4):
+        fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=gg, n_samples=ns, seed=seed, **GEOM)
+        fl.simulate(); fl.propagate()
+        rates.append(A.ElectronEventGenerator(fl, A.Material("Ar")).decays(100, 5.0))
+    us = O.UniformSource(np.random.RandomState(12345))
+    oE, oF = O.compton_simulate(pf, ma, gg, 74, O.AbsCrossSection(O.Material("W")), ns, us)
+    p = O.propagate(oE, oF, ma, O.W_ee(gg, ma), 1.0, 4.0, 0.2, geom_accept=GA)
+    ew, orate = O.decays(oE, p["decay_w"], 100, 5.0)
+    sigma = np.sqrt(np.sum(ew.astype(np.float64) ** 2))             # MC standard error of a sum of weights
+    assert abs(np.mean(rates) - orate) < 5 * sigma * np.sqrt(1 + 1 / 4)
+    assert np.std(rates) < 5 * sigma
+    # binned spectrum
+    edges = np.linspace(0, 1000, 21)
+    fl.propagate()
+    import torch
+    from alplib_b200.reduce import histogram
+    h = histogram(fl._E, fl._D32, edges).cpu().numpy()
+    oh = O.histogram(oE, p["decay_w"], edges)
+    err = np.sqrt(O.histogram(oE, p["decay_w"].astype(np.float64) ** 2, edges))
+    sel = oh > 0
+    assert np.all(np.abs(h[sel] - oh[sel]) < 6 * np.sqrt(2) * err[sel] + 1e-300)
+
+
+def test_propagate_misc(A):
+    g = load_golden("propagate_misc")
+    fl = A.FluxComptonIsotropic(np.array([[5.0, 1e9]]), A.Material("W"), axion_mass=0.9, axion_coupling=1e-6,
+                                n_samples=8, keep_f64=True, **GEOM)
+    fl.axion_energy = list(g["axion_energy"])
+    fl.axion_flux = list(g["axion_flux"])
+    fl.propagate()                                                  # W_ee = 0 below 2 m_e -> infinite lifetime
+    assert np.all(fl.decay_axion_weight == 0)
+    assert max_rel(fl.scatter_axion_weight, g["zero_scatter_w32"]) <= F32
+    fl.timing_window = float(g["tof_window"])
+    A.AxionFlux.propagate(fl, float(g["tof_width"]), float(g["tof_rescale"]), time_of_flight_cut=True)
+    assert max_rel(fl.scatter_axion_weight_f64, g["tof_scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64, g["tof_decay_w64"], g["tof_scatter_w64"], TOL)
+    # empty flux: every call is a no-op that returns empty arrays / zero rate
+    e = A.FluxComptonIsotropic(np.array([[0.3, 1e9]]), A.Material("W"), axion_mass=1.5, axion_coupling=1e-7, n_samples=4, **GEOM)
+    e.simulate(); e.propagate()
+    assert len(e.axion_energy) == 0 and len(e.decay_axion_weight) == 0
+    assert A.ElectronEventGenerator(e, A.Material("Ar")).decays(100, 5.0) == 0.0
+
+
+@pytest.mark.parametrize("name", ["katd_decay4", "decay4_boosted", "decay4_heavy"])
+def test_decay_4vectors_injected(A, name):
+    g = load_golden(name)
+    ma, ns = float(g["ma"]), int(g["n_samples"])
+    fl = A.FluxPrimakoffIsotropic(g["photon_flux"], A.Material("W"), axion_mass=ma, axion_coupling=float(g["g"]), **GEOM)
+    fl.simulate(); fl.propagate()
+    assert max_rel(fl.decay_axion_weight, g["decay_w32"]) <= F32
+    fl.decay_axion_weight = g["decay_w32"]                          # pin the parents' float32 weights to the fixture
+    gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+    npar = len(fl.axion_energy)
+    u = g["uniforms"][npar:].reshape(npar, 2, ns)                   # first n_flux draws: unused parent phis
+    l1, l2, w = gen.simulate_decay_4vectors(int(g["days"]), n_samples=ns, uniforms=u)
+    assert len(l1) == len(l2) == len(w) == npar * ns
+    scale = np.repeat(np.asarray(fl.axion_energy), ns)[:, None]
+    assert np.max(np.abs(l1.pmu - g["p1"]) / scale) < TOL           # |dp| / E_parent
+    assert np.max(np.abs(l2.pmu - g["p2"]) / scale) < TOL
+    assert np.array_equal(np.asarray(w), g["w"])
+    lv = l1[0]
+    assert isinstance(lv, A.LorentzVector) and lv.energy() == l1.pmu[0, 0]
+    if name == "katd_decay4":
+        assert lv.energy() == pytest.approx(46.15041488522627, rel=1e-12)
+        assert w[0] == 94.71786499023438 and w[3] == 26.58319664001465
+
+
+def test_decay_4vectors_free_running_and_invariants(A):
+    pf = np.stack([np.logspace(0, 5, 64), np.full(64, 1e12)], axis=1)
+    ma, ns, seed = 0.1, 3001, 991
+    fl = A.FluxPrimakoffIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=1e-5, seed=seed, **GEOM)
+    fl.simulate(); fl.propagate()
+    gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+    l1, l2, w = gen.simulate_decay_4vectors(100, n_samples=ns)
+    E = np.asarray(fl.axion_energy); npar = E.shape[0]
+    # sample by sample against the oracle on the replayed Philox variates
+    us = [np.zeros(npar)]
+    for r in range(npar):
+        u1, u2 = PX.uniform_2(seed, PX.TAG_DECAY2, r, ns)
+        us += [u1, u2]
+    o1, o2, ow = O.decay_4vectors(E, fl.decay_axion_weight, ma, 100, ns, O.UniformSource(np.concatenate(us)))
+    scale = np.repeat(E, ns)[:, None]
+    assert np.max(np.abs(l1.pmu - o1) / scale) < TOL and np.max(np.abs(l2.pmu - o2) / scale) < TOL
+    assert np.array_equal(np.asarray(w), ow)
+    # size-independent invariants: 4-momentum conservation, back-to-back transverse momenta, massless photons.
+    # (The reference's parent mass sqrt(E^2-p^2) and gamma = 1/sqrt(1-beta^2) cancel catastrophically for gamma >~ 1e4,
+    #  SURVEY section 7 hard part 1, so the invariants are asserted on the moderately boosted parents.)
+    p1, p2 = l1.pmu, l2.pmu
+    sel = np.repeat(E <= 50.0, ns)
+    assert sel.any() and not sel.all()
+    pa = np.repeat(np.sqrt(E ** 2 - ma ** 2), ns)
+    Ep = scale[:, 0]
+    assert np.max(np.abs(p1[sel, 0] + p2[sel, 0] - Ep[sel]) / Ep[sel]) < TOL
+    assert np.max(np.abs(p1[sel, 3] + p2[sel, 3] - pa[sel]) / Ep[sel]) < TOL
+    assert np.array_equal(p1[:, 1], -p2[:, 1]) and np.array_equal(p1[:, 2], -p2[:, 2])
+    m2 = p1[:, 0] ** 2 - p1[:, 1] ** 2 - p1[:, 2] ** 2 - p1[:, 3] ** 2
+    assert np.max(np.abs(m2[sel]) / Ep[sel] ** 2) < 1e-9
+    assert np.sum(np.asarray(w)) == pytest.approx(100 * 86400 * np.sum(fl.decay_axion_weight.astype(np.float64)), rel=1e-6)
+
+
+def test_histogram(A):
+    import torch
+    from alplib_b200.reduce import histogram, total
+    rs = np.random.RandomState(3)
+    x = np.concatenate([rs.uniform(-1, 11, 200001), [0.0, 10.0, 5.0, np.nan]])
+    w = rs.uniform(0, 2, x.shape[0])
+    for edges in (np.linspace(0, 10, 41), np.array([0.0, 0.1, 1.0, 2.5, 10.0]), np.logspace(-2, 1, 5000)):
+        dx = torch.from_numpy(x).cuda(); dw = torch.from_numpy(w).cuda()
+        h = histogram(dx, dw, edges).cpu().numpy()
+        ref = O.histogram(x, w, edges)
+        assert max_rel(h, ref, floor=1e-9) < 1e-10
+        h32 = histogram(dx, dw.float(), edges).cpu().numpy()
+        assert max_rel(h32, O.histogram(x, w.astype(np.float32).astype(np.float64), edges), floor=1e-9) < 1e-10
+    assert float(total(dw).item()) == pytest.approx(np.sum(w), rel=1e-13)
