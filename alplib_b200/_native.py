@@ -17,8 +17,9 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 SCRATCH_DOUBLES = 16384
 COMPTON_NP = 10
 PARENT_NP = 6
-BREM_NP = 10
-PAIRANN_NP = 12
+BREM_NP = 6
+PAIRANN_NP = 11
+GL_POINTS = 32
 
 
 class AlpkError(RuntimeError):
@@ -40,6 +41,19 @@ class EventT(C.Structure):
 class ComptonT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("aa", C.c_double), ("z", C.c_double),
                 ("n_samples", C.c_double)]
+
+
+class BremT(C.Structure):
+    _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("log10_ma", C.c_double), ("ep_min", C.c_double),
+                ("nt", C.c_double), ("pref_num", C.c_double), ("zl", C.c_double), ("zz", C.c_double),
+                ("pref_vec", C.c_double), ("ln10", C.c_double), ("n_samples", C.c_double), ("t_arg", C.c_double),
+                ("vector", C.c_int), ("use_track_length", C.c_int)]
+
+
+class PairAnnT(C.Structure):
+    _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("me2", C.c_double), ("me4", C.c_double),
+                ("pref", C.c_double), ("wconst", C.c_double), ("z", C.c_double), ("ge2", C.c_double),
+                ("ntad", C.c_double), ("hbarc2", C.c_double), ("n_samples", C.c_double)]
 
 
 def sources():
@@ -85,6 +99,13 @@ _SIGNATURES = {
     "alpk_primakoff": ([_P, _P, _U64, _P, _P, _I, _D, _D, _D, _P, _P, _P], _I),
     "alpk_compton_rows": ([_P, _P, _U64, _P, _P, _I, C.POINTER(ComptonT), _P, _P], _I),
     "alpk_compton_samples": ([_P, _U64, _U32, _P, C.POINTER(ComptonT), _P, _U64, _P, _P,
+                              C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_brem_rows": ([_P, _P, _U64, _P, _P, _U64, _P, _P, _I, _P, _P, _I, _P, _P, C.POINTER(BremT), _P, _P, _P], _I),
+    "alpk_brem_samples": ([_P, _U64, _U32, _P, C.POINTER(BremT), _P, _U64, _P, _P,
+                           C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_resonance_sum": ([_P, _P, _I, _D, _D, _D, _U64, _P, _U64, _P, _P, _P], _I),
+    "alpk_pairann_rows": ([_P, _P, _U64, C.POINTER(PairAnnT), _P, _P], _I),
+    "alpk_pairann_samples": ([_P, _U64, _U32, _P, C.POINTER(PairAnnT), _P, _U64, _P, _P,
                               C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_decay_parent_rows": ([_P, _P, _U64, _D, C.POINTER(EventT), _U32, _P, _P], _I),
     "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _P, _P, _P, _P], _I),

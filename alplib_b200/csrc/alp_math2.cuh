@@ -1,3 +1,209 @@
-// Per-sample arithmetic of the e+- channels (bremsstrahlung, resonance, associated production).
+// Per-row / per-sample arithmetic of the e+- channels: bremsstrahlung with track-length attenuation
+// (fluxes.py:257-356, prod_xs.py:209-221, 313-323), resonant production (fluxes.py:421-445) and associated production
+// e+ e- -> a gamma (fluxes.py:503-518, cross_section_mc.py:192-240, matrix_element.py:717-734).
+// Same conventions as alp_math.cuh: host+device, reference op order, no FMA contraction.
 #pragma once
 #include "alp_math.cuh"
+
+namespace alp {
+
+constexpr int kGL = 32;     // Gauss-Legendre points per panel of the track-length integral
+
+// ---- fmath.py:33-36 nu_integral(x, alpha=-1, T_max) = int_0^T x^(t-1)/Gamma(t) dt ---------------------------------------
+// The reference calls QUADPACK (scipy.integrate.quad); its result is exact to ~2e-16 on the range reached here.  A
+// 32-point Gauss-Legendre rule on the panels [0,1] and [1,T] agrees with it to <= 2e-15 for x in [1e-8, 13]
+// (measured against mpmath).  gl_x/gl_w: nodes/weights on [-1,1] (numpy.polynomial.legendre.leggauss(32)).
+ALP_HD double nu_integral_m1(double x, double T, const double* gl_x, const double* gl_w) {
+    const double lx = log(x);
+    double total = 0.0;
+    const int panels = T > 1.0 ? 2 : 1;
+    for (int p = 0; p < panels; ++p) {
+        const double a = p == 0 ? 0.0 : 1.0;
+        const double b = (panels == 1 || p == 1) ? T : 1.0;
+        const double h = 0.5 * (b - a), c = 0.5 * (b + a);
+        double acc = 0.0;
+        for (int i = 0; i < kGL; ++i) {
+            const double t = h * gl_x[i] + c;
+            acc += gl_w[i] * exp((t - 1.0) * lx - lgamma(t));
+        }
+        total += h * acc;
+    }
+    return total;
+}
+
+// fluxes.py:264-266
+ALP_HD double track_length_integrated_prob(double ei, double ef, double t_arg, const double* gl_x, const double* gl_w) {
+    const double h = heaviside(ei - ef, 1.0);
+    if (h == 0.0) return 0.0;       // (3/4)*0*nu/Ei; avoids log of a ratio < 1 raised to a real power
+    return ((0.75 * h) * nu_integral_m1(log(ei / ef), t_arg, gl_x, gl_w)) / ei;
+}
+
+// fluxes.py:257-259
+ALP_HD double track_length_prob(double ei, double ef, double t) {
+    const double b = 4.0 / 3.0;
+    return heaviside(ei - ef, 1.0) * fabs(pow(log(ei / ef), b * t - 1) / (ei * tgamma(b * t)));
+}
+
+// ---- bremsstrahlung ------------------------------------------------------------------------------------------------------
+enum BremRow { BR_E1 = 0, BR_W, BR_DL, BR_PREF, BR_EMIT, BR_DLX, BR_NP };
+
+struct BremGlobals {
+    double ma, ma2;
+    double log10_ma;        // np.log10(ma)
+    double ep_min;          // max(ma, M_E)
+    double nt;              // ntarget_area_density * HBARC**2
+    double pref_num;        // 2*r0**2*g**2/4/pi          (pseudoscalar, divided by E1 per row)
+    double zl;              // z**2*ln_el + z*ln_inel
+    double zz;              // z**2 + z
+    double pref_vec;        // chi*(4*ALPHA**2*g**2)/(4*pi) (vector)
+    double ln10;            // np.log(10)
+    double n_samples;
+    double t_arg;           // 4*max_t/3
+    int vector;             // boson_type == "vector"
+    int use_track_length;
+};
+
+// Row prelude.  e0/w0: the electron row; u: its scalar uniform (track-length mode).  fl = Phi_e(E0)+Phi_p(E0).
+ALP_HD void brem_row_params(double e0, double w0, double u, double fl, const BremGlobals& g, const double* gl_x,
+                            const double* gl_w, double* out) {
+    double e1, w;
+    if (g.use_track_length) {
+        e1 = g.ep_min + (e0 - g.ep_min) * u;                                     // fluxes.py:350
+        w = (e0 - g.ep_min) * (fl * track_length_integrated_prob(e0, e1, g.t_arg, gl_x, gl_w));   // :351, :314-316
+    } else {
+        e1 = e0; w = w0;                                                         // :354-356
+    }
+    const double r = g.ma / e1;
+    const double ea_max = e1 * (1 - r * r);                                      // :322
+    const bool emit = ea_max > g.ma;                                             // :323
+    out[BR_E1] = e1;
+    out[BR_W] = w;
+    out[BR_DL] = emit ? (log10(ea_max) - g.log10_ma) : 0.0;                      // :326, :329
+    out[BR_PREF] = g.pref_num / e1;                                              // prod_xs.py:217
+    out[BR_EMIT] = emit ? 1.0 : 0.0;
+    out[BR_DLX] = emit ? (log10(ea_max / e1) - log10(g.ma / e1)) : 0.0;          // fluxes.py:333
+}
+
+// prod_xs.py:209-221 with the z-only logs hoisted
+ALP_HD double brem_dsigma_dea(double ea, double e1, double pref_row, const BremGlobals& g) {
+    const double x = ea / e1;
+    const double q = g.ma / (x * kME);
+    const double f = (q * q) * (1 - x);
+    const double opf = 1 + f;
+    const double opf2 = opf * opf;
+    const double t1 = ((x * (1 + f / 1.5)) / opf2) * g.zl;
+    const double a = (opf * log(opf)) / (3 * (f * f));
+    const double b = ((1 + 4 * f) + 2 * (f * f)) / ((3 * f) * opf2);
+    const double ps = t1 + (x * g.zz) * (a - b);
+    return (pref_row * ps) * heaviside(ps, 0.0);
+}
+
+// prod_xs.py:313-323
+ALP_HD double brem_dsigma_dx_vector(double x, const BremGlobals& g) {
+    const double me2 = kME * kME;
+    return (g.pref_vec * ((1 - x) + (x * x) / 3)) / (((g.ma2 * (1 - x)) / x) + x * me2);
+}
+
+// fluxes.py:326-337: one sample of an emitting row.  Returns E_a, writes the production weight.
+ALP_HD double brem_sample(double u, const double* b, const BremGlobals& g, double& flux) {
+    const double lg = g.log10_ma + b[BR_DL] * u;                                 // uniform(log10 ma, log10 ea_max)
+    const double ea = pow(10.0, lg);
+    double diff_br;
+    if (!g.vector) {
+        const double mc_vol = ((g.ln10 * ea) * b[BR_DL]) / g.n_samples;          // :329
+        diff_br = (g.nt * mc_vol) * brem_dsigma_dea(ea, b[BR_E1], b[BR_PREF], g);   // :330
+    } else {
+        const double x = ea / b[BR_E1];                                          // :332
+        const double mc_vol = ((g.ln10 * x) * b[BR_DLX]) / g.n_samples;          // :333
+        diff_br = (g.nt * mc_vol) * brem_dsigma_dx_vector(x, g);                 // :334
+    }
+    flux = b[BR_W] * diff_br;                                                    // :337
+    return ea;
+}
+
+// ---- resonance: one term of the (E+, t) Monte-Carlo integral (fluxes.py:437-441, 410-411) -------------------------------------
+ALP_HD double resonance_term(double u1, double u2, double eres, double emax, double max_t, const double* pos_e,
+                             const double* pos_f, int n_pos) {
+    const double e = eres + (emax - eres) * u1;                                  // :437
+    const double t = 0.0 + (max_t - 0.0) * u2;                                   // :438
+    return interp(e, pos_e, pos_f, n_pos, 0.0, 0.0) * track_length_prob(e, eres, t);
+}
+
+// ---- associated production e+ e- -> a gamma --------------------------------------------------------------------------------------
+enum PairRow { PA_S = 0, PA_P1P3, PA_E1E3, PA_E3, PA_P3, PA_GAM, PA_M03, PA_VOL, PA_DEN, PA_TMAX, PA_C, PA_NP };
+
+struct PairGlobals {
+    double ma, ma2;
+    double me2, me4;        // M_E**2, M_E**4 (Python float pow)
+    double pref;            // (pi*ALPHA) * 1.0**2
+    double wconst;          // z * ge**2 * ntarget_area_density * HBARC**2 applied left to right after pos_wgt
+    double z, ge2, ntad, hbarc2;
+    double n_samples;
+};
+
+// Per positron row (already above threshold, fluxes.py:507): CM kinematics and the boost back to the lab.
+ALP_HD void pairann_row_params(double ep, double wgt, const PairGlobals& g, double* out) {
+    const double m1 = kME, m2 = kME, m4 = 0.0;
+    const double p1z = sqrt(ep * ep - g.me2);                                    // fluxes.py:513
+    const double e_in = ep + kME;                                                // cross_section_mc.py:208-209
+    const double pz_in = p1z + 0.0;
+    const double vz = pz_in / e_in;                                              // :211
+    const double s = ((e_in * e_in - 0.0) - 0.0) - pz_in * pz_in;                // mass2 :110-111
+    const double a1 = (s - m1 * m1) - m2 * m2;
+    const double b1 = (2 * m1) * m2;
+    const double p1 = sqrt((a1 * a1 - b1 * b1) / (4 * s));                       // :186
+    const double a3 = (s - g.ma2) - m4 * m4;
+    const double b3 = (2 * g.ma) * m4;
+    const double p3 = sqrt((a3 * a3 - b3 * b3) / (4 * s));                       // :189
+    const double e1 = sqrt(p1 * p1 + m1 * m1);                                   // :218
+    const double e3 = sqrt(p3 * p3 + g.ma2);                                   // :219
+    // lorentz_boost(p3, -v_in): v = (0,0,-vz)  (:235, :676-685)
+    const double nv = -vz;
+    const double beta = sqrt(nv * nv);
+    double gam = 1.0, m03 = 0.0;
+    if (beta != 0.0) {
+        const double nz = nv / beta;
+        gam = 1 / sqrt(1 - beta * beta);
+        m03 = ((-gam) * beta) * nz;
+    }
+    // soft-photon cut (matrix_element.py:730-732)
+    const double sa = s - 2 * g.me2;
+    const double ppos = sqrt((sa * sa - 4 * g.me4) / (4 * s));
+    const double epos = sqrt(ppos * ppos + g.me2);
+    out[PA_S] = s;
+    out[PA_P1P3] = p1 * p3;
+    out[PA_E1E3] = e1 * e3;
+    out[PA_E3] = e3;
+    out[PA_P3] = p3;
+    out[PA_GAM] = gam;
+    out[PA_M03] = m03;
+    out[PA_VOL] = ((4 * p1) * p3) / g.n_samples;                                 // :227
+    const double sp = m1 + m2, sm = m1 - m2;
+    out[PA_DEN] = ((16 * kPi) * (s - sp * sp)) * (s - sm * sm);                  // :181-182
+    out[PA_TMAX] = g.me2 - ((2 * 0.01) * epos) * epos;                           // matrix_element.py:732
+    out[PA_C] = (((wgt * g.z) * g.ge2) * g.ntad) * g.hbarc2;                     // fluxes.py:518
+}
+
+// One sample: u -> theta (the phi draw does not enter the lab energy for a beam along z).
+ALP_HD double pairann_sample(double u, const double* r, const PairGlobals& g, double& flux) {
+    const double theta = acos(1 - 2 * u);                                        // cross_section_mc.py:205
+    const double cth = cos(theta);
+    const double s = r[PA_S];
+    const double m1sq = g.me2, m3sq = g.ma2;
+    const double t = (m1sq + m3sq) + 2 * (r[PA_P1P3] * cth - r[PA_E1E3]);        // :221
+    // matrix_element.py:717-734
+    const double u_prop = ((g.me2 + g.ma2) - s) - t;
+    const double t_prop = g.me2 - t;
+    const double tail = t * (((-g.ma2) + s) + t);
+    const double mt2 = (-4 * ((3 * g.me4 - g.me2 * (g.ma2 + s)) + tail)) / (t_prop * t_prop);
+    const double mu2 = (-4 * ((7 * g.me4 + g.me2 * ((g.ma2 - 3 * s) - 4 * t)) + tail)) / (u_prop * u_prop);
+    const double mtmu = (8 * (((-3) * g.me4 + g.me2 * (s - 2 * t)) + tail)) / (u_prop * t_prop);
+    const double m2 = (mt2 + mu2) + 2 * mtmu;
+    const double val = (g.pref * m2) * heaviside(r[PA_TMAX] - t, 0.0);
+    const double wts = r[PA_VOL] * (val / r[PA_DEN]);                            // :228
+    flux = r[PA_C] * wts;
+    const double pz = r[PA_P3] * cth;                                            // :234
+    return r[PA_GAM] * r[PA_E3] + r[PA_M03] * pz;                                // boost row 0
+}
+
+}  // namespace alp

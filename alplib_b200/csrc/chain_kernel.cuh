@@ -1,0 +1,175 @@
+// Generic per-sample kernel of the flux pipeline: production (+ fused propagate (+ fused decays)).
+//
+//   Prod supplies: NP (doubles per row record), kTag (Philox stream tag), Globals, uidx() (layout of injected
+//   uniforms) and sample(u, row, globals, flux) -> E_a.  One uniform per sample.
+//
+//   Work decomposition: a CTA walks tiles of kThreads*2*kUnroll consecutive samples (grid = multiple of the SM
+//   count); the per-row records a tile touches are staged in shared memory (rows are long, so a tile touches 1-2 of
+//   them; for tiny n_samples the table is read through L1/L2 instead).  Each thread handles PAIRS of adjacent samples:
+//   one Philox4x32-10 call (2 x 53-bit uniforms) feeds both and stores are 16-byte (f64) / 8-byte (f32) vectors, fully
+//   coalesced.  Rates are reduced warp-shuffle -> shared -> one partial per CTA -> deterministic finalize kernel.
+#pragma once
+#include "common.cuh"
+
+namespace alpk {
+
+constexpr int kUnroll = 4;
+constexpr int kTile = kThreads * 2 * kUnroll;
+
+template <class Prod>
+struct ChainArgs {
+    const double* table; uint64_t n_rows; uint32_t n_samples; const uint32_t* row_ids;
+    typename Prod::Globals g; const double* uniforms; uint64_t seed;
+    double* out_e; double* out_f;
+    alp::PropConst prop; float* d32; float* s32; double* d64; double* s64;
+    alp::EventConst ev; double* event_w; double* partials;
+};
+
+template <class Prod, bool INJECT, int STAGE>   // STAGE 0: production; 1: + propagate; 2: + decays
+__global__ void __launch_bounds__(kThreads)
+chain_kernel(const ChainArgs<Prod> a) {
+    using namespace alp;
+    constexpr int NP = Prod::NP;
+    __shared__ double s_rows[kStageRows * NP];
+    __shared__ double red[32];
+    const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
+    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+    double acc = 0.0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t base = tile * kTile;
+        const uint64_t last = (base + kTile <= n ? base + kTile : n) - 1;
+        const uint64_t r0 = base / a.n_samples;
+        const uint64_t r1 = last / a.n_samples;
+        const int nrows = (int)(r1 - r0 + 1);
+        const double* rows;                          // row r -> rows + (r - r0)*NP
+        __syncthreads();                             // previous tile finished reading s_rows
+        if (nrows <= kStageRows) {
+            stage_rows<NP>(s_rows, a.table, r0, nrows);
+            rows = s_rows;
+        } else {
+            rows = a.table + r0 * NP;                // many tiny rows per tile: read through L1/L2 instead
+        }
+        __syncthreads();
+        const uint64_t row0_first = r0 * (uint64_t)a.n_samples;
+
+#pragma unroll 1
+        for (int k = 0; k < kUnroll; ++k) {
+            const uint64_t i0 = base + 2 * ((uint64_t)k * kThreads + threadIdx.x);
+            if (i0 >= n) break;
+            const bool have2 = (i0 + 1 < n);
+            double e[2], f[2], u[2];
+            float d32v[2], s32v[2];
+            double d64v[2], s64v[2], evv[2];
+            uint32_t rr[2], ss[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t off = (uint32_t)(i0 + ((j == 1 && !have2) ? 0 : j) - row0_first);
+                rr[j] = off / a.n_samples;
+                ss[j] = off - rr[j] * a.n_samples;
+            }
+            if (INJECT) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) u[j] = __ldg(a.uniforms + Prod::uidx(r0 + rr[j], ss[j], a.n_samples));
+            } else {
+                // sample s uses Philox counter s>>1, word pair s&1: adjacent samples of one row share a call
+                const uint64_t ra = r0 + rr[0];
+                const uint32_t rid0 = a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra;
+                const Philox4 q = philox4x32_10(ss[0] >> 1, 0u, rid0, Prod::kTag, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                u[0] = (ss[0] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+                if (rr[1] == rr[0] && (ss[1] >> 1) == (ss[0] >> 1)) {
+                    u[1] = (ss[1] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+                } else {
+                    const uint64_t rb = r0 + rr[1];
+                    const uint32_t rid1 = a.row_ids ? __ldg(a.row_ids + rb) : (uint32_t)rb;
+                    u[1] = uniform_1(a.seed, Prod::kTag, rid1, ss[1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                // (a lone last sample computes a throw-away duplicate in slot 1: keeps the pair loop branch-free)
+                const double* b = rows + (size_t)rr[j] * NP;
+                e[j] = Prod::sample(u[j], b, a.g, f[j]);
+                if (STAGE >= 1) {
+                    propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                    d32v[j] = prop_cast(d64v[j], a.prop);
+                    s32v[j] = prop_cast(s64v[j], a.prop);
+                }
+                if (STAGE >= 2) {
+                    evv[j] = decay_event_weight(e[j], d32v[j], a.ev);
+                    if (j == 0 || have2) acc += evv[j];
+                }
+            }
+            if (have2) {
+                if (a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
+                if (a.out_f) *reinterpret_cast<double2*>(a.out_f + i0) = make_double2(f[0], f[1]);
+                if (STAGE >= 1) {
+                    if (a.d32) *reinterpret_cast<float2*>(a.d32 + i0) = make_float2(d32v[0], d32v[1]);
+                    if (a.s32) *reinterpret_cast<float2*>(a.s32 + i0) = make_float2(s32v[0], s32v[1]);
+                    if (a.d64) *reinterpret_cast<double2*>(a.d64 + i0) = make_double2(d64v[0], d64v[1]);
+                    if (a.s64) *reinterpret_cast<double2*>(a.s64 + i0) = make_double2(s64v[0], s64v[1]);
+                }
+                if (STAGE >= 2 && a.event_w) *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
+            } else {
+                if (a.out_e) a.out_e[i0] = e[0];
+                if (a.out_f) a.out_f[i0] = f[0];
+                if (STAGE >= 1) {
+                    if (a.d32) a.d32[i0] = d32v[0];
+                    if (a.s32) a.s32[i0] = s32v[0];
+                    if (a.d64) a.d64[i0] = d64v[0];
+                    if (a.s64) a.s64[i0] = s64v[0];
+                }
+                if (STAGE >= 2 && a.event_w) a.event_w[i0] = evv[0];
+            }
+        }
+    }
+    if (STAGE >= 2) {
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) a.partials[blockIdx.x] = acc;
+    }
+}
+
+alp::PropConst to_prop(const alpk_prop_t* p);
+alp::EventConst to_event(const alpk_event_t* e);
+int finalize_sum(const double* partials, int n, double* out, cudaStream_t st);
+
+// Host-side launcher shared by every production channel.
+template <class Prod>
+int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
+                 const typename Prod::Globals& g, const double* uniforms, uint64_t seed, double* out_energy,
+                 double* out_flux, const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32, double* decay_w64,
+                 double* scatter_w64, const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
+                 void* stream) {
+    if (h_ev && (!h_prop || !rate || !scratch)) { set_error("%s: events need prop, rate and scratch", what); return 2; }
+    if (n_samples == 0 || n_samples > 0x7fffffffu - kTile) { set_error("%s: n_samples out of range", what); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t n = n_rows * (uint64_t)n_samples;
+    if (n == 0) {
+        if (h_ev) { cudaMemsetAsync(rate, 0, sizeof(double), st); }
+        return 0;
+    }
+    if (!row_table) { set_error("%s: null row table", what); return 2; }
+    ChainArgs<Prod> a;
+    memset(&a, 0, sizeof(a));
+    a.table = row_table; a.n_rows = n_rows; a.n_samples = n_samples; a.row_ids = row_ids;
+    a.g = g; a.uniforms = uniforms; a.seed = seed;
+    a.out_e = out_energy; a.out_f = out_flux;
+    const int stage = h_ev ? 2 : (h_prop ? 1 : 0);
+    if (h_prop) { a.prop = to_prop(h_prop); a.d32 = decay_w32; a.s32 = scatter_w32; a.d64 = decay_w64; a.s64 = scatter_w64; }
+    if (h_ev) { a.ev = to_event(h_ev); a.event_w = event_w; a.partials = scratch; }
+    const int grid = grid_for(n, kTile, 8);
+    const bool inj = uniforms != nullptr;
+    switch (stage * 2 + (inj ? 1 : 0)) {
+        case 0: chain_kernel<Prod, false, 0><<<grid, kThreads, 0, st>>>(a); break;
+        case 1: chain_kernel<Prod, true, 0><<<grid, kThreads, 0, st>>>(a); break;
+        case 2: chain_kernel<Prod, false, 1><<<grid, kThreads, 0, st>>>(a); break;
+        case 3: chain_kernel<Prod, true, 1><<<grid, kThreads, 0, st>>>(a); break;
+        case 4: chain_kernel<Prod, false, 2><<<grid, kThreads, 0, st>>>(a); break;
+        default: chain_kernel<Prod, true, 2><<<grid, kThreads, 0, st>>>(a); break;
+    }
+    if (check_launch(what)) return 1;
+    if (stage == 2) return finalize_sum(scratch, grid, rate, st);
+    return 0;
+}
+
+}  // namespace alpk

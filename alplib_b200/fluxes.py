@@ -24,7 +24,7 @@ from numpy import arctan, pi, power, sqrt
 
 from . import _native as N
 from . import params as P
-from .constants import AVOGADRO, HBARC, M_E
+from .constants import ALPHA, AVOGADRO, HBARC, M_E
 from .decay import W_ee, W_gg, W_gg_loop
 from .materials import Material
 from .photon_xs import AbsCrossSection
@@ -32,7 +32,8 @@ from .runtime import Runtime
 
 _EMPTY64 = np.zeros(0, dtype=np.float64)
 
-__all__ = ["AxionFlux", "FluxPrimakoffIsotropic", "FluxComptonIsotropic"]
+__all__ = ["AxionFlux", "FluxPrimakoffIsotropic", "FluxComptonIsotropic", "FluxBremIsotropic",
+           "FluxResonanceIsotropic", "FluxPairAnnihilationIsotropic", "track_length_prob"]
 
 
 def _as_flux_table(flux, name):
@@ -189,7 +190,7 @@ class AxionFlux:
         self._pending_prop = None
         rt = self._rt
         n = 0 if self._E is None else int(self._E.shape[0])
-        if self._F is None or int(self._F.shape[0]) != n:
+        if (0 if self._F is None else int(self._F.shape[0])) != n:
             raise ValueError("axion_energy and axion_flux have different lengths")
         with rt.activate():
             self._D32 = rt.empty(n, torch.float32)
@@ -310,60 +311,21 @@ class FluxPrimakoffIsotropic(AxionFlux):
             self._propagate(W_gg(self.gagamma, self.ma), 1.0, geom)
 
 
-class FluxComptonIsotropic(AxionFlux):
-    """
-    ALP flux from Compton-like scattering gamma e- -> a e- (reference: fluxes.py:188-252).  `n_samples` uniform
-    E_a draws per photon row, weighted by dsigma/dE_a / sigma_abs.
-    """
-    def __init__(self, photon_flux=[[1, 1]], target=None, det_dist=4.,
-                 det_length=0.2, det_area=0.04, axion_mass=0.1, axion_coupling=1e-3, n_samples=100,
-                 is_isotropic=True, loop_decay=False, **kwargs):
-        target = Material("W") if target is None else target
-        super().__init__(axion_mass, target, det_dist, det_length, det_area, **kwargs)
-        self.photon_flux = photon_flux
-        self.ge = axion_coupling
-        self.n_samples = n_samples
-        self.target_photon_xs = AbsCrossSection(target)
-        self.is_isotropic = is_isotropic
-        self.loop_decay = loop_decay
-        self._rows = None
-        self.row_offset = 0      # global index of photon_flux row 0 when the table is one shard of a larger one
+class _ChainFlux(AxionFlux):
+    """Flux classes whose samples come from the generic per-sample chain kernel (production -> [propagate -> [decays]]):
+    Compton, bremsstrahlung, associated production.  Subclasses stage their inputs and build the per-row table."""
+    _SAMPLES_FN = None          # C entry point of the per-sample kernel
+    _rows = None                # (row table, n_rows, n_samples, row ids, params struct, injected uniforms, seed)
 
     decay_width = _width_e
 
-    def _stage_inputs(self, uniforms=None):
-        """Host-side row filter (fluxes.py:214-216) + upload of the surviving rows, their global row ids (Philox
-        key) and, in parity mode, the injected uniforms."""
-        pf = _as_flux_table(self.photon_flux, "photon_flux")
-        s = 2 * M_E * pf[:, 0] + M_E ** 2
-        keep = ~(s < (M_E + self.ma)**2)
-        row_ids = (np.nonzero(keep)[0] + int(self.row_offset)).astype(np.uint32)
-        ns = int(self.n_samples)
-        n_rows = int(row_ids.shape[0])
-        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
-        self._seed_used = seed
-        if uniforms is not None:
-            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
-            if uniforms.shape[0] != n_rows * ns:
-                raise ValueError(f"uniforms must hold n_rows*n_samples = {n_rows * ns} variates, got {uniforms.shape[0]}")
+    def _launch_samples(self, E, F, prop, ev, d32=None, s32=None, d64=None, s64=None, evw=None, rate=None):
+        table, n_rows, ns, d_ids, par, d_u, seed = self._rows
         rt = self._rt
-        with rt.activate():
-            self._inputs = (rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1]), n_rows, ns, rt.upload(row_ids, np.uint32),
-                            rt.upload(uniforms) if uniforms is not None else None, seed)
-            self._table = rt.empty(n_rows * N.COMPTON_NP)
-        return self._inputs
-
-    def _launch_rows(self):
-        """Per-row constants (threshold window, prefactors, sigma_abs lookup) -> row table, on the device."""
-        d_eg, d_ph, n_rows, ns, d_ids, d_u, seed = self._inputs
-        par = P.compton_params(self.ma, self.ge, self.target_z, ns)
-        rt = self._rt
-        with rt.activate():
-            if n_rows:
-                le, lx, nt = self.target_photon_xs.device_table(rt)
-                N.call("alpk_compton_rows", N.ptr(d_eg), N.ptr(d_ph), n_rows, N.ptr(le), N.ptr(lx), nt,
-                       C.byref(par), N.ptr(self._table), rt.stream())
-        self._rows = (self._table, n_rows, ns, d_ids, par, d_u, seed)
+        N.call(self._SAMPLES_FN, N.ptr(table), n_rows, ns, N.ptr(d_ids), C.byref(par), N.ptr(d_u),
+               C.c_uint64(seed), N.ptr(E), N.ptr(F),
+               C.byref(prop) if prop is not None else None, N.ptr(d32), N.ptr(s32), N.ptr(d64), N.ptr(s64),
+               C.byref(ev) if ev is not None else None, N.ptr(evw), N.ptr(rate), N.ptr(rt.scratch), rt.stream())
 
     def _produce(self):
         self._pending_production = None
@@ -374,23 +336,11 @@ class FluxComptonIsotropic(AxionFlux):
             self._launch_samples(E, F, None, None)
         self._set_production(E, F)
 
-    def simulate(self, uniforms=None):
-        """uniforms: optional U[0,1) array, n_samples per row passing the threshold, row-major (parity mode)."""
-        self._reset_samples()
-        self._stage_inputs(uniforms)
-        self._launch_rows()
+    def _finish_simulate(self):
         if self.fused:
             self._pending_production = self._produce
         else:
             self._produce()
-
-    def _launch_samples(self, E, F, prop, ev, d32=None, s32=None, d64=None, s64=None, evw=None, rate=None):
-        table, n_rows, ns, d_ids, par, d_u, seed = self._rows
-        rt = self._rt
-        N.call("alpk_compton_samples", N.ptr(table), n_rows, ns, N.ptr(d_ids), C.byref(par), N.ptr(d_u),
-               C.c_uint64(seed), N.ptr(E), N.ptr(F),
-               C.byref(prop) if prop is not None else None, N.ptr(d32), N.ptr(s32), N.ptr(d64), N.ptr(s64),
-               C.byref(ev) if ev is not None else None, N.ptr(evw), N.ptr(rate), N.ptr(rt.scratch), rt.stream())
 
     def _fused_decay_rate(self, ev):
         """production -> propagate -> decays in one kernel, nothing materialised."""
@@ -435,3 +385,334 @@ class FluxComptonIsotropic(AxionFlux):
     def propagate(self, new_coupling=None):
         width, rescale = self._width_rescale(new_coupling)
         self._propagate(width, rescale, self._geom_accept() if self.is_isotropic else None)
+
+
+class FluxComptonIsotropic(_ChainFlux):
+    """
+    ALP flux from Compton-like scattering gamma e- -> a e- (reference: fluxes.py:188-252).  `n_samples` uniform
+    E_a draws per photon row, weighted by dsigma/dE_a / sigma_abs.
+    """
+    def __init__(self, photon_flux=[[1, 1]], target=None, det_dist=4.,
+                 det_length=0.2, det_area=0.04, axion_mass=0.1, axion_coupling=1e-3, n_samples=100,
+                 is_isotropic=True, loop_decay=False, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, **kwargs)
+        self.photon_flux = photon_flux
+        self.ge = axion_coupling
+        self.n_samples = n_samples
+        self.target_photon_xs = AbsCrossSection(target)
+        self.is_isotropic = is_isotropic
+        self.loop_decay = loop_decay
+        self.row_offset = 0      # global index of photon_flux row 0 when the table is one shard of a larger one
+
+    _SAMPLES_FN = "alpk_compton_samples"
+
+    def _stage_inputs(self, uniforms=None):
+        """Host-side row filter (fluxes.py:214-216) + upload of the surviving rows, their global row ids (Philox
+        key) and, in parity mode, the injected uniforms."""
+        pf = _as_flux_table(self.photon_flux, "photon_flux")
+        s = 2 * M_E * pf[:, 0] + M_E ** 2
+        keep = ~(s < (M_E + self.ma)**2)
+        row_ids = (np.nonzero(keep)[0] + int(self.row_offset)).astype(np.uint32)
+        ns = int(self.n_samples)
+        n_rows = int(row_ids.shape[0])
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        self._seed_used = seed
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+            if uniforms.shape[0] != n_rows * ns:
+                raise ValueError(f"uniforms must hold n_rows*n_samples = {n_rows * ns} variates, got {uniforms.shape[0]}")
+        rt = self._rt
+        with rt.activate():
+            self._inputs = (rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1]), n_rows, ns, rt.upload(row_ids, np.uint32),
+                            rt.upload(uniforms) if uniforms is not None else None, seed)
+            self._table = rt.empty(n_rows * N.COMPTON_NP)
+        return self._inputs
+
+    def _launch_rows(self):
+        """Per-row constants (threshold window, prefactors, sigma_abs lookup) -> row table, on the device."""
+        d_eg, d_ph, n_rows, ns, d_ids, d_u, seed = self._inputs
+        par = P.compton_params(self.ma, self.ge, self.target_z, ns)
+        rt = self._rt
+        with rt.activate():
+            if n_rows:
+                le, lx, nt = self.target_photon_xs.device_table(rt)
+                N.call("alpk_compton_rows", N.ptr(d_eg), N.ptr(d_ph), n_rows, N.ptr(le), N.ptr(lx), nt,
+                       C.byref(par), N.ptr(self._table), rt.stream())
+        self._rows = (self._table, n_rows, ns, d_ids, par, d_u, seed)
+
+    def simulate(self, uniforms=None):
+        """uniforms: optional U[0,1) array, n_samples per row passing the threshold, row-major (parity mode)."""
+        self._reset_samples()
+        self._stage_inputs(uniforms)
+        self._launch_rows()
+        self._finish_simulate()
+
+
+_DEVICE_KW = ("seed", "device", "fused", "keep_f64")
+
+
+def _split_kwargs(kwargs):
+    """The reference's e+- flux classes swallow arbitrary **kwargs; keep only the device options."""
+    return {k: kwargs[k] for k in _DEVICE_KW if k in kwargs}
+
+
+def track_length_prob(Ei, Ef, t):
+    """Track-length pdf (fluxes.py:257-259); host helper for scripts, the kernels carry their own copy."""
+    from scipy.special import gamma
+    b = 4/3
+    return np.heaviside(Ei-Ef, 1.0) * abs(power(np.log(Ei/Ef), b*t - 1) / (Ei * gamma(b*t)))
+
+
+class FluxBremIsotropic(_ChainFlux):
+    """
+    ALP bremsstrahlung flux from an electron (+ positron) shower flux (reference: fluxes.py:271-375).  With
+    `simulate(use_track_length=True)` every electron row draws one track-length-attenuated energy E1 in
+    (max(ma, me), E0) (weight: (E0-ep_min) (Phi_e+Phi_p)(E0) x the integrated track-length probability), then
+    `n_samples` log-uniform E_a draws weighted by the Tsai (pseudoscalar) or IWW (vector) spectrum.
+    """
+    _SAMPLES_FN = "alpk_brem_samples"
+
+    def __init__(self, electron_flux=[[1., 0.]], positron_flux=[1., 0.], target=None,
+                 target_length=10.0, det_dist=4., det_length=0.2, det_area=0.04,
+                 axion_mass=0.1, axion_coupling=1e-3, n_samples=100,
+                 is_isotropic=True, loop_decay=False, boson_type="pseudoscalar",
+                 max_track_length=5.0, is_monoenergetic=False, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, **_split_kwargs(kwargs))
+        self.electron_flux = electron_flux
+        self.positron_flux = positron_flux
+        self.boson_type = boson_type
+        self.ge = axion_coupling
+        self.target_density = target.density  # g/cm3
+        self.target_radius = target_length  # cm
+        self.ntargets_by_area = target_length * target.density * AVOGADRO / (2*target.z[0])  # N_T / cm^2
+        self.ntarget_area_density = target.rad_length * AVOGADRO / (2*target.z[0])
+        self._rad_length = target.rad_length
+        self.n_samples = n_samples
+        self.is_isotropic = is_isotropic
+        self.loop_decay = loop_decay
+        self.max_t = max_track_length
+        self.is_monoenergetic = is_monoenergetic
+        self.row_offset = 0
+
+    def electron_flux_dN_dE(self, energy):
+        ef = np.asarray(self.electron_flux, dtype=np.float64)
+        return np.interp(energy, ef[:, 0], ef[:, 1], left=0.0, right=0.0)
+
+    def positron_flux_dN_dE(self, energy):
+        pf = np.asarray(self.positron_flux, dtype=np.float64)
+        return np.interp(energy, pf[:, 0], pf[:, 1], left=0.0, right=0.0)
+
+    def simulate(self, use_track_length=True, uniforms=None):
+        """uniforms (parity mode): flat U[0,1) array in the reference's draw order -- per electron row with
+        E0 >= max(ma, me) one scalar, followed by `n_samples` variates iff that row emits (fluxes.py:348-352,322-326);
+        without track length: `n_samples` per emitting row."""
+        self._reset_samples()
+        ef = _as_flux_table(self.electron_flux, "electron_flux")
+        ns = int(self.n_samples)
+        par = P.brem_params(self.ma, self.ge, self.target_z, self._rad_length, ns, self.boson_type, self.max_t,
+                            use_track_length)
+        if use_track_length:
+            ep_min = max(self.ma, M_E)                                           # fluxes.py:346
+            keep = ~(ef[:, 0] < ep_min)
+            if self.is_monoenergetic:
+                if ef.shape[0] != 1:
+                    # the reference multiplies an (n_rows,) weight array into (n_samples,) samples (fluxes.py:310-314,337)
+                    raise ValueError("operands could not be broadcast together: is_monoenergetic needs a single-row electron_flux")
+                ele = ef[:, :2].copy()
+                pos = np.array([[ef[0, 0], 0.0]])
+            else:
+                ele = ef[:, :2]
+                pos = np.asarray(self.positron_flux, dtype=np.float64)
+                if pos.ndim != 2:
+                    # reference: positron_flux[:,0] on the default 1-D [1., 0.] (fluxes.py:306-307)
+                    raise TypeError("list indices must be integers or slices, not tuple: positron_flux must have shape (n, 2)")
+        else:
+            keep = np.ones(ef.shape[0], dtype=bool)
+            ele = pos = np.zeros((1, 2))
+        rows = np.nonzero(keep)[0]
+        e0, w0 = ef[keep, 0], ef[keep, 1]
+        n_rows = int(rows.shape[0])
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        self._seed_used = seed
+
+        u_rows = u_samp = None
+        if uniforms is not None:
+            u_rows, u_samp = self._split_uniforms(np.asarray(uniforms, dtype=np.float64).ravel(), e0, ns, use_track_length)
+
+        rt = self._rt
+        gx, gw = P.gauss_legendre()
+        with rt.activate():
+            table = rt.empty(n_rows * N.BREM_NP)
+            emit = torch.zeros(n_rows, dtype=torch.uint8, device=rt.device)
+            ids = (rows + int(self.row_offset)).astype(np.uint32)
+            d_ids = rt.upload(ids, np.uint32)
+            if n_rows:
+                d = [rt.upload(a) for a in (e0, w0, ele[:, 0], ele[:, 1], pos[:, 0], pos[:, 1], gx, gw)]
+                d_ur = rt.upload(u_rows) if u_rows is not None else None
+                N.call("alpk_brem_rows", N.ptr(d[0]), N.ptr(d[1]), n_rows, N.ptr(d_ids), N.ptr(d_ur), C.c_uint64(seed),
+                       N.ptr(d[2]), N.ptr(d[3]), int(ele.shape[0]), N.ptr(d[4]), N.ptr(d[5]), int(pos.shape[0]),
+                       N.ptr(d[6]), N.ptr(d[7]), C.byref(par), N.ptr(table), N.ptr(emit), rt.stream())
+            # rows whose drawn energy cannot radiate (ea_max <= ma) emit nothing (fluxes.py:322-324): compact the table
+            sel = torch.nonzero(emit, as_tuple=False).ravel()
+            n_emit = int(sel.shape[0])                                           # (device -> host: one small sync)
+            ctable = table.view(n_rows, N.BREM_NP).index_select(0, sel).contiguous().view(-1) if n_rows else table
+            cids = d_ids.index_select(0, sel).contiguous() if n_rows else d_ids
+            d_u = rt.upload(u_samp) if u_samp is not None else None
+        if u_samp is not None and u_samp.shape[0] != n_emit * ns:
+            raise ValueError("injected uniforms do not match the rows that emit")
+        self._row_table_all = table
+        self._emit = emit
+        self._rows = (ctable, n_emit, ns, cids, par, d_u, seed)
+        self._finish_simulate()
+
+    def _split_uniforms(self, u, e0, ns, use_track_length):
+        """Split the reference-ordered flat stream into the per-row scalars and the per-sample block."""
+        if not use_track_length:
+            return None, np.ascontiguousarray(u)
+        ep_min = max(self.ma, M_E)
+        u_rows = np.zeros(e0.shape[0])
+        samp = []
+        pos = 0
+        for k in range(e0.shape[0]):
+            if pos >= u.shape[0]:
+                raise ValueError("uniforms exhausted")
+            u_rows[k] = u[pos]; pos += 1
+            e1 = ep_min + (e0[k] - ep_min) * u_rows[k]                           # fluxes.py:350, same IEEE ops as the kernel
+            ea_max = e1 * (1 - (self.ma / e1) * (self.ma / e1))
+            if ea_max > self.ma:
+                samp.append(u[pos:pos + ns]); pos += ns
+        if pos != u.shape[0]:
+            raise ValueError(f"uniforms hold {u.shape[0]} variates, the reference draw order consumes {pos}")
+        return u_rows, (np.ascontiguousarray(np.concatenate(samp)) if samp else np.zeros(0))
+
+
+class FluxResonanceIsotropic(AxionFlux):
+    """
+    Resonant e+ e- -> a production from a positron flux (reference: fluxes.py:380-464): a single ALP sample at
+    E_a = ma^2/(2 me) whose weight is an `n_samples` Monte-Carlo integral over (E+, t) of flux x track-length pdf.
+    """
+    def __init__(self, positron_flux=[[1., 0.]], target=None, target_length=10.0,
+                 det_dist=4., det_length=0.2, det_area=0.04, axion_mass=0.1, axion_coupling=1e-3,
+                 n_samples=100, is_isotropic=True, loop_decay=False, boson_type="pseudoscalar",
+                 max_track_length=5.0, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, n_samples, **_split_kwargs(kwargs))
+        self.positron_flux = positron_flux
+        pf = np.asarray(positron_flux, dtype=np.float64)
+        self.positron_flux_bin_widths = pf[1:, 0] - pf[:-1, 0]
+        self.ge = axion_coupling
+        self.target_radius = target_length  # cm
+        self.ntarget_area_density = target.rad_length * AVOGADRO / (target.z[0] + target.n[0])  # fluxes.py:397
+        self.is_isotropic = is_isotropic
+        self.loop_decay = loop_decay
+        self.boson_type = boson_type
+        self.max_t = max_track_length
+
+    decay_width = _width_e
+
+    def positron_flux_dN_dE(self, energy):
+        pf = np.asarray(self.positron_flux, dtype=np.float64)
+        return np.interp(energy, pf[:, 0], pf[:, 1], left=0.0, right=0.0)
+
+    def resonance_peak(self):
+        if self.boson_type == "pseudoscalar":
+            return 2*pi*M_E*power(self.ge / self.ma, 2) / sqrt(1 - power(2*M_E/self.ma, 2))
+        elif self.boson_type == "vector":
+            return 12*pi*self.ge**2 * ALPHA / M_E / 6
+
+    def simulate(self, uniforms=None):
+        """uniforms (parity mode): [2, n_samples] -- the E+ draws then the t draws (fluxes.py:437-438)."""
+        self._reset_samples()
+        pf = _as_flux_table(self.positron_flux, "positron_flux")
+        resonant_energy = -M_E + self.ma**2 / (2 * M_E)                          # fluxes.py:427
+        emax = max(pf[:, 0])
+        if resonant_energy + M_E < self.ma or resonant_energy < M_E or resonant_energy > emax:   # :428-435
+            return
+        ns = int(self.n_samples)
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        self._seed_used = seed
+        rt = self._rt
+        with rt.activate():
+            d_u = None
+            if uniforms is not None:
+                u = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+                if u.shape[0] != 2 * ns:
+                    raise ValueError(f"uniforms must hold 2*n_samples = {2 * ns} variates")
+                d_u = rt.upload(u)
+            d_e, d_f = rt.upload(pf[:, 0]), rt.upload(pf[:, 1])
+            total = rt.empty(1)
+            N.call("alpk_resonance_sum", N.ptr(d_e), N.ptr(d_f), int(pf.shape[0]), float(resonant_energy), float(emax),
+                   float(self.max_t), ns, N.ptr(d_u), C.c_uint64(seed), N.ptr(total), N.ptr(rt.scratch), rt.stream())
+            s = float(total.item())
+        mc_vol = self.max_t*(emax - resonant_energy)                             # :439
+        attenuated_flux = mc_vol*s/self.n_samples                                # :441
+        wgt = self.target_z * (self.ntarget_area_density * HBARC**2) * self.resonance_peak() * attenuated_flux   # :442
+        self.axion_energy = [self.ma**2 / (2 * M_E)]                             # :444
+        self.axion_flux = [wgt]                                                  # :445
+
+    def propagate(self, new_coupling=None):
+        if new_coupling is not None:
+            width, rescale = self.decay_width(new_coupling, self.ma), power(new_coupling/self.ge, 2)
+        else:
+            width, rescale = self.decay_width(self.ge, self.ma), 1.0
+        self._propagate(width, rescale, self._geom_accept() if self.is_isotropic else None)
+
+
+class FluxPairAnnihilationIsotropic(_ChainFlux):
+    """
+    Associated production e+ e- -> a gamma from a positron flux on atomic electrons at rest (reference:
+    fluxes.py:469-549): per positron row above threshold, `n_samples` isotropic CM-frame draws weighted by the
+    tree-level matrix element (1% soft-photon cut), boosted to lab-frame ALP energies.
+    """
+    _SAMPLES_FN = "alpk_pairann_samples"
+
+    def __init__(self, positron_flux=[[1., 0.]], target=None,
+                 det_dist=4., det_length=0.2, det_area=0.04, axion_mass=0.1,
+                 axion_coupling=1e-3, n_samples=100, is_isotropic=True,
+                 loop_decay=False, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, n_samples, **_split_kwargs(kwargs))
+        self.positron_flux = positron_flux
+        pf = np.asarray(positron_flux, dtype=np.float64)
+        self.positron_flux_bin_widths = pf[1:, 0] - pf[:-1, 0]
+        self.ge = axion_coupling
+        self.ntarget_area_density = target.rad_length * AVOGADRO / (2*target.z[0])
+        self._rad_length = target.rad_length
+        self.is_isotropic = is_isotropic
+        self.loop_decay = loop_decay
+        self.row_offset = 0
+
+    def p1_cm(self, s):
+        return np.sqrt((np.power(s - 2*M_E**2, 2) - np.power(2*M_E**2, 2))/(4*s))
+
+    def p3_cm(self, s):
+        return np.sqrt((np.power(s - self.ma**2, 2))/(4*s))
+
+    def simulate(self, uniforms=None):
+        """uniforms (parity mode): [n_rows, 2, n_samples] for the rows above threshold -- per row the phi draws then
+        the theta draws (cross_section_mc.py:204-205)."""
+        self._reset_samples()
+        pf = _as_flux_table(self.positron_flux, "positron_flux")
+        keep = ~(pf[:, 0] < max((self.ma**2 - M_E**2)/(2*M_E), M_E))            # fluxes.py:507
+        rows = np.nonzero(keep)[0]
+        n_rows, ns = int(rows.shape[0]), int(self.n_samples)
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        self._seed_used = seed
+        par = P.pairann_params(self.ma, self.ge, self.target_z, self._rad_length, ns)
+        rt = self._rt
+        with rt.activate():
+            d_u = None
+            if uniforms is not None:
+                u = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+                if u.shape[0] != 2 * n_rows * ns:
+                    raise ValueError(f"uniforms must hold 2*n_rows*n_samples = {2 * n_rows * ns} variates")
+                d_u = rt.upload(u)
+            table = rt.empty(n_rows * N.PAIRANN_NP)
+            d_ids = rt.upload((rows + int(self.row_offset)).astype(np.uint32), np.uint32)
+            if n_rows:
+                d_e, d_w = rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1])
+                N.call("alpk_pairann_rows", N.ptr(d_e), N.ptr(d_w), n_rows, C.byref(par), N.ptr(table), rt.stream())
+        self._rows = (table, n_rows, ns, d_ids, par, d_u, seed)
+        self._finish_simulate()

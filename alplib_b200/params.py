@@ -6,7 +6,7 @@ bit-identical to the value the reference would use; the kernels then only do the
 import numpy as np
 
 from . import _native as N
-from .constants import ALPHA, C_LIGHT, M_E, METER_BY_MEV, S_PER_DAY, pi
+from .constants import ALPHA, AVOGADRO, C_LIGHT, HBARC, M_E, METER_BY_MEV, S_PER_DAY, pi
 
 R0_SCREEN = 2.2e-10 / METER_BY_MEV      # prod_xs.py:99 / det_xs.py:37 default screening parameter
 
@@ -86,3 +86,55 @@ def icompton_consts(ma, g, z):
 def iprimakoff_consts(ma, g, z, r0=R0_SCREEN):
     pref, r02 = primakoff_consts(g, z, r0)
     return (N.C.c_double * 6)(float(ma), float(ma ** 2), pref, r02, 0.0, 0.0)
+
+
+def gauss_legendre():
+    """Nodes/weights of the 32-point Gauss-Legendre rule used for the track-length integral (fmath.py:33-36)."""
+    x, w = np.polynomial.legendre.leggauss(N.GL_POINTS)
+    return np.ascontiguousarray(x), np.ascontiguousarray(w)
+
+
+def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_t=5.0, use_track_length=True):
+    """fluxes.py:276-337 + prod_xs.py:209-221, 313-323 scalars (z is the np.int64 of Material.z[0])."""
+    from numpy import log, power
+    b = N.BremT()
+    b.ma = float(ma)
+    b.ma2 = float(ma ** 2)
+    b.log10_ma = float(np.log10(ma))
+    b.ep_min = float(max(ma, M_E))                                   # fluxes.py:346
+    ntad = rad_length * AVOGADRO / (2 * z)                            # fluxes.py:290
+    b.nt = float(ntad * HBARC ** 2)                                   # :330
+    r0 = ALPHA / M_E
+    b.pref_num = float(2 * r0 ** 2 * g ** 2 / 4 / pi)                 # prod_xs.py:217 (before / Ee)
+    ln_el = log(184 * power(z, -1 / 3))
+    ln_inel = log(1194 * power(z, -2 / 3))
+    b.zl = float(z ** 2 * ln_el + z * ln_inel)
+    b.zz = float(z ** 2 + z)
+    chi = z ** 2 * ln_el + z * ln_inel
+    b.pref_vec = float(chi * (4 * ALPHA ** 2 * g ** 2) / (4 * pi))    # prod_xs.py:322
+    b.ln10 = float(np.log(10))
+    b.n_samples = float(n_samples)
+    b.t_arg = float(4 * max_t / 3)                                    # fluxes.py:266
+    if boson_type not in ("pseudoscalar", "vector"):
+        # the reference leaves diff_br unbound for any other string (fluxes.py:328-337)
+        raise UnboundLocalError("cannot access local variable 'diff_br' where it is not associated with a value")
+    b.vector = 1 if boson_type == "vector" else 0
+    b.use_track_length = 1 if use_track_length else 0
+    return b
+
+
+def pairann_params(ma, ge, z, rad_length, n_samples):
+    """fluxes.py:484,518 + matrix_element.py:717-734 scalars."""
+    p = N.PairAnnT()
+    p.ma = float(ma)
+    p.ma2 = float(ma ** 2)
+    p.me2 = float(M_E ** 2)
+    p.me4 = float(M_E ** 4)
+    p.pref = float((pi * ALPHA) * 1.0 ** 2)
+    p.wconst = 0.0
+    p.z = float(z)
+    p.ge2 = float(ge ** 2)
+    p.ntad = float(rad_length * AVOGADRO / (2 * z))
+    p.hbarc2 = float(HBARC ** 2)
+    p.n_samples = float(n_samples)
+    return p

@@ -32,8 +32,9 @@ extern "C" {
 /* number of doubles per row of the per-row parameter tables */
 #define ALPK_COMPTON_NP 10
 #define ALPK_PARENT_NP 6
-#define ALPK_BREM_NP 10
-#define ALPK_PAIRANN_NP 12
+#define ALPK_BREM_NP 6
+#define ALPK_PAIRANN_NP 11
+#define ALPK_GL_POINTS 32
 
 int alpk_version(void);
 const char* alpk_last_error(void);
@@ -129,6 +130,72 @@ int alpk_decay_parent_rows(const double* energy, const float* decay_w32, uint64_
                            const alpk_event_t* h_ev, uint32_t n_samples, double* row_table, void* stream);
 int alpk_decay2body(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
                     const double* uniforms, uint64_t seed, double* p1, double* p2, double* w, void* stream);
+
+/* ---- bremsstrahlung with track-length attenuation: fluxes.py:257-356, prod_xs.py:209-221, 313-323 ------------------------ */
+typedef struct {
+    double ma, ma2;
+    double log10_ma;         /* np.log10(ma) */
+    double ep_min;           /* max(ma, M_E)                                        fluxes.py:346 */
+    double nt;               /* ntarget_area_density * HBARC**2                     fluxes.py:290,330 */
+    double pref_num;         /* 2*r0**2*g**2/4/pi, r0 = ALPHA/M_E                   prod_xs.py:212,217 */
+    double zl;               /* z**2*ln_el + z*ln_inel                              prod_xs.py:215-219 */
+    double zz;               /* z**2 + z */
+    double pref_vec;         /* chi*(4*ALPHA**2*g**2)/(4*pi)                        prod_xs.py:317-322 */
+    double ln10;             /* np.log(10) */
+    double n_samples;
+    double t_arg;            /* 4*max_track_length/3                                fluxes.py:266 */
+    int vector;              /* boson_type == "vector" */
+    int use_track_length;    /* simulate(use_track_length=...) */
+} alpk_brem_t;
+
+/* Row prelude: one thread per electron row (rows already filtered by the host: E0 >= ep_min in track-length mode).
+ * u_rows (parity mode) / Philox (seed, row_ids): the per-row scalar draw of fluxes.py:350.  The e-/e+ dN/dE tables
+ * (np.interp, left=right=0) and the 32-point Gauss-Legendre rule gl_x/gl_w[ALPK_GL_POINTS] for the track-length
+ * integral (fmath.py:33-36) are device arrays.  Writes row_table[n_rows][ALPK_BREM_NP] and emit[n_rows]
+ * (1 = ea_max > ma, the row produces n_samples samples; fluxes.py:322-324). */
+int alpk_brem_rows(const double* e0, const double* w0, uint64_t n_rows, const uint32_t* row_ids,
+                   const double* u_rows, uint64_t seed,
+                   const double* ele_e, const double* ele_f, int n_ele, const double* pos_e, const double* pos_f, int n_pos,
+                   const double* gl_x, const double* gl_w, const alpk_brem_t* h_par,
+                   double* row_table, uint8_t* emit, void* stream);
+
+/* Per-sample kernel over the EMITTING rows (row table compacted by the caller); same fused tail as
+ * alpk_compton_samples.  uniforms (parity mode): [n_rows][n_samples]. */
+int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
+                      const alpk_brem_t* h_par, const double* uniforms, uint64_t seed,
+                      double* out_energy, double* out_flux,
+                      const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
+                      double* decay_w64, double* scatter_w64,
+                      const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream);
+
+/* ---- resonant production: fluxes.py:421-445.  *out_sum = sum_i Phi_p(E_i) * track_length_prob(E_i, E_res, t_i) over
+ * n_samples draws (E_i, t_i) ~ U(E_res, E_max) x U(0, max_t); the caller applies the scalar prefactors (:441-442).
+ * uniforms (parity mode): [2][n_samples] -- the E draws then the t draws (:437-438). */
+int alpk_resonance_sum(const double* pos_e, const double* pos_f, int n_pos, double e_res, double e_max, double max_t,
+                       uint64_t n_samples, const double* uniforms, uint64_t seed, double* out_sum, double* scratch,
+                       void* stream);
+
+/* ---- associated production e+ e- -> a gamma: fluxes.py:503-518, cross_section_mc.py:192-240, matrix_element.py:717-734 -- */
+typedef struct {
+    double ma, ma2;
+    double me2, me4;         /* M_E**2, M_E**4 */
+    double pref;             /* (pi*ALPHA)*coupling_product**2, coupling_product = 1 */
+    double wconst;           /* reserved */
+    double z, ge2, ntad, hbarc2;   /* applied left to right after the positron weight, fluxes.py:518 */
+    double n_samples;
+} alpk_pairann_t;
+
+/* rows already filtered by the host (E+ >= max((ma^2-me^2)/(2 me), me), fluxes.py:507) */
+int alpk_pairann_rows(const double* e_pos, const double* w_pos, uint64_t n_rows, const alpk_pairann_t* h_par,
+                      double* row_table, void* stream);
+/* uniforms (parity mode): [n_rows][2][n_samples] -- phi draws then theta draws per row (cross_section_mc.py:204-205);
+ * only the theta draws enter the lab energy and weight of a beam along z. */
+int alpk_pairann_samples(const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
+                         const alpk_pairann_t* h_par, const double* uniforms, uint64_t seed,
+                         double* out_energy, double* out_flux,
+                         const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
+                         double* decay_w64, double* scatter_w64,
+                         const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream);
 
 /* ---- weighted histogram: np.histogram(x, bins=edges, weights=w) (half-open bins, last bin closed) ------------------ */
 int alpk_hist(const double* x, const double* w64_or_null, const float* w32_or_null, uint64_t n,

@@ -569,5 +569,16 @@ def decay_4vectors(axion_energy, decay_axion_weight, ma, days_exposure, n_sample
 # np.histogram(E, bins=edges, weights=w) semantics used for the binned spectra
 # ---------------------------------------------------------------------------------------------------------
 def histogram(x, w, edges):
-    return np.histogram(np.asarray(x, dtype=np.float64), bins=np.asarray(edges, dtype=np.float64),
-                        weights=np.asarray(w, dtype=np.float64))[0]
+    """np.histogram(x, bins=edges, weights=w)[0] semantics -- bin k = [edges[k], edges[k+1]), last bin closed, values
+    outside the edges and NaN dropped -- evaluated as a direct per-bin sum (np.bincount).  np.histogram itself forms
+    the bins as differences of a cumulative sum over the sorted weights, which cancels catastrophically when weights
+    span many decades (decay weights do: 1e-6 .. 1e-22); tests/test_oracle_golden.py checks both agree on
+    well-conditioned input."""
+    x = np.asarray(x, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    edges = np.asarray(edges, dtype=np.float64)
+    nb = edges.shape[0] - 1
+    idx = np.searchsorted(edges, x, side="right") - 1
+    idx[x == edges[-1]] = nb - 1
+    ok = (x >= edges[0]) & (x <= edges[-1])
+    return np.bincount(idx[ok], weights=w[ok], minlength=nb)[:nb]

@@ -192,7 +192,8 @@ def test_compton_rates_statistical(A):
     oh = O.histogram(oE, p["decay_w"], edges)
     err = np.sqrt(O.histogram(oE, p["decay_w"].astype(np.float64) ** 2, edges))
     sel = oh > 0
-    assert np.all(np.abs(h[sel] - oh[sel]) < 6 * np.sqrt(2) * err[sel] + 1e-300)
+    assert sel.sum() >= 10
+    assert np.all(np.abs(h[sel] - oh[sel]) < 6 * np.sqrt(2) * err[sel])
 
 
 def test_propagate_misc(A):
@@ -286,3 +287,133 @@ def test_histogram(A):
         h32 = histogram(dx, dw.float(), edges).cpu().numpy()
         assert max_rel(h32, O.histogram(x, w.astype(np.float32).astype(np.float64), edges), floor=1e-9) < 1e-10
     assert float(total(dw).item()) == pytest.approx(np.sum(w), rel=1e-13)
+
+
+# ---- e+- channels (BASELINE config 4) -----------------------------------------------------------------------------------
+GEOM_DUNE = dict(det_dist=574.0, det_length=5.0, det_area=21.0)
+GA_DUNE = O.geom_acceptance(21.0, 574.0)
+
+
+@pytest.mark.parametrize("name", ["katb_brem", "brem_ps", "brem_vec", "brem_notl"])
+def test_brem_injected(A, name):
+    g = load_golden(name)
+    ma, gg, ns = float(g["ma"]), float(g["g"]), int(g["n_samples"])
+    boson = str(g["boson_type"]) if "boson_type" in g else "pseudoscalar"
+    tl = bool(g["use_track_length"]) if "use_track_length" in g else True
+    fl = A.FluxBremIsotropic(g["electron_flux"], g["positron_flux"], A.Material("C"), target_length=100, axion_mass=ma,
+                             axion_coupling=gg, n_samples=ns, boson_type=boson, keep_f64=True, **GEOM_DUNE)
+    fl.simulate(use_track_length=tl, uniforms=g["uniforms"])
+    assert fl._emit.cpu().numpy().astype(bool).tolist() == g["row_emit"].astype(bool).tolist()
+    assert max_rel(fl.axion_energy, g["axion_energy"]) < 1e-12
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < TOL
+    fl.propagate()
+    assert max_rel(fl.scatter_axion_weight_f64 * GA_DUNE, g["scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64 * GA_DUNE, g["decay_w64"], g["scatter_w64"], TOL)
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    assert_decay_close(fl.decay_axion_weight, g["decay_w32"], g["scatter_w32"], TOL, extra_rel=F32)
+
+
+def _brem_tables(n):
+    e = np.linspace(20.0, 1.2e5, n)
+    return np.stack([e, 1e14 * np.exp(-e / 2e4)], axis=1), np.stack([e, 0.3e14 * np.exp(-e / 2e4)], axis=1)
+
+
+def test_brem_free_running_matches_oracle(A):
+    ef, pfx = _brem_tables(53)
+    ef[0, 0] = 5.0                                        # below ep_min = ma: filtered by the host
+    ma, gg, ns, seed = 10.0, 1e-6, 301, 4242
+    fl = A.FluxBremIsotropic(ef, pfx, A.Material("C"), target_length=100, axion_mass=ma, axion_coupling=gg, n_samples=ns,
+                             seed=seed, **GEOM_DUNE)
+    fl.simulate()
+    # replay the kernel's Philox variates in the reference's draw order
+    stream = []
+    for r in range(ef.shape[0]):
+        if ef[r, 0] < max(ma, O.M_E):
+            continue
+        u = PX.uniform_1(seed, PX.TAG_BREM_ROW, r, 1)[0]
+        e1 = max(ma, O.M_E) + (ef[r, 0] - max(ma, O.M_E)) * u
+        stream.append([u])
+        if e1 * (1 - np.power(ma / e1, 2)) > ma:
+            stream.append(PX.uniform_1(seed, PX.TAG_BREM_EA, r, ns))
+    oE, oF, info = O.brem_simulate(ef, pfx, ma, gg, O.Material("C"), ns, O.UniformSource(np.concatenate(stream)))
+    assert len(fl.axion_energy) == oE.shape[0] > 0
+    assert max_rel(fl.axion_energy, oE) < 1e-12
+    assert max_rel(fl.axion_flux, oF) < TOL
+    fl.propagate()
+    p = O.propagate(oE, oF, ma, O.W_ee(gg, ma), 1.0, 574.0, 5.0, geom_accept=GA_DUNE)
+    assert max_rel(fl.scatter_axion_weight, p["scatter_w"]) <= F32
+    r_gpu = A.ElectronEventGenerator(fl, A.Material("Ar")).decays(365, 30.0)
+    _, r_cpu = O.decays(oE, p["decay_w"], 365, 30.0)
+    assert r_gpu == pytest.approx(r_cpu, rel=1e-5)
+    # NA64-style single-row monoenergetic beam (examples/ex4_na64.py shape)
+    beam = np.array([[1e5, 2.84e11 / 86400 / 365]])
+    mono = A.FluxBremIsotropic(beam, target=A.Material("W"), det_dist=43.3, det_length=1.0, det_area=0.23,
+                               target_length=2.0, axion_mass=10.0, axion_coupling=1e-5, n_samples=1000,
+                               is_isotropic=False, is_monoenergetic=True, seed=3)
+    mono.simulate(); mono.propagate()
+    assert len(mono.axion_energy) == 1000 and np.all(np.isfinite(mono.axion_flux)) and np.sum(mono.axion_flux) > 0
+    with pytest.raises(TypeError):
+        A.FluxBremIsotropic(beam, target=A.Material("W"), axion_mass=10.0).simulate()     # default 1-D positron_flux
+
+
+def test_resonance(A):
+    g = load_golden("katr_resonance")
+    fl = A.FluxResonanceIsotropic(g["positron_flux"], A.Material("C"), axion_mass=10.0, axion_coupling=1e-6,
+                                  n_samples=1000, keep_f64=True, **GEOM_DUNE)
+    fl.simulate(uniforms=g["uniforms"].reshape(2, 1000))
+    assert list(fl.axion_energy) == [97.84735812133073]
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < TOL
+    fl.propagate()
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    assert_decay_close(fl.decay_axion_weight, g["decay_w32"], g["scatter_w32"], TOL, extra_rel=F32)
+    # free-running: replay Philox through the oracle
+    seed, ns = 99, 20001
+    fr = A.FluxResonanceIsotropic(g["positron_flux"], A.Material("C"), axion_mass=10.0, axion_coupling=1e-6,
+                                  n_samples=ns, seed=seed, **GEOM_DUNE)
+    fr.simulate()
+    u1, u2 = PX.uniform_2(seed, PX.TAG_RESONANCE, 0, ns)
+    oE, oF = O.resonance_simulate(g["positron_flux"], 10.0, 1e-6, O.Material("C"), ns, O.UniformSource(np.concatenate([u1, u2])))
+    assert max_rel(fr.axion_flux, oF) < TOL
+    # guards: below 2 m_e / above the flux table -> no sample (fluxes.py:428-435)
+    for ma in (0.9, 200.0):
+        e = A.FluxResonanceIsotropic(g["positron_flux"], A.Material("C"), axion_mass=ma, axion_coupling=1e-6, **GEOM_DUNE)
+        e.simulate(); e.propagate()
+        assert len(e.axion_energy) == 0 and len(e.decay_axion_weight) == 0
+
+
+@pytest.mark.parametrize("name", ["kata_pairann", "pairann_mid"])
+def test_pairann_injected(A, name):
+    g = load_golden(name)
+    ns = int(g["n_samples"])
+    fl = A.FluxPairAnnihilationIsotropic(g["positron_flux"], A.Material("C"), axion_mass=10.0, axion_coupling=1e-6,
+                                         n_samples=ns, keep_f64=True, **GEOM_DUNE)
+    fl.simulate(uniforms=g["uniforms"])
+    assert max_rel(fl.axion_energy, g["axion_energy"]) < TOL
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < TOL
+    fl.propagate()
+    assert max_rel(fl.scatter_axion_weight_f64 * GA_DUNE, g["scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64 * GA_DUNE, g["decay_w64"], g["scatter_w64"], TOL)
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+
+
+def test_pairann_free_running_matches_oracle(A):
+    _, pfx = _brem_tables(41)
+    ma, gg, ns, seed = 10.0, 1e-6, 257, 777
+    fl = A.FluxPairAnnihilationIsotropic(pfx, A.Material("C"), axion_mass=ma, axion_coupling=gg, n_samples=ns, seed=seed,
+                                         **GEOM_DUNE)
+    fl.simulate()
+    keep = O.pairann_row_valid(pfx, ma)
+    assert 0 < keep.sum() < pfx.shape[0]
+    stream = []
+    for r in np.nonzero(keep)[0]:
+        stream += [np.zeros(ns), PX.uniform_1(seed, PX.TAG_PAIRANN, int(r), ns)]     # phi draws do not enter E_lab
+    oE, oF = O.pairann_simulate(pfx, ma, gg, O.Material("C"), ns, O.UniformSource(np.concatenate(stream)))
+    assert max_rel(fl.axion_energy, oE) < TOL
+    assert max_rel(fl.axion_flux, oF) < TOL
+    # fused one-kernel chain == separate launches
+    fl.propagate()
+    r_sep = A.ElectronEventGenerator(fl, A.Material("Ar")).decays(365, 30.0)
+    fb = A.FluxPairAnnihilationIsotropic(pfx, A.Material("C"), axion_mass=ma, axion_coupling=gg, n_samples=ns, seed=seed,
+                                         fused=True, **GEOM_DUNE)
+    fb.simulate(); fb.propagate()
+    assert A.ElectronEventGenerator(fb, A.Material("Ar")).decays(365, 30.0) == pytest.approx(r_sep, rel=1e-12)

@@ -175,3 +175,92 @@ def test_decay2body(hostcheck, name):
     assert np.array_equal(w, g["w"])
     # the host build follows the reference's op order; what is left is glibc-scalar vs NumPy-SIMD sin/cos/acos
     assert np.max(np.abs(p1 - g["p1"].T) / scale) < 1e-14 and np.max(np.abs(p2 - g["p2"].T) / scale) < 1e-14
+
+
+# ---- e+- channels ---------------------------------------------------------------------------------------------------
+def test_nu_integral_gauss_legendre(hostcheck):
+    hostcheck.hc_nu_integral.restype = C.c_double
+    gx, gw = P.gauss_legendre()
+    for x in (1e-8, 1e-6, 1e-3, 0.1, 0.9162907318741551, 2.0, 9.0, 13.0):
+        got = hostcheck.hc_nu_integral(C.c_double(x), C.c_double(20 / 3), dptr(gx), dptr(gw))
+        assert got == pytest.approx(O.nu_integral(x, -1, 20 / 3), rel=1e-13), x
+    assert hostcheck.hc_nu_integral(C.c_double(np.log(2.5)), C.c_double(20 / 3), dptr(gx), dptr(gw)) == \
+        pytest.approx(2.5972770215450707, rel=1e-13)                       # SURVEY section 8c KAT
+    assert hostcheck.hc_nu_integral(C.c_double(0.7), C.c_double(0.8), dptr(gx), dptr(gw)) == \
+        pytest.approx(O.nu_integral(0.7, -1, 0.8), rel=1e-13)              # single panel (T <= 1)
+
+
+@pytest.mark.parametrize("name", ["katb_brem", "brem_ps", "brem_vec", "brem_notl"])
+def test_brem(hostcheck, name):
+    g = load_golden(name)
+    ma, gg, ns = float(g["ma"]), float(g["g"]), int(g["n_samples"])
+    boson = str(g["boson_type"]) if "boson_type" in g else "pseudoscalar"
+    tl = bool(g["use_track_length"]) if "use_track_length" in g else True
+    C_ = O.Material("C")
+    ef, pfx = g["electron_flux"], g["positron_flux"]
+    par = P.brem_params(ma, gg, C_.z[0], C_.rad_length, ns, boson, 5.0, tl)
+    rows = g["rows"]
+    e0 = np.ascontiguousarray(ef[rows, 0]); w0 = np.ascontiguousarray(ef[rows, 1])
+    u_rows = np.ascontiguousarray(np.nan_to_num(g["row_u"]))
+    emit_ref = g["row_emit"].astype(bool)
+    # the flat uniform log interleaves [row scalar][n_samples if emitted] per row: split it
+    u = g["uniforms"]; pos = 0; samp = []
+    for k in range(rows.shape[0]):
+        if tl:
+            assert u[pos] == g["row_u"][k]; pos += 1
+        if emit_ref[k]:
+            samp.append(u[pos:pos + ns]); pos += ns
+    assert pos == u.shape[0]
+    u_samp = np.ascontiguousarray(np.concatenate(samp)) if samp else np.zeros(0)
+    n = int(emit_ref.sum()) * ns
+    gx, gw = P.gauss_legendre()
+    table = np.empty(rows.shape[0] * N.BREM_NP); emit = np.zeros(rows.shape[0], np.uint8)
+    oe, of = np.empty(n), np.empty(n)
+    ee, efl = np.ascontiguousarray(ef[:, 0]), np.ascontiguousarray(ef[:, 1])
+    pe, pfl = np.ascontiguousarray(pfx[:, 0]), np.ascontiguousarray(pfx[:, 1])
+    hostcheck.hc_brem(dptr(e0), dptr(w0), C.c_uint64(rows.shape[0]), dptr(u_rows), dptr(ee), dptr(efl), ee.shape[0],
+                      dptr(pe), dptr(pfl), pe.shape[0], dptr(gx), dptr(gw), C.byref(par), C.c_uint32(ns), dptr(u_samp),
+                      dptr(table), dptr(emit), dptr(oe), dptr(of))
+    assert np.array_equal(emit.astype(bool), emit_ref)
+    t = table.reshape(-1, N.BREM_NP)
+    assert max_rel(t[:, 0], g["row_E1"]) == 0.0                       # E1 = ep_min + (E0-ep_min)*u bit exact
+    assert max_rel(t[:, 1], g["row_W"]) < 1e-12                       # Gauss-Legendre vs QUADPACK
+    assert max_rel(oe, g["axion_energy"]) < 1e-13
+    assert max_rel(of, g["axion_flux"]) < TOL
+
+
+def test_resonance(hostcheck):
+    g = load_golden("katr_resonance")
+    hostcheck.hc_resonance_sum.restype = C.c_double
+    pf = g["positron_flux"]
+    pe, pfl = np.ascontiguousarray(pf[:, 0]), np.ascontiguousarray(pf[:, 1])
+    ma, ge, ns = 10.0, 1e-6, 1000
+    eres = -O.M_E + ma ** 2 / (2 * O.M_E)
+    emax = max(pf[:, 0])
+    u = np.ascontiguousarray(g["uniforms"])
+    s = hostcheck.hc_resonance_sum(dptr(pe), dptr(pfl), pe.shape[0], C.c_double(eres), C.c_double(emax), C.c_double(5.0),
+                                   C.c_uint64(ns), dptr(u))
+    C_ = O.Material("C")
+    ntad = C_.rad_length * O.AVOGADRO / (C_.z[0] + C_.n[0])
+    att = (5.0 * (emax - eres)) * s / ns
+    wgt = C_.z[0] * (ntad * O.HBARC ** 2) * O.resonance_peak(ge, ma) * att
+    assert wgt == pytest.approx(float(g["axion_flux"][0]), rel=1e-12)
+    assert wgt == pytest.approx(185.58954304351653, rel=1e-12)
+
+
+@pytest.mark.parametrize("name", ["kata_pairann", "pairann_mid"])
+def test_pairann(hostcheck, name):
+    g = load_golden(name)
+    ma, ge, ns = float(g["ma"]), float(g["g"]), int(g["n_samples"])
+    pf = g["positron_flux"]
+    keep = O.pairann_row_valid(pf, ma)
+    ep, wp = np.ascontiguousarray(pf[keep, 0]), np.ascontiguousarray(pf[keep, 1])
+    C_ = O.Material("C")
+    par = P.pairann_params(ma, ge, C_.z[0], C_.rad_length, ns)
+    n = ep.shape[0] * ns
+    u = np.ascontiguousarray(g["uniforms"])
+    assert u.shape[0] == 2 * n
+    oe, of = np.empty(n), np.empty(n)
+    hostcheck.hc_pairann(dptr(ep), dptr(wp), C.c_uint64(ep.shape[0]), C.byref(par), C.c_uint32(ns), dptr(u), dptr(oe), dptr(of))
+    assert max_rel(oe, g["axion_energy"]) < 1e-13
+    assert max_rel(of, g["axion_flux"]) < TOL

@@ -202,3 +202,8 @@ def test_histogram_semantics():
     w = np.arange(8, dtype=float) + 1
     h = O.histogram(x, w, [0.0, 1.0, 2.0])
     assert list(h) == [1 + 2, 3 + 4 + 5]          # last bin closed on the right, out-of-range and NaN dropped
+    assert list(np.histogram(x, bins=[0.0, 1.0, 2.0], weights=w)[0]) == list(h)
+    rs = np.random.RandomState(0)
+    xr, wr = rs.uniform(-1, 11, 5000), rs.uniform(0.5, 1.5, 5000)
+    for edges in (np.linspace(0, 10, 33), np.array([0.0, 0.3, 4.0, 4.5, 10.0])):
+        np.testing.assert_allclose(O.histogram(xr, wr, edges), np.histogram(xr, bins=edges, weights=wr)[0], rtol=1e-12)
