@@ -15,7 +15,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
 SCRATCH_DOUBLES = 16384
-COMPTON_NP = 10
+COMPTON_NP = 11
 PARENT_NP = 6
 BREM_NP = 6
 PAIRANN_NP = 11
@@ -30,7 +30,8 @@ class PropT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("width", C.c_double), ("rescale", C.c_double),
                 ("neg_dist_mbm", C.c_double), ("neg_len_mbm", C.c_double), ("geom", C.c_double),
                 ("geom32", C.c_float), ("apply_geom", C.c_int), ("geom_f64", C.c_int), ("use_tof", C.c_int),
-                ("tof_light", C.c_double), ("det_dist", C.c_double), ("timing_window", C.c_double)]
+                ("tof_light", C.c_double), ("det_dist", C.c_double), ("timing_window", C.c_double),
+                ("fast", C.c_int), ("k1", C.c_double), ("k2", C.c_double)]
 
 
 class EventT(C.Structure):
@@ -40,7 +41,7 @@ class EventT(C.Structure):
 
 class ComptonT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("aa", C.c_double), ("z", C.c_double),
-                ("n_samples", C.c_double)]
+                ("n_samples", C.c_double), ("fast", C.c_int)]
 
 
 class BremT(C.Structure):
@@ -108,7 +109,7 @@ _SIGNATURES = {
     "alpk_pairann_samples": ([_P, _U64, _U32, _P, C.POINTER(PairAnnT), _P, _U64, _P, _P,
                               C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_decay_parent_rows": ([_P, _P, _U64, _D, C.POINTER(EventT), _U32, _P, _P], _I),
-    "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _P, _P, _P, _P], _I),
+    "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _I, _P, _P, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),
     "alpk_fp64_peak": ([_U64, _I, _P, _P], _I),

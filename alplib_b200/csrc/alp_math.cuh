@@ -16,6 +16,7 @@
 #define ALP_HD __host__ __device__ __forceinline__
 #else
 #define ALP_HD inline
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 #endif
 
 namespace alp {
@@ -165,7 +166,7 @@ ALP_HD double icompton_sigma(double ea, const IComptonConst& c) {
 
 // ---- Compton production: per-bin constants (prod_xs.py:155-169, fluxes.py:210-224) -----------------------------------
 // Layout of one row of the per-bin parameter table (doubles).
-enum ComptonBin { CB_EG = 0, CB_SPAN, CB_C0, CB_XMIN, CB_XMAX, CB_P, CB_K, CB_S, CB_SIGABS, CB_PHI, CB_NP };
+enum ComptonBin { CB_EG = 0, CB_SPAN, CB_C0, CB_XMIN, CB_XMAX, CB_P, CB_K, CB_S, CB_SIGABS, CB_PHI, CB_Q, CB_NP };
 
 struct ComptonGlobals {
     double ma, ma2;      // ma, ma**2 (Python float pow on the host)
@@ -192,6 +193,8 @@ ALP_HD void compton_bin_params(double eg, double phi, double sigabs, const Compt
     out[CB_S] = s;
     out[CB_SIGABS] = sigabs;
     out[CB_PHI] = phi;
+    // fast mode: every per-row factor of the weight folded into one constant
+    out[CB_Q] = phi * (((out[CB_SPAN] * out[CB_P]) / g.n_samples) / sigabs);
 }
 
 // One Compton sample: returns E_a, writes the production weight (fluxes.py:218-224).
@@ -206,6 +209,27 @@ ALP_HD double compton_sample(double u, const double* b, const ComptonGlobals& g,
     const double dsig = (b[CB_P] * th) * ((x / omx) * inner);
     const double mc_xs = (b[CB_SPAN] * dsig) / g.n_samples;       // fluxes.py:219
     flux = b[CB_PHI] * (mc_xs / b[CB_SIGABS]);                    // :220, :224
+    return ea;
+}
+
+// Fast mode (same quantity, <= 1e-9 relative from the reference): x keeps its exact division (it is the
+// cancellation-sensitive variable), the three remaining divisions share one reciprocal 1/(x(1-x)), and the per-row
+// factors are pre-folded into CB_Q.
+ALP_HD double compton_sample_fast(double u, const double* b, const ComptonGlobals& g, double& flux) {
+    const double me2 = kME * kME;
+    const double ea = g.ma + b[CB_SPAN] * u;
+    const double x = (b[CB_C0] - ea / b[CB_EG]) + 1;
+    const bool in = (x > b[CB_XMIN]) && (x < b[CB_XMAX]);
+    const double omx = 1 - x;
+#if defined(__CUDA_ARCH__)
+    const double t = __drcp_rn(x * omx);
+#else
+    const double t = 1.0 / (x * omx);
+#endif
+    const double r_omx = x * t, r_x = omx * t;                    // 1/(1-x), 1/x
+    const double inner = b[CB_K] * ((b[CB_S] - me2 * r_omx) - g.ma2 * r_x) + x;
+    const double v = b[CB_Q] * ((x * r_omx) * inner);
+    flux = in ? v : ((x != x) ? x : 0.0 * v);                     // outside the window: 0 (NaN/inf propagate like 0*v)
     return ea;
 }
 
@@ -224,6 +248,8 @@ struct PropConst {
     double tof_light;         // det_dist / (1e-2*C_LIGHT)
     double det_dist;          // metres
     double timing_window;     // seconds
+    int    fast;              // fast mode: one rsqrt instead of sqrt + 7 divisions (<= 1e-9 relative)
+    double k1, k2;            // fast mode: neg_dist_mbm*ma*width, neg_len_mbm*ma*width (0 for width <= 0)
 };
 
 // Returns the FP64 weights before the float32 cast (decay, scatter); the casts + acceptance are prop_cast().
@@ -241,6 +267,20 @@ ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& 
     const double dec = 1 - exp((c.neg_len_mbm / va) / tau);       // :62
     s64 = (c.rescale * wgt) * surv;                               // :65
     d64 = s64 * dec;                                              // :64
+}
+
+// Fast mode: L/(hbar c v tau) = L ma Gamma / (hbar c p_a), so both exponents are a constant times 1/p_a.
+ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
+    const double d = ea * ea - c.ma2;
+    if (!(d > 0.0) || c.use_tof) {            // E_a <= m_a (v = 0 or NaN) and the time-of-flight cut: reference path
+        propagate_sample(ea, wgt, c, d64, s64);
+        return;
+    }
+    const double t = rsqrt(d);
+    const double surv = exp(c.k1 * t);
+    const double dec = 1 - exp(c.k2 * t);
+    s64 = (c.rescale * wgt) * surv;
+    d64 = s64 * dec;
 }
 
 ALP_HD float prop_cast(double w64, const PropConst& c) {
@@ -309,6 +349,26 @@ ALP_HD void decay_event(double u1, double u2, const double* p, double* p1, doubl
     p2[0] = gam * ecm + m03 * (-pz);
     p2[1] = -px; p2[2] = -py;
     p2[3] = m03 * ecm + m33 * (-pz);
+}
+
+// Fast mode: cos(theta) = 1-2u and sin(theta) = 2 sqrt(u(1-u)) directly (no acos -> sincos round trip) and
+// sincospi(2 u1) for the azimuth.  |dp|/E_parent vs the reference ~1e-15.
+ALP_HD void decay_event_fast(double u1, double u2, const double* p, double* p1, double* p2) {
+    double sphi, cphi;
+#if defined(__CUDA_ARCH__)
+    sincospi(2 * u1, &sphi, &cphi);
+#else
+    sphi = sin(kTwoPi * u1); cphi = cos(kTwoPi * u1);
+#endif
+    const double cth = 1 - 2 * u2;
+    const double sth = 2 * sqrt(u2 * (1 - u2));
+    const double pcm = p[PR_PCM], ecm = p[PR_ECM], gam = p[PR_GAM], m03 = p[PR_M03], m33 = p[PR_M33];
+    const double px = (pcm * cphi) * sth;
+    const double py = (pcm * sphi) * sth;
+    const double pz = pcm * cth;
+    const double ge = gam * ecm, me = m03 * ecm, mp = m03 * pz, m3p = m33 * pz;
+    p1[0] = ge + mp; p1[1] = px; p1[2] = py; p1[3] = me + m3p;
+    p2[0] = ge - mp; p2[1] = -px; p2[2] = -py; p2[3] = me - m3p;
 }
 
 }  // namespace alp

@@ -61,13 +61,15 @@ int finalize_sum(const double* partials, int n, double* out, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 // propagate  (fluxes.py:43-65, 159-162)
 // ---------------------------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads)
 propagate_kernel(const double* __restrict__ energy, const double* __restrict__ weight, uint64_t n, PropConst c,
                  float* __restrict__ d32, float* __restrict__ s32, double* __restrict__ d64o, double* __restrict__ s64o) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double d64, s64;
-        propagate_sample(__ldg(energy + i), __ldg(weight + i), c, d64, s64);
+        if (FAST) propagate_sample_fast(__ldg(energy + i), __ldg(weight + i), c, d64, s64);
+        else propagate_sample(__ldg(energy + i), __ldg(weight + i), c, d64, s64);
         d32[i] = prop_cast(d64, c);
         s32[i] = prop_cast(s64, c);
         if (d64o) d64o[i] = d64;
@@ -196,6 +198,9 @@ struct ComptonProd {
     __device__ static __forceinline__ double sample(double u, const double* b, const Globals& g, double& flux) {
         return compton_sample(u, b, g, flux);
     }
+    __device__ static __forceinline__ double sample_fast(double u, const double* b, const Globals& g, double& flux) {
+        return compton_sample_fast(u, b, g, flux);
+    }
 };
 
 PropConst to_prop(const alpk_prop_t* p) {
@@ -204,6 +209,7 @@ PropConst to_prop(const alpk_prop_t* p) {
     c.neg_dist_mbm = p->neg_dist_mbm; c.neg_len_mbm = p->neg_len_mbm; c.geom = p->geom; c.geom32 = p->geom32;
     c.apply_geom = p->apply_geom; c.geom_f64 = p->geom_f64; c.use_tof = p->use_tof; c.tof_light = p->tof_light;
     c.det_dist = p->det_dist; c.timing_window = p->timing_window;
+    c.fast = p->fast; c.k1 = p->k1; c.k2 = p->k2;
     return c;
 }
 
@@ -249,8 +255,12 @@ ALPK_EXPORT int alpk_propagate(const double* energy, const double* weight, uint6
     if (n == 0) return 0;
     if (!energy || !weight) { set_error("alpk_propagate: null input"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    propagate_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop), decay_w32,
-                                                                   scatter_w32, d64, s64);
+    if (h_prop->fast)
+        propagate_kernel<true><<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop), decay_w32,
+                                                                             scatter_w32, d64, s64);
+    else
+        propagate_kernel<false><<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop), decay_w32,
+                                                                              scatter_w32, d64, s64);
     return check_launch("alpk_propagate");
 }
 
@@ -335,7 +345,7 @@ ALPK_EXPORT int alpk_compton_samples(const double* row_table, uint64_t n_rows, u
                                      const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream) {
     if (!h_par) { set_error("alpk_compton_samples: null argument"); return 2; }
     return launch_chain<ComptonProd>("alpk_compton_samples", row_table, n_rows, n_samples, row_ids, to_compton(h_par),
-                                     uniforms, seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64,
+                                     h_par->fast, uniforms, seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64,
                                      scatter_w64, h_ev, event_w, rate, scratch, stream);
 }
 

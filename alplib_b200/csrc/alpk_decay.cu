@@ -40,7 +40,7 @@ struct DecayArgs {
     double* p1; double* p2; double* w;
 };
 
-template <bool INJECT>
+template <bool INJECT, bool FAST>
 __global__ void __launch_bounds__(kThreads)
 decay2body_kernel(const DecayArgs a) {
     __shared__ double s_rows[kStageRows * PR_NP];
@@ -87,7 +87,8 @@ decay2body_kernel(const DecayArgs a) {
                     const uint32_t rid = a.row_ids ? __ldg(a.row_ids + r) : (uint32_t)r;
                     uniform_2(a.seed, kTagDecay2, rid, s, u1, u2);
                 }
-                decay_event(u1, u2, p, q1[j], q2[j]);
+                if (FAST) decay_event_fast(u1, u2, p, q1[j], q2[j]);
+                else decay_event(u1, u2, p, q1[j], q2[j]);
                 wv[j] = p[PR_W];
             }
             if (have2 && planes_aligned) {
@@ -182,7 +183,7 @@ ALPK_EXPORT int alpk_decay_parent_rows(const double* energy, const float* decay_
 }
 
 ALPK_EXPORT int alpk_decay2body(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
-                                const double* uniforms, uint64_t seed, double* p1, double* p2, double* w, void* stream) {
+                                const double* uniforms, uint64_t seed, int fast, double* p1, double* p2, double* w, void* stream) {
     if (!row_table || !p1 || !p2 || !w) { set_error("alpk_decay2body: null argument"); return 2; }
     if (n_samples == 0 || n_samples > 0x7fffffffu - kDTile) { set_error("alpk_decay2body: n_samples out of range"); return 2; }
     const uint64_t n = n_parents * (uint64_t)n_samples;
@@ -191,8 +192,9 @@ ALPK_EXPORT int alpk_decay2body(const double* row_table, uint64_t n_parents, uin
     a.table = row_table; a.n_parents = n_parents; a.n_samples = n_samples; a.row_ids = row_ids;
     a.uniforms = uniforms; a.seed = seed; a.p1 = p1; a.p2 = p2; a.w = w;
     const int grid = grid_for(n, kDTile, 8);
-    if (uniforms) decay2body_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
-    else decay2body_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (uniforms) { if (fast) decay2body_kernel<true, true><<<grid, kThreads, 0, st>>>(a); else decay2body_kernel<true, false><<<grid, kThreads, 0, st>>>(a); }
+    else { if (fast) decay2body_kernel<false, true><<<grid, kThreads, 0, st>>>(a); else decay2body_kernel<false, false><<<grid, kThreads, 0, st>>>(a); }
     return check_launch("alpk_decay2body");
 }
 

@@ -20,6 +20,10 @@ struct BremProd {
     __device__ static __forceinline__ double sample(double u, const double* b, const Globals& g, double& flux) {
         return brem_sample(u, b, g, flux);
     }
+    // the production arithmetic is pow/log bound: fast mode only switches the fused propagate
+    __device__ static __forceinline__ double sample_fast(double u, const double* b, const Globals& g, double& flux) {
+        return brem_sample(u, b, g, flux);
+    }
 };
 
 static BremGlobals to_brem(const alpk_brem_t* p) {
@@ -89,6 +93,9 @@ struct PairProd {
     __device__ static __forceinline__ double sample(double u, const double* r, const Globals& g, double& flux) {
         return pairann_sample(u, r, g, flux);
     }
+    __device__ static __forceinline__ double sample_fast(double u, const double* r, const Globals& g, double& flux) {
+        return pairann_sample(u, r, g, flux);
+    }
 };
 
 static PairGlobals to_pair(const alpk_pairann_t* p) {
@@ -138,7 +145,8 @@ ALPK_EXPORT int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint
                                   double* decay_w64, double* scatter_w64,
                                   const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream) {
     if (!h_par) { set_error("alpk_brem_samples: null argument"); return 2; }
-    return launch_chain<BremProd>("alpk_brem_samples", row_table, n_rows, n_samples, row_ids, to_brem(h_par), uniforms,
+    return launch_chain<BremProd>("alpk_brem_samples", row_table, n_rows, n_samples, row_ids, to_brem(h_par),
+                                  (h_prop && h_prop->fast) ? 1 : 0, uniforms,
                                   seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64, scatter_w64,
                                   h_ev, event_w, rate, scratch, stream);
 }
@@ -173,7 +181,8 @@ ALPK_EXPORT int alpk_pairann_samples(const double* row_table, uint64_t n_rows, u
                                      double* decay_w64, double* scatter_w64,
                                      const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream) {
     if (!h_par) { set_error("alpk_pairann_samples: null argument"); return 2; }
-    return launch_chain<PairProd>("alpk_pairann_samples", row_table, n_rows, n_samples, row_ids, to_pair(h_par), uniforms,
+    return launch_chain<PairProd>("alpk_pairann_samples", row_table, n_rows, n_samples, row_ids, to_pair(h_par),
+                                  (h_prop && h_prop->fast) ? 1 : 0, uniforms,
                                   seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64, scatter_w64,
                                   h_ev, event_w, rate, scratch, stream);
 }

@@ -25,7 +25,7 @@ struct ChainArgs {
     alp::EventConst ev; double* event_w; double* partials;
 };
 
-template <class Prod, bool INJECT, int STAGE>   // STAGE 0: production; 1: + propagate; 2: + decays
+template <class Prod, bool INJECT, int STAGE, bool FAST>   // STAGE 0: production; 1: + propagate; 2: + decays
 __global__ void __launch_bounds__(kThreads)
 chain_kernel(const ChainArgs<Prod> a) {
     using namespace alp;
@@ -89,9 +89,10 @@ chain_kernel(const ChainArgs<Prod> a) {
             for (int j = 0; j < 2; ++j) {
                 // (a lone last sample computes a throw-away duplicate in slot 1: keeps the pair loop branch-free)
                 const double* b = rows + (size_t)rr[j] * NP;
-                e[j] = Prod::sample(u[j], b, a.g, f[j]);
+                e[j] = FAST ? Prod::sample_fast(u[j], b, a.g, f[j]) : Prod::sample(u[j], b, a.g, f[j]);
                 if (STAGE >= 1) {
-                    propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                    if (FAST) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                    else propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
                     d32v[j] = prop_cast(d64v[j], a.prop);
                     s32v[j] = prop_cast(s64v[j], a.prop);
                 }
@@ -136,7 +137,7 @@ int finalize_sum(const double* partials, int n, double* out, cudaStream_t st);
 // Host-side launcher shared by every production channel.
 template <class Prod>
 int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
-                 const typename Prod::Globals& g, const double* uniforms, uint64_t seed, double* out_energy,
+                 const typename Prod::Globals& g, int fast_mode, const double* uniforms, uint64_t seed, double* out_energy,
                  double* out_flux, const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32, double* decay_w64,
                  double* scatter_w64, const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
                  void* stream) {
@@ -159,14 +160,14 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     if (h_ev) { a.ev = to_event(h_ev); a.event_w = event_w; a.partials = scratch; }
     const int grid = grid_for(n, kTile, 8);
     const bool inj = uniforms != nullptr;
-    switch (stage * 2 + (inj ? 1 : 0)) {
-        case 0: chain_kernel<Prod, false, 0><<<grid, kThreads, 0, st>>>(a); break;
-        case 1: chain_kernel<Prod, true, 0><<<grid, kThreads, 0, st>>>(a); break;
-        case 2: chain_kernel<Prod, false, 1><<<grid, kThreads, 0, st>>>(a); break;
-        case 3: chain_kernel<Prod, true, 1><<<grid, kThreads, 0, st>>>(a); break;
-        case 4: chain_kernel<Prod, false, 2><<<grid, kThreads, 0, st>>>(a); break;
-        default: chain_kernel<Prod, true, 2><<<grid, kThreads, 0, st>>>(a); break;
-    }
+    const bool fast = fast_mode != 0;
+#define ALPK_CHAIN_CASE(S)                                                                                   \
+    if (inj) { if (fast) chain_kernel<Prod, true, S, true><<<grid, kThreads, 0, st>>>(a);                     \
+               else chain_kernel<Prod, true, S, false><<<grid, kThreads, 0, st>>>(a); }                        \
+    else { if (fast) chain_kernel<Prod, false, S, true><<<grid, kThreads, 0, st>>>(a);                        \
+           else chain_kernel<Prod, false, S, false><<<grid, kThreads, 0, st>>>(a); }
+    if (stage == 0) { ALPK_CHAIN_CASE(0) } else if (stage == 1) { ALPK_CHAIN_CASE(1) } else { ALPK_CHAIN_CASE(2) }
+#undef ALPK_CHAIN_CASE
     if (check_launch(what)) return 1;
     if (stage == 2) return finalize_sum(scratch, grid, rate, st);
     return 0;

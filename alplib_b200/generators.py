@@ -143,7 +143,7 @@ class PhotonEventGenerator(_EventGenerator):
                 N.call("alpk_decay_parent_rows", N.ptr(fl._E), N.ptr(fl._D32), n_flux, float(fl.ma**2), C.byref(ev), ns,
                        N.ptr(table), rt.stream())
                 N.call("alpk_decay2body", N.ptr(table), n_flux, ns, None, N.ptr(d_u), C.c_uint64(seed),
-                       N.ptr(p1), N.ptr(p2), N.ptr(w), rt.stream())
+                       1 if fl.precision == "fast" else 0, N.ptr(p1), N.ptr(p2), N.ptr(w), rt.stream())
         return LorentzVectorArray(p1), LorentzVectorArray(p2), _DeviceWeights(w)
 
 

@@ -11,7 +11,7 @@ from .constants import ALPHA, AVOGADRO, C_LIGHT, HBARC, M_E, METER_BY_MEV, S_PER
 R0_SCREEN = 2.2e-10 / METER_BY_MEV      # prod_xs.py:99 / det_xs.py:37 default screening parameter
 
 
-def prop_params(ma, width, rescale=1.0, det_dist=4.0, det_length=0.2, geom_accept=None, timing_window=None):
+def prop_params(ma, width, rescale=1.0, det_dist=4.0, det_length=0.2, geom_accept=None, timing_window=None, fast=False):
     """fluxes.py:43-65 scalars.  geom_accept None <=> is_isotropic False (fluxes.py:159)."""
     p = N.PropT()
     p.ma = float(ma)
@@ -41,6 +41,10 @@ def prop_params(ma, width, rescale=1.0, det_dist=4.0, det_length=0.2, geom_accep
         p.tof_light = 0.0
         p.timing_window = 0.0
     p.det_dist = float(det_dist)
+    # fast mode: L/(hbar c v tau) = (L/hbar c) * ma*Gamma / p_a  (exponents = constant / p_a)
+    p.fast = 1 if fast else 0
+    p.k1 = float(p.neg_dist_mbm * ma * width) if width > 0.0 else 0.0
+    p.k2 = float(p.neg_len_mbm * ma * width) if width > 0.0 else 0.0
     return p
 
 
@@ -59,13 +63,14 @@ def event_params(days_exposure, threshold):
     return e
 
 
-def compton_params(ma, g, z, n_samples):
+def compton_params(ma, g, z, n_samples, fast=False):
     c = N.ComptonT()
     c.ma = float(ma)
     c.ma2 = float(ma ** 2)
     c.aa = float(g ** 2 / 4 / pi)                        # prod_xs.py:157
     c.z = float(z)
     c.n_samples = float(n_samples)
+    c.fast = 1 if fast else 0
     return c
 
 

@@ -30,7 +30,7 @@ extern "C" {
 #define ALPK_SCRATCH_DOUBLES 16384
 
 /* number of doubles per row of the per-row parameter tables */
-#define ALPK_COMPTON_NP 10
+#define ALPK_COMPTON_NP 11
 #define ALPK_PARENT_NP 6
 #define ALPK_BREM_NP 6
 #define ALPK_PAIRANN_NP 11
@@ -58,6 +58,8 @@ typedef struct {
     double tof_light;        /* det_dist / (1e-2*C_LIGHT) */
     double det_dist;         /* metres */
     double timing_window;    /* seconds */
+    int    fast;             /* 0 = reference operation order; 1 = fast mode (one rsqrt + 2 exp per sample, <= 1e-9 rel.) */
+    double k1, k2;           /* fast mode: neg_dist_mbm*ma*width and neg_len_mbm*ma*width (0 when width <= 0) */
 } alpk_prop_t;
 
 /* event weights: generators.py:88-92 (decays), :41-46 (compton), :80-86 (inverse_primakoff) */
@@ -103,6 +105,7 @@ typedef struct {
     double aa;               /* g**2/4/pi */
     double z;                /* target Z */
     double n_samples;        /* n_samples as a double */
+    int    fast;             /* 1 = fast mode: shared reciprocal, per-row factors pre-folded (<= 1e-9 relative) */
 } alpk_compton_t;
 
 /* per-row table [n_rows][ALPK_COMPTON_NP]; rows already filtered by the host (s >= (M_E+ma)^2, fluxes.py:214-216) */
@@ -129,7 +132,7 @@ int alpk_compton_samples(const double* row_table, uint64_t n_rows, uint32_t n_sa
 int alpk_decay_parent_rows(const double* energy, const float* decay_w32, uint64_t n_parents, double ma2,
                            const alpk_event_t* h_ev, uint32_t n_samples, double* row_table, void* stream);
 int alpk_decay2body(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
-                    const double* uniforms, uint64_t seed, double* p1, double* p2, double* w, void* stream);
+                    const double* uniforms, uint64_t seed, int fast, double* p1, double* p2, double* w, void* stream);
 
 /* ---- bremsstrahlung with track-length attenuation: fluxes.py:257-356, prod_xs.py:209-221, 313-323 ------------------------ */
 typedef struct {

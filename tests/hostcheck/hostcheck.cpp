@@ -17,6 +17,7 @@ static PropConst to_prop(const alpk_prop_t* p) {
     c.neg_dist_mbm = p->neg_dist_mbm; c.neg_len_mbm = p->neg_len_mbm; c.geom = p->geom; c.geom32 = p->geom32;
     c.apply_geom = p->apply_geom; c.geom_f64 = p->geom_f64; c.use_tof = p->use_tof; c.tof_light = p->tof_light;
     c.det_dist = p->det_dist; c.timing_window = p->timing_window;
+    c.fast = p->fast; c.k1 = p->k1; c.k2 = p->k2;
     return c;
 }
 
@@ -55,7 +56,7 @@ void hc_compton(const double* eg, const double* phi, uint64_t n_rows, uint32_t n
         compton_bin_params(eg[r], phi[r], abs_sigma_mev(eg[r], le, lx, nt), g, row);
         for (uint32_t s = 0; s < n_samples; ++s) {
             const uint64_t i = r * n_samples + s;
-            oe[i] = compton_sample(u[i], row, g, of[i]);
+            oe[i] = par->fast ? compton_sample_fast(u[i], row, g, of[i]) : compton_sample(u[i], row, g, of[i]);
         }
     }
 }
@@ -64,7 +65,8 @@ void hc_propagate(const double* e, const double* w, uint64_t n, const alpk_prop_
                   double* d64, double* s64) {
     const PropConst c = to_prop(p);
     for (uint64_t i = 0; i < n; ++i) {
-        propagate_sample(e[i], w[i], c, d64[i], s64[i]);
+        if (c.fast) propagate_sample_fast(e[i], w[i], c, d64[i], s64[i]);
+        else propagate_sample(e[i], w[i], c, d64[i], s64[i]);
         d32[i] = prop_cast(d64[i], c);
         s32[i] = prop_cast(s64[i], c);
     }
@@ -87,7 +89,7 @@ void hc_scatter(int kind, const double* e, const float* w32, uint64_t n, const d
 }
 
 void hc_decay2body(const double* e, const float* w32, uint64_t n_parents, double ma2, const alpk_event_t* ev,
-                   uint32_t n_samples, const double* u, double* p1, double* p2, double* w) {
+                   uint32_t n_samples, const double* u, int fast, double* p1, double* p2, double* w) {
     const EventConst c = to_event(ev);
     const uint64_t n = n_parents * n_samples;
     for (uint64_t r = 0; r < n_parents; ++r) {
@@ -98,7 +100,8 @@ void hc_decay2body(const double* e, const float* w32, uint64_t n_parents, double
         for (uint32_t s = 0; s < n_samples; ++s) {
             const uint64_t i = r * n_samples + s;
             double q1[4], q2[4];
-            decay_event(u[(r * 2) * n_samples + s], u[(r * 2 + 1) * n_samples + s], row, q1, q2);
+            if (fast) decay_event_fast(u[(r * 2) * n_samples + s], u[(r * 2 + 1) * n_samples + s], row, q1, q2);
+            else decay_event(u[(r * 2) * n_samples + s], u[(r * 2 + 1) * n_samples + s], row, q1, q2);
             for (int k = 0; k < 4; ++k) { p1[k * n + i] = q1[k]; p2[k * n + i] = q2[k]; }
             w[i] = row[PR_W];
         }

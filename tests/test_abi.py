@@ -40,9 +40,10 @@ def test_lib_binds_and_reports_version(libpath):
 
 def test_struct_layouts_match_header():
     # field order/size of the ctypes mirrors (doubles are 8-aligned, float+3 ints pack into 16 bytes)
-    assert ctypes.sizeof(N.PropT) == 7 * 8 + 16 + 3 * 8
+    assert ctypes.sizeof(N.PropT) == 7 * 8 + 16 + 3 * 8 + 8 + 16
     assert ctypes.sizeof(N.EventT) == 8 + 8 + 8
-    assert ctypes.sizeof(N.ComptonT) == 5 * 8
+    assert ctypes.sizeof(N.ComptonT) == 5 * 8 + 8
+    assert N.PropT.k1.offset == 104 and ctypes.sizeof(N.BremT) == 12 * 8 + 8 and ctypes.sizeof(N.PairAnnT) == 11 * 8
     assert N.PropT.geom32.offset == 56 and N.PropT.tof_light.offset == 72
     assert N.EventT.threshold.offset == 16
 

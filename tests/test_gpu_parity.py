@@ -17,6 +17,16 @@ GEOM = dict(det_dist=4.0, det_length=0.2, det_area=0.04)
 GA = O.geom_acceptance(0.04, 4.0)
 
 
+@pytest.fixture(autouse=True, params=["fast", "faithful"])
+def precision(request):
+    """Every GPU parity test runs in both arithmetic modes (alplib_b200.config.PRECISION)."""
+    from alplib_b200 import config
+    old = config.PRECISION
+    config.PRECISION = request.param
+    yield request.param
+    config.PRECISION = old
+
+
 @pytest.fixture(scope="module")
 def A():
     import torch
