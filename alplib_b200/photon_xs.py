@@ -13,16 +13,29 @@ _XS_DIM = {"NaI": 149.89 / AVOGADRO, "CsI": 259.81 / AVOGADRO, "CH2": 14.027 / A
            "N2": 28.0 / AVOGADRO, "O2": 32.0 / AVOGADRO, "TeO2": 32.0 / AVOGADRO}      # photon_xs.py:27-38
 
 
+_TABLE_CACHE = {}
+_DEVICE_TABLES = {}
+
+
+def _load_table(path, skip_header):
+    """np.genfromtxt(path, skip_header=...) with the parsed file kept in memory (the reference re-reads it per object)."""
+    key = (path, skip_header)
+    t = _TABLE_CACHE.get(key)
+    if t is None:
+        t = _TABLE_CACHE[key] = np.genfromtxt(path, skip_header=skip_header)
+    return t.copy()
+
+
 class AbsCrossSection:
     """Total photon absorption cross section vs energy [MeV] (photon_xs.py:18-52)."""
 
     def __init__(self, material: Material):
         self.xs_dim = _XS_DIM.get(material.mat_name, 1e-24)          # barns -> cm2, or cm2/g -> cm2/molecule
         self.mat_name = material.mat_name
-        self.pe_data = np.genfromtxt(data_path("photon_absorption", "photon_abs_" + self.mat_name + ".txt"),
-                                     skip_header=3)
+        self.pe_data = _load_table(data_path("photon_absorption", "photon_abs_" + self.mat_name + ".txt"), 3)
         self.cleanPEData()
-        self._dev = {}
+        # device copies are shared by every instance built from the same table (scans build one flux per point)
+        self._dev = _DEVICE_TABLES.setdefault((self.mat_name, self.xs_dim), {})
 
     def cleanPEData(self):
         # keep the first row of every duplicated edge energy (photon_xs.py:42-43)

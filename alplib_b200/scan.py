@@ -1,0 +1,98 @@
+"""Batched (m_a, g) sensitivity scans.
+
+The reference has no scan driver: users loop `Flux*(ma, g0).simulate(); propagate(new_coupling=g); decays()` over a grid
+(README.md:199-226, examples/ex4_na64.py:30-40), re-running the whole chain per point.  `scan_rates` evaluates the same
+event-rate map in a single kernel launch (grid = mass x sample tile, threads = couplings), sharded over GPUs by mass.
+The samples are the ones the per-point API would generate with the same seed, so each map entry equals the per-point
+result up to the order of the final sum.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from numpy import power
+
+from . import _native as N
+from . import config
+from . import params as P
+from .constants import M_E, pi
+from .decay import W_ee, W_gg, W_gg_loop
+from .dist import merge_row_blocks, shard_range, world as _world
+from .fluxes import _as_flux_table, _draw_seed
+from .materials import Material
+from .photon_xs import AbsCrossSection
+from .runtime import Runtime
+
+COMPTON, PRIMAKOFF = 0, 1
+_PROC = {"compton": COMPTON, "primakoff": PRIMAKOFF}
+
+
+def scan_rates(process, photon_flux, target, ma_grid, g_grid, n_samples=100, det_dist=4.0, det_length=0.2,
+               det_area=0.04, days_exposure=100, threshold=0.0, g0=None, is_isotropic=True, loop_decay=False,
+               seed=None, precision=None, device=None, row_offset=0, return_device=False):
+    """Decay-event rates on the (m_a, g) grid for `process` ("compton": FluxComptonIsotropic + ElectronEventGenerator;
+    "primakoff": FluxPrimakoffIsotropic + PhotonEventGenerator).  Returns rates[n_ma, n_g]: entry (i, j) is what
+
+        f = Flux*Isotropic(photon_flux, target, ..., axion_mass=ma[i], axion_coupling=g0, n_samples=n_samples, seed=seed)
+        f.simulate(); f.propagate(new_coupling=g[j]); EventGenerator(f, det).decays(days_exposure, threshold)
+
+    returns.  g0 defaults to g_grid[0]."""
+    proc = _PROC[process] if isinstance(process, str) else int(process)
+    pf = _as_flux_table(photon_flux, "photon_flux")
+    ma = np.ascontiguousarray(ma_grid, dtype=np.float64).ravel()
+    g = np.ascontiguousarray(g_grid, dtype=np.float64).ravel()
+    n_ma, n_g = int(ma.shape[0]), int(g.shape[0])
+    g0 = float(g[0]) if g0 is None else float(g0)
+    precision = precision if precision is not None else config.PRECISION
+    seed = seed if seed is not None else _draw_seed()
+    z = target.z[0]
+    width = np.empty((n_ma, n_g))
+    for i, m in enumerate(ma):
+        for j, gj in enumerate(g):
+            if proc == COMPTON:
+                width[i, j] = W_ee(gj, m) + (W_gg_loop(gj, m, M_E) if loop_decay else 0.0)
+            else:
+                width[i, j] = W_gg(gj, m)
+    rescale = power(g / g0, 2)
+    if proc == COMPTON:
+        c0, c1 = float(g0 ** 2 / 4 / pi), 0.0
+        np_row = N.COMPTON_NP
+    else:
+        c0, c1 = P.primakoff_consts(g0, z)
+        np_row = 2
+        n_samples = 1
+    geom = det_area / (4 * pi * det_dist ** 2) if is_isotropic else None
+    prop = P.prop_params(1.0, 0.0, 1.0, det_dist, det_length, geom_accept=geom, fast=precision == "fast")
+    ev = P.event_params(days_exposure, threshold)
+    rt = Runtime.get(device)
+    xs = AbsCrossSection(target)
+    n_rows = int(pf.shape[0])
+    with rt.activate():
+        le, lx, nt = xs.device_table(rt)
+        d_e, d_p = rt.upload(pf[:, 0]), rt.upload(pf[:, 1])
+        d_ma, d_ma2 = rt.upload(ma), rt.upload(ma ** 2)
+        d_w, d_r = rt.upload(width), rt.upload(rescale)
+        n_tiles = int(N.lib().alpk_scan_tiles(n_rows, int(n_samples)))
+        tables = rt.empty(max(1, n_ma * n_rows * np_row))
+        partials = rt.empty(max(1, n_ma * n_tiles * n_g))
+        out = rt.empty(n_ma * n_g)
+        N.call("alpk_scan", proc, N.ptr(d_e), N.ptr(d_p), n_rows, int(row_offset), N.ptr(le), N.ptr(lx), nt,
+               N.ptr(d_ma), N.ptr(d_ma2), n_ma, N.ptr(d_w), N.ptr(d_r), n_g, c0, c1, float(z), int(n_samples),
+               C.c_uint64(seed), C.byref(prop), C.byref(ev), N.ptr(tables), N.ptr(partials), N.ptr(out), rt.stream())
+    out = out.view(n_ma, n_g)
+    return out if return_device else out.cpu().numpy()
+
+
+def scan_rates_distributed(process, photon_flux, target, ma_grid, g_grid, group=None, **kw):
+    """`scan_rates` with the mass axis sharded over the ranks of a torch.distributed process group (one process per
+    GPU).  Every rank returns the full map; the only communication is one all-reduce of the (n_ma x n_g) map
+    (NCCL over NVLink on the GPU box)."""
+    rank, nranks = _world(group)
+    ma = np.ascontiguousarray(ma_grid, dtype=np.float64).ravel()
+    g = np.ascontiguousarray(g_grid, dtype=np.float64).ravel()
+    lo, hi = shard_range(ma.shape[0], rank, nranks)
+    kw = dict(kw)
+    kw.setdefault("g0", float(g[0]))
+    kw["return_device"] = True
+    local = scan_rates(process, photon_flux, target, ma[lo:hi], g, **kw)
+    return merge_row_blocks(local, lo, ma.shape[0], group).cpu().numpy()

@@ -204,6 +204,25 @@ int alpk_pairann_samples(const double* row_table, uint64_t n_rows, uint32_t n_sa
 int alpk_hist(const double* x, const double* w64_or_null, const float* w32_or_null, uint64_t n,
               const double* edges, int n_edges, double* hist /* [n_edges-1], accumulated into */, void* stream);
 
+/* ---- batched (m_a, g) scan: README.md:199-226 / examples/ex4_na64.py:30-40 pattern (one simulate() per m_a, one
+ * propagate(new_coupling=g) + decays() per point, fluxes.py:153-162,235-245; generators.py:88-92) in one launch grid.
+ * process 0 = Compton  (c0 = g0**2/4/pi, z = target Z, n_samples per row),
+ * process 1 = Primakoff (c0 = (g0 z)**2/(2*137), c1 = r0**2; one sample per row).
+ * e_gamma/phi_gamma: the FULL flux table (rows failing a mass's threshold contribute nothing for that mass);
+ * row_offset: global index of row 0 (Philox key) when the table is a shard.
+ * ma_grid/ma2_grid[n_ma] (ma, ma**2); width[n_ma][n_g] decay widths; rescale[n_g] = (g/g0)**2.
+ * h_geom: detector geometry / acceptance / fast flag of alpk_prop_t (ma, width, rescale fields ignored).
+ * tables: scratch [n_ma][n_rows][ALPK_COMPTON_NP or 2]; partials: scratch [n_ma][alpk_scan_tiles()][n_g];
+ * out_rates[n_ma][n_g] = decays(days, threshold) of every grid point. */
+uint32_t alpk_scan_tiles(uint32_t n_rows, uint32_t n_samples);
+int alpk_scan(int process, const double* e_gamma, const double* phi_gamma, uint32_t n_rows, uint32_t row_offset,
+              const double* log10_e, const double* log10_xs, int n_table,
+              const double* ma_grid, const double* ma2_grid, int n_ma,
+              const double* width, const double* rescale, int n_g,
+              double c0, double c1, double z, uint32_t n_samples, uint64_t seed,
+              const alpk_prop_t* h_geom, const alpk_event_t* h_ev,
+              double* tables, double* partials, double* out_rates, void* stream);
+
 /* FP64 issue-rate microbenchmark: `blocks` CTAs x 256 threads x 8 independent DFMA chains x iters (bench.py uses it
  * to measure the FP64 roofline denominator on the box).  out: >= blocks*256 doubles (never written in practice). */
 int alpk_fp64_peak(uint64_t iters, int blocks, double* out, void* stream);

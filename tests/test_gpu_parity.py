@@ -5,7 +5,7 @@ ulp) on the reference's float32 attributes; decay weights use the conditioned to
 import numpy as np
 import pytest
 
-from conftest import assert_decay_close, load_golden, max_rel
+from conftest import assert_decay_close, decay_tol, load_golden, max_rel
 from oracle import alp_oracle as O
 from oracle import philox as PX
 
@@ -427,3 +427,51 @@ def test_pairann_free_running_matches_oracle(A):
                                          fused=True, **GEOM_DUNE)
     fb.simulate(); fb.propagate()
     assert A.ElectronEventGenerator(fb, A.Material("Ar")).decays(365, 30.0) == pytest.approx(r_sep, rel=1e-12)
+
+
+# ---- batched (m_a, g) scan (BASELINE config 5) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("process", ["compton", "primakoff"])
+def test_scan_matches_per_point_api(A, process):
+    from alplib_b200.scan import scan_rates
+    pf = _c2_flux(60)
+    ma_grid = np.array([0.01, 0.3, 1.5, 4.0, 30.0, 2000.0])          # last mass: above every photon energy -> all zero
+    g_grid = np.logspace(-8, -4, 7) if process == "compton" else np.logspace(-7, -3, 7)
+    ns, seed = 128, 31337
+    rates = scan_rates(process, pf, A.Material("W"), ma_grid, g_grid, n_samples=ns, days_exposure=100, threshold=5.0,
+                       seed=seed, **GEOM)
+    assert rates.shape == (6, 7) and np.all(rates[-1] == 0) and np.all(np.isfinite(rates))
+    ref = np.zeros_like(rates)
+    for i, m in enumerate(ma_grid):
+        if process == "compton":
+            fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=m, axion_coupling=g_grid[0], n_samples=ns, seed=seed, **GEOM)
+            gen = A.ElectronEventGenerator(fl, A.Material("Ar"))
+        else:
+            fl = A.FluxPrimakoffIsotropic(pf, A.Material("W"), axion_mass=m, axion_coupling=g_grid[0], **GEOM)
+            gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+        fl.simulate()
+        for j, g in enumerate(g_grid):
+            fl.propagate(new_coupling=g)
+            ref[i, j] = gen.decays(100, 5.0)
+    nz = ref != 0
+    assert nz.sum() > 15
+    assert max_rel(rates[nz], ref[nz]) < 1e-11                        # same samples, same arithmetic: only the sum order differs
+    assert np.all(rates[~nz] == 0)
+
+
+def test_scan_matches_oracle(A):
+    from alplib_b200.scan import scan_rates
+    pf = _c2_flux(25)
+    ma_grid, g_grid, ns, seed = np.array([0.5, 2.0]), np.array([1e-7, 3e-6, 1e-4]), 200, 5
+    rates = scan_rates("compton", pf, A.Material("W"), ma_grid, g_grid, n_samples=ns, days_exposure=100, threshold=5.0,
+                       seed=seed, **GEOM)
+    W = O.AbsCrossSection(O.Material("W"))
+    for i, m in enumerate(ma_grid):
+        keep = O.compton_row_valid(pf, m)
+        u = np.concatenate([PX.uniform_1(seed, PX.TAG_COMPTON_EA, int(r), ns) for r in np.nonzero(keep)[0]])
+        oE, oF = O.compton_simulate(pf, m, g_grid[0], 74, W, ns, O.UniformSource(u))
+        for j, g in enumerate(g_grid):
+            p = O.propagate(oE, oF, m, O.W_ee(g, m), np.power(g / g_grid[0], 2), 4.0, 0.2, geom_accept=GA)
+            ew, r = O.decays(oE, p["decay_w"], 100, 5.0)
+            # decay_prob = 1-exp(-x) cancels for long-lived points: compare with the summed conditioned tolerance
+            tol = float(np.sum(np.abs(ew) * (decay_tol(p["decay_w64"], p["scatter_w64"], 1e-9) + 2 * F32)) / max(abs(r), 1e-300))
+            assert abs(rates[i, j] - r) <= tol * abs(r) + 1e-300, (i, j, rates[i, j], r, tol)
