@@ -15,7 +15,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
 SCRATCH_DOUBLES = 16384
-COMPTON_NP = 11
+COMPTON_NP = 12
 PARENT_NP = 6
 BREM_NP = 6
 PAIRANN_NP = 11

@@ -166,7 +166,7 @@ ALP_HD double icompton_sigma(double ea, const IComptonConst& c) {
 
 // ---- Compton production: per-bin constants (prod_xs.py:155-169, fluxes.py:210-224) -----------------------------------
 // Layout of one row of the per-bin parameter table (doubles).
-enum ComptonBin { CB_EG = 0, CB_SPAN, CB_C0, CB_XMIN, CB_XMAX, CB_P, CB_K, CB_S, CB_SIGABS, CB_PHI, CB_Q, CB_NP };
+enum ComptonBin { CB_EG = 0, CB_SPAN, CB_C0, CB_XMIN, CB_XMAX, CB_P, CB_K, CB_S, CB_SIGABS, CB_PHI, CB_Q, CB_INVEG, CB_NP };
 
 struct ComptonGlobals {
     double ma, ma2;      // ma, ma**2 (Python float pow on the host)
@@ -195,6 +195,7 @@ ALP_HD void compton_bin_params(double eg, double phi, double sigabs, const Compt
     out[CB_PHI] = phi;
     // fast mode: every per-row factor of the weight folded into one constant
     out[CB_Q] = phi * (((out[CB_SPAN] * out[CB_P]) / g.n_samples) / sigabs);
+    out[CB_INVEG] = 1 / eg;
 }
 
 // One Compton sample: returns E_a, writes the production weight (fluxes.py:218-224).
@@ -218,7 +219,11 @@ ALP_HD double compton_sample(double u, const double* b, const ComptonGlobals& g,
 ALP_HD double compton_sample_fast(double u, const double* b, const ComptonGlobals& g, double& flux) {
     const double me2 = kME * kME;
     const double ea = g.ma + b[CB_SPAN] * u;
-    const double x = (b[CB_C0] - ea / b[CB_EG]) + 1;
+    // ea/eg by reciprocal + one fused correction step: the correctly rounded quotient in all but rare last-bit cases
+    // (x is the cancellation-sensitive variable, so its quotient is kept to that accuracy)
+    const double q0 = ea * b[CB_INVEG];
+    const double q = fma(fma(-q0, b[CB_EG], ea), b[CB_INVEG], q0);
+    const double x = (b[CB_C0] - q) + 1;
     const bool in = (x > b[CB_XMIN]) && (x < b[CB_XMAX]);
     const double omx = 1 - x;
 #if defined(__CUDA_ARCH__)

@@ -23,6 +23,7 @@ struct ChainArgs {
     double* out_e; double* out_f;
     alp::PropConst prop; float* d32; float* s32; double* d64; double* s64;
     alp::EventConst ev; double* event_w; double* partials;
+    uint32_t tile_elems;
 };
 
 template <class Prod, bool INJECT, int STAGE, bool FAST>   // STAGE 0: production; 1: + propagate; 2: + decays
@@ -33,40 +34,42 @@ chain_kernel(const ChainArgs<Prod> a) {
     __shared__ double s_rows[kStageRows * NP];
     __shared__ double red[32];
     const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
-    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+    const uint32_t tile_elems = a.tile_elems;        // kTile, or fewer when rows are so short that a full tile would
+    const uint64_t n_tiles = (n + tile_elems - 1) / tile_elems;   // touch more than kStageRows of them
+    const bool long_rows = a.n_samples >= tile_elems;              // a tile then touches at most two rows
     double acc = 0.0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t base = tile * kTile;
-        const uint64_t last = (base + kTile <= n ? base + kTile : n) - 1;
+        const uint64_t base = tile * tile_elems;
+        const uint64_t last = (base + tile_elems <= n ? base + tile_elems : n) - 1;
         const uint64_t r0 = base / a.n_samples;
         const uint64_t r1 = last / a.n_samples;
-        const int nrows = (int)(r1 - r0 + 1);
-        const double* rows;                          // row r -> rows + (r - r0)*NP
+        const int nrows = (int)(r1 - r0 + 1);        // <= kStageRows by construction of tile_elems
+        const double* rows = s_rows;                 // row r -> rows + (r - r0)*NP
         __syncthreads();                             // previous tile finished reading s_rows
-        if (nrows <= kStageRows) {
-            stage_rows<NP>(s_rows, a.table, r0, nrows);
-            rows = s_rows;
-        } else {
-            rows = a.table + r0 * NP;                // many tiny rows per tile: read through L1/L2 instead
-        }
+        stage_rows<NP>(s_rows, a.table, r0, nrows);
         __syncthreads();
         const uint64_t row0_first = r0 * (uint64_t)a.n_samples;
 
 #pragma unroll 1
         for (int k = 0; k < kUnroll; ++k) {
-            const uint64_t i0 = base + 2 * ((uint64_t)k * kThreads + threadIdx.x);
+            const uint32_t local = 2 * ((uint32_t)k * kThreads + threadIdx.x);
+            if (local >= tile_elems) break;
+            const uint64_t i0 = base + local;
             if (i0 >= n) break;
             const bool have2 = (i0 + 1 < n);
             double e[2], f[2], u[2];
             float d32v[2], s32v[2];
             double d64v[2], s64v[2], evv[2];
             uint32_t rr[2], ss[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const uint32_t off = (uint32_t)(i0 + ((j == 1 && !have2) ? 0 : j) - row0_first);
-                rr[j] = off / a.n_samples;
-                ss[j] = off - rr[j] * a.n_samples;
+            {
+                // (row, sample) of the pair: one integer division at most; none when rows are longer than a tile
+                const uint32_t off = (uint32_t)(i0 - row0_first);
+                if (long_rows) { rr[0] = off >= a.n_samples ? 1u : 0u; ss[0] = off - (rr[0] ? a.n_samples : 0u); }
+                else { rr[0] = off / a.n_samples; ss[0] = off - rr[0] * a.n_samples; }
+                const bool wrap = ss[0] + 1u == a.n_samples;
+                rr[1] = have2 ? (wrap ? rr[0] + 1u : rr[0]) : rr[0];
+                ss[1] = have2 ? (wrap ? 0u : ss[0] + 1u) : ss[0];
             }
             if (INJECT) {
 #pragma unroll
@@ -158,7 +161,10 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const int stage = h_ev ? 2 : (h_prop ? 1 : 0);
     if (h_prop) { a.prop = to_prop(h_prop); a.d32 = decay_w32; a.s32 = scatter_w32; a.d64 = decay_w64; a.s64 = scatter_w64; }
     if (h_ev) { a.ev = to_event(h_ev); a.event_w = event_w; a.partials = scratch; }
-    const int grid = grid_for(n, kTile, 8);
+    // rows per tile <= tile/n_samples + 2 must fit the shared-memory stage
+    uint64_t te = (uint64_t)(kStageRows - 2) * n_samples;
+    a.tile_elems = (uint32_t)(te >= (uint64_t)kTile ? (uint64_t)kTile : (te < 2 ? 2 : (te & ~1ull)));
+    const int grid = grid_for(n, (int)a.tile_elems, 8);
     const bool inj = uniforms != nullptr;
     const bool fast = fast_mode != 0;
 #define ALPK_CHAIN_CASE(S)                                                                                   \

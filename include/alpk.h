@@ -30,7 +30,7 @@ extern "C" {
 #define ALPK_SCRATCH_DOUBLES 16384
 
 /* number of doubles per row of the per-row parameter tables */
-#define ALPK_COMPTON_NP 11
+#define ALPK_COMPTON_NP 12
 #define ALPK_PARENT_NP 6
 #define ALPK_BREM_NP 6
 #define ALPK_PAIRANN_NP 11
