@@ -13,7 +13,13 @@
 
 namespace alpk {
 
-constexpr int kUnroll = 4;
+#ifndef ALPK_UNROLL
+#define ALPK_UNROLL 16
+#endif
+#ifndef ALPK_MIN_BLOCKS
+#define ALPK_MIN_BLOCKS 4
+#endif
+constexpr int kUnroll = ALPK_UNROLL;
 constexpr int kTile = kThreads * 2 * kUnroll;
 
 template <class Prod>
@@ -27,7 +33,7 @@ struct ChainArgs {
 };
 
 template <class Prod, bool INJECT, int STAGE, bool FAST>   // STAGE 0: production; 1: + propagate; 2: + decays
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, ALPK_MIN_BLOCKS)
 chain_kernel(const ChainArgs<Prod> a) {
     using namespace alp;
     constexpr int NP = Prod::NP;
@@ -42,9 +48,9 @@ chain_kernel(const ChainArgs<Prod> a) {
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t base = tile * tile_elems;
         const uint64_t last = (base + tile_elems <= n ? base + tile_elems : n) - 1;
-        const uint64_t r0 = base / a.n_samples;
-        const uint64_t r1 = last / a.n_samples;
-        const int nrows = (int)(r1 - r0 + 1);        // <= kStageRows by construction of tile_elems
+        const uint64_t r0 = base / a.n_samples;       // the only 64-bit division, once per tile
+        const uint32_t off_last = (uint32_t)(last - r0 * (uint64_t)a.n_samples);
+        const int nrows = (int)(long_rows ? (off_last >= a.n_samples ? 2u : 1u) : off_last / a.n_samples + 1u);   // <= kStageRows
         const double* rows = s_rows;                 // row r -> rows + (r - r0)*NP
         __syncthreads();                             // previous tile finished reading s_rows
         stage_rows<NP>(s_rows, a.table, r0, nrows);
