@@ -7,7 +7,7 @@ ElectronEventGenerator, Material, the decay widths and the constants -- same nam
 `__graft_entry__.build()`); there is no CPU fallback.
 """
 from .constants import *            # noqa: F401,F403
-from .materials import Material     # noqa: F401
+from .materials import Material, DetectorGeometry     # noqa: F401
 from .decay import W_gg, W_ee, W_ff, W_gg_loop, fp2, b1   # noqa: F401
 from .photon_xs import AbsCrossSection                   # noqa: F401
 from .vectors import Vector3, LorentzVector, LorentzVectorArray   # noqa: F401

@@ -113,6 +113,8 @@ _SIGNATURES = {
     "alpk_scan_tiles": ([_U32, _U32], _U32),
     "alpk_scan": ([_I, _P, _P, _U32, _U32, _P, _P, _I, _P, _P, _I, _P, _P, _I, _D, _D, _D, _U32, _U64,
                    C.POINTER(PropT), C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_vol_int_chunks": ([_U64, _U32], _U32),
+    "alpk_vol_int": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _U32, _D, _D, _P, _P, _P, _P, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),
     "alpk_fp64_peak": ([_U64, _I, _P, _P], _I),

@@ -209,3 +209,111 @@ ALPK_EXPORT int alpk_hist(const double* x, const double* w64, const float* w32, 
     else hist_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, w64, w32, n, edges, n_edges, hist);
     return check_launch("alpk_hist");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// propagate_iso_vol_int (fluxes.py:67-89): per sample, Monte-Carlo integral over detector-volume points of
+//   f(l) = (1/(hbar c v tau)) exp(-l/(hbar c v tau)) / (4 pi l^2)        (materials.py:98-124 DetectorGeometry.integrate)
+// thread = sample; the geometry points (host-prepared: -l/METER_BY_MEV, 4 pi l^2, jacobian) are walked from shared
+// memory in tiles (broadcast reads); blockIdx.y splits the points, partial sums are reduced in fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+namespace alpk {
+
+constexpr int kVolTile = 1024;
+
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads)
+vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __restrict__ nxm,
+               const double* __restrict__ bden, const double* __restrict__ jac, uint32_t n_points, uint32_t chunk,
+               double ma, double ma2, double width, double inv_mbm, double* __restrict__ partials) {
+    __shared__ double s_x[kVolTile], s_b[kVolTile], s_j[kVolTile];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k0 = blockIdx.y * chunk;
+    const uint32_t k1 = (k0 + chunk < n_points) ? k0 + chunk : n_points;
+    double va = 1.0, tau = 1.0, A = 0.0, c = 0.0;
+    const bool live = i < n;
+    if (live) {
+        const double ea = __ldg(energy + i);
+        const double pa = sqrt(ea * ea - ma2);                               // fluxes.py:72
+        va = pa / ea;                                                        // :73
+        const double boost = ea / ma;                                        // :74
+        tau = width > 0.0 ? boost / width : INFINITY;                        // :75
+        A = (inv_mbm / va) / tau;                                            // 1/METER_BY_MEV/v/tau   :84
+        c = width > 0.0 ? (ma * width) / pa : 0.0;                           // fast: 1/(v tau)
+    }
+    double acc = 0.0;
+    for (uint32_t t0 = k0; t0 < k1; t0 += kVolTile) {
+        const uint32_t cnt = (t0 + kVolTile <= k1) ? kVolTile : k1 - t0;
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
+            s_x[k] = __ldg(nxm + t0 + k); s_b[k] = __ldg(bden + t0 + k); s_j[k] = __ldg(jac + t0 + k);
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const double e = FAST ? exp(s_x[k] * c) : exp((s_x[k] / va) / tau);      // :85
+                acc += s_j[k] * ((A * e) / s_b[k]);
+            }
+        }
+    }
+    if (live) partials[(uint64_t)blockIdx.y * n + i] = acc;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads)
+vol_int_finish_kernel(const double* __restrict__ energy, const double* __restrict__ weight, uint64_t n,
+                      const double* __restrict__ partials, uint32_t n_chunks, double vol_over_n, PropConst c,
+                      float* __restrict__ d32, float* __restrict__ s32, double* __restrict__ d64o, double* __restrict__ s64o) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double sum = 0.0;
+        for (uint32_t q = 0; q < n_chunks; ++q) sum += partials[(uint64_t)q * n + i];
+        const double vol = vol_over_n * sum;                      // V * np.sum(...) / n_samples (materials.py:103,110,117)
+        double d_unused, s64;
+        if (FAST) propagate_sample_fast(__ldg(energy + i), __ldg(weight + i), c, d_unused, s64);
+        else propagate_sample(__ldg(energy + i), __ldg(weight + i), c, d_unused, s64);   // scatter weight, fluxes.py:77-78,89
+        const double d64 = (c.rescale * __ldg(weight + i)) * vol;                        // :88
+        d32[i] = (float)d64;
+        s32[i] = (float)s64;
+        if (d64o) d64o[i] = d64;
+        if (s64o) s64o[i] = s64;
+    }
+}
+
+}  // namespace alpk
+
+ALPK_EXPORT uint32_t alpk_vol_int_chunks(uint64_t n, uint32_t n_points) {
+    // enough (sample block, point chunk) CTAs to fill the GPU even for a handful of samples
+    const uint64_t blocks = (n + kThreads - 1) / kThreads;
+    uint32_t want = (uint32_t)((2ull * 148 + blocks - 1) / (blocks ? blocks : 1));
+    uint32_t maxc = (n_points + kVolTile - 1) / kVolTile;
+    if (want < 1) want = 1;
+    return want < maxc ? want : (maxc ? maxc : 1);
+}
+
+ALPK_EXPORT int alpk_vol_int(const double* energy, const double* weight, uint64_t n, const alpk_prop_t* h_prop,
+                             const double* nxm, const double* bden, const double* jac, uint32_t n_points,
+                             double volume_over_n, double inv_mbm, float* decay_w32, float* scatter_w32,
+                             double* decay_w64, double* scatter_w64, double* partials, void* stream) {
+    if (!h_prop || !decay_w32 || !scatter_w32 || !partials || !nxm || !bden || !jac) { set_error("alpk_vol_int: null argument"); return 2; }
+    if (n == 0) return 0;
+    if (n_points == 0) { set_error("alpk_vol_int: no geometry points"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t n_chunks = alpk_vol_int_chunks(n, n_points);
+    uint32_t chunk = (n_points + n_chunks - 1) / n_chunks;
+    chunk = ((chunk + kVolTile - 1) / kVolTile) * kVolTile;
+    const uint32_t used = (n_points + chunk - 1) / chunk;
+    dim3 grid((unsigned)((n + kThreads - 1) / kThreads), used);
+    PropConst c;
+    c.ma = h_prop->ma; c.ma2 = h_prop->ma2; c.width = h_prop->width; c.rescale = h_prop->rescale;
+    c.neg_dist_mbm = h_prop->neg_dist_mbm; c.neg_len_mbm = h_prop->neg_len_mbm; c.geom = 1.0; c.geom32 = 1.0f;
+    c.apply_geom = 0; c.geom_f64 = 0; c.use_tof = 0; c.tof_light = 0; c.det_dist = h_prop->det_dist; c.timing_window = 0;
+    c.fast = h_prop->fast; c.k1 = h_prop->k1; c.k2 = h_prop->k2;
+    if (h_prop->fast) vol_int_kernel<true><<<grid, kThreads, 0, st>>>(energy, n, nxm, bden, jac, n_points, chunk, c.ma, c.ma2, c.width, inv_mbm, partials);
+    else vol_int_kernel<false><<<grid, kThreads, 0, st>>>(energy, n, nxm, bden, jac, n_points, chunk, c.ma, c.ma2, c.width, inv_mbm, partials);
+    if (check_launch("alpk_vol_int")) return 1;
+    const int g2 = grid_for(n, kThreads, 8);
+    if (h_prop->fast) vol_int_finish_kernel<true><<<g2, kThreads, 0, st>>>(energy, weight, n, partials, used, volume_over_n, c, decay_w32, scatter_w32, decay_w64, scatter_w64);
+    else vol_int_finish_kernel<false><<<g2, kThreads, 0, st>>>(energy, weight, n, partials, used, volume_over_n, c, decay_w32, scatter_w32, decay_w64, scatter_w64);
+    return check_launch("alpk_vol_int(finish)");
+}

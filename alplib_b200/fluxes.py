@@ -29,9 +29,9 @@ from numpy import arctan, pi, power, sqrt
 from . import _native as N
 from . import config
 from . import params as P
-from .constants import ALPHA, AVOGADRO, HBARC, M_E
+from .constants import ALPHA, AVOGADRO, HBARC, M_E, METER_BY_MEV
 from .decay import W_ee, W_gg, W_gg_loop
-from .materials import Material
+from .materials import DetectorGeometry, Material
 from .photon_xs import AbsCrossSection
 from .runtime import Runtime
 
@@ -227,6 +227,35 @@ class AxionFlux:
         """Survival x decay probability weights (reference: AxionFlux.propagate, fluxes.py:43-65)."""
         self._propagate(decay_width, rescale_factor, None, time_of_flight_cut)
 
+    def propagate_iso_vol_int(self, geom: DetectorGeometry, decay_width, rescale_factor=1.0):
+        """Decay weights from a Monte-Carlo integral of the decay probability density over the detector volume
+        (reference: AxionFlux.propagate_iso_vol_int, fluxes.py:67-89): n_flux x geom.n_samples evaluations."""
+        self._ensure_production()
+        self._pending_prop = None
+        rt = self._rt
+        n = 0 if self._E is None else int(self._E.shape[0])
+        if (0 if self._F is None else int(self._F.shape[0])) != n:
+            raise ValueError("axion_energy and axion_flux have different lengths")
+        prop = self._prop_params(decay_width, rescale_factor, None, None)
+        ls, jac, vol = geom.point_table()
+        npts = int(ls.shape[0])
+        with rt.activate():
+            self._D32 = rt.empty(n, torch.float32)
+            self._S32 = rt.empty(n, torch.float32)
+            self._D64 = rt.empty(n) if self.keep_f64 else None
+            self._S64 = rt.empty(n) if self.keep_f64 else None
+            if n:
+                d_nx = rt.upload(-ls / METER_BY_MEV)                     # fluxes.py:85  -x / METER_BY_MEV
+                d_b = rt.upload(4*pi*ls**2)                              # :85  4*pi*x**2
+                d_j = rt.upload(jac)
+                chunks = int(N.lib().alpk_vol_int_chunks(n, npts))
+                partials = rt.empty(chunks * n)
+                N.call("alpk_vol_int", N.ptr(self._E), N.ptr(self._F), n, C.byref(prop), N.ptr(d_nx), N.ptr(d_b),
+                       N.ptr(d_j), npts, float(vol / geom.n_samples), float(1 / METER_BY_MEV), N.ptr(self._D32),
+                       N.ptr(self._S32), N.ptr(self._D64), N.ptr(self._S64), N.ptr(partials), rt.stream())
+        for k in ("D32", "S32", "D64", "S64"):
+            self._host.pop(k, None)
+
     def _geom_accept(self):
         return self.det_area / (4*pi*self.det_dist**2)          # fluxes.py:160
 
@@ -320,6 +349,23 @@ class FluxPrimakoffIsotropic(AxionFlux):
         else:
             self._propagate(W_gg(self.gagamma, self.ma), 1.0, geom)
 
+    def propagate_iso_vol_int(self, geom: DetectorGeometry, new_coupling=None):
+        if new_coupling is not None:
+            rescale = power(new_coupling/self.gagamma, 2)
+            super().propagate_iso_vol_int(geom, W_gg(new_coupling, self.ma), rescale)
+        else:
+            super().propagate_iso_vol_int(geom, W_gg(self.gagamma, self.ma))
+
+
+def _vol_int_e(self, geom: DetectorGeometry, new_coupling=None):
+    """propagate_iso_vol_int of the electron-coupled flux classes (fluxes.py:247-252, 370-375, 459-464, 544-549):
+    uses W_ee only, like the reference (no loop-induced width here)."""
+    if new_coupling is not None:
+        rescale = power(new_coupling/self.ge, 2)
+        AxionFlux.propagate_iso_vol_int(self, geom, W_ee(new_coupling, self.ma), rescale)
+    else:
+        AxionFlux.propagate_iso_vol_int(self, geom, W_ee(self.ge, self.ma))
+
 
 class _ChainFlux(AxionFlux):
     """Flux classes whose samples come from the generic per-sample chain kernel (production -> [propagate -> [decays]]):
@@ -328,6 +374,7 @@ class _ChainFlux(AxionFlux):
     _rows = None                # (row table, n_rows, n_samples, row ids, params struct, injected uniforms, seed)
 
     decay_width = _width_e
+    propagate_iso_vol_int = _vol_int_e
 
     def _launch_samples(self, E, F, prop, ev, d32=None, s32=None, d64=None, s64=None, evw=None, rate=None):
         table, n_rows, ns, d_ids, par, d_u, seed = self._rows
@@ -621,6 +668,7 @@ class FluxResonanceIsotropic(AxionFlux):
         self.max_t = max_track_length
 
     decay_width = _width_e
+    propagate_iso_vol_int = _vol_int_e
 
     def positron_flux_dN_dE(self, energy):
         pf = np.asarray(self.positron_flux, dtype=np.float64)

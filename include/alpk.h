@@ -200,6 +200,18 @@ int alpk_pairann_samples(const double* row_table, uint64_t n_rows, uint32_t n_sa
                          double* decay_w64, double* scatter_w64,
                          const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream);
 
+/* ---- propagate_iso_vol_int: fluxes.py:67-89 with DetectorGeometry.integrate materials.py:98-124 ---------------------------
+ * Per sample the Monte-Carlo volume integral of (1/(hbar c v tau)) exp(-l/(hbar c v tau))/(4 pi l^2) over the
+ * detector points.  Host-prepared per point: nxm = -l/METER_BY_MEV, bden = 4*pi*l**2, jac = 1 (box), u1**2*sin(u2)
+ * (sphere), u1 (cylinder).  volume_over_n: the geometry's volume factor / n_points; inv_mbm = 1/METER_BY_MEV.
+ * decay_w = float32(rescale*w*integral) (no acceptance factor), scatter_w = float32(rescale*w*surv).
+ * partials: scratch of alpk_vol_int_chunks(n, n_points) * n doubles. */
+uint32_t alpk_vol_int_chunks(uint64_t n, uint32_t n_points);
+int alpk_vol_int(const double* energy, const double* weight, uint64_t n, const alpk_prop_t* h_prop,
+                 const double* nxm, const double* bden, const double* jac, uint32_t n_points,
+                 double volume_over_n, double inv_mbm, float* decay_w32, float* scatter_w32,
+                 double* decay_w64_or_null, double* scatter_w64_or_null, double* partials, void* stream);
+
 /* ---- weighted histogram: np.histogram(x, bins=edges, weights=w) (half-open bins, last bin closed) ------------------ */
 int alpk_hist(const double* x, const double* w64_or_null, const float* w32_or_null, uint64_t n,
               const double* edges, int n_edges, double* hist /* [n_edges-1], accumulated into */, void* stream);

@@ -272,6 +272,54 @@ def propagate(e_a, wgt, ma, decay_width, rescale_factor, det_dist, det_length,
     return {"decay_w64": d64, "scatter_w64": s64, "decay_w": d32, "scatter_w": s32}
 
 
+# ---------------------------------------------------------------------------------------------------------
+# materials.py:51-124 DetectorGeometry + fluxes.py:67-89 propagate_iso_vol_int
+# ---------------------------------------------------------------------------------------------------------
+class DetectorGeometry:
+    def __init__(self, distance_to_source, geometry, params, n_samples, usrc):
+        """usrc: UniformSource -- three blocks of n_samples draws (materials.py:58-60)."""
+        self.l0, self.n_samples, self.geom, self.params = distance_to_source, n_samples, geometry, params
+        u1, u2, u3 = usrc.uniform(0, 1, n_samples), usrc.uniform(0, 1, n_samples), usrc.uniform(0, 1, n_samples)
+        if geometry == "box":                                                        # :64-70
+            self.u1, self.u2, self.u3 = params[0] * (u1 - 0.5), params[1] * (u2 - 0.5), params[2] * (u3 - 0.5)
+        elif geometry == "sphere":                                                   # :71-77
+            self.u1, self.u2, self.u3 = params[0] * u1, np.arccos(1 - 2 * u2), 2 * pi * u3
+        elif geometry == "cylinder":                                                 # :78-84 (azimuth from u3: reference quirk)
+            self.u1, self.u2, self.u3 = params[0] * u1, 2 * pi * u3, params[1] * (u3 - 0.5)
+        else:
+            raise Exception("Geometry %s not found", geometry)
+
+    def integrate(self, f_int):                                                      # :98-124
+        if self.geom == "box":
+            ls = np.sqrt(self.u1 ** 2 + self.u2 ** 2 + (self.u3 - self.l0) ** 2)
+            return (self.params[0] * self.params[1] * self.params[2]) * np.sum(f_int(ls)) / self.n_samples
+        if self.geom == "sphere":
+            ls = np.sqrt(self.u1 ** 2 + self.l0 ** 2 - 2 * self.u1 * self.l0 * np.sin(self.u2) * np.cos(self.u3))
+            return (4 * pi * self.params[0] ** 3 / 3) * np.sum(self.u1 ** 2 * np.sin(self.u2) * f_int(ls)) / self.n_samples
+        ls = np.sqrt(self.u1 ** 2 + self.l0 ** 2 - 2 * self.u1 * self.l0 * np.cos(self.u2) + self.u3 ** 2)
+        return (self.params[1] * pi * self.params[0] ** 2) * np.sum(self.u1 * f_int(ls)) / self.n_samples
+
+
+def propagate_iso_vol_int(e_a, wgt, ma, decay_width, rescale_factor, det_dist, geom):
+    """fluxes.py:67-89.  Returns f64 pre-cast weights and the float32 attributes."""
+    e_a = np.asarray(e_a, dtype=np.float64)
+    wgt = np.asarray(wgt, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        p_a = np.sqrt(e_a ** 2 - ma ** 2)
+        v_a = p_a / e_a
+        boost = e_a / ma
+        tau = boost / decay_width if decay_width > 0.0 else np.inf * np.ones_like(boost)
+        surv = np.array([np.exp(-det_dist / METER_BY_MEV / v_a[i] / tau[i]) for i in range(len(v_a))])
+        vol = []
+        for i in range(len(e_a)):
+            f = lambda x: (1 / METER_BY_MEV / v_a[i] / tau[i]) * np.exp(-x / METER_BY_MEV / v_a[i] / tau[i]) / (4 * pi * x ** 2)
+            vol.append(geom.integrate(f))
+        d64 = rescale_factor * wgt * np.array(vol)
+        s64 = rescale_factor * wgt * surv
+    return {"decay_w64": d64, "scatter_w64": s64, "decay_w": np.asarray(d64, dtype=np.float32),
+            "scatter_w": np.asarray(s64, dtype=np.float32)}
+
+
 def geom_acceptance(det_area, det_dist):                                             # fluxes.py:160
     return det_area / (4 * pi * det_dist ** 2)
 

@@ -372,6 +372,33 @@ def case_decay4():
              axion_energy=fl.axion_energy, decay_w32=np.array(fl.decay_axion_weight), p1=p1, p2=p2, w=w)
 
 
+def case_vol_int():
+    print("propagate_iso_vol_int (box / sphere / cylinder)")
+    W = F.Material("W")
+    pf = np.array([[3.0, 1e9], [40.0, 3e9], [700.0, 1e8]])
+    for tag, geo, params, ma, g in (("volint_box", "box", [1.0, 2.0, 0.5], 1.5, 1e-4), ("volint_sphere", "sphere", [0.8], 1.5, 3e-5),
+                                    ("volint_cyl", "cylinder", [0.6, 1.2], 2.0, 1e-6)):
+        np.random.seed(77)
+        fl = F.FluxComptonIsotropic(pf, W, axion_mass=ma, axion_coupling=g, n_samples=12, **GEOM_DEFAULT)
+        fl.simulate()
+        np.random.seed(78)
+        geom = F.DetectorGeometry(4.0, geo, params, n_samples=700)
+        with f32_cast_bypassed():
+            fl.propagate_iso_vol_int(geom, new_coupling=2 * g)
+            d64 = np.array(fl.decay_axion_weight, dtype=np.float64); s64 = np.array(fl.scatter_axion_weight, dtype=np.float64)
+        fl.propagate_iso_vol_int(geom, new_coupling=2 * g)
+        d32 = np.array(fl.decay_axion_weight); s32 = np.array(fl.scatter_axion_weight)
+        us = O.UniformSource(np.random.RandomState(78))
+        og = O.DetectorGeometry(4.0, geo, params, 700, us)
+        op = O.propagate_iso_vol_int(fl.axion_energy, fl.axion_flux, ma, O.W_ee(2 * g, ma), np.power(2 * g / g, 2), 4.0, og)
+        check(tag + " decay_w f64", op["decay_w64"], d64, 1e-13)
+        check(tag + " scatter_w f64", op["scatter_w64"], s64, 1e-13)
+        check(tag + " decay_w f32", op["decay_w"], d32, 1.3e-7)
+        save(tag, photon_flux=pf, ma=ma, g=g, new_coupling=2 * g, geometry=geo, params=np.array(params), l0=4.0, n_geom=700,
+             geom_uniforms=np.concatenate(us.log), axion_energy=fl.axion_energy, axion_flux=fl.axion_flux,
+             decay_w32=d32, scatter_w32=s32, decay_w64=d64, scatter_w64=s64)
+
+
 if __name__ == "__main__":
     kat_scalars()
     case_primakoff()
@@ -381,4 +408,5 @@ if __name__ == "__main__":
     case_resonance()
     case_pairann()
     case_decay4()
+    case_vol_int()
     print("all golden fixtures written; oracle pinned against the reference")

@@ -475,3 +475,44 @@ def test_scan_matches_oracle(A):
             # decay_prob = 1-exp(-x) cancels for long-lived points: compare with the summed conditioned tolerance
             tol = float(np.sum(np.abs(ew) * (decay_tol(p["decay_w64"], p["scatter_w64"], 1e-9) + 2 * F32)) / max(abs(r), 1e-300))
             assert abs(rates[i, j] - r) <= tol * abs(r) + 1e-300, (i, j, rates[i, j], r, tol)
+
+
+# ---- propagate_iso_vol_int + DetectorGeometry -------------------------------------------------------
+@pytest.mark.parametrize("name", ["volint_box", "volint_sphere", "volint_cyl"])
+def test_propagate_iso_vol_int(A, name):
+    g = load_golden(name)
+    ma, gg, nc = float(g["ma"]), float(g["g"]), float(g["new_coupling"])
+    fl = A.FluxComptonIsotropic(g["photon_flux"], A.Material("W"), axion_mass=ma, axion_coupling=gg, n_samples=12,
+                                keep_f64=True, **GEOM)
+    fl.axion_energy = g["axion_energy"]
+    fl.axion_flux = g["axion_flux"]
+    np.random.seed(78)                                   # the fixture's geometry draws (legacy global RNG, as the reference)
+    geom = A.DetectorGeometry(float(g["l0"]), str(g["geometry"]), list(g["params"]), n_samples=int(g["n_geom"]))
+    fl.propagate_iso_vol_int(geom, new_coupling=nc)
+    assert max_rel(fl.decay_axion_weight_f64, g["decay_w64"]) < TOL
+    assert max_rel(fl.scatter_axion_weight_f64, g["scatter_w64"]) < TOL
+    assert max_rel(fl.decay_axion_weight, g["decay_w32"]) <= F32 and max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    assert fl.decay_axion_weight.dtype == np.float32
+    rate = A.ElectronEventGenerator(fl, A.Material("Ar")).decays(100, 1.0)
+    _, orate = O.decays(g["axion_energy"], g["decay_w32"], 100, 1.0)
+    assert rate == pytest.approx(orate, rel=1e-6)
+    with pytest.raises(Exception, match="closer than 0.0"):
+        A.DetectorGeometry(0.0)
+
+
+def test_propagate_iso_vol_int_large(A):
+    """1e4 samples x 1e4 volume points (the reference needs ~1 s per 100 samples): long-detector limit check --
+    for a thin, distant box the volume integral tends to decay_prob * area/(4 pi L^2) of the plain propagate."""
+    pf = _c2_flux(100)
+    fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=1.5, axion_coupling=1e-6, n_samples=100, seed=4, keep_f64=True,
+                                det_dist=50.0, det_length=0.2, det_area=0.04)
+    fl.simulate()
+    np.random.seed(1)
+    geom = A.DetectorGeometry(50.0, "box", [0.2, 0.2, 0.2], n_samples=10000)
+    fl.propagate_iso_vol_int(geom)
+    vol = np.array(fl.decay_axion_weight_f64)
+    fl.propagate()
+    plain = np.array(fl.decay_axion_weight_f64) * O.geom_acceptance(0.04, 50.0)
+    sel = plain > 1e-3 * plain.max()
+    # same physics up to O(det_length/det_dist) geometry corrections and the MC error of 1e4 points
+    assert np.max(np.abs(vol[sel] / plain[sel] - 1)) < 0.03

@@ -207,3 +207,14 @@ def test_histogram_semantics():
     xr, wr = rs.uniform(-1, 11, 5000), rs.uniform(0.5, 1.5, 5000)
     for edges in (np.linspace(0, 10, 33), np.array([0.0, 0.3, 4.0, 4.5, 10.0])):
         np.testing.assert_allclose(O.histogram(xr, wr, edges), np.histogram(xr, bins=edges, weights=wr)[0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["volint_box", "volint_sphere", "volint_cyl"])
+def test_propagate_iso_vol_int(name):
+    g = load_golden(name)
+    ma, gg, nc = float(g["ma"]), float(g["g"]), float(g["new_coupling"])
+    geom = O.DetectorGeometry(float(g["l0"]), str(g["geometry"]), list(g["params"]), int(g["n_geom"]),
+                              O.UniformSource(g["geom_uniforms"]))
+    p = O.propagate_iso_vol_int(g["axion_energy"], g["axion_flux"], ma, O.W_ee(nc, ma), np.power(nc / gg, 2), 4.0, geom)
+    assert max_rel(p["decay_w64"], g["decay_w64"]) < 1e-14 and max_rel(p["scatter_w64"], g["scatter_w64"]) < 1e-14
+    assert max_rel(p["decay_w"], g["decay_w32"]) == 0.0
