@@ -9,7 +9,7 @@ ElectronEventGenerator, Material, the decay widths and the constants -- same nam
 from .constants import *            # noqa: F401,F403
 from .materials import Material, DetectorGeometry     # noqa: F401
 from .decay import W_gg, W_ee, W_ff, W_gg_loop, fp2, b1   # noqa: F401
-from .photon_xs import AbsCrossSection                   # noqa: F401
+from .photon_xs import AbsCrossSection, ALPPairProdutionCrossSection   # noqa: F401
 from .vectors import Vector3, LorentzVector, LorentzVectorArray   # noqa: F401
 from .fluxes import *               # noqa: F401,F403
 from .generators import PhotonEventGenerator, ElectronEventGenerator   # noqa: F401

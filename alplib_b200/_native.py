@@ -96,6 +96,7 @@ _SIGNATURES = {
     "alpk_propagate": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _P, _P], _I),
     "alpk_decays": ([_P, _P, _U64, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_scatter_events": ([_I, _P, _P, _U64, C.POINTER(_D), _D, _D, C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_pair_events": ([_P, _P, _U64, _P, _P, _I, _D, _D, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_abs_sigma_mev": ([_P, _P, _I, _P, _U64, _P, _P], _I),
     "alpk_primakoff": ([_P, _P, _U64, _P, _P, _I, _D, _D, _D, _P, _P, _P], _I),
     "alpk_compton_rows": ([_P, _P, _U64, _P, _P, _I, C.POINTER(ComptonT), _P, _P], _I),

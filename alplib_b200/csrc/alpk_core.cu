@@ -9,6 +9,8 @@ using namespace alp;
 
 namespace alpk {
 
+constexpr int kMaxTable = 512;
+
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;      // kernels launched through this library (bench.py reports it)
 
@@ -121,6 +123,30 @@ scatter_kernel(const double* __restrict__ energy, const float* __restrict__ w32,
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
+// pair production a e- -> e- e+ e- (generators.py:33-39, photon_xs.py:95-125): tabulated cross section,
+// heaviside(E-2me,0) * 10**interp(log10 E; left=-inf, right=fp[-1])
+__global__ void __launch_bounds__(kThreads)
+pair_kernel(const double* __restrict__ energy, const float* __restrict__ w32, uint64_t n,
+            const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
+            double lead, double mbm2, EventConst c, double* __restrict__ event_w, double* __restrict__ partials) {
+    __shared__ double red[32];
+    __shared__ double s_e[kMaxTable], s_xs[kMaxTable];
+    for (int i = threadIdx.x; i < n_table; i += blockDim.x) { s_e[i] = __ldg(log10_e + i); s_xs[i] = __ldg(log10_xs + i); }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ea = __ldg(energy + i);
+        const double y = interp(log10(ea), s_e, s_xs, n_table, -INFINITY, s_xs[n_table - 1]);
+        const double xs = heaviside(ea - 2 * kME, 0.0) * pow(10.0, y);            // photon_xs.py:122-125
+        const double ev = (((lead * xs) * mbm2) * (double)__ldg(w32 + i)) * heaviside(ea - c.threshold, 1.0);
+        if (event_w) event_w[i] = ev;
+        acc += ev;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
 __global__ void __launch_bounds__(kThreads)
 sum_kernel(const double* __restrict__ x, uint64_t n, double* __restrict__ partials) {
     __shared__ double red[32];
@@ -134,7 +160,6 @@ sum_kernel(const double* __restrict__ x, uint64_t n, double* __restrict__ partia
 // ---------------------------------------------------------------------------------------------------------------
 // table lookup + Primakoff rows + Compton rows (one thread per flux row; the XCOM table lives in shared memory)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kMaxTable = 512;
 
 __device__ __forceinline__ void stage_table(double* s_e, double* s_xs, const double* __restrict__ log10_e,
                                             const double* __restrict__ log10_xs, int n_table) {
@@ -294,6 +319,19 @@ ALPK_EXPORT int alpk_scatter_events(int kind, const double* energy, const float*
     const int grid = grid_for(n, kThreads * 2, 8);
     scatter_kernel<<<grid, kThreads, 0, st>>>(energy, scatter_w32, n, sc, to_event(h_ev), event_w, scratch);
     if (check_launch("alpk_scatter_events")) return 1;
+    return finalize_sum(scratch, grid, rate, st);
+}
+
+ALPK_EXPORT int alpk_pair_events(const double* energy, const float* scatter_w32, uint64_t n, const double* log10_e,
+                                 const double* log10_xs, int n_table, double lead, double mbm2, const alpk_event_t* h_ev,
+                                 double* event_w, double* rate, double* scratch, void* stream) {
+    if (!h_ev || !rate || !scratch || !log10_e || !log10_xs) { set_error("alpk_pair_events: null argument"); return 2; }
+    if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_pair_events: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(rate, 0, sizeof(double), st); return 0; }
+    const int grid = grid_for(n, kThreads * 2, 8);
+    pair_kernel<<<grid, kThreads, 0, st>>>(energy, scatter_w32, n, log10_e, log10_xs, n_table, lead, mbm2, to_event(h_ev), event_w, scratch);
+    if (check_launch("alpk_pair_events")) return 1;
     return finalize_sum(scratch, grid, rate, st);
 }
 

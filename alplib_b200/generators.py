@@ -17,6 +17,7 @@ from . import params as P
 from .constants import METER_BY_MEV
 from .fluxes import AxionFlux, _draw_seed
 from .materials import Material
+from .photon_xs import ALPPairProdutionCrossSection
 from .vectors import LorentzVectorArray
 
 
@@ -92,7 +93,31 @@ class _EventGenerator:
 
 
 class ElectronEventGenerator(_EventGenerator):
-    """ALP-electron coupling: decay and inverse-Compton scattering rates (generators.py:18-52)."""
+    """ALP-electron coupling: decay, inverse-Compton and pair-production rates (generators.py:18-52)."""
+
+    def __init__(self, flux: AxionFlux, detector: Material):
+        super().__init__(flux, detector)
+        self.pair_xs = ALPPairProdutionCrossSection(detector, ma=flux.ma)        # generators.py:31
+
+    def pair_production(self, ge, ntargets, days_exposure, threshold):
+        """days*S_PER_DAY*(ntargets/area)*ge^2*sigma_pair(E)*METER_BY_MEV^2*scatter_w*heaviside (generators.py:33-39)."""
+        fl = self.flux
+        fl._ensure_production()
+        fl._ensure_propagated()
+        rt = fl._rt
+        n = 0 if fl._E is None else int(fl._E.shape[0])
+        if fl._S32 is None or int(fl._S32.shape[0]) != n:
+            raise ValueError("propagate() must run first: scatter_axion_weight does not match axion_energy")
+        ev = P.event_params(days_exposure, threshold)
+        lead = days_exposure * P.S_PER_DAY * (ntargets / fl.det_area) * np.power(ge, 2)
+        with rt.activate():
+            le, lx, nt = self.pair_xs.device_table(rt)
+            rate = rt.empty(1)
+            evw = rt.empty(n) if self.materialize_weights else None
+            N.call("alpk_pair_events", N.ptr(fl._E), N.ptr(fl._S32), n, N.ptr(le), N.ptr(lx), nt, float(lead),
+                   float(METER_BY_MEV**2), C.byref(ev), N.ptr(evw), N.ptr(rate), N.ptr(rt.scratch), rt.stream())
+        self._store("pair", evw)
+        return np.float64(rate.item())
 
     def compton(self, ge, ma, ntargets, days_exposure, threshold):
         return self._scatter(0, P.icompton_consts(ma, ge, self.det_z), ntargets, days_exposure, threshold)

@@ -68,3 +68,28 @@ class AbsCrossSection:
 
     def mu(self, E, n):
         return self.sigma_cm2(E) * n
+
+
+class ALPPairProdutionCrossSection:
+    """Tabulated ALP pair-production cross section a e- -> e- e+ e- on argon, rescaled by (Z/18)^2 (reference:
+    photon_xs.py:95-125, name kept as spelled there).  The table is picked by the closest mass control point at or
+    below `ma`, exactly as the reference picks it."""
+
+    def __init__(self, material: Material, ma=0.1):
+        self.xs_dim = 1e-24
+        self.mat_name = material.mat_name
+        mass_extension = ["100keV", "400keV", "500keV", "600keV", "700keV", "800keV", "900keV", "1MeV", "1.1MeV"]
+        mass_control_points = [0.1, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1]
+        mass_idx = np.arange(0, 9, 1)
+        idx_closest = np.clip(int(np.interp(ma, mass_control_points, mass_idx)), a_min=0, a_max=9)
+        self.argon_rescale = np.power(material.z[0]/18, 2)
+        self.xs_data = _load_table(data_path("alp_pair_production", "pair_production_xs_table_" + mass_extension[idx_closest] + ".txt"), 0)
+        self.log10_e = np.log10(self.xs_data[:, 0])
+        self.log10_xs_mev = np.log10(self.argon_rescale * self.xs_dim * self.xs_data[:, 1] / MEV2_CM2)
+        self._dev = {}
+
+    def device_table(self, rt: Runtime):
+        t = self._dev.get(rt.index)
+        if t is None:
+            t = self._dev[rt.index] = (rt.upload(self.log10_e), rt.upload(self.log10_xs_mev), int(self.log10_e.shape[0]))
+        return t

@@ -89,6 +89,13 @@ int alpk_scatter_events(int kind, const double* energy, const float* scatter_w32
                         const double* h_xs, double prefactor, double mbm2, const alpk_event_t* h_ev,
                         double* event_w_or_null, double* rate, double* scratch, void* stream);
 
+/* pair production a e- -> e- e+ e-: ElectronEventGenerator.pair_production (generators.py:33-39) with the tabulated
+ * ALPPairProdutionCrossSection.sigma_mev (photon_xs.py:122-125): heaviside(E-2me,0)*10**interp(log10 E; left=-inf).
+ * log10_xs = log10(argon_rescale*xs_dim*sigma_i/MEV2_CM2); lead = days*S_PER_DAY*(ntargets/det_area)*ge**2. */
+int alpk_pair_events(const double* energy, const float* scatter_w32, uint64_t n, const double* log10_e,
+                     const double* log10_xs, int n_table, double lead, double mbm2, const alpk_event_t* h_ev,
+                     double* event_w_or_null, double* rate, double* scratch, void* stream);
+
 /* ---- photon absorption table: photon_xs.py:48-49 (AbsCrossSection.sigma_mev) --------------------------------- */
 int alpk_abs_sigma_mev(const double* log10_e, const double* log10_xs, int n_table, const double* energy, uint64_t n,
                        double* sigma_mev, void* stream);

@@ -572,6 +572,31 @@ def inverse_primakoff_events(axion_energy, scatter_axion_weight, gagamma, ma, nt
     return w, np.sum(w)
 
 
+class ALPPairProdutionCrossSection:                                                  # photon_xs.py:95-125
+    def __init__(self, material, ma=0.1):
+        ext = ["100keV", "400keV", "500keV", "600keV", "700keV", "800keV", "900keV", "1MeV", "1.1MeV"]
+        cp = [0.1, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1]
+        idx = np.clip(int(np.interp(ma, cp, np.arange(0, 9, 1))), a_min=0, a_max=9)
+        self.argon_rescale = np.power(material.z[0] / 18, 2)
+        self.xs_dim = 1e-24
+        self.xs_data = np.genfromtxt(os.path.join(_DATA_DIR, "alp_pair_production", "pair_production_xs_table_" + ext[idx] + ".txt"))
+
+    def sigma_mev(self, E):
+        with np.errstate(all="ignore"):
+            return np.heaviside(E - 2 * M_E, 0.0) * np.power(10, np.interp(
+                np.log10(E), np.log10(self.xs_data[:, 0]),
+                np.log10(self.argon_rescale * self.xs_dim * self.xs_data[:, 1] / MEV2_CM2), left=-np.inf))
+
+
+def pair_production_events(axion_energy, scatter_axion_weight, pair_xs, ge, ntargets, det_area, days_exposure,
+                           threshold):                                               # generators.py:33-39
+    e = np.asarray(axion_energy, dtype=np.float64)
+    w = days_exposure * S_PER_DAY * (ntargets / det_area) \
+        * np.power(ge, 2) * pair_xs.sigma_mev(e) \
+        * METER_BY_MEV ** 2 * scatter_axion_weight * np.heaviside(e - threshold, 1.0)
+    return w, np.sum(w)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # generators.py:94-128 + cross_section_mc.py:510-544  simulate_decay_4vectors (forward parents, theta = 0)
 # ---------------------------------------------------------------------------------------------------------

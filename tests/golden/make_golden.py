@@ -225,6 +225,7 @@ def case_compton():
         gen = G.ElectronEventGenerator(fl, Ar)
         r_dec = gen.decays(100, 5.0); dw = np.array(gen.decay_weights)
         r_com = gen.compton(g, ma, 1e27, 100, 5.0); sw = np.array(gen.scatter_weights)
+        r_pair = gen.pair_production(g, 1e27, 100, 1.0); pw = np.array(gen.pair_weights)
         us = O.UniformSource(np.random.RandomState(2024))
         oE, oF = O.compton_simulate(pf, ma, g, 74, oabs, 64, us)
         check(tag + " E", oE, fl.axion_energy, 0)
@@ -238,10 +239,14 @@ def case_compton():
         check(tag + " decays()", orate, r_dec, 1e-7)
         _, ocom = O.compton_events(oE, op["scatter_w"], g, ma, 1e27, 0.04, 18, 100, 5.0)
         check(tag + " compton()", ocom, r_com, 1e-7)
+        opw, opair = O.pair_production_events(oE, op["scatter_w"], O.ALPPairProdutionCrossSection(O.Material("Ar"), ma), g,
+                                              1e27, 0.04, 100, 1.0)
+        check(tag + " pair_production()", opair, r_pair, 1e-12)
         save(tag, photon_flux=pf, ma=ma, g=g, n_samples=64, loop_decay=loop, is_isotropic=iso,
              uniforms=np.concatenate(us.log), axion_energy=fl.axion_energy, axion_flux=fl.axion_flux,
              decay_w32=d32, scatter_w32=s32, decay_w64=d64, scatter_w64=s64, width=width,
-             decays_100_5=r_dec, compton_1e27_100_5=r_com, decay_weights=dw, scatter_weights=sw)
+             decays_100_5=r_dec, compton_1e27_100_5=r_com, decay_weights=dw, scatter_weights=sw,
+             pair_1e27_100_1=r_pair, pair_weights=pw)
 
 
 def case_propagate_misc():

@@ -117,6 +117,10 @@ def test_compton_chain_injected(A, name):
         assert r_dec == pytest.approx(float(g["decays_100_5"]), rel=1e-4 if name == "compton_loop" else 1e-6)
     if "scatter_weights" in g:
         assert max_rel(gen.scatter_weights, g["scatter_weights"], floor=1e-300) < 2 * F32
+    if "pair_weights" in g:
+        r_pair = gen.pair_production(gg, 1e27, 100, 1.0)
+        assert r_pair == pytest.approx(float(g["pair_1e27_100_1"]), rel=1e-6) and r_pair > 0
+        assert max_rel(gen.pair_weights, g["pair_weights"], floor=1e-300) < 2 * F32
     if "new_coupling" in g:
         fl.propagate(new_coupling=float(g["new_coupling"]))
         assert_decay_close(fl.decay_axion_weight_f64 * GA, g["decay_w64_new"], g["scatter_w64_new"], TOL)

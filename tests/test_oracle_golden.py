@@ -110,6 +110,10 @@ def test_compton_chain(name):
     assert max_rel(r, g["decays_100_5"]) < 1e-15
     _, r = O.compton_events(E, p["scatter_w"], gg, ma, 1e27, 0.04, 18, 100, 5.0)
     assert max_rel(r, g["compton_1e27_100_5"]) < 1e-15
+    if "pair_weights" in g:
+        pw, r = O.pair_production_events(E, p["scatter_w"], O.ALPPairProdutionCrossSection(O.Material("Ar"), ma), gg,
+                                         1e27, 0.04, 100, 1.0)
+        assert max_rel(pw, g["pair_weights"]) == 0.0 and r > 0
 
 
 def test_katc_values():
