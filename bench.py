@@ -288,7 +288,9 @@ def run_gpu(args):
     e2e = {}
     e2e_steps = max(3, min(args.steps, 30))
     for tag, fused in (("e2e", False), ("e2e_fused", True)):
-        for _ in range(4):
+        # warm-up: the first eager steps pay cudaMalloc; the first ~30 deferred steps after a materialising phase show
+        # allocator/driver hiccups of several ms every other step (tools/dbg_fused.py) before settling
+        for _ in range(40 if fused else 8):
             res = e2e_step(fused)
         del res
         barrier()
