@@ -251,7 +251,7 @@ vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __re
         if (live) {
 #pragma unroll 4
             for (uint32_t k = 0; k < cnt; ++k) {
-                const double e = FAST ? exp(s_x[k] * c) : exp((s_x[k] / va) / tau);      // :85
+                const double e = FAST ? exp_fast(s_x[k] * c) : exp((s_x[k] / va) / tau);      // :85
                 acc += s_j[k] * ((A * e) / s_b[k]);
             }
         }

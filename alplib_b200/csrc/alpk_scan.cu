@@ -164,8 +164,8 @@ scan_kernel(const ScanArgs a) {
             double surv, dec;
             if (FAST) {
                 const double t = s_t[k];
-                surv = exp(k1 * t);
-                dec = 1 - exp(k2 * t);
+                surv = exp_fast(k1 * t);
+                dec = 1 - exp_fast(k2 * t);
             } else {
                 const double va = s_t[k];
                 const double tau = width > 0.0 ? s_b[k] / width : INFINITY;      // fluxes.py:51

@@ -36,6 +36,10 @@ void hc_philox(uint64_t seed, uint32_t tag, uint32_t row, uint64_t n, int two, d
     }
 }
 
+void hc_exp_fast(const double* x, uint64_t n, double* out) {
+    for (uint64_t i = 0; i < n; ++i) out[i] = exp_fast(x[i]);
+}
+
 void hc_abs_sigma(const double* le, const double* lx, int nt, const double* e, uint64_t n, double* out) {
     for (uint64_t i = 0; i < n; ++i) out[i] = abs_sigma_mev(e[i], le, lx, nt);
 }
