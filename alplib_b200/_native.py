@@ -71,12 +71,28 @@ def build(force=False, verbose=False):
         if all(os.path.getmtime(d) <= t for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # one nvcc per translation unit, in parallel, then link
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    procs = []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        procs.append((obj, subprocess.Popen([nvcc] + cflags + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+    objs, log, failed = [], "", False
+    for obj, pr in procs:
+        out, _ = pr.communicate()
+        log += out
+        failed |= pr.returncode != 0
+        objs.append(obj)
     if verbose:
-        sys.stderr.write(r.stderr)
+        sys.stderr.write(log)
+    if failed:
+        raise AlpkError("nvcc failed:\n" + log)
+    r = subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + objs, capture_output=True, text=True)
     if r.returncode != 0:
-        raise AlpkError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise AlpkError("link failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 
@@ -101,14 +117,14 @@ _SIGNATURES = {
     "alpk_primakoff": ([_P, _P, _U64, _P, _P, _I, _D, _D, _D, _P, _P, _P], _I),
     "alpk_compton_rows": ([_P, _P, _U64, _P, _P, _I, C.POINTER(ComptonT), _P, _P], _I),
     "alpk_compton_samples": ([_P, _U64, _U32, _P, C.POINTER(ComptonT), _P, _U64, _P, _P,
-                              C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
+                              C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),
     "alpk_brem_rows": ([_P, _P, _U64, _P, _P, _U64, _P, _P, _I, _P, _P, _I, _P, _P, C.POINTER(BremT), _P, _P, _P], _I),
     "alpk_brem_samples": ([_P, _U64, _U32, _P, C.POINTER(BremT), _P, _U64, _P, _P,
-                           C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
+                           C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),
     "alpk_resonance_sum": ([_P, _P, _I, _D, _D, _D, _U64, _P, _U64, _P, _P, _P], _I),
     "alpk_pairann_rows": ([_P, _P, _U64, C.POINTER(PairAnnT), _P, _P], _I),
     "alpk_pairann_samples": ([_P, _U64, _U32, _P, C.POINTER(PairAnnT), _P, _U64, _P, _P,
-                              C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P], _I),
+                              C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),
     "alpk_decay_parent_rows": ([_P, _P, _U64, _D, C.POINTER(EventT), _U32, _P, _P], _I),
     "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _I, _P, _P, _P, _P], _I),
     "alpk_scan_tiles": ([_U32, _U32], _U32),

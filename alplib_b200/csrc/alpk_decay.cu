@@ -121,17 +121,6 @@ decay2body_kernel(const DecayArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // weighted histogram, np.histogram(x, bins=edges, weights=w): bin k = [edges[k], edges[k+1]), last bin closed
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int find_bin(double x, const double* edges, int n_edges) {
-    if (!(x >= edges[0]) || !(x <= edges[n_edges - 1])) return -1;    // also drops NaN
-    if (x == edges[n_edges - 1]) return n_edges - 2;
-    int lo = 0, hi = n_edges - 1;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (x >= edges[mid]) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 template <bool SMEM>
 __global__ void __launch_bounds__(kThreads)
 hist_kernel(const double* __restrict__ x, const double* __restrict__ w64, const float* __restrict__ w32, uint64_t n,

@@ -143,12 +143,13 @@ ALPK_EXPORT int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint
                                   double* out_energy, double* out_flux,
                                   const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
                                   double* decay_w64, double* scatter_w64,
-                                  const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream) {
+                                  const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
+                                     const double* hist_edges, int n_edges, double* hist, void* stream) {
     if (!h_par) { set_error("alpk_brem_samples: null argument"); return 2; }
     return launch_chain<BremProd>("alpk_brem_samples", row_table, n_rows, n_samples, row_ids, to_brem(h_par),
                                   (h_prop && h_prop->fast) ? 1 : 0, uniforms,
                                   seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64, scatter_w64,
-                                  h_ev, event_w, rate, scratch, stream);
+                                  h_ev, event_w, rate, scratch, hist_edges, n_edges, hist, stream);
 }
 
 ALPK_EXPORT int alpk_resonance_sum(const double* pos_e, const double* pos_f, int n_pos, double e_res, double e_max,
@@ -179,10 +180,11 @@ ALPK_EXPORT int alpk_pairann_samples(const double* row_table, uint64_t n_rows, u
                                      double* out_energy, double* out_flux,
                                      const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
                                      double* decay_w64, double* scatter_w64,
-                                     const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream) {
+                                     const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
+                                     const double* hist_edges, int n_edges, double* hist, void* stream) {
     if (!h_par) { set_error("alpk_pairann_samples: null argument"); return 2; }
     return launch_chain<PairProd>("alpk_pairann_samples", row_table, n_rows, n_samples, row_ids, to_pair(h_par),
                                   (h_prop && h_prop->fast) ? 1 : 0, uniforms,
                                   seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64, scatter_w64,
-                                  h_ev, event_w, rate, scratch, stream);
+                                  h_ev, event_w, rate, scratch, hist_edges, n_edges, hist, stream);
 }

@@ -30,6 +30,7 @@ struct ChainArgs {
     alp::PropConst prop; float* d32; float* s32; double* d64; double* s64;
     alp::EventConst ev; double* event_w; double* partials;
     uint32_t tile_elems;
+    const double* hist_edges; int n_edges; double* hist;     // optional fused weighted histogram of E_a
 };
 
 template <class Prod, bool INJECT, int STAGE, bool FAST>   // STAGE 0: production; 1: + propagate; 2: + decays
@@ -39,6 +40,14 @@ chain_kernel(const ChainArgs<Prod> a) {
     constexpr int NP = Prod::NP;
     __shared__ double s_rows[kStageRows * NP];
     __shared__ double red[32];
+    extern __shared__ double s_hist_mem[];           // [n_edges] edges + [n_edges-1] privatised bins (only if a.hist)
+    double* s_edges = s_hist_mem;
+    double* s_bins = s_hist_mem + a.n_edges;
+    if (a.hist) {
+        for (int i = threadIdx.x; i < a.n_edges; i += blockDim.x) s_edges[i] = __ldg(a.hist_edges + i);
+        for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) s_bins[i] = 0.0;
+        // (made visible by the __syncthreads of the first tile)
+    }
     const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
     const uint32_t tile_elems = a.tile_elems;        // kTile, or fewer when rows are so short that a full tile would
     const uint64_t n_tiles = (n + tile_elems - 1) / tile_elems;   // touch more than kStageRows of them
@@ -109,6 +118,12 @@ chain_kernel(const ChainArgs<Prod> a) {
                     evv[j] = decay_event_weight(e[j], d32v[j], a.ev);
                     if (j == 0 || have2) acc += evv[j];
                 }
+                if (a.hist && (j == 0 || have2)) {
+                    // np.histogram(E_a, bins=edges, weights=<weight of the last fused stage>)
+                    const double hw = STAGE >= 2 ? evv[j] : (STAGE == 1 ? (double)d32v[j] : f[j]);
+                    const int bin = find_bin(e[j], s_edges, a.n_edges);
+                    if (bin >= 0 && hw != 0.0) atomicAdd(s_bins + bin, hw);
+                }
             }
             if (have2) {
                 if (a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
@@ -137,6 +152,13 @@ chain_kernel(const ChainArgs<Prod> a) {
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) a.partials[blockIdx.x] = acc;
     }
+    if (a.hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) {
+            const double v = s_bins[i];
+            if (v != 0.0) atomicAdd(a.hist + i, v);
+        }
+    }
 }
 
 alp::PropConst to_prop(const alpk_prop_t* p);
@@ -149,7 +171,7 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
                  const typename Prod::Globals& g, int fast_mode, const double* uniforms, uint64_t seed, double* out_energy,
                  double* out_flux, const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32, double* decay_w64,
                  double* scatter_w64, const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
-                 void* stream) {
+                 const double* hist_edges, int n_edges, double* hist, void* stream) {
     if (h_ev && (!h_prop || !rate || !scratch)) { set_error("%s: events need prop, rate and scratch", what); return 2; }
     if (n_samples == 0 || n_samples > 0x7fffffffu - kTile) { set_error("%s: n_samples out of range", what); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -167,6 +189,13 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const int stage = h_ev ? 2 : (h_prop ? 1 : 0);
     if (h_prop) { a.prop = to_prop(h_prop); a.d32 = decay_w32; a.s32 = scatter_w32; a.d64 = decay_w64; a.s64 = scatter_w64; }
     if (h_ev) { a.ev = to_event(h_ev); a.event_w = event_w; a.partials = scratch; }
+    size_t smem = 0;
+    if (hist) {
+        if (!hist_edges || n_edges < 2) { set_error("%s: histogram needs >= 2 edges", what); return 2; }
+        smem = (size_t)(2 * n_edges - 1) * sizeof(double);
+        if (smem > 40 * 1024) { set_error("%s: fused histogram supports at most %d edges (use alpk_hist)", what, (40 * 1024 / 8 + 1) / 2); return 2; }
+        a.hist_edges = hist_edges; a.n_edges = n_edges; a.hist = hist;
+    }
     // rows per tile <= tile/n_samples + 2 must fit the shared-memory stage
     uint64_t te = (uint64_t)(kStageRows - 2) * n_samples;
     a.tile_elems = (uint32_t)(te >= (uint64_t)kTile ? (uint64_t)kTile : (te < 2 ? 2 : (te & ~1ull)));
@@ -174,10 +203,10 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const bool inj = uniforms != nullptr;
     const bool fast = fast_mode != 0;
 #define ALPK_CHAIN_CASE(S)                                                                                   \
-    if (inj) { if (fast) chain_kernel<Prod, true, S, true><<<grid, kThreads, 0, st>>>(a);                     \
-               else chain_kernel<Prod, true, S, false><<<grid, kThreads, 0, st>>>(a); }                        \
-    else { if (fast) chain_kernel<Prod, false, S, true><<<grid, kThreads, 0, st>>>(a);                        \
-           else chain_kernel<Prod, false, S, false><<<grid, kThreads, 0, st>>>(a); }
+    if (inj) { if (fast) chain_kernel<Prod, true, S, true><<<grid, kThreads, smem, st>>>(a);                     \
+               else chain_kernel<Prod, true, S, false><<<grid, kThreads, smem, st>>>(a); }                        \
+    else { if (fast) chain_kernel<Prod, false, S, true><<<grid, kThreads, smem, st>>>(a);                        \
+           else chain_kernel<Prod, false, S, false><<<grid, kThreads, smem, st>>>(a); }
     if (stage == 0) { ALPK_CHAIN_CASE(0) } else if (stage == 1) { ALPK_CHAIN_CASE(1) } else { ALPK_CHAIN_CASE(2) }
 #undef ALPK_CHAIN_CASE
     if (check_launch(what)) return 1;

@@ -48,6 +48,19 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return v;
 }
 
+// np.histogram bin lookup: bin k = [edges[k], edges[k+1]), last bin closed; -1 outside (also NaN)
+__device__ __forceinline__ int find_bin(double x, const double* edges, int n_edges) {
+    if (!(x >= edges[0]) || !(x <= edges[n_edges - 1])) return -1;    // also drops NaN
+    if (x == edges[n_edges - 1]) return n_edges - 2;
+    int lo = 0, hi = n_edges - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= edges[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+
 // Stage `nrows` records of `NP` doubles starting at row r0 of a row-major table into shared memory.
 template <int NP>
 __device__ __forceinline__ void stage_rows(double* dst, const double* __restrict__ table, uint64_t r0, int nrows) {

@@ -376,13 +376,15 @@ class _ChainFlux(AxionFlux):
     decay_width = _width_e
     propagate_iso_vol_int = _vol_int_e
 
-    def _launch_samples(self, E, F, prop, ev, d32=None, s32=None, d64=None, s64=None, evw=None, rate=None):
+    def _launch_samples(self, E, F, prop, ev, d32=None, s32=None, d64=None, s64=None, evw=None, rate=None,
+                        hist_edges=None, hist=None):
         table, n_rows, ns, d_ids, par, d_u, seed = self._rows
         rt = self._rt
         N.call(self._SAMPLES_FN, N.ptr(table), n_rows, ns, N.ptr(d_ids), C.byref(par), N.ptr(d_u),
                C.c_uint64(seed), N.ptr(E), N.ptr(F),
                C.byref(prop) if prop is not None else None, N.ptr(d32), N.ptr(s32), N.ptr(d64), N.ptr(s64),
-               C.byref(ev) if ev is not None else None, N.ptr(evw), N.ptr(rate), N.ptr(rt.scratch), rt.stream())
+               C.byref(ev) if ev is not None else None, N.ptr(evw), N.ptr(rate), N.ptr(rt.scratch),
+               N.ptr(hist_edges), 0 if hist_edges is None else int(hist_edges.shape[0]), N.ptr(hist), rt.stream())
 
     def _produce(self):
         self._pending_production = None
@@ -409,9 +411,11 @@ class _ChainFlux(AxionFlux):
             self._launch_samples(None, None, self._pending_prop, ev, rate=rate)
         return rate
 
-    def chain(self, days_exposure, threshold, new_coupling=None, materialize=True):
+    def chain(self, days_exposure, threshold, new_coupling=None, materialize=True, hist_edges=None, hist=None):
         """One-kernel production -> propagate -> decays.  With materialize=True also fills axion_energy/axion_flux/
-        decay_axion_weight/scatter_axion_weight (device) and returns (rate tensor, event-weight tensor)."""
+        decay_axion_weight/scatter_axion_weight (device) and returns (rate tensor, event-weight tensor).
+        hist_edges (array or CUDA tensor): also accumulate the event-weighted E_a spectrum (np.histogram semantics)
+        in the same pass; it is added into `hist` (CUDA tensor) or returned as `self.last_hist`."""
         if self._rows is None:
             raise RuntimeError("simulate() must be called first")
         width, rescale = self._width_rescale(new_coupling)
@@ -421,17 +425,22 @@ class _ChainFlux(AxionFlux):
         n = self._rows[1] * self._rows[2]
         with rt.activate():
             rate = rt.empty(1)
+            hk = {}
+            if hist_edges is not None:
+                ed = hist_edges if torch.is_tensor(hist_edges) else rt.upload(np.asarray(hist_edges, dtype=np.float64))
+                self.last_hist = hist if hist is not None else rt.zeros(int(ed.shape[0]) - 1)
+                hk = dict(hist_edges=ed, hist=self.last_hist)
             if materialize:
                 E, F = rt.empty(n), rt.empty(n)
                 d32, s32 = rt.empty(n, torch.float32), rt.empty(n, torch.float32)
                 evw = rt.empty(n)
-                self._launch_samples(E, F, prop, ev, d32=d32, s32=s32, evw=evw, rate=rate)
+                self._launch_samples(E, F, prop, ev, d32=d32, s32=s32, evw=evw, rate=rate, **hk)
                 self._pending_production = None
                 self._pending_prop = None
                 self._set_production(E, F)
                 self._D32, self._S32 = d32, s32
                 return rate, evw
-            self._launch_samples(None, None, prop, ev, rate=rate)
+            self._launch_samples(None, None, prop, ev, rate=rate, **hk)
             return rate, None
 
     def _width_rescale(self, new_coupling):

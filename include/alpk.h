@@ -123,13 +123,17 @@ int alpk_compton_rows(const double* e_gamma, const double* phi_gamma, uint64_t n
 /* Per-sample kernel.  n = n_rows*n_samples samples, row-major (all samples of row 0, then row 1, ...).
  * Outputs (each may be NULL): out_energy/out_flux f64 (axion_energy/axion_flux), and -- when h_prop != NULL -- the
  * fused propagate (decay_w32/scatter_w32, optional f64 pre-cast weights) and -- when h_ev != NULL too -- the fused
- * decays() event weights and total rate.  row_ids: global row index per table row for the Philox key (NULL = 0..). */
+ * decays() event weights and total rate.  row_ids: global row index per table row for the Philox key (NULL = 0..).
+ * hist != NULL: also accumulate np.histogram(E_a, bins=hist_edges[n_edges], weights=w) into hist[n_edges-1] with
+ * per-CTA privatised bins in shared memory (w = the last fused stage's weight: event weight, else decay_w32, else
+ * the production weight).  Same trailing arguments for alpk_brem_samples / alpk_pairann_samples. */
 int alpk_compton_samples(const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
                          const alpk_compton_t* h_par, const double* uniforms, uint64_t seed,
                          double* out_energy, double* out_flux,
                          const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
                          double* decay_w64, double* scatter_w64,
-                         const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream);
+                         const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
+                         const double* hist_edges, int n_edges, double* hist, void* stream);
 
 /* ---- a -> gamma gamma decay MC: generators.py:94-128, cross_section_mc.py:510-544, 669-685 ------------------------------
  * parents: energy[n_parents] f64 and decay_w32[n_parents]; n_samples decays each, parent-major order.
@@ -176,7 +180,8 @@ int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint32_t n_sampl
                       double* out_energy, double* out_flux,
                       const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
                       double* decay_w64, double* scatter_w64,
-                      const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream);
+                      const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
+                         const double* hist_edges, int n_edges, double* hist, void* stream);
 
 /* ---- resonant production: fluxes.py:421-445.  *out_sum = sum_i Phi_p(E_i) * track_length_prob(E_i, E_res, t_i) over
  * n_samples draws (E_i, t_i) ~ U(E_res, E_max) x U(0, max_t); the caller applies the scalar prefactors (:441-442).
@@ -205,7 +210,8 @@ int alpk_pairann_samples(const double* row_table, uint64_t n_rows, uint32_t n_sa
                          double* out_energy, double* out_flux,
                          const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32,
                          double* decay_w64, double* scatter_w64,
-                         const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch, void* stream);
+                         const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
+                         const double* hist_edges, int n_edges, double* hist, void* stream);
 
 /* ---- propagate_iso_vol_int: fluxes.py:67-89 with DetectorGeometry.integrate materials.py:98-124 ---------------------------
  * Per sample the Monte-Carlo volume integral of (1/(hbar c v tau)) exp(-l/(hbar c v tau))/(4 pi l^2) over the

@@ -520,3 +520,22 @@ def test_propagate_iso_vol_int_large(A):
     sel = plain > 1e-3 * plain.max()
     # same physics up to O(det_length/det_dist) geometry corrections and the MC error of 1e4 points
     assert np.max(np.abs(vol[sel] / plain[sel] - 1)) < 0.03
+
+
+def test_chain_fused_histogram(A):
+    """Event-weighted E_a spectrum accumulated inside the chain kernel == np.histogram of the materialised arrays."""
+    from alplib_b200.reduce import histogram
+    pf = _c2_flux(150)
+    fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=1.5, axion_coupling=3e-6, n_samples=999, seed=8, **GEOM)
+    fl.simulate()
+    for edges in (np.linspace(0.0, 1000.0, 51), np.logspace(0, 3, 33)):
+        rate, evw = fl.chain(100, 5.0, materialize=True, hist_edges=edges)
+        h = fl.last_hist.cpu().numpy()
+        ref = O.histogram(np.asarray(fl.axion_energy), evw.cpu().numpy(), edges)
+        assert max_rel(h, ref, floor=1e-300) < 1e-10
+        assert max_rel(histogram(fl._E, evw, edges).cpu().numpy(), ref, floor=1e-300) < 1e-10
+        assert h.sum() == pytest.approx(float(rate.item()) - evw.cpu().numpy()[np.asarray(fl.axion_energy) > edges[-1]].sum()
+                                        - evw.cpu().numpy()[np.asarray(fl.axion_energy) < edges[0]].sum(), rel=1e-9)
+        # reduce-only pass fills the same histogram without materialising anything
+        rate2, _ = fl.chain(100, 5.0, materialize=False, hist_edges=edges)
+        assert max_rel(fl.last_hist.cpu().numpy(), ref, floor=1e-300) < 1e-10
