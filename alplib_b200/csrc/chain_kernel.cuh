@@ -33,7 +33,7 @@ struct ChainArgs {
     const double* hist_edges; int n_edges; double* hist;     // optional fused weighted histogram of E_a
 };
 
-template <class Prod, bool INJECT, int STAGE, bool FAST>   // STAGE 0: production; 1: + propagate; 2: + decays
+template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST>   // STAGE 0: production; 1: + propagate; 2: + decays
 __global__ void __launch_bounds__(kThreads, ALPK_MIN_BLOCKS)
 chain_kernel(const ChainArgs<Prod> a) {
     using namespace alp;
@@ -43,7 +43,7 @@ chain_kernel(const ChainArgs<Prod> a) {
     extern __shared__ double s_hist_mem[];           // [n_edges] edges + [n_edges-1] privatised bins (only if a.hist)
     double* s_edges = s_hist_mem;
     double* s_bins = s_hist_mem + a.n_edges;
-    if (a.hist) {
+    if (HIST) {
         for (int i = threadIdx.x; i < a.n_edges; i += blockDim.x) s_edges[i] = __ldg(a.hist_edges + i);
         for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) s_bins[i] = 0.0;
         // (made visible by the __syncthreads of the first tile)
@@ -118,7 +118,7 @@ chain_kernel(const ChainArgs<Prod> a) {
                     evv[j] = decay_event_weight(e[j], d32v[j], a.ev);
                     if (j == 0 || have2) acc += evv[j];
                 }
-                if (a.hist && (j == 0 || have2)) {
+                if (HIST && (j == 0 || have2)) {
                     // np.histogram(E_a, bins=edges, weights=<weight of the last fused stage>)
                     const double hw = STAGE >= 2 ? evv[j] : (STAGE == 1 ? (double)d32v[j] : f[j]);
                     const int bin = find_bin(e[j], s_edges, a.n_edges);
@@ -152,7 +152,7 @@ chain_kernel(const ChainArgs<Prod> a) {
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) a.partials[blockIdx.x] = acc;
     }
-    if (a.hist) {
+    if (HIST) {
         __syncthreads();
         for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) {
             const double v = s_bins[i];
@@ -202,12 +202,15 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const int grid = grid_for(n, (int)a.tile_elems, 8);
     const bool inj = uniforms != nullptr;
     const bool fast = fast_mode != 0;
+#define ALPK_CHAIN_LAUNCH(I, S, F, H) chain_kernel<Prod, I, S, F, H><<<grid, kThreads, smem, st>>>(a)
 #define ALPK_CHAIN_CASE(S)                                                                                   \
-    if (inj) { if (fast) chain_kernel<Prod, true, S, true><<<grid, kThreads, smem, st>>>(a);                     \
-               else chain_kernel<Prod, true, S, false><<<grid, kThreads, smem, st>>>(a); }                        \
-    else { if (fast) chain_kernel<Prod, false, S, true><<<grid, kThreads, smem, st>>>(a);                        \
-           else chain_kernel<Prod, false, S, false><<<grid, kThreads, smem, st>>>(a); }
+    if (hist) {   /* histogram variants only for the free-running RNG */                                      \
+        if (inj) { set_error("%s: fused histogram is not available with injected uniforms", what); return 2; } \
+        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true); else ALPK_CHAIN_LAUNCH(false, S, false, true);     \
+    } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false); else ALPK_CHAIN_LAUNCH(true, S, false, false); } \
+    else { if (fast) ALPK_CHAIN_LAUNCH(false, S, true, false); else ALPK_CHAIN_LAUNCH(false, S, false, false); }
     if (stage == 0) { ALPK_CHAIN_CASE(0) } else if (stage == 1) { ALPK_CHAIN_CASE(1) } else { ALPK_CHAIN_CASE(2) }
+#undef ALPK_CHAIN_LAUNCH
 #undef ALPK_CHAIN_CASE
     if (check_launch(what)) return 1;
     if (stage == 2) return finalize_sum(scratch, grid, rate, st);
