@@ -539,3 +539,48 @@ def test_chain_fused_histogram(A):
         # reduce-only pass fills the same histogram without materialising anything
         rate2, _ = fl.chain(100, 5.0, materialize=False, hist_edges=edges)
         assert max_rel(fl.last_hist.cpu().numpy(), ref, floor=1e-300) < 1e-10
+
+
+def test_output_bounds_canaries(A):
+    """compute-sanitizer is closed on this pool: check for out-of-bounds stores with guard regions instead.  Every output
+    of the chain / decay / propagate kernels is a slice of a sentinel-filled buffer; the guards must be untouched."""
+    import ctypes as C
+    import torch
+    from alplib_b200 import _native as N, params as P
+    pf = _c2_flux(23)
+    fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=1.5, axion_coupling=1e-6, n_samples=333, seed=1, **GEOM)   # odd n
+    fl._stage_inputs(); fl._launch_rows()
+    n = fl._rows[1] * fl._rows[2]
+    assert n % 2 == 1
+    G, S = 64, -7.25
+    rt = fl._rt
+
+    def guarded(count, dtype):
+        buf = torch.full((count + 2 * G,), S, dtype=dtype, device=rt.device)
+        return buf, buf[G:G + count]
+
+    bufs = {k: guarded(n, torch.float64) for k in ("E", "F", "d64", "s64", "evw")}
+    bufs.update({k: guarded(n, torch.float32) for k in ("d32", "s32")})
+    rate = rt.empty(1)
+    prop = fl._prop_params(*fl._width_rescale(None), fl._geom_accept(), None)
+    fl._launch_samples(bufs["E"][1], bufs["F"][1], prop, P.event_params(100, 5.0), d32=bufs["d32"][1], s32=bufs["s32"][1],
+                       d64=bufs["d64"][1], s64=bufs["s64"][1], evw=bufs["evw"][1], rate=rate)
+    torch.cuda.synchronize()
+    for k, (buf, view) in bufs.items():
+        assert torch.all(buf[:G] == S) and torch.all(buf[-G:] == S), k
+        assert not torch.any(view == S), k
+    # decay MC with an odd event count (odd planes are not 16-byte aligned)
+    fp = A.FluxPrimakoffIsotropic(np.array([[100.0, 1e12], [40.0, 1e11], [7.0, 1e10]]), A.Material("W"), axion_mass=0.1,
+                                  axion_coupling=1e-5, **GEOM)
+    fp.simulate(); fp.propagate()
+    npar, ns = 3, 111
+    nev = npar * ns
+    table = rt.empty(npar * N.PARENT_NP)
+    ev = P.event_params(100, 0.0)
+    N.call("alpk_decay_parent_rows", N.ptr(fp._E), N.ptr(fp._D32), npar, float(0.1 ** 2), C.byref(ev), ns, N.ptr(table), rt.stream())
+    b1, p1 = guarded(4 * nev, torch.float64); b2, p2 = guarded(4 * nev, torch.float64); bw, w = guarded(nev, torch.float64)
+    for fast in (0, 1):
+        N.call("alpk_decay2body", N.ptr(table), npar, ns, None, None, C.c_uint64(5), fast, N.ptr(p1), N.ptr(p2), N.ptr(w), rt.stream())
+        torch.cuda.synchronize()
+        for buf, view in ((b1, p1), (b2, p2), (bw, w)):
+            assert torch.all(buf[:G] == S) and torch.all(buf[-G:] == S) and not torch.any(view == S)
