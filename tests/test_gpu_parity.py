@@ -584,3 +584,61 @@ def test_output_bounds_canaries(A):
         torch.cuda.synchronize()
         for buf, view in ((b1, p1), (b2, p2), (bw, w)):
             assert torch.all(buf[:G] == S) and torch.all(buf[-G:] == S) and not torch.any(view == S)
+
+
+# ---- BASELINE full sizes: size-independent properties, evaluated on the device ------------------------------------------------
+def test_full_size_c2_chain_properties(A):
+    """configs[1] at full size (1e4 bins x 1e4 samples = 7.4e7 live samples): the fused chain's invariants."""
+    import torch
+    pf = _c2_flux(10_000)
+    ma = 1.5
+    fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=1e-7, n_samples=10_000, seed=0xA1B2C3D4 + 2, **GEOM)
+    fl.simulate_rows_only = None
+    fl._reset_samples(); fl._stage_inputs(); fl._launch_rows()
+    edges = np.concatenate([[0.0], np.logspace(0, 3, 60), [1e9]])
+    rate, evw = fl.chain(100, 5.0, materialize=True, hist_edges=edges)
+    n_live = int(O.compton_row_valid(pf, ma).sum()) * 10_000
+    E, F, D, S = fl._E, fl._F, fl._D32, fl._S32
+    assert E.shape[0] == n_live == evw.shape[0] and 7.3e7 < n_live < 7.5e7
+    r = float(rate.item())
+    assert r == pytest.approx(float(evw.sum().item()), rel=1e-10)
+    assert float(fl.last_hist.sum().item()) == pytest.approx(r, rel=1e-10)           # checksum of the binned spectrum
+    rate2, _ = fl.chain(100, 5.0, materialize=False)
+    assert float(rate2.item()) == pytest.approx(r, rel=1e-12)                         # reduce-only == materialising
+    assert bool(torch.isfinite(F).all()) and bool(torch.isfinite(D).all()) and bool((F >= 0).all())
+    assert float(E.min().item()) >= ma and float(E.max().item()) <= pf[-1, 0]
+    assert bool((D <= S).all()) and bool((D >= 0).all())                              # decay prob <= 1
+    eg = torch.from_numpy(np.repeat(pf[O.compton_row_valid(pf, ma), 0], 10_000)).to(E.device)
+    assert bool((E <= eg).all())                                                      # E_a drawn in [ma, E_gamma] of its own row
+    # the eager three-kernel path reproduces the same arrays bit for bit
+    fl2 = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=1e-7, n_samples=10_000, seed=0xA1B2C3D4 + 2, **GEOM)
+    fl2.simulate(); fl2.propagate()
+    assert torch.equal(fl2._E, E) and torch.equal(fl2._F, F) and torch.equal(fl2._D32, D) and torch.equal(fl2._S32, S)
+
+
+def test_full_size_c3_decay_properties(A):
+    """configs[2]: 1e4 parents x 1e4 decays = 1e8 events (7.2 GB of 4-vectors): conservation laws on the device."""
+    import torch
+    pf = _c2_flux(10_000)
+    fl = A.FluxPrimakoffIsotropic(pf, A.Material("W"), axion_mass=0.1, axion_coupling=1e-5, **GEOM)
+    fl.simulate(); fl.propagate()
+    gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+    l1, l2, w = gen.simulate_decay_4vectors(100, n_samples=10_000, seed=3)
+    p1, p2 = l1.device, l2.device
+    n = p1.shape[1]
+    assert n == 10_000 * 10_000
+    Ep = fl._E.repeat_interleave(10_000)
+    assert torch.equal(p1[1], -p2[1]) and torch.equal(p1[2], -p2[2])                  # back-to-back transverse momenta
+    # the reference's sqrt(E^2-p^2) / 1/sqrt(1-beta^2) lose ~gamma^2 * 1e-16; assert where that is < 1e-9 (gamma <= 1000)
+    sel = Ep <= 100.0
+    dE = ((p1[0] + p2[0] - Ep).abs() / Ep)[sel]
+    assert float(dE.max().item()) < 1e-9
+    pz = torch.sqrt(Ep * Ep - 0.1 ** 2)
+    assert float((((p1[3] + p2[3] - pz).abs() / Ep)[sel]).max().item()) < 1e-9
+    m2 = (p1[0] ** 2 - p1[1] ** 2 - p1[2] ** 2 - p1[3] ** 2).abs() / Ep ** 2
+    assert float(m2[sel].max().item()) < 1e-9
+    assert bool((p1[0] > 0).all()) and bool((p2[0] > 0).all())
+    assert float(w.device.sum().item()) == pytest.approx(100 * 86400 * float(fl._D32.double().sum().item()), rel=1e-6)
+    # isotropy in the parent frame <=> E1/E_parent uniform in [(1-beta)/2, (1+beta)/2]: mean 1/2, variance beta^2/12
+    x = (p1[0] / Ep)[~sel]
+    assert abs(float(x.mean().item()) - 0.5) < 1e-3 and abs(float(x.var().item()) - 1 / 12) < 1e-3

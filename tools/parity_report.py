@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Measured parity of the CUDA path against the reference's golden fixtures, both arithmetic modes, written to
+profiles/parity_r1.json (run on the GPU box)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import decay_tol, load_golden, max_rel   # noqa: E402
+import alplib_b200 as A                                  # noqa: E402
+from alplib_b200 import config                           # noqa: E402
+
+GEOM = dict(det_dist=4.0, det_length=0.2, det_area=0.04)
+DUNE = dict(det_dist=574.0, det_length=5.0, det_area=21.0)
+
+
+def cond_err(d, d_ref, s_ref):
+    """max over samples of |d - d_ref| / (|d_ref| * conditioned tolerance unit) -- in units of the 1e-9 + 4 ulp bound."""
+    d, d_ref = np.asarray(d, float), np.asarray(d_ref, float)
+    t = decay_tol(d_ref, s_ref, 1e-9, 4.0)
+    nz = d_ref != 0
+    if not nz.any():
+        return 0.0
+    return float(np.max(np.abs(d[nz] - d_ref[nz]) / (np.abs(d_ref[nz]) * t[nz])))
+
+
+def report():
+    out = {}
+    for mode in ("faithful", "fast"):
+        config.PRECISION = mode
+        r = {}
+        for name in ("c1_primakoff", "primakoff_ragged"):
+            g = load_golden(name)
+            fl = A.FluxPrimakoffIsotropic(g["photon_flux"], A.Material("W"), axion_mass=float(g["ma"]), axion_coupling=float(g["g"]), keep_f64=True, **GEOM)
+            fl.simulate(); fl.propagate()
+            ga = 0.04 / (4 * np.pi * 16.0)
+            r[name] = {"flux": max_rel(fl.axion_flux, g["axion_flux"]), "scatter_w64": max_rel(fl.scatter_axion_weight_f64 * ga, g["scatter_w64"]),
+                       "decay_w64_in_units_of_tolerance": cond_err(fl.decay_axion_weight_f64 * ga, g["decay_w64"], g["scatter_w64"]),
+                       "scatter_w32": max_rel(fl.scatter_axion_weight, g["scatter_w32"])}
+        for name in ("katc_compton", "compton_mid", "compton_loop"):
+            g = load_golden(name)
+            loop = bool(g["loop_decay"]) if "loop_decay" in g else False
+            iso = bool(g["is_isotropic"]) if "is_isotropic" in g else True
+            fl = A.FluxComptonIsotropic(g["photon_flux"], A.Material("W"), axion_mass=float(g["ma"]), axion_coupling=float(g["g"]),
+                                        n_samples=int(g["n_samples"]), loop_decay=loop, is_isotropic=iso, keep_f64=True, **GEOM)
+            fl.simulate(uniforms=g["uniforms"]); fl.propagate()
+            ga = 0.04 / (4 * np.pi * 16.0) if iso else 1.0
+            r[name] = {"energy_bit_exact": bool(np.array_equal(fl.axion_energy, g["axion_energy"])), "flux": max_rel(fl.axion_flux, g["axion_flux"]),
+                       "scatter_w64": max_rel(fl.scatter_axion_weight_f64 * ga, g["scatter_w64"]),
+                       "decay_w64_in_units_of_tolerance": cond_err(fl.decay_axion_weight_f64 * ga, g["decay_w64"], g["scatter_w64"]),
+                       "scatter_w32": max_rel(fl.scatter_axion_weight, g["scatter_w32"]),
+                       "scatter_w32_bit_identical_fraction": float(np.mean(np.asarray(fl.scatter_axion_weight) == g["scatter_w32"]))}
+        for name in ("katb_brem", "brem_ps", "brem_vec", "brem_notl"):
+            g = load_golden(name)
+            boson = str(g["boson_type"]) if "boson_type" in g else "pseudoscalar"
+            tl = bool(g["use_track_length"]) if "use_track_length" in g else True
+            fl = A.FluxBremIsotropic(g["electron_flux"], g["positron_flux"], A.Material("C"), target_length=100, axion_mass=float(g["ma"]),
+                                     axion_coupling=float(g["g"]), n_samples=int(g["n_samples"]), boson_type=boson, keep_f64=True, **DUNE)
+            fl.simulate(use_track_length=tl, uniforms=g["uniforms"]); fl.propagate()
+            r[name] = {"energy": max_rel(fl.axion_energy, g["axion_energy"]), "flux": max_rel(fl.axion_flux, g["axion_flux"])}
+        g = load_golden("katr_resonance")
+        fl = A.FluxResonanceIsotropic(g["positron_flux"], A.Material("C"), axion_mass=10.0, axion_coupling=1e-6, n_samples=1000, **DUNE)
+        fl.simulate(uniforms=g["uniforms"])
+        r["katr_resonance"] = {"flux": max_rel(fl.axion_flux, g["axion_flux"])}
+        for name in ("kata_pairann", "pairann_mid"):
+            g = load_golden(name)
+            fl = A.FluxPairAnnihilationIsotropic(g["positron_flux"], A.Material("C"), axion_mass=10.0, axion_coupling=1e-6,
+                                                 n_samples=int(g["n_samples"]), **DUNE)
+            fl.simulate(uniforms=g["uniforms"])
+            r[name] = {"energy": max_rel(fl.axion_energy, g["axion_energy"]), "flux": max_rel(fl.axion_flux, g["axion_flux"])}
+        for name in ("katd_decay4", "decay4_boosted", "decay4_heavy"):
+            g = load_golden(name)
+            ns = int(g["n_samples"])
+            fl = A.FluxPrimakoffIsotropic(g["photon_flux"], A.Material("W"), axion_mass=float(g["ma"]), axion_coupling=float(g["g"]), **GEOM)
+            fl.simulate(); fl.propagate(); fl.decay_axion_weight = g["decay_w32"]
+            npar = len(fl.axion_energy)
+            l1, l2, w = A.PhotonEventGenerator(fl, A.Material("Ar")).simulate_decay_4vectors(int(g["days"]), n_samples=ns,
+                                                                                            uniforms=g["uniforms"][npar:].reshape(npar, 2, ns))
+            scale = np.repeat(np.asarray(fl.axion_energy), ns)[:, None]
+            r[name] = {"max_dp_over_E_parent": float(max(np.max(np.abs(l1.pmu - g["p1"]) / scale), np.max(np.abs(l2.pmu - g["p2"]) / scale))),
+                       "weights_bit_exact": bool(np.array_equal(np.asarray(w), g["w"]))}
+        for name in ("volint_box", "volint_sphere", "volint_cyl"):
+            g = load_golden(name)
+            fl = A.FluxComptonIsotropic(g["photon_flux"], A.Material("W"), axion_mass=float(g["ma"]), axion_coupling=float(g["g"]), n_samples=12, keep_f64=True, **GEOM)
+            fl.axion_energy = g["axion_energy"]; fl.axion_flux = g["axion_flux"]
+            np.random.seed(78)
+            geom = A.DetectorGeometry(float(g["l0"]), str(g["geometry"]), list(g["params"]), n_samples=int(g["n_geom"]))
+            fl.propagate_iso_vol_int(geom, new_coupling=float(g["new_coupling"]))
+            r[name] = {"decay_w64": max_rel(fl.decay_axion_weight_f64, g["decay_w64"]), "scatter_w64": max_rel(fl.scatter_axion_weight_f64, g["scatter_w64"])}
+        out[mode] = r
+    out["tolerance"] = {"fp64_relative": 1e-9, "float32_attributes": 1.2e-7,
+                        "decay_weights": "1e-9 + 4*2^-53/decay_prob (reported in units of that bound; <= 1 passes)"}
+    worst = {m: max(v for c in out[m].values() for k, v in c.items() if isinstance(v, float) and "fraction" not in k and "units" not in k and "w32" not in k) for m in ("faithful", "fast")}
+    out["worst_fp64_relative_error"] = worst
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "parity_r1.json"), "w"), indent=1)
+    print(json.dumps(out["worst_fp64_relative_error"]))
+    for m in ("faithful", "fast"):
+        for c, v in out[m].items():
+            print(m, c, {k: (f"{x:.2e}" if isinstance(x, float) else x) for k, x in v.items()})
+
+
+if __name__ == "__main__":
+    report()
