@@ -109,6 +109,12 @@ _SIGNATURES = {
     "alpk_last_error": ([], C.c_char_p),
     "alpk_launch_count": ([], C.c_uint64),
     "alpk_device_info": ([_I, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
+    "alpk_set_device": ([_I], _I),
+    "alpk_malloc": ([C.POINTER(C.c_void_p), _U64], _I),
+    "alpk_free": ([_P], _I),
+    "alpk_memcpy_h2d": ([_P, _P, _U64, _P], _I),
+    "alpk_memcpy_d2h": ([_P, _P, _U64, _P], _I),
+    "alpk_sync": ([_P], _I),
     "alpk_propagate": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _P, _P], _I),
     "alpk_decays": ([_P, _P, _U64, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_scatter_events": ([_I, _P, _P, _U64, C.POINTER(_D), _D, _D, C.POINTER(EventT), _P, _P, _P, _P], _I),

@@ -274,6 +274,44 @@ ALPK_EXPORT int alpk_device_info(int device, char* h_name, int name_len, int* h_
     return 0;
 }
 
+// ---- minimal device-memory helpers so that a caller without PyTorch / the CUDA runtime can drive the library -----------
+ALPK_EXPORT int alpk_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+ALPK_EXPORT int alpk_malloc(void** d_ptr, uint64_t bytes) {
+    if (!d_ptr) { set_error("alpk_malloc: null argument"); return 2; }
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+ALPK_EXPORT int alpk_free(void* d_ptr) {
+    cudaError_t e = cudaFree(d_ptr);
+    if (e != cudaSuccess) { set_error("cudaFree: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+ALPK_EXPORT int alpk_memcpy_h2d(void* d_dst, const void* h_src, uint64_t bytes, void* stream) {
+    cudaError_t e = cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("alpk_memcpy_h2d: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+ALPK_EXPORT int alpk_memcpy_d2h(void* h_dst, const void* d_src, uint64_t bytes, void* stream) {
+    cudaError_t e = cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("alpk_memcpy_d2h: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+ALPK_EXPORT int alpk_sync(void* stream) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("alpk_sync: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
 ALPK_EXPORT int alpk_propagate(const double* energy, const double* weight, uint64_t n, const alpk_prop_t* h_prop,
                                float* decay_w32, float* scatter_w32, double* d64, double* s64, void* stream) {
     if (!h_prop || !decay_w32 || !scatter_w32) { set_error("alpk_propagate: null argument"); return 2; }

@@ -43,6 +43,15 @@ uint64_t alpk_launch_count(void);
 /* writes name, SM count, compute capability of `device`; used by the loader to refuse non-sm_100 devices */
 int alpk_device_info(int device, char* h_name, int name_len, int* h_sm_count, int* h_cc_major, int* h_cc_minor);
 
+/* ---- device-memory helpers: enough for a caller without PyTorch or the CUDA runtime API to drive the library
+ * (the Python package itself uses torch tensors for device memory and passes their pointers). -------------------- */
+int alpk_set_device(int device);
+int alpk_malloc(void** d_ptr, uint64_t bytes);
+int alpk_free(void* d_ptr);
+int alpk_memcpy_h2d(void* d_dst, const void* h_src, uint64_t bytes, void* stream);
+int alpk_memcpy_d2h(void* h_dst, const void* d_src, uint64_t bytes, void* stream);
+int alpk_sync(void* stream);
+
 /* ---- propagate: fluxes.py:43-65 (AxionFlux.propagate) + fluxes.py:159-162 (isotropic acceptance) ------------ */
 typedef struct {
     double ma, ma2;          /* axion mass, ma**2 */

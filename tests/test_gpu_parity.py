@@ -642,3 +642,43 @@ def test_full_size_c3_decay_properties(A):
     # isotropy in the parent frame <=> E1/E_parent uniform in [(1-beta)/2, (1+beta)/2]: mean 1/2, variance beta^2/12
     x = (p1[0] / Ep)[~sel]
     assert abs(float(x.mean().item()) - 0.5) < 1e-3 and abs(float(x.var().item()) - 1 / 12) < 1e-3
+
+
+def test_c_abi_without_torch_tensors(A):
+    """The C ABI alone (ctypes + the library's own device-memory helpers, no torch tensors): README Primakoff chain."""
+    import ctypes as C
+    from alplib_b200 import _native as N, params as P
+    L = N.lib()
+    g = load_golden("c1_primakoff")
+    xs = O.AbsCrossSection(O.Material("W"))
+    host = {"eg": np.array([100.0]), "ph": np.array([1e12]), "le": np.ascontiguousarray(xs.log10_e), "lx": np.ascontiguousarray(xs.log10_xs)}
+    dev = {}
+
+    def dmalloc(nbytes):
+        p = C.c_void_p()
+        assert L.alpk_malloc(C.byref(p), nbytes) == 0, L.alpk_last_error()
+        return p
+
+    assert L.alpk_set_device(0) == 0
+    for k, a in host.items():
+        dev[k] = dmalloc(a.nbytes)
+        assert L.alpk_memcpy_h2d(dev[k], a.ctypes.data_as(C.c_void_p), a.nbytes, None) == 0
+    for k, nb in (("E", 8), ("F", 8), ("d32", 4), ("s32", 4), ("rate", 8), ("scratch", 8 * N.SCRATCH_DOUBLES)):
+        dev[k] = dmalloc(nb)
+    pref, r02 = P.primakoff_consts(1e-5, np.int64(74))
+    assert L.alpk_primakoff(dev["eg"], dev["ph"], 1, dev["le"], dev["lx"], host["le"].shape[0], 0.1, pref, r02, dev["E"], dev["F"], None) == 0
+    prop = P.prop_params(0.1, O.W_gg(1e-5, 0.1), 1.0, 4.0, 0.2, geom_accept=GA, fast=False)
+    assert L.alpk_propagate(dev["E"], dev["F"], 1, C.byref(prop), dev["d32"], dev["s32"], None, None, None) == 0
+    ev = P.event_params(100, 5.0)
+    assert L.alpk_decays(dev["E"], dev["d32"], 1, C.byref(ev), None, dev["rate"], dev["scratch"], None) == 0
+    rate, flux, d32 = np.zeros(1), np.zeros(1), np.zeros(1, np.float32)
+    for dst, src in ((rate, "rate"), (flux, "F"), (d32, "d32")):
+        assert L.alpk_memcpy_d2h(dst.ctypes.data_as(C.c_void_p), dev[src], dst.nbytes, None) == 0
+    assert L.alpk_sync(None) == 0
+    assert flux[0] == pytest.approx(327952.3965351194, rel=1e-12)
+    assert d32[0] == g["decay_w32"][0] and rate[0] == pytest.approx(284.1535949707031, rel=2e-7)
+    # error path: status code + message, no exception across the boundary
+    assert L.alpk_propagate(None, None, 5, None, None, None, None, None, None) != 0
+    assert b"alpk_propagate" in L.alpk_last_error()
+    for p in dev.values():
+        assert L.alpk_free(p) == 0
