@@ -282,11 +282,11 @@ def run_gpu(args):
         c.row_offset = rank * N_BINS
         c.simulate(); c.propagate()
         gen_c = A.ElectronEventGenerator(c, Ar)
-        rate_c = gen_c.decays_device(DAYS, THR) if not fused else None       # queued behind propagate, no sync yet
+        rate_c = gen_c.decays_device(DAYS, THR)          # kernels queued, no sync yet (fused: the one chain kernel)
         p = A.FluxPrimakoffIsotropic(pf, W, axion_mass=MA_P, axion_coupling=G_P, fused=fused, **GEOM)
         p.simulate(); p.propagate()
         rp = A.PhotonEventGenerator(p, Ar).decays(DAYS, THR)
-        rc = float(rate_c.item()) if rate_c is not None else gen_c.decays(DAYS, THR)
+        rc = float(rate_c.item())
         return rp, rc, p, c
 
     e2e = {}
