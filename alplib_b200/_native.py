@@ -10,7 +10,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ALPK_LIB_PATH") or os.path.join(_HERE, "libalpk.so")   # override: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_scan.cu"]
+SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_scan.cu", "alpk_misc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
@@ -138,6 +138,9 @@ _SIGNATURES = {
                    C.POINTER(PropT), C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_vol_int_chunks": ([_U64, _U32], _U32),
     "alpk_vol_int": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _U32, _D, _D, _P, _P, _P, _P, _P, _P], _I),
+    "alpk_nuclear": ([_P, _U64, _D, _D, _D, _D, _D, _P, _P, _P], _I),
+    "alpk_pi0_flux": ([_P, _U64, _P, _U64, _D, _D, _D, _D, _D, _D, _D, _P, _P, _P, _P], _I),
+    "alpk_scale": ([_P, _U64, _D, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),
     "alpk_fp64_peak": ([_U64, _I, _P, _P], _I),

@@ -19,6 +19,8 @@ AVOGADRO = 6.022e23                    # constants.py:29
 M_E = 0.511                            # constants.py:32  MeV
 M_P = 938.0                            # constants.py:33
 M_MU = 105.658369                      # constants.py:34
+M_PI = 139.57                          # constants.py:41
+M_PI0 = 134.98                         # constants.py:42
 METER_BY_MEV = 6.58212e-22 * 2.998e8   # constants.py:60  MeV m
 MEV_PER_KG = 5.6095887e29              # constants.py:61
 MEV2_CM2 = (METER_BY_MEV * 100) ** 2   # constants.py:65

@@ -1,0 +1,82 @@
+// libalpk: small flux sources beyond the photon / e+- channels -- nuclear de-excitation lines (fluxes.py:554-600) and
+// pi0 -> gamma a two-body decay in flight (fluxes.py:926-991).  One thread per input row.
+#include "../../include/alpk.h"
+#include "common.cuh"
+
+using namespace alp;
+
+namespace alpk {
+
+// fluxes.py:571-577 (br) and :587-590 (simulate); rows already filtered by the host (E > ma)
+__global__ void __launch_bounds__(kThreads)
+nuclear_kernel(const double* __restrict__ rates4, uint64_t n, double ma2, double c0, double expo, double gann0,
+               double gann1, double* __restrict__ out_e, double* __restrict__ out_f) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = __ldg(rates4 + 4 * i), rate = __ldg(rates4 + 4 * i + 1);
+        const double beta = __ldg(rates4 + 4 * i + 2), eta = __ldg(rates4 + 4 * i + 3);
+        const double mu0 = 0.88, mu1 = 4.71;
+        const double kin = pow(sqrt(e * e - ma2) / e, expo);
+        const double ratio = (gann0 * beta + gann1) / ((mu0 - 0.5) * beta + (mu1 - eta));
+        const double br = (c0 * kin) * (ratio * ratio);
+        out_e[i] = e;
+        out_f[i] = rate * br;
+    }
+}
+
+// fluxes.py:955-968: one isotropic decay per pi0 momentum, boosted along z; keep[i] = passes the energy/angle cuts
+__global__ void __launch_bounds__(kThreads)
+pi0_flux_kernel(const double* __restrict__ p, uint64_t n, const double* __restrict__ uniforms, uint64_t seed,
+                double mm2, double ma2, double p_cm, double e1_cm, double energy_cut, double angle_cut, double wgt,
+                double* __restrict__ out_e, double* __restrict__ out_f, uint8_t* __restrict__ keep) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double u = uniforms ? __ldg(uniforms + i) : uniform_1(seed, 8u /* pi0 stream */, 0u, i);
+        const double c = -1 + (1 - (-1)) * u;                                    // np.random.uniform(-1, 1)
+        const double pm = __ldg(p + i);
+        const double beta = pm / sqrt(pm * pm + mm2);                             // :959
+        const double boost = pow(1 - beta * beta, -0.5);                          // :960
+        const double e_lab = boost * (e1_cm + (beta * p_cm) * c);                 // :961
+        const double pz_lab = boost * (p_cm * c + beta * e1_cm);                  // :962
+        const double angle = acos(pz_lab / sqrt(e_lab * e_lab - ma2));            // :963
+        out_e[i] = e_lab;
+        out_f[i] = wgt;
+        keep[i] = (!(e_lab < energy_cut) && !(angle > angle_cut)) ? 1 : 0;        // :964-967
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+scale_kernel(const double* __restrict__ x, uint64_t n, double factor, double* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = factor * __ldg(x + i);
+}
+
+}  // namespace alpk
+
+using namespace alpk;
+
+ALPK_EXPORT int alpk_scale(const double* x, uint64_t n, double factor, double* out, void* stream) {
+    if (n == 0) return 0;
+    if (!x || !out) { set_error("alpk_scale: null argument"); return 2; }
+    scale_kernel<<<grid_for(n, kThreads * 4, 8), kThreads, 0, (cudaStream_t)stream>>>(x, n, factor, out);
+    return check_launch("alpk_scale");
+}
+
+ALPK_EXPORT int alpk_nuclear(const double* rates4, uint64_t n_rows, double ma2, double c0, double expo, double gann0,
+                             double gann1, double* out_energy, double* out_flux, void* stream) {
+    if (n_rows == 0) return 0;
+    if (!rates4 || !out_energy || !out_flux) { set_error("alpk_nuclear: null argument"); return 2; }
+    nuclear_kernel<<<grid_for(n_rows, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(rates4, n_rows, ma2, c0, expo, gann0,
+                                                                                       gann1, out_energy, out_flux);
+    return check_launch("alpk_nuclear");
+}
+
+ALPK_EXPORT int alpk_pi0_flux(const double* momenta, uint64_t n, const double* uniforms, uint64_t seed, double mm2,
+                              double ma2, double p_cm, double e1_cm, double energy_cut, double angle_cut, double weight,
+                              double* out_energy, double* out_flux, uint8_t* keep, void* stream) {
+    if (n == 0) return 0;
+    if (!momenta || !out_energy || !out_flux || !keep) { set_error("alpk_pi0_flux: null argument"); return 2; }
+    pi0_flux_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+        momenta, n, uniforms, seed, mm2, ma2, p_cm, e1_cm, energy_cut, angle_cut, weight, out_energy, out_flux, keep);
+    return check_launch("alpk_pi0_flux");
+}

@@ -38,7 +38,8 @@ from .runtime import Runtime
 _EMPTY64 = np.zeros(0, dtype=np.float64)
 
 __all__ = ["AxionFlux", "FluxPrimakoffIsotropic", "FluxComptonIsotropic", "FluxBremIsotropic",
-           "FluxResonanceIsotropic", "FluxPairAnnihilationIsotropic", "track_length_prob"]
+           "FluxResonanceIsotropic", "FluxPairAnnihilationIsotropic", "FluxNuclearIsotropic", "FluxPi0Isotropic",
+           "track_length_prob"]
 
 
 def _as_flux_table(flux, name):
@@ -783,3 +784,120 @@ class FluxPairAnnihilationIsotropic(_ChainFlux):
                 N.call("alpk_pairann_rows", N.ptr(d_e), N.ptr(d_w), n_rows, C.byref(par), N.ptr(table), rt.stream())
         self._rows = (table, n_rows, ns, d_ids, par, d_u, seed)
         self._finish_simulate()
+
+
+class FluxNuclearIsotropic(AxionFlux):
+    """
+    ALP flux from nuclear de-excitation lines: rows of [E_transition, decays/s, beta, eta] times the a/gamma branching
+    ratio (reference: fluxes.py:554-600).
+    """
+    def __init__(self, transition_rates=np.array([[1.0, 0.0, 1.0, 0.5]]), target=None,
+                 det_dist=4., det_length=0.2, det_area=0.04, is_isotropic=True,
+                 axion_mass=0.1, gann0=1e-3, gann1=1e-3, gae=0.0, gagamma=0.0, n_samples=100, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, n_samples, **_split_kwargs(kwargs))
+        self.rates = transition_rates
+        self.gann0 = gann0
+        self.gann1 = gann1
+        self.gae = gae
+        self.gagamma = gagamma
+        self.is_isotropic = is_isotropic
+
+    def decay_width(self):
+        return W_ee(self.gae, self.ma) + W_ee(self.gagamma, self.ma)
+
+    def simulate(self, j=1, delta=0.0):
+        self._reset_samples()
+        rates = np.asarray(self.rates, dtype=np.float64)
+        keep = rates[:, 0] > self.ma                                              # fluxes.py:588
+        rows = np.ascontiguousarray(rates[keep, :4])
+        n = int(rows.shape[0])
+        c0 = (j/(j+1)) / (1 + delta**2) / pi / ALPHA                              # :574
+        rt = self._rt
+        with rt.activate():
+            E, F = rt.empty(n), rt.empty(n)
+            if n:
+                N.call("alpk_nuclear", N.ptr(rt.upload(rows.ravel())), n, float(self.ma**2), float(c0), float(2*j + 1),
+                       float(self.gann0), float(self.gann1), N.ptr(E), N.ptr(F), rt.stream())
+        self._set_production(E, F)
+
+    def propagate(self):
+        self._propagate(W_ee(self.gae, self.ma), 1.0, self._geom_accept() if self.is_isotropic else None)
+
+    def propagate_iso_vol_int(self, geom: DetectorGeometry):
+        AxionFlux.propagate_iso_vol_int(self, geom, self.decay_width())
+
+
+class FluxPi0Isotropic(AxionFlux):
+    """
+    ALPs (or dark photons) from pi0 -> gamma + a (reference: fluxes.py:926-991): `simulate()` for pi0 at rest,
+    `simulate_flux(momenta)` for a list of pi0 momenta along z with optional energy / angle cuts.  `propagate()` keeps
+    float64 weights (no decays, acceptance only), as the reference does for this class.
+    """
+    def __init__(self, pi0_rate=0.0259, boson_mass=0.1, coupling=1.0,
+                 det_dist=20.0, det_area=2.0, det_length=1.0,
+                 target=None, n_samples=1000, **kwargs):
+        from .constants import M_PI0
+        target = Material("W") if target is None else target
+        super().__init__(boson_mass, target, det_dist, det_length, det_area, **_split_kwargs(kwargs))
+        self.meson_rate = pi0_rate
+        self.n_samples = n_samples
+        self.g = coupling
+        self.boson_mass = boson_mass
+        self.mm = M_PI0
+
+    def br(self):
+        return 2 * (self.g)**2 * (1 - power(self.ma / self.mm, 2))**3 / sqrt(4*pi*ALPHA)
+
+    def _cm(self):
+        p_cm = (self.mm**2 - self.ma**2)/(2*self.mm)
+        return p_cm, sqrt(p_cm**2 + self.ma**2)
+
+    def simulate_flux(self, pi0_flux, energy_cut=0.0, angle_cut=np.pi, uniforms=None):
+        """pi0_flux: array of pi0 momenta [MeV], normalised to the pi0 rate.  uniforms: U[0,1) per momentum (parity)."""
+        self._reset_samples()
+        if self.ma > self.mm:
+            return
+        p = np.ascontiguousarray(pi0_flux, dtype=np.float64).ravel()
+        n = int(p.shape[0])
+        p_cm, e1_cm = self._cm()
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        rt = self._rt
+        with rt.activate():
+            E, F = rt.empty(n), rt.empty(n)
+            keep = torch.zeros(n, dtype=torch.uint8, device=rt.device)
+            if n:
+                d_u = rt.upload(np.asarray(uniforms, dtype=np.float64).ravel()) if uniforms is not None else None
+                N.call("alpk_pi0_flux", N.ptr(rt.upload(p)), n, N.ptr(d_u), C.c_uint64(seed), float(self.mm**2),
+                       float(self.ma**2), float(p_cm), float(e1_cm), float(energy_cut), float(angle_cut),
+                       float(self.meson_rate*self.br()/n), N.ptr(E), N.ptr(F), N.ptr(keep), rt.stream())
+                sel = torch.nonzero(keep, as_tuple=False).ravel()
+                E, F = E.index_select(0, sel).contiguous(), F.index_select(0, sel).contiguous()
+        self._set_production(E, F)
+
+    def simulate(self):
+        self._reset_samples()
+        if self.ma > self.mm:
+            return
+        p_cm, e1_cm = self._cm()
+        ns = int(self.n_samples)
+        rt = self._rt
+        with rt.activate():                       # constant arrays (fluxes.py:982-983): device fills, no arithmetic
+            E = torch.full((ns,), float(e1_cm), dtype=torch.float64, device=rt.device)
+            F = torch.full((ns,), float(self.meson_rate * self.br() * 1.0 / np.sum(self.n_samples)), dtype=torch.float64,
+                           device=rt.device)
+        self._set_production(E, F)
+
+    def propagate(self, is_isotropic=True):
+        self._ensure_production()
+        wgt = self._F if self._F is not None else torch.zeros(0, dtype=torch.float64, device=self._rt.device)
+        geom = self.det_area / (4*pi*self.det_dist**2)
+        rt = self._rt
+        n = int(wgt.shape[0])
+        with rt.activate():                       # float64 weights for this class (fluxes.py:985-991)
+            d, s_ = rt.empty(n), rt.empty(n)
+            N.call("alpk_scale", N.ptr(wgt), n, 0.0, N.ptr(d), rt.stream())
+            N.call("alpk_scale", N.ptr(wgt), n, float(geom) if is_isotropic else 1.0, N.ptr(s_), rt.stream())
+        self._D32, self._S32 = d, s_
+        for k in ("D32", "S32"):
+            self._host.pop(k, None)

@@ -57,6 +57,12 @@ class _EventGenerator:
     def pair_weights(self):
         return self._weights("pair", self.flux.scatter_axion_weight)
 
+    @staticmethod
+    def _need_f32(t, what):
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError(f"{what} is float64: flux classes that keep float64 weights (FluxPi0Isotropic) feed the "
+                            "dark-sector generators, which are outside this path")
+
     def _store(self, name, t):
         self._dev[name] = t
         self._hostcache.pop(name, None)
@@ -64,6 +70,8 @@ class _EventGenerator:
     def decays(self, days_exposure, threshold):
         """days*S_PER_DAY * decay_axion_weight * heaviside(E - threshold, 1), summed (generators.py:48-52, 88-92)."""
         ev = P.event_params(days_exposure, threshold)
+        self.flux._ensure_propagated()
+        self._need_f32(self.flux._D32, "decay_axion_weight")
         rate, evw = self.flux._decay_rate(ev, self.materialize_weights and not self.flux.fused)
         self._store("decay", evw)
         return np.float64(rate.item())
@@ -82,6 +90,7 @@ class _EventGenerator:
         n = 0 if fl._E is None else int(fl._E.shape[0])
         if fl._S32 is None or int(fl._S32.shape[0]) != n:
             raise ValueError("propagate() must run first: scatter_axion_weight does not match axion_energy")
+        self._need_f32(fl._S32, "scatter_axion_weight")
         ev = P.event_params(days_exposure, threshold)
         with rt.activate():
             rate = rt.empty(1)

@@ -234,6 +234,20 @@ int alpk_vol_int(const double* energy, const double* weight, uint64_t n, const a
                  double volume_over_n, double inv_mbm, float* decay_w32, float* scatter_w32,
                  double* decay_w64_or_null, double* scatter_w64_or_null, double* partials, void* stream);
 
+/* ---- small flux sources ---------------------------------------------------------------------------
+ * nuclear de-excitation lines: FluxNuclearIsotropic.simulate/br (fluxes.py:571-590).  rates4[n][4] = {E, rate, beta, eta}
+ * (rows with E > ma, filtered by the host); c0 = (j/(j+1))/(1+delta**2)/pi/ALPHA; expo = 2j+1. */
+int alpk_nuclear(const double* rates4, uint64_t n_rows, double ma2, double c0, double expo, double gann0, double gann1,
+                 double* out_energy, double* out_flux, void* stream);
+/* pi0 -> gamma a in flight: FluxPi0Isotropic.simulate_flux (fluxes.py:941-968).  One cos(theta*) draw per pi0 momentum
+ * (uniforms[n] in parity mode); keep[i] = 1 if the sample passes the energy / angle cuts (the caller compacts). */
+int alpk_pi0_flux(const double* momenta, uint64_t n, const double* uniforms, uint64_t seed, double mm2, double ma2,
+                  double p_cm, double e1_cm, double energy_cut, double angle_cut, double weight,
+                  double* out_energy, double* out_flux, uint8_t* keep, void* stream);
+
+/* out[i] = factor * x[i]  (float64 weights of FluxPi0Isotropic.propagate, fluxes.py:985-991) */
+int alpk_scale(const double* x, uint64_t n, double factor, double* out, void* stream);
+
 /* ---- weighted histogram: np.histogram(x, bins=edges, weights=w) (half-open bins, last bin closed) ------------------ */
 int alpk_hist(const double* x, const double* w64_or_null, const float* w32_or_null, uint64_t n,
               const double* edges, int n_edges, double* hist /* [n_edges-1], accumulated into */, void* stream);

@@ -460,6 +460,48 @@ def resonance_simulate(positron_flux, ma, g, target, n_samples, usrc, boson_type
 
 
 # ---------------------------------------------------------------------------------------------------------
+# fluxes.py:554-600 FluxNuclearIsotropic, fluxes.py:926-991 FluxPi0Isotropic
+# ---------------------------------------------------------------------------------------------------------
+M_PI0 = 134.98                                                                       # constants.py:42
+
+
+def nuclear_simulate(rates, ma, gann0, gann1, j=1, delta=0.0):
+    energy, flux = [], []
+    mu0, mu1 = 0.88, 4.71
+    for r in np.asarray(rates, dtype=np.float64):
+        if r[0] > ma:                                                                # fluxes.py:588
+            br = ((j / (j + 1)) / (1 + delta ** 2) / pi / ALPHA) \
+                * np.power(np.sqrt(r[0] ** 2 - ma ** 2) / r[0], 2 * j + 1) \
+                * np.power((gann0 * r[2] + gann1) / ((mu0 - 0.5) * r[2] + (mu1 - r[3])), 2)      # :571-577
+            energy.append(r[0]); flux.append(r[1] * br)
+    return np.array(energy), np.array(flux)
+
+
+def pi0_br(g, ma):                                                                   # fluxes.py:938-939
+    return 2 * g ** 2 * (1 - np.power(ma / M_PI0, 2)) ** 3 / np.sqrt(4 * pi * ALPHA)
+
+
+def pi0_simulate_flux(pi0_flux, ma, g, meson_rate, usrc, energy_cut=0.0, angle_cut=np.pi):
+    pi0_flux = np.asarray(pi0_flux, dtype=np.float64)
+    if ma > M_PI0:
+        return np.zeros(0), np.zeros(0)
+    p_cm = (M_PI0 ** 2 - ma ** 2) / (2 * M_PI0)
+    e1_cm = np.sqrt(p_cm ** 2 + ma ** 2)
+    cos_rnd = usrc.uniform(-1, 1, pi0_flux.shape[0])                                 # :953
+    energy, flux = [], []
+    for i, p in enumerate(pi0_flux):
+        beta = p / np.sqrt(p ** 2 + M_PI0 ** 2)
+        boost = np.power(1 - beta ** 2, -0.5)
+        e_lab = boost * (e1_cm + beta * p_cm * cos_rnd[i])
+        pz_lab = boost * (p_cm * cos_rnd[i] + beta * e1_cm)
+        angle_lab = np.arccos(pz_lab / np.sqrt(e_lab ** 2 - ma ** 2))
+        if e_lab < energy_cut or angle_lab > angle_cut:
+            continue
+        energy.append(e_lab); flux.append(meson_rate * pi0_br(g, ma) / pi0_flux.shape[0])
+    return np.array(energy), np.array(flux)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # cross_section_mc.py:669-685  lorentz_boost for a boost along +-z (the only case the in-scope flux classes
 # produce: parents and beams are on the z axis).  Row sums are evaluated in the order NumPy's 4x4 `mat @ pmu`
 # produces for rows with two non-zero terms.

@@ -404,6 +404,36 @@ def case_vol_int():
              decay_w32=d32, scatter_w32=s32, decay_w64=d64, scatter_w64=s64)
 
 
+def case_nuclear_pi0():
+    print("FluxNuclearIsotropic / FluxPi0Isotropic")
+    W = F.Material("W")
+    rates = np.array([[0.478, 1e10, 1.0, 0.5], [2.2, 3e9, 0.9, 0.4], [7.6, 1e8, 1.1, 0.6], [0.05, 1e12, 1.0, 0.5]])
+    fl = F.FluxNuclearIsotropic(rates, W, axion_mass=0.3, gann0=2e-4, gann1=1e-3, gae=1e-6, **GEOM_DEFAULT)
+    fl.simulate(j=1, delta=0.2)
+    d64, s64, d32, s32 = propagate_both(fl)
+    oE, oF = O.nuclear_simulate(rates, 0.3, 2e-4, 1e-3, 1, 0.2)
+    check("nuclear E", oE, fl.axion_energy, 0)
+    check("nuclear flux", oF, fl.axion_flux, 1e-15)
+    save("nuclear", rates=rates, ma=0.3, gann0=2e-4, gann1=1e-3, gae=1e-6, j=1, delta=0.2, axion_energy=fl.axion_energy,
+         axion_flux=fl.axion_flux, decay_w32=d32, scatter_w32=s32, decay_w64=d64, scatter_w64=s64)
+    rs = np.random.RandomState(3)
+    mom = 10 ** rs.uniform(0.5, 3.5, 400)
+    np.random.seed(17)
+    fp = F.FluxPi0Isotropic(pi0_rate=0.0259, boson_mass=30.0, coupling=1e-3, det_dist=20.0, det_area=2.0, det_length=1.0, target=W)
+    fp.simulate_flux(mom, energy_cut=50.0, angle_cut=0.3)
+    fp.propagate()
+    us = O.UniformSource(np.random.RandomState(17))
+    oE, oF = O.pi0_simulate_flux(mom, 30.0, 1e-3, 0.0259, us, 50.0, 0.3)
+    check("pi0 E", oE, fp.axion_energy, 1e-15)
+    check("pi0 flux", oF, fp.axion_flux, 1e-15)
+    save("pi0_flux", momenta=mom, ma=30.0, g=1e-3, rate=0.0259, energy_cut=50.0, angle_cut=0.3, uniforms=np.concatenate(us.log),
+         axion_energy=fp.axion_energy, axion_flux=fp.axion_flux, scatter_w=np.array(fp.scatter_axion_weight),
+         decay_w=np.array(fp.decay_axion_weight))
+    fr = F.FluxPi0Isotropic(pi0_rate=0.0259, boson_mass=30.0, coupling=1e-3, n_samples=5, target=W)
+    fr.simulate(); fr.propagate(is_isotropic=False)
+    save("pi0_rest", axion_energy=fr.axion_energy, axion_flux=fr.axion_flux, scatter_w=np.array(fr.scatter_axion_weight))
+
+
 if __name__ == "__main__":
     kat_scalars()
     case_primakoff()
@@ -414,4 +444,5 @@ if __name__ == "__main__":
     case_pairann()
     case_decay4()
     case_vol_int()
+    case_nuclear_pi0()
     print("all golden fixtures written; oracle pinned against the reference")

@@ -682,3 +682,39 @@ def test_c_abi_without_torch_tensors(A):
     assert b"alpk_propagate" in L.alpk_last_error()
     for p in dev.values():
         assert L.alpk_free(p) == 0
+
+
+# ---- further flux sources ----------------------------------------------------------------------------
+def test_nuclear_flux(A):
+    g = load_golden("nuclear")
+    fl = A.FluxNuclearIsotropic(g["rates"], A.Material("W"), axion_mass=0.3, gann0=float(g["gann0"]), gann1=float(g["gann1"]),
+                                gae=float(g["gae"]), keep_f64=True, **GEOM)
+    fl.simulate(j=1, delta=0.2)
+    assert np.array_equal(fl.axion_energy, g["axion_energy"])
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < TOL
+    fl.propagate()
+    assert max_rel(fl.scatter_axion_weight_f64 * GA, g["scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64 * GA, g["decay_w64"], g["scatter_w64"], TOL)
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    assert A.ElectronEventGenerator(fl, A.Material("Ar")).decays(100, 0.1) >= 0.0
+
+
+def test_pi0_flux(A):
+    g = load_golden("pi0_flux")
+    fp = A.FluxPi0Isotropic(pi0_rate=0.0259, boson_mass=30.0, coupling=1e-3, det_dist=20.0, det_area=2.0, det_length=1.0,
+                            target=A.Material("W"))
+    fp.simulate_flux(g["momenta"], energy_cut=50.0, angle_cut=0.3, uniforms=g["uniforms"])
+    assert max_rel(fp.axion_energy, g["axion_energy"]) < TOL
+    assert max_rel(fp.axion_flux, g["axion_flux"]) < TOL
+    fp.propagate()
+    assert fp.scatter_axion_weight.dtype == np.float64                 # this class keeps float64 weights
+    assert max_rel(fp.scatter_axion_weight, g["scatter_w"]) < 1e-15 and np.all(fp.decay_axion_weight == 0)
+    with pytest.raises(TypeError):
+        A.PhotonEventGenerator(fp, A.Material("Ar")).decays(100, 0.0)
+    r = load_golden("pi0_rest")
+    fr = A.FluxPi0Isotropic(pi0_rate=0.0259, boson_mass=30.0, coupling=1e-3, n_samples=5, target=A.Material("W"))
+    fr.simulate(); fr.propagate(is_isotropic=False)
+    assert max_rel(fr.axion_energy, r["axion_energy"]) < 1e-15 and max_rel(fr.scatter_axion_weight, r["scatter_w"]) < 1e-15
+    heavy = A.FluxPi0Isotropic(boson_mass=500.0, target=A.Material("W"))
+    heavy.simulate()
+    assert len(heavy.axion_energy) == 0                               # kinematically forbidden (fluxes.py:974-976)

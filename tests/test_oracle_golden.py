@@ -222,3 +222,15 @@ def test_propagate_iso_vol_int(name):
     p = O.propagate_iso_vol_int(g["axion_energy"], g["axion_flux"], ma, O.W_ee(nc, ma), np.power(nc / gg, 2), 4.0, geom)
     assert max_rel(p["decay_w64"], g["decay_w64"]) < 1e-14 and max_rel(p["scatter_w64"], g["scatter_w64"]) < 1e-14
     assert max_rel(p["decay_w"], g["decay_w32"]) == 0.0
+
+
+def test_nuclear_and_pi0():
+    g = load_golden("nuclear")
+    E, F = O.nuclear_simulate(g["rates"], float(g["ma"]), float(g["gann0"]), float(g["gann1"]), int(g["j"]), float(g["delta"]))
+    assert np.array_equal(E, g["axion_energy"]) and max_rel(F, g["axion_flux"]) < 1e-15 and E.shape[0] == 3
+    p = O.propagate(E, F, 0.3, O.W_ee(float(g["gae"]), 0.3), 1.0, geom_accept=GA, **GEOM)
+    assert max_rel(p["scatter_w"], g["scatter_w32"]) == 0.0
+    g = load_golden("pi0_flux")
+    E, F = O.pi0_simulate_flux(g["momenta"], 30.0, 1e-3, 0.0259, O.UniformSource(g["uniforms"]), 50.0, 0.3)
+    assert max_rel(E, g["axion_energy"]) < 1e-15 and max_rel(F, g["axion_flux"]) < 1e-15
+    assert 0 < E.shape[0] < g["momenta"].shape[0]                  # the cuts bite
