@@ -70,8 +70,7 @@ class _EventGenerator:
     def decays(self, days_exposure, threshold):
         """days*S_PER_DAY * decay_axion_weight * heaviside(E - threshold, 1), summed (generators.py:48-52, 88-92)."""
         ev = P.event_params(days_exposure, threshold)
-        self.flux._ensure_propagated()
-        self._need_f32(self.flux._D32, "decay_axion_weight")
+        self._need_f32(self.flux._D32, "decay_axion_weight")       # (None while a fused chain is still pending)
         rate, evw = self.flux._decay_rate(ev, self.materialize_weights and not self.flux.fused)
         self._store("decay", evw)
         return np.float64(rate.item())
