@@ -57,6 +57,12 @@ class PairAnnT(C.Structure):
                 ("ntad", C.c_double), ("hbarc2", C.c_double), ("n_samples", C.c_double)]
 
 
+class PairGammaT(C.Structure):
+    _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("ma4", C.c_double), ("me2", C.c_double), ("me4", C.c_double),
+                ("ep_min", C.c_double), ("nt", C.c_double), ("zc", C.c_double), ("n_samples", C.c_double),
+                ("max_t", C.c_double)]
+
+
 def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
@@ -140,6 +146,7 @@ _SIGNATURES = {
     "alpk_vol_int": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _U32, _D, _D, _P, _P, _P, _P, _P, _P], _I),
     "alpk_nuclear": ([_P, _U64, _D, _D, _D, _D, _D, _P, _P, _P], _I),
     "alpk_pi0_flux": ([_P, _U64, _P, _U64, _D, _D, _D, _D, _D, _D, _D, _P, _P, _P, _P], _I),
+    "alpk_pairgamma": ([_P, _P, _U64, _U32, _P, _P, _P, _I, C.POINTER(PairGammaT), _P, _P, _U64, _P, _P, _P], _I),
     "alpk_scale": ([_P, _U64, _D, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),

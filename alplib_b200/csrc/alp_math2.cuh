@@ -206,4 +206,63 @@ ALP_HD double pairann_sample(double u, const double* r, const PairGlobals& g, do
     return r[PA_GAM] * r[PA_E3] + r[PA_M03] * pz;                                // boost row 0
 }
 
+// ---- e+ e- -> gamma a through a virtual photon (fluxes.py:1058-1131, prod_xs.py:109-129) ----------------------------------
+struct PairGammaGlobals {
+    double ma, ma2, ma4;
+    double me2, me4;          // M_E**2, M_E**4
+    double ep_min;            // max((ma**2 - M_E**2)/(2*M_E), M_E)
+    double nt;                // ntarget_area_density * HBARC**2
+    double zc;                // z*4*pi*ALPHA*g**2  (left to right)
+    double n_samples;
+    double max_t;             // 5.0 radiation lengths (fluxes.py:1099,1103)
+};
+
+// fluxes.py:1078-1080 (note heaviside(., 0.0) here, 1.0 in the module-level track_length_prob)
+ALP_HD double track_length_prob0(double ei, double ef, double t) {
+    const double b = 4.0 / 3.0;
+    return heaviside(ei - ef, 0.0) * fabs(pow(log(ei / ef), b * t - 1) / (ei * tgamma(b * t)));
+}
+
+// prod_xs.py:109-129
+ALP_HD double epem_to_alp_photon_dsigma_de(double ea, double ep, const PairGammaGlobals& g) {
+    const double s = (2 * kME) * (kME + ep);
+    const double d = s - g.ma2;
+    const double ps = sqrt((d * d) / (4 * s));
+    const double a = s - 2 * g.me2;
+    const double pp = sqrt((a * a - 4 * g.me4) / (4 * s));
+    const double es = sqrt(ps * ps + g.ma2);
+    const double epc = sqrt(pp * pp + g.me2);
+    const double beta = sqrt(ep * ep - g.me2) / (kME + ep);
+    const double gam = pow(1 - beta * beta, -0.5);
+    const double ct = (ea / gam - es) / (beta * ps);
+    const double t = (g.ma2 + g.me2) - 2 * (epc * es - (pp * ps) * ct);
+    const double inner = ((2 * s) * g.me4 + (2 * g.me2) * ((g.ma4 - s * g.ma2) - (2 * s) * t))
+                         + s * (((((g.ma4 - (2 * g.ma2) * (s + t)) + s * s) + (2 * s) * t)) + 2 * (t * t));
+    const double m_st = (g.zc * inner) / (s * s);
+    const double jac = ((2 * pp) / gam) / beta;
+    return ((heaviside(ep - g.ep_min, 1.0) * jac) * m_st) / (((16 * kPi) * (s - 4 * g.me2)) * s);
+}
+
+// One sample of bin (center e_lab, width, dN/dE at the centre): u1 -> depth t, u2 -> smeared E+, u3 -> E_a.
+ALP_HD double pairgamma_sample(double u1, double u2, double u3, double e_lab, double width, double flux_c,
+                               const PairGammaGlobals& g, double& flux) {
+    const double t = 0.0 + (g.max_t - 0.0) * u1;                                 // fluxes.py:1099
+    const double ep = g.ep_min + (e_lab - g.ep_min) * u2;                        // :1100
+    const double fw = flux_c * track_length_prob0(e_lab, ep, t);                 // :1102, :1085-1086
+    const double pos_flux = (((width * 5.0) * (e_lab - g.ep_min)) * fw) / g.n_samples;   // :1103
+    const double beta = sqrt(ep * ep - g.me2) / (kME + ep);                      // :1118
+    const double gam = pow(1 - beta * beta, -0.5);
+    const double s = (2 * kME) * (kME + ep);
+    const double d = s - g.ma2;
+    const double ps = sqrt((d * d) / (4 * s));
+    const double es = sqrt(ps * ps + g.ma2);
+    const double es_min = gam * (es - ps * beta);                                // :1124
+    const double es_max = gam * (es + ps * beta);
+    const double ea = es_min + (es_max - es_min) * u3;                           // :1126
+    const double mc_vol = ((2 * gam) * beta) * ps;                               // :1127
+    const double cm = g.nt * epem_to_alp_photon_dsigma_de(ea, ep, g);            // :1129-1130
+    flux = (cm * pos_flux) * mc_vol;                                             // :1134
+    return ea;
+}
+
 }  // namespace alp

@@ -1,6 +1,7 @@
 // libalpk: small flux sources beyond the photon / e+- channels -- nuclear de-excitation lines (fluxes.py:554-600) and
 // pi0 -> gamma a two-body decay in flight (fluxes.py:926-991).  One thread per input row.
 #include "../../include/alpk.h"
+#include "alp_math2.cuh"
 #include "common.cuh"
 
 using namespace alp;
@@ -45,6 +46,35 @@ pi0_flux_kernel(const double* __restrict__ p, uint64_t n, const double* __restri
     }
 }
 
+// fluxes.py:1090-1134: thread = sample; bins are the positron-table bin centres above threshold (host-filtered)
+__global__ void __launch_bounds__(kThreads)
+pairgamma_kernel(const double* __restrict__ centers, const double* __restrict__ widths, uint64_t n_bins, uint32_t n_samples,
+                 const uint32_t* __restrict__ bin_ids, const double* __restrict__ pos_e, const double* __restrict__ pos_f,
+                 int n_pos, PairGammaGlobals g, const double* __restrict__ u_bins, const double* __restrict__ u_alp,
+                 uint64_t seed, double* __restrict__ out_e, double* __restrict__ out_f) {
+    const uint64_t n = n_bins * (uint64_t)n_samples;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t b = i / n_samples;
+        const uint32_t sidx = (uint32_t)(i - b * n_samples);
+        const double e_lab = __ldg(centers + b);
+        const double fc = interp(e_lab, pos_e, pos_f, n_pos, 0.0, 0.0);
+        double u1, u2, u3;
+        if (u_bins) {
+            u1 = __ldg(u_bins + (b * 2) * n_samples + sidx);        // [bin][2][n]: depths then smeared energies
+            u2 = __ldg(u_bins + (b * 2 + 1) * n_samples + sidx);
+            u3 = __ldg(u_alp + i);                                  // then one draw per sample, in sample order
+        } else {
+            const uint32_t rid = bin_ids ? __ldg(bin_ids + b) : (uint32_t)b;
+            uniform_2(seed, 9u, rid, sidx, u1, u2);
+            u3 = uniform_1(seed, 10u, rid, sidx);
+        }
+        double f;
+        out_e[i] = pairgamma_sample(u1, u2, u3, e_lab, __ldg(widths + b), fc, g, f);
+        out_f[i] = f;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 scale_kernel(const double* __restrict__ x, uint64_t n, double factor, double* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -54,6 +84,22 @@ scale_kernel(const double* __restrict__ x, uint64_t n, double factor, double* __
 }  // namespace alpk
 
 using namespace alpk;
+
+ALPK_EXPORT int alpk_pairgamma(const double* centers, const double* widths, uint64_t n_bins, uint32_t n_samples,
+                               const uint32_t* bin_ids, const double* pos_e, const double* pos_f, int n_pos,
+                               const alpk_pairgamma_t* h_par, const double* u_bins, const double* u_alp, uint64_t seed,
+                               double* out_energy, double* out_flux, void* stream) {
+    if (!h_par || !out_energy || !out_flux) { set_error("alpk_pairgamma: null argument"); return 2; }
+    if (n_bins == 0 || n_samples == 0) return 0;
+    if (!centers || !widths || !pos_e || !pos_f || n_pos < 1) { set_error("alpk_pairgamma: null input"); return 2; }
+    if ((u_bins == nullptr) != (u_alp == nullptr)) { set_error("alpk_pairgamma: inject both uniform blocks or none"); return 2; }
+    PairGammaGlobals g;
+    g.ma = h_par->ma; g.ma2 = h_par->ma2; g.ma4 = h_par->ma4; g.me2 = h_par->me2; g.me4 = h_par->me4; g.ep_min = h_par->ep_min;
+    g.nt = h_par->nt; g.zc = h_par->zc; g.n_samples = h_par->n_samples; g.max_t = h_par->max_t;
+    pairgamma_kernel<<<grid_for(n_bins * (uint64_t)n_samples, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
+        centers, widths, n_bins, n_samples, bin_ids, pos_e, pos_f, n_pos, g, u_bins, u_alp, seed, out_energy, out_flux);
+    return check_launch("alpk_pairgamma");
+}
 
 ALPK_EXPORT int alpk_scale(const double* x, uint64_t n, double factor, double* out, void* stream) {
     if (n == 0) return 0;

@@ -39,7 +39,7 @@ _EMPTY64 = np.zeros(0, dtype=np.float64)
 
 __all__ = ["AxionFlux", "FluxPrimakoffIsotropic", "FluxComptonIsotropic", "FluxBremIsotropic",
            "FluxResonanceIsotropic", "FluxPairAnnihilationIsotropic", "FluxNuclearIsotropic", "FluxPi0Isotropic",
-           "track_length_prob"]
+           "FluxPairAnnihilationGamma", "track_length_prob"]
 
 
 def _as_flux_table(flux, name):
@@ -901,3 +901,71 @@ class FluxPi0Isotropic(AxionFlux):
         self._D32, self._S32 = d, s_
         for k in ("D32", "S32"):
             self._host.pop(k, None)
+
+
+class FluxPairAnnihilationGamma(AxionFlux):
+    """
+    Associated production e+ e- -> gamma a through a virtual photon (photon coupling) from a positron flux, with
+    track-length smearing of the positron energy (reference: fluxes.py:1058-1148).  Per positron-table bin centre above
+    threshold: `n_samples` (depth, smeared energy) draws, then one E_a draw per smeared positron.
+    """
+    def __init__(self, positron_flux=[1., 0.], target=None,
+                 target_radiation_length=6.76, det_dist=4., det_length=0.2, det_area=0.04,
+                 axion_mass=0.1, axion_coupling=1e-3, n_samples=100, is_isotropic=True, **kwargs):
+        target = Material("W") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, n_samples, **_split_kwargs(kwargs))
+        self.positron_flux = positron_flux
+        pf = np.asarray(positron_flux, dtype=np.float64)
+        self.positron_flux_bin_widths = pf[1:, 0] - pf[:-1, 0]
+        self.positron_flux_bin_centers = (pf[1:, 0] + pf[:-1, 0])/2
+        self.gagamma = axion_coupling
+        self.ntarget_area_density = target_radiation_length * AVOGADRO / (2*target.z[0])
+        self.is_isotropic = is_isotropic
+        self.row_offset = 0
+
+    def positron_flux_dN_dE(self, energy):
+        pf = np.asarray(self.positron_flux, dtype=np.float64)
+        return np.interp(energy, pf[:, 0], pf[:, 1], left=0.0, right=0.0)
+
+    def simulate(self, uniforms=None):
+        """uniforms (parity mode): flat stream in the reference's draw order -- per bin above threshold `n_samples`
+        depths then `n_samples` smeared energies (fluxes.py:1099-1100), followed by one E_a draw per sample (:1126)."""
+        self._reset_samples()
+        pf = _as_flux_table(self.positron_flux, "positron_flux")
+        ma, ns = self.ma, int(self.n_samples)
+        ep_min = max((ma**2 - M_E**2)/(2*M_E), M_E)                              # fluxes.py:1093
+        keep = ~(self.positron_flux_bin_centers < ep_min)                        # :1096
+        bins = np.nonzero(keep)[0]
+        nb = int(bins.shape[0])
+        par = N.PairGammaT()
+        par.ma, par.ma2, par.ma4 = float(ma), float(ma**2), float(ma**4)
+        par.me2, par.me4 = float(M_E**2), float(M_E**4)
+        par.ep_min = float(ep_min)
+        par.nt = float(self.ntarget_area_density * HBARC**2)
+        par.zc = float(self.target_z * 4*pi*ALPHA*self.gagamma**2)
+        par.n_samples, par.max_t = float(ns), 5.0
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        rt = self._rt
+        n = nb * ns
+        with rt.activate():
+            E, F = rt.empty(n), rt.empty(n)
+            if n:
+                d_ub = d_ua = None
+                if uniforms is not None:
+                    u = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+                    if u.shape[0] != 3 * n:
+                        raise ValueError(f"uniforms must hold 3*n_bins*n_samples = {3 * n} variates")
+                    d_ub, d_ua = rt.upload(u[:2 * n]), rt.upload(u[2 * n:])
+                N.call("alpk_pairgamma", N.ptr(rt.upload(self.positron_flux_bin_centers[keep])),
+                       N.ptr(rt.upload(self.positron_flux_bin_widths[keep])), nb, ns,
+                       N.ptr(rt.upload((bins + int(self.row_offset)).astype(np.uint32), np.uint32)),
+                       N.ptr(rt.upload(pf[:, 0])), N.ptr(rt.upload(pf[:, 1])), int(pf.shape[0]), C.byref(par),
+                       N.ptr(d_ub), N.ptr(d_ua), C.c_uint64(seed), N.ptr(E), N.ptr(F), rt.stream())
+        self._set_production(E, F)
+
+    def propagate(self, new_coupling=None):
+        geom = self._geom_accept() if self.is_isotropic else None
+        if new_coupling is not None:
+            self._propagate(W_gg(new_coupling, self.ma), power(new_coupling/self.gagamma, 2), geom)
+        else:
+            self._propagate(W_gg(self.gagamma, self.ma), 1.0, geom)

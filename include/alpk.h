@@ -245,6 +245,23 @@ int alpk_pi0_flux(const double* momenta, uint64_t n, const double* uniforms, uin
                   double p_cm, double e1_cm, double energy_cut, double angle_cut, double weight,
                   double* out_energy, double* out_flux, uint8_t* keep, void* stream);
 
+/* e+ e- -> gamma a through a virtual photon: FluxPairAnnihilationGamma.simulate (fluxes.py:1090-1134) with
+ * epem_to_alp_photon_dsigma_de (prod_xs.py:109-129).  bins = positron-table bin centres above threshold (host-filtered),
+ * n_samples (depth, smeared E+, E_a) draws each.  Parity mode: u_bins[n_bins][2][n_samples] then u_alp[n_bins*n_samples]. */
+typedef struct {
+    double ma, ma2, ma4;
+    double me2, me4;
+    double ep_min;           /* max((ma**2 - M_E**2)/(2*M_E), M_E) */
+    double nt;               /* ntarget_area_density * HBARC**2 */
+    double zc;               /* z*4*pi*ALPHA*g**2 */
+    double n_samples;
+    double max_t;            /* 5.0 */
+} alpk_pairgamma_t;
+int alpk_pairgamma(const double* centers, const double* widths, uint64_t n_bins, uint32_t n_samples,
+                   const uint32_t* bin_ids, const double* pos_e, const double* pos_f, int n_pos,
+                   const alpk_pairgamma_t* h_par, const double* u_bins, const double* u_alp, uint64_t seed,
+                   double* out_energy, double* out_flux, void* stream);
+
 /* out[i] = factor * x[i]  (float64 weights of FluxPi0Isotropic.propagate, fluxes.py:985-991) */
 int alpk_scale(const double* x, uint64_t n, double factor, double* out, void* stream);
 

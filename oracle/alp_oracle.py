@@ -501,6 +501,61 @@ def pi0_simulate_flux(pi0_flux, ma, g, meson_rate, usrc, energy_cut=0.0, angle_c
     return np.array(energy), np.array(flux)
 
 
+def epem_to_alp_photon_dsigma_de(ea, ep, g=1.0, ma=1.0, z=1):                        # prod_xs.py:109-129
+    s = 2 * M_E * (M_E + ep)
+    ps_cm = np.sqrt((s - ma ** 2) ** 2 / (4 * s))
+    pp_cm = np.sqrt(((s - 2 * M_E ** 2) ** 2 - 4 * M_E ** 4) / (4 * s))
+    es_cm = np.sqrt(ps_cm ** 2 + ma ** 2)
+    ep_cm = np.sqrt(pp_cm ** 2 + M_E ** 2)
+    beta = np.sqrt(ep ** 2 - M_E ** 2) / (M_E + ep)
+    gamma = np.power(1 - beta ** 2, -0.5)
+    costheta = (ea / gamma - es_cm) / (beta * ps_cm)
+    t = ma ** 2 + M_E ** 2 - 2 * (ep_cm * es_cm - pp_cm * ps_cm * costheta)
+    m_st = z * 4 * pi * ALPHA * g ** 2 * (2 * s * M_E ** 4 + 2 * M_E ** 2 * (ma ** 4 - s * ma ** 2 - 2 * s * t)
+                                          + s * (ma ** 4 - 2 * ma ** 2 * (s + t) + s ** 2 + 2 * s * t + 2 * t ** 2)) / s ** 2
+    jacobian = 2 * pp_cm / gamma / beta
+    return np.heaviside(ep - max((ma ** 2 - M_E ** 2) / (2 * M_E), M_E), 1.0) * jacobian * m_st / (16 * pi * (s - 4 * M_E ** 2) * s)
+
+
+def pairgamma_simulate(positron_flux, ma, g, target, n_samples, usrc, target_radiation_length=6.76):
+    """FluxPairAnnihilationGamma.simulate (fluxes.py:1090-1134)."""
+    pf = np.asarray(positron_flux, dtype=np.float64)
+    widths = pf[1:, 0] - pf[:-1, 0]
+    centers = (pf[1:, 0] + pf[:-1, 0]) / 2
+    z = target.z[0]
+    ntad = target_radiation_length * AVOGADRO / (2 * z)
+    ep_min = max((ma ** 2 - M_E ** 2) / (2 * M_E), M_E)
+    sm_e, sm_w = [], []
+    with np.errstate(all="ignore"):
+        for i in range(centers.shape[0]):
+            ep_lab = centers[i]
+            if ep_lab < ep_min:
+                continue
+            t_depths = usrc.uniform(0.0, 5.0, n_samples)
+            smeared = usrc.uniform(ep_min, ep_lab, n_samples)
+            b = 4 / 3
+            tlp = np.heaviside(ep_lab - smeared, 0.0) * abs(np.power(np.log(ep_lab / smeared), b * t_depths - 1)
+                                                           / (ep_lab * _gamma(b * t_depths)))
+            fw = np.interp(ep_lab, pf[:, 0], pf[:, 1], left=0.0, right=0.0) * tlp
+            sm_w.extend(widths[i] * 5.0 * (ep_lab - ep_min) * fw / n_samples)
+            sm_e.extend(smeared)
+        energy, flux = [], []
+        for ep, pos_flux in zip(sm_e, sm_w):
+            beta = np.sqrt(ep ** 2 - M_E ** 2) / (M_E + ep)
+            gamma = np.power(1 - beta ** 2, -0.5)
+            s = 2 * M_E * (M_E + ep)
+            ps_cm = np.sqrt((s - ma ** 2) ** 2 / (4 * s))
+            es_cm = np.sqrt(ps_cm ** 2 + ma ** 2)
+            es_min = gamma * (es_cm - ps_cm * beta)
+            es_max = gamma * (es_cm + ps_cm * beta)
+            ea = usrc.uniform(es_min, es_max, 1)
+            mc_vol = 2 * gamma * beta * ps_cm
+            cm = (ntad * HBARC ** 2) * epem_to_alp_photon_dsigma_de(ea, ep, g, ma, z)
+            energy.extend(ea)
+            flux.extend(cm * pos_flux * mc_vol)
+    return np.array(energy), np.array(flux)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # cross_section_mc.py:669-685  lorentz_boost for a boost along +-z (the only case the in-scope flux classes
 # produce: parents and beams are on the z axis).  Row sums are evaluated in the order NumPy's 4x4 `mat @ pmu`

@@ -434,6 +434,23 @@ def case_nuclear_pi0():
     save("pi0_rest", axion_energy=fr.axion_energy, axion_flux=fr.axion_flux, scatter_w=np.array(fr.scatter_axion_weight))
 
 
+def case_pairgamma():
+    print("FluxPairAnnihilationGamma")
+    C = F.Material("C")
+    e = np.linspace(5.0, 3000.0, 14)
+    pfx = np.stack([e, 1e11 * np.exp(-e / 900)], axis=1)
+    np.random.seed(31)
+    fl = F.FluxPairAnnihilationGamma(pfx, C, target_radiation_length=42.7, axion_mass=8.0, axion_coupling=1e-5, n_samples=6, **GEOM_DUNE)
+    fl.simulate()
+    d64, s64, d32, s32 = propagate_both(fl)
+    us = O.UniformSource(np.random.RandomState(31))
+    oE, oF = O.pairgamma_simulate(pfx, 8.0, 1e-5, O.Material("C"), 6, us, 42.7)
+    check("pairgamma E", oE, fl.axion_energy, 1e-15)
+    check("pairgamma flux", oF, fl.axion_flux, 1e-13)
+    save("pairgamma", positron_flux=pfx, ma=8.0, g=1e-5, n_samples=6, rad_length=42.7, uniforms=np.concatenate([np.atleast_1d(x) for x in us.log]),
+         axion_energy=fl.axion_energy, axion_flux=fl.axion_flux, decay_w32=d32, scatter_w32=s32, decay_w64=d64, scatter_w64=s64)
+
+
 if __name__ == "__main__":
     kat_scalars()
     case_primakoff()
@@ -445,4 +462,5 @@ if __name__ == "__main__":
     case_decay4()
     case_vol_int()
     case_nuclear_pi0()
+    case_pairgamma()
     print("all golden fixtures written; oracle pinned against the reference")

@@ -718,3 +718,22 @@ def test_pi0_flux(A):
     heavy = A.FluxPi0Isotropic(boson_mass=500.0, target=A.Material("W"))
     heavy.simulate()
     assert len(heavy.axion_energy) == 0                               # kinematically forbidden (fluxes.py:974-976)
+
+
+def test_pair_annihilation_gamma(A):
+    g = load_golden("pairgamma")
+    ns = int(g["n_samples"])
+    fl = A.FluxPairAnnihilationGamma(g["positron_flux"], A.Material("C"), target_radiation_length=float(g["rad_length"]),
+                                     axion_mass=float(g["ma"]), axion_coupling=float(g["g"]), n_samples=ns, keep_f64=True, **GEOM_DUNE)
+    fl.simulate(uniforms=g["uniforms"])
+    assert max_rel(fl.axion_energy, g["axion_energy"]) < TOL
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < TOL
+    fl.propagate()
+    assert max_rel(fl.scatter_axion_weight_f64 * GA_DUNE, g["scatter_w64"]) < TOL
+    assert_decay_close(fl.decay_axion_weight_f64 * GA_DUNE, g["decay_w64"], g["scatter_w64"], TOL)
+    assert max_rel(fl.scatter_axion_weight, g["scatter_w32"]) <= F32
+    # free-running mode: finite, positive, reproducible with the seed
+    a = A.FluxPairAnnihilationGamma(g["positron_flux"], A.Material("C"), axion_mass=8.0, axion_coupling=1e-5, n_samples=500, seed=5, **GEOM_DUNE)
+    b = A.FluxPairAnnihilationGamma(g["positron_flux"], A.Material("C"), axion_mass=8.0, axion_coupling=1e-5, n_samples=500, seed=5, **GEOM_DUNE)
+    a.simulate(); b.simulate()
+    assert np.array_equal(a.axion_flux, b.axion_flux) and np.all(np.isfinite(a.axion_flux)) and np.sum(a.axion_flux) > 0

@@ -288,3 +288,27 @@ def test_exp_fast_accuracy(hostcheck):
     with np.errstate(all="ignore"):
         e = np.exp(y)
     assert np.array_equal(o[~np.isnan(e)], e[~np.isnan(e)]) and np.isnan(o[4])
+
+
+def test_pairgamma(hostcheck):
+    g = load_golden("pairgamma")
+    pf, ma, gg, ns = g["positron_flux"], float(g["ma"]), float(g["g"]), int(g["n_samples"])
+    widths, centers = pf[1:, 0] - pf[:-1, 0], (pf[1:, 0] + pf[:-1, 0]) / 2
+    ep_min = max((ma ** 2 - O.M_E ** 2) / (2 * O.M_E), O.M_E)
+    keep = ~(centers < ep_min)
+    par = N.PairGammaT()
+    par.ma, par.ma2, par.ma4, par.me2, par.me4 = ma, ma ** 2, ma ** 4, O.M_E ** 2, O.M_E ** 4
+    par.ep_min = ep_min
+    par.nt = float(g["rad_length"]) * O.AVOGADRO / (2 * 6) * O.HBARC ** 2
+    par.zc = np.int64(6) * 4 * np.pi * O.ALPHA * gg ** 2
+    par.n_samples, par.max_t = float(ns), 5.0
+    nb = int(keep.sum()); n = nb * ns
+    u = np.ascontiguousarray(g["uniforms"])
+    assert u.shape[0] == 3 * n and 0 < nb < centers.shape[0]
+    oe, of = np.empty(n), np.empty(n)
+    c, w = np.ascontiguousarray(centers[keep]), np.ascontiguousarray(widths[keep])
+    pe, pfl = np.ascontiguousarray(pf[:, 0]), np.ascontiguousarray(pf[:, 1])
+    hostcheck.hc_pairgamma(dptr(c), dptr(w), C.c_uint64(nb), C.c_uint32(ns), dptr(pe), dptr(pfl), pe.shape[0], C.byref(par),
+                           dptr(np.ascontiguousarray(u[:2 * n])), dptr(np.ascontiguousarray(u[2 * n:])), dptr(oe), dptr(of))
+    assert max_rel(oe, g["axion_energy"]) < 1e-13
+    assert max_rel(of, g["axion_flux"]) < TOL
