@@ -817,7 +817,8 @@ class FluxNuclearIsotropic(AxionFlux):
         with rt.activate():
             E, F = rt.empty(n), rt.empty(n)
             if n:
-                N.call("alpk_nuclear", N.ptr(rt.upload(rows.ravel())), n, float(self.ma**2), float(c0), float(2*j + 1),
+                d_rows = rt.upload(rows.ravel())
+                N.call("alpk_nuclear", N.ptr(d_rows), n, float(self.ma**2), float(c0), float(2*j + 1),
                        float(self.gann0), float(self.gann1), N.ptr(E), N.ptr(F), rt.stream())
         self._set_production(E, F)
 
@@ -868,7 +869,8 @@ class FluxPi0Isotropic(AxionFlux):
             keep = torch.zeros(n, dtype=torch.uint8, device=rt.device)
             if n:
                 d_u = rt.upload(np.asarray(uniforms, dtype=np.float64).ravel()) if uniforms is not None else None
-                N.call("alpk_pi0_flux", N.ptr(rt.upload(p)), n, N.ptr(d_u), C.c_uint64(seed), float(self.mm**2),
+                d_p = rt.upload(p)
+                N.call("alpk_pi0_flux", N.ptr(d_p), n, N.ptr(d_u), C.c_uint64(seed), float(self.mm**2),
                        float(self.ma**2), float(p_cm), float(e1_cm), float(energy_cut), float(angle_cut),
                        float(self.meson_rate*self.br()/n), N.ptr(E), N.ptr(F), N.ptr(keep), rt.stream())
                 sel = torch.nonzero(keep, as_tuple=False).ravel()
@@ -956,11 +958,13 @@ class FluxPairAnnihilationGamma(AxionFlux):
                     if u.shape[0] != 3 * n:
                         raise ValueError(f"uniforms must hold 3*n_bins*n_samples = {3 * n} variates")
                     d_ub, d_ua = rt.upload(u[:2 * n]), rt.upload(u[2 * n:])
-                N.call("alpk_pairgamma", N.ptr(rt.upload(self.positron_flux_bin_centers[keep])),
-                       N.ptr(rt.upload(self.positron_flux_bin_widths[keep])), nb, ns,
-                       N.ptr(rt.upload((bins + int(self.row_offset)).astype(np.uint32), np.uint32)),
-                       N.ptr(rt.upload(pf[:, 0])), N.ptr(rt.upload(pf[:, 1])), int(pf.shape[0]), C.byref(par),
-                       N.ptr(d_ub), N.ptr(d_ua), C.c_uint64(seed), N.ptr(E), N.ptr(F), rt.stream())
+                # (keep every uploaded tensor referenced until the launch: temporaries would be recycled by the allocator)
+                d_c, d_w = rt.upload(self.positron_flux_bin_centers[keep]), rt.upload(self.positron_flux_bin_widths[keep])
+                d_ids = rt.upload((bins + int(self.row_offset)).astype(np.uint32), np.uint32)
+                d_pe, d_pf = rt.upload(pf[:, 0]), rt.upload(pf[:, 1])
+                N.call("alpk_pairgamma", N.ptr(d_c), N.ptr(d_w), nb, ns, N.ptr(d_ids), N.ptr(d_pe), N.ptr(d_pf),
+                       int(pf.shape[0]), C.byref(par), N.ptr(d_ub), N.ptr(d_ua), C.c_uint64(seed), N.ptr(E), N.ptr(F),
+                       rt.stream())
         self._set_production(E, F)
 
     def propagate(self, new_coupling=None):

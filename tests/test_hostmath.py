@@ -304,7 +304,7 @@ def test_pairgamma(hostcheck):
     par.n_samples, par.max_t = float(ns), 5.0
     nb = int(keep.sum()); n = nb * ns
     u = np.ascontiguousarray(g["uniforms"])
-    assert u.shape[0] == 3 * n and 0 < nb < centers.shape[0]
+    assert u.shape[0] == 3 * n and 0 < nb <= centers.shape[0]
     oe, of = np.empty(n), np.empty(n)
     c, w = np.ascontiguousarray(centers[keep]), np.ascontiguousarray(widths[keep])
     pe, pfl = np.ascontiguousarray(pf[:, 0]), np.ascontiguousarray(pf[:, 1])
