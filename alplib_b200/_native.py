@@ -17,6 +17,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 SCRATCH_DOUBLES = 16384
 COMPTON_NP = 12
 PARENT_NP = 6
+PARENT_GENERAL_NP = 20
 BREM_NP = 6
 PAIRANN_NP = 11
 GL_POINTS = 32
@@ -139,6 +140,7 @@ _SIGNATURES = {
                               C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),
     "alpk_decay_parent_rows": ([_P, _P, _U64, _D, C.POINTER(EventT), _U32, _P, _P], _I),
     "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _I, _P, _P, _P, _P], _I),
+    "alpk_decay2body_general": ([_P, _P, _U64, _D, _D, _U32, _P, _P, _U64, _P, _P, _P, _P, _P, _P], _I),
     "alpk_scan_tiles": ([_U32, _U32], _U32),
     "alpk_scan": ([_I, _P, _P, _U32, _U32, _P, _P, _I, _P, _P, _I, _P, _P, _I, _D, _D, _D, _U32, _U64,
                    C.POINTER(PropT), C.POINTER(EventT), _P, _P, _P, _P], _I),

@@ -400,6 +400,56 @@ ALP_HD void decay_event(double u1, double u2, const double* p, double* p1, doubl
     p2[3] = m03 * ecm + m33 * (-pz);
 }
 
+// ---- general 2-body decay: parent with arbitrary direction, daughter masses m1, m2 -------------------------------------------
+// (Decay2Body.__init__/decay cross_section_mc.py:496-544 with the dense 4x4 lorentz_boost :669-685; used by parents
+// with a polar angle, generators.py:117-121, and by FluxNeutralMeson2BodyDecay fluxes.py:1026-1031)
+enum ParentGRow { PG_MAT = 0, PG_E1 = 16, PG_E2, PG_PCM, PG_W, PG_NP };
+
+ALP_HD void decay_parent_params_general(double e, double px, double py, double pz, double m1, double m2, double w,
+                                        double* out) {
+    const double mp = sqrt(((e * e - px * px) - py * py) - pz * pz);              // LorentzVector.mass() :113-114
+    const double mp2 = mp * mp;
+    const double dm = m2 - m1, sm = m2 + m1;
+    const double pcm = sqrt((mp2 - dm * dm) * (mp2 - sm * sm)) / (2 * mp);         // :524
+    out[PG_E1] = sqrt(pcm * pcm + m1 * m1);                                        // :525
+    out[PG_E2] = sqrt(pcm * pcm + m2 * m2);                                        // :526
+    out[PG_PCM] = pcm;
+    out[PG_W] = w;
+    const double vx = -(px / e), vy = -(py / e), vz = -(pz / e);                   // :532  v_in = -velocity
+    const double beta = sqrt((vx * vx + vy * vy) + vz * vz);                       // Vector3.mag :59-60
+    double* m = out + PG_MAT;
+    if (beta == 0.0) {                                                             // :678-679 momentum returned unchanged
+        for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0;
+        return;
+    }
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+    if (!(beta < 1e-40)) { n0 = vx / beta; n1 = vy / beta; n2 = vz / beta; }       // unit_vec :49-53
+    const double g = 1 / sqrt(1 - beta * beta);                                    // :680
+    const double gb = (-g) * beta, gm1 = g - 1;
+    m[0] = g;        m[1] = gb * n0;              m[2] = gb * n1;              m[3] = gb * n2;
+    m[4] = gb * n0;  m[5] = 1 + (gm1 * n0) * n0;  m[6] = (gm1 * n0) * n1;      m[7] = (gm1 * n0) * n2;
+    m[8] = gb * n1;  m[9] = (gm1 * n1) * n0;      m[10] = 1 + (gm1 * n1) * n1; m[11] = (gm1 * n1) * n2;
+    m[12] = gb * n2; m[13] = (gm1 * n2) * n0;     m[14] = (gm1 * n2) * n1;     m[15] = 1 + (gm1 * n2) * n2;
+}
+
+ALP_HD void boost_apply(const double* m, double p0, double p1, double p2, double p3, double* out) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)                                                    // mat @ pmu, row by row
+        out[r] = ((m[4 * r] * p0 + m[4 * r + 1] * p1) + m[4 * r + 2] * p2) + m[4 * r + 3] * p3;
+}
+
+// One decay; q1/q2 = lab 4-vectors (E, px, py, pz); returns theta of daughter 1 (LorentzVector.theta :131-132)
+ALP_HD double decay_event_general(double u1, double u2, const double* row, double* q1, double* q2) {
+    const double phi = kTwoPi * u1;
+    const double th = acos(1 - 2 * u2);
+    const double pcm = row[PG_PCM];
+    const double px = (pcm * cos(phi)) * sin(th), py = (pcm * sin(phi)) * sin(th), pz = pcm * cos(th);
+    boost_apply(row + PG_MAT, row[PG_E1], px, py, pz, q1);
+    boost_apply(row + PG_MAT, row[PG_E2], -px, -py, -pz, q2);
+    const double pm = sqrt((q1[1] * q1[1] + q1[2] * q1[2]) + q1[3] * q1[3]);
+    return acos(q1[3] / pm);
+}
+
 // Fast mode: cos(theta) = 1-2u and sin(theta) = 2 sqrt(u(1-u)) directly (no acos -> sincos round trip) and
 // sincospi(2 u1) for the azimuth.  |dp|/E_parent vs the reference ~1e-15.
 ALP_HD void decay_event_fast(double u1, double u2, const double* p, double* p1, double* p2) {

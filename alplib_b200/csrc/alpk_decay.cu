@@ -119,6 +119,51 @@ decay2body_kernel(const DecayArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// general 2-body decay (arbitrary parent direction, massive daughters): one thread per event, dense 4x4 boost
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+decay_general_rows_kernel(const double* __restrict__ p4, const double* __restrict__ w, uint64_t n, double m1, double m2,
+                          double* __restrict__ table) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double row[PG_NP];
+        decay_parent_params_general(__ldg(p4 + 4 * i), __ldg(p4 + 4 * i + 1), __ldg(p4 + 4 * i + 2), __ldg(p4 + 4 * i + 3),
+                                    m1, m2, w ? __ldg(w + i) : 1.0, row);
+        for (int k = 0; k < PG_NP; ++k) table[i * PG_NP + k] = row[k];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+decay_general_kernel(const double* __restrict__ table, uint64_t n_parents, uint32_t n_samples,
+                     const uint32_t* __restrict__ row_ids, const double* __restrict__ uniforms, uint64_t seed,
+                     double* __restrict__ p1, double* __restrict__ p2, double* __restrict__ wout,
+                     double* __restrict__ theta1) {
+    const uint64_t n = n_parents * (uint64_t)n_samples;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r = i / n_samples;
+        const uint32_t s = (uint32_t)(i - r * n_samples);
+        double row[PG_NP];
+        for (int k = 0; k < PG_NP; ++k) row[k] = __ldg(table + r * PG_NP + k);
+        double u1, u2;
+        if (uniforms) {
+            u1 = __ldg(uniforms + (r * 2) * n_samples + s);
+            u2 = __ldg(uniforms + (r * 2 + 1) * n_samples + s);
+        } else {
+            uniform_2(seed, kTagDecay2, row_ids ? __ldg(row_ids + r) : (uint32_t)r, s, u1, u2);
+        }
+        double q1[4], q2[4];
+        const double th = decay_event_general(u1, u2, row, q1, q2);
+        for (int c = 0; c < 4; ++c) {
+            p1[(uint64_t)c * n + i] = q1[c];
+            if (p2) p2[(uint64_t)c * n + i] = q2[c];
+        }
+        if (wout) wout[i] = row[PG_W];
+        if (theta1) theta1[i] = th;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // weighted histogram, np.histogram(x, bins=edges, weights=w): bin k = [edges[k], edges[k+1]), last bin closed
 // ---------------------------------------------------------------------------------------------------------------
 template <bool SMEM>
@@ -185,6 +230,21 @@ ALPK_EXPORT int alpk_decay2body(const double* row_table, uint64_t n_parents, uin
     if (uniforms) { if (fast) decay2body_kernel<true, true><<<grid, kThreads, 0, st>>>(a); else decay2body_kernel<true, false><<<grid, kThreads, 0, st>>>(a); }
     else { if (fast) decay2body_kernel<false, true><<<grid, kThreads, 0, st>>>(a); else decay2body_kernel<false, false><<<grid, kThreads, 0, st>>>(a); }
     return check_launch("alpk_decay2body");
+}
+
+ALPK_EXPORT int alpk_decay2body_general(const double* parents_p4, const double* parent_w, uint64_t n_parents, double m1,
+                                        double m2, uint32_t n_samples, const uint32_t* row_ids, const double* uniforms,
+                                        uint64_t seed, double* row_table, double* p1, double* p2, double* w,
+                                        double* theta1, void* stream) {
+    static_assert(PG_NP == ALPK_PARENT_GENERAL_NP, "header/table layout mismatch");
+    if (!parents_p4 || !row_table || !p1) { set_error("alpk_decay2body_general: null argument"); return 2; }
+    if (n_parents == 0 || n_samples == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    decay_general_rows_kernel<<<grid_for(n_parents, kThreads, 4), kThreads, 0, st>>>(parents_p4, parent_w, n_parents, m1, m2, row_table);
+    if (check_launch("alpk_decay2body_general(rows)")) return 1;
+    decay_general_kernel<<<grid_for(n_parents * (uint64_t)n_samples, kThreads, 8), kThreads, 0, st>>>(
+        row_table, n_parents, n_samples, row_ids, uniforms, seed, p1, p2, w, theta1);
+    return check_launch("alpk_decay2body_general");
 }
 
 ALPK_EXPORT int alpk_hist(const double* x, const double* w64, const float* w32, uint64_t n, const double* edges,

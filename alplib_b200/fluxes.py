@@ -39,7 +39,7 @@ _EMPTY64 = np.zeros(0, dtype=np.float64)
 
 __all__ = ["AxionFlux", "FluxPrimakoffIsotropic", "FluxComptonIsotropic", "FluxBremIsotropic",
            "FluxResonanceIsotropic", "FluxPairAnnihilationIsotropic", "FluxNuclearIsotropic", "FluxPi0Isotropic",
-           "FluxPairAnnihilationGamma", "track_length_prob"]
+           "FluxPairAnnihilationGamma", "FluxNeutralMeson2BodyDecay", "track_length_prob"]
 
 
 def _as_flux_table(flux, name):
@@ -973,3 +973,103 @@ class FluxPairAnnihilationGamma(AxionFlux):
             self._propagate(W_gg(new_coupling, self.ma), power(new_coupling/self.gagamma, 2), geom)
         else:
             self._propagate(W_gg(self.gagamma, self.ma), 1.0, geom)
+
+
+class FluxNeutralMeson2BodyDecay(AxionFlux):
+    """
+    ALP / dark-photon flux from neutral mesons decaying in flight, meson -> gamma + a (reference: fluxes.py:996-1052).
+    `meson_flux`: rows (px, py, pz, E).  Every meson is decayed `n_samples` times with the general two-body decay kernel
+    (dense Lorentz boost); ALP energies, polar angles and weights are appended to `axion_energy` / `axion_angle` /
+    `axion_flux` -- like the reference, `simulate()` does not clear earlier results.  Weights stay float64.
+    """
+    def __init__(self, meson_flux, flux_weight, boson_mass=0.1, coupling=1.0, meson_mass=None,
+                 det_dist=20.0, det_area=2.0, det_length=1.0, apply_angle_cut=False,
+                 n_samples=10, off_axis_angle=0.0, **kwargs):
+        from .constants import M_PI0
+        super().__init__(boson_mass, Material("Be"), det_dist, det_length, det_area, **_split_kwargs(kwargs))
+        self.meson_flux = meson_flux
+        self.m_meson = M_PI0 if meson_mass is None else meson_mass
+        self.n_samples = n_samples
+        self.g = coupling
+        self.boson_mass = boson_mass
+        self.mm = M_PI0
+        self.apply_angle_cut = apply_angle_cut
+        self.flux_weight = flux_weight
+        self.off_axis_angle = off_axis_angle
+        self.phi_range = 2*pi
+        if off_axis_angle > 0.0:
+            self.phi_range = 2*self.det_sa()
+        self._A = None                    # device float64: axion_angle
+
+    @property
+    def axion_angle(self):
+        a = getattr(self, "_A", None)
+        return [] if a is None else self._host_get("A", a, [])
+
+    @axion_angle.setter
+    def axion_angle(self, v):
+        if isinstance(v, list) and len(v) == 0:
+            self._A = None
+        else:
+            self._A = self._rt.upload(np.asarray(v, dtype=np.float64).ravel())
+        if hasattr(self, "_host"):
+            self._host.pop("A", None)
+
+    def br(self):
+        if self.ma > self.m_meson:
+            return 0.0
+        return 2 * (self.g)**2 * (1 - power(self.ma / self.m_meson, 2))**3 / (4*pi*ALPHA)
+
+    def simulate(self, uniforms=None):
+        """uniforms (parity mode): [n_mesons, 2, n_samples] -- per meson the phi draws then the theta draws."""
+        mes = np.ascontiguousarray(self.meson_flux, dtype=np.float64)
+        if mes.ndim != 2 or mes.shape[1] < 4:
+            raise IndexError("meson_flux must have shape (n, 4): rows of [px, py, pz, E]")
+        nm, ns = int(mes.shape[0]), int(self.n_samples)
+        n = nm * ns
+        w = self.br() * (1.0 / ns) * self.flux_weight                            # fluxes.py:1031 (mc.weights = 1/n)
+        if self.apply_angle_cut:
+            w_final = w * self.phi_range/(2*pi)                                   # :1037
+        else:
+            w_final = self.det_area * w / (4*pi*self.det_dist**2)                 # :1040
+        seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
+        rt = self._rt
+        with rt.activate():
+            p4 = rt.upload(np.ascontiguousarray(mes[:, [3, 0, 1, 2]]).ravel())    # (E, px, py, pz)  :1027
+            table = rt.empty(nm * N.PARENT_GENERAL_NP)
+            p1 = torch.empty((4, n), dtype=torch.float64, device=rt.device)
+            theta = rt.empty(n)
+            d_u = None
+            if uniforms is not None:
+                u = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+                if u.shape[0] != 2 * n:
+                    raise ValueError(f"uniforms must hold 2*n_mesons*n_samples = {2 * n} variates")
+                d_u = rt.upload(u)
+            if n:
+                N.call("alpk_decay2body_general", N.ptr(p4), None, nm, float(self.boson_mass), 0.0, ns, None, N.ptr(d_u),
+                       C.c_uint64(seed), N.ptr(table), N.ptr(p1), None, None, N.ptr(theta), rt.stream())
+            E = p1[0].contiguous()
+            if self.apply_angle_cut:
+                sa = float(self.det_sa())
+                keep = (theta < sa + self.off_axis_angle) & (theta > self.off_axis_angle - sa)        # :1034-1035
+                sel = torch.nonzero(keep, as_tuple=False).ravel()
+                E, theta = E.index_select(0, sel), theta.index_select(0, sel)
+            F = torch.full((int(E.shape[0]),), float(w_final), dtype=torch.float64, device=rt.device)
+            if self._E is not None and int(self._E.shape[0]):                    # the reference keeps appending
+                E, F, theta = torch.cat([self._E, E]), torch.cat([self._F, F]), torch.cat([self._A, theta])
+        self._set_production(E.contiguous(), F.contiguous())
+        self._A = theta.contiguous()
+        self._host.pop("A", None)
+
+    def propagate(self):
+        self._ensure_production()
+        rt = self._rt
+        wgt = self._F if self._F is not None else rt.zeros(0)
+        n = int(wgt.shape[0])
+        with rt.activate():                       # float64 weights (fluxes.py:1048-1051)
+            d, s_ = rt.empty(n), rt.empty(n)
+            N.call("alpk_scale", N.ptr(wgt), n, 0.0, N.ptr(d), rt.stream())
+            N.call("alpk_scale", N.ptr(wgt), n, 1.0, N.ptr(s_), rt.stream())
+        self._D32, self._S32 = d, s_
+        for k in ("D32", "S32"):
+            self._host.pop(k, None)

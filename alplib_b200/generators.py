@@ -140,25 +140,26 @@ class PhotonEventGenerator(_EventGenerator):
     def inverse_primakoff(self, gagamma, ma, ntargets, days_exposure, threshold=0.0):
         return self._scatter(1, P.iprimakoff_consts(ma, gagamma, self.det_z), ntargets, days_exposure, threshold)
 
-    def simulate_decay_4vectors(self, days_exposure, n_samples=1, uniforms=None, seed=None):
+    def simulate_decay_4vectors(self, days_exposure, n_samples=1, uniforms=None, seed=None, parent_phis=None):
         """2-body decay a -> gamma gamma of every flux sample, `n_samples` decays each (generators.py:94-128).
 
         Returns (photon-1 4-vectors, photon-2 4-vectors, weights): two LorentzVectorArray (sequence of
         LorentzVector) and a float64 array, length n_flux*n_samples in parent-major order.  Parents are forward
-        (theta = 0) as for every flux class on this path (`axion_angle` empty, generators.py:111-112).
+        (theta = 0) when `flux.axion_angle` is empty (generators.py:111-112); otherwise each parent points along
+        (theta_i, phi_i) with phi_i drawn like the reference draws it (or given as `parent_phis`).
         `uniforms` (parity mode): array [n_flux, 2, n_samples] -- per parent the phi draws then the theta draws."""
         fl = self.flux
-        if len(fl.axion_angle) != 0:
-            raise NotImplementedError("parents with a polar angle come from flux classes outside this path")
         fl._ensure_production()
         fl._ensure_propagated()
         rt = fl._rt
         n_flux = 0 if fl._F is None else int(fl._F.shape[0])        # generators.py:98
         if fl._D32 is None or int(fl._D32.shape[0]) != n_flux:
             raise ValueError("propagate() must run before simulate_decay_4vectors()")
+        self._need_f32(fl._D32, "decay_axion_weight")
         ns = int(n_samples)
         n = n_flux * ns
         ev = P.event_params(days_exposure, 0.0)
+        angled = len(fl.axion_angle) != 0                           # generators.py:111-114
         if uniforms is not None:
             uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
             if uniforms.shape[0] != 2 * n:
@@ -167,16 +168,30 @@ class PhotonEventGenerator(_EventGenerator):
         elif seed is None:
             seed = fl.seed if fl.seed is not None else _draw_seed()
         with rt.activate():
-            table = rt.empty(n_flux * N.PARENT_NP)
             p1 = torch.empty((4, n), dtype=torch.float64, device=rt.device)
             p2 = torch.empty((4, n), dtype=torch.float64, device=rt.device)
             w = rt.empty(n)
-            if n:
-                d_u = rt.upload(uniforms) if uniforms is not None else None
+            d_u = rt.upload(uniforms) if (uniforms is not None and n) else None
+            if n and not angled:
+                table = rt.empty(n_flux * N.PARENT_NP)
                 N.call("alpk_decay_parent_rows", N.ptr(fl._E), N.ptr(fl._D32), n_flux, float(fl.ma**2), C.byref(ev), ns,
                        N.ptr(table), rt.stream())
                 N.call("alpk_decay2body", N.ptr(table), n_flux, ns, None, N.ptr(d_u), C.c_uint64(seed),
                        1 if fl.precision == "fast" else 0, N.ptr(p1), N.ptr(p2), N.ptr(w), rt.stream())
+            elif n:
+                # parents with a polar angle: 4-vectors assembled per parent exactly as generators.py:117-120 (the
+                # azimuths come from the global NumPy stream like the reference's, or from `parent_phis`), then the
+                # general decay kernel with the dense 4x4 boost
+                ea = np.asarray(fl.axion_energy, dtype=np.float64)
+                thetas = np.asarray(fl.axion_angle, dtype=np.float64)
+                phis = np.random.uniform(0.0, 2*np.pi, n_flux) if parent_phis is None else np.asarray(parent_phis, dtype=np.float64)
+                pa = np.sqrt(ea**2 - fl.ma**2)
+                p4 = np.stack([ea, pa*np.cos(phis)*np.sin(thetas), pa*np.sin(phis)*np.sin(thetas), pa*np.cos(thetas)], axis=1)
+                ew = days_exposure * P.S_PER_DAY * np.asarray(fl.decay_axion_weight) / ns      # generators.py:97 (float32)
+                d_p4, d_w = rt.upload(p4.ravel()), rt.upload(ew.astype(np.float64))
+                table = rt.empty(n_flux * N.PARENT_GENERAL_NP)
+                N.call("alpk_decay2body_general", N.ptr(d_p4), N.ptr(d_w), n_flux, 0.0, 0.0, ns, None, N.ptr(d_u),
+                       C.c_uint64(seed), N.ptr(table), N.ptr(p1), N.ptr(p2), N.ptr(w), None, rt.stream())
         return LorentzVectorArray(p1), LorentzVectorArray(p2), _DeviceWeights(w)
 
 

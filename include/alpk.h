@@ -32,6 +32,7 @@ extern "C" {
 /* number of doubles per row of the per-row parameter tables */
 #define ALPK_COMPTON_NP 12
 #define ALPK_PARENT_NP 6
+#define ALPK_PARENT_GENERAL_NP 20
 #define ALPK_BREM_NP 6
 #define ALPK_PAIRANN_NP 11
 #define ALPK_GL_POINTS 32
@@ -153,6 +154,15 @@ int alpk_decay_parent_rows(const double* energy, const float* decay_w32, uint64_
                            const alpk_event_t* h_ev, uint32_t n_samples, double* row_table, void* stream);
 int alpk_decay2body(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
                     const double* uniforms, uint64_t seed, int fast, double* p1, double* p2, double* w, void* stream);
+
+/* General 2-body decay: parents with arbitrary direction (rows {E, px, py, pz}), daughter masses m1, m2, dense 4x4
+ * boost -- Decay2Body + lorentz_boost (cross_section_mc.py:496-544, 669-685) as used for parents with a polar angle
+ * (generators.py:117-121) and by FluxNeutralMeson2BodyDecay (fluxes.py:1026-1031).  parent_w (may be NULL -> 1): weight
+ * copied to every event of the parent.  row_table: scratch [n_parents][ALPK_PARENT_GENERAL_NP].  Outputs: p1[4][N]
+ * (required), p2[4][N], w[N], theta1[N] = polar angle of daughter 1 (each may be NULL).  uniforms as alpk_decay2body. */
+int alpk_decay2body_general(const double* parents_p4, const double* parent_w, uint64_t n_parents, double m1, double m2,
+                            uint32_t n_samples, const uint32_t* row_ids, const double* uniforms, uint64_t seed,
+                            double* row_table, double* p1, double* p2, double* w, double* theta1, void* stream);
 
 /* ---- bremsstrahlung with track-length attenuation: fluxes.py:257-356, prod_xs.py:209-221, 313-323 ------------------------ */
 typedef struct {

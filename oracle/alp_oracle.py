@@ -736,6 +736,61 @@ def decay_4vectors(axion_energy, decay_axion_weight, ma, days_exposure, n_sample
 
 
 # ---------------------------------------------------------------------------------------------------------
+# General Decay2Body (cross_section_mc.py:496-544) with the dense lorentz_boost (:669-685); row sums evaluated
+# left to right (NumPy/BLAS may associate differently at the 1-ulp level)
+# ---------------------------------------------------------------------------------------------------------
+def decay2body_general(parent_p4, m1, m2, n_samples, usrc):
+    """parent_p4 = (E, px, py, pz).  Returns p1[n,4], p2[n,4] lab 4-vectors.  Draws: n phi then n theta."""
+    e, px, py, pz = (float(x) for x in parent_p4)
+    with np.errstate(all="ignore"):
+        mp = np.sqrt(((e * e - px * px) - py * py) - pz * pz)
+        p_cm = np.power((mp ** 2 - (m2 - m1) ** 2) * (mp ** 2 - (m2 + m1) ** 2), 0.5) / (2 * mp)
+        e1 = np.sqrt(p_cm ** 2 + m1 ** 2)
+        e2 = np.sqrt(p_cm ** 2 + m2 ** 2)
+        phi = 2 * pi * usrc.take(n_samples)
+        th = np.arccos(1 - 2 * usrc.take(n_samples))
+        v = np.array([-(px / e), -(py / e), -(pz / e)])
+        beta = np.sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])
+        cx, cy, cz = p_cm * np.cos(phi) * np.sin(th), p_cm * np.sin(phi) * np.sin(th), p_cm * np.cos(th)
+        a = np.stack([e1 * np.ones(n_samples), cx, cy, cz], axis=1)
+        b = np.stack([e2 * np.ones(n_samples), -cx, -cy, -cz], axis=1)
+        if beta == 0.0:
+            return a, b
+        n = v / beta if not beta < 1e-40 else np.zeros(3)
+        g = 1 / np.sqrt(1 - beta ** 2)
+        mat = np.array([[g, -g * beta * n[0], -g * beta * n[1], -g * beta * n[2]],
+                        [-g * beta * n[0], 1 + (g - 1) * n[0] * n[0], (g - 1) * n[0] * n[1], (g - 1) * n[0] * n[2]],
+                        [-g * beta * n[1], (g - 1) * n[1] * n[0], 1 + (g - 1) * n[1] * n[1], (g - 1) * n[1] * n[2]],
+                        [-g * beta * n[2], (g - 1) * n[2] * n[0], (g - 1) * n[2] * n[1], 1 + (g - 1) * n[2] * n[2]]])
+
+        def apply(p):
+            return np.stack([((mat[r, 0] * p[:, 0] + mat[r, 1] * p[:, 1]) + mat[r, 2] * p[:, 2]) + mat[r, 3] * p[:, 3]
+                             for r in range(4)], axis=1)
+        return apply(a), apply(b)
+
+
+def neutral_meson_simulate(meson_flux, flux_weight, ma, g, m_meson, n_samples, det_dist, det_area, usrc,
+                           apply_angle_cut=False, off_axis_angle=0.0):
+    """FluxNeutralMeson2BodyDecay.simulate (fluxes.py:1024-1046).  Returns (E, flux, theta)."""
+    det_sa = np.arctan(np.sqrt(det_area / pi) / det_dist)
+    phi_range = 2 * det_sa if off_axis_angle > 0.0 else 2 * pi
+    br = 0.0 if ma > m_meson else 2 * g ** 2 * (1 - np.power(ma / m_meson, 2)) ** 3 / (4 * pi * ALPHA)
+    E, F, T = [], [], []
+    for m in np.asarray(meson_flux, dtype=np.float64):
+        p1, _ = decay2body_general((m[3], m[0], m[1], m[2]), ma, 0.0, n_samples, usrc)
+        en = p1[:, 0]
+        th = np.arccos(p1[:, 3] / np.sqrt((p1[:, 1] ** 2 + p1[:, 2] ** 2) + p1[:, 3] ** 2))
+        w = br * (np.ones(n_samples) / n_samples) * flux_weight
+        if apply_angle_cut:
+            mask = (th < det_sa + off_axis_angle) * (th > off_axis_angle - det_sa)
+            en, w, th = en[mask], w[mask] * phi_range / (2 * pi), th[mask]
+        else:
+            w = det_area * w / (4 * pi * det_dist ** 2)
+        E.append(en); F.append(w); T.append(th)
+    return np.concatenate(E), np.concatenate(F), np.concatenate(T)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # np.histogram(E, bins=edges, weights=w) semantics used for the binned spectra
 # ---------------------------------------------------------------------------------------------------------
 def histogram(x, w, edges):

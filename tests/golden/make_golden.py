@@ -451,6 +451,55 @@ def case_pairgamma():
          axion_energy=fl.axion_energy, axion_flux=fl.axion_flux, decay_w32=d32, scatter_w32=s32, decay_w64=d64, scatter_w64=s64)
 
 
+def case_general_decay():
+    print("general 2-body decay: neutral-meson flux + simulate_decay_4vectors with polar angles")
+    rs = np.random.RandomState(8)
+    n = 6
+    pz = 10 ** rs.uniform(1.5, 3.5, n); pt = rs.uniform(0, 150, n); ph = rs.uniform(0, 2 * np.pi, n)
+    mes = np.stack([pt * np.cos(ph), pt * np.sin(ph), pz, np.sqrt(pz ** 2 + pt ** 2 + F.M_PI0 ** 2)], axis=1)
+    for tag, cut, off in (("meson2body", False, 0.0), ("meson2body_cut", True, 0.05)):
+        np.random.seed(41)
+        fl = F.FluxNeutralMeson2BodyDecay(mes, flux_weight=2.5e3, boson_mass=20.0, coupling=1e-3, meson_mass=F.M_PI0, det_dist=20.0,
+                                          det_area=60.0, det_length=1.0, apply_angle_cut=cut, n_samples=40, off_axis_angle=off)
+        fl.simulate(); fl.propagate()
+        us = O.UniformSource(np.random.RandomState(41))
+        oE, oF, oT = O.neutral_meson_simulate(mes, 2.5e3, 20.0, 1e-3, F.M_PI0, 40, 20.0, 60.0, us, cut, off)
+        check(tag + " E", oE, fl.axion_energy, 1e-13)
+        check(tag + " flux", oF, fl.axion_flux, 1e-14)
+        check(tag + " theta", oT, fl.axion_angle, 1e-9)
+        save(tag, meson_flux=mes, flux_weight=2.5e3, ma=20.0, g=1e-3, n_samples=40, det_dist=20.0, det_area=60.0, angle_cut=cut,
+             off_axis=off, uniforms=np.concatenate(us.log), axion_energy=fl.axion_energy, axion_flux=fl.axion_flux,
+             axion_angle=fl.axion_angle, scatter_w=np.array(fl.scatter_axion_weight))
+    # decay MC of parents with a polar angle: the dense-boost branch of generators.py:117-121
+    W, Ar = F.Material("W"), F.Material("Ar")
+    pf = np.array([[300.0, 1e12], [60.0, 1e11], [2000.0, 1e10]])
+    fl = F.FluxPrimakoffIsotropic(pf, W, axion_mass=5.0, axion_coupling=1e-6, **GEOM_DEFAULT)
+    fl.simulate(); fl.propagate()
+    fl.axion_angle = [0.02, 0.3, 0.001]
+    gen = G.PhotonEventGenerator(fl, Ar)
+    np.random.seed(19)
+    l1, l2, wl = gen.simulate_decay_4vectors(100, n_samples=50)
+    p1 = np.array([lv.pmu for lv in l1]); p2 = np.array([lv.pmu for lv in l2])
+    rs2 = np.random.RandomState(19)
+    phis = rs2.uniform(0.0, 2 * np.pi, 3)
+    us = O.UniformSource(rs2)
+    o1, o2 = [], []
+    for i in range(3):
+        ea = fl.axion_energy[i]; pa = np.sqrt(ea ** 2 - 5.0 ** 2); th = fl.axion_angle[i]
+        a, b = O.decay2body_general((ea, pa * np.cos(phis[i]) * np.sin(th), pa * np.sin(phis[i]) * np.sin(th), pa * np.cos(th)),
+                                    0.0, 0.0, 50, us)
+        o1.append(a); o2.append(b)
+    o1, o2 = np.concatenate(o1), np.concatenate(o2)
+    scale = np.repeat(np.array(fl.axion_energy), 50)[:, None]
+    d = max(np.max(np.abs(o1 - p1) / scale), np.max(np.abs(o2 - p2) / scale))
+    print(f"  decay4_angled: max |dp|/E_parent = {d:.3e}")
+    if d > 1e-13:
+        raise SystemExit("oracle disagrees with the reference on decay4_angled")
+    save("decay4_angled", photon_flux=pf, ma=5.0, g=1e-6, n_samples=50, days=100, axion_angle=np.array(fl.axion_angle),
+         parent_phi_uniforms=phis / (2 * np.pi), parent_phis=phis, uniforms=np.concatenate(us.log), axion_energy=fl.axion_energy,
+         decay_w32=np.array(fl.decay_axion_weight), p1=p1, p2=p2, w=np.array(wl))
+
+
 if __name__ == "__main__":
     kat_scalars()
     case_primakoff()
@@ -463,4 +512,5 @@ if __name__ == "__main__":
     case_vol_int()
     case_nuclear_pi0()
     case_pairgamma()
+    case_general_decay()
     print("all golden fixtures written; oracle pinned against the reference")

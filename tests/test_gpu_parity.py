@@ -737,3 +737,46 @@ def test_pair_annihilation_gamma(A):
     b = A.FluxPairAnnihilationGamma(g["positron_flux"], A.Material("C"), axion_mass=8.0, axion_coupling=1e-5, n_samples=500, seed=5, **GEOM_DUNE)
     a.simulate(); b.simulate()
     assert np.array_equal(a.axion_flux, b.axion_flux) and np.all(np.isfinite(a.axion_flux)) and np.sum(a.axion_flux) > 0
+
+
+@pytest.mark.parametrize("name", ["meson2body", "meson2body_cut"])
+def test_neutral_meson_flux(A, name):
+    g = load_golden(name)
+    fl = A.FluxNeutralMeson2BodyDecay(g["meson_flux"], flux_weight=float(g["flux_weight"]), boson_mass=float(g["ma"]),
+                                      coupling=float(g["g"]), det_dist=float(g["det_dist"]), det_area=float(g["det_area"]),
+                                      det_length=1.0, apply_angle_cut=bool(g["angle_cut"]), n_samples=int(g["n_samples"]),
+                                      off_axis_angle=float(g["off_axis"]))
+    assert len(fl.axion_angle) == 0
+    fl.simulate(uniforms=g["uniforms"])
+    assert max_rel(fl.axion_energy, g["axion_energy"]) < TOL
+    assert max_rel(fl.axion_flux, g["axion_flux"]) < 1e-14
+    assert max_rel(fl.axion_angle, g["axion_angle"]) < TOL
+    fl.propagate()
+    assert fl.scatter_axion_weight.dtype == np.float64 and max_rel(fl.scatter_axion_weight, g["scatter_w"]) < 1e-14
+    n0 = len(fl.axion_energy)
+    fl.simulate(uniforms=g["uniforms"])                       # the reference appends (no reset in simulate)
+    assert len(fl.axion_energy) == 2 * n0 == len(fl.axion_angle)
+
+
+def test_decay_4vectors_with_polar_angles(A):
+    g = load_golden("decay4_angled")
+    ma, ns = float(g["ma"]), int(g["n_samples"])
+    fl = A.FluxPrimakoffIsotropic(g["photon_flux"], A.Material("W"), axion_mass=ma, axion_coupling=float(g["g"]), **GEOM)
+    fl.simulate(); fl.propagate()
+    fl.decay_axion_weight = g["decay_w32"]
+    fl.axion_angle = list(g["axion_angle"])
+    gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+    l1, l2, w = gen.simulate_decay_4vectors(int(g["days"]), n_samples=ns, uniforms=g["uniforms"].reshape(3, 2, ns),
+                                            parent_phis=g["parent_phis"])
+    scale = np.repeat(np.asarray(fl.axion_energy), ns)[:, None]
+    assert np.max(np.abs(l1.pmu - g["p1"]) / scale) < TOL and np.max(np.abs(l2.pmu - g["p2"]) / scale) < TOL
+    assert np.array_equal(np.asarray(w), g["w"])
+    # free running: the azimuths come from the global NumPy stream, like the reference
+    np.random.seed(19)
+    a1, _, _ = gen.simulate_decay_4vectors(100, n_samples=ns, seed=1)
+    np.random.seed(19)
+    b1, _, _ = gen.simulate_decay_4vectors(100, n_samples=ns, seed=1)
+    assert np.array_equal(a1.pmu, b1.pmu)
+    tot = a1.pmu  # 4-momentum conservation with the angled parents
+    ea = np.asarray(fl.axion_energy)
+    assert np.all(np.isfinite(tot)) and abs(np.mean(a1.energy()) / np.mean(ea) - 0.5) < 0.1

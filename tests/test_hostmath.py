@@ -312,3 +312,27 @@ def test_pairgamma(hostcheck):
                            dptr(np.ascontiguousarray(u[:2 * n])), dptr(np.ascontiguousarray(u[2 * n:])), dptr(oe), dptr(of))
     assert max_rel(oe, g["axion_energy"]) < 1e-13
     assert max_rel(of, g["axion_flux"]) < TOL
+
+
+def test_general_decay(hostcheck):
+    g = load_golden("decay4_angled")
+    ma, ns = float(g["ma"]), int(g["n_samples"])
+    ea, th, ph = g["axion_energy"], g["axion_angle"], g["parent_phis"]
+    pa = np.sqrt(ea ** 2 - ma ** 2)
+    p4 = np.ascontiguousarray(np.stack([ea, pa * np.cos(ph) * np.sin(th), pa * np.sin(ph) * np.sin(th), pa * np.cos(th)], axis=1))
+    n = 3 * ns
+    p1, p2, t1 = np.empty((4, n)), np.empty((4, n)), np.empty(n)
+    hostcheck.hc_decay_general(dptr(p4), C.c_uint64(3), C.c_double(0.0), C.c_double(0.0), C.c_uint32(ns),
+                               dptr(np.ascontiguousarray(g["uniforms"])), dptr(p1), dptr(p2), dptr(t1))
+    scale = np.repeat(ea, ns)[None, :]
+    assert np.max(np.abs(p1 - g["p1"].T) / scale) < 1e-13 and np.max(np.abs(p2 - g["p2"].T) / scale) < 1e-13
+    m = load_golden("meson2body")
+    mes = m["meson_flux"]
+    p4 = np.ascontiguousarray(mes[:, [3, 0, 1, 2]])
+    nm, ns = mes.shape[0], int(m["n_samples"])
+    n = nm * ns
+    p1, p2, t1 = np.empty((4, n)), np.empty((4, n)), np.empty(n)
+    hostcheck.hc_decay_general(dptr(p4), C.c_uint64(nm), C.c_double(float(m["ma"])), C.c_double(0.0), C.c_uint32(ns),
+                               dptr(np.ascontiguousarray(m["uniforms"])), dptr(p1), dptr(p2), dptr(t1))
+    assert max_rel(p1[0], m["axion_energy"]) < 1e-12
+    assert max_rel(t1, m["axion_angle"]) < TOL

@@ -234,3 +234,14 @@ def test_nuclear_and_pi0():
     E, F = O.pi0_simulate_flux(g["momenta"], 30.0, 1e-3, 0.0259, O.UniformSource(g["uniforms"]), 50.0, 0.3)
     assert max_rel(E, g["axion_energy"]) < 1e-15 and max_rel(F, g["axion_flux"]) < 1e-15
     assert 0 < E.shape[0] < g["momenta"].shape[0]                  # the cuts bite
+
+
+@pytest.mark.parametrize("name", ["meson2body", "meson2body_cut"])
+def test_neutral_meson(name):
+    g = load_golden(name)
+    E, F, T = O.neutral_meson_simulate(g["meson_flux"], float(g["flux_weight"]), float(g["ma"]), float(g["g"]), O.M_PI0,
+                                       int(g["n_samples"]), float(g["det_dist"]), float(g["det_area"]),
+                                       O.UniformSource(g["uniforms"]), bool(g["angle_cut"]), float(g["off_axis"]))
+    assert max_rel(E, g["axion_energy"]) < 1e-13 and max_rel(F, g["axion_flux"]) < 1e-14 and max_rel(T, g["axion_angle"]) < 1e-9
+    if name == "meson2body_cut":
+        assert 0 < E.shape[0] < g["meson_flux"].shape[0] * int(g["n_samples"])
