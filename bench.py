@@ -317,31 +317,35 @@ def run_gpu(args):
 
     # ---- (m_a, g) scan, BASELINE config 5: 200 x 200 grid, 1e3 bins x 100 Compton samples + 1e3 Primakoff, masses
     #      sharded over the ranks, one all-reduce of each rate map -----------------------------------------------------
-    from alplib_b200.scan import scan_rates_distributed
-    pf_scan = c2_spectrum(N_BINS)[::10]
-    ma_grid, g_grid = np.logspace(-2, 2, 200), np.logspace(-9, -3, 200)
+    scan = None
+    try:
+        from alplib_b200.scan import scan_rates_distributed
+        pf_scan = c2_spectrum(N_BINS)[::10]
+        ma_grid, g_grid = np.logspace(-2, 2, 200), np.logspace(-9, -3, 200)
 
-    def scan_once():
-        kw = dict(days_exposure=DAYS, threshold=THR, seed=SEED, **GEOM)
-        mc = scan_rates_distributed("compton", pf_scan, W, ma_grid, g_grid, n_samples=100, **kw)
-        mp_ = scan_rates_distributed("primakoff", pf_scan, W, ma_grid, g_grid, **kw)
-        return mc, mp_
+        def scan_once():
+            kw = dict(days_exposure=DAYS, threshold=THR, seed=SEED, **GEOM)
+            mc = scan_rates_distributed("compton", pf_scan, W, ma_grid, g_grid, n_samples=100, **kw)
+            mp_ = scan_rates_distributed("primakoff", pf_scan, W, ma_grid, g_grid, **kw)
+            return mc, mp_
 
-    scan_once()
-    barrier()
-    t0 = time.perf_counter()
-    scan_reps = 3
-    for _ in range(scan_reps):
-        mc, mp_ = scan_once()
-    barrier()
-    dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=rt.device)
-    if world > 1:
-        dist.all_reduce(dts, op=dist.ReduceOp.MAX)
-    scan = {"points_per_s": scan_reps * ma_grid.size * g_grid.size / float(dts.item()), "grid": [200, 200],
-            "sample_evals_per_point": int(pf_scan.shape[0] * 101), "seconds_per_map_pair": float(dts.item()) / scan_reps,
-            "config": "C5: ma=logspace(-2,2,200), g=logspace(-9,-3,200), 1e3 bins x (100 Compton + 1 Primakoff) samples, "
-                      "decays(100 d, 5 MeV); host grids in, host maps out (end to end)",
-            "nonzero_points": [int(np.count_nonzero(mc)), int(np.count_nonzero(mp_))]}
+        scan_once()
+        barrier()
+        t0 = time.perf_counter()
+        scan_reps = 3
+        for _ in range(scan_reps):
+            mc, mp_ = scan_once()
+        barrier()
+        dts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=rt.device)
+        if world > 1:
+            dist.all_reduce(dts, op=dist.ReduceOp.MAX)
+        scan = {"points_per_s": scan_reps * ma_grid.size * g_grid.size / float(dts.item()), "grid": [200, 200],
+                "sample_evals_per_point": int(pf_scan.shape[0] * 101), "seconds_per_map_pair": float(dts.item()) / scan_reps,
+                "config": "C5: ma=logspace(-2,2,200), g=logspace(-9,-3,200), 1e3 bins x (100 Compton + 1 Primakoff) samples, "
+                          "decays(100 d, 5 MeV); host grids in, host maps out (end to end)",
+                "nonzero_points": [int(np.count_nonzero(mc)), int(np.count_nonzero(mp_))]}
+    except Exception as exc:          # noqa: BLE001 -- the scan line is auxiliary: never lose the headline over it
+        scan = {"error": repr(exc)[:300]}
 
     if rank == 0:
         # ---- roofline of the dominant kernel (fused Compton production->propagate->decays, materialising) ------------
@@ -364,7 +368,7 @@ def run_gpu(args):
         NV.call("alpk_fp64_peak", iters, blocks, NV.ptr(scratch), rt.stream())
         f1.record()
         torch.cuda.synchronize()
-        fp64_peak = blocks * 256 * 16.0 * iters / (f0.elapsed_time(f1) * 1e-3) / 1e12
+        fp64_peak = max(blocks * 256 * 16.0 * iters / (f0.elapsed_time(f1) * 1e-3) / 1e12, 1e-9)
         fp64_ach = n_compton * FLOPS_PER_SAMPLE / (kms * 1e-3) / 1e12
         traffic = None
         try:
@@ -383,10 +387,13 @@ def run_gpu(args):
                                      "expanded accounting (div 8, sqrt 10, exp 25)"}}
         # ---- CPU baseline beside it (bounded sample, 1 core) -------------------------------------------------------------
         ns_cpu = 1000
-        n_cpu, dt_cpu, r_cpu = cpu_pass(c2_spectrum(N_BINS), ns_cpu, 1)
-        cpu_baseline = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"C2 with n_samples={ns_cpu} per bin (all {N_BINS} bins): {n_cpu} samples in {dt_cpu:.2f} s",
-                        "rates": list(r_cpu)}
+        try:
+            n_cpu, dt_cpu, r_cpu = cpu_pass(c2_spectrum(N_BINS), ns_cpu, 1)
+            cpu_baseline = {"value": n_cpu / dt_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"C2 with n_samples={ns_cpu} per bin (all {N_BINS} bins): {n_cpu} samples in {dt_cpu:.2f} s",
+                            "rates": list(r_cpu)}
+        except Exception as exc:      # noqa: BLE001
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: " + repr(exc)[:200]}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
