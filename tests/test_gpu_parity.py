@@ -780,3 +780,47 @@ def test_decay_4vectors_with_polar_angles(A):
     tot = a1.pmu  # 4-momentum conservation with the angled parents
     ea = np.asarray(fl.axion_energy)
     assert np.all(np.isfinite(tot)) and abs(np.mean(a1.energy()) / np.mean(ea) - 0.5) < 0.1
+
+
+# ---- randomised differential test: free-running kernels vs the oracle on replayed Philox variates --------------------------------
+def test_compton_chain_fuzz(A):
+    rs = np.random.RandomState(2024)
+    W = O.AbsCrossSection(O.Material("W"))
+    for trial in range(14):
+        n_rows = int(rs.choice([1, 2, 7, 40, 130]))
+        ns = int(rs.choice([1, 2, 3, 17, 43, 44, 45, 256, 1001]))
+        ma = float(10 ** rs.uniform(-2, 1.3))
+        g = float(10 ** rs.uniform(-8, -3.5))
+        eg = np.sort(10 ** rs.uniform(-1, 4, n_rows))
+        pf = np.stack([eg, 10 ** rs.uniform(5, 15, n_rows)], axis=1)
+        dist, length, area = float(10 ** rs.uniform(0, 2.5)), float(10 ** rs.uniform(-1, 1)), float(10 ** rs.uniform(-2, 1.5))
+        loop, iso = bool(rs.randint(2)), bool(rs.randint(2))
+        seed = int(rs.randint(1, 2 ** 31))
+        fl = A.FluxComptonIsotropic(pf, A.Material("W"), det_dist=dist, det_length=length, det_area=area, axion_mass=ma,
+                                    axion_coupling=g, n_samples=ns, is_isotropic=iso, loop_decay=loop, seed=seed, keep_f64=True)
+        fl.row_offset = 11 * trial
+        fl.simulate(); fl.propagate()
+        keep = O.compton_row_valid(pf, ma)
+        if not keep.any():
+            assert len(fl.axion_energy) == 0
+            continue
+        u = np.concatenate([PX.uniform_1(seed, PX.TAG_COMPTON_EA, int(r) + 11 * trial, ns) for r in np.nonzero(keep)[0]])
+        oE, oF = O.compton_simulate(pf, ma, g, 74, W, ns, O.UniformSource(u))
+        width = O.W_ee(g, ma) + (O.W_gg_loop(g, ma, O.M_E) if loop else 0.0)
+        ga = O.geom_acceptance(area, dist) if iso else None
+        p = O.propagate(oE, oF, ma, width, 1.0, dist, length, geom_accept=ga)
+        ctx = (trial, n_rows, ns, ma, g)
+        assert np.array_equal(fl.axion_energy, oE), ctx
+        assert max_rel(fl.axion_flux, oF) < TOL, ctx
+        assert max_rel(fl.scatter_axion_weight_f64, p["scatter_w64"]) < TOL, ctx
+        assert_decay_close(fl.decay_axion_weight_f64, p["decay_w64"], p["scatter_w64"], TOL)
+        assert max_rel(fl.scatter_axion_weight, p["scatter_w"], floor=1e-44) <= F32, ctx      # (float32 denormals excluded)
+        # fused reduce-only rate == separate launches, and == the oracle within the conditioned tolerance
+        thr = float(rs.uniform(0, eg.max()))
+        r_sep = A.ElectronEventGenerator(fl, A.Material("Ar")).decays(30, thr)
+        fb = A.FluxComptonIsotropic(pf, A.Material("W"), det_dist=dist, det_length=length, det_area=area, axion_mass=ma,
+                                    axion_coupling=g, n_samples=ns, is_isotropic=iso, loop_decay=loop, seed=seed, fused=True)
+        fb.row_offset = 11 * trial
+        fb.simulate(); fb.propagate()
+        r_fused = A.ElectronEventGenerator(fb, A.Material("Ar")).decays(30, thr)
+        assert r_fused == pytest.approx(r_sep, rel=1e-12, abs=1e-300), ctx
