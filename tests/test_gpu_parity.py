@@ -824,3 +824,57 @@ def test_compton_chain_fuzz(A):
         fb.simulate(); fb.propagate()
         r_fused = A.ElectronEventGenerator(fb, A.Material("Ar")).decays(30, thr)
         assert r_fused == pytest.approx(r_sep, rel=1e-12, abs=1e-300), ctx
+
+
+def test_full_size_c4_epm_channels(A):
+    """configs[3]: 1e4-row e+- shower fluxes on graphite, DUNE-like geometry, ma = 10 MeV, g = 1e-6:
+    Brem 1e4 x 1000, Resonance 1e6 draws, PairAnn 1e4 x 100.  Device-side invariants + a sub-sampled oracle comparison."""
+    import torch
+    e = np.linspace(20.0, 1.2e5, 10_000)
+    ef = np.stack([e, 1e14 * np.exp(-e / 2e4)], axis=1)
+    pfx = np.stack([e, 0.3e14 * np.exp(-e / 2e4)], axis=1)
+    ma, g = 10.0, 1e-6
+    C_ = A.Material("C")
+    # --- Brem
+    fb = A.FluxBremIsotropic(ef, pfx, C_, target_length=100, axion_mass=ma, axion_coupling=g, n_samples=1000, seed=11, **GEOM_DUNE)
+    fb.simulate(); fb.propagate()
+    n_emit = int(fb._emit.sum().item())
+    assert fb._E.shape[0] == n_emit * 1000 and n_emit > 9000
+    assert bool(torch.isfinite(fb._F).all()) and bool((fb._F >= 0).all()) and float(fb._E.min().item()) >= ma
+    r_b = A.ElectronEventGenerator(fb, A.Material("Ar")).decays(365, 30.0)
+    # sub-sample: rows 5000..5007 through the oracle with the replayed variates (row ids are global)
+    sub = slice(5000, 5008)
+    stream = []
+    for r in range(sub.start, sub.stop):
+        u = PX.uniform_1(11, PX.TAG_BREM_ROW, r, 1)[0]
+        stream += [[u], PX.uniform_1(11, PX.TAG_BREM_EA, r, 1000)]
+    oE, oF, info = O.brem_simulate(ef[sub], pfx, ma, g, O.Material("C"), 1000, O.UniformSource(np.concatenate(stream)))
+    assert info["row_emit"].all()
+    emit = fb._emit.cpu().numpy().astype(bool)
+    first = int(emit[:sub.start].sum()) * 1000
+    got_E = fb._E[first:first + 8000].cpu().numpy()
+    got_F = fb._F[first:first + 8000].cpu().numpy()
+    assert max_rel(got_E, oE) < 1e-12
+    # the row weight interpolates Phi_e + Phi_p at E0, a table knot: identical whether the oracle sees 8 rows or 1e4
+    assert max_rel(got_F, oF) < TOL
+    # --- Resonance
+    fr = A.FluxResonanceIsotropic(pfx, C_, axion_mass=ma, axion_coupling=g, n_samples=1_000_000, seed=12, **GEOM_DUNE)
+    fr.simulate(); fr.propagate()
+    u1, u2 = PX.uniform_2(12, PX.TAG_RESONANCE, 0, 1_000_000)
+    _, oFr = O.resonance_simulate(pfx, ma, g, O.Material("C"), 1_000_000, O.UniformSource(np.concatenate([u1, u2])))
+    assert max_rel(fr.axion_flux, oFr) < 1e-9
+    # --- PairAnn
+    fa = A.FluxPairAnnihilationIsotropic(pfx, C_, axion_mass=ma, axion_coupling=g, n_samples=100, seed=13, **GEOM_DUNE)
+    fa.simulate(); fa.propagate()
+    keep = O.pairann_row_valid(pfx, ma)
+    assert fa._E.shape[0] == int(keep.sum()) * 100
+    assert bool(torch.isfinite(fa._F).all()) and bool((fa._F >= 0).all())
+    rows = np.nonzero(keep)[0][[0, 17, 4000, -1]]
+    stream = []
+    for r in rows:
+        stream += [np.zeros(100), PX.uniform_1(13, PX.TAG_PAIRANN, int(r), 100)]
+    oE, oF = O.pairann_simulate(pfx[rows], ma, g, O.Material("C"), 100, O.UniformSource(np.concatenate(stream)))
+    idx = np.concatenate([np.arange(100) + 100 * int(np.searchsorted(np.nonzero(keep)[0], r)) for r in rows])
+    assert max_rel(fa._E.cpu().numpy()[idx], oE) < TOL and max_rel(fa._F.cpu().numpy()[idx], oF) < TOL
+    r_a = A.ElectronEventGenerator(fa, A.Material("Ar")).decays(365, 30.0)
+    assert np.isfinite(r_b) and np.isfinite(r_a) and r_b >= 0 and r_a >= 0
