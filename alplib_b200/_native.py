@@ -140,6 +140,7 @@ _SIGNATURES = {
                               C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),
     "alpk_decay_parent_rows": ([_P, _P, _U64, _D, C.POINTER(EventT), _U32, _P, _P], _I),
     "alpk_decay2body": ([_P, _U64, _U32, _P, _P, _U64, _I, _P, _P, _P, _P], _I),
+    "alpk_decay2body_f32": ([_P, _U64, _U32, _P, _U64, _P, _P, _P, _P], _I),
     "alpk_decay2body_general": ([_P, _P, _U64, _D, _D, _U32, _P, _P, _U64, _P, _P, _P, _P, _P, _P], _I),
     "alpk_scan_tiles": ([_U32, _U32], _U32),
     "alpk_scan": ([_I, _P, _P, _U32, _U32, _P, _P, _I, _P, _P, _I, _P, _P, _I, _D, _D, _D, _U32, _U64,

@@ -119,6 +119,65 @@ decay2body_kernel(const DecayArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// optional FP32 mode of the decay MC (north star: 1e-5 relative): per-parent constants stay FP64 (they contain the
+// cancellations), per-event arithmetic, RNG mantissas (24 bit) and outputs are float -> 36 B/event instead of 72.
+// thread = 4 consecutive events: two Philox calls, 16-byte float4 stores per plane.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+decay2body_f32_kernel(const DecayArgs a, float* __restrict__ p1, float* __restrict__ p2, float* __restrict__ w) {
+    const uint64_t n = a.n_parents * (uint64_t)a.n_samples;
+    const uint64_t n_quads = (n + 3) / 4;
+    const bool aligned = (n & 3ull) == 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t qd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < n_quads; qd += stride) {
+        const uint64_t i0 = qd * 4;
+        float q1[4][4], q2[4][4], wv[4];
+        // (row, sample) of the first event by one 64-bit division, the next three by increment
+        uint64_t r = i0 / a.n_samples;
+        uint32_t s = (uint32_t)(i0 - r * a.n_samples);
+        Philox4 x = {0u, 0u, 0u, 0u};
+        uint32_t have_ctr = 0xffffffffu; uint64_t have_row = ~0ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j > 0 && i0 + j < n) { if (++s == a.n_samples) { s = 0; ++r; } }
+            const double* p = a.table + r * PR_NP;
+            // event s uses Philox counter s>>1 and word pair s&1 (24-bit mantissas): neighbours share the call
+            if ((s >> 1) != have_ctr || r != have_row) {
+                const uint32_t rid = a.row_ids ? __ldg(a.row_ids + r) : (uint32_t)r;
+                x = philox4x32_10(s >> 1, 0u, rid, kTagDecay2 + 16u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                have_ctr = s >> 1; have_row = r;
+            }
+            const float u1 = (float)(((s & 1u) ? x.z : x.x) >> 8) * 5.9604644775390625e-8f;
+            const float u2 = (float)(((s & 1u) ? x.w : x.y) >> 8) * 5.9604644775390625e-8f;
+            float sphi, cphi;
+            sincospif(2.0f * u1, &sphi, &cphi);
+            const float cth = 1.0f - 2.0f * u2;
+            const float sth = 2.0f * sqrtf(u2 * (1.0f - u2));
+            const float pcm = (float)__ldg(p + PR_PCM), ecm = (float)__ldg(p + PR_ECM), gam = (float)__ldg(p + PR_GAM);
+            const float m03 = (float)__ldg(p + PR_M03), m33 = (float)__ldg(p + PR_M33);
+            const float px = pcm * cphi * sth, py = pcm * sphi * sth, pz = pcm * cth;
+            const float ge = gam * ecm, me = m03 * ecm, mp = m03 * pz, m3p = m33 * pz;
+            q1[j][0] = ge + mp; q1[j][1] = px;  q1[j][2] = py;  q1[j][3] = me + m3p;
+            q2[j][0] = ge - mp; q2[j][1] = -px; q2[j][2] = -py; q2[j][3] = me - m3p;
+            wv[j] = (float)__ldg(p + PR_W);
+        }
+        if (aligned) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<float4*>(p1 + (uint64_t)c * n + i0) = make_float4(q1[0][c], q1[1][c], q1[2][c], q1[3][c]);
+                *reinterpret_cast<float4*>(p2 + (uint64_t)c * n + i0) = make_float4(q2[0][c], q2[1][c], q2[2][c], q2[3][c]);
+            }
+            *reinterpret_cast<float4*>(w + i0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        } else {
+            for (int j = 0; j < 4 && i0 + j < n; ++j) {
+                for (int c = 0; c < 4; ++c) { p1[(uint64_t)c * n + i0 + j] = q1[j][c]; p2[(uint64_t)c * n + i0 + j] = q2[j][c]; }
+                w[i0 + j] = wv[j];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // general 2-body decay (arbitrary parent direction, massive daughters): one thread per event, dense 4x4 boost
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -230,6 +289,19 @@ ALPK_EXPORT int alpk_decay2body(const double* row_table, uint64_t n_parents, uin
     if (uniforms) { if (fast) decay2body_kernel<true, true><<<grid, kThreads, 0, st>>>(a); else decay2body_kernel<true, false><<<grid, kThreads, 0, st>>>(a); }
     else { if (fast) decay2body_kernel<false, true><<<grid, kThreads, 0, st>>>(a); else decay2body_kernel<false, false><<<grid, kThreads, 0, st>>>(a); }
     return check_launch("alpk_decay2body");
+}
+
+ALPK_EXPORT int alpk_decay2body_f32(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
+                                    uint64_t seed, float* p1, float* p2, float* w, void* stream) {
+    if (!row_table || !p1 || !p2 || !w) { set_error("alpk_decay2body_f32: null argument"); return 2; }
+    if (n_samples == 0) { set_error("alpk_decay2body_f32: n_samples out of range"); return 2; }
+    const uint64_t n = n_parents * (uint64_t)n_samples;
+    if (n == 0) return 0;
+    DecayArgs a;
+    a.table = row_table; a.n_parents = n_parents; a.n_samples = n_samples; a.row_ids = row_ids;
+    a.uniforms = nullptr; a.seed = seed; a.p1 = nullptr; a.p2 = nullptr; a.w = nullptr;
+    decay2body_f32_kernel<<<grid_for((n + 3) / 4, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(a, p1, p2, w);
+    return check_launch("alpk_decay2body_f32");
 }
 
 ALPK_EXPORT int alpk_decay2body_general(const double* parents_p4, const double* parent_w, uint64_t n_parents, double m1,

@@ -155,6 +155,12 @@ int alpk_decay_parent_rows(const double* energy, const float* decay_w32, uint64_
 int alpk_decay2body(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
                     const double* uniforms, uint64_t seed, int fast, double* p1, double* p2, double* w, void* stream);
 
+/* Optional FP32 mode of alpk_decay2body (north star: 1e-5 relative): float planes p1[4][N], p2[4][N], w[N] (36 B/event),
+ * per-parent constants still from the FP64 row table, 24-bit Philox mantissas (event s: counter s>>1, word pair s&1,
+ * stream tag kTagDecay2+16).  Free-running RNG only. */
+int alpk_decay2body_f32(const double* row_table, uint64_t n_parents, uint32_t n_samples, const uint32_t* row_ids,
+                        uint64_t seed, float* p1, float* p2, float* w, void* stream);
+
 /* General 2-body decay: parents with arbitrary direction (rows {E, px, py, pz}), daughter masses m1, m2, dense 4x4
  * boost -- Decay2Body + lorentz_boost (cross_section_mc.py:496-544, 669-685) as used for parents with a polar angle
  * (generators.py:117-121) and by FluxNeutralMeson2BodyDecay (fluxes.py:1026-1031).  parent_w (may be NULL -> 1): weight

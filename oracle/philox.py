@@ -44,3 +44,15 @@ def uniform_2(seed, tag, row, n):
     x, y, z, w = philox4x32_10((s & np.uint64(0xFFFFFFFF)).astype(np.uint32), (s >> np.uint64(32)).astype(np.uint32),
                                np.uint32(row), np.uint32(tag), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     return u53(x, y), u53(z, w)
+
+
+def uniform_2_f32(seed, tag, row, n):
+    """The 24-bit uniform pairs of the FP32 decay kernel: event s = counter s>>1, word pair s&1, (x|z, y|w) >> 8."""
+    s_ = np.arange(n, dtype=np.uint64)
+    c = s_ >> np.uint64(1)
+    x, y, z, w = philox4x32_10((c & np.uint64(0xFFFFFFFF)).astype(np.uint32), np.uint32(0), np.uint32(row), np.uint32(tag),
+                               seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    odd = (s_ & np.uint64(1)) == 1
+    a = np.where(odd, z, x) >> np.uint32(8)
+    b = np.where(odd, w, y) >> np.uint32(8)
+    return a.astype(np.float64) * 2.0 ** -24, b.astype(np.float64) * 2.0 ** -24

@@ -878,3 +878,24 @@ def test_full_size_c4_epm_channels(A):
     assert max_rel(fa._E.cpu().numpy()[idx], oE) < TOL and max_rel(fa._F.cpu().numpy()[idx], oF) < TOL
     r_a = A.ElectronEventGenerator(fa, A.Material("Ar")).decays(365, 30.0)
     assert np.isfinite(r_b) and np.isfinite(r_a) and r_b >= 0 and r_a >= 0
+
+
+def test_decay_4vectors_fp32_mode(A):
+    """Optional single-precision decay MC: <= 1e-5 of the parent energy from the FP64 oracle on the same variates."""
+    pf = np.stack([np.logspace(0.5, 4, 40), np.full(40, 1e12)], axis=1)
+    ma, ns, seed = 0.1, 2003, 77
+    fl = A.FluxPrimakoffIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=1e-5, seed=seed, **GEOM)
+    fl.simulate(); fl.propagate()
+    gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+    l1, l2, w = gen.simulate_decay_4vectors(100, n_samples=ns, dtype=np.float32)
+    assert l1.pmu.dtype == np.float32 and np.asarray(w).dtype == np.float32 and len(l1) == 40 * ns
+    E = np.asarray(fl.axion_energy)
+    us = [np.zeros(40)]
+    for r in range(40):
+        u1, u2 = PX.uniform_2_f32(seed, PX.TAG_DECAY2 + 16, r, ns)
+        us += [u1, u2]
+    o1, o2, ow = O.decay_4vectors(E, fl.decay_axion_weight, ma, 100, ns, O.UniformSource(np.concatenate(us)))
+    scale = np.repeat(E, ns)[:, None]
+    err = max(np.max(np.abs(l1.pmu - o1) / scale), np.max(np.abs(l2.pmu - o2) / scale))
+    assert err < 1e-5, err
+    assert np.max(np.abs(np.asarray(w) / ow - 1)) < 1e-6
