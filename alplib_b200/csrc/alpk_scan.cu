@@ -111,44 +111,68 @@ scan_kernel(const ScanArgs a) {
     const double* table = a.tables + (uint64_t)im * a.n_rows * NP;
     const ComptonGlobals cg{ma, ma2, a.aa, a.z, (double)a.n_samples};
 
-    // ---- stage 1: regenerate the tile's samples ---------------------------------------------------------------------
-    for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    // ---- stage 1: regenerate the tile's samples; keep only those that can contribute (weight != 0 above threshold),
+    //      compacted in their original order (block-wide exclusive scan), so stage 2 walks live samples only and the
+    //      sums are bit-identical to walking the whole tile (the skipped terms are exact zeros) ------------------------
+    __shared__ int s_warp[kScanThreads / 32];
+    __shared__ int s_live;
+    constexpr int kPer = kScanTile / kScanThreads;                  // consecutive samples per thread
+    double rt_[kPer], rb_[kPer], rw_[kPer], rh_[kPer];
+    int nkeep = 0;
+    unsigned keepmask = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int k = threadIdx.x * kPer + q;
+        if (k >= count) continue;
         const uint64_t i = base + k;
         const uint32_t r = (uint32_t)(i / a.n_samples), s = (uint32_t)(i - (uint64_t)r * a.n_samples);
         const double* b = table + (size_t)r * NP;
         double ea = 0.0, w = 0.0;
-        bool live = __ldg(b) >= 0.0;
+        const bool live = __ldg(b) >= 0.0;
         if (live) {
             if (COMPTON) {
                 double row[CB_NP];
 #pragma unroll
-                for (int q = 0; q < CB_NP; ++q) row[q] = __ldg(b + q);
+                for (int c = 0; c < CB_NP; ++c) row[c] = __ldg(b + c);
                 const double u = uniform_1(a.seed, kTagComptonEa, a.row_offset + r, s);
                 ea = FAST ? compton_sample_fast(u, row, cg, w) : compton_sample(u, row, cg, w);
             } else {
                 ea = __ldg(b); w = __ldg(b + 1);
             }
         }
+        const double h = live ? heaviside(ea - a.geo.ev.threshold, 1.0) : 0.0;
+        if (!((w * h != 0.0) || (w != w))) continue;                // exact zero contribution for every coupling
         const double d = ea * ea - ma2;
-        double t = 0.0, bo = 0.0;
-        if (live) {
-            if (FAST && d > 0.0) {
-                t = rsqrt(d);
-            } else if (FAST) {
-                // E_a <= m_a: the reference gives surv = exp(-inf) = 0 (v = 0) or NaN (E_a < m_a); 1/p_a = inf / NaN
-                t = (d == 0.0) ? INFINITY : NAN;
-            } else {
-                const double pa = sqrt(d);
-                t = pa / ea;                 // v_a
-                bo = ea / ma;                // boost
-            }
+        double t, bo = 0.0;
+        if (FAST) {
+            // E_a <= m_a: the reference gives surv = exp(-inf) = 0 (v = 0) or NaN (E_a < m_a); 1/p_a = inf / NaN
+            t = d > 0.0 ? rsqrt(d) : ((d == 0.0) ? INFINITY : NAN);
         } else {
-            w = 0.0; t = 1.0; bo = 1.0;
+            const double pa = sqrt(d);
+            t = pa / ea;                 // v_a
+            bo = ea / ma;                // boost
         }
-        s_t[k] = t; s_b[k] = bo; s_w[k] = w;
-        s_h[k] = live ? heaviside(ea - a.geo.ev.threshold, 1.0) : 0.0;
+        rt_[q] = t; rb_[q] = bo; rw_[q] = w; rh_[q] = h;      // (static register indexing; compacted on the store)
+        keepmask |= 1u << q;
+        ++nkeep;
+    }
+    // exclusive scan of nkeep over the CTA (warp shuffle scan + per-warp totals)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = nkeep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int q = 0; q < wid; ++q) woff += s_warp[q];
+    if (threadIdx.x == blockDim.x - 1) s_live = woff + incl;
+    int pos = woff + incl - nkeep;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        if (keepmask & (1u << q)) { s_t[pos] = rt_[q]; s_b[pos] = rb_[q]; s_w[pos] = rw_[q]; s_h[pos] = rh_[q]; ++pos; }
     }
     __syncthreads();
+    const int n_live = s_live;
 
     // ---- stage 2: one coupling per thread, broadcast walk over the tile ------------------------------------------------
     const ScanGeom& G = a.geo;
@@ -159,7 +183,7 @@ scan_kernel(const ScanArgs a) {
         const double k2 = width > 0.0 ? (G.neg_len_mbm * ma) * width : 0.0;
         double acc = 0.0;
 #pragma unroll 2
-        for (int k = 0; k < count; ++k) {
+        for (int k = 0; k < n_live; ++k) {
             const double w = s_w[k];
             double surv, dec;
             if (FAST) {
