@@ -14,9 +14,12 @@ opt-in or invisible to a script that only uses the documented attributes:
     simplified arithmetic (one reciprocal square root instead of seven divisions in `propagate`, a shared reciprocal in
     the Compton spectrum); results agree with the reference to <= 1e-9 relative.  `precision="faithful"` follows the
     reference's operation order expression by expression (bit-identical wherever libm allows).
-  * `fused=True` defers `simulate()`/`propagate()` and lets `EventGenerator.decays()` run production -> propagate ->
-    decay-rate in ONE kernel without materialising per-sample arrays (they are recomputed on demand, bit-identically,
-    because the variates are a pure function of the seed).
+  * execution is deferred by default (`fused="auto"`, `alplib_b200.config.FUSED`): `simulate()` / `propagate()` record
+    their arguments and kernels are launched when a result is demanded -- `decays()` then runs production -> propagate
+    -> decay weights in ONE kernel that also materialises every per-sample array in HBM; reading `axion_energy` etc.
+    earlier launches just what that attribute needs.  The variates are a pure function of the seed, so every schedule
+    gives bit-identical arrays.  `fused=False` launches one kernel per call (the reference's schedule); `fused=True`
+    never materialises per-sample arrays unless they are read (reduce-only decay rates).
 
 There is no CPU fallback: every array operation below is a CUDA kernel in libalpk.so.
 """
@@ -59,7 +62,7 @@ class AxionFlux:
     """Generic superclass (reference: fluxes.py:20-89)."""
 
     def __init__(self, axion_mass, target: Material, det_dist, det_length, det_area, n_samples=1000,
-                 off_axis_angle=0.0, timing_window_ns=np.inf, seed=None, device=None, fused=False, keep_f64=False,
+                 off_axis_angle=0.0, timing_window_ns=np.inf, seed=None, device=None, fused=None, keep_f64=False,
                  precision=None):
         self.ma = axion_mass
         self.target_z = target.z[0]
@@ -74,7 +77,7 @@ class AxionFlux:
         self.timing_window = 1e-9 * timing_window_ns
         # --- device state ---
         self.seed = seed
-        self.fused = fused
+        self.fused = config.FUSED if fused is None else fused      # False | True | "auto" (see config.py)
         self.keep_f64 = keep_f64          # also keep the float64 weights before the float32 cast (parity / fp64 mode)
         self.precision = precision if precision is not None else config.PRECISION
         if self.precision not in ("fast", "faithful"):
@@ -264,9 +267,14 @@ class AxionFlux:
     def _decay_rate(self, ev, want_event_w):
         """(rate tensor[1], event_w tensor or None): generators.py:88-92 on the device."""
         rt = self._rt
-        fused = self._fused_decay_rate(ev) if (self.fused and not want_event_w) else None
-        if fused is not None:
-            return fused, None
+        if self.fused is True and not want_event_w:
+            fused = self._fused_decay_rate(ev)
+            if fused is not None:
+                return fused, None
+        elif self.fused == "auto":
+            both = self._fused_decay_materialize(ev, want_event_w)
+            if both is not None:
+                return both
         self._ensure_production()
         self._ensure_propagated()
         n = 0 if self._E is None else int(self._E.shape[0])
@@ -281,6 +289,9 @@ class AxionFlux:
 
     def _fused_decay_rate(self, ev):
         return None      # flux classes with a fused production->propagate->decays kernel override this
+
+    def _fused_decay_materialize(self, ev, want_event_w):
+        return None
 
 
 def _width_e(self, ge, ma):
@@ -411,6 +422,25 @@ class _ChainFlux(AxionFlux):
             rate = rt.empty(1)
             self._launch_samples(None, None, self._pending_prop, ev, rate=rate)
         return rate
+
+    def _fused_decay_materialize(self, ev, want_event_w):
+        """"auto" schedule: production -> propagate -> decays in one kernel that also writes every per-sample array."""
+        if self._rows is None or self._pending_prop is None or self._E is not None or self.keep_f64:
+            return None
+        rt = self._rt
+        n = self._rows[1] * self._rows[2]
+        prop = self._pending_prop
+        with rt.activate():
+            rate = rt.empty(1)
+            E, F = rt.empty(n), rt.empty(n)
+            d32, s32 = rt.empty(n, torch.float32), rt.empty(n, torch.float32)
+            evw = rt.empty(n) if want_event_w else None
+            self._launch_samples(E, F, prop, ev, d32=d32, s32=s32, evw=evw, rate=rate)
+        self._pending_production = None
+        self._pending_prop = None
+        self._set_production(E, F)
+        self._D32, self._S32 = d32, s32
+        return rate, evw
 
     def chain(self, days_exposure, threshold, new_coupling=None, materialize=True, hist_edges=None, hist=None):
         """One-kernel production -> propagate -> decays.  With materialize=True also fills axion_energy/axion_flux/

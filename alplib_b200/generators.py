@@ -71,7 +71,7 @@ class _EventGenerator:
         """days*S_PER_DAY * decay_axion_weight * heaviside(E - threshold, 1), summed (generators.py:48-52, 88-92)."""
         ev = P.event_params(days_exposure, threshold)
         self._need_f32(self.flux._D32, "decay_axion_weight")       # (None while a fused chain is still pending)
-        rate, evw = self.flux._decay_rate(ev, self.materialize_weights and not self.flux.fused)
+        rate, evw = self.flux._decay_rate(ev, self.materialize_weights and self.flux.fused is not True)
         self._store("decay", evw)
         return np.float64(rate.item())
 

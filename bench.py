@@ -291,10 +291,10 @@ def run_gpu(args):
 
     e2e = {}
     e2e_steps = max(3, min(args.steps, 30))
-    for tag, fused in (("e2e", False), ("e2e_fused", True)):
+    for tag, fused in (("e2e", None), ("e2e_eager", False), ("e2e_fused", True)):
         # warm-up: the first eager steps pay cudaMalloc; the first ~30 deferred steps after a materialising phase show
         # allocator/driver hiccups of several ms every other step (tools/dbg_fused.py) before settling
-        for _ in range(40 if fused else 8):
+        for _ in range(40 if fused is not False else 8):
             res = e2e_step(fused)
         del res
         barrier()
@@ -309,8 +309,9 @@ def run_gpu(args):
         e2e[tag] = {"value": world * n_step * e2e_steps / float(dt.item()), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "steps": e2e_steps,
                     "api": "Flux*Isotropic.simulate()/propagate() + EventGenerator.decays()/decays_device()"
-                           + (" with fused=True (deferred, one reduce-only kernel)" if fused else
-                              " (default: every per-sample array materialised in HBM)"),
+                           + (" with fused=True (deferred, one reduce-only kernel)" if fused is True else
+                              " with fused=False (one kernel per call, every per-sample array materialised in HBM)" if fused is False else
+                              " (default schedule: deferred, one kernel that also materialises every per-sample array in HBM)"),
                     "rates": [float(rp), float(rc)]}
         del p, c
     clocks = sampler.stop(t_host0, t_host1) if rank == 0 else None
@@ -397,7 +398,8 @@ def run_gpu(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": workload_config(world), "clocks": clocks, "e2e": e2e["e2e"], "e2e_fused": e2e["e2e_fused"],
+               "config": workload_config(world), "clocks": clocks, "e2e": e2e["e2e"], "e2e_eager": e2e["e2e_eager"],
+               "e2e_fused": e2e["e2e_fused"],
                "gpu_launches": int(launches), "samples_per_step": world * n_step, "rates": final_rates,
                "roofline": roofline, "cpu_baseline": cpu_baseline, "scan": scan}
         print(json.dumps(out))

@@ -159,7 +159,7 @@ def test_compton_fused_equals_unfused(A):
     """One-kernel chain (materialising and reduce-only) vs the three separate launches: identical samples."""
     pf = _c2_flux(300)
     kw = dict(axion_mass=1.5, axion_coupling=1e-7, n_samples=1000, seed=77, **GEOM)
-    a = A.FluxComptonIsotropic(pf, A.Material("W"), **kw)
+    a = A.FluxComptonIsotropic(pf, A.Material("W"), fused=False, **kw)
     a.simulate(); a.propagate(new_coupling=3e-7)
     gen_a = A.ElectronEventGenerator(a, A.Material("Ar"))
     ra = gen_a.decays(100, 5.0)
@@ -179,6 +179,23 @@ def test_compton_fused_equals_unfused(A):
     assert rc == pytest.approx(ra, rel=1e-12)
     assert np.array_equal(c.axion_energy, a.axion_energy)          # recomputed on demand, bit-identical
     assert np.array_equal(c.decay_axion_weight, a.decay_axion_weight)
+    # default schedule ("auto"): deferred, then ONE kernel at decays() that materialises every array
+    d = A.FluxComptonIsotropic(pf, A.Material("W"), **kw)
+    assert d.fused == "auto"
+    d.simulate(); d.propagate(new_coupling=3e-7)
+    assert d._E is None and d._D32 is None
+    gen_d = A.ElectronEventGenerator(d, A.Material("Ar"))
+    rd = gen_d.decays(100, 5.0)
+    assert d._E is not None and d._D32 is not None and rd == pytest.approx(ra, rel=1e-12)
+    assert np.array_equal(d.axion_energy, a.axion_energy) and np.array_equal(d.axion_flux, a.axion_flux)
+    assert np.array_equal(d.decay_axion_weight, a.decay_axion_weight) and np.array_equal(d.scatter_axion_weight, a.scatter_axion_weight)
+    assert np.array_equal(gen_d.decay_weights, gen_a.decay_weights)
+    # reading an attribute before decays() launches just what it needs
+    e_ = A.FluxComptonIsotropic(pf, A.Material("W"), **kw)
+    e_.simulate()
+    assert np.array_equal(e_.axion_flux, a.axion_flux) and len(e_.decay_axion_weight) == 0
+    e_.propagate(new_coupling=3e-7)
+    assert np.array_equal(e_.scatter_axion_weight, a.scatter_axion_weight)
 
 
 def test_compton_rates_statistical(A):
@@ -611,7 +628,8 @@ def test_full_size_c2_chain_properties(A):
     eg = torch.from_numpy(np.repeat(pf[O.compton_row_valid(pf, ma), 0], 10_000)).to(E.device)
     assert bool((E <= eg).all())                                                      # E_a drawn in [ma, E_gamma] of its own row
     # the eager three-kernel path reproduces the same arrays bit for bit
-    fl2 = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=1e-7, n_samples=10_000, seed=0xA1B2C3D4 + 2, **GEOM)
+    fl2 = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=1e-7, n_samples=10_000, seed=0xA1B2C3D4 + 2,
+                                 fused=False, **GEOM)
     fl2.simulate(); fl2.propagate()
     assert torch.equal(fl2._E, E) and torch.equal(fl2._F, F) and torch.equal(fl2._D32, D) and torch.equal(fl2._S32, S)
 
@@ -837,7 +855,7 @@ def test_full_size_c4_epm_channels(A):
     C_ = A.Material("C")
     # --- Brem
     fb = A.FluxBremIsotropic(ef, pfx, C_, target_length=100, axion_mass=ma, axion_coupling=g, n_samples=1000, seed=11, **GEOM_DUNE)
-    fb.simulate(); fb.propagate()
+    fb.simulate(); fb.propagate(); fb.device_arrays()
     n_emit = int(fb._emit.sum().item())
     assert fb._E.shape[0] == n_emit * 1000 and n_emit > 9000
     assert bool(torch.isfinite(fb._F).all()) and bool((fb._F >= 0).all()) and float(fb._E.min().item()) >= ma
@@ -865,7 +883,7 @@ def test_full_size_c4_epm_channels(A):
     assert max_rel(fr.axion_flux, oFr) < 1e-9
     # --- PairAnn
     fa = A.FluxPairAnnihilationIsotropic(pfx, C_, axion_mass=ma, axion_coupling=g, n_samples=100, seed=13, **GEOM_DUNE)
-    fa.simulate(); fa.propagate()
+    fa.simulate(); fa.propagate(); fa.device_arrays()
     keep = O.pairann_row_valid(pfx, ma)
     assert fa._E.shape[0] == int(keep.sum()) * 100
     assert bool(torch.isfinite(fa._F).all()) and bool((fa._F >= 0).all())
