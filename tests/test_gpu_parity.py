@@ -219,7 +219,8 @@ def test_compton_rates_statistical(A):
     fl.propagate()
     import torch
     from alplib_b200.reduce import histogram
-    h = histogram(fl._E, fl._D32, edges).cpu().numpy()
+    dev = fl.device_arrays()                                         # (launches whatever is still pending)
+    h = histogram(dev["axion_energy"], dev["decay_axion_weight"], edges).cpu().numpy()
     oh = O.histogram(oE, p["decay_w"], edges)
     err = np.sqrt(O.histogram(oE, p["decay_w"].astype(np.float64) ** 2, edges))
     sel = oh > 0
