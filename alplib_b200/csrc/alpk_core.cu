@@ -332,6 +332,7 @@ ALPK_EXPORT int alpk_decays(const double* energy, const float* decay_w32, uint64
     if (!h_ev || !rate || !scratch) { set_error("alpk_decays: null argument"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { cudaMemsetAsync(rate, 0, sizeof(double), st); return check_launch("alpk_decays(memset)"); }
+    if (!energy || !decay_w32) { set_error("alpk_decays: null input"); return 2; }
     const int grid = grid_for(n, kThreads * 4, 8);
     decays_kernel<<<grid, kThreads, 0, st>>>(energy, decay_w32, n, to_event(h_ev), event_w, scratch);
     if (check_launch("alpk_decays")) return 1;
@@ -345,6 +346,7 @@ ALPK_EXPORT int alpk_scatter_events(int kind, const double* energy, const float*
     if (kind != 0 && kind != 1) { set_error("alpk_scatter_events: unknown kind %d", kind); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { cudaMemsetAsync(rate, 0, sizeof(double), st); return check_launch("alpk_scatter_events(memset)"); }
+    if (!energy || !scatter_w32) { set_error("alpk_scatter_events: null input"); return 2; }
     ScatterConst sc;
     memset(&sc, 0, sizeof(sc));
     sc.kind = kind;
@@ -367,6 +369,7 @@ ALPK_EXPORT int alpk_pair_events(const double* energy, const float* scatter_w32,
     if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_pair_events: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { cudaMemsetAsync(rate, 0, sizeof(double), st); return 0; }
+    if (!energy || !scatter_w32) { set_error("alpk_pair_events: null input"); return 2; }
     const int grid = grid_for(n, kThreads * 2, 8);
     pair_kernel<<<grid, kThreads, 0, st>>>(energy, scatter_w32, n, log10_e, log10_xs, n_table, lead, mbm2, to_event(h_ev), event_w, scratch);
     if (check_launch("alpk_pair_events")) return 1;
@@ -377,6 +380,7 @@ ALPK_EXPORT int alpk_sum(const double* x, uint64_t n, double* out, double* scrat
     if (!out || !scratch) { set_error("alpk_sum: null argument"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { cudaMemsetAsync(out, 0, sizeof(double), st); return check_launch("alpk_sum(memset)"); }
+    if (!x) { set_error("alpk_sum: null input"); return 2; }
     const int grid = grid_for(n, kThreads * 8, 8);
     sum_kernel<<<grid, kThreads, 0, st>>>(x, n, scratch);
     if (check_launch("alpk_sum")) return 1;
@@ -387,6 +391,7 @@ ALPK_EXPORT int alpk_abs_sigma_mev(const double* log10_e, const double* log10_xs
                                    uint64_t n, double* sigma_mev, void* stream) {
     if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_abs_sigma_mev: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
     if (n == 0) return 0;
+    if (!log10_e || !log10_xs || !energy || !sigma_mev) { set_error("alpk_abs_sigma_mev: null argument"); return 2; }
     abs_sigma_kernel<<<grid_for(n, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(log10_e, log10_xs, n_table, energy, n, sigma_mev);
     return check_launch("alpk_abs_sigma_mev");
 }
@@ -396,6 +401,7 @@ ALPK_EXPORT int alpk_primakoff(const double* e_gamma, const double* phi_gamma, u
                                double ma, double pref, double r02, double* out_energy, double* out_flux, void* stream) {
     if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_primakoff: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
     if (n_rows == 0) return 0;
+    if (!e_gamma || !phi_gamma || !log10_e || !log10_xs || !out_energy || !out_flux) { set_error("alpk_primakoff: null argument"); return 2; }
     primakoff_kernel<<<grid_for(n_rows, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(
         e_gamma, phi_gamma, n_rows, log10_e, log10_xs, n_table, ma, pref, r02, out_energy, out_flux);
     return check_launch("alpk_primakoff");
@@ -408,6 +414,7 @@ ALPK_EXPORT int alpk_compton_rows(const double* e_gamma, const double* phi_gamma
     if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_compton_rows: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
     if (!h_par) { set_error("alpk_compton_rows: null argument"); return 2; }
     if (n_rows == 0) return 0;
+    if (!e_gamma || !phi_gamma || !log10_e || !log10_xs || !row_table) { set_error("alpk_compton_rows: null argument"); return 2; }
     compton_rows_kernel<<<grid_for(n_rows, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(
         e_gamma, phi_gamma, n_rows, log10_e, log10_xs, n_table, to_compton(h_par), row_table);
     return check_launch("alpk_compton_rows");

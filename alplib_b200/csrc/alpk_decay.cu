@@ -268,6 +268,7 @@ ALPK_EXPORT int alpk_decay_parent_rows(const double* energy, const float* decay_
     static_assert(PR_NP == ALPK_PARENT_NP, "header/table layout mismatch");
     if (!h_ev || !row_table) { set_error("alpk_decay_parent_rows: null argument"); return 2; }
     if (n_parents == 0) return 0;
+    if (!energy || !decay_w32) { set_error("alpk_decay_parent_rows: null input"); return 2; }
     EventConst ev;
     ev.days_sec = h_ev->days_sec; ev.days_sec32 = h_ev->days_sec32; ev.days_f64 = h_ev->days_f64; ev.threshold = h_ev->threshold;
     decay_parent_rows_kernel<<<grid_for(n_parents, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(

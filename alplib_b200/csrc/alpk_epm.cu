@@ -132,6 +132,7 @@ ALPK_EXPORT int alpk_brem_rows(const double* e0, const double* w0, uint64_t n_ro
         set_error("alpk_brem_rows: track-length mode needs the electron and positron dN/dE tables"); return 2;
     }
     if (n_rows == 0) return 0;
+    if (!e0 || !w0) { set_error("alpk_brem_rows: null input"); return 2; }
     brem_rows_kernel<<<grid_for(n_rows, 128, 8), 128, 0, (cudaStream_t)stream>>>(
         e0, w0, n_rows, row_ids, u_rows, seed, ele_e, ele_f, n_ele, pos_e, pos_f, n_pos, gl_x, gl_w, to_brem(h_par),
         row_table, emit);
@@ -170,6 +171,7 @@ ALPK_EXPORT int alpk_pairann_rows(const double* e_pos, const double* w_pos, uint
     static_assert(PA_NP == ALPK_PAIRANN_NP, "header/table layout mismatch");
     if (!h_par || !row_table) { set_error("alpk_pairann_rows: null argument"); return 2; }
     if (n_rows == 0) return 0;
+    if (!e_pos || !w_pos) { set_error("alpk_pairann_rows: null input"); return 2; }
     pairann_rows_kernel<<<grid_for(n_rows, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(e_pos, w_pos, n_rows,
                                                                                          to_pair(h_par), row_table);
     return check_launch("alpk_pairann_rows");

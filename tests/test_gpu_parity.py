@@ -590,7 +590,7 @@ def test_output_bounds_canaries(A):
     # decay MC with an odd event count (odd planes are not 16-byte aligned)
     fp = A.FluxPrimakoffIsotropic(np.array([[100.0, 1e12], [40.0, 1e11], [7.0, 1e10]]), A.Material("W"), axion_mass=0.1,
                                   axion_coupling=1e-5, **GEOM)
-    fp.simulate(); fp.propagate()
+    fp.simulate(); fp.propagate(); fp.device_arrays()
     npar, ns = 3, 111
     nev = npar * ns
     table = rt.empty(npar * N.PARENT_NP)
