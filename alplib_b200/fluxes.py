@@ -134,6 +134,7 @@ class AxionFlux:
 
     @axion_energy.setter
     def axion_energy(self, v):
+        self._ensure_production()            # a deferred simulate() must not overwrite (or lose) the other array
         self._pending_production = None
         self._E = self._rt.upload(np.asarray(v, dtype=np.float64).ravel())
         self._host.pop("E", None)
@@ -145,6 +146,7 @@ class AxionFlux:
 
     @axion_flux.setter
     def axion_flux(self, v):
+        self._ensure_production()
         self._pending_production = None
         self._F = self._rt.upload(np.asarray(v, dtype=np.float64).ravel())
         self._host.pop("F", None)
@@ -156,6 +158,8 @@ class AxionFlux:
 
     @decay_axion_weight.setter
     def decay_axion_weight(self, v):
+        self._ensure_production()
+        self._ensure_propagated()
         self._pending_prop = None
         self._D32 = self._rt.upload(np.asarray(v, dtype=np.float32).ravel(), np.float32)
         self._host.pop("D32", None)
@@ -167,6 +171,8 @@ class AxionFlux:
 
     @scatter_axion_weight.setter
     def scatter_axion_weight(self, v):
+        self._ensure_production()
+        self._ensure_propagated()
         self._pending_prop = None
         self._S32 = self._rt.upload(np.asarray(v, dtype=np.float32).ravel(), np.float32)
         self._host.pop("S32", None)
