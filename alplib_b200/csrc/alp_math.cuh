@@ -109,8 +109,7 @@ static const double kExpCoefHost[16] = ALP_EXP_COEFS;
 // of exp on [-ln2/2, ln2/2] computed with 60-digit arithmetic: relative error 1.6e-17, c0 = c1 = 1 exactly), 2^n applied
 // to the exponent field.  <= 1 ulp on [-708, 708] (tests/test_hostmath.py measures it against glibc); anything outside
 // (including NaN) takes the library exp.  Branch-free on the fast path, so two calls interleave.
-ALP_HD double exp_fast(double x) {
-    if (!(fabs(x) <= 708.0)) return exp(x);
+ALP_HD double exp_fast_core(double x) {          // requires |x| <= 708
     const double kShift = 6755399441055744.0;                       // 1.5 * 2^52: rounds to nearest integer
     const double t = fma(x, ALP_EXPC(0), kShift);                   // x * log2(e)
     const double fn = t - kShift;
@@ -133,6 +132,11 @@ ALP_HD double exp_fast(double x) {
     __builtin_memcpy(&out, &bits, 8);
     return out;
 #endif
+}
+
+ALP_HD double exp_fast(double x) {
+    if (!(fabs(x) <= 708.0)) return exp(x);
+    return exp_fast_core(x);
 }
 
 // ---- np.heaviside ---------------------------------------------------------------------------------------------
@@ -302,6 +306,7 @@ struct PropConst {
     double timing_window;     // seconds
     int    fast;              // fast mode: one rsqrt instead of sqrt + 7 divisions (<= 1e-9 relative)
     double k1, k2;            // fast mode: neg_dist_mbm*ma*width, neg_len_mbm*ma*width (0 for width <= 0)
+    double t_safe;            // fast mode: 708/max(|k1|,|k2|) -- largest 1/p_a for which exp_fast_core applies
 };
 
 // Returns the FP64 weights before the float32 cast (decay, scatter); the casts + acceptance are prop_cast().
@@ -329,8 +334,14 @@ ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, dou
         return;
     }
     const double t = rsqrt(d);
-    const double surv = exp_fast(c.k1 * t);
-    const double dec = 1 - exp_fast(c.k2 * t);
+    double surv, dec;
+    if (t <= c.t_safe) {                      // both exponents within [-708, 0]: one range check for the pair
+        surv = exp_fast_core(c.k1 * t);
+        dec = 1 - exp_fast_core(c.k2 * t);
+    } else {
+        surv = exp(c.k1 * t);
+        dec = 1 - exp(c.k2 * t);
+    }
     s64 = (c.rescale * wgt) * surv;
     d64 = s64 * dec;
 }
@@ -341,6 +352,10 @@ ALP_HD float prop_cast(double w64, const PropConst& c) {
     if (c.geom_f64) return (float)((double)w * c.geom);        // (set only together with apply_geom)
     return w * c.geom32;
 }
+
+// Fast mode: always the float32 multiply (an np.float64 acceptance factor would be applied in float64 by the reference:
+// <= 1 float32 ulp apart, the tolerance of the float32 attributes).
+ALP_HD float prop_cast_fast(double w64, const PropConst& c) { return (float)w64 * c.geom32; }
 
 // ---- generators.py:88-92  decays: days*S_PER_DAY*w32*heaviside(E-thr,1) ---------------------------------------------------
 struct EventConst {

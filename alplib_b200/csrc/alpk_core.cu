@@ -72,8 +72,8 @@ propagate_kernel(const double* __restrict__ energy, const double* __restrict__ w
         double d64, s64;
         if (FAST) propagate_sample_fast(__ldg(energy + i), __ldg(weight + i), c, d64, s64);
         else propagate_sample(__ldg(energy + i), __ldg(weight + i), c, d64, s64);
-        d32[i] = prop_cast(d64, c);
-        s32[i] = prop_cast(s64, c);
+        d32[i] = FAST ? prop_cast_fast(d64, c) : prop_cast(d64, c);
+        s32[i] = FAST ? prop_cast_fast(s64, c) : prop_cast(s64, c);
         if (d64o) d64o[i] = d64;
         if (s64o) s64o[i] = s64;
     }
@@ -235,6 +235,7 @@ PropConst to_prop(const alpk_prop_t* p) {
     c.apply_geom = p->apply_geom; c.geom_f64 = p->geom_f64; c.use_tof = p->use_tof; c.tof_light = p->tof_light;
     c.det_dist = p->det_dist; c.timing_window = p->timing_window;
     c.fast = p->fast; c.k1 = p->k1; c.k2 = p->k2;
+    { const double m = fmax(fabs(c.k1), fabs(c.k2)); c.t_safe = m > 0.0 ? 708.0 / m : INFINITY; }
     return c;
 }
 

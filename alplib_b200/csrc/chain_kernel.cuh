@@ -111,8 +111,8 @@ chain_kernel(const ChainArgs<Prod> a) {
                 if (STAGE >= 1) {
                     if (FAST) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
                     else propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
-                    d32v[j] = prop_cast(d64v[j], a.prop);
-                    s32v[j] = prop_cast(s64v[j], a.prop);
+                    d32v[j] = FAST ? prop_cast_fast(d64v[j], a.prop) : prop_cast(d64v[j], a.prop);
+                    s32v[j] = FAST ? prop_cast_fast(s64v[j], a.prop) : prop_cast(s64v[j], a.prop);
                 }
                 if (STAGE >= 2) {
                     evv[j] = decay_event_weight(e[j], d32v[j], a.ev);
