@@ -285,7 +285,7 @@ ALP_HD double compton_sample_fast(double u, const double* b, const ComptonGlobal
     const double r_omx = x * t, r_x = omx * t;                    // 1/(1-x), 1/x
     const double inner = b[CB_K] * ((b[CB_S] - me2 * r_omx) - g.ma2 * r_x) + x;
     const double v = b[CB_Q] * ((x * r_omx) * inner);
-    flux = in ? v : ((x != x) ? x : 0.0 * v);                     // outside the window: 0 (NaN/inf propagate like 0*v)
+    flux = in ? v : 0.0 * v;                                      // outside the window: 0 (NaN/inf propagate like 0*v)
     return ea;
 }
 
