@@ -170,6 +170,19 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and not os.environ.get("ALPK_NO_AUTOBUILD") and not os.environ.get("ALPK_LIB_PATH"):
+        # the library is a build artefact (git-ignored): compile it on first use if nvcc is there.  One builder at a
+        # time (torchrun starts one process per GPU); this is still the CUDA path -- there is no CPU fallback.
+        import fcntl
+        import shutil
+        if shutil.which(os.environ.get("NVCC", "nvcc")):
+            with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    if not os.path.exists(LIB_PATH):
+                        build()
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
     if not os.path.exists(LIB_PATH):
         raise AlpkError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(nvcc, sm_100a).  alplib_b200 has no CPU fallback.")
