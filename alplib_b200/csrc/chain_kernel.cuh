@@ -19,7 +19,11 @@ namespace alpk {
 #ifndef ALPK_MIN_BLOCKS
 #define ALPK_MIN_BLOCKS 4
 #endif
+#ifndef ALPK_INNER_UNROLL
+#define ALPK_INNER_UNROLL 1
+#endif
 constexpr int kUnroll = ALPK_UNROLL;
+constexpr int kInnerUnroll = ALPK_INNER_UNROLL;
 constexpr int kTile = kThreads * 2 * kUnroll;
 
 template <class Prod>
@@ -66,7 +70,7 @@ chain_kernel(const ChainArgs<Prod> a) {
         __syncthreads();
         const uint64_t row0_first = r0 * (uint64_t)a.n_samples;
 
-#pragma unroll 1
+#pragma unroll kInnerUnroll
         for (int k = 0; k < kUnroll; ++k) {
             const uint32_t local = 2 * ((uint32_t)k * kThreads + threadIdx.x);
             if (local >= tile_elems) break;
