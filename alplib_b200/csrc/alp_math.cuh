@@ -17,6 +17,7 @@
 #else
 #define ALP_HD inline
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #endif
 
 namespace alp {
@@ -304,7 +305,7 @@ struct PropConst {
     double tof_light;         // det_dist / (1e-2*C_LIGHT)
     double det_dist;          // metres
     double timing_window;     // seconds
-    int    fast;              // fast mode: one rsqrt instead of sqrt + 7 divisions (<= 1e-9 relative)
+    int    fast;              // 1: fast mode, one rsqrt instead of sqrt + 7 divisions (<= 1e-9 relative); 2: + FP32 transcendentals
     double k1, k2;            // fast mode: neg_dist_mbm*ma*width, neg_len_mbm*ma*width (0 for width <= 0)
     double t_safe;            // fast mode: 708/max(|k1|,|k2|) -- largest 1/p_a for which exp_fast_core applies
 };
@@ -331,6 +332,17 @@ ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, dou
     const double d = ea * ea - c.ma2;
     if (!(d > 0.0) || c.use_tof) {            // E_a <= m_a (v = 0 or NaN) and the time-of-flight cut: reference path
         propagate_sample(ea, wgt, c, d64, s64);
+        return;
+    }
+    if (c.fast == 2) {
+        // optional FP32 mode (north star: 1e-5 relative): only the transcendental part is single precision -- rsqrt and
+        // the two exponentials (~1e-7 relative each); the decay probability uses expm1f, which unlike the reference's
+        // 1 - exp(-x) does not cancel for long-lived ALPs.  Products stay FP64 so the dynamic range is unchanged.
+        const float tf = rsqrtf((float)d);
+        const float surv_f = expf((float)c.k1 * tf);
+        const float dec_f = -expm1f((float)c.k2 * tf);
+        s64 = (c.rescale * wgt) * (double)surv_f;
+        d64 = s64 * (double)dec_f;
         return;
     }
     const double t = rsqrt(d);

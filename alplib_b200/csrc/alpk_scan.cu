@@ -186,7 +186,11 @@ scan_kernel(const ScanArgs a) {
         for (int k = 0; k < n_live; ++k) {
             const double w = s_w[k];
             double surv, dec;
-            if (FAST) {
+            if (FAST && G.fast == 2) {               // optional FP32 transcendentals (see propagate_sample_fast)
+                const float tf = (float)s_t[k];
+                surv = (double)expf((float)k1 * tf);
+                dec = (double)(-expm1f((float)k2 * tf));
+            } else if (FAST) {
                 const double t = s_t[k];
                 surv = exp_fast(k1 * t);
                 dec = 1 - exp_fast(k2 * t);

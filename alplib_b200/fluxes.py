@@ -13,7 +13,9 @@ opt-in or invisible to a script that only uses the documented attributes:
   * `precision="fast"` (default, `alplib_b200.config.PRECISION`) evaluates the same quantities with algebraically
     simplified arithmetic (one reciprocal square root instead of seven divisions in `propagate`, a shared reciprocal in
     the Compton spectrum); results agree with the reference to <= 1e-9 relative.  `precision="faithful"` follows the
-    reference's operation order expression by expression (bit-identical wherever libm allows).
+    reference's operation order expression by expression (bit-identical wherever libm allows).  `precision="fp32"` is the
+    optional single-precision mode of the north star: production stays FP64, the survival / decay probabilities use
+    float rsqrt / exp / expm1 (weights within ~1e-6 of the reference where its own `1 - exp(-x)` is well conditioned).
   * execution is deferred by default (`fused="auto"`, `alplib_b200.config.FUSED`): `simulate()` / `propagate()` record
     their arguments and kernels are launched when a result is demanded -- `decays()` then runs production -> propagate
     -> decay weights in ONE kernel that also materialises every per-sample array in HBM; reading `axion_energy` etc.
@@ -80,8 +82,8 @@ class AxionFlux:
         self.fused = config.FUSED if fused is None else fused      # False | True | "auto" (see config.py)
         self.keep_f64 = keep_f64          # also keep the float64 weights before the float32 cast (parity / fp64 mode)
         self.precision = precision if precision is not None else config.PRECISION
-        if self.precision not in ("fast", "faithful"):
-            raise ValueError("precision must be 'fast' or 'faithful'")
+        if self.precision not in ("fast", "faithful", "fp32"):
+            raise ValueError("precision must be 'fast', 'faithful' or 'fp32'")
         self._device = device
         self._rt_cached = None
         self._reset_samples()
@@ -203,7 +205,7 @@ class AxionFlux:
         return P.prop_params(self.ma, decay_width, rescale_factor, self.det_dist, self.det_length,
                              geom_accept=geom_accept,
                              timing_window=self.timing_window if time_of_flight_cut is not None else None,
-                             fast=self.precision == "fast")
+                             fast="fp32" if self.precision == "fp32" else self.precision == "fast")
 
     def _run_propagate(self, prop):
         self._ensure_production()
@@ -535,7 +537,7 @@ class FluxComptonIsotropic(_ChainFlux):
     def _launch_rows(self):
         """Per-row constants (threshold window, prefactors, sigma_abs lookup) -> row table, on the device."""
         d_eg, d_ph, n_rows, ns, d_ids, d_u, seed = self._inputs
-        par = P.compton_params(self.ma, self.ge, self.target_z, ns, fast=self.precision == "fast")
+        par = P.compton_params(self.ma, self.ge, self.target_z, ns, fast=self.precision != "faithful")
         rt = self._rt
         with rt.activate():
             if n_rows:

@@ -190,7 +190,7 @@ class PhotonEventGenerator(_EventGenerator):
                 N.call("alpk_decay_parent_rows", N.ptr(fl._E), N.ptr(fl._D32), n_flux, float(fl.ma**2), C.byref(ev), ns,
                        N.ptr(table), rt.stream())
                 N.call("alpk_decay2body", N.ptr(table), n_flux, ns, None, N.ptr(d_u), C.c_uint64(seed),
-                       1 if fl.precision == "fast" else 0, N.ptr(p1), N.ptr(p2), N.ptr(w), rt.stream())
+                       1 if fl.precision != "faithful" else 0, N.ptr(p1), N.ptr(p2), N.ptr(w), rt.stream())
             elif n:
                 # parents with a polar angle: 4-vectors assembled per parent exactly as generators.py:117-120 (the
                 # azimuths come from the global NumPy stream like the reference's, or from `parent_phis`), then the

@@ -42,7 +42,7 @@ def prop_params(ma, width, rescale=1.0, det_dist=4.0, det_length=0.2, geom_accep
         p.timing_window = 0.0
     p.det_dist = float(det_dist)
     # fast mode: L/(hbar c v tau) = (L/hbar c) * ma*Gamma / p_a  (exponents = constant / p_a)
-    p.fast = 1 if fast else 0
+    p.fast = 2 if fast == "fp32" else (1 if fast else 0)
     p.k1 = float(p.neg_dist_mbm * ma * width) if width > 0.0 else 0.0
     p.k2 = float(p.neg_len_mbm * ma * width) if width > 0.0 else 0.0
     return p

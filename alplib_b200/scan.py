@@ -70,7 +70,8 @@ def scan_rates(process, photon_flux, target, ma_grid, g_grid, n_samples=100, det
         np_row = 2
         n_samples = 1
     geom = det_area / (4 * pi * det_dist ** 2) if is_isotropic else None
-    prop = P.prop_params(1.0, 0.0, 1.0, det_dist, det_length, geom_accept=geom, fast=precision == "fast")
+    prop = P.prop_params(1.0, 0.0, 1.0, det_dist, det_length, geom_accept=geom,
+                         fast="fp32" if precision == "fp32" else precision == "fast")
     ev = P.event_params(days_exposure, threshold)
     rt = Runtime.get(device)
     xs = AbsCrossSection(target)

@@ -68,7 +68,8 @@ typedef struct {
     double tof_light;        /* det_dist / (1e-2*C_LIGHT) */
     double det_dist;         /* metres */
     double timing_window;    /* seconds */
-    int    fast;             /* 0 = reference operation order; 1 = fast mode (one rsqrt + 2 exp per sample, <= 1e-9 rel.) */
+    int    fast;             /* 0 = reference operation order; 1 = fast mode (one rsqrt + 2 exp per sample, <= 1e-9 rel.);
+                                2 = fast mode with single-precision rsqrt/exp/expm1 (optional FP32 mode, <= 1e-5 rel.) */
     double k1, k2;           /* fast mode: neg_dist_mbm*ma*width and neg_len_mbm*ma*width (0 when width <= 0) */
 } alpk_prop_t;
 

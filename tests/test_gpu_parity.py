@@ -918,3 +918,36 @@ def test_decay_4vectors_fp32_mode(A):
     err = max(np.max(np.abs(l1.pmu - o1) / scale), np.max(np.abs(l2.pmu - o2) / scale))
     assert err < 1e-5, err
     assert np.max(np.abs(np.asarray(w) / ow - 1)) < 1e-6
+
+
+def test_fp32_mode_weights(A, precision):
+    """Optional single-precision mode: weights within 1e-5 of the FP64 oracle (north star) wherever the reference's own
+    1 - exp(-x) is well conditioned (decay_prob > 1e-9; below that the reference loses digits, the expm1f path does not)."""
+    if precision != "fast":
+        pytest.skip("mode under test is selected explicitly")
+    pf = _c2_flux(120)
+    ma, g, ns, seed = 1.5, 3e-6, 400, 9
+    fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=g, n_samples=ns, seed=seed, precision="fp32",
+                                keep_f64=True, **GEOM)
+    fl.simulate(); fl.propagate()
+    keep = O.compton_row_valid(pf, ma)
+    u = np.concatenate([PX.uniform_1(seed, PX.TAG_COMPTON_EA, int(r), ns) for r in np.nonzero(keep)[0]])
+    oE, oF = O.compton_simulate(pf, ma, g, 74, O.AbsCrossSection(O.Material("W")), ns, O.UniformSource(u))
+    assert np.array_equal(fl.axion_energy, oE) and max_rel(fl.axion_flux, oF) < TOL          # production stays FP64
+    p = O.propagate(oE, oF, ma, O.W_ee(g, ma), 1.0, 4.0, 0.2, geom_accept=GA)
+    nz = p["scatter_w64"] != 0
+    assert max_rel(fl.scatter_axion_weight_f64[nz], p["scatter_w64"][nz]) < 1e-5
+    with np.errstate(all="ignore"):
+        dec = np.where(nz, p["decay_w64"] / p["scatter_w64"], 0.0)
+    ok = nz & (dec > 1e-9)
+    assert ok.sum() > 1000
+    assert max_rel(fl.decay_axion_weight_f64[ok], p["decay_w64"][ok]) < 1e-5
+    r32 = A.ElectronEventGenerator(fl, A.Material("Ar")).decays(100, 5.0)
+    _, r64 = O.decays(oE, p["decay_w"], 100, 5.0)
+    assert r32 == pytest.approx(r64, rel=1e-5)
+    # scan in the same mode
+    from alplib_b200.scan import scan_rates
+    gg = np.logspace(-7, -4, 5)
+    m32 = scan_rates("compton", pf, A.Material("W"), [ma], gg, n_samples=ns, days_exposure=100, threshold=5.0, seed=seed, precision="fp32", **GEOM)
+    m64 = scan_rates("compton", pf, A.Material("W"), [ma], gg, n_samples=ns, days_exposure=100, threshold=5.0, seed=seed, precision="fast", **GEOM)
+    assert max_rel(m32, m64) < 1e-5
