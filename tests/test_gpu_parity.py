@@ -951,3 +951,17 @@ def test_fp32_mode_weights(A, precision):
     m32 = scan_rates("compton", pf, A.Material("W"), [ma], gg, n_samples=ns, days_exposure=100, threshold=5.0, seed=seed, precision="fp32", **GEOM)
     m64 = scan_rates("compton", pf, A.Material("W"), [ma], gg, n_samples=ns, days_exposure=100, threshold=5.0, seed=seed, precision="fast", **GEOM)
     assert max_rel(m32, m64) < 1e-5
+
+
+def test_examples_run(A, precision):
+    """The example scripts (reference usage patterns with the import switched) run end to end."""
+    if precision != "fast":
+        pytest.skip("once is enough")
+    import runpy
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runpy.run_path(os.path.join(root, "examples", "ex_readme_primakoff.py"), run_name="__main__")
+    ns = runpy.run_path(os.path.join(root, "examples", "ex_na64_brem.py"), run_name="na64")
+    energies, weights, n_decay, n_compton = ns["get_events"](10.0, 1e-6, use_loop=True)
+    assert energies.shape == weights.shape == (10000,) and np.isfinite(n_decay) and np.isfinite(n_compton)
+    assert n_decay >= 0 and n_compton >= 0 and np.sum(weights) == pytest.approx(n_decay + n_compton, rel=1e-6)
