@@ -3,7 +3,12 @@
 rates on a 200 x 200 grid in two kernel launches, then two-sided limits per mass (reference pattern: README.md:199-226,
 fit.py:12-58 -- one full simulate/propagate/decays chain per grid point).  Needs a B200; `torchrun --nproc-per-node N`
 shards the mass axis over N GPUs."""
+import os
+import sys
+
 import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))   # repo root
 import torch.distributed as dist
 
 from alplib_b200 import Material

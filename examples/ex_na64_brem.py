@@ -2,7 +2,12 @@
 """NA64 missing-energy style flux from ALP bremsstrahlung (reference: examples/ex4_na64.py, README.md:176-236) with the
 B200 drop-in.  The reference script omits `positron_flux`, which makes its default track-length mode raise TypeError
 (SURVEY.md section 4 item 2); a monoenergetic beam is expressed with is_monoenergetic=True.  Needs a B200."""
+import os
+import sys
+
 import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))   # repo root
 
 from alplib_b200 import *   # noqa: F401,F403
 

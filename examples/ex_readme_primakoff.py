@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """README Primakoff example of the reference (README.md:88-117), unchanged apart from the import and the 2-D photon
 table (the README's 1-D `gammas` raises IndexError in the reference as well).  Needs a B200."""
+import os
+import sys
+
 import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))   # repo root
 
 from alplib_b200 import *   # noqa: F401,F403  (was: from alplib.fluxes import *; from alplib.generators import *)
 
