@@ -65,7 +65,42 @@ ALP_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 // 53-bit uniform in [0,1) from two 32-bit words (same construction as MT19937 genrand_res53 / numpy legacy
 // random_sample, so the free-running stream has the reference's granularity).
 ALP_HD double u53(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    // The same value built in the mantissa fields (no int->double conversions, every step exact):
+    //   A = 2^25 + (a>>5) 2^-27,  B = 2^-1 + (b>>6) 2^-53,  u = (A - (2^25 + 2^-1)) + B
+    const double A = __hiloint2double(0x41800000, (int)(a >> 5));
+    const double B = __hiloint2double(0x3FE00000, (int)(b >> 6));
+    return (A - 33554432.5) + B;
+#else
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+#endif
+}
+
+// ---- branch-free reciprocal / reciprocal square root for the fast mode --------------------------------------------
+// Hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-22 relative) + one cubically convergent correction: ~1 ulp for normal,
+// finite, non-zero arguments; no special-case branch (callers guard the argument range), so several of them interleave.
+ALP_HD double rcp_fast(double a) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    e = fma(e, e, e);
+    return fma(y, e, y);
+#else
+    return 1.0 / a;
+#endif
+}
+
+ALP_HD double rsqrt_fast(double d) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = fma(-d, y * y, 1.0);
+    const double p = fma(h, 0.375, 0.5);
+    return fma(p, y * h, y);
+#else
+    return 1.0 / sqrt(d);
+#endif
 }
 
 // Stream tags: 4th counter word.  A variate is a pure function of (seed, tag, row, sample) -- independent of the
@@ -278,13 +313,9 @@ ALP_HD double compton_sample_fast(double u, const double* b, const ComptonGlobal
     const double x = (b[CB_C0] - q) + 1;
     const bool in = (x > b[CB_XMIN]) && (x < b[CB_XMAX]);
     const double omx = 1 - x;
-#if defined(__CUDA_ARCH__)
-    const double t = __drcp_rn(x * omx);
-#else
-    const double t = 1.0 / (x * omx);
-#endif
+    const double t = rcp_fast(x * omx);
     const double r_omx = x * t, r_x = omx * t;                    // 1/(1-x), 1/x
-    const double inner = b[CB_K] * ((b[CB_S] - me2 * r_omx) - g.ma2 * r_x) + x;
+    const double inner = fma(b[CB_K], fma(-g.ma2, r_x, fma(-me2, r_omx, b[CB_S])), x);
     const double v = b[CB_Q] * ((x * r_omx) * inner);
     flux = in ? v : 0.0 * v;                                      // outside the window: 0 (NaN/inf propagate like 0*v)
     return ea;
@@ -308,7 +339,15 @@ struct PropConst {
     int    fast;              // 1: fast mode, one rsqrt instead of sqrt + 7 divisions (<= 1e-9 relative); 2: + FP32 transcendentals
     double k1, k2;            // fast mode: neg_dist_mbm*ma*width, neg_len_mbm*ma*width (0 for width <= 0)
     double t_safe;            // fast mode: 708/max(|k1|,|k2|) -- largest 1/p_a for which exp_fast_core applies
+    double t_fast;            // t_safe when the branch-free path applies (fast == 1, no time-of-flight cut), else -1
 };
+
+// Derived fields of PropConst (after the plain ones are filled in).
+ALP_HD void prop_derive(PropConst& c) {
+    const double m = fmax(fabs(c.k1), fabs(c.k2));
+    c.t_safe = m > 0.0 ? 708.0 / m : INFINITY;
+    c.t_fast = (c.fast == 1 && !c.use_tof) ? c.t_safe : -1.0;
+}
 
 // Returns the FP64 weights before the float32 cast (decay, scatter); the casts + acceptance are prop_cast().
 ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
@@ -328,7 +367,20 @@ ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& 
 }
 
 // Fast mode: L/(hbar c v tau) = L ma Gamma / (hbar c p_a), so both exponents are a constant times 1/p_a.
+// Branch-free attempt: valid (returns true) for the plain FP64 fast mode when p_a^2 is a positive normal number and both
+// exponents lie in [-708, 0]; otherwise the outputs are garbage and propagate_sample_fast() redoes the sample.
+ALP_HD bool propagate_try_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
+    const double d = ea * ea - c.ma2;
+    const double t = rsqrt_fast(d);
+    const double surv = exp_fast_core(c.k1 * t);
+    const double dec = 1 - exp_fast_core(c.k2 * t);
+    s64 = (c.rescale * wgt) * surv;
+    d64 = s64 * dec;
+    return (d > 1e-300) & (t <= c.t_fast);
+}
+
 ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
+    if (propagate_try_fast(ea, wgt, c, d64, s64)) return;
     const double d = ea * ea - c.ma2;
     if (!(d > 0.0) || c.use_tof) {            // E_a <= m_a (v = 0 or NaN) and the time-of-flight cut: reference path
         propagate_sample(ea, wgt, c, d64, s64);
@@ -345,15 +397,9 @@ ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, dou
         d64 = s64 * (double)dec_f;
         return;
     }
-    const double t = rsqrt(d);
-    double surv, dec;
-    if (t <= c.t_safe) {                      // both exponents within [-708, 0]: one range check for the pair
-        surv = exp_fast_core(c.k1 * t);
-        dec = 1 - exp_fast_core(c.k2 * t);
-    } else {
-        surv = exp(c.k1 * t);
-        dec = 1 - exp(c.k2 * t);
-    }
+    const double t = rsqrt(d);                // exponents below -708 (or a subnormal p_a^2): library functions
+    const double surv = exp(c.k1 * t);
+    const double dec = 1 - exp(c.k2 * t);
     s64 = (c.rescale * wgt) * surv;
     d64 = s64 * dec;
 }

@@ -431,7 +431,7 @@ ALPK_EXPORT int alpk_vol_int(const double* energy, const double* weight, uint64_
     c.neg_dist_mbm = h_prop->neg_dist_mbm; c.neg_len_mbm = h_prop->neg_len_mbm; c.geom = 1.0; c.geom32 = 1.0f;
     c.apply_geom = 0; c.geom_f64 = 0; c.use_tof = 0; c.tof_light = 0; c.det_dist = h_prop->det_dist; c.timing_window = 0;
     c.fast = h_prop->fast; c.k1 = h_prop->k1; c.k2 = h_prop->k2;
-    { const double m = fmax(fabs(c.k1), fabs(c.k2)); c.t_safe = m > 0.0 ? 708.0 / m : INFINITY; }
+    prop_derive(c);
     if (h_prop->fast) vol_int_kernel<true><<<grid, kThreads, 0, st>>>(energy, n, nxm, bden, jac, n_points, chunk, c.ma, c.ma2, c.width, inv_mbm, partials);
     else vol_int_kernel<false><<<grid, kThreads, 0, st>>>(energy, n, nxm, bden, jac, n_points, chunk, c.ma, c.ma2, c.width, inv_mbm, partials);
     if (check_launch("alpk_vol_int")) return 1;

@@ -146,7 +146,7 @@ scan_kernel(const ScanArgs a) {
         double t, bo = 0.0;
         if (FAST) {
             // E_a <= m_a: the reference gives surv = exp(-inf) = 0 (v = 0) or NaN (E_a < m_a); 1/p_a = inf / NaN
-            t = d > 0.0 ? rsqrt(d) : ((d == 0.0) ? INFINITY : NAN);
+            t = d > 1e-300 ? rsqrt_fast(d) : (d > 0.0 ? rsqrt(d) : ((d == 0.0) ? INFINITY : NAN));   // as propagate_sample_fast
         } else {
             const double pa = sqrt(d);
             t = pa / ea;                 // v_a

@@ -37,7 +37,9 @@ struct ChainArgs {
     const double* hist_edges; int n_edges; double* hist;     // optional fused weighted histogram of E_a
 };
 
-template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST>   // STAGE 0: production; 1: + propagate; 2: + decays
+// PAIRED: n_samples is even, so the two samples of a thread's pair always lie in the same row and share one Philox call
+// (counter s>>1): no row-straddle / lone-sample handling and no word selects in the hot loop.
+template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED>   // STAGE 0: production; 1: + propagate; 2: + decays
 __global__ void __launch_bounds__(kThreads, ALPK_MIN_BLOCKS)
 chain_kernel(const ChainArgs<Prod> a) {
     using namespace alp;
@@ -60,35 +62,38 @@ chain_kernel(const ChainArgs<Prod> a) {
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t base = tile * tile_elems;
-        const uint64_t last = (base + tile_elems <= n ? base + tile_elems : n) - 1;
+        const uint64_t left = n - base;
+        const uint32_t lim = left < (uint64_t)tile_elems ? (uint32_t)left : tile_elems;   // samples in this tile
         const uint64_t r0 = base / a.n_samples;       // the only 64-bit division, once per tile
-        const uint32_t off_last = (uint32_t)(last - r0 * (uint64_t)a.n_samples);
+        const uint32_t off_last = (uint32_t)((base + lim - 1) - r0 * (uint64_t)a.n_samples);
         const int nrows = (int)(long_rows ? (off_last >= a.n_samples ? 2u : 1u) : off_last / a.n_samples + 1u);   // <= kStageRows
         const double* rows = s_rows;                 // row r -> rows + (r - r0)*NP
         __syncthreads();                             // previous tile finished reading s_rows
         stage_rows<NP>(s_rows, a.table, r0, nrows);
         __syncthreads();
-        const uint64_t row0_first = r0 * (uint64_t)a.n_samples;
+        const uint32_t off0 = (uint32_t)(base - r0 * (uint64_t)a.n_samples);   // offset of the tile in its first row
 
 #pragma unroll kInnerUnroll
         for (int k = 0; k < kUnroll; ++k) {
             const uint32_t local = 2 * ((uint32_t)k * kThreads + threadIdx.x);
-            if (local >= tile_elems) break;
+            if (local >= lim) break;
             const uint64_t i0 = base + local;
-            if (i0 >= n) break;
-            const bool have2 = (i0 + 1 < n);
+            const bool have2 = PAIRED || (local + 1 < lim);
             double e[2], f[2], u[2];
             float d32v[2], s32v[2];
             double d64v[2], s64v[2], evv[2];
             uint32_t rr[2], ss[2];
             {
                 // (row, sample) of the pair: one integer division at most; none when rows are longer than a tile
-                const uint32_t off = (uint32_t)(i0 - row0_first);
+                const uint32_t off = off0 + local;
                 if (long_rows) { rr[0] = off >= a.n_samples ? 1u : 0u; ss[0] = off - (rr[0] ? a.n_samples : 0u); }
                 else { rr[0] = off / a.n_samples; ss[0] = off - rr[0] * a.n_samples; }
-                const bool wrap = ss[0] + 1u == a.n_samples;
-                rr[1] = have2 ? (wrap ? rr[0] + 1u : rr[0]) : rr[0];
-                ss[1] = have2 ? (wrap ? 0u : ss[0] + 1u) : ss[0];
+                if (PAIRED) { rr[1] = rr[0]; ss[1] = ss[0] + 1u; }
+                else {
+                    const bool wrap = ss[0] + 1u == a.n_samples;
+                    rr[1] = have2 ? (wrap ? rr[0] + 1u : rr[0]) : rr[0];
+                    ss[1] = have2 ? (wrap ? 0u : ss[0] + 1u) : ss[0];
+                }
             }
             if (INJECT) {
 #pragma unroll
@@ -98,26 +103,53 @@ chain_kernel(const ChainArgs<Prod> a) {
                 const uint64_t ra = r0 + rr[0];
                 const uint32_t rid0 = a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra;
                 const Philox4 q = philox4x32_10(ss[0] >> 1, 0u, rid0, Prod::kTag, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                u[0] = (ss[0] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
-                if (rr[1] == rr[0] && (ss[1] >> 1) == (ss[0] >> 1)) {
-                    u[1] = (ss[1] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+                if (PAIRED) {                        // ss[0] is even
+                    u[0] = u53(q.x, q.y);
+                    u[1] = u53(q.z, q.w);
                 } else {
-                    const uint64_t rb = r0 + rr[1];
-                    const uint32_t rid1 = a.row_ids ? __ldg(a.row_ids + rb) : (uint32_t)rb;
-                    u[1] = uniform_1(a.seed, Prod::kTag, rid1, ss[1]);
+                    u[0] = (ss[0] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+                    if (rr[1] == rr[0] && (ss[1] >> 1) == (ss[0] >> 1)) {
+                        u[1] = (ss[1] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+                    } else {
+                        const uint64_t rb = r0 + rr[1];
+                        const uint32_t rid1 = a.row_ids ? __ldg(a.row_ids + rb) : (uint32_t)rb;
+                        u[1] = uniform_1(a.seed, Prod::kTag, rid1, ss[1]);
+                    }
+                }
+            }
+            // (a lone last sample computes a throw-away duplicate in slot 1: keeps the pair loop branch-free)
+            if (FAST) {
+                // straight-line arithmetic for both samples (the independent exp / rsqrt / rcp chains interleave); the rare
+                // samples outside the branch-free domain are redone afterwards
+#pragma unroll
+                for (int j = 0; j < 2; ++j) e[j] = Prod::sample_fast(u[j], rows + (size_t)rr[j] * NP, a.g, f[j]);
+                if (STAGE >= 1) {
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) ok &= propagate_try_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                    if (!ok) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        d32v[j] = prop_cast_fast(d64v[j], a.prop);
+                        s32v[j] = prop_cast_fast(s64v[j], a.prop);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    e[j] = Prod::sample(u[j], rows + (size_t)rr[j] * NP, a.g, f[j]);
+                    if (STAGE >= 1) {
+                        propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                        d32v[j] = prop_cast(d64v[j], a.prop);
+                        s32v[j] = prop_cast(s64v[j], a.prop);
+                    }
                 }
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                // (a lone last sample computes a throw-away duplicate in slot 1: keeps the pair loop branch-free)
-                const double* b = rows + (size_t)rr[j] * NP;
-                e[j] = FAST ? Prod::sample_fast(u[j], b, a.g, f[j]) : Prod::sample(u[j], b, a.g, f[j]);
-                if (STAGE >= 1) {
-                    if (FAST) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
-                    else propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
-                    d32v[j] = FAST ? prop_cast_fast(d64v[j], a.prop) : prop_cast(d64v[j], a.prop);
-                    s32v[j] = FAST ? prop_cast_fast(s64v[j], a.prop) : prop_cast(s64v[j], a.prop);
-                }
                 if (STAGE >= 2) {
                     evv[j] = decay_event_weight(e[j], d32v[j], a.ev);
                     if (j == 0 || have2) acc += evv[j];
@@ -206,13 +238,16 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const int grid = grid_for(n, (int)a.tile_elems, 8);
     const bool inj = uniforms != nullptr;
     const bool fast = fast_mode != 0;
-#define ALPK_CHAIN_LAUNCH(I, S, F, H) chain_kernel<Prod, I, S, F, H><<<grid, kThreads, smem, st>>>(a)
+    // the PAIRED specialisation exists for the production configuration (fast arithmetic, free-running RNG, no histogram)
+    const bool paired = (n_samples % 2u) == 0u;
+#define ALPK_CHAIN_LAUNCH(I, S, F, H, P) chain_kernel<Prod, I, S, F, H, P><<<grid, kThreads, smem, st>>>(a)
 #define ALPK_CHAIN_CASE(S)                                                                                   \
     if (hist) {   /* histogram variants only for the free-running RNG */                                      \
         if (inj) { set_error("%s: fused histogram is not available with injected uniforms", what); return 2; } \
-        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true); else ALPK_CHAIN_LAUNCH(false, S, false, true);     \
-    } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false); else ALPK_CHAIN_LAUNCH(true, S, false, false); } \
-    else { if (fast) ALPK_CHAIN_LAUNCH(false, S, true, false); else ALPK_CHAIN_LAUNCH(false, S, false, false); }
+        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true, false); else ALPK_CHAIN_LAUNCH(false, S, false, true, false);     \
+    } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false, false); else ALPK_CHAIN_LAUNCH(true, S, false, false, false); } \
+    else if (fast) { if (paired) ALPK_CHAIN_LAUNCH(false, S, true, false, true); else ALPK_CHAIN_LAUNCH(false, S, true, false, false); } \
+    else ALPK_CHAIN_LAUNCH(false, S, false, false, false);
     if (stage == 0) { ALPK_CHAIN_CASE(0) } else if (stage == 1) { ALPK_CHAIN_CASE(1) } else { ALPK_CHAIN_CASE(2) }
 #undef ALPK_CHAIN_LAUNCH
 #undef ALPK_CHAIN_CASE

@@ -18,7 +18,7 @@ static PropConst to_prop(const alpk_prop_t* p) {
     c.apply_geom = p->apply_geom; c.geom_f64 = p->geom_f64; c.use_tof = p->use_tof; c.tof_light = p->tof_light;
     c.det_dist = p->det_dist; c.timing_window = p->timing_window;
     c.fast = p->fast; c.k1 = p->k1; c.k2 = p->k2;
-    { const double m = fmax(fabs(c.k1), fabs(c.k2)); c.t_safe = m > 0.0 ? 708.0 / m : INFINITY; }
+    prop_derive(c);
     return c;
 }
 
