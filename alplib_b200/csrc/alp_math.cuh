@@ -124,16 +124,35 @@ ALP_HD void uniform_2(uint64_t seed, uint32_t tag, uint32_t row, uint64_t s, dou
     u2 = u53(r.z, r.w);
 }
 
-// Polynomial / reduction constants of exp_fast live in constant memory on the device so that each Horner step is a
-// single DFMA with a constant-bank operand (64-bit immediates would cost two extra moves per step).
-#define ALP_EXP_COEFS {1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10, \
-    2.5110049204818658e-08, 2.763265472252779e-07, 2.755724088722987e-06, 2.4801485441561313e-05, \
-    0.00019841269890076403, 0.0013888888952352863, 0.008333333333319589, 0.04166666666648795, \
-    0.1666666666666668, 0.5000000000000019, 1.0, 0.0, 0.0}
+// Reduction / polynomial constants of exp_fast live in constant memory on the device so that each step is a single
+// DFMA with a constant-bank operand (64-bit immediates would cost two extra moves per step).
+//   [0] 64/ln2   [1],[2] -ln2/64 split high (32 trailing zero bits) / low   [3..6] c2..c5 of exp(r)-1-r ~ r^2 (c2+c3 r+c4 r^2+c5 r^3)
+#define ALP_EXP_COEFS {92.33248261689366, -0.01083042469326756, -2.9815858269852933e-12, 0.4999999999998504, \
+    0.16666666666664529, 0.041666707435930685, 0.008333339157513314, 0.0}
+// 2^(j/64), j = 0..63, rounded to nearest
+#define ALP_EXP_TABLE { \
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, \
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, \
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0, \
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0, \
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0, \
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0, \
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0, \
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0, \
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0, \
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0, \
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0, \
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0, \
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, \
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, \
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0, \
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0 }
 #if defined(__CUDACC__)
-static __constant__ double kExpCoefDev[16] = ALP_EXP_COEFS;
+static __constant__ double kExpCoefDev[8] = ALP_EXP_COEFS;
+static __device__ const double kExpTabDev[64] = ALP_EXP_TABLE;
 #endif
-static const double kExpCoefHost[16] = ALP_EXP_COEFS;
+static const double kExpCoefHost[8] = ALP_EXP_COEFS;
+static const double kExpTabHost[64] = ALP_EXP_TABLE;
 #if defined(__CUDA_ARCH__)
 #define ALP_EXPC(i) kExpCoefDev[i]
 #else
@@ -141,29 +160,35 @@ static const double kExpCoefHost[16] = ALP_EXP_COEFS;
 #endif
 
 // ---- exp for the fast mode ---------------------------------------------------------------------------------------
-// Cody-Waite reduction x = n ln2 + r (|r| <= 0.347), degree-11 polynomial in Horner form (Chebyshev-node interpolant
-// of exp on [-ln2/2, ln2/2] computed with 60-digit arithmetic: relative error 1.6e-17, c0 = c1 = 1 exactly), 2^n applied
-// to the exponent field.  <= 1 ulp on [-708, 708] (tests/test_hostmath.py measures it against glibc); anything outside
-// (including NaN) takes the library exp.  Branch-free on the fast path, so two calls interleave.
+// Table-driven: x = (64 n + j) ln2/64 + r with |r| <= ln2/128 (Cody-Waite, two-part ln2/64), exp(x) = 2^n 2^(j/64) exp(r);
+// 2^(j/64) from a 64-entry table (512 B, L1-resident), exp(r)-1 from a degree-5 polynomial (Chebyshev-node interpolant
+// computed with 60-digit arithmetic, 0.04 ulp), 2^n applied to the exponent field.  10 FP64 instructions, dependency depth 9.
+// Within 1 ulp of glibc on [-708, 708] (tests/test_hostmath.py measures it); anything outside (including NaN) takes
+// the library exp.  Branch-free, so several calls interleave.
 ALP_HD double exp_fast_core(double x) {          // requires |x| <= 708
     const double kShift = 6755399441055744.0;                       // 1.5 * 2^52: rounds to nearest integer
-    const double t = fma(x, ALP_EXPC(0), kShift);                   // x * log2(e)
-    const double fn = t - kShift;
-    double r = fma(fn, ALP_EXPC(1), x);                             // - ln2 high part (32 trailing zero bits)
-    r = fma(fn, ALP_EXPC(2), r);                                    // - ln2 low part
-    double p = ALP_EXPC(3);                                         // c11
-#pragma unroll
-    for (int k = 4; k < 13; ++k) p = fma(p, r, ALP_EXPC(k));       // c10 ... c2
-    p = fma(p, r, ALP_EXPC(13));                                    // c1 = 1
-    p = fma(p, r, ALP_EXPC(13));                                    // c0 = 1
+    const double kd = fma(x, ALP_EXPC(0), kShift);                  // 64 x / ln2
+    const double fn = kd - kShift;
+    double r = fma(fn, ALP_EXPC(1), x);
+    r = fma(fn, ALP_EXPC(2), r);
+    const double r2 = r * r;
+    double q = fma(ALP_EXPC(6), r, ALP_EXPC(5));
+    q = fma(q, r, ALP_EXPC(4));
+    q = fma(q, r, ALP_EXPC(3));
+    const double t = fma(q, r2, r);                                 // exp(r) - 1
 #if defined(__CUDA_ARCH__)
-    const int n = __double2loint(t);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    const int ki = __double2loint(kd);                              // 64 n + j, two's complement
+    const double T = __ldg(&kExpTabDev[ki & 63]);
+    const double p = fma(T, t, T);
+    return __hiloint2double(__double2hiint(p) + ((ki & ~63) << 14), __double2loint(p));
 #else
     int64_t bits, tb;
-    __builtin_memcpy(&tb, &t, 8);
+    __builtin_memcpy(&tb, &kd, 8);
+    const int32_t ki = (int32_t)(uint32_t)tb;
+    const double T = kExpTabHost[ki & 63];
+    const double p = fma(T, t, T);
     __builtin_memcpy(&bits, &p, 8);
-    bits += (int64_t)(int32_t)(uint32_t)tb << 52;
+    bits += (int64_t)(ki >> 6) << 52;
     double out;
     __builtin_memcpy(&out, &bits, 8);
     return out;
