@@ -62,6 +62,31 @@ ALP_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     return Philox4{c0, c1, c2, c3};
 }
 
+// The key schedule (k0 + r W0, k1 + r W1) depends only on the seed: kernels take it precomputed (kernel parameter ->
+// constant bank), which turns each round's key bump + xor into one LOP3 with a constant operand.
+struct PhiloxKeys { uint32_t k[20]; };
+
+ALP_HD PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys rk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return rk;
+}
+
+ALP_HD Philox4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& rk) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c0, hi0, lo0);
+        mulhilo32(M1, c2, hi1, lo1);
+        const uint32_t n0 = hi1 ^ c1 ^ rk.k[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
 // 53-bit uniform in [0,1) from two 32-bit words (same construction as MT19937 genrand_res53 / numpy legacy
 // random_sample, so the free-running stream has the reference's granularity).
 ALP_HD double u53(uint32_t a, uint32_t b) {
@@ -129,24 +154,25 @@ ALP_HD void uniform_2(uint64_t seed, uint32_t tag, uint32_t row, uint64_t s, dou
 //   [0] 64/ln2   [1],[2] -ln2/64 split high (32 trailing zero bits) / low   [3..6] c2..c5 of exp(r)-1-r ~ r^2 (c2+c3 r+c4 r^2+c5 r^3)
 #define ALP_EXP_COEFS {92.33248261689366, -0.01083042469326756, -2.9815858269852933e-12, 0.4999999999998504, \
     0.16666666666664529, 0.041666707435930685, 0.008333339157513314, 0.0}
-// 2^(j/64), j = 0..63, rounded to nearest
+// Entry j holds the bit pattern of 2^(j/64) (rounded to nearest) minus (j << 46), so that adding (64 n + j) << 46 to it
+// yields 2^n 2^(j/64) with a single integer add (the construction of glibc's exp table).
 #define ALP_EXP_TABLE { \
-    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, \
-    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, \
-    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0, \
-    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0, \
-    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0, \
-    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0, \
-    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0, \
-    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0, \
-    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0, \
-    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0, \
-    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0, \
-    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0, \
-    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, \
-    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, \
-    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0, \
-    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0 }
+    0x1.0000000000000p+0, 0x1.fec9a3e778061p-1, 0x1.fd9b0d3158574p-1, 0x1.fc74518759bc8p-1, \
+    0x1.fb5586cf9890fp-1, 0x1.fa3ec32d3d1a2p-1, 0x1.f9301d0125b51p-1, 0x1.f829aaea92de0p-1, \
+    0x1.f72b83c7d517bp-1, 0x1.f635beb6fcb75p-1, 0x1.f54873168b9aap-1, 0x1.f463b88628cd6p-1, \
+    0x1.f387a6e756238p-1, 0x1.f2b4565e27cddp-1, 0x1.f1e9df51fdee1p-1, 0x1.f1285a6e4030bp-1, \
+    0x1.f06fe0a31b715p-1, 0x1.efc08b26416ffp-1, 0x1.ef1a7373aa9cbp-1, 0x1.ee7db34e59ff7p-1, \
+    0x1.edea64c123422p-1, 0x1.ed60a21f72e2ap-1, 0x1.ece086061892dp-1, 0x1.ec6a2b5c13cd0p-1, \
+    0x1.ebfdad5362a27p-1, 0x1.eb9b2769d2ca7p-1, 0x1.eb42b569d4f82p-1, 0x1.eaf4736b527dap-1, \
+    0x1.eab07dd485429p-1, 0x1.ea76f15ad2148p-1, 0x1.ea47eb03a5585p-1, 0x1.ea23882552225p-1, \
+    0x1.ea09e667f3bcdp-1, 0x1.e9fb23c651a2fp-1, 0x1.e9f75e8ec5f74p-1, 0x1.e9feb564267c9p-1, \
+    0x1.ea11473eb0187p-1, 0x1.ea2f336cf4e62p-1, 0x1.ea589994cce13p-1, 0x1.ea8d99b4492edp-1, \
+    0x1.eace5422aa0dbp-1, 0x1.eb1ae99157736p-1, 0x1.eb737b0cdc5e5p-1, 0x1.ebd829fde4e50p-1, \
+    0x1.ec49182a3f090p-1, 0x1.ecc667b5de565p-1, 0x1.ed503b23e255dp-1, 0x1.ede6b5579fdbfp-1, \
+    0x1.ee89f995ad3adp-1, 0x1.ef3a2b84f15fbp-1, 0x1.eff76f2fb5e47p-1, 0x1.f0c1e904bc1d2p-1, \
+    0x1.f199bdd85529cp-1, 0x1.f27f12e57d14bp-1, 0x1.f3720dcef9069p-1, 0x1.f472d4a07897cp-1, \
+    0x1.f5818dcfba487p-1, 0x1.f69e603db3285p-1, 0x1.f7c97337b9b5fp-1, 0x1.f902ee78b3ff6p-1, \
+    0x1.fa4afa2a490dap-1, 0x1.fba1bee615a27p-1, 0x1.fd0765b6e4540p-1, 0x1.fe7c1819e90d8p-1 }
 #if defined(__CUDACC__)
 static __constant__ double kExpCoefDev[8] = ALP_EXP_COEFS;
 static __device__ const double kExpTabDev[64] = ALP_EXP_TABLE;
@@ -165,7 +191,7 @@ static const double kExpTabHost[64] = ALP_EXP_TABLE;
 // computed with 60-digit arithmetic, 0.04 ulp), 2^n applied to the exponent field.  10 FP64 instructions, dependency depth 9.
 // Within 1 ulp of glibc on [-708, 708] (tests/test_hostmath.py measures it); anything outside (including NaN) takes
 // the library exp.  Branch-free, so several calls interleave.
-ALP_HD double exp_fast_core(double x) {          // requires |x| <= 708
+ALP_HD double exp_fast_core(double x, const double* tab = nullptr) {          // requires |x| <= 708
     const double kShift = 6755399441055744.0;                       // 1.5 * 2^52: rounds to nearest integer
     const double kd = fma(x, ALP_EXPC(0), kShift);                  // 64 x / ln2
     const double fn = kd - kShift;
@@ -178,20 +204,20 @@ ALP_HD double exp_fast_core(double x) {          // requires |x| <= 708
     const double t = fma(q, r2, r);                                 // exp(r) - 1
 #if defined(__CUDA_ARCH__)
     const int ki = __double2loint(kd);                              // 64 n + j, two's complement
-    const double T = __ldg(&kExpTabDev[ki & 63]);
-    const double p = fma(T, t, T);
-    return __hiloint2double(__double2hiint(p) + ((ki & ~63) << 14), __double2loint(p));
+    // `tab`: a copy of the table in shared memory (the chain kernels); default: the global copy through L1
+    const double tv = tab ? tab[ki & 63] : __ldg(&kExpTabDev[ki & 63]);
+    const double S = __hiloint2double(__double2hiint(tv) + (ki << 14), __double2loint(tv));   // 2^n 2^(j/64)
+    return fma(S, t, S);
 #else
     int64_t bits, tb;
     __builtin_memcpy(&tb, &kd, 8);
     const int32_t ki = (int32_t)(uint32_t)tb;
-    const double T = kExpTabHost[ki & 63];
-    const double p = fma(T, t, T);
-    __builtin_memcpy(&bits, &p, 8);
-    bits += (int64_t)(ki >> 6) << 52;
-    double out;
-    __builtin_memcpy(&out, &bits, 8);
-    return out;
+    const double tv = tab ? tab[ki & 63] : kExpTabHost[ki & 63];
+    __builtin_memcpy(&bits, &tv, 8);
+    bits += (int64_t)((uint64_t)(int64_t)ki << 46);
+    double S;
+    __builtin_memcpy(&S, &bits, 8);
+    return fma(S, t, S);
 #endif
 }
 
@@ -364,14 +390,14 @@ struct PropConst {
     int    fast;              // 1: fast mode, one rsqrt instead of sqrt + 7 divisions (<= 1e-9 relative); 2: + FP32 transcendentals
     double k1, k2;            // fast mode: neg_dist_mbm*ma*width, neg_len_mbm*ma*width (0 for width <= 0)
     double t_safe;            // fast mode: 708/max(|k1|,|k2|) -- largest 1/p_a for which exp_fast_core applies
-    double t_fast;            // t_safe when the branch-free path applies (fast == 1, no time-of-flight cut), else -1
+    double t_fast;            // min(t_safe, 1e140) when the branch-free path applies (fast == 1, no time-of-flight cut), else -1
 };
 
 // Derived fields of PropConst (after the plain ones are filled in).
 ALP_HD void prop_derive(PropConst& c) {
     const double m = fmax(fabs(c.k1), fabs(c.k2));
     c.t_safe = m > 0.0 ? 708.0 / m : INFINITY;
-    c.t_fast = (c.fast == 1 && !c.use_tof) ? c.t_safe : -1.0;
+    c.t_fast = (c.fast == 1 && !c.use_tof) ? fmin(c.t_safe, 1e140) : -1.0;
 }
 
 // Returns the FP64 weights before the float32 cast (decay, scatter); the casts + acceptance are prop_cast().
@@ -394,14 +420,16 @@ ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& 
 // Fast mode: L/(hbar c v tau) = L ma Gamma / (hbar c p_a), so both exponents are a constant times 1/p_a.
 // Branch-free attempt: valid (returns true) for the plain FP64 fast mode when p_a^2 is a positive normal number and both
 // exponents lie in [-708, 0]; otherwise the outputs are garbage and propagate_sample_fast() redoes the sample.
-ALP_HD bool propagate_try_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
+// (d <= 1e-300, negative or NaN gives t >= 1e150, inf or NaN: t_fast <= 1e140 rejects them with the one comparison.)
+ALP_HD bool propagate_try_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64,
+                               const double* exp_tab = nullptr) {
     const double d = ea * ea - c.ma2;
     const double t = rsqrt_fast(d);
-    const double surv = exp_fast_core(c.k1 * t);
-    const double dec = 1 - exp_fast_core(c.k2 * t);
+    const double surv = exp_fast_core(c.k1 * t, exp_tab);
+    const double dec = 1 - exp_fast_core(c.k2 * t, exp_tab);
     s64 = (c.rescale * wgt) * surv;
     d64 = s64 * dec;
-    return (d > 1e-300) & (t <= c.t_fast);
+    return t <= c.t_fast;
 }
 
 ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
@@ -452,6 +480,14 @@ ALP_HD double decay_event_weight(double ea, float w32, const EventConst& c) {
     const double base = c.days_f64 ? c.days_sec * (double)w32 : (double)(c.days_sec32 * w32);
     const double d = ea - c.threshold;
     return base * (d >= 0.0 ? 1.0 : (d < 0.0 ? 0.0 : d));        // heaviside(d, 1.0); NaN propagates
+}
+
+// The same inside the fused chain, where E_a and the weight come from the same sample (a NaN E_a implies a NaN weight, so
+// the NaN branch of heaviside is covered by the product) and E_a - threshold >= 0 <=> E_a >= threshold (IEEE subtraction
+// is zero only for equal operands).
+ALP_HD double decay_event_weight_coupled(double ea, float w32, const EventConst& c) {
+    const double base = c.days_f64 ? c.days_sec * (double)w32 : (double)(c.days_sec32 * w32);
+    return ea >= c.threshold ? base : base * 0.0;
 }
 
 // ---- 2-body decay a -> gamma gamma of a forward parent (generators.py:116-126, cross_section_mc.py:510-544,669-685) ----------

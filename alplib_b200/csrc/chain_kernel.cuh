@@ -30,6 +30,7 @@ template <class Prod>
 struct ChainArgs {
     const double* table; uint64_t n_rows; uint32_t n_samples; const uint32_t* row_ids;
     typename Prod::Globals g; const double* uniforms; uint64_t seed;
+    alp::PhiloxKeys rk;                                       // key schedule of `seed`
     double* out_e; double* out_f;
     alp::PropConst prop; float* d32; float* s32; double* d64; double* s64;
     alp::EventConst ev; double* event_w; double* partials;
@@ -37,23 +38,149 @@ struct ChainArgs {
     const double* hist_edges; int n_edges; double* hist;     // optional fused weighted histogram of E_a
 };
 
-// PAIRED: n_samples is even, so the two samples of a thread's pair always lie in the same row and share one Philox call
-// (counter s>>1): no row-straddle / lone-sample handling and no word selects in the hot loop.
-template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED>   // STAGE 0: production; 1: + propagate; 2: + decays
+// Which per-sample arrays a launch writes: checked once on the host so the specialised kernels carry no null tests.
+enum ChainOut : int {
+    kOutGeneric = 0,      // any subset (null pointer = not written)
+    kOutStandard = 1,     // exactly the reference's attributes of the stage: E_a, flux [, f32 decay/scatter weights [, event weights]]
+    kOutNone = 2          // nothing (rate / histogram only)
+};
+
+// One pair of adjacent samples (i0 = base + local, i0 even relative to the tile).
+//   PAIRED: n_samples is even, so the two samples always lie in the same row and share one Philox call (counter s>>1):
+//           no row-straddle / lone-sample handling and no word selects.
+//   CHECK:  the tile may be partial (have2 can be false).
+template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT, bool CHECK>
+__device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const double* rows, const double* s_tab,
+                                           const double* s_edges, double* s_bins, uint64_t r0, uint32_t off0,
+                                           uint64_t base, uint32_t local, uint32_t lim, bool long_rows, double& acc) {
+    using namespace alp;
+    constexpr int NP = Prod::NP;
+    const uint64_t i0 = base + local;
+    const bool have2 = (PAIRED && !CHECK) || (local + 1 < lim);
+    double e[2], f[2], u[2];
+    float d32v[2], s32v[2];
+    double d64v[2], s64v[2], evv[2];
+    uint32_t rr[2], ss[2];
+    {
+        // (row, sample) of the pair: one integer division at most; none when rows are longer than a tile
+        const uint32_t off = off0 + local;
+        if (long_rows) { rr[0] = off >= a.n_samples ? 1u : 0u; ss[0] = off - (rr[0] ? a.n_samples : 0u); }
+        else { rr[0] = off / a.n_samples; ss[0] = off - rr[0] * a.n_samples; }
+        if (PAIRED) { rr[1] = rr[0]; ss[1] = ss[0] + 1u; }
+        else {
+            const bool wrap = ss[0] + 1u == a.n_samples;
+            rr[1] = have2 ? (wrap ? rr[0] + 1u : rr[0]) : rr[0];
+            ss[1] = have2 ? (wrap ? 0u : ss[0] + 1u) : ss[0];
+        }
+    }
+    if (INJECT) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) u[j] = __ldg(a.uniforms + Prod::uidx(r0 + rr[j], ss[j], a.n_samples));
+    } else {
+        // sample s uses Philox counter s>>1, word pair s&1: adjacent samples of one row share a call
+        const uint64_t ra = r0 + rr[0];
+        const uint32_t rid0 = a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra;
+        const Philox4 q = philox4x32_10_rk(ss[0] >> 1, 0u, rid0, Prod::kTag, a.rk);
+        if (PAIRED) {                        // ss[0] is even
+            u[0] = u53(q.x, q.y);
+            u[1] = u53(q.z, q.w);
+        } else {
+            u[0] = (ss[0] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+            if (rr[1] == rr[0] && (ss[1] >> 1) == (ss[0] >> 1)) {
+                u[1] = (ss[1] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
+            } else {
+                const uint64_t rb = r0 + rr[1];
+                const uint32_t rid1 = a.row_ids ? __ldg(a.row_ids + rb) : (uint32_t)rb;
+                u[1] = uniform_1(a.seed, Prod::kTag, rid1, ss[1]);
+            }
+        }
+    }
+    // (a lone last sample computes a throw-away duplicate in slot 1: keeps the pair code branch-free)
+    if (FAST) {
+        // straight-line arithmetic for both samples (the independent exp / rsqrt / rcp chains interleave); the rare
+        // samples outside the branch-free domain are redone afterwards
+#pragma unroll
+        for (int j = 0; j < 2; ++j) e[j] = Prod::sample_fast(u[j], rows + (size_t)rr[j] * NP, a.g, f[j]);
+        if (STAGE >= 1) {
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) ok &= propagate_try_fast(e[j], f[j], a.prop, d64v[j], s64v[j], s_tab);
+            if (!ok) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                d32v[j] = prop_cast_fast(d64v[j], a.prop);
+                s32v[j] = prop_cast_fast(s64v[j], a.prop);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            e[j] = Prod::sample(u[j], rows + (size_t)rr[j] * NP, a.g, f[j]);
+            if (STAGE >= 1) {
+                propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                d32v[j] = prop_cast(d64v[j], a.prop);
+                s32v[j] = prop_cast(s64v[j], a.prop);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (STAGE >= 2) {
+            evv[j] = FAST ? decay_event_weight_coupled(e[j], d32v[j], a.ev) : decay_event_weight(e[j], d32v[j], a.ev);
+            if (j == 0 || have2) acc += evv[j];
+        }
+        if (HIST && (j == 0 || have2)) {
+            // np.histogram(E_a, bins=edges, weights=<weight of the last fused stage>)
+            const double hw = STAGE >= 2 ? evv[j] : (STAGE == 1 ? (double)d32v[j] : f[j]);
+            const int bin = find_bin(e[j], s_edges, a.n_edges);
+            if (bin >= 0 && hw != 0.0) atomicAdd(s_bins + bin, hw);
+        }
+    }
+    if (OUT == kOutNone) return;
+    constexpr bool kAll = OUT == kOutStandard;          // pointers known non-null (d64 / s64 known null)
+    if (have2) {
+        if (kAll || a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
+        if (kAll || a.out_f) *reinterpret_cast<double2*>(a.out_f + i0) = make_double2(f[0], f[1]);
+        if (STAGE >= 1) {
+            if (kAll || a.d32) *reinterpret_cast<float2*>(a.d32 + i0) = make_float2(d32v[0], d32v[1]);
+            if (kAll || a.s32) *reinterpret_cast<float2*>(a.s32 + i0) = make_float2(s32v[0], s32v[1]);
+            if (!kAll && a.d64) *reinterpret_cast<double2*>(a.d64 + i0) = make_double2(d64v[0], d64v[1]);
+            if (!kAll && a.s64) *reinterpret_cast<double2*>(a.s64 + i0) = make_double2(s64v[0], s64v[1]);
+        }
+        if (STAGE >= 2 && (kAll || a.event_w)) *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
+    } else {
+        if (kAll || a.out_e) a.out_e[i0] = e[0];
+        if (kAll || a.out_f) a.out_f[i0] = f[0];
+        if (STAGE >= 1) {
+            if (kAll || a.d32) a.d32[i0] = d32v[0];
+            if (kAll || a.s32) a.s32[i0] = s32v[0];
+            if (!kAll && a.d64) a.d64[i0] = d64v[0];
+            if (!kAll && a.s64) a.s64[i0] = s64v[0];
+        }
+        if (STAGE >= 2 && (kAll || a.event_w)) a.event_w[i0] = evv[0];
+    }
+}
+
+template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT>   // STAGE 0: production; 1: + propagate; 2: + decays
 __global__ void __launch_bounds__(kThreads, ALPK_MIN_BLOCKS)
 chain_kernel(const ChainArgs<Prod> a) {
     using namespace alp;
     constexpr int NP = Prod::NP;
     __shared__ double s_rows[kStageRows * NP];
     __shared__ double red[32];
+    __shared__ double s_tab[64];                     // exp_fast table (fast mode, STAGE >= 1)
     extern __shared__ double s_hist_mem[];           // [n_edges] edges + [n_edges-1] privatised bins (only if a.hist)
     double* s_edges = s_hist_mem;
     double* s_bins = s_hist_mem + a.n_edges;
     if (HIST) {
         for (int i = threadIdx.x; i < a.n_edges; i += blockDim.x) s_edges[i] = __ldg(a.hist_edges + i);
         for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) s_bins[i] = 0.0;
-        // (made visible by the __syncthreads of the first tile)
     }
+    if (FAST && STAGE >= 1 && threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    // (all made visible by the __syncthreads of the first tile)
     const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
     const uint32_t tile_elems = a.tile_elems;        // kTile, or fewer when rows are so short that a full tile would
     const uint64_t n_tiles = (n + tile_elems - 1) / tile_elems;   // touch more than kStageRows of them
@@ -67,120 +194,23 @@ chain_kernel(const ChainArgs<Prod> a) {
         const uint64_t r0 = base / a.n_samples;       // the only 64-bit division, once per tile
         const uint32_t off_last = (uint32_t)((base + lim - 1) - r0 * (uint64_t)a.n_samples);
         const int nrows = (int)(long_rows ? (off_last >= a.n_samples ? 2u : 1u) : off_last / a.n_samples + 1u);   // <= kStageRows
-        const double* rows = s_rows;                 // row r -> rows + (r - r0)*NP
         __syncthreads();                             // previous tile finished reading s_rows
         stage_rows<NP>(s_rows, a.table, r0, nrows);
         __syncthreads();
         const uint32_t off0 = (uint32_t)(base - r0 * (uint64_t)a.n_samples);   // offset of the tile in its first row
 
+        if (PAIRED && lim == (uint32_t)kTile) {       // full tile: no bounds tests in the loop
 #pragma unroll kInnerUnroll
-        for (int k = 0; k < kUnroll; ++k) {
-            const uint32_t local = 2 * ((uint32_t)k * kThreads + threadIdx.x);
-            if (local >= lim) break;
-            const uint64_t i0 = base + local;
-            const bool have2 = PAIRED || (local + 1 < lim);
-            double e[2], f[2], u[2];
-            float d32v[2], s32v[2];
-            double d64v[2], s64v[2], evv[2];
-            uint32_t rr[2], ss[2];
-            {
-                // (row, sample) of the pair: one integer division at most; none when rows are longer than a tile
-                const uint32_t off = off0 + local;
-                if (long_rows) { rr[0] = off >= a.n_samples ? 1u : 0u; ss[0] = off - (rr[0] ? a.n_samples : 0u); }
-                else { rr[0] = off / a.n_samples; ss[0] = off - rr[0] * a.n_samples; }
-                if (PAIRED) { rr[1] = rr[0]; ss[1] = ss[0] + 1u; }
-                else {
-                    const bool wrap = ss[0] + 1u == a.n_samples;
-                    rr[1] = have2 ? (wrap ? rr[0] + 1u : rr[0]) : rr[0];
-                    ss[1] = have2 ? (wrap ? 0u : ss[0] + 1u) : ss[0];
-                }
-            }
-            if (INJECT) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) u[j] = __ldg(a.uniforms + Prod::uidx(r0 + rr[j], ss[j], a.n_samples));
-            } else {
-                // sample s uses Philox counter s>>1, word pair s&1: adjacent samples of one row share a call
-                const uint64_t ra = r0 + rr[0];
-                const uint32_t rid0 = a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra;
-                const Philox4 q = philox4x32_10(ss[0] >> 1, 0u, rid0, Prod::kTag, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                if (PAIRED) {                        // ss[0] is even
-                    u[0] = u53(q.x, q.y);
-                    u[1] = u53(q.z, q.w);
-                } else {
-                    u[0] = (ss[0] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
-                    if (rr[1] == rr[0] && (ss[1] >> 1) == (ss[0] >> 1)) {
-                        u[1] = (ss[1] & 1u) ? u53(q.z, q.w) : u53(q.x, q.y);
-                    } else {
-                        const uint64_t rb = r0 + rr[1];
-                        const uint32_t rid1 = a.row_ids ? __ldg(a.row_ids + rb) : (uint32_t)rb;
-                        u[1] = uniform_1(a.seed, Prod::kTag, rid1, ss[1]);
-                    }
-                }
-            }
-            // (a lone last sample computes a throw-away duplicate in slot 1: keeps the pair loop branch-free)
-            if (FAST) {
-                // straight-line arithmetic for both samples (the independent exp / rsqrt / rcp chains interleave); the rare
-                // samples outside the branch-free domain are redone afterwards
-#pragma unroll
-                for (int j = 0; j < 2; ++j) e[j] = Prod::sample_fast(u[j], rows + (size_t)rr[j] * NP, a.g, f[j]);
-                if (STAGE >= 1) {
-                    bool ok = true;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) ok &= propagate_try_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
-                    if (!ok) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        d32v[j] = prop_cast_fast(d64v[j], a.prop);
-                        s32v[j] = prop_cast_fast(s64v[j], a.prop);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    e[j] = Prod::sample(u[j], rows + (size_t)rr[j] * NP, a.g, f[j]);
-                    if (STAGE >= 1) {
-                        propagate_sample(e[j], f[j], a.prop, d64v[j], s64v[j]);
-                        d32v[j] = prop_cast(d64v[j], a.prop);
-                        s32v[j] = prop_cast(s64v[j], a.prop);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (STAGE >= 2) {
-                    evv[j] = decay_event_weight(e[j], d32v[j], a.ev);
-                    if (j == 0 || have2) acc += evv[j];
-                }
-                if (HIST && (j == 0 || have2)) {
-                    // np.histogram(E_a, bins=edges, weights=<weight of the last fused stage>)
-                    const double hw = STAGE >= 2 ? evv[j] : (STAGE == 1 ? (double)d32v[j] : f[j]);
-                    const int bin = find_bin(e[j], s_edges, a.n_edges);
-                    if (bin >= 0 && hw != 0.0) atomicAdd(s_bins + bin, hw);
-                }
-            }
-            if (have2) {
-                if (a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
-                if (a.out_f) *reinterpret_cast<double2*>(a.out_f + i0) = make_double2(f[0], f[1]);
-                if (STAGE >= 1) {
-                    if (a.d32) *reinterpret_cast<float2*>(a.d32 + i0) = make_float2(d32v[0], d32v[1]);
-                    if (a.s32) *reinterpret_cast<float2*>(a.s32 + i0) = make_float2(s32v[0], s32v[1]);
-                    if (a.d64) *reinterpret_cast<double2*>(a.d64 + i0) = make_double2(d64v[0], d64v[1]);
-                    if (a.s64) *reinterpret_cast<double2*>(a.s64 + i0) = make_double2(s64v[0], s64v[1]);
-                }
-                if (STAGE >= 2 && a.event_w) *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
-            } else {
-                if (a.out_e) a.out_e[i0] = e[0];
-                if (a.out_f) a.out_f[i0] = f[0];
-                if (STAGE >= 1) {
-                    if (a.d32) a.d32[i0] = d32v[0];
-                    if (a.s32) a.s32[i0] = s32v[0];
-                    if (a.d64) a.d64[i0] = d64v[0];
-                    if (a.s64) a.s64[i0] = s64v[0];
-                }
-                if (STAGE >= 2 && a.event_w) a.event_w[i0] = evv[0];
+            for (int k = 0; k < kUnroll; ++k)
+                chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, false>(
+                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, 2 * ((uint32_t)k * kThreads + threadIdx.x), lim, long_rows, acc);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < kUnroll; ++k) {
+                const uint32_t local = 2 * ((uint32_t)k * kThreads + threadIdx.x);
+                if (local >= lim) break;
+                chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, true>(
+                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, local, lim, long_rows, acc);
             }
         }
     }
@@ -220,7 +250,7 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     ChainArgs<Prod> a;
     memset(&a, 0, sizeof(a));
     a.table = row_table; a.n_rows = n_rows; a.n_samples = n_samples; a.row_ids = row_ids;
-    a.g = g; a.uniforms = uniforms; a.seed = seed;
+    a.g = g; a.uniforms = uniforms; a.seed = seed; a.rk = alp::philox_keys(seed);
     a.out_e = out_energy; a.out_f = out_flux;
     const int stage = h_ev ? 2 : (h_prop ? 1 : 0);
     if (h_prop) { a.prop = to_prop(h_prop); a.d32 = decay_w32; a.s32 = scatter_w32; a.d64 = decay_w64; a.s64 = scatter_w64; }
@@ -238,16 +268,24 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const int grid = grid_for(n, (int)a.tile_elems, 8);
     const bool inj = uniforms != nullptr;
     const bool fast = fast_mode != 0;
-    // the PAIRED specialisation exists for the production configuration (fast arithmetic, free-running RNG, no histogram)
+    // the PAIRED / output-set specialisations exist for the production configuration (fast arithmetic, free-running RNG,
+    // no histogram)
     const bool paired = (n_samples % 2u) == 0u;
-#define ALPK_CHAIN_LAUNCH(I, S, F, H, P) chain_kernel<Prod, I, S, F, H, P><<<grid, kThreads, smem, st>>>(a)
+    const bool none = !out_energy && !out_flux && !decay_w32 && !scatter_w32 && !decay_w64 && !scatter_w64 && !event_w;
+    const bool standard = out_energy && out_flux && !decay_w64 && !scatter_w64 && (stage < 1 || (decay_w32 && scatter_w32)) &&
+                          (stage < 2 || event_w);
+#define ALPK_CHAIN_LAUNCH(I, S, F, H, P, O) chain_kernel<Prod, I, S, F, H, P, O><<<grid, kThreads, smem, st>>>(a)
 #define ALPK_CHAIN_CASE(S)                                                                                   \
     if (hist) {   /* histogram variants only for the free-running RNG */                                      \
         if (inj) { set_error("%s: fused histogram is not available with injected uniforms", what); return 2; } \
-        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true, false); else ALPK_CHAIN_LAUNCH(false, S, false, true, false);     \
-    } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false, false); else ALPK_CHAIN_LAUNCH(true, S, false, false, false); } \
-    else if (fast) { if (paired) ALPK_CHAIN_LAUNCH(false, S, true, false, true); else ALPK_CHAIN_LAUNCH(false, S, true, false, false); } \
-    else ALPK_CHAIN_LAUNCH(false, S, false, false, false);
+        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true, false, kOutGeneric); else ALPK_CHAIN_LAUNCH(false, S, false, true, false, kOutGeneric); \
+    } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false, false, kOutGeneric); else ALPK_CHAIN_LAUNCH(true, S, false, false, false, kOutGeneric); } \
+    else if (fast && paired) {                                                                                 \
+        if (standard) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutStandard);                            \
+        else if (none) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutNone);                               \
+        else ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutGeneric);                                      \
+    } else if (fast) ALPK_CHAIN_LAUNCH(false, S, true, false, false, kOutGeneric);                             \
+    else ALPK_CHAIN_LAUNCH(false, S, false, false, false, kOutGeneric);
     if (stage == 0) { ALPK_CHAIN_CASE(0) } else if (stage == 1) { ALPK_CHAIN_CASE(1) } else { ALPK_CHAIN_CASE(2) }
 #undef ALPK_CHAIN_LAUNCH
 #undef ALPK_CHAIN_CASE
