@@ -79,9 +79,12 @@ def build(force=False, verbose=False):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     # one nvcc per translation unit, in parallel, then link
-    objdir = os.path.join(_HERE, "build")
+    # (kernel-variant experiments: ALPK_LIB_PATH picks the output, ALPK_NVCC_EXTRA adds -D flags; objects kept apart)
+    objdir = os.path.join(_HERE, "build" if LIB_PATH == os.path.join(_HERE, "libalpk.so") else
+                          "build_" + os.path.basename(LIB_PATH).replace(".", "_"))
     os.makedirs(objdir, exist_ok=True)
-    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) \
+        + os.environ.get("ALPK_NVCC_EXTRA", "").split()
     procs = []
     for src in srcs:
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
