@@ -55,6 +55,17 @@ def _as_flux_table(flux, name):
     return a
 
 
+def _kept_columns(pf, keep):
+    """(row indices, energy column, weight column) of the rows with keep == True, as cheap views where possible:
+    a threshold cut on a sorted spectrum keeps one contiguous block, which is sliced instead of gathered."""
+    idx = np.flatnonzero(keep)
+    n = int(idx.shape[0])
+    if n and int(idx[-1]) - int(idx[0]) + 1 == n:
+        sl = slice(int(idx[0]), int(idx[-1]) + 1)
+        return idx, pf[sl, 0], pf[sl, 1]
+    return idx, np.take(pf[:, 0], idx), np.take(pf[:, 1], idx)
+
+
 def _draw_seed():
     # one draw from the global legacy NumPy RNG, so np.random.seed(s) pins the Philox key like it pins the reference
     return int(np.random.randint(0, 2**63 - 1, dtype=np.int64))
@@ -334,9 +345,11 @@ class FluxPrimakoffIsotropic(AxionFlux):
         """Host-side row filter (fluxes.py:136) + upload of the surviving rows (SoA: energies, weights)."""
         pf = _as_flux_table(self.photon_flux, "photon_flux")
         keep = ~(pf[:, 0] < self.ma)
+        idx, e_k, w_k = _kept_columns(pf, keep)
         rt = self._rt
         with rt.activate():
-            self._inputs = (rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1]), int(np.count_nonzero(keep)))
+            d_e, d_w = rt.upload_packed([(e_k, np.float64), (w_k, np.float64)])
+            self._inputs = (d_e, d_w, int(idx.shape[0]))
         return self._inputs
 
     def _produce(self):
@@ -518,7 +531,8 @@ class FluxComptonIsotropic(_ChainFlux):
         pf = _as_flux_table(self.photon_flux, "photon_flux")
         s = 2 * M_E * pf[:, 0] + M_E ** 2
         keep = ~(s < (M_E + self.ma)**2)
-        row_ids = (np.nonzero(keep)[0] + int(self.row_offset)).astype(np.uint32)
+        idx, e_k, w_k = _kept_columns(pf, keep)
+        row_ids = idx + int(self.row_offset)                     # (cast to uint32 while packing)
         ns = int(self.n_samples)
         n_rows = int(row_ids.shape[0])
         seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
@@ -529,8 +543,8 @@ class FluxComptonIsotropic(_ChainFlux):
                 raise ValueError(f"uniforms must hold n_rows*n_samples = {n_rows * ns} variates, got {uniforms.shape[0]}")
         rt = self._rt
         with rt.activate():
-            self._inputs = (rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1]), n_rows, ns, rt.upload(row_ids, np.uint32),
-                            rt.upload(uniforms) if uniforms is not None else None, seed)
+            d_e, d_w, d_ids = rt.upload_packed([(e_k, np.float64), (w_k, np.float64), (row_ids, np.uint32)])
+            self._inputs = (d_e, d_w, n_rows, ns, d_ids, rt.upload(uniforms) if uniforms is not None else None, seed)
             self._table = rt.empty(n_rows * N.COMPTON_NP)
         return self._inputs
 

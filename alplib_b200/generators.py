@@ -105,7 +105,19 @@ class ElectronEventGenerator(_EventGenerator):
 
     def __init__(self, flux: AxionFlux, detector: Material):
         super().__init__(flux, detector)
-        self.pair_xs = ALPPairProdutionCrossSection(detector, ma=flux.ma)        # generators.py:31
+        self._detector = detector
+        self._pair_xs = None
+
+    @property
+    def pair_xs(self):
+        """ALPPairProdutionCrossSection(detector, ma=flux.ma) (generators.py:31), built when first used."""
+        if self._pair_xs is None:
+            self._pair_xs = ALPPairProdutionCrossSection(self._detector, ma=self.flux.ma)
+        return self._pair_xs
+
+    @pair_xs.setter
+    def pair_xs(self, v):
+        self._pair_xs = v
 
     def pair_production(self, ge, ntargets, days_exposure, threshold):
         """days*S_PER_DAY*(ntargets/area)*ge^2*sigma_pair(E)*METER_BY_MEV^2*scatter_w*heaviside (generators.py:33-39)."""

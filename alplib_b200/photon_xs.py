@@ -14,6 +14,7 @@ _XS_DIM = {"NaI": 149.89 / AVOGADRO, "CsI": 259.81 / AVOGADRO, "CH2": 14.027 / A
 
 
 _TABLE_CACHE = {}
+_CLEAN_CACHE = {}
 _DEVICE_TABLES = {}
 
 
@@ -32,8 +33,14 @@ class AbsCrossSection:
     def __init__(self, material: Material):
         self.xs_dim = _XS_DIM.get(material.mat_name, 1e-24)          # barns -> cm2, or cm2/g -> cm2/molecule
         self.mat_name = material.mat_name
-        self.pe_data = _load_table(data_path("photon_absorption", "photon_abs_" + self.mat_name + ".txt"), 3)
-        self.cleanPEData()
+        path = data_path("photon_absorption", "photon_abs_" + self.mat_name + ".txt")
+        cached = _CLEAN_CACHE.get((path, self.xs_dim))
+        if cached is None:
+            self.pe_data = _load_table(path, 3)
+            self.cleanPEData()
+            _CLEAN_CACHE[(path, self.xs_dim)] = (self.pe_data.copy(), self.log10_e.copy(), self.log10_xs.copy())
+        else:                                    # scans build one flux object per grid point: skip unique/log10
+            self.pe_data, self.log10_e, self.log10_xs = (a.copy() for a in cached)
         # device copies are shared by every instance built from the same table (scans build one flux per point)
         self._dev = _DEVICE_TABLES.setdefault((self.mat_name, self.xs_dim), {})
 

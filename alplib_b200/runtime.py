@@ -10,6 +10,10 @@ import torch
 from . import _native as N
 
 
+_TORCH_DTYPE = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
+                np.dtype(np.uint32): torch.int32, np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
+
+
 class Runtime:
     _instances = {}
 
@@ -59,6 +63,37 @@ class Runtime:
         a = np.ascontiguousarray(host, dtype=dtype)
         t = torch.from_numpy(a)
         return t.to(self.device, non_blocking=True)
+
+    def upload_packed(self, arrays):
+        """Several host arrays -> device tensors with ONE asynchronous H2D copy from pinned memory.
+
+        `arrays`: list of (source ndarray -- may be a strided view --, numpy dtype).  The sources are gathered into a
+        pinned staging slot (ring of slots, each guarded by a CUDA event so a slot is not rewritten while its copy is
+        in flight) and land in one device buffer; the returned tensors are typed views of it."""
+        offs, total = [], 0
+        for a, dt in arrays:
+            offs.append(total)
+            total += (int(a.shape[0]) * np.dtype(dt).itemsize + 255) & ~255
+        if total == 0:
+            return [torch.empty(0, dtype=_TORCH_DTYPE[np.dtype(dt)], device=self.device) for _, dt in arrays]
+        ring = self.__dict__.setdefault("_pin_ring", [None] * 8)
+        k = self.__dict__["_pin_next"] = (self.__dict__.get("_pin_next", -1) + 1) % len(ring)
+        slot = ring[k]
+        if slot is None or slot[0].shape[0] < total:
+            slot = ring[k] = (torch.empty(max(total, 1 << 16), dtype=torch.uint8, pin_memory=True), torch.cuda.Event())
+            slot = ring[k] = (slot[0], slot[1], slot[0].numpy())
+        else:
+            slot[1].synchronize()                       # previous copy out of this slot has completed
+        hbuf, ev, hnp = slot
+        for (a, dt), o in zip(arrays, offs):
+            n = int(a.shape[0])
+            if n:
+                np.copyto(hnp[o:o + n * np.dtype(dt).itemsize].view(dt), a, casting="unsafe")
+        dev = torch.empty(total, dtype=torch.uint8, device=self.device)
+        dev.copy_(hbuf[:total], non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return [dev[o:o + int(a.shape[0]) * np.dtype(dt).itemsize].view(_TORCH_DTYPE[np.dtype(dt)])
+                for (a, dt), o in zip(arrays, offs)]
 
     def activate(self):
         return torch.cuda.device(self.device)
