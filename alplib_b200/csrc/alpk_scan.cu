@@ -116,6 +116,12 @@ scan_kernel(const ScanArgs a) {
     //      sums are bit-identical to walking the whole tile (the skipped terms are exact zeros) ------------------------
     __shared__ int s_warp[kScanThreads / 32];
     __shared__ int s_live;
+    __shared__ double s_tab[64];                 // exp_fast table
+    __shared__ unsigned long long s_tmax_bits;   // max over live samples of 1/p_a (non-finite / NaN -> +inf), as ordered bits
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    if (threadIdx.x == 0) s_tmax_bits = 0ull;
+    __syncthreads();
+    unsigned long long my_tmax = 0ull;
     constexpr int kPer = kScanTile / kScanThreads;                  // consecutive samples per thread
     double rt_[kPer], rb_[kPer], rw_[kPer], rh_[kPer];
     int nkeep = 0;
@@ -153,6 +159,11 @@ scan_kernel(const ScanArgs a) {
             bo = ea / ma;                // boost
         }
         rt_[q] = t; rb_[q] = bo; rw_[q] = w; rh_[q] = h;      // (static register indexing; compacted on the store)
+        {   // t >= 0 or NaN: non-negative doubles order like their bit patterns
+            const unsigned long long tb = (t >= 0.0 && t < INFINITY) ? (unsigned long long)__double_as_longlong(t)
+                                                                     : 0x7ff0000000000000ull;
+            my_tmax = tb > my_tmax ? tb : my_tmax;
+        }
         keepmask |= 1u << q;
         ++nkeep;
     }
@@ -162,6 +173,7 @@ scan_kernel(const ScanArgs a) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) s_warp[wid] = incl;
+    if (my_tmax) atomicMax(&s_tmax_bits, my_tmax);
     __syncthreads();
     int woff = 0;
     for (int q = 0; q < wid; ++q) woff += s_warp[q];
@@ -174,40 +186,60 @@ scan_kernel(const ScanArgs a) {
     __syncthreads();
     const int n_live = s_live;
 
-    // ---- stage 2: one coupling per thread, broadcast walk over the tile ------------------------------------------------
+    // ---- stage 2: one coupling per WARP at a time, the 32 lanes stride over the tile's live samples (conflict-free
+    //      shared-memory reads, every lane busy for any n_g), lane partials combined by a shuffle tree (fixed order) ----
     const ScanGeom& G = a.geo;
-    for (int j = threadIdx.x; j < a.n_g; j += blockDim.x) {
+    const double tmax = __longlong_as_double((long long)s_tmax_bits);      // largest finite 1/p_a of the tile (or +inf)
+    for (int j = wid; j < a.n_g; j += kScanThreads / 32) {
         const double width = __ldg(a.width + (size_t)im * a.n_g + j);
         const double resc = __ldg(a.rescale + j);
         const double k1 = width > 0.0 ? (G.neg_dist_mbm * ma) * width : 0.0;
         const double k2 = width > 0.0 ? (G.neg_len_mbm * ma) * width : 0.0;
+        // same validity rule as propagate_try_fast / prop_derive
+        const double kmax = fmax(fabs(k1), fabs(k2));
+        const double tf = fmin(kmax > 0.0 ? 708.0 / kmax : INFINITY, 1e140);
         double acc = 0.0;
+        if (FAST && G.fast == 1 && !G.ev.days_f64 && tmax <= tf) {
+            // every sample of the tile is inside the branch-free domain: straight-line body, two samples in flight
 #pragma unroll 2
-        for (int k = 0; k < n_live; ++k) {
-            const double w = s_w[k];
-            double surv, dec;
-            if (FAST && G.fast == 2) {               // optional FP32 transcendentals (see propagate_sample_fast)
-                const float tf = (float)s_t[k];
-                surv = (double)expf((float)k1 * tf);
-                dec = (double)(-expm1f((float)k2 * tf));
-            } else if (FAST) {
+            for (int k = lane; k < n_live; k += 32) {
                 const double t = s_t[k];
-                surv = exp_fast(k1 * t);
-                dec = 1 - exp_fast(k2 * t);
-            } else {
-                const double va = s_t[k];
-                const double tau = width > 0.0 ? s_b[k] / width : INFINITY;      // fluxes.py:51
-                surv = exp((G.neg_dist_mbm / va) / tau);                          // :61
-                dec = 1 - exp((G.neg_len_mbm / va) / tau);                        // :62
+                const double surv = exp_fast_core(k1 * t, s_tab);
+                const double dec = 1 - exp_fast_core(k2 * t, s_tab);
+                const double s64 = (resc * s_w[k]) * surv;
+                const double d64 = s64 * dec;                                         // fluxes.py:64
+                const float d32 = (float)d64 * G.geom32;                              // prop_cast_fast (:159-162)
+                acc += (double)(G.ev.days_sec32 * d32) * s_h[k];                      // generators.py:90
             }
-            const double s64 = (resc * w) * surv;
-            const double d64 = s64 * dec;                                         // :64
-            float d32 = (float)d64;
-            if (G.apply_geom) d32 = G.geom_f64 ? (float)((double)d32 * G.geom) : d32 * G.geom32;   // :159-162
-            const double base_w = G.ev.days_f64 ? G.ev.days_sec * (double)d32 : (double)(G.ev.days_sec32 * d32);
-            acc += base_w * s_h[k];                                               // generators.py:90
+        } else {
+            for (int k = lane; k < n_live; k += 32) {
+                const double w = s_w[k];
+                double surv, dec;
+                if (FAST && G.fast == 2) {               // optional FP32 transcendentals (see propagate_sample_fast)
+                    const float tf32 = (float)s_t[k];
+                    surv = (double)expf((float)k1 * tf32);
+                    dec = (double)(-expm1f((float)k2 * tf32));
+                } else if (FAST) {
+                    const double t = s_t[k];
+                    if (t <= tf) { surv = exp_fast_core(k1 * t, s_tab); dec = 1 - exp_fast_core(k2 * t, s_tab); }
+                    else { surv = exp(k1 * t); dec = 1 - exp(k2 * t); }
+                } else {
+                    const double va = s_t[k];
+                    const double tau = width > 0.0 ? s_b[k] / width : INFINITY;      // fluxes.py:51
+                    surv = exp((G.neg_dist_mbm / va) / tau);                          // :61
+                    dec = 1 - exp((G.neg_len_mbm / va) / tau);                        // :62
+                }
+                const double s64 = (resc * w) * surv;
+                const double d64 = s64 * dec;                                         // :64
+                float d32 = (float)d64;
+                if (FAST) d32 = d32 * G.geom32;                                       // prop_cast_fast
+                else if (G.apply_geom) d32 = G.geom_f64 ? (float)((double)d32 * G.geom) : d32 * G.geom32;   // :159-162
+                const double base_w = G.ev.days_f64 ? G.ev.days_sec * (double)d32 : (double)(G.ev.days_sec32 * d32);
+                acc += base_w * s_h[k];                                               // generators.py:90
+            }
         }
-        a.partials[((size_t)im * a.n_tiles + tile) * a.n_g + j] = acc;
+        acc = warp_sum(acc);
+        if (lane == 0) a.partials[((size_t)im * a.n_tiles + tile) * a.n_g + j] = acc;
     }
 }
 
