@@ -205,7 +205,15 @@ ALP_HD double exp_fast_core(double x, const double* tab = nullptr) {          //
 #if defined(__CUDA_ARCH__)
     const int ki = __double2loint(kd);                              // 64 n + j, two's complement
     // `tab`: a copy of the table in shared memory (the chain kernels); default: the global copy through L1
-    const double tv = tab ? tab[ki & 63] : __ldg(&kExpTabDev[ki & 63]);
+    double tv;
+    if (tab) {
+        // shared-memory copy: address = base + 8 (ki & 63) as one LOP3 + one IMAD (the compiler's own sequence is three)
+        unsigned addr;
+        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(ki & 63), "r"((unsigned)__cvta_generic_to_shared(tab)));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(addr));
+    } else {
+        tv = __ldg(&kExpTabDev[ki & 63]);
+    }
     const double S = __hiloint2double(__double2hiint(tv) + (ki << 14), __double2loint(tv));   // 2^n 2^(j/64)
     return fma(S, t, S);
 #else

@@ -101,6 +101,7 @@ scan_kernel(const ScanArgs a) {
     __shared__ double s_b[kScanTile];       //                  faithful: boost = E_a/m_a
     __shared__ double s_w[kScanTile];       // production weight (0 for dead samples)
     __shared__ double s_h[kScanTile];       // heaviside(E_a - threshold, 1)
+    __shared__ double s_wh[kScanTile];      // fast path: weight with the (exact 0/1/NaN) threshold flag folded in
     constexpr int NP = COMPTON ? (int)CB_NP : 2;
     const int im = blockIdx.y;
     const uint32_t tile = blockIdx.x;
@@ -181,7 +182,13 @@ scan_kernel(const ScanArgs a) {
     int pos = woff + incl - nkeep;
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
-        if (keepmask & (1u << q)) { s_t[pos] = rt_[q]; s_b[pos] = rb_[q]; s_w[pos] = rw_[q]; s_h[pos] = rh_[q]; ++pos; }
+        if (keepmask & (1u << q)) {
+            // s_wh: the weight with the threshold flag folded in for the fast loop -- h is exactly 1 for a kept sample
+            // unless the weight is inf/NaN (w*0 = NaN, NaN*h = NaN), which the product reproduces
+            s_t[pos] = rt_[q]; s_b[pos] = rb_[q]; s_w[pos] = rw_[q]; s_h[pos] = rh_[q];
+            s_wh[pos] = rh_[q] == 1.0 ? rw_[q] : rw_[q] * rh_[q];
+            ++pos;
+        }
     }
     __syncthreads();
     const int n_live = s_live;
@@ -206,10 +213,10 @@ scan_kernel(const ScanArgs a) {
                 const double t = s_t[k];
                 const double surv = exp_fast_core(k1 * t, s_tab);
                 const double dec = 1 - exp_fast_core(k2 * t, s_tab);
-                const double s64 = (resc * s_w[k]) * surv;
+                const double s64 = (resc * s_wh[k]) * surv;
                 const double d64 = s64 * dec;                                         // fluxes.py:64
                 const float d32 = (float)d64 * G.geom32;                              // prop_cast_fast (:159-162)
-                acc += (double)(G.ev.days_sec32 * d32) * s_h[k];                      // generators.py:90
+                acc += (double)(G.ev.days_sec32 * d32);                               // generators.py:90 (h folded into s_wh)
             }
         } else {
             for (int k = lane; k < n_live; k += 32) {
