@@ -125,6 +125,8 @@ _SIGNATURES = {
     "alpk_memcpy_h2d": ([_P, _P, _U64, _P], _I),
     "alpk_memcpy_d2h": ([_P, _P, _U64, _P], _I),
     "alpk_sync": ([_P], _I),
+    "alpk_stage_flux_rows": ([_P, _U64, _U32, _I, _D, _U32, _P, _U64, _P, C.POINTER(_U64), C.POINTER(_U64),
+                              C.POINTER(_U64), _P], _I),
     "alpk_propagate": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _P, _P], _I),
     "alpk_decays": ([_P, _P, _U64, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_scatter_events": ([_I, _P, _P, _U64, C.POINTER(_D), _D, _D, C.POINTER(EventT), _P, _P, _P, _P], _I),

@@ -307,6 +307,47 @@ ALPK_EXPORT int alpk_memcpy_d2h(void* h_dst, const void* d_src, uint64_t bytes, 
     return 0;
 }
 
+// Host-side staging of a flux table for the production kernels (fluxes.py:136 / :214-216 row filter + SoA split):
+// one pass over the caller's row-major [n_rows][row_stride] table gathers the kept rows' energies, weights and global
+// row ids into the pinned staging buffer, then ONE asynchronous H2D copy moves the block.
+ALPK_EXPORT int alpk_stage_flux_rows(const double* h_table, uint64_t n_rows, uint32_t row_stride, int rule, double cut,
+                                     uint32_t row_offset, void* h_pinned, uint64_t pinned_bytes, void* d_dst,
+                                     uint64_t* h_n_kept, uint64_t* h_off_weight, uint64_t* h_off_ids, void* stream) {
+    if (!h_n_kept || !h_off_weight || !h_off_ids) { set_error("alpk_stage_flux_rows: null output"); return 2; }
+    *h_n_kept = 0; *h_off_weight = 0; *h_off_ids = 0;
+    if (n_rows == 0) return 0;
+    if (!h_table || !h_pinned || !d_dst || row_stride < 2) { set_error("alpk_stage_flux_rows: null argument"); return 2; }
+    if (rule != 0 && rule != 1) { set_error("alpk_stage_flux_rows: rule must be 0 (E >= m_a) or 1 (Compton threshold)"); return 2; }
+    const uint64_t cap = (n_rows * 8 + 255) & ~255ull;                    // per-array capacity in the staging block
+    if (pinned_bytes < 2 * cap + n_rows * 4) { set_error("alpk_stage_flux_rows: staging buffer too small"); return 2; }
+    double* e = (double*)h_pinned;
+    double* w = (double*)((char*)h_pinned + cap);
+    uint32_t* ids = (uint32_t*)((char*)h_pinned + 2 * cap);
+    const double me = alp::kME, me2 = alp::kME * alp::kME;
+    uint64_t k = 0;
+    for (uint64_t r = 0; r < n_rows; ++r) {
+        const double en = h_table[r * row_stride];
+        bool drop;
+        if (rule == 0) drop = en < cut;                                   // fluxes.py:136   if photon[0] < self.ma: return
+        else drop = ((2 * me) * en + me2) < cut;                          // :214-215  s < (M_E + ma)**2
+        if (drop) continue;
+        e[k] = en; w[k] = h_table[r * row_stride + 1]; ids[k] = (uint32_t)r + row_offset;
+        ++k;
+    }
+    *h_n_kept = k;
+    if (k == 0) return 0;
+    // compact layout on both sides: [E: k][pad][w: k][pad][ids: k], arrays 256-byte aligned
+    const uint64_t seg = (k * 8 + 255) & ~255ull;
+    if (seg != cap) {
+        memmove((char*)h_pinned + seg, w, k * 8);
+        memmove((char*)h_pinned + 2 * seg, ids, k * 4);
+    }
+    *h_off_weight = seg; *h_off_ids = 2 * seg;
+    cudaError_t err = cudaMemcpyAsync(d_dst, h_pinned, 2 * seg + k * 4, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (err != cudaSuccess) { set_error("alpk_stage_flux_rows: %s", cudaGetErrorString(err)); return 1; }
+    return 0;
+}
+
 ALPK_EXPORT int alpk_sync(void* stream) {
     cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) { set_error("alpk_sync: %s", cudaGetErrorString(e)); return 1; }

@@ -344,12 +344,16 @@ class FluxPrimakoffIsotropic(AxionFlux):
     def _stage_inputs(self):
         """Host-side row filter (fluxes.py:136) + upload of the surviving rows (SoA: energies, weights)."""
         pf = _as_flux_table(self.photon_flux, "photon_flux")
-        keep = ~(pf[:, 0] < self.ma)
-        idx, e_k, w_k = _kept_columns(pf, keep)
         rt = self._rt
         with rt.activate():
-            d_e, d_w = rt.upload_packed([(e_k, np.float64), (w_k, np.float64)])
-            self._inputs = (d_e, d_w, int(idx.shape[0]))
+            if pf.flags.c_contiguous:
+                d_e, d_w, _, n = rt.stage_flux_rows(pf, 0, float(self.ma))
+            else:
+                keep = ~(pf[:, 0] < self.ma)
+                idx, e_k, w_k = _kept_columns(pf, keep)
+                d_e, d_w = rt.upload_packed([(e_k, np.float64), (w_k, np.float64)])
+                n = int(idx.shape[0])
+            self._inputs = (d_e, d_w, n)
         return self._inputs
 
     def _produce(self):
@@ -529,21 +533,24 @@ class FluxComptonIsotropic(_ChainFlux):
         """Host-side row filter (fluxes.py:214-216) + upload of the surviving rows, their global row ids (Philox
         key) and, in parity mode, the injected uniforms."""
         pf = _as_flux_table(self.photon_flux, "photon_flux")
-        s = 2 * M_E * pf[:, 0] + M_E ** 2
-        keep = ~(s < (M_E + self.ma)**2)
-        idx, e_k, w_k = _kept_columns(pf, keep)
-        row_ids = idx + int(self.row_offset)                     # (cast to uint32 while packing)
         ns = int(self.n_samples)
-        n_rows = int(row_ids.shape[0])
         seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
         self._seed_used = seed
-        if uniforms is not None:
-            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
-            if uniforms.shape[0] != n_rows * ns:
-                raise ValueError(f"uniforms must hold n_rows*n_samples = {n_rows * ns} variates, got {uniforms.shape[0]}")
         rt = self._rt
         with rt.activate():
-            d_e, d_w, d_ids = rt.upload_packed([(e_k, np.float64), (w_k, np.float64), (row_ids, np.uint32)])
+            if pf.flags.c_contiguous:
+                d_e, d_w, d_ids, n_rows = rt.stage_flux_rows(pf, 1, float((M_E + self.ma)**2), int(self.row_offset))
+            else:
+                s = 2 * M_E * pf[:, 0] + M_E ** 2
+                keep = ~(s < (M_E + self.ma)**2)
+                idx, e_k, w_k = _kept_columns(pf, keep)
+                n_rows = int(idx.shape[0])
+                d_e, d_w, d_ids = rt.upload_packed([(e_k, np.float64), (w_k, np.float64),
+                                                    (idx + int(self.row_offset), np.uint32)])
+            if uniforms is not None:
+                uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).ravel()
+                if uniforms.shape[0] != n_rows * ns:
+                    raise ValueError(f"uniforms must hold n_rows*n_samples = {n_rows * ns} variates, got {uniforms.shape[0]}")
             self._inputs = (d_e, d_w, n_rows, ns, d_ids, rt.upload(uniforms) if uniforms is not None else None, seed)
             self._table = rt.empty(n_rows * N.COMPTON_NP)
         return self._inputs

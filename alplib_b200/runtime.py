@@ -2,6 +2,7 @@
 
 PyTorch is used for plumbing only (device memory, streams, torch.distributed); every kernel is in libalpk.so.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -10,6 +11,7 @@ import torch
 from . import _native as N
 
 
+_NULL_CTX = contextlib.nullcontext()
 _TORCH_DTYPE = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32,
                 np.dtype(np.uint32): torch.int32, np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
 
@@ -76,14 +78,7 @@ class Runtime:
             total += (int(a.shape[0]) * np.dtype(dt).itemsize + 255) & ~255
         if total == 0:
             return [torch.empty(0, dtype=_TORCH_DTYPE[np.dtype(dt)], device=self.device) for _, dt in arrays]
-        ring = self.__dict__.setdefault("_pin_ring", [None] * 8)
-        k = self.__dict__["_pin_next"] = (self.__dict__.get("_pin_next", -1) + 1) % len(ring)
-        slot = ring[k]
-        if slot is None or slot[0].shape[0] < total:
-            slot = ring[k] = (torch.empty(max(total, 1 << 16), dtype=torch.uint8, pin_memory=True), torch.cuda.Event())
-            slot = ring[k] = (slot[0], slot[1], slot[0].numpy())
-        else:
-            slot[1].synchronize()                       # previous copy out of this slot has completed
+        slot = self._pin_slot(total)
         hbuf, ev, hnp = slot
         for (a, dt), o in zip(arrays, offs):
             n = int(a.shape[0])
@@ -95,5 +90,36 @@ class Runtime:
         return [dev[o:o + int(a.shape[0]) * np.dtype(dt).itemsize].view(_TORCH_DTYPE[np.dtype(dt)])
                 for (a, dt), o in zip(arrays, offs)]
 
+    def _pin_slot(self, nbytes):
+        """Next pinned staging slot of the ring (>= nbytes), safe to overwrite: (tensor, event, numpy view)."""
+        ring = self.__dict__.setdefault("_pin_ring", [None] * 8)
+        k = self.__dict__["_pin_next"] = (self.__dict__.get("_pin_next", -1) + 1) % len(ring)
+        slot = ring[k]
+        if slot is None or slot[0].shape[0] < nbytes:
+            buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, pin_memory=True)
+            slot = ring[k] = (buf, torch.cuda.Event(), buf.numpy())
+        else:
+            slot[1].synchronize()                       # previous copy out of this slot has completed
+        return slot
+
+    def stage_flux_rows(self, table, rule, cut, row_offset=0):
+        """Row filter + SoA split + one pinned H2D copy of a (n, >=2) float64 flux table, done by libalpk
+        (alpk_stage_flux_rows).  Returns (energies, weights, row ids [int32 view of uint32], n_kept) on the device."""
+        n, stride = int(table.shape[0]), int(table.shape[1])
+        cap = ((n * 8 + 255) & ~255) * 2 + n * 4
+        hbuf, ev, _ = self._pin_slot(cap)
+        dev = torch.empty(max(cap, 1), dtype=torch.uint8, device=self.device)
+        nk, ow, oi = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        N.call("alpk_stage_flux_rows", C.c_void_p(table.ctypes.data), n, stride, int(rule), float(cut), int(row_offset),
+               C.c_void_p(hbuf.data_ptr()), int(hbuf.shape[0]), C.c_void_p(dev.data_ptr()), C.byref(nk), C.byref(ow),
+               C.byref(oi), self.stream())
+        ev.record(torch.cuda.current_stream(self.device))
+        k, ow, oi = int(nk.value), int(ow.value), int(oi.value)
+        return (dev[0:k * 8].view(torch.float64), dev[ow:ow + k * 8].view(torch.float64),
+                dev[oi:oi + k * 4].view(torch.int32), k)
+
     def activate(self):
+        """Context manager making this runtime's device current (a no-op object when it already is)."""
+        if torch.cuda.current_device() == self.index:
+            return _NULL_CTX
         return torch.cuda.device(self.device)

@@ -53,6 +53,16 @@ int alpk_memcpy_h2d(void* d_dst, const void* h_src, uint64_t bytes, void* stream
 int alpk_memcpy_d2h(void* h_dst, const void* d_src, uint64_t bytes, void* stream);
 int alpk_sync(void* stream);
 
+/* ---- host-side staging of a flux table (fluxes.py:136 and :214-216: the per-row `return` of simulate_single) -------
+ * h_table: row-major [n_rows][row_stride] doubles (energy, weight, ...).  rule 0 keeps rows with !(E < cut) (Primakoff,
+ * cut = m_a); rule 1 keeps rows with !(2 M_E E + M_E^2 < cut) (Compton, cut = (M_E + m_a)^2).  The kept rows' energies,
+ * weights and global row ids (row + row_offset, uint32) are gathered into the pinned block h_pinned (>= 2*align256(8 n_rows)
+ * + 4 n_rows bytes) and copied with one cudaMemcpyAsync to d_dst (same capacity): energies at byte 0, weights at
+ * *h_off_weight, ids at *h_off_ids.  The caller must not rewrite h_pinned before the copy has completed. */
+int alpk_stage_flux_rows(const double* h_table, uint64_t n_rows, uint32_t row_stride, int rule, double cut,
+                         uint32_t row_offset, void* h_pinned, uint64_t pinned_bytes, void* d_dst,
+                         uint64_t* h_n_kept, uint64_t* h_off_weight, uint64_t* h_off_ids, void* stream);
+
 /* ---- propagate: fluxes.py:43-65 (AxionFlux.propagate) + fluxes.py:159-162 (isotropic acceptance) ------------ */
 typedef struct {
     double ma, ma2;          /* axion mass, ma**2 */
