@@ -79,6 +79,43 @@ propagate_kernel(const double* __restrict__ energy, const double* __restrict__ w
     }
 }
 
+// Fast mode, pair-vectorised: each thread takes two adjacent samples (16-byte loads, 8-byte float stores), the exp table
+// sits in shared memory and the arithmetic of both samples is straight-line (see chain_pair); rare samples outside the
+// branch-free domain are redone through propagate_sample_fast.  Needs 16-byte aligned arrays (the launcher checks).
+__global__ void __launch_bounds__(kThreads)
+propagate_pairs_kernel(const double* __restrict__ energy, const double* __restrict__ weight, uint64_t n, PropConst c,
+                       float* __restrict__ d32, float* __restrict__ s32, double* __restrict__ d64o, double* __restrict__ s64o) {
+    __shared__ double s_tab[64];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    __syncthreads();
+    const uint64_t n_pairs = n >> 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+        const double2 e = __ldg(reinterpret_cast<const double2*>(energy) + p);
+        const double2 w = __ldg(reinterpret_cast<const double2*>(weight) + p);
+        double d0, s0, d1, s1;
+        bool ok = propagate_try_fast(e.x, w.x, c, d0, s0, s_tab);
+        ok &= propagate_try_fast(e.y, w.y, c, d1, s1, s_tab);
+        if (!ok) {
+            propagate_sample_fast(e.x, w.x, c, d0, s0);
+            propagate_sample_fast(e.y, w.y, c, d1, s1);
+        }
+        reinterpret_cast<float2*>(d32)[p] = make_float2(prop_cast_fast(d0, c), prop_cast_fast(d1, c));
+        reinterpret_cast<float2*>(s32)[p] = make_float2(prop_cast_fast(s0, c), prop_cast_fast(s1, c));
+        if (d64o) reinterpret_cast<double2*>(d64o)[p] = make_double2(d0, d1);
+        if (s64o) reinterpret_cast<double2*>(s64o)[p] = make_double2(s0, s1);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {          // odd tail
+        const uint64_t i = n - 1;
+        double d64, s64;
+        propagate_sample_fast(__ldg(energy + i), __ldg(weight + i), c, d64, s64);
+        d32[i] = prop_cast_fast(d64, c);
+        s32[i] = prop_cast_fast(s64, c);
+        if (d64o) d64o[i] = d64;
+        if (s64o) s64o[i] = s64;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // decays / scatter event weights + rate  (generators.py:41-46, 80-92)
 // ---------------------------------------------------------------------------------------------------------------
@@ -360,7 +397,12 @@ ALPK_EXPORT int alpk_propagate(const double* energy, const double* weight, uint6
     if (n == 0) return 0;
     if (!energy || !weight) { set_error("alpk_propagate: null input"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
-    if (h_prop->fast)
+    const uintptr_t align = (uintptr_t)energy | (uintptr_t)weight | (uintptr_t)decay_w32 | (uintptr_t)scatter_w32 |
+                            (uintptr_t)d64 | (uintptr_t)s64;
+    if (h_prop->fast && (align & 15) == 0)
+        propagate_pairs_kernel<<<grid_for(n, kThreads * 2 * 4, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop),
+                                                                                     decay_w32, scatter_w32, d64, s64);
+    else if (h_prop->fast)
         propagate_kernel<true><<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop), decay_w32,
                                                                              scatter_w32, d64, s64);
     else

@@ -42,7 +42,8 @@ struct ChainArgs {
 enum ChainOut : int {
     kOutGeneric = 0,      // any subset (null pointer = not written)
     kOutStandard = 1,     // exactly the reference's attributes of the stage: E_a, flux [, f32 decay/scatter weights [, event weights]]
-    kOutNone = 2          // nothing (rate / histogram only)
+    kOutNone = 2,         // nothing (rate / histogram only)
+    kOutNoEvents = 3      // STAGE 2: E_a, flux, f32 decay/scatter weights but no per-sample event weights (decays() rate only)
 };
 
 // One pair of adjacent samples (i0 = base + local, i0 even relative to the tile).
@@ -140,7 +141,8 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
         }
     }
     if (OUT == kOutNone) return;
-    constexpr bool kAll = OUT == kOutStandard;          // pointers known non-null (d64 / s64 known null)
+    constexpr bool kAll = OUT == kOutStandard || OUT == kOutNoEvents;   // pointers known non-null (d64 / s64 known null)
+    constexpr bool kEvw = OUT == kOutStandard;                            // event_w known non-null
     if (have2) {
         if (kAll || a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
         if (kAll || a.out_f) *reinterpret_cast<double2*>(a.out_f + i0) = make_double2(f[0], f[1]);
@@ -150,7 +152,7 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
             if (!kAll && a.d64) *reinterpret_cast<double2*>(a.d64 + i0) = make_double2(d64v[0], d64v[1]);
             if (!kAll && a.s64) *reinterpret_cast<double2*>(a.s64 + i0) = make_double2(s64v[0], s64v[1]);
         }
-        if (STAGE >= 2 && (kAll || a.event_w)) *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
+        if (STAGE >= 2 && (kEvw || (OUT == kOutGeneric && a.event_w))) *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
     } else {
         if (kAll || a.out_e) a.out_e[i0] = e[0];
         if (kAll || a.out_f) a.out_f[i0] = f[0];
@@ -160,7 +162,7 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
             if (!kAll && a.d64) a.d64[i0] = d64v[0];
             if (!kAll && a.s64) a.s64[i0] = s64v[0];
         }
-        if (STAGE >= 2 && (kAll || a.event_w)) a.event_w[i0] = evv[0];
+        if (STAGE >= 2 && (kEvw || (OUT == kOutGeneric && a.event_w))) a.event_w[i0] = evv[0];
     }
 }
 
@@ -274,6 +276,7 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const bool none = !out_energy && !out_flux && !decay_w32 && !scatter_w32 && !decay_w64 && !scatter_w64 && !event_w;
     const bool standard = out_energy && out_flux && !decay_w64 && !scatter_w64 && (stage < 1 || (decay_w32 && scatter_w32)) &&
                           (stage < 2 || event_w);
+    const bool noevents = stage == 2 && out_energy && out_flux && decay_w32 && scatter_w32 && !decay_w64 && !scatter_w64 && !event_w;
 #define ALPK_CHAIN_LAUNCH(I, S, F, H, P, O) chain_kernel<Prod, I, S, F, H, P, O><<<grid, kThreads, smem, st>>>(a)
 #define ALPK_CHAIN_CASE(S)                                                                                   \
     if (hist) {   /* histogram variants only for the free-running RNG */                                      \
@@ -282,6 +285,7 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false, false, kOutGeneric); else ALPK_CHAIN_LAUNCH(true, S, false, false, false, kOutGeneric); } \
     else if (fast && paired) {                                                                                 \
         if (standard) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutStandard);                            \
+        else if (S == 2 && noevents) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutNoEvents);             \
         else if (none) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutNone);                               \
         else ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutGeneric);                                      \
     } else if (fast) ALPK_CHAIN_LAUNCH(false, S, true, false, false, kOutGeneric);                             \

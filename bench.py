@@ -376,7 +376,8 @@ def run_gpu(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("compton_chain_bytes_per_launch")
         except Exception:
             pass
-        roofline = {"kernel": "alpk::compton_samples_kernel<false,2> (production+propagate+decays, materialising)",
+        roofline = {"kernel": "alpk::chain_kernel<ComptonProd, INJECT=0, STAGE=2, FAST=1, HIST=0, PAIRED=1, OUT=standard> "
+                              "(production+propagate+decays, materialising; launched by alpk_compton_samples)",
                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": n_compton * BYTES_PER_SAMPLE,
@@ -384,8 +385,10 @@ def run_gpu(args):
                     "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
                              "flops_per_sample": FLOPS_PER_SAMPLE,
                              "peak_source": "DFMA loop measured in this run (alpk_fp64_peak)",
-                             "note": "the kernel is FP64-issue bound, not HBM bound; flops use SURVEY section 8d's "
-                                     "expanded accounting (div 8, sqrt 10, exp 25)"}}
+                             "note": "the kernel is instruction-issue bound (an FP64 instruction holds the issue port "
+                                     "for two cycles), not HBM bound; flops use SURVEY section 8d's expanded accounting "
+                                     "(div 8, sqrt 10, exp 25), the kernel itself executes ~62 FP64 + ~98 other "
+                                     "instructions per sample (profiles/ncu_r1_hot_kernels.txt)"}}
         # ---- CPU baseline beside it (bounded sample, 1 core) -------------------------------------------------------------
         ns_cpu = 1000
         try:
