@@ -10,7 +10,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ALPK_LIB_PATH") or os.path.join(_HERE, "libalpk.so")   # override: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_scan.cu", "alpk_misc.cu"]
+SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_scan.cu", "alpk_misc.cu", "alpk_meson.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
@@ -62,6 +62,15 @@ class PairGammaT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("ma4", C.c_double), ("me2", C.c_double), ("me4", C.c_double),
                 ("ep_min", C.c_double), ("nt", C.c_double), ("zc", C.c_double), ("n_samples", C.c_double),
                 ("max_t", C.c_double)]
+
+
+class Meson3T(C.Structure):
+    _fields_ = [("mm", C.c_double), ("ma", C.c_double), ("fM", C.c_double), ("ckm", C.c_double),
+                ("total_width", C.c_double), ("c0", C.c_double), ("coupling", C.c_double), ("a", C.c_double),
+                ("b", C.c_double), ("d", C.c_double), ("pref", C.c_double), ("n_samples", C.c_double), ("model", C.c_int)]
+
+
+MESON3_NP = 13
 
 
 def sources():
@@ -154,6 +163,11 @@ _SIGNATURES = {
     "alpk_vol_int": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _U32, _D, _D, _P, _P, _P, _P, _P, _P], _I),
     "alpk_nuclear": ([_P, _U64, _D, _D, _D, _D, _D, _P, _P, _P], _I),
     "alpk_pi0_flux": ([_P, _U64, _P, _U64, _D, _D, _D, _D, _D, _D, _D, _P, _P, _P, _P], _I),
+    "alpk_meson3_rows": ([_I, _P, _U64, _P, _P, _U64, C.POINTER(Meson3T), _D, _D, _P, _U64, _U32, _P, _P], _I),
+    "alpk_meson3_samples": ([_I, _P, _U64, _U32, C.POINTER(Meson3T), _D, _I, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _P,
+                             _P, _P], _I),
+    "alpk_meson3_dgamma": ([_P, _U64, _D, C.POINTER(Meson3T), _P, _P], _I),
+    "alpk_meson3_m2": ([_D, _P, _U64, _D, C.POINTER(Meson3T), _P, _P], _I),
     "alpk_pairgamma": ([_P, _P, _U64, _U32, _P, _P, _P, _I, C.POINTER(PairGammaT), _P, _P, _U64, _P, _P, _P], _I),
     "alpk_scale": ([_P, _U64, _D, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),

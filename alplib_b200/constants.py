@@ -21,6 +21,17 @@ M_P = 938.0                            # constants.py:33
 M_MU = 105.658369                      # constants.py:34
 M_PI = 139.57                          # constants.py:41
 M_PI0 = 134.98                         # constants.py:42
+M_K = 493.677                          # constants.py:53  charged kaon
+G_F = 1.16638e-11                      # constants.py:73  MeV^-2
+CABIBBO = 0.9743                       # constants.py:74
+V_UD = 0.97373                         # constants.py:78
+V_US = 0.2243                          # constants.py:79
+F_PI = 130.2                           # constants.py:91  pion decay constant
+F_K = 155.7                            # constants.py:92  kaon decay constant
+KAON_LIFETIME = 1.238e-8               # constants.py:105  s
+PION_LIFETIME = 2.6e-8                 # constants.py:108  s
+PION_WIDTH = 2.524e-14                 # constants.py:112  MeV
+KAON_WIDTH = 5.317e-14                 # constants.py:114  MeV
 METER_BY_MEV = 6.58212e-22 * 2.998e8   # constants.py:60  MeV m
 MEV_PER_KG = 5.6095887e29              # constants.py:61
 MEV2_CM2 = (METER_BY_MEV * 100) ** 2   # constants.py:65

@@ -322,6 +322,43 @@ int alpk_fp64_peak(uint64_t iters, int blocks, double* out, void* stream);
 /* sum of a f64 array (deterministic two-stage) */
 int alpk_sum(const double* x, uint64_t n, double* out, double* scratch, void* stream);
 
+/* ---- charged-meson 3-body decay fluxes M -> l nu X: FluxChargedMeson3BodyIsotropic (fluxes.py:811-922) and
+ * FluxChargedMeson3BodyDecay (fluxes.py:605-808), with M2Meson3BodyDecay (matrix_element.py:419-518) integrated over the
+ * Dalitz variable m_23^2 by the 21-point Gauss-Kronrod rule QUADPACK applies for scipy.integrate.quad (fluxes.py:639-661).
+ * model: 0 scalar_ib1, 1 pseudoscalar_ib1, 2 vector_ib1, 3 scalar_ib2, 4 vector_ib2, 5 vector_ib9, 6 sd,
+ * 7 vector_contact, 8 any other string (zero matrix element). */
+typedef struct {
+    double mm, ma;            /* meson mass, boson mass */
+    double fM, ckm;           /* decay constant, CKM element */
+    double total_width;       /* meson total width [MeV] */
+    double c0;                /* contact-model parameter */
+    double coupling;
+    double a, b, d;           /* vector_ib9 free parameters (abd) */
+    double pref;              /* (2*mm)/(32*power(2*pi*mm, 3)) */
+    double n_samples;         /* n_samples as a double (divisor) */
+    int model;
+} alpk_meson3_t;
+#define ALPK_MESON3_NP 13
+/* rows: one per (meson, allowed lepton) -- row_meson[r] indexes `mesons`, row_ml[r] is the lepton mass.  mode 0:
+ * mesons[n][2] = {p, weight}; mode 1: mesons[n][3] = {p, theta, weight} and one exponential decay position per meson
+ * (u_pos[n_mesons] in parity mode, else Philox keyed by meson index + meson_offset).  row_table: [n_rows][ALPK_MESON3_NP];
+ * entry 12 is the row's live flag (decay position <= 52 m, fluxes.py:671). */
+int alpk_meson3_rows(int mode, const double* mesons, uint64_t n_mesons, const uint32_t* row_meson, const double* row_ml,
+                     uint64_t n_rows, const alpk_meson3_t* h_par, double det_dist, double det_length, const double* u_pos,
+                     uint64_t seed, uint32_t meson_offset, double* row_table, void* stream);
+/* samples: n_samples per row.  Parity mode: uniforms[block][2 or 3][n_samples] (energies, cosines[, azimuths]) with
+ * block_of_row[r] the block of live row r.  mode 0 writes out_energy / out_flux (the rest may be NULL); mode 1 writes all
+ * arrays and keep[i] = 1 for samples of live rows that pass the solid-angle acceptance (or all, if the cut is off). */
+int alpk_meson3_samples(int mode, const double* row_table, uint64_t n_rows, uint32_t n_samples, const alpk_meson3_t* h_par,
+                        double energy_cut, int cut_on_solid_angle, const double* uniforms, const int32_t* block_of_row,
+                        uint64_t seed, uint32_t row_offset, double* out_energy, double* out_flux, double* out_cos,
+                        double* out_theta, double* out_solid_angle, double* out_decay_pos, uint8_t* keep, void* stream);
+/* dGammadEa(E_a, ml) (fluxes.py:639-661 / 841-863) on an array of energies */
+int alpk_meson3_dgamma(const double* ea, uint64_t n, double lepton_mass, const alpk_meson3_t* h_par, double* out, void* stream);
+/* M2Meson3BodyDecay.__call__(m122, m232) (matrix_element.py:443-518) on an array of m232 */
+int alpk_meson3_m2(double m122, const double* m232, uint64_t n, double lepton_mass, const alpk_meson3_t* h_par, double* out,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

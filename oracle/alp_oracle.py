@@ -807,3 +807,192 @@ def histogram(x, w, edges):
     idx[x == edges[-1]] = nb - 1
     ok = (x >= edges[0]) & (x <= edges[-1])
     return np.bincount(idx[ok], weights=w[ok], minlength=nb)[:nb]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Charged-meson 3-body decay fluxes  M -> l nu X  (fluxes.py:605-922, matrix_element.py:50-68, 419-518)
+# ---------------------------------------------------------------------------------------------------------
+M_MU = 105.658369                     # constants.py:34
+M_PI = 139.57                         # constants.py:41
+M_K = 493.677                         # constants.py:53
+G_F = 1.16638e-11                     # constants.py:73
+CABIBBO = 0.9743                      # constants.py:74
+V_UD = 0.97373                        # constants.py:78
+V_US = 0.2243                         # constants.py:79
+F_PI = 130.2                          # constants.py:91
+F_K = 155.7                           # constants.py:92
+PION_LIFETIME = 2.6e-8                # constants.py:108
+PION_WIDTH = 2.524e-14                # constants.py:112
+KAON_WIDTH = 5.317e-14                # constants.py:114
+MESON_PARAMS = {"pion": (M_PI, V_UD, F_PI, PION_WIDTH), "kaon": (M_K, V_US, F_K, KAON_WIDTH)}   # fluxes.py:612-615
+
+
+def W_ff(g, mf, ma):                                                                 # decay.py:18-21
+    return g ** 2 * ma * np.sqrt(1 - (2 * mf / ma) ** 2) / (8 * pi) if 1 - 4 * (mf / ma) ** 2 > 0 else 0.0
+
+
+def heaviside(x, h0):
+    return np.heaviside(x, h0)
+
+
+def m3_scalar_products(M, m1, m2, m3, m122, m232):                                   # matrix_element.py:60-68
+    sp03 = (M ** 2 + m3 ** 2 - m122) / 2
+    sp01 = (M ** 2 + m1 ** 2 - m232) / 2
+    sp02 = (m122 + m232 - m1 ** 2 - m3 ** 2) / 2
+    sp13 = (M ** 2 + m2 ** 2 - m122 - m232) / 2
+    sp23 = (m232 - m2 ** 2 - m3 ** 2) / 2
+    sp12 = (m122 - m1 ** 2 - m2 ** 2) / 2
+    return sp01, sp02, sp03, sp12, sp13, sp23
+
+
+def m2_meson3body(m122, m232, model, M, m1, m3, fM, ckm, c0=0.0, coupling=1.0, abd=(0, 0, 0)):
+    """M2Meson3BodyDecay.__call__ (matrix_element.py:443-518); m2 (neutrino) = 0."""
+    power, sqrt = np.power, np.sqrt
+    lp, pq, kp, lq, kl, kq = m3_scalar_products(M, m1, 0.0, m3, m122, m232)
+    if model in ("scalar_ib1", "pseudoscalar_ib1"):                                  # :445-464
+        e3star = (M ** 2 - m122 - m3 ** 2) / (2 * sqrt(m122))
+        ev = (m122 + m232 - m1 ** 2 - m3 ** 2) / (2 * M)
+        emu = (M ** 2 - m232 + m1 ** 2) / (2 * M)
+        q2 = M ** 2 - 2 * M * ev
+        prefactor = heaviside(e3star - m3, 0.0) * (coupling * G_F * fM * ckm / (q2 - m1 ** 2)) ** 2
+        head = (2 * M * emu * q2 * (q2 - m1 ** 2) - (q2 ** 2 - (m1 * M) ** 2) * (q2 + m1 ** 2 - m3 ** 2))
+        tail = (2 * q2 * m1 ** 2 * (M ** 2 - q2))
+        return prefactor * (head + tail) if model == "scalar_ib1" else prefactor * (head - tail)
+    if model == "vector_ib1":                                                        # :465-472
+        q2 = M ** 2 - 2 * M * (m122 + m232 - m1 ** 2 - m3 ** 2) / (2 * M)
+        prefactor = 8 * power(G_F * fM * ckm / (q2 - m1 ** 2) / m3, 2)
+        kl, kq, kp, lq, lp, pq = m3_scalar_products(M, m1, 0.0, m3, m122, m232)
+        cr = cl = coupling
+        return -prefactor * ((power(cr * M * m1, 2) - power(cl * q2, 2)) * (lq * m3 ** 2 + 2 * lp * pq)
+                             - 2 * cr * m1 ** 2 * kq * (cr * m3 ** 2 * kl + 2 * cr * kp * lp - 3 * cl * q2 * m3 ** 2))
+    if model == "scalar_ib2":                                                        # :473-474
+        return 0.0 * m232
+    if model == "vector_ib2":                                                        # :475-478
+        prefactor = 2 * power(coupling * G_F * fM * m1, 2)
+        return -prefactor * ((m1 ** 2 - m122) * ((M ** 2 - m122 + m3 ** 2) ** 2 - 4 * M ** 2 * m3 ** 2)) \
+            / (m3 ** 2 * (M ** 2 - m122) ** 2) + 0.0 * m232
+    if model == "vector_ib9":                                                        # :479-482, 500-518
+        a, b, d = abd
+        mV, ml, F, g = m3, m1, 1, coupling
+        res = 1/2 * mV**-2 * (b**2 * (M**2 + -1 * m122 + -1 * m232)**3 * (m232 + -1 * mV**2) + 2 * b * d * ml**2 * (m232 + -1 * mV**2)**3 + 4 * b * (a
+            * m122 + (a + 2 * d * m122) * ml**2) * mV**2 * (-1 * m232 + mV**2) + -4 * (m122 + -1 * ml**2) * mV**2 * (-1 * a**2 + 2 * a * d * ml**2
+            + d**2 * m122 * ml**2 + (-1 * b**2 * m122 + F**2 * (m122 + ml**2)) * mV**2)
+            + (m232 + -1 * mV**2)**2 * (4 * a * d * ml**2 + d**2 * ml**2 * (m122 + -1 * ml**2) + (b**2 * (-1 * m122 + ml**2)
+            + 2 * F**2 * (m122 + ml**2)) * mV**2) + 2 * (-1 * M**2 + m122 + m232)**2 * (b * (2 * a + d * ml**2)
+            * (m232 + -1 * mV**2) + b**2 * (m232 + -1 * mV**2)**2 + 1 / 2 * (m122 + -1 * ml**2) * (d**2 * ml**2 + -1 *
+            (b**2 + -2 * F**2) * mV**2)) + (M**2 + -1 * m122 + -1 * m232) * (4 * a * b * (-1 * m122 + ml**2) * mV**2
+            + 4 * b * (a + d * ml**2) * (m232 + -1 * mV**2)**2 + b**2 * (m232 + -1 * mV**2)**3 + 2 * (m232 + -1
+            * mV**2) * (2 * a**2 + 2 * a * d * ml**2 + d**2 * ml**2 * (m122 + -1 * ml**2) + b**2 * (-3 * m122 + ml**2) * mV**2)))
+        return g**2 * res * G_F**2 * fM**2
+    if model == "sd":                                                                # :483-490
+        prefactor = 8 * power(coupling * G_F * CABIBBO / sqrt(2) / M, 2)
+        fv = 0.0265
+        fa = 0.58 * fv
+        return prefactor * (2 * kl * (power(fa - fv, 2) * kp * pq - M ** 2 * (fa ** 2 + fv ** 2) * kq)
+                            + m3 ** 2 * (power(fa * M, 2) * lq - 2 * fv ** 2 * lp * pq)
+                            + 2 * power(fa + fv, 2) * kp * kq * lp)
+    if model == "vector_contact":                                                    # :491-496
+        denom = power((c0 + 1) * m3 * (m3 ** 2 - kp), 2)
+        numerator1 = 8 * m3 ** 2 * (2 * c0 * (kq * lp) * (kp - m3 ** 2)
+                                    - lq * ((1 - c0 ** 2) * kp ** 2 - 2 * m3 ** 2 * kp + power(c0 * M * m3, 2) + m3 ** 4))
+        numerator2 = 16 * kl * (kq * ((c0 + 1) * kp + m3 * (c0 * M - m3)) * (m3 * (c0 * M + m3) - (c0 + 1) * kp)
+                                + c0 * m3 ** 2 * pq * (kp - m3 ** 2))
+        return -power(coupling * G_F * fM * ckm / sqrt(2), 2) * (numerator1 + numerator2) / denom
+    return 0.0 * m232                                                                # MatrixElementDecay3.__call__ :57-58
+
+
+def meson3_dgamma_dea(Ea, ml, ma, mm, fM, ckm, model, c0, coupling, abd=(0, 0, 0)):
+    """dGammadEa (fluxes.py:639-661 / 841-863): Dalitz integral over m_23^2 with scipy quad, like the reference.
+    Only the two hard-wired lepton masses give a non-zero result (:649-661)."""
+    sqrt, power = np.sqrt, np.power
+    m212 = mm ** 2 + ma ** 2 - 2 * mm * Ea
+    e2star = (m212 - ml ** 2) / (2 * sqrt(m212))
+    e3star = (mm ** 2 - m212 - ma ** 2) / (2 * sqrt(m212))
+    if ma > e3star:
+        return 0.0
+    m223Max = (e2star + e3star) ** 2 - (sqrt(e2star ** 2) - sqrt(e3star ** 2 - ma ** 2)) ** 2
+    m223Min = (e2star + e3star) ** 2 - (sqrt(e2star ** 2) + sqrt(e3star ** 2 - ma ** 2)) ** 2
+    if ml != M_MU and ml != M_E:
+        return 0.0
+
+    def matrix_element2(m223):
+        return m2_meson3body(m212, m223, model, mm, ml, ma, fM, ckm, c0=c0, coupling=coupling, abd=abd)
+
+    return (2 * mm) / (32 * power(2 * pi * mm, 3)) * quad(matrix_element2, m223Min, m223Max)[0]
+
+
+def charged_meson_isotropic_simulate(meson_flux, ma, coupling, meson_type, model, n_samples, c0, lepton_masses, abd, usrc):
+    """FluxChargedMeson3BodyIsotropic.simulate (fluxes.py:877-915).  Draw order per (meson row, allowed lepton):
+    n energies, then n cosines."""
+    mm, ckm, fM, total_width = MESON_PARAMS[meson_type]
+    energy, flux = [], []
+    for p in meson_flux:
+        for ml in lepton_masses:
+            if ma > mm - ml:                                                         # :908
+                continue
+            ea_min = ma
+            ea_max = (mm ** 2 + ma ** 2 - ml ** 2) / (2 * mm)
+            energies = usrc.uniform(ea_min, ea_max, n_samples)                       # :882
+            momenta = np.sqrt(energies ** 2 - ma ** 2)
+            cosines = usrc.uniform(-1, 1, n_samples)                                 # :884
+            pz = momenta * cosines
+            beta = p[0] / np.sqrt(p[0] ** 2 + mm ** 2)                               # :888
+            boost = np.power(1 - beta ** 2, -0.5)
+            e_lab = boost * (energies + beta * pz)                                   # :890
+            mc_vol = ea_max - ea_min
+            weights = np.array([p[1] * mc_vol * meson3_dgamma_dea(ea, ml, ma, mm, fM, ckm, model, c0, coupling, abd)
+                                / total_width / n_samples for ea in energies])      # :898-899
+            energy.extend(e_lab); flux.extend(weights)
+    return np.array(energy), np.array(flux)
+
+
+def charged_meson_decay_simulate(meson_flux, ma, coupling, meson_type, model, n_samples, c0, lepton_masses,
+                                 energy_cut, det_dist, det_length, usrc, cut_on_solid_angle=True):
+    """FluxChargedMeson3BodyDecay.simulate / simulate_single, single-process branch (fluxes.py:669-741).
+    Draw order per meson row: one exponential decay position (scipy expon.rvs -> legacy standard_exponential =
+    -log(1 - u)); then per allowed lepton (if decay_pos <= 52): n energies, n cosines, n azimuths.
+    Returns dict of arrays: energy, cosine, flux, angle, solid_angle, decay_pos."""
+    mm, ckm, fM, total_width = MESON_PARAMS[meson_type]
+    cos, sin, arccos, arctan, sqrt, power = np.cos, np.sin, np.arccos, np.arctan, np.sqrt, np.power
+    out = {k: [] for k in ("energy", "cosine", "flux", "angle", "solid_angle", "decay_pos")}
+    positions = []
+    for p in meson_flux:
+        scale = p[0] * PION_LIFETIME * 0.01 * C_LIGHT / M_PI                         # :740
+        x = -np.log(1.0 - usrc.take()) * scale + 0.0
+        positions.append(x)
+        for ml in lepton_masses:
+            if ma > mm - ml:                                                         # :747
+                continue
+            if x > 52.0:                                                             # :671
+                continue
+            ea_min = ma
+            ea_max = (mm ** 2 + ma ** 2 - ml ** 2) / (2 * mm)
+            beta = p[0] / sqrt(p[0] ** 2 + mm ** 2)                                  # :682
+            boost = power(1 - beta ** 2, -0.5)
+            solid_angle_cosine = cos(arctan(det_length / (det_dist - x)))            # :686
+            min_cm_cos = cos(min(boost * arccos(solid_angle_cosine), pi))            # :687
+            energies = usrc.uniform(ea_min, ea_max, n_samples)                       # :689
+            momenta = sqrt(energies ** 2 - ma ** 2)
+            cosines = usrc.uniform(min_cm_cos, 1, n_samples)                         # :691
+            pz = momenta * cosines
+            e_lab = boost * (energies + beta * pz)                                   # :695
+            pz_lab = boost * (pz + beta * energies)
+            theta_lab = arccos(pz_lab / sqrt(e_lab ** 2 - ma ** 2))
+            phi_lab = usrc.uniform(0, 2 * pi, n_samples)                             # :698
+            thetas_z = arccos(cos(theta_lab) * cos(p[1]) + cos(phi_lab) * sin(theta_lab) * sin(p[1]))   # :701
+            mc_vol_lab = (1.0 - min_cm_cos) * boost * beta * sqrt(e_lab ** 2 - ma ** 2)               # :705
+            weights = np.array([p[2] * mc_vol_lab[i] * meson3_dgamma_dea(energies[i], ml, ma, mm, fM, ckm, model, c0, coupling)
+                                / total_width / n_samples for i in range(energies.shape[0])])         # :708-709
+            for i in range(n_samples):                                               # :715-725
+                accept = heaviside(cos(theta_lab[i]) - solid_angle_cosine, 0.0)
+                if accept == 0.0 and cut_on_solid_angle:
+                    continue
+                out["energy"].append(e_lab[i])
+                out["cosine"].append(cos(theta_lab[i]))
+                out["flux"].append(weights[i] * heaviside(e_lab[i] - energy_cut, 1.0))
+                out["angle"].append(thetas_z[i])
+                out["solid_angle"].append(solid_angle_cosine)
+                out["decay_pos"].append(x)
+    res = {k: np.array(v, dtype=np.float64) for k, v in out.items()}
+    res["positions"] = np.array(positions)
+    return res

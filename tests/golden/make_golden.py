@@ -500,7 +500,86 @@ def case_general_decay():
          decay_w32=np.array(fl.decay_axion_weight), p1=p1, p2=p2, w=np.array(wl))
 
 
+def case_meson3body():
+    """Charged-meson 3-body decay fluxes (fluxes.py:605-922): every interaction model of the isotropic class on pion and
+    kaon tables, and the decay-in-flight class (exponential decay positions, solid-angle acceptance, energy cut)."""
+    print("charged-meson 3-body decays")
+    models = ["scalar_ib1", "pseudoscalar_ib1", "vector_ib1", "scalar_ib2", "vector_ib2", "vector_ib9", "sd", "vector_contact"]
+    mf = np.array([[0.0, 0.0259], [120.0, 1.0], [900.0, 2.5], [4000.0, 0.3]])
+    abd = (1.0, 0.5, 0.2)
+    ns = 6
+    iso = {}
+    k = 0
+    for model in models:
+        for mt, ma, g in (("pion", 0.1, 1e-3), ("pion", 30.0, 1e-3), ("kaon", 5.0, 1e-2), ("kaon", 120.0, 1.0)):
+            seed = 100 + k
+            np.random.seed(seed)
+            fl = F.FluxChargedMeson3BodyIsotropic(meson_flux=mf, boson_mass=ma, coupling=g, meson_type=mt,
+                                                  interaction_model=model, n_samples=ns, c0=-0.97, abd=abd)
+            fl.simulate()
+            fl.propagate()
+            us = O.UniformSource(np.random.RandomState(seed))
+            oE, oF = O.charged_meson_isotropic_simulate(mf, ma, g, mt, model, ns, -0.97, [O.M_E, O.M_MU], abd, us)
+            check(f"meson3 iso {model} {mt} ma={ma} E", oE, fl.axion_energy, 0.0)
+            check(f"meson3 iso {model} {mt} ma={ma} flux", oF, fl.axion_flux, 0.0)
+            tag = f"c{k}"
+            iso[tag + "_cfg"] = np.array([models.index(model), 0 if mt == "pion" else 1, ma, g])
+            iso[tag + "_u"] = np.concatenate(us.log) if us.log else np.zeros(0)
+            iso[tag + "_E"] = np.array(fl.axion_energy)
+            iso[tag + "_F"] = np.array(fl.axion_flux)
+            iso[tag + "_S"] = np.array(fl.scatter_axion_weight)
+            k += 1
+    save("meson3_iso", meson_flux=mf, abd=np.array(abd), n_samples=ns, c0=-0.97, n_cases=k, **iso)
+
+    mfd = np.array([[300.0, 0.01, 1.0], [800.0, 0.05, 2.0], [3000.0, 0.002, 0.5], [50.0, 0.3, 1.0], [1500.0, 0.02, 0.7]])
+    dec = {}
+    k = 0
+    for model, mt, ma, g, cut in (("scalar_ib1", "pion", 0.1, 1e-3, True), ("scalar_ib1", "kaon", 20.0, 1e-3, False),
+                                  ("vector_ib1", "kaon", 0.1, 1.0, True), ("vector_contact", "pion", 20.0, 1e-2, True),
+                                  ("pseudoscalar_ib1", "pion", 50.0, 1e-3, True)):
+        seed = 300 + k
+        np.random.seed(seed)
+        fl = F.FluxChargedMeson3BodyDecay(mfd, boson_mass=ma, coupling=g, n_samples=8, meson_type=mt, interaction_model=model,
+                                          energy_cut=140.0)
+        fl.simulate(cut_on_solid_angle=cut)
+        us = O.UniformSource(np.random.RandomState(seed))
+        r = O.charged_meson_decay_simulate(mfd, ma, g, mt, model, 8, -0.95, [O.M_E, O.M_MU], 140.0, 541, 10.0, us, cut)
+        for key, attr in (("energy", "axion_energy"), ("cosine", "cosines"), ("flux", "axion_flux"), ("angle", "axion_angle"),
+                          ("solid_angle", "solid_angles"), ("decay_pos", "decay_pos")):
+            check(f"meson3 decay {model} {mt} ma={ma} {key}", r[key], getattr(fl, attr), 0.0)
+        # split the replayed stream: one position variate per meson, then 3*n per live (meson, lepton) row
+        ulog = np.concatenate(us.log)
+        pos_u, blocks, p = [], [], 0
+        mm = O.MESON_PARAMS[mt][0]
+        n_lep = sum(1 for ml in (O.M_E, O.M_MU) if not (ma > mm - ml))
+        for i in range(mfd.shape[0]):
+            pos_u.append(ulog[p]); p += 1
+            if r["positions"][i] <= 52.0:
+                for _ in range(n_lep):
+                    blocks.append(ulog[p:p + 24]); p += 24
+        assert p == ulog.shape[0]
+        with f32_cast_bypassed():
+            fl.propagate(decay="electron")
+            d64 = np.array(fl.decay_axion_weight, dtype=np.float64); s64 = np.array(fl.scatter_axion_weight, dtype=np.float64)
+        fl.propagate(decay="electron")
+        tag = f"c{k}"
+        dec[tag + "_cfg"] = np.array([models.index(model), 0 if mt == "pion" else 1, ma, g, 1.0 if cut else 0.0])
+        dec[tag + "_upos"] = np.array(pos_u)
+        dec[tag + "_usamp"] = np.concatenate(blocks) if blocks else np.zeros(0)
+        for key in ("energy", "cosine", "flux", "angle", "solid_angle", "decay_pos", "positions"):
+            dec[tag + "_" + key] = r[key] if key == "positions" else np.array(getattr(fl, {"energy": "axion_energy", "cosine": "cosines", "flux": "axion_flux", "angle": "axion_angle", "solid_angle": "solid_angles", "decay_pos": "decay_pos"}[key]))
+        dec[tag + "_d64"] = d64; dec[tag + "_s64"] = s64
+        dec[tag + "_d32"] = np.array(fl.decay_axion_weight); dec[tag + "_s32"] = np.array(fl.scatter_axion_weight)
+        k += 1
+    save("meson3_decay", meson_flux=mfd, n_samples=8, c0=-0.95, energy_cut=140.0, det_dist=541.0, det_length=10.0,
+         n_cases=k, **dec)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                      # regenerate selected cases only: python make_golden.py case_meson3body
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     kat_scalars()
     case_primakoff()
     case_compton()
@@ -513,4 +592,5 @@ if __name__ == "__main__":
     case_nuclear_pi0()
     case_pairgamma()
     case_general_decay()
+    case_meson3body()
     print("all golden fixtures written; oracle pinned against the reference")

@@ -7,6 +7,7 @@
 
 #include "../../alplib_b200/csrc/alp_math.cuh"
 #include "../../alplib_b200/csrc/alp_math2.cuh"
+#include "../../alplib_b200/csrc/alp_math3.cuh"
 #include "../../include/alpk.h"
 
 using namespace alp;

@@ -965,3 +965,73 @@ def test_examples_run(A, precision):
     energies, weights, n_decay, n_compton = ns["get_events"](10.0, 1e-6, use_loop=True)
     assert energies.shape == weights.shape == (10000,) and np.isfinite(n_decay) and np.isfinite(n_compton)
     assert n_decay >= 0 and n_compton >= 0 and np.sum(weights) == pytest.approx(n_decay + n_compton, rel=1e-6)
+
+
+# ---- charged-meson 3-body decay fluxes (fluxes.py:605-922) -----------------------------------------------------------------
+MESON3_MODELS = ["scalar_ib1", "pseudoscalar_ib1", "vector_ib1", "scalar_ib2", "vector_ib2", "vector_ib9", "sd", "vector_contact"]
+
+
+def test_meson3body_isotropic(A):
+    """FluxChargedMeson3BodyIsotropic against the reference on the same variates: all interaction models, pion / kaon."""
+    g = load_golden("meson3_iso")
+    ns, c0, abd = int(g["n_samples"]), float(g["c0"]), tuple(float(x) for x in g["abd"])
+    worst = 0.0
+    for k in range(int(g["n_cases"])):
+        mi, mt, ma, cpl = g[f"c{k}_cfg"]
+        fl = A.FluxChargedMeson3BodyIsotropic(meson_flux=g["meson_flux"], boson_mass=float(ma), coupling=float(cpl),
+                                              meson_type=["pion", "kaon"][int(mt)], interaction_model=MESON3_MODELS[int(mi)],
+                                              n_samples=ns, c0=c0, abd=abd)
+        fl.simulate(uniforms=g[f"c{k}_u"])
+        assert max_rel(fl.axion_energy, g[f"c{k}_E"]) < 1e-13
+        worst = max(worst, max_rel(fl.axion_flux, g[f"c{k}_F"]))
+        fl.propagate()
+        assert fl.scatter_axion_weight.dtype == np.float64 and np.all(fl.decay_axion_weight == 0)
+        assert max_rel(fl.scatter_axion_weight, g[f"c{k}_S"]) < TOL
+    assert worst < TOL, worst
+
+
+def test_meson3body_decay_in_flight(A):
+    """FluxChargedMeson3BodyDecay: decay positions, acceptance, energy cut, then propagate(decay=...) (f32 weights)."""
+    g = load_golden("meson3_decay")
+    ns = int(g["n_samples"])
+    for k in range(int(g["n_cases"])):
+        mi, mt, ma, cpl, cut = g[f"c{k}_cfg"]
+        fl = A.FluxChargedMeson3BodyDecay(g["meson_flux"], boson_mass=float(ma), coupling=float(cpl), n_samples=ns,
+                                          meson_type=["pion", "kaon"][int(mt)], interaction_model=MESON3_MODELS[int(mi)],
+                                          energy_cut=float(g["energy_cut"]), keep_f64=True)
+        fl.simulate(cut_on_solid_angle=bool(cut), uniforms=dict(pos=g[f"c{k}_upos"], samples=g[f"c{k}_usamp"]))
+        assert max_rel(fl.axion_energy, g[f"c{k}_energy"]) < 1e-13
+        assert max_rel(fl.axion_flux, g[f"c{k}_flux"]) < TOL
+        assert max_rel(fl.cosines, g[f"c{k}_cosine"]) < 1e-12
+        assert max_rel(fl.axion_angle, g[f"c{k}_angle"]) < TOL
+        assert max_rel(fl.solid_angles, g[f"c{k}_solid_angle"]) < 1e-14
+        assert max_rel(fl.decay_pos, g[f"c{k}_decay_pos"]) < 1e-14
+        fl.propagate(decay="electron")
+        assert fl.decay_axion_weight.dtype == np.float32
+        assert max_rel(fl.scatter_axion_weight_f64, g[f"c{k}_s64"]) < TOL
+        assert_decay_close(fl.decay_axion_weight_f64, g[f"c{k}_d64"], g[f"c{k}_s64"], TOL)
+        assert max_rel(fl.scatter_axion_weight, g[f"c{k}_s32"]) <= F32
+        fl.propagate()                                                    # no decays: float64 copies of the flux
+        assert fl.scatter_axion_weight.dtype == np.float64 and max_rel(fl.scatter_axion_weight, g[f"c{k}_flux"]) < TOL
+
+
+def test_meson3body_free_running(A):
+    """Philox mode: reproducible, independent of row sharding, statistically consistent with the oracle's total rate."""
+    mf = np.stack([np.linspace(50.0, 3000.0, 40), np.full(40, 0.5)], axis=1)
+    kw = dict(boson_mass=5.0, coupling=1e-3, meson_type="kaon", interaction_model="scalar_ib1", n_samples=2000)
+    a = A.FluxChargedMeson3BodyIsotropic(meson_flux=mf, seed=9, **kw); a.simulate()
+    b = A.FluxChargedMeson3BodyIsotropic(meson_flux=mf, seed=9, **kw); b.simulate()
+    assert np.array_equal(a.axion_flux, b.axion_flux) and np.array_equal(a.axion_energy, b.axion_energy)
+    half = A.FluxChargedMeson3BodyIsotropic(meson_flux=mf[20:], seed=9, **kw)
+    half.row_offset = 40                                                  # 20 mesons x 2 leptons precede this shard
+    half.simulate()
+    assert np.array_equal(half.axion_flux, a.axion_flux[40 * 2000:])
+    us = O.UniformSource(np.random.RandomState(1))
+    oE, oF = O.charged_meson_isotropic_simulate(mf[:4], 5.0, 1e-3, "kaon", "scalar_ib1", 2000, -0.97, [O.M_E, O.M_MU], (0, 0, 0), us)
+    tot_gpu = np.sum(a.axion_flux[:4 * 2 * 2000])
+    assert abs(tot_gpu / np.sum(oF) - 1) < 0.1                            # two independent MC estimates of the same rate
+    # dGammadEa / total_br through the public methods
+    d = a.dGammadEa(np.array([10.0, 100.0, 200.0]), O.M_MU)
+    ref = [O.meson3_dgamma_dea(e, O.M_MU, 5.0, O.M_K, O.F_K, O.V_US, "scalar_ib1", -0.97, 1e-3) for e in (10.0, 100.0, 200.0)]
+    assert max_rel(d, ref) < TOL
+    assert a.total_br() > 0

@@ -336,3 +336,84 @@ def test_general_decay(hostcheck):
                                dptr(np.ascontiguousarray(m["uniforms"])), dptr(p1), dptr(p2), dptr(t1))
     assert max_rel(p1[0], m["axion_energy"]) < 1e-12
     assert max_rel(t1, m["axion_angle"]) < TOL
+
+
+# ---- charged-meson 3-body decays (alp_math3.cuh): the kernels' arithmetic, host build, against the reference fixtures ----
+MESON3_MODELS = ["scalar_ib1", "pseudoscalar_ib1", "vector_ib1", "scalar_ib2", "vector_ib2", "vector_ib9", "sd", "vector_contact"]
+
+
+def _meson3_par(mt, ma, model, c0, g, abd, ns):
+    from alplib_b200 import _native as NV
+    from oracle import alp_oracle as O
+    mm, ckm, fM, tw = O.MESON_PARAMS[mt]
+    p = NV.Meson3T()
+    p.mm, p.ma, p.fM, p.ckm, p.total_width, p.c0, p.coupling = mm, ma, fM, ckm, tw, c0, g
+    p.a, p.b, p.d = abd
+    p.pref = (2 * mm) / (32 * np.power(2 * np.pi * mm, 3))
+    p.n_samples = float(ns)
+    p.model = MESON3_MODELS.index(model)
+    return p, mm
+
+
+def _meson3_rows(n_mesons, leptons):
+    return (np.repeat(np.arange(n_mesons, dtype=np.uint32), len(leptons)),
+            np.tile(np.asarray(leptons, dtype=np.float64), n_mesons))
+
+
+def test_meson3_isotropic_host(hostcheck):
+    from oracle import alp_oracle as O
+    g = load_golden("meson3_iso")
+    ns, c0, abd = int(g["n_samples"]), float(g["c0"]), tuple(float(x) for x in g["abd"])
+    mf = np.ascontiguousarray(g["meson_flux"])
+    worst = 0.0
+    for k in range(int(g["n_cases"])):
+        mi, mt, ma, cpl = g[f"c{k}_cfg"]
+        par, mm = _meson3_par(["pion", "kaon"][int(mt)], float(ma), MESON3_MODELS[int(mi)], c0, float(cpl), abd, ns)
+        leptons = [ml for ml in (O.M_E, O.M_MU) if not (ma > mm - ml)]
+        rm, rl = _meson3_rows(mf.shape[0], leptons)
+        n = rm.shape[0] * ns
+        oe, of = np.empty(n), np.empty(n)
+        u = np.ascontiguousarray(g[f"c{k}_u"])
+        hostcheck.hc_meson3_isotropic(dptr(mf), dptr(rm), dptr(rl), C.c_uint64(rm.shape[0]), C.c_uint32(ns), C.byref(par),
+                                      dptr(u), dptr(oe), dptr(of))
+        assert max_rel(oe, g[f"c{k}_E"]) < 1e-14
+        worst = max(worst, max_rel(of, g[f"c{k}_F"]))
+    assert worst < 1e-9, worst
+
+
+def test_meson3_decay_host(hostcheck):
+    from oracle import alp_oracle as O
+    g = load_golden("meson3_decay")
+    ns = int(g["n_samples"])
+    mf = np.ascontiguousarray(g["meson_flux"])
+    for k in range(int(g["n_cases"])):
+        mi, mt, ma, cpl, cut = g[f"c{k}_cfg"]
+        par, mm = _meson3_par(["pion", "kaon"][int(mt)], float(ma), MESON3_MODELS[int(mi)], float(g["c0"]), float(cpl), (0, 0, 0), ns)
+        leptons = [ml for ml in (O.M_E, O.M_MU) if not (ma > mm - ml)]
+        rm, rl = _meson3_rows(mf.shape[0], leptons)
+        n = rm.shape[0] * ns
+        outs = [np.empty(n) for _ in range(6)]
+        keep = np.zeros(n, dtype=np.uint8)
+        up, us = np.ascontiguousarray(g[f"c{k}_upos"]), np.ascontiguousarray(g[f"c{k}_usamp"])
+        hostcheck.hc_meson3_decay(dptr(mf), dptr(rm), dptr(rl), C.c_uint64(rm.shape[0]), C.c_uint32(ns), C.byref(par),
+                                  C.c_double(float(g["det_dist"])), C.c_double(float(g["det_length"])),
+                                  C.c_double(float(g["energy_cut"])), C.c_int(int(cut)), dptr(up), dptr(us),
+                                  *[dptr(o) for o in outs], dptr(keep))
+        sel = keep != 0
+        for o, key, tol in zip(outs, ("energy", "flux", "cosine", "angle", "solid_angle", "decay_pos"),
+                               (1e-13, 1e-9, 1e-12, 1e-9, 1e-14, 1e-14)):
+            assert max_rel(o[sel], g[f"c{k}_{key}"]) < tol, (k, key)
+
+
+def test_meson3_quadrature_refines_like_quad(hostcheck):
+    """Couplings of order one push the Dalitz integral above quad's epsabs: the kernels' QAGS-style bisection must follow."""
+    from oracle import alp_oracle as O
+    rng = np.random.default_rng(4)
+    for model, mt, ma, ml in (("vector_ib1", "kaon", 0.1, O.M_E), ("vector_ib9", "kaon", 5.0, O.M_MU), ("sd", "kaon", 30.0, O.M_E)):
+        par, mm = _meson3_par(mt, ma, model, -0.95, 1.0, (1.0, 0.5, 0.2), 10)
+        ea = ma + ((mm ** 2 + ma ** 2 - ml ** 2) / (2 * mm) - ma) * rng.random(60)
+        out = np.empty_like(ea)
+        hostcheck.hc_meson3_dgamma(dptr(ea), C.c_uint64(ea.size), C.c_double(ml), C.byref(par), dptr(out))
+        _, ckm, fM, _ = O.MESON_PARAMS[mt]
+        ref = np.array([O.meson3_dgamma_dea(e, ml, ma, mm, fM, ckm, model, -0.95, 1.0, (1.0, 0.5, 0.2)) for e in ea])
+        assert max_rel(out, ref) < 1e-9

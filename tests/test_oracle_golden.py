@@ -245,3 +245,47 @@ def test_neutral_meson(name):
     assert max_rel(E, g["axion_energy"]) < 1e-13 and max_rel(F, g["axion_flux"]) < 1e-14 and max_rel(T, g["axion_angle"]) < 1e-9
     if name == "meson2body_cut":
         assert 0 < E.shape[0] < g["meson_flux"].shape[0] * int(g["n_samples"])
+
+
+MESON3_MODELS = ["scalar_ib1", "pseudoscalar_ib1", "vector_ib1", "scalar_ib2", "vector_ib2", "vector_ib9", "sd", "vector_contact"]
+
+
+def test_meson3body_isotropic_oracle():
+    """Charged-meson 3-body isotropic flux (fluxes.py:811-922): every interaction model, pion and kaon tables."""
+    g = load_golden("meson3_iso")
+    ns, c0, abd = int(g["n_samples"]), float(g["c0"]), tuple(g["abd"])
+    for k in range(int(g["n_cases"])):
+        mi, mt, ma, cpl = g[f"c{k}_cfg"]
+        E, F = O.charged_meson_isotropic_simulate(g["meson_flux"], float(ma), float(cpl), ["pion", "kaon"][int(mt)],
+                                                  MESON3_MODELS[int(mi)], ns, c0, [O.M_E, O.M_MU], abd,
+                                                  O.UniformSource(g[f"c{k}_u"]))
+        assert np.array_equal(E, g[f"c{k}_E"]) and np.array_equal(F, g[f"c{k}_F"])
+        assert max_rel(F * (2 / (4 * np.pi * 20 ** 2)), g[f"c{k}_S"]) < 1e-15            # propagate: acceptance only (:917-920)
+    assert any(np.any(g[f"c{k}_F"] != 0) for k in range(int(g["n_cases"])))
+
+
+def test_meson3body_decay_oracle():
+    """Decay-in-flight class (fluxes.py:605-808): exponential decay positions, solid-angle acceptance, energy cut."""
+    g = load_golden("meson3_decay")
+    ns = int(g["n_samples"])
+    n_dead = 0
+    for k in range(int(g["n_cases"])):
+        mi, mt, ma, cpl, cut = g[f"c{k}_cfg"]
+        # rebuild the flat stream in draw order from the structured fixture
+        pos_u, blocks = g[f"c{k}_upos"], g[f"c{k}_usamp"].reshape(-1, 3 * ns)
+        mm = O.MESON_PARAMS[["pion", "kaon"][int(mt)]][0]
+        n_lep = sum(1 for ml in (O.M_E, O.M_MU) if not (ma > mm - ml))
+        flat, b = [], 0
+        for i in range(pos_u.shape[0]):
+            flat.append(pos_u[i:i + 1])
+            if g[f"c{k}_positions"][i] <= 52.0:
+                flat.extend(blocks[b:b + n_lep]); b += n_lep
+            else:
+                n_dead += 1
+        r = O.charged_meson_decay_simulate(g["meson_flux"], float(ma), float(cpl), ["pion", "kaon"][int(mt)],
+                                           MESON3_MODELS[int(mi)], ns, float(g["c0"]), [O.M_E, O.M_MU],
+                                           float(g["energy_cut"]), float(g["det_dist"]), float(g["det_length"]),
+                                           O.UniformSource(np.concatenate(flat)), bool(cut))
+        for key in ("energy", "cosine", "flux", "angle", "solid_angle", "decay_pos"):
+            assert np.array_equal(r[key], g[f"c{k}_{key}"]), (k, key)
+    assert n_dead > 0                                                  # some mesons decay beyond the dump
