@@ -52,8 +52,16 @@ ALP_HD SP6 m3_scalar_products(double M, double m1, double m3, double m122, doubl
 
 ALP_HD double cube(double x) { return (x * x) * x; }
 
-// M2Meson3BodyDecay.__call__ (matrix_element.py:443-518).  m1 = lepton mass.
-ALP_HD double m2_meson3body(double m122, double m232, double m1, const Meson3Const& K) {
+// The part of the *_ib1 matrix elements that depends on m122 only (matrix_element.py:446, 451): the threshold factor
+// heaviside(e3star - m3, 0).  Evaluated once per Dalitz integral instead of once per node (same value, bit for bit).
+ALP_HD double m2_threshold_factor(double m122, const Meson3Const& K) {
+    if (K.model != kM3ScalarIB1 && K.model != kM3PseudoscalarIB1) return 1.0;
+    const double e3star = ((K.mm * K.mm - m122) - K.ma * K.ma) / (2 * sqrt(m122));
+    return heaviside(e3star - K.ma, 0.0);
+}
+
+// M2Meson3BodyDecay.__call__ (matrix_element.py:443-518).  m1 = lepton mass; hv = m2_threshold_factor(m122, K).
+ALP_HD double m2_meson3body(double m122, double m232, double m1, const Meson3Const& K, double hv) {
     const double M = K.mm, m3 = K.ma, g = K.coupling;
     const double M2 = M * M, m12 = m1 * m1, m32 = m3 * m3;
     const SP6 sp = m3_scalar_products(M, m1, m3, m122, m232);
@@ -62,12 +70,11 @@ ALP_HD double m2_meson3body(double m122, double m232, double m1, const Meson3Con
     switch (K.model) {
     case kM3ScalarIB1:
     case kM3PseudoscalarIB1: {                                                        // :445-464
-        const double e3star = ((M2 - m122) - m32) / (2 * sqrt(m122));
         const double ev = (((m122 + m232) - m12) - m32) / (2 * M);
         const double emu = ((M2 - m232) + m12) / (2 * M);
         const double q2 = M2 - (2 * M) * ev;
         const double r = (((g * kGF) * K.fM) * K.ckm) / (q2 - m12);
-        const double prefactor = heaviside(e3star - m3, 0.0) * (r * r);
+        const double prefactor = hv * (r * r);
         const double m1M = m1 * M;
         const double head = (((2 * M) * emu) * q2) * (q2 - m12) - (q2 * q2 - m1M * m1M) * ((q2 + m12) - m32);
         const double tail = ((2 * q2) * m12) * (M2 - q2);
@@ -173,30 +180,37 @@ static const double kGK21WgHost[5] = ALP_GK21_WG;
 struct GK21 { double result, abserr, resabs, resasc; };
 
 // dqk21 with the integrand f(x) = m2_meson3body(m122, x, m1, K); same evaluation and summation order as QUADPACK.
-ALP_HD GK21 gk21_m2(double a, double b, double m122, double m1, const Meson3Const& K) {
+#if defined(__CUDACC__)
+#define ALP_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define ALP_HD_NOINLINE inline
+#endif
+// (not inlined on the device: the adaptive stage calls it from several places and each inlined copy carries the whole
+// matrix-element switch)
+ALP_HD_NOINLINE GK21 gk21_m2(double a, double b, double m122, double m1, const Meson3Const& K, double hv) {
     const double epmach = 2.220446049250313e-16, uflow = 2.2250738585072014e-308;
     const double centr = 0.5 * (a + b), hlgth = 0.5 * (b - a), dhlgth = fabs(hlgth);
     double fv1[10], fv2[10];
     double resg = 0.0;
-    const double fc = m2_meson3body(m122, centr, m1, K);
+    const double fc = m2_meson3body(m122, centr, m1, K, hv);
     double resk = ALP_WGK(10) * fc;
     double resabs = fabs(resk);
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 5; ++j) {                         // Gauss nodes
         const int jtw = 2 * j + 1;
         const double absc = hlgth * ALP_XGK(jtw);
-        const double f1 = m2_meson3body(m122, centr - absc, m1, K), f2 = m2_meson3body(m122, centr + absc, m1, K);
+        const double f1 = m2_meson3body(m122, centr - absc, m1, K, hv), f2 = m2_meson3body(m122, centr + absc, m1, K, hv);
         fv1[jtw] = f1; fv2[jtw] = f2;
         const double fsum = f1 + f2;
         resg = resg + ALP_WG(j) * fsum;
         resk = resk + ALP_WGK(jtw) * fsum;
         resabs = resabs + ALP_WGK(jtw) * (fabs(f1) + fabs(f2));
     }
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 5; ++j) {                         // Kronrod nodes
         const int jtwm1 = 2 * j;
         const double absc = hlgth * ALP_XGK(jtwm1);
-        const double f1 = m2_meson3body(m122, centr - absc, m1, K), f2 = m2_meson3body(m122, centr + absc, m1, K);
+        const double f1 = m2_meson3body(m122, centr - absc, m1, K, hv), f2 = m2_meson3body(m122, centr + absc, m1, K, hv);
         fv1[jtwm1] = f1; fv2[jtwm1] = f2;
         const double fsum = f1 + f2;
         resk = resk + ALP_WGK(jtwm1) * fsum;
@@ -204,7 +218,7 @@ ALP_HD GK21 gk21_m2(double a, double b, double m122, double m1, const Meson3Cons
     }
     const double reskh = resk * 0.5;
     double resasc = ALP_WGK(10) * fabs(fc - reskh);
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 10; ++j) resasc = resasc + ALP_WGK(j) * (fabs(fv1[j] - reskh) + fabs(fv2[j] - reskh));
     GK21 r;
     r.result = resk * hlgth;
@@ -225,24 +239,35 @@ constexpr int kQagsIntervals = 8;
 
 ALP_HD double qags21_m2(double a, double b, double m122, double m1, const Meson3Const& K) {
     const double epsabs = 1.49e-8, epsrel = 1.49e-8, epmach = 2.220446049250313e-16;
-    GK21 r = gk21_m2(a, b, m122, m1, K);
+    const double hv = m2_threshold_factor(m122, K);
+    GK21 r = gk21_m2(a, b, m122, m1, K, hv);
     double errbnd = fmax(epsabs, epsrel * fabs(r.result));
     const bool roundoff = r.abserr <= 100.0 * epmach * r.resabs && r.abserr > errbnd;        // ier = 2
     if (roundoff || (r.abserr <= errbnd && r.abserr != r.resasc) || r.abserr == 0.0) return r.result;
-    // adaptive stage (rare: integral above ~1e-8 and not yet converged)
+    // adaptive stage: the 21-point estimate is not trusted (integral above ~1e-8, or a peak the rule does not resolve --
+    // the collinear peak of the *_ib1 models with an electron).  First bisection without bookkeeping arrays: QAGS's usual exit.
+    const double mid = 0.5 * (a + b);
+    const GK21 h1 = gk21_m2(a, mid, m122, m1, K, hv), h2 = gk21_m2(mid, b, m122, m1, K, hv);
+    double area = (r.result + (h1.result + h2.result)) - r.result;
+    double errsum = (r.abserr + (h1.abserr + h2.abserr)) - r.abserr;
+    errbnd = fmax(epsabs, epsrel * fabs(area));
+    if (errsum <= errbnd) return h2.abserr > h1.abserr ? (h2.result + h1.result) : (h1.result + h2.result);
     double al[kQagsIntervals], bl[kQagsIntervals], rl[kQagsIntervals], el[kQagsIntervals];
-    al[0] = a; bl[0] = b; rl[0] = r.result; el[0] = r.abserr;
-    double area = r.result, errsum = r.abserr;
-    int last = 1;
+    {
+        const bool sw = h2.abserr > h1.abserr;             // larger error estimate in slot 0 (dqagse labels 20/30)
+        al[0] = sw ? mid : a;   bl[0] = sw ? b : mid;   rl[0] = sw ? h2.result : h1.result;   el[0] = sw ? h2.abserr : h1.abserr;
+        al[1] = sw ? a : mid;   bl[1] = sw ? mid : b;   rl[1] = sw ? h1.result : h2.result;   el[1] = sw ? h1.abserr : h2.abserr;
+    }
+    int last = 2;
     while (last < kQagsIntervals) {
         int mx = 0;
         for (int k = 1; k < last; ++k) if (el[k] > el[mx]) mx = k;
         const double a1 = al[mx], b1 = 0.5 * (al[mx] + bl[mx]), a2 = b1, b2 = bl[mx];
-        const GK21 r1 = gk21_m2(a1, b1, m122, m1, K), r2 = gk21_m2(a2, b2, m122, m1, K);
+        const GK21 r1 = gk21_m2(a1, b1, m122, m1, K, hv), r2 = gk21_m2(a2, b2, m122, m1, K, hv);
         const double area12 = r1.result + r2.result, erro12 = r1.abserr + r2.abserr;
         errsum = (errsum + erro12) - el[mx];
         area = (area + area12) - rl[mx];
-        if (r2.abserr > r1.abserr) {       // keep the larger error in slot mx (dqagse labels 20/30)
+        if (r2.abserr > r1.abserr) {
             al[mx] = a2; bl[mx] = b2; rl[mx] = r2.result; el[mx] = r2.abserr;
             al[last] = a1; bl[last] = b1; rl[last] = r1.result; el[last] = r1.abserr;
         } else {

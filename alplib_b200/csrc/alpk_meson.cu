@@ -48,7 +48,7 @@ meson3_rows_kernel(int mode, const double* __restrict__ mesons, const uint32_t* 
 
 // samples: thread = (row, sample).  Injected uniforms: block_of_row[r] >= 0 is the index of the row's block in
 // `uniforms`, laid out [block][2 or 3][n_samples] (energies, cosines[, azimuths] -- the reference's draw order).
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 meson3_samples_kernel(int mode, const double* __restrict__ table, uint64_t n_rows, uint32_t n_samples, Meson3Const K,
                       double energy_cut, int cut_on_solid_angle, const double* __restrict__ uniforms,
                       const int32_t* __restrict__ block_of_row, uint64_t seed, uint32_t row_offset,
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads)
 meson3_m2_kernel(double m122, const double* __restrict__ m232, uint64_t n, double ml, Meson3Const K, double* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = m2_meson3body(m122, __ldg(m232 + i), ml, K);
+        out[i] = m2_meson3body(m122, __ldg(m232 + i), ml, K, m2_threshold_factor(m122, K));
 }
 
 }  // namespace alpk
