@@ -2,7 +2,9 @@
 
 # "fast": algebraically simplified per-sample arithmetic, <= 1e-9 relative from the reference (the parity tolerance).
 # "faithful": the reference's operation order expression by expression.
-PRECISION = "fast"
+import os as _os
+
+PRECISION = _os.environ.get("ALPK_PRECISION", "fast")          # (env override: benchmarking the other modes)
 
 # Execution schedule of the drop-in classes (same results in every mode; the variates are a pure function of the seed):
 #   "auto"  (default) simulate()/propagate() record their arguments; work is launched when a result is demanded.

@@ -432,6 +432,17 @@ ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& 
 ALP_HD bool propagate_try_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64,
                                const double* exp_tab = nullptr) {
     const double d = ea * ea - c.ma2;
+    if (c.fast == 2) {
+        // optional FP32 mode (north star: 1e-5 relative): only the transcendental part is single precision -- rsqrt and
+        // the two exponentials (~1e-7 relative each); the decay probability uses expm1f, which unlike the reference's
+        // 1 - exp(-x) does not cancel for long-lived ALPs.  Products stay FP64 so the dynamic range is unchanged.
+        const float tf = rsqrtf((float)d);
+        const float surv_f = expf((float)c.k1 * tf);
+        const float dec_f = -expm1f((float)c.k2 * tf);
+        s64 = (c.rescale * wgt) * (double)surv_f;
+        d64 = s64 * (double)dec_f;
+        return (d > 0.0) & (c.use_tof == 0);
+    }
     const double t = rsqrt_fast(d);
     const double surv = exp_fast_core(c.k1 * t, exp_tab);
     const double dec = 1 - exp_fast_core(c.k2 * t, exp_tab);
@@ -445,17 +456,6 @@ ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, dou
     const double d = ea * ea - c.ma2;
     if (!(d > 0.0) || c.use_tof) {            // E_a <= m_a (v = 0 or NaN) and the time-of-flight cut: reference path
         propagate_sample(ea, wgt, c, d64, s64);
-        return;
-    }
-    if (c.fast == 2) {
-        // optional FP32 mode (north star: 1e-5 relative): only the transcendental part is single precision -- rsqrt and
-        // the two exponentials (~1e-7 relative each); the decay probability uses expm1f, which unlike the reference's
-        // 1 - exp(-x) does not cancel for long-lived ALPs.  Products stay FP64 so the dynamic range is unchanged.
-        const float tf = rsqrtf((float)d);
-        const float surv_f = expf((float)c.k1 * tf);
-        const float dec_f = -expm1f((float)c.k2 * tf);
-        s64 = (c.rescale * wgt) * (double)surv_f;
-        d64 = s64 * (double)dec_f;
         return;
     }
     const double t = rsqrt(d);                // exponents below -708 (or a subnormal p_a^2): library functions
