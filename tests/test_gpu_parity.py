@@ -132,10 +132,11 @@ def _c2_flux(n_bins):
     return np.stack([e, 1e16 * e ** -1.5 * np.exp(-e / 150)], axis=1)
 
 
-def test_compton_free_running_matches_oracle_sample_by_sample(A):
+@pytest.mark.parametrize("ns", [501, 1000, 20000])      # odd: pairs straddle rows; even: paired kernels, short / long rows
+def test_compton_free_running_matches_oracle_sample_by_sample(A, ns):
     """Free-running Philox mode: replay the kernel's uniforms with the NumPy Philox and feed them to the oracle."""
     pf = _c2_flux(37)
-    ma, gg, ns, seed = 1.5, 1e-7, 501, 0xA1B2C3D4 + 2          # odd n_samples: pairs straddle rows
+    ma, gg, seed = 1.5, 1e-7, 0xA1B2C3D4 + 2
     fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=ma, axion_coupling=gg, n_samples=ns, seed=seed,
                                 keep_f64=True, **GEOM)
     fl.simulate()
@@ -149,7 +150,9 @@ def test_compton_free_running_matches_oracle_sample_by_sample(A):
     p = O.propagate(oE, oF, ma, O.W_ee(gg, ma), 1.0, 4.0, 0.2, geom_accept=GA)
     assert max_rel(fl.scatter_axion_weight_f64, p["scatter_w64"]) < TOL
     assert_decay_close(fl.decay_axion_weight_f64, p["decay_w64"], p["scatter_w64"], TOL)
-    assert_decay_close(fl.decay_axion_weight, p["decay_w"], p["scatter_w"], TOL, extra_rel=F32)
+    # float32 attribute = float32(w64) * float32(acceptance): two roundings, so FP64 values that agree to 1e-15 but straddle a
+    # float32 rounding boundary can end up two float32 ulps apart (seen once in 5.4e5 samples)
+    assert_decay_close(fl.decay_axion_weight, p["decay_w"], p["scatter_w"], TOL, extra_rel=2 * F32)
     _, orate = O.decays(oE, p["decay_w"], 100, 5.0)
     rate = A.ElectronEventGenerator(fl, A.Material("Ar")).decays(100, 5.0)
     assert rate == pytest.approx(orate, rel=1e-6)
