@@ -120,9 +120,11 @@ scan_kernel(const ScanArgs a) {
     __shared__ double s_tab[64];                 // exp_fast table
     __shared__ unsigned long long s_tmax_bits;   // max over live samples of 1/p_a (non-finite / NaN -> +inf), as ordered bits
     if (threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
-    if (threadIdx.x == 0) s_tmax_bits = 0ull;
+    __shared__ unsigned long long s_tmin_bits;   // min over live samples of 1/p_a; 0 if any live sample has a NaN 1/p_a or a non-finite weight
+    __shared__ unsigned long long s_wmax_bits;   // max |weight| over live samples
+    if (threadIdx.x == 0) { s_tmax_bits = 0ull; s_tmin_bits = 0x7ff0000000000000ull; s_wmax_bits = 0ull; }
     __syncthreads();
-    unsigned long long my_tmax = 0ull;
+    unsigned long long my_tmax = 0ull, my_tmin = 0x7ff0000000000000ull, my_wmax = 0ull;
     constexpr int kPer = kScanTile / kScanThreads;                  // consecutive samples per thread
     double rt_[kPer], rb_[kPer], rw_[kPer], rh_[kPer];
     int nkeep = 0;
@@ -164,6 +166,11 @@ scan_kernel(const ScanArgs a) {
             const unsigned long long tb = (t >= 0.0 && t < INFINITY) ? (unsigned long long)__double_as_longlong(t)
                                                                      : 0x7ff0000000000000ull;
             my_tmax = tb > my_tmax ? tb : my_tmax;
+            const bool clean = (t >= 0.0) && (fabs(w) < INFINITY);         // (false for NaN t / NaN or infinite w)
+            const unsigned long long lb = clean ? (unsigned long long)__double_as_longlong(t) : 0ull;
+            my_tmin = lb < my_tmin ? lb : my_tmin;
+            const unsigned long long wb = clean ? (unsigned long long)__double_as_longlong(fabs(w)) : 0ull;
+            my_wmax = wb > my_wmax ? wb : my_wmax;
         }
         keepmask |= 1u << q;
         ++nkeep;
@@ -175,6 +182,8 @@ scan_kernel(const ScanArgs a) {
     for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) s_warp[wid] = incl;
     if (my_tmax) atomicMax(&s_tmax_bits, my_tmax);
+    if (my_tmin != 0x7ff0000000000000ull) atomicMin(&s_tmin_bits, my_tmin);
+    if (my_wmax) atomicMax(&s_wmax_bits, my_wmax);
     __syncthreads();
     int woff = 0;
     for (int q = 0; q < wid; ++q) woff += s_warp[q];
@@ -197,6 +206,8 @@ scan_kernel(const ScanArgs a) {
     //      shared-memory reads, every lane busy for any n_g), lane partials combined by a shuffle tree (fixed order) ----
     const ScanGeom& G = a.geo;
     const double tmax = __longlong_as_double((long long)s_tmax_bits);      // largest finite 1/p_a of the tile (or +inf)
+    const double tmin = __longlong_as_double((long long)s_tmin_bits);      // smallest 1/p_a (0 if a live sample is not clean)
+    const double wmax = __longlong_as_double((long long)s_wmax_bits);
     for (int j = wid; j < a.n_g; j += kScanThreads / 32) {
         const double width = __ldg(a.width + (size_t)im * a.n_g + j);
         const double resc = __ldg(a.rescale + j);
@@ -206,7 +217,15 @@ scan_kernel(const ScanArgs a) {
         const double kmax = fmax(fabs(k1), fabs(k2));
         const double tf = fmin(kmax > 0.0 ? 708.0 / kmax : INFINITY, 1e140);
         double acc = 0.0;
-        if (FAST && G.fast == 1 && !G.ev.days_f64 && tmax <= tf) {
+        if (FAST && G.fast == 1 && tmin > 0.0 &&
+            ((!(width > 0.0) && tmax < INFINITY) || (width > 0.0 && k1 * tmin + log(fabs(resc) * wmax) < -105.0))) {
+            // stable ALP (width <= 0, e.g. m_a < 2 m_e for the electron coupling: half of the C5 mass axis): the decay
+            // probability 1 - exp(0) is exactly 0 for every (clean) sample, so is every term of the sum.
+            // short-lived corner of the grid: every decay weight of the tile is below half the smallest float32 denormal
+            // (2^-150 = e^-103.97), i.e. the reference's float32 cast (fluxes.py:64) makes it exactly 0 --
+            //   |resc w surv dec| <= |resc| w_max exp(k1 t_min),  dec in [0, 1],  surv <= exp(k1 t_min) as k1 < 0 <= t_min <= t
+            // -- so every term of this (tile, coupling) sum is an exact zero and the walk is skipped.
+        } else if (FAST && G.fast == 1 && !G.ev.days_f64 && tmax <= tf) {
             // every sample of the tile is inside the branch-free domain: straight-line body, two samples in flight
 #pragma unroll 2
             for (int k = lane; k < n_live; k += 32) {
