@@ -552,7 +552,7 @@ class FluxComptonIsotropic(_ChainFlux):
                 if uniforms.shape[0] != n_rows * ns:
                     raise ValueError(f"uniforms must hold n_rows*n_samples = {n_rows * ns} variates, got {uniforms.shape[0]}")
             self._inputs = (d_e, d_w, n_rows, ns, d_ids, rt.upload(uniforms) if uniforms is not None else None, seed)
-            self._table = rt.empty(n_rows * N.COMPTON_NP)
+            self._table = rt.empty_block(n_rows * N.COMPTON_NP)
         return self._inputs
 
     def _launch_rows(self):
@@ -670,7 +670,7 @@ class FluxBremIsotropic(_ChainFlux):
         rt = self._rt
         gx, gw = P.gauss_legendre()
         with rt.activate():
-            table = rt.empty(n_rows * N.BREM_NP)
+            table = rt.empty_block(n_rows * N.BREM_NP)
             emit = torch.zeros(n_rows, dtype=torch.uint8, device=rt.device)
             ids = (rows + int(self.row_offset)).astype(np.uint32)
             d_ids = rt.upload(ids, np.uint32)
@@ -836,7 +836,7 @@ class FluxPairAnnihilationIsotropic(_ChainFlux):
                 if u.shape[0] != 2 * n_rows * ns:
                     raise ValueError(f"uniforms must hold 2*n_rows*n_samples = {2 * n_rows * ns} variates")
                 d_u = rt.upload(u)
-            table = rt.empty(n_rows * N.PAIRANN_NP)
+            table = rt.empty_block(n_rows * N.PAIRANN_NP)
             d_ids = rt.upload((rows + int(self.row_offset)).astype(np.uint32), np.uint32)
             if n_rows:
                 d_e, d_w = rt.upload(pf[keep, 0]), rt.upload(pf[keep, 1])

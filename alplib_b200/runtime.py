@@ -57,6 +57,16 @@ class Runtime:
     def empty(self, n, dtype=torch.float64):
         return torch.empty(int(n), dtype=dtype, device=self.device)
 
+    def empty_block(self, n, dtype=torch.float64):
+        """Like empty() for per-call work buffers of 0.1-1 MB (row tables, staging blocks): the request is padded past
+        1 MiB so that PyTorch's caching allocator serves it from its large pool.  Its small pool (2 MiB segments) was
+        measured to stall such allocations for 1-4 ms every other step once multi-GB blocks are cached
+        (tools/dbg_fused3.py); HBM is not the scarce resource here."""
+        item = torch.empty(0, dtype=dtype).element_size()
+        n = int(n)
+        pad = max(n, ((1 << 20) + 512 + item - 1) // item)
+        return torch.empty(pad, dtype=dtype, device=self.device)[:n]
+
     def zeros(self, n, dtype=torch.float64):
         return torch.zeros(int(n), dtype=dtype, device=self.device)
 
@@ -84,7 +94,7 @@ class Runtime:
             n = int(a.shape[0])
             if n:
                 np.copyto(hnp[o:o + n * np.dtype(dt).itemsize].view(dt), a, casting="unsafe")
-        dev = torch.empty(total, dtype=torch.uint8, device=self.device)
+        dev = self.empty_block(total, torch.uint8)
         dev.copy_(hbuf[:total], non_blocking=True)
         ev.record(torch.cuda.current_stream(self.device))
         return [dev[o:o + int(a.shape[0]) * np.dtype(dt).itemsize].view(_TORCH_DTYPE[np.dtype(dt)])
@@ -108,7 +118,7 @@ class Runtime:
         n, stride = int(table.shape[0]), int(table.shape[1])
         cap = ((n * 8 + 255) & ~255) * 2 + n * 4
         hbuf, ev, _ = self._pin_slot(cap)
-        dev = torch.empty(max(cap, 1), dtype=torch.uint8, device=self.device)
+        dev = self.empty_block(max(cap, 1), torch.uint8)
         nk, ow, oi = C.c_uint64(), C.c_uint64(), C.c_uint64()
         N.call("alpk_stage_flux_rows", C.c_void_p(table.ctypes.data), n, stride, int(rule), float(cut), int(row_offset),
                C.c_void_p(hbuf.data_ptr()), int(hbuf.shape[0]), C.c_void_p(dev.data_ptr()), C.byref(nk), C.byref(ow),

@@ -294,6 +294,7 @@ def run_gpu(args):
     for tag, fused in (("e2e", None), ("e2e_eager", False), ("e2e_fused", True)):
         # warm-up: the first eager steps pay cudaMalloc; the first ~30 deferred steps after a materialising phase show
         # allocator/driver hiccups of several ms every other step (tools/dbg_fused.py) before settling
+        torch.cuda.empty_cache()              # give the previous schedule's multi-GB sample blocks back to the driver
         for _ in range(40 if fused is not False else 8):
             res = e2e_step(fused)
         del res
