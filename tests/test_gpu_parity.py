@@ -1038,3 +1038,28 @@ def test_meson3body_free_running(A):
     ref = [O.meson3_dgamma_dea(e, O.M_MU, 5.0, O.M_K, O.F_K, O.V_US, "scalar_ib1", -0.97, 1e-3) for e in (10.0, 100.0, 200.0)]
     assert max_rel(d, ref) < TOL
     assert a.total_br() > 0
+
+
+def test_propagate_edge_energies(A):
+    """The straight-line fast path must hand samples outside its domain to the general code: E_a == m_a (v = 0), E_a < m_a
+    (NaN momentum), exponents far below -708, stable ALPs, huge energies -- element by element against the oracle, NaNs
+    included, for odd and even lengths (scalar tail of the pair kernel)."""
+    ma = 2.0
+    e = np.array([ma, np.nextafter(ma, 3.0), ma * (1 + 1e-9), 0.5 * ma, 2.5, 10.0, 1e3, 1e8, 1e150, 3.0, 7.0])
+    w = np.array([1.0, 2.0, 3.0, 4.0, 5e3, 6e-3, 7.0, 8.0, 9.0, 0.0, 1e300])
+    for n in (e.shape[0], e.shape[0] - 1):
+        for width in (0.0, 1e-20, 1e-12, 1e-6, 1.0):
+            fl = A.FluxComptonIsotropic(np.array([[5.0, 1e9]]), A.Material("W"), axion_mass=ma, axion_coupling=1e-6,
+                                        n_samples=2, keep_f64=True, **GEOM)
+            fl.axion_energy = list(e[:n])
+            fl.axion_flux = list(w[:n])
+            A.AxionFlux.propagate(fl, width, 1.5)
+            with np.errstate(all="ignore"):
+                p = O.propagate(e[:n], w[:n], ma, width, 1.5, 4.0, 0.2)
+            d, s_ = fl.decay_axion_weight_f64, fl.scatter_axion_weight_f64
+            assert np.array_equal(np.isnan(s_), np.isnan(p["scatter_w64"])), (n, width, s_, p["scatter_w64"])
+            assert np.array_equal(np.isnan(d), np.isnan(p["decay_w64"])), (n, width, d, p["decay_w64"])
+            ok = ~np.isnan(p["scatter_w64"])
+            assert max_rel(s_[ok], p["scatter_w64"][ok]) < TOL, (n, width)
+            okd = ~np.isnan(p["decay_w64"])
+            assert_decay_close(d[okd], p["decay_w64"][okd], p["scatter_w64"][okd], TOL)
