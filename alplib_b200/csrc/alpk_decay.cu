@@ -348,6 +348,9 @@ vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __re
                const double* __restrict__ bden, const double* __restrict__ jac, uint32_t n_points, uint32_t chunk,
                double ma, double ma2, double width, double inv_mbm, double* __restrict__ partials) {
     __shared__ double s_x[kVolTile], s_b[kVolTile], s_j[kVolTile];
+    __shared__ double s_tab[64];                     // exp_fast table
+    __shared__ unsigned long long s_xmax_bits;       // fast mode: largest |x| of the staged tile (ordered bits)
+    if (FAST && threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t k0 = blockIdx.y * chunk;
     const uint32_t k1 = (k0 + chunk < n_points) ? k0 + chunk : n_points;
@@ -366,15 +369,35 @@ vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __re
     for (uint32_t t0 = k0; t0 < k1; t0 += kVolTile) {
         const uint32_t cnt = (t0 + kVolTile <= k1) ? kVolTile : k1 - t0;
         __syncthreads();
+        if (FAST && threadIdx.x == 0) s_xmax_bits = 0ull;
+        __syncthreads();
+        unsigned long long my_max = 0ull;
         for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
-            s_x[k] = __ldg(nxm + t0 + k); s_b[k] = __ldg(bden + t0 + k); s_j[k] = __ldg(jac + t0 + k);
+            const double x = __ldg(nxm + t0 + k), b = __ldg(bden + t0 + k), j = __ldg(jac + t0 + k);
+            s_x[k] = x; s_b[k] = b; s_j[k] = j;
+            if (FAST) {
+                s_b[k] = j / b;                      // fast mode: the per-point factor jacobian / (4 pi l^2), one division per point
+                const double ax = fabs(x);           // (NaN -> +inf: no straight-line loop for this tile)
+                const unsigned long long xb = (ax == ax) ? (unsigned long long)__double_as_longlong(ax) : 0x7ff0000000000000ull;
+                my_max = xb > my_max ? xb : my_max;
+            }
         }
+        if (FAST && my_max) atomicMax(&s_xmax_bits, my_max);
         __syncthreads();
         if (live) {
+            if (FAST && c * __longlong_as_double((long long)s_xmax_bits) <= 708.0) {
+                // every exponent of the tile lies in [-708, 0]: straight-line body, four points in flight
 #pragma unroll 4
-            for (uint32_t k = 0; k < cnt; ++k) {
-                const double e = FAST ? exp_fast(s_x[k] * c) : exp((s_x[k] / va) / tau);      // :85
-                acc += s_j[k] * ((A * e) / s_b[k]);
+                for (uint32_t k = 0; k < cnt; ++k) acc += (A * exp_fast_core(s_x[k] * c, s_tab)) * s_b[k];
+            } else if (FAST) {
+#pragma unroll 2
+                for (uint32_t k = 0; k < cnt; ++k) acc += (A * exp_fast(s_x[k] * c)) * s_b[k];
+            } else {
+#pragma unroll 4
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    const double e = exp((s_x[k] / va) / tau);                                // :85
+                    acc += s_j[k] * ((A * e) / s_b[k]);
+                }
             }
         }
     }
