@@ -310,6 +310,38 @@ ALP_HD double icompton_sigma(double ea, const IComptonConst& c) {
     return r;
 }
 
+// Fast mode of the two detection cross sections (<= 1e-9 relative from the reference expressions above): the seven
+// divisions of icompton_sigma become four reciprocals (hardware seed + one correction,
+// no special-case branches); samples outside the straight-line domain (E_a <= m_a, below threshold) take the reference
+// expression, which also reproduces its nan_to_num corner cases.
+ALP_HD double icompton_sigma_fast(double ea, const IComptonConst& c) {
+    const double d = ea * ea - c.ma2;
+    if (!(d > 1e-290) || !(ea < 1e140) || !(ea > 0.0)) return icompton_sigma(ea, c);       // (rare: keeps warps converged)
+    const double me = kME, me2 = kME * kME;
+    const double y = (2 * me) * ea + c.ma2;
+    // p_a keeps its correctly rounded square root: (m_e + E_a) - p_a cancels by a factor ~E_a/m_e, so an ulp of p_a would be
+    // amplified beyond 1e-9 above ~1 TeV; with the same p_a the difference is the reference's, bit for bit
+    const double pa = sqrt(d);
+    const double r_pa = rcp_fast(pa);
+    const double m2y = me2 + y;
+    const double r_y = rcp_fast(y), r_m = rcp_fast(m2y);
+    const double A = me + ea;
+    const double tme = (2 * me) * ea, tmp = (2 * me) * pa;
+    const double t1 = ((((2 * me2) * A) * y) * r_m) * r_m;
+    const double t2 = (((4 * me) * (c.c2 - tme * tme)) * r_y) * r_m;
+    const double t3 = ((log((A + pa) * rcp_fast(A - pa)) * (tmp * tmp + c.ma4)) * r_pa) * r_y;
+    // below threshold the reference's prefactor is heaviside(.) * zfac / (8 p_a) = 0 and nan_to_num maps 0 * (anything) to 0
+    return ea > c.ethr ? ((c.zfac * 0.125) * r_pa) * ((t1 + t2) + t3) : 0.0;
+}
+
+ALP_HD double iprimakoff_sigma_fast(double ea, double ma, double ma2, double pref, double r02) {
+    const double eta2 = r02 * (ea * ea - ma2);
+    // (eta2 << 1, i.e. within ~1e-8 of threshold: the bracket cancels like 1/eta2 and amplifies the last bit of the
+    // quotient -- keep the reference's own division there)
+    if (!(ea > ma) || !(eta2 > 1e-2) || !(eta2 < 1e140)) return iprimakoff_sigma(ea, ma, ma2, pref, r02);
+    return pref * (((2 * eta2 + 1) * (0.25 * rcp_fast(eta2))) * log(1 + 4 * eta2) - 1);
+}
+
 // ---- Compton production: per-bin constants (prod_xs.py:155-169, fluxes.py:210-224) -----------------------------------
 // Layout of one row of the per-bin parameter table (doubles).
 enum ComptonBin { CB_EG = 0, CB_SPAN, CB_C0, CB_XMIN, CB_XMAX, CB_P, CB_K, CB_S, CB_SIGABS, CB_PHI, CB_Q, CB_INVEG, CB_NP };

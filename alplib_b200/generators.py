@@ -91,6 +91,8 @@ class _EventGenerator:
             raise ValueError("propagate() must run first: scatter_axion_weight does not match axion_energy")
         self._need_f32(fl._S32, "scatter_axion_weight")
         ev = P.event_params(days_exposure, threshold)
+        if fl.precision != "faithful":
+            kind += 2                               # fast arithmetic mode of the cross section (include/alpk.h)
         with rt.activate():
             rate = rt.empty(1)
             evw = rt.empty(n) if self.materialize_weights else None

@@ -102,7 +102,8 @@ int alpk_decays(const double* energy, const float* decay_w32, uint64_t n, const 
                 double* event_w_or_null, double* rate, double* scratch, void* stream);
 
 /* scatter channels: kind 0 = inverse Compton (generators.py:41-46, det_xs.py:89-98),
- *                   kind 1 = inverse Primakoff (generators.py:80-86, det_xs.py:37-42).
+ *                   kind 1 = inverse Primakoff (generators.py:80-86, det_xs.py:37-42);
+ *                   kind 2 / 3 = the same two in the fast arithmetic mode (<= 1e-9 relative: reciprocals instead of divisions).
  * h_xs: kind 0 -> {ma, ma**2, ma**4, e_thr, z*ALPHA*(g/M_E)**2, ma**4 + 2 (ma M_E)**2}
  *       kind 1 -> {ma, ma**2, (g z)**2/(2*137), r0**2, 0, 0}
  * prefactor = ntargets/det_area (applied after days*S_PER_DAY), mbm2 = METER_BY_MEV**2. */

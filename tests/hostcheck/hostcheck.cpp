@@ -89,7 +89,11 @@ void hc_scatter(int kind, const double* e, const float* w32, uint64_t n, const d
     IComptonConst ic{xs[0], xs[1], xs[2], xs[3], xs[4], xs[5]};
     const double lead = c.days_sec * prefactor;
     for (uint64_t i = 0; i < n; ++i) {
-        const double s = kind == 0 ? icompton_sigma(e[i], ic) : iprimakoff_sigma(e[i], xs[0], xs[1], xs[2], xs[3]);
+        double s;
+        if (kind == 0) s = icompton_sigma(e[i], ic);
+        else if (kind == 1) s = iprimakoff_sigma(e[i], xs[0], xs[1], xs[2], xs[3]);
+        else if (kind == 2) s = icompton_sigma_fast(e[i], ic);
+        else s = iprimakoff_sigma_fast(e[i], xs[0], xs[1], xs[2], xs[3]);
         out[i] = (((lead * s) * mbm2) * (double)w32[i]) * heaviside(e[i] - c.threshold, 1.0);
     }
 }
