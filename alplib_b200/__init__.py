@@ -8,11 +8,12 @@ ElectronEventGenerator, Material, the decay widths and the constants -- same nam
 """
 from .constants import *            # noqa: F401,F403
 from .materials import Material, DetectorGeometry     # noqa: F401
-from .decay import W_gg, W_ee, W_ff, W_gg_loop, fp2, b1   # noqa: F401
+from .decay import W_gg, W_ee, W_ff, W_gg_loop, W_agg_hadronic, fp2, b1   # noqa: F401
 from .photon_xs import AbsCrossSection, ALPPairProdutionCrossSection   # noqa: F401
 from .vectors import Vector3, LorentzVector, LorentzVectorArray   # noqa: F401
 from .fluxes import *               # noqa: F401,F403
-from .meson_fluxes import FluxChargedMeson3BodyIsotropic, FluxChargedMeson3BodyDecay, M2Meson3BodyDecay   # noqa: F401
+from .meson_fluxes import (FluxChargedMeson3BodyIsotropic, FluxChargedMeson3BodyDecay, M2Meson3BodyDecay,   # noqa: F401
+                           FluxAxionMesonMixing)
 from .generators import PhotonEventGenerator, ElectronEventGenerator   # noqa: F401
 
 __version__ = "0.1.0"

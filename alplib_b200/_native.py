@@ -167,6 +167,7 @@ _SIGNATURES = {
     "alpk_meson3_samples": ([_I, _P, _U64, _U32, C.POINTER(Meson3T), _D, _I, _P, _P, _U64, _U32, _P, _P, _P, _P, _P, _P,
                              _P, _P], _I),
     "alpk_meson3_dgamma": ([_P, _U64, _D, C.POINTER(Meson3T), _P, _P], _I),
+    "alpk_meson_mixing": ([_P, _U64, _D, _D, _D, _P, _P, _P, _P, _P], _I),
     "alpk_meson3_m2": ([_D, _P, _U64, _D, C.POINTER(Meson3T), _P, _P], _I),
     "alpk_pairgamma": ([_P, _P, _U64, _U32, _P, _P, _P, _I, C.POINTER(PairGammaT), _P, _P, _U64, _P, _P, _P], _I),
     "alpk_scale": ([_P, _U64, _D, _P, _P], _I),

@@ -21,6 +21,8 @@ M_P = 938.0                            # constants.py:33
 M_MU = 105.658369                      # constants.py:34
 M_PI = 139.57                          # constants.py:41
 M_PI0 = 134.98                         # constants.py:42
+M_ETA = 547.862                        # constants.py:43
+M_ETA_PRIME = 957.78                   # constants.py:44
 M_K = 493.677                          # constants.py:53  charged kaon
 G_F = 1.16638e-11                      # constants.py:73  MeV^-2
 CABIBBO = 0.9743                       # constants.py:74

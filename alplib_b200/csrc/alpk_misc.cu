@@ -75,6 +75,21 @@ pairgamma_kernel(const double* __restrict__ centers, const double* __restrict__ 
     }
 }
 
+// fluxes.py:1202-1224 FluxAxionMesonMixing.simulate: one ALP per meson 4-vector [E, px, py, pz] that is above the mass and
+// inside the detector's half opening angle; every kept sample carries the same rate
+__global__ void __launch_bounds__(kThreads)
+meson_mixing_kernel(const double* __restrict__ p4, uint64_t n, double ma, double det_sa, double rate,
+                    double* __restrict__ out_e, double* __restrict__ out_angle, double* __restrict__ out_f,
+                    uint8_t* __restrict__ keep) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = __ldg(p4 + 4 * i), px = __ldg(p4 + 4 * i + 1), py = __ldg(p4 + 4 * i + 2), pz = __ldg(p4 + 4 * i + 3);
+        const double angle = acos(pz / sqrt((px * px + py * py) + pz * pz));          // :1214
+        out_e[i] = e; out_angle[i] = angle; out_f[i] = rate;
+        keep[i] = (!(e < ma) && !(angle > det_sa)) ? 1 : 0;                           // :1211-1217
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 scale_kernel(const double* __restrict__ x, uint64_t n, double factor, double* __restrict__ out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -99,6 +114,15 @@ ALPK_EXPORT int alpk_pairgamma(const double* centers, const double* widths, uint
     pairgamma_kernel<<<grid_for(n_bins * (uint64_t)n_samples, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
         centers, widths, n_bins, n_samples, bin_ids, pos_e, pos_f, n_pos, g, u_bins, u_alp, seed, out_energy, out_flux);
     return check_launch("alpk_pairgamma");
+}
+
+ALPK_EXPORT int alpk_meson_mixing(const double* p4, uint64_t n, double ma, double det_sa, double rate, double* out_energy,
+                                  double* out_angle, double* out_flux, uint8_t* keep, void* stream) {
+    if (n == 0) return 0;
+    if (!p4 || !out_energy || !out_angle || !out_flux || !keep) { set_error("alpk_meson_mixing: null argument"); return 2; }
+    meson_mixing_kernel<<<grid_for(n, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(p4, n, ma, det_sa, rate, out_energy,
+                                                                                        out_angle, out_flux, keep);
+    return check_launch("alpk_meson_mixing");
 }
 
 ALPK_EXPORT int alpk_scale(const double* x, uint64_t n, double factor, double* out, void* stream) {

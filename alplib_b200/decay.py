@@ -37,3 +37,17 @@ def W_gg_loop(g_af, ma, mf):
     """a -> gamma gamma through a fermion loop (decay.py:48-52)."""
     g_agamma_eff = g_af * ALPHA * b1(power(2*mf/ma, 2)) / (4*pi)
     return W_gg(g_agamma_eff, ma)
+
+
+_GLUDOM = None
+
+
+def W_agg_hadronic(f_a, ma):
+    """a -> hadrons total width from the tabulated gluon-dominance widths (decay.py:65-72); f_a, ma in MeV."""
+    global _GLUDOM
+    if _GLUDOM is None:
+        from .materials import data_path
+        _GLUDOM = np.genfromtxt(data_path("gluon_dominance_widths_nogamma.txt"))
+    eV_fact = 1e-9
+    Lambda_scale = (32 * pi**2 * f_a / 1e6)**2  # data is normalized to an EFT scale of 1 TeV
+    return np.interp(ma*1e-3, _GLUDOM[:, 0], _GLUDOM[:, 1]) * eV_fact / Lambda_scale

@@ -22,12 +22,13 @@ import torch
 from numpy import arctan, cos, pi, power, sqrt
 
 from . import _native as N
-from .constants import F_K, F_PI, KAON_WIDTH, M_E, M_K, M_MU, M_PI, PION_WIDTH, V_UD, V_US
-from .decay import W_ff, W_gg
+from .constants import (ALPHA, F_K, F_PI, KAON_WIDTH, M_E, M_ETA, M_ETA_PRIME, M_K, M_MU, M_PI, M_PI0, PION_WIDTH, V_UD,
+                        V_US)
+from .decay import W_agg_hadronic, W_ff, W_gg
 from .fluxes import AxionFlux, _draw_seed, _split_kwargs
 from .materials import Material
 
-__all__ = ["FluxChargedMeson3BodyIsotropic", "FluxChargedMeson3BodyDecay", "M2Meson3BodyDecay"]
+__all__ = ["FluxChargedMeson3BodyIsotropic", "FluxChargedMeson3BodyDecay", "M2Meson3BodyDecay", "FluxAxionMesonMixing"]
 
 _MODELS = ["scalar_ib1", "pseudoscalar_ib1", "vector_ib1", "scalar_ib2", "vector_ib2", "vector_ib9", "sd", "vector_contact"]
 _PARAMS = {"pion": [M_PI, V_UD, F_PI, PION_WIDTH], "kaon": [M_K, V_US, F_K, KAON_WIDTH]}      # fluxes.py:612-615
@@ -341,3 +342,108 @@ class FluxChargedMeson3BodyDecay(_Meson3Flux):
             self._D32, self._S32 = d, s_
             for k in ("D32", "S32"):
                 self._host.pop(k, None)
+
+
+class FluxAxionMesonMixing(AxionFlux):
+    """
+    ALP flux from pi0 / eta mixing (reference: fluxes.py:1148-1240, after Kelly, Kumar, Liu 2011.05995); f_a in MeV.
+    meson_flux rows are 4-vectors [E, px, py, pz]; a meson above the ALP mass and inside the detector's half opening angle
+    becomes one ALP of the same energy with the mixing-suppressed rate.
+    """
+    def __init__(self, meson_flux=None, meson_mass=M_PI0, target=None,
+                 det_dist=574.0, det_length=5.0, det_area=21.0,
+                 axion_mass=0.1, f_a=1000.0, meson_type="Pi0", total_pot=1e21,
+                 n_samples=1, mesons_per_pot=2.89, c1=1.0, c2=1.0, c3=1.0, **kwargs):
+        self.c1 = c1
+        self.c2 = c2
+        self.c3 = c3
+        self.f_a = f_a
+        target = Material("C") if target is None else target
+        super().__init__(axion_mass, target, det_dist, det_length, det_area, **_split_kwargs(kwargs))
+        self.axion_coupling = self.photon_coupling(f_a)
+        self.meson_flux = meson_flux
+        self.n_samples = n_samples
+        self.support = np.ones(n_samples)
+        self.meson_mass = meson_mass
+        self.mesons_per_pot = mesons_per_pot
+        self.total_pot = total_pot
+        self.meson_norm_wgt = 1.0/meson_flux.shape[0]
+        self.meson_type = meson_type
+        self._angle = None
+
+    def photon_coupling(self, f_a):
+        # ma < QCD scale
+        c_gamma = self.c2 + (5/3)*self.c1 + self.c3 * (
+            -1.92
+            + (1/3) * (self.ma**2 / (self.ma**2 - M_PI0**2))
+            + (8/9) * ((self.ma**2 - (4/9)*M_PI0**2) / (self.ma**2 - M_ETA**2))
+            + (7/9) * ((self.ma**2 - (16/9)*M_PI0**2) / (self.ma**2 - M_ETA_PRIME**2))
+        )
+        return c_gamma * ALPHA / (2 * pi * f_a)  # in MeV^-1
+
+    def set_new_coupling(self, f_a):
+        self.f_a = f_a
+        self.axion_coupling = self.photon_coupling(f_a)
+
+    def mixing(self):
+        if self.meson_type == "Pi0":
+            return (1/6) * (F_PI/self.f_a) * (self.ma**2 / (self.ma**2 - M_PI0**2))
+        elif self.meson_type == "Eta":
+            return (1/sqrt(6)) * (F_PI/self.f_a) * ((self.ma**2 - 4*M_PI0**2 / 9) / (self.ma**2 - M_ETA**2))
+
+    def phase_space_factor(self):
+        if self.ma <= self.meson_mass:
+            return 1.0
+        return np.power(self.ma / self.meson_mass, -1.6)
+
+    @property
+    def axion_angle(self):
+        self._ensure_production()
+        t = getattr(self, "_angle", None)
+        if t is None:
+            return []
+        h = self._host.get("angle")
+        if h is None:
+            h = self._host["angle"] = t.cpu().numpy()
+        return h
+
+    @axion_angle.setter
+    def axion_angle(self, v):
+        if isinstance(v, list) and not v:
+            self._angle = None
+            return
+        self._angle = self._rt.upload(np.asarray(v, dtype=np.float64).ravel())
+        if hasattr(self, "_host"):
+            self._host.pop("angle", None)
+
+    def simulate(self):
+        self._reset_samples()
+        self._angle = None
+        mf = np.ascontiguousarray(np.asarray(self.meson_flux, dtype=np.float64))
+        if mf.ndim != 2 or mf.shape[1] < 4:
+            raise IndexError("meson_flux must have shape (n, 4): rows of [E, px, py, pz]")
+        mf = np.ascontiguousarray(mf[:, :4])
+        n = int(mf.shape[0])
+        rate = self.total_pot * self.mesons_per_pot * self.meson_norm_wgt \
+            * self.phase_space_factor() * (self.mixing())**2                         # fluxes.py:1222-1223
+        rt = self._rt
+        with rt.activate():
+            E, Th, F = rt.empty(n), rt.empty(n), rt.empty(n)
+            if n:
+                keep = torch.zeros(n, dtype=torch.uint8, device=rt.device)
+                d_m = rt.upload(mf.ravel())
+                N.call("alpk_meson_mixing", N.ptr(d_m), n, float(self.ma), float(self.det_sa()), float(rate), N.ptr(E),
+                       N.ptr(Th), N.ptr(F), N.ptr(keep), rt.stream())
+                sel = torch.nonzero(keep, as_tuple=False).ravel()
+                E, Th, F = (t.index_select(0, sel).contiguous() for t in (E, Th, F))
+        self._set_production(E, F)
+        self._angle = Th
+
+    def propagate(self, new_fa=None):
+        """fluxes.py:1226-1236 (without new_fa the reference propagates with the photon width only)."""
+        if new_fa is not None:
+            total_width = W_gg(self.photon_coupling(new_fa), self.ma) + W_agg_hadronic(new_fa, self.ma)
+            rescale = power(self.f_a/new_fa, 2)
+            super().propagate(total_width, rescale)
+        else:
+            super().propagate(W_gg(self.axion_coupling, self.ma))

@@ -356,6 +356,10 @@ int alpk_meson3_samples(int mode, const double* row_table, uint64_t n_rows, uint
                         double* out_theta, double* out_solid_angle, double* out_decay_pos, uint8_t* keep, void* stream);
 /* dGammadEa(E_a, ml) (fluxes.py:639-661 / 841-863) on an array of energies */
 int alpk_meson3_dgamma(const double* ea, uint64_t n, double lepton_mass, const alpk_meson3_t* h_par, double* out, void* stream);
+/* FluxAxionMesonMixing.simulate (fluxes.py:1202-1224): p4[n][4] = {E, px, py, pz}; writes E, the polar angle and the
+ * (constant) rate per meson, keep[i] = 1 for mesons with E >= m_a inside the half opening angle det_sa. */
+int alpk_meson_mixing(const double* p4, uint64_t n, double ma, double det_sa, double rate, double* out_energy,
+                      double* out_angle, double* out_flux, uint8_t* keep, void* stream);
 /* M2Meson3BodyDecay.__call__(m122, m232) (matrix_element.py:443-518) on an array of m232 */
 int alpk_meson3_m2(double m122, const double* m232, uint64_t n, double lepton_mass, const alpk_meson3_t* h_par, double* out,
                    void* stream);

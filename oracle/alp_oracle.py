@@ -996,3 +996,45 @@ def charged_meson_decay_simulate(meson_flux, ma, coupling, meson_type, model, n_
     res = {k: np.array(v, dtype=np.float64) for k, v in out.items()}
     res["positions"] = np.array(positions)
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# FluxAxionMesonMixing (fluxes.py:1148-1240)
+# ---------------------------------------------------------------------------------------------------------
+M_ETA = 547.862                       # constants.py:43
+M_ETA_PRIME = 957.78                  # constants.py:44
+
+
+def meson_mixing_photon_coupling(ma, f_a, c1=1.0, c2=1.0, c3=1.0):                  # fluxes.py:1176-1185
+    c_gamma = c2 + (5/3)*c1 + c3 * (
+        -1.92
+        + (1/3) * (ma**2 / (ma**2 - M_PI0**2))
+        + (8/9) * ((ma**2 - (4/9)*M_PI0**2) / (ma**2 - M_ETA**2))
+        + (7/9) * ((ma**2 - (16/9)*M_PI0**2) / (ma**2 - M_ETA_PRIME**2))
+    )
+    return c_gamma * ALPHA / (2 * pi * f_a)
+
+
+def W_agg_hadronic(f_a, ma):                                                         # decay.py:67-72
+    data = np.genfromtxt(os.path.join(_DATA_DIR, "gluon_dominance_widths_nogamma.txt"))
+    return np.interp(ma*1e-3, data[:, 0], data[:, 1]) * 1e-9 / (32 * pi**2 * f_a / 1e6)**2
+
+
+def meson_mixing_simulate(meson_flux, ma, f_a, meson_mass, meson_type, total_pot, mesons_per_pot, det_dist, det_area):
+    """FluxAxionMesonMixing.simulate (fluxes.py:1202-1224): (energy, angle, flux)."""
+    if meson_type == "Pi0":
+        mixing = (1/6) * (F_PI/f_a) * (ma**2 / (ma**2 - M_PI0**2))
+    else:
+        mixing = (1/np.sqrt(6)) * (F_PI/f_a) * ((ma**2 - 4*M_PI0**2 / 9) / (ma**2 - M_ETA**2))
+    psf = 1.0 if ma <= meson_mass else np.power(ma / meson_mass, -1.6)
+    det_sa = np.arctan(np.sqrt(det_area / pi) / det_dist)                            # fluxes.py:40-41
+    e_, th_, f_ = [], [], []
+    for m in meson_flux:
+        if m[0] < ma:
+            continue
+        angle = np.arccos(m[3]/np.sqrt(m[1]**2 + m[2]**2 + m[3]**2))
+        if angle > det_sa:
+            continue
+        e_.append(m[0]); th_.append(angle)
+        f_.append(total_pot * mesons_per_pot * (1.0/meson_flux.shape[0]) * psf * mixing**2)
+    return np.array(e_), np.array(th_), np.array(f_)

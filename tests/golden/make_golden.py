@@ -575,6 +575,46 @@ def case_meson3body():
          n_cases=k, **dec)
 
 
+def case_meson_mixing():
+    """FluxAxionMesonMixing (fluxes.py:1148-1240): pi0 and eta mixing, energy / angle filters, both propagate branches."""
+    print("axion-meson mixing")
+    rs = np.random.RandomState(77)
+    n = 400
+    pz = 10 ** rs.uniform(1.5, 4, n)
+    pt = pz * 10 ** rs.uniform(-4, -1.2, n)
+    phi = rs.uniform(0, 2 * np.pi, n)
+    out = {}
+    k = 0
+    for mtype, mmass, ma, fa in (("Pi0", O.M_PI0, 20.0, 1e5), ("Pi0", O.M_PI0, 300.0, 3e4), ("Eta", O.M_ETA, 700.0, 1e6),
+                                 ("Eta", O.M_ETA, 90.0, 2e5)):
+        e = np.sqrt(pz ** 2 + pt ** 2 + mmass ** 2) * np.where(rs.random_sample(n) < 0.1, 1e-3, 1.0)   # some below the ALP mass
+        mf = np.stack([e, pt * np.cos(phi), pt * np.sin(phi), pz], axis=1)
+        fl = F.FluxAxionMesonMixing(meson_flux=mf, meson_mass=mmass, axion_mass=ma, f_a=fa, meson_type=mtype,
+                                    det_dist=574.0, det_length=5.0, det_area=21.0)
+        fl.simulate()
+        oE, oT, oF = O.meson_mixing_simulate(mf, ma, fa, mmass, mtype, 1e21, 2.89, 574.0, 21.0)
+        check(f"mixing {mtype} ma={ma} E", oE, fl.axion_energy, 0.0)
+        check(f"mixing {mtype} ma={ma} angle", oT, fl.axion_angle, 0.0)
+        check(f"mixing {mtype} ma={ma} flux", oF, fl.axion_flux, 0.0)
+        assert 0 < len(fl.axion_energy) < n
+        assert abs(O.meson_mixing_photon_coupling(ma, fa) / fl.axion_coupling - 1) < 1e-15
+        d64, s64, d32, s32 = propagate_both(fl)
+        new_fa = 2.5 * fa
+        with f32_cast_bypassed():
+            fl.propagate(new_fa)
+            d64n = np.array(fl.decay_axion_weight, dtype=np.float64); s64n = np.array(fl.scatter_axion_weight, dtype=np.float64)
+        assert abs(O.W_agg_hadronic(new_fa, ma) / F.W_agg_hadronic(new_fa, ma) - 1) < 1e-15 if F.W_agg_hadronic(new_fa, ma) else True
+        t = f"c{k}"
+        out[t + "_cfg"] = np.array([0 if mtype == "Pi0" else 1, mmass, ma, fa, new_fa])
+        out[t + "_mf"] = mf
+        out[t + "_E"] = np.array(fl.axion_energy); out[t + "_T"] = np.array(fl.axion_angle); out[t + "_F"] = np.array(fl.axion_flux)
+        out[t + "_d64"] = d64; out[t + "_s64"] = s64; out[t + "_d32"] = d32; out[t + "_s32"] = s32
+        out[t + "_d64n"] = d64n; out[t + "_s64n"] = s64n
+        out[t + "_g"] = np.array([fl.axion_coupling, F.W_agg_hadronic(new_fa, ma)])
+        k += 1
+    save("meson_mixing", n_cases=k, **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                      # regenerate selected cases only: python make_golden.py case_meson3body
         for name in sys.argv[1:]:
@@ -593,4 +633,5 @@ if __name__ == "__main__":
     case_pairgamma()
     case_general_decay()
     case_meson3body()
+    case_meson_mixing()
     print("all golden fixtures written; oracle pinned against the reference")

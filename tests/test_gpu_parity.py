@@ -1063,3 +1063,25 @@ def test_propagate_edge_energies(A):
             assert max_rel(s_[ok], p["scatter_w64"][ok]) < TOL, (n, width)
             okd = ~np.isnan(p["decay_w64"])
             assert_decay_close(d[okd], p["decay_w64"][okd], p["scatter_w64"][okd], TOL)
+
+
+def test_axion_meson_mixing(A):
+    """FluxAxionMesonMixing: energy / angle filters on the device, both propagate branches (photon width; photon + hadronic)."""
+    g = load_golden("meson_mixing")
+    for k in range(int(g["n_cases"])):
+        mt, mmass, ma, fa, new_fa = g[f"c{k}_cfg"]
+        fl = A.FluxAxionMesonMixing(meson_flux=g[f"c{k}_mf"], meson_mass=float(mmass), axion_mass=float(ma), f_a=float(fa),
+                                    meson_type=["Pi0", "Eta"][int(mt)], keep_f64=True)
+        fl.simulate()
+        assert np.array_equal(fl.axion_energy, g[f"c{k}_E"])
+        assert max_rel(fl.axion_angle, g[f"c{k}_T"]) < 1e-13
+        assert max_rel(fl.axion_flux, g[f"c{k}_F"]) < 1e-15
+        assert fl.axion_coupling == pytest.approx(float(g[f"c{k}_g"][0]), rel=1e-15)
+        fl.propagate()
+        assert max_rel(fl.scatter_axion_weight_f64, g[f"c{k}_s64"]) < TOL
+        assert_decay_close(fl.decay_axion_weight_f64, g[f"c{k}_d64"], g[f"c{k}_s64"], TOL)
+        assert max_rel(fl.scatter_axion_weight, g[f"c{k}_s32"], floor=1e-44) <= F32
+        fl.propagate(float(new_fa))
+        assert max_rel(fl.scatter_axion_weight_f64, g[f"c{k}_s64n"]) < TOL
+        assert_decay_close(fl.decay_axion_weight_f64, g[f"c{k}_d64n"], g[f"c{k}_s64n"], TOL)
+        assert A.PhotonEventGenerator(fl, A.Material("Ar")).decays(100, 0.0) >= 0.0

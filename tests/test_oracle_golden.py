@@ -289,3 +289,19 @@ def test_meson3body_decay_oracle():
         for key in ("energy", "cosine", "flux", "angle", "solid_angle", "decay_pos"):
             assert np.array_equal(r[key], g[f"c{k}_{key}"]), (k, key)
     assert n_dead > 0                                                  # some mesons decay beyond the dump
+
+
+def test_meson_mixing_oracle():
+    """FluxAxionMesonMixing (fluxes.py:1148-1240) restated: filters, constant rate, photon coupling, hadronic width."""
+    g = load_golden("meson_mixing")
+    for k in range(int(g["n_cases"])):
+        mt, mmass, ma, fa, new_fa = g[f"c{k}_cfg"]
+        E, T, F = O.meson_mixing_simulate(g[f"c{k}_mf"], float(ma), float(fa), float(mmass), ["Pi0", "Eta"][int(mt)], 1e21, 2.89,
+                                          574.0, 21.0)
+        assert np.array_equal(E, g[f"c{k}_E"]) and np.array_equal(T, g[f"c{k}_T"]) and np.array_equal(F, g[f"c{k}_F"])
+        assert 0 < E.shape[0] < g[f"c{k}_mf"].shape[0]
+        gc, wh = g[f"c{k}_g"]
+        assert O.meson_mixing_photon_coupling(float(ma), float(fa)) == pytest.approx(gc, rel=1e-15)
+        assert O.W_agg_hadronic(float(new_fa), float(ma)) == pytest.approx(wh, rel=1e-15, abs=0)
+        p = O.propagate(E, F, float(ma), O.W_gg(gc, float(ma)), 1.0, 574.0, 5.0)
+        assert max_rel(p["scatter_w64"], g[f"c{k}_s64"]) < 1e-14
