@@ -229,6 +229,45 @@ ALP_HD double exp_fast_core(double x, const double* tab = nullptr) {          //
 #endif
 }
 
+// 10^x with the same table and polynomial: x = (64 n + j) log10(2)/64 + t, 10^x = 2^n 2^(j/64) exp(t ln10).
+// Requires |x| <= 300.  ~1 ulp; used for the log-uniform energy draw of the bremsstrahlung channel (fluxes.py:326-327).
+ALP_HD double exp10_fast_core(double x, const double* tab = nullptr) {
+    const double kShift = 6755399441055744.0;
+    const double kd = fma(x, 212.60339807279118, kShift);           // 64 x log2(10)
+    const double fn = kd - kShift;
+    double t = fma(fn, -0.004703592509031296, x);                   // log10(2)/64, high part (32 trailing zero bits)
+    t = fma(fn, -1.1732184103988474e-09, t);                        // low part
+    const double r = t * 2.302585092994046;                         // |r| <= ln2/128
+    const double r2 = r * r;
+    double q = fma(ALP_EXPC(6), r, ALP_EXPC(5));
+    q = fma(q, r, ALP_EXPC(4));
+    q = fma(q, r, ALP_EXPC(3));
+    const double p = fma(q, r2, r);
+#if defined(__CUDA_ARCH__)
+    const int ki = __double2loint(kd);
+    double tv;
+    if (tab) {
+        unsigned addr;
+        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(ki & 63), "r"((unsigned)__cvta_generic_to_shared(tab)));
+        asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(addr));
+    } else {
+        tv = __ldg(&kExpTabDev[ki & 63]);
+    }
+    const double S = __hiloint2double(__double2hiint(tv) + (ki << 14), __double2loint(tv));
+    return fma(S, p, S);
+#else
+    int64_t bits, tb;
+    __builtin_memcpy(&tb, &kd, 8);
+    const int32_t ki = (int32_t)(uint32_t)tb;
+    const double tv = tab ? tab[ki & 63] : kExpTabHost[ki & 63];
+    __builtin_memcpy(&bits, &tv, 8);
+    bits += (int64_t)((uint64_t)(int64_t)ki << 46);
+    double S;
+    __builtin_memcpy(&S, &bits, 8);
+    return fma(S, p, S);
+#endif
+}
+
 ALP_HD double exp_fast(double x) {
     if (!(fabs(x) <= 708.0)) return exp(x);
     return exp_fast_core(x);
@@ -430,6 +469,7 @@ struct PropConst {
     int    fast;              // 1: fast mode, one rsqrt instead of sqrt + 7 divisions (<= 1e-9 relative); 2: + FP32 transcendentals
     double k1, k2;            // fast mode: neg_dist_mbm*ma*width, neg_len_mbm*ma*width (0 for width <= 0)
     double t_safe;            // fast mode: 708/max(|k1|,|k2|) -- largest 1/p_a for which exp_fast_core applies
+    int    short_lived;       // fast mode: exponents reach -708 at p_a >= 1 MeV (see prop_derive / propagate_try_fast)
     double t_fast;            // min(t_safe, 1e140) when the branch-free path applies (fast == 1, no time-of-flight cut), else -1
 };
 
@@ -438,6 +478,9 @@ ALP_HD void prop_derive(PropConst& c) {
     const double m = fmax(fabs(c.k1), fabs(c.k2));
     c.t_safe = m > 0.0 ? 708.0 / m : INFINITY;
     c.t_fast = (c.fast == 1 && !c.use_tof) ? fmin(c.t_safe, 1e140) : -1.0;
+    // short-lived regime: exponents fall below -708 for p_a < 1/t_safe; once that is 1 MeV or more a sizeable share of the
+    // samples is affected -> the launchers use the SHORT_LIVED kernels
+    c.short_lived = (c.fast == 1 && !c.use_tof && c.t_safe < 1.0) ? 1 : 0;
 }
 
 // Returns the FP64 weights before the float32 cast (decay, scatter); the casts + acceptance are prop_cast().
@@ -461,6 +504,11 @@ ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& 
 // Branch-free attempt: valid (returns true) for the plain FP64 fast mode when p_a^2 is a positive normal number and both
 // exponents lie in [-708, 0]; otherwise the outputs are garbage and propagate_sample_fast() redoes the sample.
 // (d <= 1e-300, negative or NaN gives t >= 1e150, inf or NaN: t_fast <= 1e140 rejects them with the one comparison.)
+// SHORT_LIVED: variant for decay lengths far below the baseline, where a sizeable fraction of the samples has exponents
+// below -708.  Each exponential is then handled on its own: below -746 it is exactly 0 (survival 0 / decay probability 1),
+// so only the narrow band (-746, -708) of denormal results still goes to the library path.  The launchers pick the
+// variant from the host-known exponent scale (PropConst::short_lived); the long-lived regime pays nothing for it.
+template <bool SHORT_LIVED = false>
 ALP_HD bool propagate_try_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64,
                                const double* exp_tab = nullptr) {
     const double d = ea * ea - c.ma2;
@@ -476,15 +524,26 @@ ALP_HD bool propagate_try_fast(double ea, double wgt, const PropConst& c, double
         return (d > 0.0) & (c.use_tof == 0);
     }
     const double t = rsqrt_fast(d);
-    const double surv = exp_fast_core(c.k1 * t, exp_tab);
-    const double dec = 1 - exp_fast_core(c.k2 * t, exp_tab);
+    if (!SHORT_LIVED) {
+        const double surv = exp_fast_core(c.k1 * t, exp_tab);
+        const double dec = 1 - exp_fast_core(c.k2 * t, exp_tab);
+        s64 = (c.rescale * wgt) * surv;
+        d64 = s64 * dec;
+        return t <= c.t_fast;
+    }
+    const double x1 = c.k1 * t, x2 = c.k2 * t;                     // both <= 0 (or NaN)
+    const bool z1 = x1 < -746.0, z2 = x2 < -746.0;
+    const double e1 = exp_fast_core(z1 ? -1.0 : x1, exp_tab), e2 = exp_fast_core(z2 ? -1.0 : x2, exp_tab);
+    const double surv = z1 ? 0.0 : e1;
+    const double dec = 1 - (z2 ? 0.0 : e2);
     s64 = (c.rescale * wgt) * surv;
     d64 = s64 * dec;
-    return t <= c.t_fast;
+    return (z1 | (x1 >= -708.0)) & (z2 | (x2 >= -708.0)) & (c.t_fast >= 0.0);      // (NaN exponents fail both tests)
 }
 
 ALP_HD void propagate_sample_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64) {
-    if (propagate_try_fast(ea, wgt, c, d64, s64)) return;
+    // (the same variant as the pair kernels of this launch, so every kernel gives the same bits for a sample)
+    if (c.short_lived ? propagate_try_fast<true>(ea, wgt, c, d64, s64) : propagate_try_fast<false>(ea, wgt, c, d64, s64)) return;
     const double d = ea * ea - c.ma2;
     if (!(d > 0.0) || c.use_tof) {            // E_a <= m_a (v = 0 or NaN) and the time-of-flight cut: reference path
         propagate_sample(ea, wgt, c, d64, s64);

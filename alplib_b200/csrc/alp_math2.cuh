@@ -121,6 +121,38 @@ ALP_HD double brem_sample(double u, const double* b, const BremGlobals& g, doubl
     return ea;
 }
 
+// Fast mode (<= 1e-9 relative): 10^x from the exp table instead of pow (E_a to ~1 ulp), the eight divisions of the spectrum
+// folded into two reciprocals (1/(x m_e) and 1/(3 f^2 (1+f)^2), from which 1/(1+f)^2, 1/(3f^2) and 1/(3f(1+f)^2) follow).
+// Near the kinematic end point (f < 1e-3) the bracket a - b cancels like 1/f and the reference expression is used.
+ALP_HD double brem_sample_fast(double u, const double* b, const BremGlobals& g, double& flux, const double* exp_tab = nullptr) {
+    const double lg = g.log10_ma + b[BR_DL] * u;
+    if (!(fabs(lg) <= 300.0)) return brem_sample(u, b, g, flux);
+    const double ea = exp10_fast_core(lg, exp_tab);
+    const double x = ea * rcp_fast(b[BR_E1]);
+    double diff_br;
+    if (!g.vector) {
+        const double q = g.ma * rcp_fast(x * kME);
+        const double omx = 1 - x;
+        const double f = (q * q) * omx;
+        if (!(f > 1e-3) || !(f < 1e100)) return brem_sample(u, b, g, flux);
+        const double opf = 1 + f, opf2 = opf * opf, f2 = f * f;
+        const double R = rcp_fast((3 * f2) * opf2);
+        const double t1 = ((x * (1 + f * (1.0 / 1.5))) * ((3 * f2) * R)) * g.zl;
+        const double aa = (opf * log(opf)) * (opf2 * R);
+        const double bb = ((1 + 4 * f) + 2 * f2) * (f * R);
+        const double ps = t1 + (x * g.zz) * (aa - bb);
+        const double mc_vol = ((g.ln10 * ea) * b[BR_DL]) / g.n_samples;
+        diff_br = (g.nt * mc_vol) * (ps > 0.0 ? b[BR_PREF] * ps : (ps == ps ? 0.0 * (b[BR_PREF] * ps) : ps));
+    } else {
+        const double omx = 1 - x;
+        const double den = g.ma2 * omx + (x * x) * (kME * kME);     // x * ( ma2 (1-x)/x + x me2 )
+        const double mc_vol = ((g.ln10 * x) * b[BR_DLX]) / g.n_samples;
+        diff_br = (g.nt * mc_vol) * (((g.pref_vec * (omx + (x * x) / 3)) * x) * rcp_fast(den));
+    }
+    flux = b[BR_W] * diff_br;
+    return ea;
+}
+
 // ---- resonance: one term of the (E+, t) Monte-Carlo integral (fluxes.py:437-441, 410-411) -------------------------------------
 ALP_HD double resonance_term(double u1, double u2, double eres, double emax, double max_t, const double* pos_e,
                              const double* pos_f, int n_pos) {

@@ -82,6 +82,7 @@ propagate_kernel(const double* __restrict__ energy, const double* __restrict__ w
 // Fast mode, pair-vectorised: each thread takes two adjacent samples (16-byte loads, 8-byte float stores), the exp table
 // sits in shared memory and the arithmetic of both samples is straight-line (see chain_pair); rare samples outside the
 // branch-free domain are redone through propagate_sample_fast.  Needs 16-byte aligned arrays (the launcher checks).
+template <bool SHORT>
 __global__ void __launch_bounds__(kThreads)
 propagate_pairs_kernel(const double* __restrict__ energy, const double* __restrict__ weight, uint64_t n, PropConst c,
                        float* __restrict__ d32, float* __restrict__ s32, double* __restrict__ d64o, double* __restrict__ s64o) {
@@ -94,8 +95,8 @@ propagate_pairs_kernel(const double* __restrict__ energy, const double* __restri
         const double2 e = __ldg(reinterpret_cast<const double2*>(energy) + p);
         const double2 w = __ldg(reinterpret_cast<const double2*>(weight) + p);
         double d0, s0, d1, s1;
-        bool ok = propagate_try_fast(e.x, w.x, c, d0, s0, s_tab);
-        ok &= propagate_try_fast(e.y, w.y, c, d1, s1, s_tab);
+        bool ok = propagate_try_fast<SHORT>(e.x, w.x, c, d0, s0, s_tab);
+        ok &= propagate_try_fast<SHORT>(e.y, w.y, c, d1, s1, s_tab);
         if (!ok) {
             propagate_sample_fast(e.x, w.x, c, d0, s0);
             propagate_sample_fast(e.y, w.y, c, d1, s1);
@@ -279,7 +280,7 @@ struct ComptonProd {
     __device__ static __forceinline__ double sample(double u, const double* b, const Globals& g, double& flux) {
         return compton_sample(u, b, g, flux);
     }
-    __device__ static __forceinline__ double sample_fast(double u, const double* b, const Globals& g, double& flux) {
+    __device__ static __forceinline__ double sample_fast(double u, const double* b, const Globals& g, double& flux, const double* exp_tab) {
         return compton_sample_fast(u, b, g, flux);
     }
 };
@@ -418,10 +419,11 @@ ALPK_EXPORT int alpk_propagate(const double* energy, const double* weight, uint6
     cudaStream_t st = (cudaStream_t)stream;
     const uintptr_t align = (uintptr_t)energy | (uintptr_t)weight | (uintptr_t)decay_w32 | (uintptr_t)scatter_w32 |
                             (uintptr_t)d64 | (uintptr_t)s64;
-    if (h_prop->fast && (align & 15) == 0)
-        propagate_pairs_kernel<<<grid_for(n, kThreads * 2 * 4, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop),
-                                                                                     decay_w32, scatter_w32, d64, s64);
-    else if (h_prop->fast)
+    if (h_prop->fast && (align & 15) == 0) {
+        const PropConst c = to_prop(h_prop);
+        if (c.short_lived) propagate_pairs_kernel<true><<<grid_for(n, kThreads * 2 * 4, 8), kThreads, 0, st>>>(energy, weight, n, c, decay_w32, scatter_w32, d64, s64);
+        else propagate_pairs_kernel<false><<<grid_for(n, kThreads * 2 * 4, 8), kThreads, 0, st>>>(energy, weight, n, c, decay_w32, scatter_w32, d64, s64);
+    } else if (h_prop->fast)
         propagate_kernel<true><<<grid_for(n, kThreads, 8), kThreads, 0, st>>>(energy, weight, n, to_prop(h_prop), decay_w32,
                                                                              scatter_w32, d64, s64);
     else

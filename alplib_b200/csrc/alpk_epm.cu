@@ -20,9 +20,8 @@ struct BremProd {
     __device__ static __forceinline__ double sample(double u, const double* b, const Globals& g, double& flux) {
         return brem_sample(u, b, g, flux);
     }
-    // the production arithmetic is pow/log bound: fast mode only switches the fused propagate
-    __device__ static __forceinline__ double sample_fast(double u, const double* b, const Globals& g, double& flux) {
-        return brem_sample(u, b, g, flux);
+    __device__ static __forceinline__ double sample_fast(double u, const double* b, const Globals& g, double& flux, const double* exp_tab) {
+        return brem_sample_fast(u, b, g, flux, exp_tab);
     }
 };
 
@@ -93,7 +92,7 @@ struct PairProd {
     __device__ static __forceinline__ double sample(double u, const double* r, const Globals& g, double& flux) {
         return pairann_sample(u, r, g, flux);
     }
-    __device__ static __forceinline__ double sample_fast(double u, const double* r, const Globals& g, double& flux) {
+    __device__ static __forceinline__ double sample_fast(double u, const double* r, const Globals& g, double& flux, const double* exp_tab) {
         return pairann_sample(u, r, g, flux);
     }
 };

@@ -50,7 +50,7 @@ enum ChainOut : int {
 //   PAIRED: n_samples is even, so the two samples always lie in the same row and share one Philox call (counter s>>1):
 //           no row-straddle / lone-sample handling and no word selects.
 //   CHECK:  the tile may be partial (have2 can be false).
-template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT, bool CHECK>
+template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT, bool SHORT, bool CHECK>
 __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const double* rows, const double* s_tab,
                                            const double* s_edges, double* s_bins, uint64_t r0, uint32_t off0,
                                            uint64_t base, uint32_t local, uint32_t lim, bool long_rows, double& acc) {
@@ -101,11 +101,13 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
         // straight-line arithmetic for both samples (the independent exp / rsqrt / rcp chains interleave); the rare
         // samples outside the branch-free domain are redone afterwards
 #pragma unroll
-        for (int j = 0; j < 2; ++j) e[j] = Prod::sample_fast(u[j], rows + (size_t)rr[j] * NP, a.g, f[j]);
+        for (int j = 0; j < 2; ++j) e[j] = Prod::sample_fast(u[j], rows + (size_t)rr[j] * NP, a.g, f[j], s_tab);
         if (STAGE >= 1) {
             bool ok = true;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) ok &= propagate_try_fast(e[j], f[j], a.prop, d64v[j], s64v[j], s_tab);
+            for (int j = 0; j < 2; ++j)
+                ok &= (PAIRED || !a.prop.short_lived) ? propagate_try_fast<SHORT>(e[j], f[j], a.prop, d64v[j], s64v[j], s_tab)
+                                                      : propagate_try_fast<true>(e[j], f[j], a.prop, d64v[j], s64v[j], s_tab);
             if (!ok) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
@@ -166,14 +168,15 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
     }
 }
 
-template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT>   // STAGE 0: production; 1: + propagate; 2: + decays
+// SHORT: the short-lived variant of the straight-line propagate (see propagate_try_fast); only with PAIRED && FAST.
+template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT, bool SHORT>   // STAGE 0: production; 1: + propagate; 2: + decays
 __global__ void __launch_bounds__(kThreads, ALPK_MIN_BLOCKS)
 chain_kernel(const ChainArgs<Prod> a) {
     using namespace alp;
     constexpr int NP = Prod::NP;
     __shared__ double s_rows[kStageRows * NP];
     __shared__ double red[32];
-    __shared__ double s_tab[64];                     // exp_fast table (fast mode, STAGE >= 1)
+    __shared__ double s_tab[64];                     // exp_fast table (fast mode)
     extern __shared__ double s_hist_mem[];           // [n_edges] edges + [n_edges-1] privatised bins (only if a.hist)
     double* s_edges = s_hist_mem;
     double* s_bins = s_hist_mem + a.n_edges;
@@ -181,7 +184,7 @@ chain_kernel(const ChainArgs<Prod> a) {
         for (int i = threadIdx.x; i < a.n_edges; i += blockDim.x) s_edges[i] = __ldg(a.hist_edges + i);
         for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) s_bins[i] = 0.0;
     }
-    if (FAST && STAGE >= 1 && threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    if (FAST && threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
     // (all made visible by the __syncthreads of the first tile)
     const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
     const uint32_t tile_elems = a.tile_elems;        // kTile, or fewer when rows are so short that a full tile would
@@ -204,14 +207,14 @@ chain_kernel(const ChainArgs<Prod> a) {
         if (PAIRED && lim == (uint32_t)kTile) {       // full tile: no bounds tests in the loop
 #pragma unroll kInnerUnroll
             for (int k = 0; k < kUnroll; ++k)
-                chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, false>(
+                chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, SHORT, false>(
                     a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, 2 * ((uint32_t)k * kThreads + threadIdx.x), lim, long_rows, acc);
         } else {
 #pragma unroll 1
             for (int k = 0; k < kUnroll; ++k) {
                 const uint32_t local = 2 * ((uint32_t)k * kThreads + threadIdx.x);
                 if (local >= lim) break;
-                chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, true>(
+                chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, SHORT, true>(
                     a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, local, lim, long_rows, acc);
             }
         }
@@ -277,21 +280,24 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const bool standard = out_energy && out_flux && !decay_w64 && !scatter_w64 && (stage < 1 || (decay_w32 && scatter_w32)) &&
                           (stage < 2 || event_w);
     const bool noevents = stage == 2 && out_energy && out_flux && decay_w32 && scatter_w32 && !decay_w64 && !scatter_w64 && !event_w;
-#define ALPK_CHAIN_LAUNCH(I, S, F, H, P, O) chain_kernel<Prod, I, S, F, H, P, O><<<grid, kThreads, smem, st>>>(a)
+#define ALPK_CHAIN_LAUNCH(I, S, F, H, P, O, SH) chain_kernel<Prod, I, S, F, H, P, O, SH><<<grid, kThreads, smem, st>>>(a)
+#define ALPK_CHAIN_PAIRED(S, O) { if (S >= 1 && a.prop.short_lived) ALPK_CHAIN_LAUNCH(false, S, true, false, true, O, true); \
+                                  else ALPK_CHAIN_LAUNCH(false, S, true, false, true, O, false); }
 #define ALPK_CHAIN_CASE(S)                                                                                   \
     if (hist) {   /* histogram variants only for the free-running RNG */                                      \
         if (inj) { set_error("%s: fused histogram is not available with injected uniforms", what); return 2; } \
-        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true, false, kOutGeneric); else ALPK_CHAIN_LAUNCH(false, S, false, true, false, kOutGeneric); \
-    } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false, false, kOutGeneric); else ALPK_CHAIN_LAUNCH(true, S, false, false, false, kOutGeneric); } \
+        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true, false, kOutGeneric, false); else ALPK_CHAIN_LAUNCH(false, S, false, true, false, kOutGeneric, false); \
+    } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false, false, kOutGeneric, false); else ALPK_CHAIN_LAUNCH(true, S, false, false, false, kOutGeneric, false); } \
     else if (fast && paired) {                                                                                 \
-        if (standard) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutStandard);                            \
-        else if (S == 2 && noevents) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutNoEvents);             \
-        else if (none) ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutNone);                               \
-        else ALPK_CHAIN_LAUNCH(false, S, true, false, true, kOutGeneric);                                      \
-    } else if (fast) ALPK_CHAIN_LAUNCH(false, S, true, false, false, kOutGeneric);                             \
-    else ALPK_CHAIN_LAUNCH(false, S, false, false, false, kOutGeneric);
+        if (standard) ALPK_CHAIN_PAIRED(S, kOutStandard)                                                       \
+        else if (S == 2 && noevents) ALPK_CHAIN_PAIRED(S, kOutNoEvents)                                        \
+        else if (none) ALPK_CHAIN_PAIRED(S, kOutNone)                                                          \
+        else ALPK_CHAIN_PAIRED(S, kOutGeneric)                                                                 \
+    } else if (fast) ALPK_CHAIN_LAUNCH(false, S, true, false, false, kOutGeneric, false);                      \
+    else ALPK_CHAIN_LAUNCH(false, S, false, false, false, kOutGeneric, false);
     if (stage == 0) { ALPK_CHAIN_CASE(0) } else if (stage == 1) { ALPK_CHAIN_CASE(1) } else { ALPK_CHAIN_CASE(2) }
 #undef ALPK_CHAIN_LAUNCH
+#undef ALPK_CHAIN_PAIRED
 #undef ALPK_CHAIN_CASE
     if (check_launch(what)) return 1;
     if (stage == 2) return finalize_sum(scratch, grid, rate, st);

@@ -438,3 +438,35 @@ def test_detection_cross_sections_fast_mode(hostcheck):
         with np.errstate(all="ignore"):
             ref = O.iprimakoff_sigma(e, 1e-5, ma, 18)
         assert max_rel(out, ref, floor=1e-300) < TOL, ma
+
+
+def test_brem_fast_production(hostcheck):
+    """Fast-mode bremsstrahlung sample (table 10^x, shared reciprocals) against the reference-order expression on random rows,
+    pseudoscalar and vector, including the end-point region that falls back to the reference expression."""
+    rng = np.random.default_rng(12)
+    hostcheck.hc_exp10_fast.restype = C.c_double
+    x = rng.uniform(-300, 300, 20000)
+    y = np.array([hostcheck.hc_exp10_fast(C.c_double(v)) for v in x[:4000]])
+    assert max_rel(y, np.power(10.0, x[:4000])) < 4e-16
+    n = 40000
+    for vector in (0, 1):
+        for ma in (0.05, 10.0, 300.0):
+            from alplib_b200.materials import Material
+            mat = Material("C")
+            par = P.brem_params(ma, 1e-6, mat.z[0], mat.rad_length, 100, "vector" if vector else "pseudoscalar", 5.0, True)
+            e1 = 10 ** rng.uniform(np.log10(max(ma, 0.511)) + 0.01, 5.5, n)
+            ea_max = e1 * (1 - (ma / e1) ** 2)
+            ok = ea_max > ma
+            e1, ea_max = e1[ok], ea_max[ok]
+            m = e1.shape[0]
+            rows = np.zeros((m, N.BREM_NP))
+            rows[:, 0] = e1; rows[:, 1] = 10 ** rng.uniform(5, 12, m)
+            rows[:, 2] = np.log10(ea_max) - np.log10(ma)
+            rows[:, 3] = par.pref_num / e1
+            rows[:, 4] = 1.0
+            rows[:, 5] = np.log10(ea_max / e1) - np.log10(ma / e1)
+            u = np.concatenate([rng.random(m - 200), 1 - 10 ** rng.uniform(-12, -3, 200)])      # some at the end point
+            ref, fast = np.empty(2 * m), np.empty(2 * m)
+            hostcheck.hc_brem_sample_pair(dptr(np.ascontiguousarray(rows)), dptr(u), C.c_uint64(m), C.byref(par), dptr(ref), dptr(fast))
+            assert max_rel(fast[:m], ref[:m]) < 1e-14, (vector, ma)
+            assert max_rel(fast[m:], ref[m:], floor=1e-300) < TOL, (vector, ma)
