@@ -49,13 +49,13 @@ class BremT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("log10_ma", C.c_double), ("ep_min", C.c_double),
                 ("nt", C.c_double), ("pref_num", C.c_double), ("zl", C.c_double), ("zz", C.c_double),
                 ("pref_vec", C.c_double), ("ln10", C.c_double), ("n_samples", C.c_double), ("t_arg", C.c_double),
-                ("vector", C.c_int), ("use_track_length", C.c_int)]
+                ("vector", C.c_int), ("use_track_length", C.c_int), ("fast", C.c_int)]
 
 
 class PairAnnT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("me2", C.c_double), ("me4", C.c_double),
                 ("pref", C.c_double), ("wconst", C.c_double), ("z", C.c_double), ("ge2", C.c_double),
-                ("ntad", C.c_double), ("hbarc2", C.c_double), ("n_samples", C.c_double)]
+                ("ntad", C.c_double), ("hbarc2", C.c_double), ("n_samples", C.c_double), ("fast", C.c_int)]
 
 
 class PairGammaT(C.Structure):

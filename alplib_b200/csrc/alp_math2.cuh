@@ -238,6 +238,29 @@ ALP_HD double pairann_sample(double u, const double* r, const PairGlobals& g, do
     return r[PA_GAM] * r[PA_E3] + r[PA_M03] * pz;                                // boost row 0
 }
 
+// Fast mode (<= 1e-9 relative): cos(acos(1 - 2u)) = 1 - 2u, and the three propagator divisions share one reciprocal
+// 1/(t_prop u_prop).
+ALP_HD double pairann_sample_fast(double u, const double* r, const PairGlobals& g, double& flux) {
+    const double cth = 1 - 2 * u;
+    const double s = r[PA_S];
+    const double t = (g.me2 + g.ma2) + 2 * (r[PA_P1P3] * cth - r[PA_E1E3]);
+    const double u_prop = ((g.me2 + g.ma2) - s) - t;
+    const double t_prop = g.me2 - t;
+    const double den = t_prop * u_prop;
+    if (!(fabs(den) > 1e-290) || !(fabs(den) < 1e290)) return pairann_sample(u, r, g, flux);
+    const double R = rcp_fast(den);
+    const double it = u_prop * R, iu = t_prop * R;                 // 1/t_prop, 1/u_prop
+    const double tail = t * (((-g.ma2) + s) + t);
+    const double mt2 = (-4 * ((3 * g.me4 - g.me2 * (g.ma2 + s)) + tail)) * (it * it);
+    const double mu2 = (-4 * ((7 * g.me4 + g.me2 * ((g.ma2 - 3 * s) - 4 * t)) + tail)) * (iu * iu);
+    const double mtmu = (8 * (((-3) * g.me4 + g.me2 * (s - 2 * t)) + tail)) * R;
+    const double m2 = (mt2 + mu2) + 2 * mtmu;
+    const double val = (g.pref * m2) * heaviside(r[PA_TMAX] - t, 0.0);
+    const double wts = r[PA_VOL] * (val * rcp_fast(r[PA_DEN]));
+    flux = r[PA_C] * wts;
+    return r[PA_GAM] * r[PA_E3] + r[PA_M03] * (r[PA_P3] * cth);
+}
+
 // ---- e+ e- -> gamma a through a virtual photon (fluxes.py:1058-1131, prod_xs.py:109-129) ----------------------------------
 struct PairGammaGlobals {
     double ma, ma2, ma4;

@@ -93,7 +93,7 @@ struct PairProd {
         return pairann_sample(u, r, g, flux);
     }
     __device__ static __forceinline__ double sample_fast(double u, const double* r, const Globals& g, double& flux, const double* exp_tab) {
-        return pairann_sample(u, r, g, flux);
+        return pairann_sample_fast(u, r, g, flux);
     }
 };
 
@@ -146,8 +146,9 @@ ALPK_EXPORT int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint
                                   const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
                                      const double* hist_edges, int n_edges, double* hist, void* stream) {
     if (!h_par) { set_error("alpk_brem_samples: null argument"); return 2; }
+    if (h_prop && (h_prop->fast != 0) != (h_par->fast != 0)) { set_error("alpk_brem_samples: production and propagate precision modes differ"); return 2; }
     return launch_chain<BremProd>("alpk_brem_samples", row_table, n_rows, n_samples, row_ids, to_brem(h_par),
-                                  (h_prop && h_prop->fast) ? 1 : 0, uniforms,
+                                  h_par->fast ? 1 : 0, uniforms,
                                   seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64, scatter_w64,
                                   h_ev, event_w, rate, scratch, hist_edges, n_edges, hist, stream);
 }
@@ -184,8 +185,9 @@ ALPK_EXPORT int alpk_pairann_samples(const double* row_table, uint64_t n_rows, u
                                      const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
                                      const double* hist_edges, int n_edges, double* hist, void* stream) {
     if (!h_par) { set_error("alpk_pairann_samples: null argument"); return 2; }
+    if (h_prop && (h_prop->fast != 0) != (h_par->fast != 0)) { set_error("alpk_pairann_samples: production and propagate precision modes differ"); return 2; }
     return launch_chain<PairProd>("alpk_pairann_samples", row_table, n_rows, n_samples, row_ids, to_pair(h_par),
-                                  (h_prop && h_prop->fast) ? 1 : 0, uniforms,
+                                  h_par->fast ? 1 : 0, uniforms,
                                   seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64, scatter_w64,
                                   h_ev, event_w, rate, scratch, hist_edges, n_edges, hist, stream);
 }

@@ -638,7 +638,7 @@ class FluxBremIsotropic(_ChainFlux):
         ef = _as_flux_table(self.electron_flux, "electron_flux")
         ns = int(self.n_samples)
         par = P.brem_params(self.ma, self.ge, self.target_z, self._rad_length, ns, self.boson_type, self.max_t,
-                            use_track_length)
+                            use_track_length, fast=self.precision != "faithful")
         if use_track_length:
             ep_min = max(self.ma, M_E)                                           # fluxes.py:346
             keep = ~(ef[:, 0] < ep_min)
@@ -827,7 +827,7 @@ class FluxPairAnnihilationIsotropic(_ChainFlux):
         n_rows, ns = int(rows.shape[0]), int(self.n_samples)
         seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
         self._seed_used = seed
-        par = P.pairann_params(self.ma, self.ge, self.target_z, self._rad_length, ns)
+        par = P.pairann_params(self.ma, self.ge, self.target_z, self._rad_length, ns, fast=self.precision != "faithful")
         rt = self._rt
         with rt.activate():
             d_u = None

@@ -99,7 +99,7 @@ def gauss_legendre():
     return np.ascontiguousarray(x), np.ascontiguousarray(w)
 
 
-def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_t=5.0, use_track_length=True):
+def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_t=5.0, use_track_length=True, fast=False):
     """fluxes.py:276-337 + prod_xs.py:209-221, 313-323 scalars (z is the np.int64 of Material.z[0])."""
     from numpy import log, power
     b = N.BremT()
@@ -125,10 +125,11 @@ def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_
         raise UnboundLocalError("cannot access local variable 'diff_br' where it is not associated with a value")
     b.vector = 1 if boson_type == "vector" else 0
     b.use_track_length = 1 if use_track_length else 0
+    b.fast = 1 if fast else 0
     return b
 
 
-def pairann_params(ma, ge, z, rad_length, n_samples):
+def pairann_params(ma, ge, z, rad_length, n_samples, fast=False):
     """fluxes.py:484,518 + matrix_element.py:717-734 scalars."""
     p = N.PairAnnT()
     p.ma = float(ma)
@@ -142,4 +143,5 @@ def pairann_params(ma, ge, z, rad_length, n_samples):
     p.ntad = float(rad_length * AVOGADRO / (2 * z))
     p.hbarc2 = float(HBARC ** 2)
     p.n_samples = float(n_samples)
+    p.fast = 1 if fast else 0
     return p

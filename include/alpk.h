@@ -197,6 +197,8 @@ typedef struct {
     double t_arg;            /* 4*max_track_length/3                                fluxes.py:266 */
     int vector;              /* boson_type == "vector" */
     int use_track_length;    /* simulate(use_track_length=...) */
+    int fast;                /* 1: fast arithmetic mode of the per-sample production (<= 1e-9 relative); must equal the mode of a
+                                fused alpk_prop_t so that every schedule produces the same bits */
 } alpk_brem_t;
 
 /* Row prelude: one thread per electron row (rows already filtered by the host: E0 >= ep_min in track-length mode).
@@ -235,6 +237,7 @@ typedef struct {
     double wconst;           /* reserved */
     double z, ge2, ntad, hbarc2;   /* applied left to right after the positron weight, fluxes.py:518 */
     double n_samples;
+    int fast;                /* as in alpk_brem_t */
 } alpk_pairann_t;
 
 /* rows already filtered by the host (E+ >= max((ma^2-me^2)/(2 me), me), fluxes.py:507) */

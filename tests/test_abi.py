@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(N.PropT) == 7 * 8 + 16 + 3 * 8 + 8 + 16
     assert ctypes.sizeof(N.EventT) == 8 + 8 + 8
     assert ctypes.sizeof(N.ComptonT) == 5 * 8 + 8
-    assert N.PropT.k1.offset == 104 and ctypes.sizeof(N.BremT) == 12 * 8 + 8 and ctypes.sizeof(N.PairAnnT) == 11 * 8
+    assert N.PropT.k1.offset == 104 and ctypes.sizeof(N.BremT) == 12 * 8 + 16 and ctypes.sizeof(N.PairAnnT) == 11 * 8 + 8
     assert N.PropT.geom32.offset == 56 and N.PropT.tof_light.offset == 72
     assert N.EventT.threshold.offset == 16
 

@@ -1085,3 +1085,31 @@ def test_axion_meson_mixing(A):
         assert max_rel(fl.scatter_axion_weight_f64, g[f"c{k}_s64n"]) < TOL
         assert_decay_close(fl.decay_axion_weight_f64, g[f"c{k}_d64n"], g[f"c{k}_s64n"], TOL)
         assert A.PhotonEventGenerator(fl, A.Material("Ar")).decays(100, 0.0) >= 0.0
+
+
+@pytest.mark.parametrize("channel", ["brem", "brem_vector", "pairann"])
+def test_epm_fused_equals_unfused(A, channel):
+    """Call-by-call schedule vs the one-kernel chain for the e+- channels: identical bits for every per-sample array (the
+    production arithmetic mode and the short-lived propagate variant are the same in every kernel of a launch)."""
+    ef, pfx = _brem_tables(211)
+    kw = dict(target_length=100, axion_mass=10.0, axion_coupling=1e-6, n_samples=500, seed=31, **GEOM_DUNE)
+
+    def make(fused):
+        if channel == "pairann":
+            return A.FluxPairAnnihilationIsotropic(pfx, A.Material("C"), fused=fused, **kw)
+        return A.FluxBremIsotropic(ef, pfx, A.Material("C"), fused=fused,
+                                   boson_type="vector" if channel == "brem_vector" else "pseudoscalar", **kw)
+    a = make(False)
+    a.simulate(); a.propagate()
+    ra = A.ElectronEventGenerator(a, A.Material("Ar")).decays(100, 5.0)
+    b = make("auto")
+    b.simulate(); b.propagate()
+    rb = A.ElectronEventGenerator(b, A.Material("Ar")).decays(100, 5.0)
+    assert len(a.axion_energy) > 1000
+    for attr in ("axion_energy", "axion_flux", "decay_axion_weight", "scatter_axion_weight"):
+        assert np.array_equal(getattr(a, attr), getattr(b, attr)), attr
+    assert rb == pytest.approx(ra, rel=1e-12)
+    c = make(True)
+    c.simulate(); c.propagate()
+    assert A.ElectronEventGenerator(c, A.Material("Ar")).decays(100, 5.0) == pytest.approx(ra, rel=1e-12)
+    assert np.array_equal(c.axion_flux, a.axion_flux)              # regenerated on demand after the reduce-only chain

@@ -470,3 +470,23 @@ def test_brem_fast_production(hostcheck):
             hostcheck.hc_brem_sample_pair(dptr(np.ascontiguousarray(rows)), dptr(u), C.c_uint64(m), C.byref(par), dptr(ref), dptr(fast))
             assert max_rel(fast[:m], ref[:m]) < 1e-14, (vector, ma)
             assert max_rel(fast[m:], ref[m:], floor=1e-300) < TOL, (vector, ma)
+
+
+def test_pairann_fast_production(hostcheck):
+    """Fast-mode associated-production sample (cos theta = 1 - 2u, one shared reciprocal) against the reference-order one."""
+    from alplib_b200.materials import Material
+    rng = np.random.default_rng(21)
+    mat = Material("C")
+    for ma in (0.05, 10.0, 60.0):
+        par = P.pairann_params(ma, 1e-6, mat.z[0], mat.rad_length, 100)
+        thr = max((ma ** 2 - 2 * 0.511 ** 2) / (2 * 0.511), 0.511)
+        n = 30000
+        ep = thr * (1 + 10 ** rng.uniform(-6, 4, n))
+        wgt = 10 ** rng.uniform(5, 12, n)
+        u = rng.random(n)
+        ref, fast = np.empty(2 * n), np.empty(2 * n)
+        hostcheck.hc_pairann_sample_pair(dptr(ep), dptr(wgt), dptr(u), C.c_uint64(n), C.byref(par), dptr(ref), dptr(fast))
+        ok = np.isfinite(ref[n:])
+        assert ok.mean() > 0.9
+        assert max_rel(fast[:n][ok], ref[:n][ok]) < 1e-12, ma
+        assert max_rel(fast[n:][ok], ref[n:][ok], floor=1e-300) < TOL, ma
