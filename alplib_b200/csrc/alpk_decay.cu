@@ -225,35 +225,57 @@ decay_general_kernel(const double* __restrict__ table, uint64_t n_parents, uint3
 // ---------------------------------------------------------------------------------------------------------------
 // weighted histogram, np.histogram(x, bins=edges, weights=w): bin k = [edges[k], edges[k+1]), last bin closed
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SMEM>
+// WARP_PRIVATE: every warp owns a copy of the bins in shared memory and adds to it without atomics (warp_hist_add);
+// otherwise (too many bins for 8 copies) one copy per CTA with shared atomics, or global atomics when even that does not
+// fit.  Four samples per trip with the loads issued first.
+template <int MODE>      // 0: global atomics, 1: per-CTA shared bins, 2: per-warp shared bins
 __global__ void __launch_bounds__(kThreads)
 hist_kernel(const double* __restrict__ x, const double* __restrict__ w64, const float* __restrict__ w32, uint64_t n,
             const double* __restrict__ edges, int n_edges, double* __restrict__ hist) {
     extern __shared__ double sm[];
     const int n_bins = n_edges - 1;
+    const int copies = MODE == 2 ? kThreads / 32 : 1;
     const double* ed = edges;
     double* h = hist;
-    if (SMEM) {
+    BinGuess guess{0, 0.0, 0.0};
+    if (MODE >= 1) {
         double* s_edges = sm;
         double* s_hist = sm + n_edges;
         for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = __ldg(edges + i);
-        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) s_hist[i] = 0.0;
+        for (int i = threadIdx.x; i < n_bins * copies; i += blockDim.x) s_hist[i] = 0.0;
         __syncthreads();
+        guess = detect_spacing(s_edges, n_edges);
         ed = s_edges;
-        h = s_hist;
+        h = s_hist + (MODE == 2 ? (threadIdx.x >> 5) * n_bins : 0);
     }
+    constexpr int U = 4;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int b = find_bin(__ldg(x + i), ed, n_edges);
-        if (b >= 0) {
-            const double w = w64 ? __ldg(w64 + i) : (w32 ? (double)__ldg(w32 + i) : 1.0);
-            atomicAdd(h + b, w);
+    // whole warps iterate together (warp_hist_add needs every lane): trip count from the warp's first lane
+    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31);
+    for (uint64_t base = first; base < n; base += U * stride) {
+        double xv[U], wv[U];
+        bool ok[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            const uint64_t i = base + (threadIdx.x & 31) + q * stride;
+            ok[q] = i < n;
+            xv[q] = ok[q] ? __ldg(x + i) : 0.0;
+            wv[q] = !ok[q] ? 0.0 : (w64 ? __ldg(w64 + i) : (w32 ? (double)__ldg(w32 + i) : 1.0));
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (base + q * stride >= n) break;                       // warp-uniform
+            const int b = ok[q] ? find_bin_guess(xv[q], ed, n_edges, guess) : -1;
+            if (MODE == 2) warp_hist_add(h, b, wv[q], b >= 0);
+            else if (b >= 0) atomicAdd(h + b, wv[q]);
         }
     }
-    if (SMEM) {
+    if (MODE >= 1) {
         __syncthreads();
+        double* s_hist = sm + n_edges;
         for (int i = threadIdx.x; i < n_bins; i += blockDim.x) {
-            const double v = h[i];
+            double v = 0.0;
+            for (int c = 0; c < copies; ++c) v += s_hist[c * n_bins + i];
             if (v != 0.0) atomicAdd(hist + i, v);
         }
     }
@@ -325,10 +347,12 @@ ALPK_EXPORT int alpk_hist(const double* x, const double* w64, const float* w32, 
     if (n_edges < 2) { set_error("alpk_hist: need at least 2 edges"); return 2; }
     if (!x || !edges || !hist) { set_error("alpk_hist: null argument"); return 2; }
     if (n == 0) return 0;
-    const size_t smem = (size_t)(2 * n_edges - 1) * sizeof(double);
+    const size_t smem1 = (size_t)(2 * n_edges - 1) * sizeof(double);
+    const size_t smem8 = (size_t)(n_edges + (kThreads / 32) * (n_edges - 1)) * sizeof(double);
     const int grid = grid_for(n, kThreads * 8, 4);
-    if (smem <= 48 * 1024) hist_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(x, w64, w32, n, edges, n_edges, hist);
-    else hist_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, w64, w32, n, edges, n_edges, hist);
+    if (smem8 <= 48 * 1024) hist_kernel<2><<<grid, kThreads, smem8, (cudaStream_t)stream>>>(x, w64, w32, n, edges, n_edges, hist);
+    else if (smem1 <= 48 * 1024) hist_kernel<1><<<grid, kThreads, smem1, (cudaStream_t)stream>>>(x, w64, w32, n, edges, n_edges, hist);
+    else hist_kernel<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, w64, w32, n, edges, n_edges, hist);
     return check_launch("alpk_hist");
 }
 

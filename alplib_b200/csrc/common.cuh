@@ -61,6 +61,83 @@ __device__ __forceinline__ int find_bin(double x, const double* edges, int n_edg
 }
 
 
+// ---- weighted-histogram building blocks ---------------------------------------------------------------------------------
+// How the bin edges are spaced, detected once per CTA from the staged edges; a spacing guess is always verified against
+// the actual edges (np.histogram semantics stay exact), it only replaces the binary search.
+struct BinGuess { int mode; double x0, scale; };      // mode 0: none, 1: linear, 2: logarithmic (guess from float log2)
+
+__device__ __forceinline__ BinGuess detect_spacing(const double* s_edges, int n_edges) {
+    // (call with all threads of the CTA; s_edges visible)
+    const int nb = n_edges - 1;
+    const double e0 = s_edges[0], e1 = s_edges[nb];
+    bool lin = nb >= 1 && e1 > e0, lg = lin && e0 > 0.0;
+    const double w = (e1 - e0) / nb;
+    const double l0 = lg ? (double)__log2f((float)e0) : 0.0, lw = lg ? ((double)__log2f((float)e1) - l0) / nb : 1.0;
+    for (int i = threadIdx.x; i <= nb; i += blockDim.x) {
+        const double e = s_edges[i];
+        lin = lin && fabs(e - (e0 + i * w)) <= 0.25 * w;
+        lg = lg && e > 0.0 && fabs(((double)__log2f((float)e) - l0) - i * lw) <= 0.25 * lw;
+    }
+    const int all_lin = __syncthreads_and(lin), all_lg = __syncthreads_and(lg);
+    BinGuess g;
+    if (all_lin) { g.mode = 1; g.x0 = e0; g.scale = 1.0 / w; }
+    else if (all_lg) { g.mode = 2; g.x0 = l0; g.scale = 1.0 / lw; }
+    else { g.mode = 0; g.x0 = 0.0; g.scale = 0.0; }
+    return g;
+}
+
+// np.histogram bin of x (as find_bin), trying the spacing guess first
+__device__ __forceinline__ int find_bin_guess(double x, const double* edges, int n_edges, const BinGuess& g) {
+    if (g.mode != 0) {
+        if (!(x >= edges[0]) || !(x <= edges[n_edges - 1])) return -1;
+        const double pos = g.mode == 1 ? (x - g.x0) * g.scale : ((double)__log2f((float)x) - g.x0) * g.scale;
+        int b = (int)pos;
+        b = b < 0 ? 0 : (b > n_edges - 2 ? n_edges - 2 : b);
+        // exact placement: at most one step either way when the guess is good
+        if (x < edges[b]) { if (b > 0 && x >= edges[b - 1]) return b - 1; }
+        else if (x < edges[b + 1] || b == n_edges - 2) return b;
+        else if (b + 2 <= n_edges - 1 && (x < edges[b + 2] || b + 2 == n_edges - 1)) return b + 1;
+    }
+    return find_bin(x, edges, n_edges);
+}
+
+// Add w to bins[b] for the valid lanes of a fully converged warp, without atomics: `bins` is private to this warp.  Lanes
+// that hit the same bin are combined first (match.any); the leader of each group does a plain read-modify-write.  Two
+// schedules: few distinct bins -> one masked butterfly sum per bin; many distinct bins -> the leaders walk their peers.
+__device__ __forceinline__ void warp_hist_add(double* bins, int b, double w, bool valid) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(full, valid ? b : -1 - lane);       // invalid lanes: unique negative keys
+    const bool leader = valid && (lane == __ffs(peers) - 1);
+    const unsigned leaders = __ballot_sync(full, leader);
+    if (leaders == 0) return;
+    const int n_groups = __popc(leaders);
+    const int max_group = __reduce_max_sync(full, valid ? __popc(peers) : 0);
+    if (n_groups <= max_group) {
+        unsigned todo = leaders;
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned grp = __shfl_sync(full, peers, l);
+            double v = ((grp >> lane) & 1u) ? w : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+            if (lane == l) bins[b] += v;
+        }
+    } else {
+        double acc = w;
+        unsigned rem = peers & ~(1u << lane);
+        for (int r = 1; r < max_group; ++r) {
+            const bool have = rem != 0;
+            const int src = have ? __ffs(rem) - 1 : lane;
+            rem &= rem - 1;
+            const double v = __shfl_sync(full, w, src);
+            if (leader && have) acc += v;
+        }
+        if (leader) bins[b] += acc;
+    }
+}
+
 // Stage `nrows` records of `NP` doubles starting at row r0 of a row-major table into shared memory.
 template <int NP>
 __device__ __forceinline__ void stage_rows(double* dst, const double* __restrict__ table, uint64_t r0, int nrows) {
