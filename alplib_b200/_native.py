@@ -174,6 +174,7 @@ _SIGNATURES = {
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),
     "alpk_fp64_peak": ([_U64, _I, _P, _P], _I),
+    "alpk_exp_peak": ([_I, _U64, _I, _P, _P], _I),
 }
 
 

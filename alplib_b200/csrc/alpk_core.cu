@@ -552,7 +552,33 @@ fp64_peak_kernel(uint64_t iters, double a, double b, double* __restrict__ out) {
     const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;     // never true; keeps the chains alive
 }
+// FP64 exp throughput (SURVEY section 8d asks for it next to the DFMA peak): four independent evaluations per trip of
+// either the library exp (kind 0) or the fast-mode table exp with the table in shared memory (kind 1), arguments in [-20, 0]
+template <int KIND>
+__global__ void __launch_bounds__(256)
+exp_peak_kernel(uint64_t iters, double* __restrict__ out) {
+    __shared__ double s_tab[64];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = alp::kExpTabDev[threadIdx.x];
+    __syncthreads();
+    double x0 = -1e-3 * threadIdx.x - 0.5, x1 = x0 - 1.0, x2 = x0 - 2.0, x3 = x0 - 3.0, acc = 0.0;
+    for (uint64_t i = 0; i < iters; ++i) {
+        const double e0 = KIND ? alp::exp_fast_core(x0, s_tab) : exp(x0), e1 = KIND ? alp::exp_fast_core(x1, s_tab) : exp(x1);
+        const double e2 = KIND ? alp::exp_fast_core(x2, s_tab) : exp(x2), e3 = KIND ? alp::exp_fast_core(x3, s_tab) : exp(x3);
+        acc += (e0 + e1) + (e2 + e3);
+        x0 = x0 * 0.999 - e0 * 1e-3; x1 = x1 * 0.999 - e1 * 1e-3; x2 = x2 * 0.999 - e2 * 1e-3; x3 = x3 * 0.999 - e3 * 1e-3;
+        x0 = x0 < -20.0 ? x0 + 19.0 : x0; x1 = x1 < -20.0 ? x1 + 19.0 : x1; x2 = x2 < -20.0 ? x2 + 19.0 : x2; x3 = x3 < -20.0 ? x3 + 19.0 : x3;
+    }
+    if (acc == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
 }  // namespace alpk
+
+// launches `blocks` CTAs of 256 threads, each thread evaluating 4*iters exponentials (kind 0: library exp, 1: exp_fast_core)
+ALPK_EXPORT int alpk_exp_peak(int kind, uint64_t iters, int blocks, double* out, void* stream) {
+    if (!out || blocks < 1 || (kind != 0 && kind != 1)) { set_error("alpk_exp_peak: bad argument"); return 2; }
+    if (kind) exp_peak_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
+    else exp_peak_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
+    return check_launch("alpk_exp_peak");
+}
 
 // launches `blocks` CTAs of 256 threads, each thread doing 8*iters dependent-chain DFMAs (16*iters flops)
 ALPK_EXPORT int alpk_fp64_peak(uint64_t iters, int blocks, double* out, void* stream) {

@@ -372,19 +372,38 @@ def run_gpu(args):
         torch.cuda.synchronize()
         fp64_peak = max(blocks * 256 * 16.0 * iters / (f0.elapsed_time(f1) * 1e-3) / 1e12, 1e-9)
         fp64_ach = n_compton * FLOPS_PER_SAMPLE / (kms * 1e-3) / 1e12
+        # FP64 exp throughput: library exp and the fast-mode table exp, 4 evaluations per thread-trip
+        exp_rates = {}
+        for kind, name in ((0, "libdevice_exp_per_s"), (1, "table_exp_per_s")):
+            NV.call("alpk_exp_peak", kind, 200, blocks, NV.ptr(scratch), rt.stream())
+            torch.cuda.synchronize()
+            f0.record()
+            NV.call("alpk_exp_peak", kind, 2000, blocks, NV.ptr(scratch), rt.stream())
+            f1.record()
+            torch.cuda.synchronize()
+            exp_rates[name] = blocks * 256 * 4.0 * 2000 / (f0.elapsed_time(f1) * 1e-3)
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("compton_chain_bytes_per_launch")
         except Exception:
             pass
-        roofline = {"kernel": "alpk::chain_kernel<ComptonProd, INJECT=0, STAGE=2, FAST=1, HIST=0, PAIRED=1, OUT=standard> "
+        # issue-slot model: an FP64 instruction holds the issue port of its SM sub-partition for two
+        # cycles; instruction counts per sample from the ncu source page of this kernel (profiles/ncu_r1_hot_kernels.txt)
+        n_fp64, n_other = 62, 98
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        cyc = kms * 1e-3 * sm_mhz * 1e6 * rt.sm_count * 4 / (n_compton / 32.0)
+        issue = {"fp64_instr_per_sample": n_fp64, "other_instr_per_sample": n_other,
+                 "model_cycles_per_warp_sample": n_other + 2 * n_fp64, "measured_cycles_per_warp_sample": cyc,
+                 "frac": (n_other + 2 * n_fp64) / cyc, "sm_mhz": sm_mhz,
+                 "source": "instruction counts: profiles/ncu_r1_hot_kernels.txt (ncu source page); time and clock: this run"}
+        roofline = {"kernel": "alpk::chain_kernel<ComptonProd, INJECT=0, STAGE=2, FAST=1, HIST=0, PAIRED=1, OUT=standard, SHORT=0> "
                               "(production+propagate+decays, materialising; launched by alpk_compton_samples)",
                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": n_compton * BYTES_PER_SAMPLE,
-                    "kernel_ms": kms, "kernel_ms_samples": len(kernel_ms),
+                    "kernel_ms": kms, "kernel_ms_samples": len(kernel_ms), "issue_slots": issue,
                     "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_ach / fp64_peak,
-                             "flops_per_sample": FLOPS_PER_SAMPLE,
+                             "flops_per_sample": FLOPS_PER_SAMPLE, **exp_rates,
                              "peak_source": "DFMA loop measured in this run (alpk_fp64_peak)",
                              "note": "the kernel is instruction-issue bound (an FP64 instruction holds the issue port "
                                      "for two cycles), not HBM bound; flops use SURVEY section 8d's expanded accounting "

@@ -322,6 +322,8 @@ int alpk_scan(int process, const double* e_gamma, const double* phi_gamma, uint3
 /* FP64 issue-rate microbenchmark: `blocks` CTAs x 256 threads x 8 independent DFMA chains x iters (bench.py uses it
  * to measure the FP64 roofline denominator on the box).  out: >= blocks*256 doubles (never written in practice). */
 int alpk_fp64_peak(uint64_t iters, int blocks, double* out, void* stream);
+/* FP64 exp throughput: `blocks` CTAs x 256 threads x 4*iters evaluations; kind 0 = library exp, 1 = the fast-mode table exp */
+int alpk_exp_peak(int kind, uint64_t iters, int blocks, double* out, void* stream);
 
 /* sum of a f64 array (deterministic two-stage) */
 int alpk_sum(const double* x, uint64_t n, double* out, double* scratch, void* stream);
