@@ -467,7 +467,7 @@ class _ChainFlux(AxionFlux):
         self._D32, self._S32 = d32, s32
         return rate, evw
 
-    def chain(self, days_exposure, threshold, new_coupling=None, materialize=True, hist_edges=None, hist=None):
+    def chain(self, days_exposure, threshold, new_coupling=None, materialize=True, hist_edges=None, hist=None, events=None):
         """One-kernel production -> propagate -> decays.  With materialize=True also fills axion_energy/axion_flux/
         decay_axion_weight/scatter_axion_weight (device) and returns (rate tensor, event-weight tensor).
         hist_edges (array or CUDA tensor): also accumulate the event-weighted E_a spectrum (np.histogram semantics)
@@ -490,13 +490,21 @@ class _ChainFlux(AxionFlux):
                 E, F = rt.empty(n), rt.empty(n)
                 d32, s32 = rt.empty(n, torch.float32), rt.empty(n, torch.float32)
                 evw = rt.empty(n)
+                if events is not None:                      # (start, stop) CUDA events recorded right around the launch
+                    events[0].record()
                 self._launch_samples(E, F, prop, ev, d32=d32, s32=s32, evw=evw, rate=rate, **hk)
+                if events is not None:
+                    events[1].record()
                 self._pending_production = None
                 self._pending_prop = None
                 self._set_production(E, F)
                 self._D32, self._S32 = d32, s32
                 return rate, evw
+            if events is not None:
+                events[0].record()
             self._launch_samples(None, None, prop, ev, rate=rate, **hk)
+            if events is not None:
+                events[1].record()
             return rate, None
 
     def _width_rescale(self, new_coupling):

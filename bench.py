@@ -231,11 +231,7 @@ def run_gpu(args):
         prim.propagate()
         r1 = genP.decays_device(DAYS, THR)
         comp._launch_rows()
-        if kpair is not None:
-            kpair[0].record()
-        r2, _ = comp.chain(DAYS, THR, materialize=True)
-        if kpair is not None:
-            kpair[1].record()
+        r2, _ = comp.chain(DAYS, THR, materialize=True, events=kpair)   # events recorded right around the kernel launch
         rates[0:1].copy_(r1)
         rates[1:2].copy_(r2)
         if world > 1:

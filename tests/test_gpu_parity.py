@@ -968,6 +968,9 @@ def test_examples_run(A, precision):
     energies, weights, n_decay, n_compton = ns["get_events"](10.0, 1e-6, use_loop=True)
     assert energies.shape == weights.shape == (10000,) and np.isfinite(n_decay) and np.isfinite(n_compton)
     assert n_decay >= 0 and n_compton >= 0 and np.sum(weights) == pytest.approx(n_decay + n_compton, rel=1e-6)
+    ns = runpy.run_path(os.path.join(root, "examples", "ex_meson_decays.py"), run_name="__main__")
+    assert len(ns["iso"].axion_energy) == 3 * 2 * 20000 and np.sum(ns["iso"].axion_flux) > 0
+    assert 0 < len(ns["E_"]) <= 2000 * 2 * 500 and np.all(np.isfinite(ns["w"]))
 
 
 # ---- charged-meson 3-body decay fluxes (fluxes.py:605-922) -----------------------------------------------------------------
