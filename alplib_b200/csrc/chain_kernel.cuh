@@ -50,10 +50,17 @@ enum ChainOut : int {
 //   PAIRED: n_samples is even, so the two samples always lie in the same row and share one Philox call (counter s>>1):
 //           no row-straddle / lone-sample handling and no word selects.
 //   CHECK:  the tile may be partial (have2 can be false).
-template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT, bool SHORT, bool CHECK>
+// Row / sample / Philox row id of the first row(s) of a tile, computed once per tile for the LONG fast loop (rows longer
+// than a tile: a tile touches at most two rows, split at sample `split` of the tile).
+struct TileRows { uint32_t split, rid0, rid1; };
+
+//   LONG:   (with PAIRED, full tiles) rows are longer than a tile: row / sample index and row id of a pair come from the
+//           tile-level TileRows with three instructions instead of the general index arithmetic and a row-id load.
+template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED, int OUT, bool SHORT, bool CHECK, bool LONG = false>
 __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const double* rows, const double* s_tab,
                                            const double* s_edges, double* s_bins, uint64_t r0, uint32_t off0,
-                                           uint64_t base, uint32_t local, uint32_t lim, bool long_rows, double& acc) {
+                                           uint64_t base, uint32_t local, uint32_t lim, bool long_rows, double& acc,
+                                           const TileRows& tr = TileRows{0u, 0u, 0u}) {
     using namespace alp;
     constexpr int NP = Prod::NP;
     const uint64_t i0 = base + local;
@@ -62,7 +69,14 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
     float d32v[2], s32v[2];
     double d64v[2], s64v[2], evv[2];
     uint32_t rr[2], ss[2];
-    {
+    uint32_t rid_long = 0;
+    if (LONG) {
+        const bool second = local >= tr.split;
+        rr[0] = rr[1] = second ? 1u : 0u;
+        ss[0] = second ? local - tr.split : off0 + local;
+        ss[1] = ss[0] + 1u;
+        rid_long = second ? tr.rid1 : tr.rid0;
+    } else {
         // (row, sample) of the pair: one integer division at most; none when rows are longer than a tile
         const uint32_t off = off0 + local;
         if (long_rows) { rr[0] = off >= a.n_samples ? 1u : 0u; ss[0] = off - (rr[0] ? a.n_samples : 0u); }
@@ -80,7 +94,7 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
     } else {
         // sample s uses Philox counter s>>1, word pair s&1: adjacent samples of one row share a call
         const uint64_t ra = r0 + rr[0];
-        const uint32_t rid0 = a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra;
+        const uint32_t rid0 = LONG ? rid_long : (a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra);
         const Philox4 q = philox4x32_10_rk(ss[0] >> 1, 0u, rid0, Prod::kTag, a.rk);
         if (PAIRED) {                        // ss[0] is even
             u[0] = u53(q.x, q.y);
@@ -204,7 +218,18 @@ chain_kernel(const ChainArgs<Prod> a) {
         __syncthreads();
         const uint32_t off0 = (uint32_t)(base - r0 * (uint64_t)a.n_samples);   // offset of the tile in its first row
 
-        if (PAIRED && lim == (uint32_t)kTile) {       // full tile: no bounds tests in the loop
+        if (PAIRED && !INJECT && lim == (uint32_t)kTile && long_rows) {
+            // full tile of long rows: no bounds tests, row bookkeeping hoisted to the tile
+            TileRows tr;
+            tr.split = a.n_samples - off0;             // samples of this tile that belong to row r0 (>= kTile: all of them)
+            tr.rid0 = a.row_ids ? __ldg(a.row_ids + r0) : (uint32_t)r0;
+            tr.rid1 = (tr.split < (uint32_t)kTile) ? (a.row_ids ? __ldg(a.row_ids + r0 + 1) : (uint32_t)(r0 + 1)) : tr.rid0;
+            const uint32_t local0 = 2 * threadIdx.x;
+#pragma unroll kInnerUnroll
+            for (int k = 0; k < kUnroll; ++k)
+                chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, SHORT, false, true>(
+                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, local0 + (uint32_t)k * (2 * kThreads), lim, true, acc, tr);
+        } else if (PAIRED && lim == (uint32_t)kTile) {       // full tile: no bounds tests in the loop
 #pragma unroll kInnerUnroll
             for (int k = 0; k < kUnroll; ++k)
                 chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, SHORT, false>(
