@@ -91,6 +91,39 @@ def report():
             geom = A.DetectorGeometry(float(g["l0"]), str(g["geometry"]), list(g["params"]), n_samples=int(g["n_geom"]))
             fl.propagate_iso_vol_int(geom, new_coupling=float(g["new_coupling"]))
             r[name] = {"decay_w64": max_rel(fl.decay_axion_weight_f64, g["decay_w64"]), "scatter_w64": max_rel(fl.scatter_axion_weight_f64, g["scatter_w64"])}
+        # charged-meson 3-body decays and axion-meson mixing
+        models = ["scalar_ib1", "pseudoscalar_ib1", "vector_ib1", "scalar_ib2", "vector_ib2", "vector_ib9", "sd", "vector_contact"]
+        g = load_golden("meson3_iso")
+        we, wf = 0.0, 0.0
+        for k in range(int(g["n_cases"])):
+            mi, mt, ma, cpl = g[f"c{k}_cfg"]
+            fl = A.FluxChargedMeson3BodyIsotropic(meson_flux=g["meson_flux"], boson_mass=float(ma), coupling=float(cpl),
+                                                  meson_type=["pion", "kaon"][int(mt)], interaction_model=models[int(mi)],
+                                                  n_samples=int(g["n_samples"]), c0=float(g["c0"]), abd=tuple(float(x) for x in g["abd"]))
+            fl.simulate(uniforms=g[f"c{k}_u"])
+            we = max(we, max_rel(fl.axion_energy, g[f"c{k}_E"])); wf = max(wf, max_rel(fl.axion_flux, g[f"c{k}_F"]))
+        r["meson3_iso (32 cases: 8 models x pion/kaon x masses)"] = {"energy": we, "flux": wf}
+        g = load_golden("meson3_decay")
+        wd = {"energy": 0.0, "flux": 0.0, "cosine": 0.0, "angle": 0.0}
+        for k in range(int(g["n_cases"])):
+            mi, mt, ma, cpl, cut = g[f"c{k}_cfg"]
+            fl = A.FluxChargedMeson3BodyDecay(g["meson_flux"], boson_mass=float(ma), coupling=float(cpl), n_samples=int(g["n_samples"]),
+                                              meson_type=["pion", "kaon"][int(mt)], interaction_model=models[int(mi)],
+                                              energy_cut=float(g["energy_cut"]))
+            fl.simulate(cut_on_solid_angle=bool(cut), uniforms=dict(pos=g[f"c{k}_upos"], samples=g[f"c{k}_usamp"]))
+            for key, attr in (("energy", "axion_energy"), ("flux", "axion_flux"), ("cosine", "cosines"), ("angle", "axion_angle")):
+                wd[key] = max(wd[key], max_rel(getattr(fl, attr), g[f"c{k}_{key}"]))
+        r["meson3_decay (5 cases)"] = wd
+        g = load_golden("meson_mixing")
+        wm = {"angle": 0.0, "flux": 0.0, "scatter_w64": 0.0}
+        for k in range(int(g["n_cases"])):
+            mt, mmass, ma, fa, new_fa = g[f"c{k}_cfg"]
+            fl = A.FluxAxionMesonMixing(meson_flux=g[f"c{k}_mf"], meson_mass=float(mmass), axion_mass=float(ma), f_a=float(fa),
+                                        meson_type=["Pi0", "Eta"][int(mt)], keep_f64=True)
+            fl.simulate(); fl.propagate()
+            wm["angle"] = max(wm["angle"], max_rel(fl.axion_angle, g[f"c{k}_T"])); wm["flux"] = max(wm["flux"], max_rel(fl.axion_flux, g[f"c{k}_F"]))
+            wm["scatter_w64"] = max(wm["scatter_w64"], max_rel(fl.scatter_axion_weight_f64, g[f"c{k}_s64"]))
+        r["meson_mixing (4 cases)"] = wm
         out[mode] = r
     out["tolerance"] = {"fp64_relative": 1e-9, "float32_attributes": 1.2e-7,
                         "decay_weights": "1e-9 + 4*2^-53/decay_prob (reported in units of that bound; <= 1 passes)"}
