@@ -239,9 +239,6 @@ class FluxChargedMeson3BodyDecay(_Meson3Flux):
     def _br_leptons(self):
         return [M_E, M_MU]                       # the reference's total_br is hard-wired to e and mu (fluxes.py:663-667)
 
-    def _model_param(self):
-        return self.model
-
     # per-sample lists of the reference, device resident, copied lazily
     def _extra_get(self, key):
         self._ensure_production()
