@@ -110,7 +110,9 @@ class AxionFlux:
         self._E = self._F = None            # device float64: axion_energy / axion_flux
         self._D32 = self._S32 = None        # device float32: decay / scatter weights
         self._D64 = self._S64 = None        # device float64 pre-cast weights (keep_f64)
-        self._pending_production = None     # callable materialising _E/_F (fused mode)
+        self._pending_production = None     # True: a deferred simulate() still has to run self._produce() (fused mode); a flag,
+                                            # not the bound method -- that would make every flux object a reference cycle
+                                            # whose GBs of device arrays wait for the cyclic garbage collector
         self._pending_prop = None           # (PropT) recorded by propagate() in fused mode
         self._host = {}
 
@@ -120,7 +122,7 @@ class AxionFlux:
 
     def _ensure_production(self):
         if self._E is None and self._pending_production is not None:
-            self._pending_production()
+            self._produce()
 
     def _ensure_propagated(self):
         if self._D32 is None and self._pending_prop is not None:
@@ -374,7 +376,7 @@ class FluxPrimakoffIsotropic(AxionFlux):
         self._reset_samples()
         self._stage_inputs()
         if self.fused:
-            self._pending_production = self._produce
+            self._pending_production = True
         else:
             self._produce()
 
@@ -434,7 +436,7 @@ class _ChainFlux(AxionFlux):
 
     def _finish_simulate(self):
         if self.fused:
-            self._pending_production = self._produce
+            self._pending_production = True
         else:
             self._produce()
 

@@ -290,14 +290,16 @@ def run_gpu(args):
     for tag, fused in (("e2e", None), ("e2e_eager", False), ("e2e_fused", True)):
         # warm-up: the first eager steps pay cudaMalloc; the first ~30 deferred steps after a materialising phase show
         # allocator/driver hiccups of several ms every other step (tools/dbg_fused.py) before settling
-        torch.cuda.empty_cache()              # give the previous schedule's multi-GB sample blocks back to the driver
         for _ in range(40 if fused is not False else 8):
             res = e2e_step(fused)
         del res
         barrier()
         t0 = time.perf_counter()
+        step_ms = []
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             rp, rc, p, c = e2e_step(fused)
+            step_ms.append((time.perf_counter() - ts) * 1e3)      # (each step ends with the D2H read of its rates)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=rt.device)
         if world > 1:
@@ -305,6 +307,7 @@ def run_gpu(args):
         h2d = sum(int(t.numel() * t.element_size()) for t in (p._inputs[0], p._inputs[1], c._inputs[0], c._inputs[1], c._inputs[4]))
         e2e[tag] = {"value": world * n_step * e2e_steps / float(dt.item()), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16, "steps": e2e_steps,
+                    "step_ms": {"median": float(np.median(step_ms)), "max": float(np.max(step_ms)), "min": float(np.min(step_ms))},
                     "api": "Flux*Isotropic.simulate()/propagate() + EventGenerator.decays()/decays_device()"
                            + (" with fused=True (deferred, one reduce-only kernel)" if fused is True else
                               " with fused=False (one kernel per call, every per-sample array materialised in HBM)" if fused is False else

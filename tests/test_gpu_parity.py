@@ -1116,3 +1116,29 @@ def test_epm_fused_equals_unfused(A, channel):
     c.simulate(); c.propagate()
     assert A.ElectronEventGenerator(c, A.Material("Ar")).decays(100, 5.0) == pytest.approx(ra, rel=1e-12)
     assert np.array_equal(c.axion_flux, a.axion_flux)              # regenerated on demand after the reduce-only chain
+
+
+def test_flux_objects_are_freed_by_refcount(A):
+    """No reference cycles in the flux / generator objects: dropping the last reference releases the (multi-GB at full
+    size) device arrays at once instead of waiting for Python's cyclic garbage collector."""
+    import gc
+    import weakref
+    gc.collect()
+    gc.disable()
+    try:
+        for fused in ("auto", True, False):
+            fl = A.FluxComptonIsotropic(_c2_flux(50), A.Material("W"), axion_mass=1.5, axion_coupling=1e-7, n_samples=200,
+                                        seed=3, fused=fused, **GEOM)
+            fl.simulate(); fl.propagate()
+            gen = A.ElectronEventGenerator(fl, A.Material("Ar"))
+            gen.decays(100, 5.0)
+            r1, r2 = weakref.ref(fl), weakref.ref(gen)
+            del fl, gen
+            assert r1() is None and r2() is None, fused
+        p = A.FluxPrimakoffIsotropic(_c2_flux(50), A.Material("W"), axion_mass=0.1, axion_coupling=1e-5, **GEOM)
+        p.simulate()
+        r = weakref.ref(p)
+        del p
+        assert r() is None
+    finally:
+        gc.enable()
