@@ -36,6 +36,7 @@ struct ChainArgs {
     alp::EventConst ev; double* event_w; double* partials;
     uint32_t tile_elems;
     const double* hist_edges; int n_edges; double* hist;     // optional fused weighted histogram of E_a
+    int hist_copies;                                          // kThreads/32: one copy of the bins per warp; 1: one per CTA
 };
 
 // Which per-sample arrays a launch writes: checked once on the host so the specialised kernels carry no null tests.
@@ -60,7 +61,8 @@ template <class Prod, bool INJECT, int STAGE, bool FAST, bool HIST, bool PAIRED,
 __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const double* rows, const double* s_tab,
                                            const double* s_edges, double* s_bins, uint64_t r0, uint32_t off0,
                                            uint64_t base, uint32_t local, uint32_t lim, bool long_rows, double& acc,
-                                           const TileRows& tr = TileRows{0u, 0u, 0u}) {
+                                           const TileRows& tr = TileRows{0u, 0u, 0u},
+                                           const BinGuess& guess = BinGuess{0, 0.0, 0.0}) {
     using namespace alp;
     constexpr int NP = Prod::NP;
     const uint64_t i0 = base + local;
@@ -152,8 +154,11 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
         if (HIST && (j == 0 || have2)) {
             // np.histogram(E_a, bins=edges, weights=<weight of the last fused stage>)
             const double hw = STAGE >= 2 ? evv[j] : (STAGE == 1 ? (double)d32v[j] : f[j]);
-            const int bin = find_bin(e[j], s_edges, a.n_edges);
-            if (bin >= 0 && hw != 0.0) atomicAdd(s_bins + bin, hw);
+            const int bin = find_bin_guess(e[j], s_edges, a.n_edges, guess);
+            // s_bins: this warp's copy of the bins (or the CTA's).  Full tiles keep every lane of the warp here, so the
+            // aggregated atomic-free add applies; partial tiles fall back to shared atomics
+            if (!CHECK && PAIRED && a.hist_copies > 1) warp_hist_add(s_bins, bin, hw, bin >= 0 && hw != 0.0);
+            else if (bin >= 0 && hw != 0.0) atomicAdd(s_bins + bin, hw);
         }
     }
     if (OUT == kOutNone) return;
@@ -193,10 +198,15 @@ chain_kernel(const ChainArgs<Prod> a) {
     __shared__ double s_tab[64];                     // exp_fast table (fast mode)
     extern __shared__ double s_hist_mem[];           // [n_edges] edges + [n_edges-1] privatised bins (only if a.hist)
     double* s_edges = s_hist_mem;
-    double* s_bins = s_hist_mem + a.n_edges;
+    double* s_bins_all = s_hist_mem + a.n_edges;
+    double* s_bins = s_bins_all;
+    BinGuess guess{0, 0.0, 0.0};
     if (HIST) {
         for (int i = threadIdx.x; i < a.n_edges; i += blockDim.x) s_edges[i] = __ldg(a.hist_edges + i);
-        for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) s_bins[i] = 0.0;
+        for (int i = threadIdx.x; i < (a.n_edges - 1) * a.hist_copies; i += blockDim.x) s_bins_all[i] = 0.0;
+        __syncthreads();
+        guess = detect_spacing(s_edges, a.n_edges);
+        if (a.hist_copies > 1) s_bins = s_bins_all + (threadIdx.x >> 5) * (a.n_edges - 1);
     }
     if (FAST && threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
     // (all made visible by the __syncthreads of the first tile)
@@ -228,19 +238,20 @@ chain_kernel(const ChainArgs<Prod> a) {
 #pragma unroll kInnerUnroll
             for (int k = 0; k < kUnroll; ++k)
                 chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, SHORT, false, true>(
-                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, local0 + (uint32_t)k * (2 * kThreads), lim, true, acc, tr);
+                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, local0 + (uint32_t)k * (2 * kThreads), lim, true, acc, tr, guess);
         } else if (PAIRED && lim == (uint32_t)kTile) {       // full tile: no bounds tests in the loop
 #pragma unroll kInnerUnroll
             for (int k = 0; k < kUnroll; ++k)
                 chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, SHORT, false>(
-                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, 2 * ((uint32_t)k * kThreads + threadIdx.x), lim, long_rows, acc);
+                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, 2 * ((uint32_t)k * kThreads + threadIdx.x), lim, long_rows, acc,
+                    TileRows{0u, 0u, 0u}, guess);
         } else {
 #pragma unroll 1
             for (int k = 0; k < kUnroll; ++k) {
                 const uint32_t local = 2 * ((uint32_t)k * kThreads + threadIdx.x);
                 if (local >= lim) break;
                 chain_pair<Prod, INJECT, STAGE, FAST, HIST, PAIRED, OUT, SHORT, true>(
-                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, local, lim, long_rows, acc);
+                    a, s_rows, s_tab, s_edges, s_bins, r0, off0, base, local, lim, long_rows, acc, TileRows{0u, 0u, 0u}, guess);
             }
         }
     }
@@ -251,7 +262,8 @@ chain_kernel(const ChainArgs<Prod> a) {
     if (HIST) {
         __syncthreads();
         for (int i = threadIdx.x; i < a.n_edges - 1; i += blockDim.x) {
-            const double v = s_bins[i];
+            double v = 0.0;
+            for (int c = 0; c < a.hist_copies; ++c) v += s_bins_all[c * (a.n_edges - 1) + i];
             if (v != 0.0) atomicAdd(a.hist + i, v);
         }
     }
@@ -288,7 +300,9 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     size_t smem = 0;
     if (hist) {
         if (!hist_edges || n_edges < 2) { set_error("%s: histogram needs >= 2 edges", what); return 2; }
-        smem = (size_t)(2 * n_edges - 1) * sizeof(double);
+        const size_t smem8 = (size_t)(n_edges + (kThreads / 32) * (n_edges - 1)) * sizeof(double);
+        a.hist_copies = smem8 <= 40 * 1024 ? kThreads / 32 : 1;
+        smem = a.hist_copies > 1 ? smem8 : (size_t)(2 * n_edges - 1) * sizeof(double);
         if (smem > 40 * 1024) { set_error("%s: fused histogram supports at most %d edges (use alpk_hist)", what, (40 * 1024 / 8 + 1) / 2); return 2; }
         a.hist_edges = hist_edges; a.n_edges = n_edges; a.hist = hist;
     }
@@ -311,7 +325,9 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
 #define ALPK_CHAIN_CASE(S)                                                                                   \
     if (hist) {   /* histogram variants only for the free-running RNG */                                      \
         if (inj) { set_error("%s: fused histogram is not available with injected uniforms", what); return 2; } \
-        if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true, false, kOutGeneric, false); else ALPK_CHAIN_LAUNCH(false, S, false, true, false, kOutGeneric, false); \
+        if (fast && paired) ALPK_CHAIN_LAUNCH(false, S, true, true, true, kOutGeneric, false);                   \
+        else if (fast) ALPK_CHAIN_LAUNCH(false, S, true, true, false, kOutGeneric, false);                       \
+        else ALPK_CHAIN_LAUNCH(false, S, false, true, false, kOutGeneric, false);                                \
     } else if (inj) { if (fast) ALPK_CHAIN_LAUNCH(true, S, true, false, false, kOutGeneric, false); else ALPK_CHAIN_LAUNCH(true, S, false, false, false, kOutGeneric, false); } \
     else if (fast && paired) {                                                                                 \
         if (standard) ALPK_CHAIN_PAIRED(S, kOutStandard)                                                       \
