@@ -412,10 +412,10 @@ vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __re
             if (FAST && c * __longlong_as_double((long long)s_xmax_bits) <= 708.0) {
                 // every exponent of the tile lies in [-708, 0]: straight-line body, four points in flight
 #pragma unroll 4
-                for (uint32_t k = 0; k < cnt; ++k) acc += (A * exp_fast_core(s_x[k] * c, s_tab)) * s_b[k];
+                for (uint32_t k = 0; k < cnt; ++k) acc += exp_fast_core(s_x[k] * c, s_tab) * s_b[k];     // (x A after the walk)
             } else if (FAST) {
 #pragma unroll 2
-                for (uint32_t k = 0; k < cnt; ++k) acc += (A * exp_fast(s_x[k] * c)) * s_b[k];
+                for (uint32_t k = 0; k < cnt; ++k) acc += exp_fast(s_x[k] * c) * s_b[k];
             } else {
 #pragma unroll 4
                 for (uint32_t k = 0; k < cnt; ++k) {
@@ -425,7 +425,7 @@ vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __re
             }
         }
     }
-    if (live) partials[(uint64_t)blockIdx.y * n + i] = acc;
+    if (live) partials[(uint64_t)blockIdx.y * n + i] = FAST ? A * acc : acc;       // fast mode: the sample's 1/(hbar c v tau) once
 }
 
 template <bool FAST>
