@@ -224,6 +224,9 @@ def run_gpu(args):
     n_step = prim._inputs[2] + comp._inputs[2] * N_SAMPLES          # identical on every rank
     n_compton = comp._inputs[2] * N_SAMPLES
     rates = torch.zeros(2, dtype=torch.float64, device=rt.device)
+    rate_bufs = [torch.zeros(2, dtype=torch.float64, device=rt.device) for _ in range(2)]   # double-buffered for the async merge
+    pending = []
+    step_no = [0]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(8)]
 
     def step(kpair=None):
@@ -232,11 +235,28 @@ def run_gpu(args):
         r1 = genP.decays_device(DAYS, THR)
         comp._launch_rows()
         r2, _ = comp.chain(DAYS, THR, materialize=True, events=kpair)   # events recorded right around the kernel launch
-        rates[0:1].copy_(r1)
-        rates[1:2].copy_(r2)
-        if world > 1:
-            dist.all_reduce(rates)             # the path's only exchange: merged rates (NCCL over NVLink)
+        if world == 1:
+            rates[0:1].copy_(r1)
+            rates[1:2].copy_(r2)
+            return rates
+        # the path's only exchange: the merged rates of every step (NCCL over NVLink).  The all-reduce is issued
+        # asynchronously on NCCL's stream and joined one step later, so its latency overlaps the next step's kernels
+        buf = rate_bufs[step_no[0] & 1]
+        step_no[0] += 1
+        buf[0:1].copy_(r1)
+        buf[1:2].copy_(r2)
+        pending.append((dist.all_reduce(buf, async_op=True), buf))
+        if len(pending) > 1:
+            w, b = pending.pop(0)
+            w.wait()                           # stream-side join: the compute stream waits, the host does not
+            rates.copy_(b)
         return rates
+
+    def drain():
+        while pending:
+            w, b = pending.pop(0)
+            w.wait()
+            rates.copy_(b)
 
     def barrier():
         if world > 1:
@@ -245,6 +265,7 @@ def run_gpu(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -257,6 +278,7 @@ def run_gpu(args):
     ev0.record()
     for k in range(args.steps):
         step(kev[k] if k < len(kev) else None)  # per-launch duration of the dominant kernel: CUDA events on its stream
+    drain()                                    # the last step's merge is inside the timed region
     ev1.record()
     barrier()
     t_host1 = time.perf_counter()
