@@ -10,7 +10,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ALPK_LIB_PATH") or os.path.join(_HERE, "libalpk.so")   # override: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_scan.cu", "alpk_misc.cu", "alpk_meson.cu"]
+SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_pairann.cu", "alpk_scan.cu", "alpk_misc.cu", "alpk_meson.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
