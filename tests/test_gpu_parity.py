@@ -1146,3 +1146,24 @@ def test_flux_objects_are_freed_by_refcount(A):
         assert r() is None
     finally:
         gc.enable()
+
+
+def test_noncontiguous_flux_tables(A):
+    """Strided / Fortran-ordered flux tables take the NumPy staging fallback (gather + packed pinned upload) instead of the
+    native one-pass staging: identical samples either way, including tables with extra columns."""
+    base = _c2_flux(120)
+    wide = np.concatenate([base, np.arange(base.shape[0])[:, None] * 1.0], axis=1)        # an extra column, ignored
+    variants = {"strided": np.repeat(base, 2, axis=0)[::2], "fortran": np.asfortranarray(base), "wide": wide,
+                "wide_view": wide[:, :2]}
+    kw = dict(axion_mass=1.5, axion_coupling=1e-7, n_samples=200, seed=5, **GEOM)
+    ref = A.FluxComptonIsotropic(np.ascontiguousarray(base), A.Material("W"), **kw)
+    ref.simulate()
+    refp = A.FluxPrimakoffIsotropic(np.ascontiguousarray(base), A.Material("W"), axion_mass=1.5, axion_coupling=1e-5, **GEOM)
+    refp.simulate()
+    for name, tab in variants.items():
+        c = A.FluxComptonIsotropic(tab, A.Material("W"), **kw)
+        c.simulate()
+        assert np.array_equal(c.axion_energy, ref.axion_energy) and np.array_equal(c.axion_flux, ref.axion_flux), name
+        p = A.FluxPrimakoffIsotropic(tab, A.Material("W"), axion_mass=1.5, axion_coupling=1e-5, **GEOM)
+        p.simulate()
+        assert np.array_equal(p.axion_energy, refp.axion_energy) and np.array_equal(p.axion_flux, refp.axion_flux), name
