@@ -148,7 +148,7 @@ _SIGNATURES = {
     "alpk_brem_rows": ([_P, _P, _U64, _P, _P, _U64, _P, _P, _I, _P, _P, _I, _P, _P, C.POINTER(BremT), _P, _P, _P], _I),
     "alpk_brem_samples": ([_P, _U64, _U32, _P, C.POINTER(BremT), _P, _U64, _P, _P,
                            C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),
-    "alpk_resonance_sum": ([_P, _P, _I, _D, _D, _D, _U64, _P, _U64, _P, _P, _P], _I),
+    "alpk_resonance_sum": ([_P, _P, _I, _D, _D, _D, _U64, _P, _U64, _I, _P, _P, _P], _I),
     "alpk_pairann_rows": ([_P, _P, _U64, C.POINTER(PairAnnT), _P, _P], _I),
     "alpk_pairann_samples": ([_P, _U64, _U32, _P, C.POINTER(PairAnnT), _P, _U64, _P, _P,
                               C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),

@@ -161,6 +161,58 @@ ALP_HD double resonance_term(double u1, double u2, double eres, double emax, dou
     return interp(e, pos_e, pos_f, n_pos, 0.0, 0.0) * track_length_prob(e, eres, t);
 }
 
+// ---- fast mode of the resonance term (<= 1e-9 relative) ----------------------------------------------------------------------
+// 1/Gamma(z) for 0 < z < 170: recurrence to w = z - k in [1, 2), degree-14 polynomial in (w - 1.5) (Chebyshev-node
+// interpolant, 1.7e-16 relative), one reciprocal for the product (z-1)...(z-k).
+ALP_HD double rgamma_fast(double z) {
+    const double c[15] = {1.1283791670955126, -0.04117452644528216, -0.5266544355255445, 0.17510202604379396,
+                          0.05096686024771327, -0.04215516936245979, 0.006612897826512947, 0.002120731326787741,
+                          -0.00111073024865264, 0.00015235875380774502, 2.5355146572834772e-05, -1.3902747279703676e-05,
+                          2.1565111610410453e-06, 7.383394654158106e-08, -8.996935696824659e-08};
+    double w = z, scale = 1.0;
+    bool inv = false;
+    if (z < 1.0) { scale = z; w = z + 1.0; }               // 1/Gamma(z) = z / Gamma(z + 1)
+    else {
+        double prod = 1.0;
+        while (w >= 2.0) { w -= 1.0; prod *= w; inv = true; }      // Gamma(z) = (z-1)(z-2)...(w) Gamma(w)
+        scale = prod;
+    }
+    const double x = w - 1.5;
+    double p = c[14];
+#pragma unroll
+    for (int k = 13; k >= 0; --k) p = fma(p, x, c[k]);
+    return inv ? p * rcp_fast(scale) : p * scale;
+}
+
+// np.interp on a uniformly spaced abscissa: index from the spacing, verified against the table (falls back to the
+// binary search of interp() when the guess is off by more than one or the table is not uniform: inv_dx = 0)
+ALP_HD double interp_uniform(double x, const double* xp, const double* fp, int n, double left, double right, double inv_dx) {
+    if (!(inv_dx > 0.0) || n < 3 || !(x > xp[0]) || !(x < xp[n - 1])) return interp(x, xp, fp, n, left, right);
+    int i = (int)((x - xp[0]) * inv_dx);
+    i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+    if (x < xp[i]) { if (i > 0 && x >= xp[i - 1]) i = i - 1; else return interp(x, xp, fp, n, left, right); }
+    else if (!(x < xp[i + 1])) { if (i + 2 <= n - 1 && x < xp[i + 2]) i = i + 1; else return interp(x, xp, fp, n, left, right); }
+    if (xp[i] == x) return fp[i];
+    const double slope = (fp[i + 1] - fp[i]) / (xp[i + 1] - xp[i]);
+    double r = slope * (x - xp[i]) + fp[i];
+    if (r != r) return interp(x, xp, fp, n, left, right);
+    return r;
+}
+
+// track_length_prob with pow(L, y) = exp(y log L) from the exp table and 1/Gamma from rgamma_fast (fluxes.py:257-259)
+ALP_HD double resonance_term_fast(double u1, double u2, double eres, double emax, double max_t, const double* pos_e,
+                                  const double* pos_f, int n_pos, double inv_dx, const double* exp_tab = nullptr) {
+    const double e = eres + (emax - eres) * u1;
+    const double t = 0.0 + (max_t - 0.0) * u2;
+    const double z = (4.0 / 3.0) * t;
+    const double L = log(e / eres);
+    const double y = (z - 1) * log(L);
+    if (!(L > 0.0) || !(fabs(y) <= 700.0) || !(z > 1e-300) || !(z < 170.0))
+        return resonance_term(u1, u2, eres, emax, max_t, pos_e, pos_f, n_pos);
+    const double tl = fabs((exp_fast_core(y, exp_tab) * rgamma_fast(z)) * rcp_fast(e));
+    return interp_uniform(e, pos_e, pos_f, n_pos, 0.0, 0.0, inv_dx) * tl;
+}
+
 // ---- associated production e+ e- -> a gamma --------------------------------------------------------------------------------------
 enum PairRow { PA_S = 0, PA_P1P3, PA_E1E3, PA_E3, PA_P3, PA_GAM, PA_M03, PA_VOL, PA_DEN, PA_TMAX, PA_C, PA_NP };
 

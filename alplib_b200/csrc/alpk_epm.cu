@@ -63,18 +63,27 @@ brem_rows_kernel(const double* __restrict__ e0, const double* __restrict__ w0, u
 // ---------------------------------------------------------------------------------------------------------------
 // resonance: block-reduced Monte-Carlo integral
 // ---------------------------------------------------------------------------------------------------------------
-template <bool INJECT>
+template <bool INJECT, bool FAST>
 __global__ void __launch_bounds__(kThreads)
 resonance_kernel(const double* __restrict__ pos_e, const double* __restrict__ pos_f, int n_pos, double eres, double emax,
                  double max_t, uint64_t n, const double* __restrict__ uniforms, uint64_t seed, double* __restrict__ partials) {
     __shared__ double red[32];
+    __shared__ double s_tab[64];
+    double inv_dx = 0.0;
+    if (FAST) {
+        if (threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+        // uniformly spaced positron table (the usual linspace): index from the spacing instead of a binary search
+        const BinGuess g = detect_spacing(pos_e, n_pos);      // (contains the CTA-wide barriers that also publish s_tab)
+        inv_dx = g.mode == 1 ? g.scale : 0.0;
+    }
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     double acc = 0.0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double u1, u2;
         if (INJECT) { u1 = __ldg(uniforms + i); u2 = __ldg(uniforms + n + i); }
         else uniform_2(seed, kTagResonance, 0u, i, u1, u2);
-        acc += resonance_term(u1, u2, eres, emax, max_t, pos_e, pos_f, n_pos);
+        acc += FAST ? resonance_term_fast(u1, u2, eres, emax, max_t, pos_e, pos_f, n_pos, inv_dx, s_tab)
+                    : resonance_term(u1, u2, eres, emax, max_t, pos_e, pos_f, n_pos);
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
@@ -118,14 +127,16 @@ ALPK_EXPORT int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint
 }
 
 ALPK_EXPORT int alpk_resonance_sum(const double* pos_e, const double* pos_f, int n_pos, double e_res, double e_max,
-                                   double max_t, uint64_t n_samples, const double* uniforms, uint64_t seed,
+                                   double max_t, uint64_t n_samples, const double* uniforms, uint64_t seed, int fast,
                                    double* out_sum, double* scratch, void* stream) {
     if (!pos_e || !pos_f || n_pos < 1 || !out_sum || !scratch) { set_error("alpk_resonance_sum: bad argument"); return 2; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n_samples == 0) { cudaMemsetAsync(out_sum, 0, sizeof(double), st); return 0; }
     const int grid = grid_for(n_samples, kThreads * 4, 8);
-    if (uniforms) resonance_kernel<true><<<grid, kThreads, 0, st>>>(pos_e, pos_f, n_pos, e_res, e_max, max_t, n_samples, uniforms, seed, scratch);
-    else resonance_kernel<false><<<grid, kThreads, 0, st>>>(pos_e, pos_f, n_pos, e_res, e_max, max_t, n_samples, uniforms, seed, scratch);
+#define ALPK_RES(I, F) resonance_kernel<I, F><<<grid, kThreads, 0, st>>>(pos_e, pos_f, n_pos, e_res, e_max, max_t, n_samples, uniforms, seed, scratch)
+    if (uniforms) { if (fast) ALPK_RES(true, true); else ALPK_RES(true, false); }
+    else { if (fast) ALPK_RES(false, true); else ALPK_RES(false, false); }
+#undef ALPK_RES
     if (check_launch("alpk_resonance_sum")) return 1;
     return finalize_sum(scratch, grid, out_sum, st);
 }

@@ -781,7 +781,8 @@ class FluxResonanceIsotropic(AxionFlux):
             d_e, d_f = rt.upload(pf[:, 0]), rt.upload(pf[:, 1])
             total = rt.empty(1)
             N.call("alpk_resonance_sum", N.ptr(d_e), N.ptr(d_f), int(pf.shape[0]), float(resonant_energy), float(emax),
-                   float(self.max_t), ns, N.ptr(d_u), C.c_uint64(seed), N.ptr(total), N.ptr(rt.scratch), rt.stream())
+                   float(self.max_t), ns, N.ptr(d_u), C.c_uint64(seed), 0 if self.precision == "faithful" else 1,
+                   N.ptr(total), N.ptr(rt.scratch), rt.stream())
             s = float(total.item())
         mc_vol = self.max_t*(emax - resonant_energy)                             # :439
         attenuated_flux = mc_vol*s/self.n_samples                                # :441

@@ -226,8 +226,8 @@ int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint32_t n_sampl
  * n_samples draws (E_i, t_i) ~ U(E_res, E_max) x U(0, max_t); the caller applies the scalar prefactors (:441-442).
  * uniforms (parity mode): [2][n_samples] -- the E draws then the t draws (:437-438). */
 int alpk_resonance_sum(const double* pos_e, const double* pos_f, int n_pos, double e_res, double e_max, double max_t,
-                       uint64_t n_samples, const double* uniforms, uint64_t seed, double* out_sum, double* scratch,
-                       void* stream);
+                       uint64_t n_samples, const double* uniforms, uint64_t seed, int fast, double* out_sum, double* scratch,
+                       void* stream);   /* fast: 1 = fast arithmetic mode (<= 1e-9 relative: exp-table pow, polynomial 1/Gamma) */
 
 /* ---- associated production e+ e- -> a gamma: fluxes.py:503-518, cross_section_mc.py:192-240, matrix_element.py:717-734 -- */
 typedef struct {

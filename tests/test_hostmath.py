@@ -490,3 +490,26 @@ def test_pairann_fast_production(hostcheck):
         assert ok.mean() > 0.9
         assert max_rel(fast[:n][ok], ref[:n][ok]) < 1e-12, ma
         assert max_rel(fast[n:][ok], ref[n:][ok], floor=1e-300) < TOL, ma
+
+
+def test_resonance_fast_term(hostcheck):
+    """Fast-mode resonance term (exp-table pow, polynomial 1/Gamma, spacing-guessed np.interp) against the reference-order
+    term, uniform and non-uniform positron tables; 1/Gamma against scipy over the range reached (and beyond)."""
+    from scipy.special import gamma
+    hostcheck.hc_rgamma_fast.restype = C.c_double
+    z = np.concatenate([10 ** np.random.default_rng(2).uniform(-8, np.log10(30.0), 4000), [1.0, 2.0, 3.0, 1.5, 6.6667, 1e-12]])
+    r = np.array([hostcheck.hc_rgamma_fast(C.c_double(v)) for v in z])
+    assert max_rel(r, 1.0 / gamma(z)) < 1e-14
+    rng = np.random.default_rng(5)
+    n = 50000
+    u = rng.random(2 * n)
+    for uniform in (True, False):
+        pe = np.linspace(10.0, 5000.0, 200) if uniform else np.sort(10 ** rng.uniform(1, 3.7, 200))
+        pfl = 3e11 * np.exp(-pe / 600.0)
+        inv_dx = 1.0 / ((pe[-1] - pe[0]) / (pe.shape[0] - 1)) if uniform else 0.0
+        for eres, emax, max_t in ((97.3, 5000.0, 5.0), (10.0, 4000.0, 5.0), (2000.0, 6000.0, 3.0)):
+            ref, fast = np.empty(n), np.empty(n)
+            hostcheck.hc_resonance_terms(dptr(pe), dptr(pfl), pe.shape[0], C.c_double(eres), C.c_double(emax), C.c_double(max_t),
+                                         C.c_uint64(n), dptr(u), C.c_double(inv_dx), dptr(ref), dptr(fast))
+            assert max_rel(fast, ref, floor=1e-300) < TOL, (uniform, eres)
+            assert abs(fast.sum() / ref.sum() - 1) < 1e-13
