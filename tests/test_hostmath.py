@@ -513,3 +513,25 @@ def test_resonance_fast_term(hostcheck):
                                          C.c_uint64(n), dptr(u), C.c_double(inv_dx), dptr(ref), dptr(fast))
             assert max_rel(fast, ref, floor=1e-300) < TOL, (uniform, eres)
             assert abs(fast.sum() / ref.sum() - 1) < 1e-13
+
+
+@pytest.mark.parametrize("regime", ["long_lived", "short_lived", "stable", "very_short"])
+def test_propagate_fast_regimes(hostcheck, regime):
+    """The fast propagate in every lifetime regime against the oracle: long-lived (single range test), short-lived (each
+    exponential on its own, exact zeros below -746, library path only in the denormal band), stable (width 0) and so
+    short-lived that every sample is fully decayed -- energies from threshold to 1e6 MeV, element by element."""
+    ma = 10.0
+    width = {"long_lived": 1e-22, "short_lived": 4e-13, "stable": 0.0, "very_short": 1e-3}[regime]
+    rng = np.random.default_rng(17)
+    e = np.concatenate([ma * (1 + 10 ** rng.uniform(-9, 0, 3000)), 10 ** rng.uniform(np.log10(2 * ma), 6, 3000)])
+    w = 10 ** rng.uniform(-5, 8, e.shape[0])
+    prop = P.prop_params(ma, width, 1.7, 574.0, 5.0, geom_accept=GA, fast=True)
+    d32, s32, d64, s64 = run_propagate(hostcheck, e, w, prop)
+    with np.errstate(all="ignore"):
+        p = O.propagate(e, w, ma, width, 1.7, 574.0, 5.0)
+    assert max_rel(s64, p["scatter_w64"], floor=1e-300) < TOL
+    assert_decay_close(d64, p["decay_w64"], p["scatter_w64"], TOL)
+    if regime == "very_short":
+        assert np.all(s64 == 0) and np.all(p["scatter_w64"] == 0)
+    if regime == "short_lived":
+        assert 0 < np.count_nonzero(s64 == 0) < e.shape[0]          # both the exact-zero and the regular branch are exercised
