@@ -61,7 +61,7 @@ class PairAnnT(C.Structure):
 class PairGammaT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("ma4", C.c_double), ("me2", C.c_double), ("me4", C.c_double),
                 ("ep_min", C.c_double), ("nt", C.c_double), ("zc", C.c_double), ("n_samples", C.c_double),
-                ("max_t", C.c_double)]
+                ("max_t", C.c_double), ("fast", C.c_int)]
 
 
 class Meson3T(C.Structure):

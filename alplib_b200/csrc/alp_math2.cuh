@@ -322,12 +322,22 @@ struct PairGammaGlobals {
     double zc;                // z*4*pi*ALPHA*g**2  (left to right)
     double n_samples;
     double max_t;             // 5.0 radiation lengths (fluxes.py:1099,1103)
+    int fast;                 // fast arithmetic mode of the track-length factor (exp-table pow, polynomial 1/Gamma)
 };
 
 // fluxes.py:1078-1080 (note heaviside(., 0.0) here, 1.0 in the module-level track_length_prob)
 ALP_HD double track_length_prob0(double ei, double ef, double t) {
     const double b = 4.0 / 3.0;
     return heaviside(ei - ef, 0.0) * fabs(pow(log(ei / ef), b * t - 1) / (ei * tgamma(b * t)));
+}
+
+// Fast mode of the same factor (<= 1e-9 relative): pow(L, y) = exp(y log L) from the exp table, 1/Gamma from rgamma_fast.
+ALP_HD double track_length_prob0_fast(double ei, double ef, double t) {
+    const double z = (4.0 / 3.0) * t;
+    const double L = log(ei / ef);
+    const double y = (z - 1) * log(L);
+    if (!(ei > ef) || !(L > 0.0) || !(fabs(y) <= 700.0) || !(z > 1e-300) || !(z < 170.0)) return track_length_prob0(ei, ef, t);
+    return fabs((exp_fast_core(y) * rgamma_fast(z)) * rcp_fast(ei));
 }
 
 // prod_xs.py:109-129
@@ -355,7 +365,7 @@ ALP_HD double pairgamma_sample(double u1, double u2, double u3, double e_lab, do
                                const PairGammaGlobals& g, double& flux) {
     const double t = 0.0 + (g.max_t - 0.0) * u1;                                 // fluxes.py:1099
     const double ep = g.ep_min + (e_lab - g.ep_min) * u2;                        // :1100
-    const double fw = flux_c * track_length_prob0(e_lab, ep, t);                 // :1102, :1085-1086
+    const double fw = flux_c * (g.fast ? track_length_prob0_fast(e_lab, ep, t) : track_length_prob0(e_lab, ep, t));   // :1102, :1085-1086
     const double pos_flux = (((width * 5.0) * (e_lab - g.ep_min)) * fw) / g.n_samples;   // :1103
     const double beta = sqrt(ep * ep - g.me2) / (kME + ep);                      // :1118
     const double gam = pow(1 - beta * beta, -0.5);

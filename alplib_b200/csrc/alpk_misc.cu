@@ -110,7 +110,7 @@ ALPK_EXPORT int alpk_pairgamma(const double* centers, const double* widths, uint
     if ((u_bins == nullptr) != (u_alp == nullptr)) { set_error("alpk_pairgamma: inject both uniform blocks or none"); return 2; }
     PairGammaGlobals g;
     g.ma = h_par->ma; g.ma2 = h_par->ma2; g.ma4 = h_par->ma4; g.me2 = h_par->me2; g.me4 = h_par->me4; g.ep_min = h_par->ep_min;
-    g.nt = h_par->nt; g.zc = h_par->zc; g.n_samples = h_par->n_samples; g.max_t = h_par->max_t;
+    g.nt = h_par->nt; g.zc = h_par->zc; g.n_samples = h_par->n_samples; g.max_t = h_par->max_t; g.fast = h_par->fast;
     pairgamma_kernel<<<grid_for(n_bins * (uint64_t)n_samples, kThreads, 8), kThreads, 0, (cudaStream_t)stream>>>(
         centers, widths, n_bins, n_samples, bin_ids, pos_e, pos_f, n_pos, g, u_bins, u_alp, seed, out_energy, out_flux);
     return check_launch("alpk_pairgamma");

@@ -1016,6 +1016,7 @@ class FluxPairAnnihilationGamma(AxionFlux):
         par.nt = float(self.ntarget_area_density * HBARC**2)
         par.zc = float(self.target_z * 4*pi*ALPHA*self.gagamma**2)
         par.n_samples, par.max_t = float(ns), 5.0
+        par.fast = 0 if self.precision == "faithful" else 1
         seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
         rt = self._rt
         n = nb * ns

@@ -287,6 +287,7 @@ typedef struct {
     double zc;               /* z*4*pi*ALPHA*g**2 */
     double n_samples;
     double max_t;            /* 5.0 */
+    int fast;                /* 1: fast arithmetic mode of the track-length factor (<= 1e-9 relative) */
 } alpk_pairgamma_t;
 int alpk_pairgamma(const double* centers, const double* widths, uint64_t n_bins, uint32_t n_samples,
                    const uint32_t* bin_ids, const double* pos_e, const double* pos_f, int n_pos,

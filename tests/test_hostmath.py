@@ -290,7 +290,8 @@ def test_exp_fast_accuracy(hostcheck):
     assert np.array_equal(o[~np.isnan(e)], e[~np.isnan(e)]) and np.isnan(o[4])
 
 
-def test_pairgamma(hostcheck):
+@pytest.mark.parametrize("fast", [0, 1])
+def test_pairgamma(hostcheck, fast):
     g = load_golden("pairgamma")
     pf, ma, gg, ns = g["positron_flux"], float(g["ma"]), float(g["g"]), int(g["n_samples"])
     widths, centers = pf[1:, 0] - pf[:-1, 0], (pf[1:, 0] + pf[:-1, 0]) / 2
@@ -302,6 +303,7 @@ def test_pairgamma(hostcheck):
     par.nt = float(g["rad_length"]) * O.AVOGADRO / (2 * 6) * O.HBARC ** 2
     par.zc = np.int64(6) * 4 * np.pi * O.ALPHA * gg ** 2
     par.n_samples, par.max_t = float(ns), 5.0
+    par.fast = fast
     nb = int(keep.sum()); n = nb * ns
     u = np.ascontiguousarray(g["uniforms"])
     assert u.shape[0] == 3 * n and 0 < nb <= centers.shape[0]
