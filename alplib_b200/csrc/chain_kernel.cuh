@@ -19,6 +19,9 @@ namespace alpk {
 #ifndef ALPK_MIN_BLOCKS
 #define ALPK_MIN_BLOCKS 4
 #endif
+#ifndef ALPK_GRID_PER_SM
+#define ALPK_GRID_PER_SM 8
+#endif
 #ifndef ALPK_INNER_UNROLL
 #define ALPK_INNER_UNROLL 1
 #endif
@@ -309,7 +312,7 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     // rows per tile <= tile/n_samples + 2 must fit the shared-memory stage
     uint64_t te = (uint64_t)(kStageRows - 2) * n_samples;
     a.tile_elems = (uint32_t)(te >= (uint64_t)kTile ? (uint64_t)kTile : (te < 2 ? 2 : (te & ~1ull)));
-    const int grid = grid_for(n, (int)a.tile_elems, 8);
+    const int grid = grid_for(n, (int)a.tile_elems, ALPK_GRID_PER_SM);
     const bool inj = uniforms != nullptr;
     const bool fast = fast_mode != 0;
     // the PAIRED / output-set specialisations exist for the production configuration (fast arithmetic, free-running RNG,
