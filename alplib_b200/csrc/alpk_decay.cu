@@ -372,9 +372,9 @@ vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __re
                const double* __restrict__ bden, const double* __restrict__ jac, uint32_t n_points, uint32_t chunk,
                double ma, double ma2, double width, double inv_mbm, double* __restrict__ partials) {
     __shared__ double s_x[kVolTile], s_b[kVolTile], s_j[kVolTile];
-    __shared__ double s_tab[64];                     // exp_fast table
+    __shared__ double s_tab[alp::kExpTabSize];                     // exp_fast table
     __shared__ unsigned long long s_xmax_bits;       // fast mode: largest |x| of the staged tile (ordered bits)
-    if (FAST && threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    if (FAST && threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t k0 = blockIdx.y * chunk;
     const uint32_t k1 = (k0 + chunk < n_points) ? k0 + chunk : n_points;

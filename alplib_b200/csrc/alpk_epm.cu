@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(kThreads)
 resonance_kernel(const double* __restrict__ pos_e, const double* __restrict__ pos_f, int n_pos, double eres, double emax,
                  double max_t, uint64_t n, const double* __restrict__ uniforms, uint64_t seed, double* __restrict__ partials) {
     __shared__ double red[32];
-    __shared__ double s_tab[64];
+    __shared__ double s_tab[alp::kExpTabSize];
     double inv_dx = 0.0;
     if (FAST) {
-        if (threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+        if (threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
         // uniformly spaced positron table (the usual linspace): index from the spacing instead of a binary search
         const BinGuess g = detect_spacing(pos_e, n_pos);      // (contains the CTA-wide barriers that also publish s_tab)
         inv_dx = g.mode == 1 ? g.scale : 0.0;

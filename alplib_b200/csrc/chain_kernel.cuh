@@ -198,7 +198,7 @@ chain_kernel(const ChainArgs<Prod> a) {
     constexpr int NP = Prod::NP;
     __shared__ double s_rows[kStageRows * NP];
     __shared__ double red[32];
-    __shared__ double s_tab[64];                     // exp_fast table (fast mode)
+    __shared__ double s_tab[alp::kExpTabSize];                     // exp_fast table (fast mode)
     extern __shared__ double s_hist_mem[];           // [n_edges] edges + [n_edges-1] privatised bins (only if a.hist)
     double* s_edges = s_hist_mem;
     double* s_bins_all = s_hist_mem + a.n_edges;
@@ -211,7 +211,7 @@ chain_kernel(const ChainArgs<Prod> a) {
         guess = detect_spacing(s_edges, a.n_edges);
         if (a.hist_copies > 1) s_bins = s_bins_all + (threadIdx.x >> 5) * (a.n_edges - 1);
     }
-    if (FAST && threadIdx.x < 64) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    if (FAST && threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
     // (all made visible by the __syncthreads of the first tile)
     const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
     const uint32_t tile_elems = a.tile_elems;        // kTile, or fewer when rows are so short that a full tile would

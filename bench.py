@@ -410,7 +410,7 @@ def run_gpu(args):
             pass
         # issue-slot model: an FP64 instruction holds the issue port of its SM sub-partition for two
         # cycles; instruction counts per sample from the ncu source page of this kernel (profiles/ncu_r1_hot_kernels.txt)
-        n_fp64, n_other = 62, 95
+        n_fp64, n_other = 60, 95
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         cyc = kms * 1e-3 * sm_mhz * 1e6 * rt.sm_count * 4 / (n_compton / 32.0)
         issue = {"fp64_instr_per_sample": n_fp64, "other_instr_per_sample": n_other,
@@ -428,7 +428,7 @@ def run_gpu(args):
                              "peak_source": "DFMA loop measured in this run (alpk_fp64_peak)",
                              "note": "the kernel is instruction-issue bound (an FP64 instruction holds the issue port "
                                      "for two cycles), not HBM bound; flops use SURVEY section 8d's expanded accounting "
-                                     "(div 8, sqrt 10, exp 25), the kernel itself executes ~62 FP64 + ~95 other "
+                                     "(div 8, sqrt 10, exp 25), the kernel itself executes ~60 FP64 + ~95 other "
                                      "instructions per sample (profiles/ncu_r1_hot_kernels.txt)"}}
         # ---- CPU baseline beside it (bounded sample, 1 core) -------------------------------------------------------------
         ns_cpu = 1000
