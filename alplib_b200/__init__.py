@@ -15,5 +15,9 @@ from .fluxes import *               # noqa: F401,F403
 from .meson_fluxes import (FluxChargedMeson3BodyIsotropic, FluxChargedMeson3BodyDecay, M2Meson3BodyDecay,   # noqa: F401
                            FluxAxionMesonMixing)
 from .generators import PhotonEventGenerator, ElectronEventGenerator   # noqa: F401
+from .form_factors import AtomicElasticFF   # noqa: F401
+from .matrix_element import (MatrixElement2, M2Compton, M2InverseCompton, M2InversePrimakoff, M2Primakoff,   # noqa: F401
+                             M2AssociatedProduction)
+from .cross_section_mc import Scatter2to2MC, lorentz_boost   # noqa: F401
 
 __version__ = "0.1.0"

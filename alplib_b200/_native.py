@@ -10,7 +10,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ALPK_LIB_PATH") or os.path.join(_HERE, "libalpk.so")   # override: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_pairann.cu", "alpk_scan.cu", "alpk_misc.cu", "alpk_meson.cu"]
+SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_pairann.cu", "alpk_scan.cu", "alpk_misc.cu", "alpk_meson.cu",
+           "alpk_scatter2.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
@@ -68,6 +69,19 @@ class Meson3T(C.Structure):
     _fields_ = [("mm", C.c_double), ("ma", C.c_double), ("fM", C.c_double), ("ckm", C.c_double),
                 ("total_width", C.c_double), ("c0", C.c_double), ("coupling", C.c_double), ("a", C.c_double),
                 ("b", C.c_double), ("d", C.c_double), ("pref", C.c_double), ("n_samples", C.c_double), ("model", C.c_int)]
+
+
+class M2T(C.Structure):
+    _fields_ = [("model", C.c_int), ("ma2", C.c_double), ("ma4", C.c_double), ("mN2", C.c_double), ("mN4", C.c_double),
+                ("z", C.c_double), ("ff_a2", C.c_double), ("pref", C.c_double), ("me2", C.c_double), ("me4", C.c_double),
+                ("tmax", C.c_double)]
+
+
+class Scatter2T(C.Structure):
+    _fields_ = [("m2", M2T), ("s", C.c_double), ("msum", C.c_double), ("pp", C.c_double), ("ee", C.c_double),
+                ("p3_cm", C.c_double), ("e3_cm", C.c_double), ("vol", C.c_double), ("p1_cm", C.c_double),
+                ("n_samples", C.c_double), ("den", C.c_double), ("mat", C.c_double * 16), ("p12", C.c_double * 4),
+                ("log_sampling", C.c_int)]
 
 
 MESON3_NP = 13
@@ -170,6 +184,9 @@ _SIGNATURES = {
     "alpk_meson_mixing": ([_P, _U64, _D, _D, _D, _P, _P, _P, _P, _P], _I),
     "alpk_meson3_m2": ([_D, _P, _U64, _D, C.POINTER(Meson3T), _P, _P], _I),
     "alpk_pairgamma": ([_P, _P, _U64, _U32, _P, _P, _P, _I, C.POINTER(PairGammaT), _P, _P, _U64, _P, _P, _P], _I),
+    "alpk_m2_eval": ([C.POINTER(M2T), _P, _U64, _P, _U64, _D, _P, _P], _I),
+    "alpk_atomic_ff2": ([_P, _U64, _D, _D, _P, _P], _I),
+    "alpk_scatter2to2": ([C.POINTER(Scatter2T), _U64, _P, _U64, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "alpk_scale": ([_P, _U64, _D, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),

@@ -73,10 +73,13 @@ ALP_HD PhiloxKeys philox_keys(uint64_t seed) {
     return rk;
 }
 
+#ifndef ALPK_PHILOX_ROUNDS
+#define ALPK_PHILOX_ROUNDS 10          // (kernel-variant experiments only: the stream definition is Philox4x32-10)
+#endif
 ALP_HD Philox4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& rk) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ALPK_PHILOX_ROUNDS; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo32(M0, c0, hi0, lo0);
         mulhilo32(M1, c2, hi1, lo1);

@@ -276,6 +276,11 @@ alp::PropConst to_prop(const alpk_prop_t* p);
 alp::EventConst to_event(const alpk_event_t* e);
 int finalize_sum(const double* partials, int n, double* out, cudaStream_t st);
 
+// Row-aligned warp-unit kernel (chain_rows.cuh); returns -1 when the configuration is not one it covers.
+template <class Prod>
+int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool standard, bool noevents, bool none,
+                      double* rate, double* scratch, cudaStream_t st);
+
 // Host-side launcher shared by every production channel.
 template <class Prod>
 int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
@@ -322,6 +327,10 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const bool standard = out_energy && out_flux && !decay_w64 && !scatter_w64 && (stage < 1 || (decay_w32 && scatter_w32)) &&
                           (stage < 2 || event_w);
     const bool noevents = stage == 2 && out_energy && out_flux && decay_w32 && scatter_w32 && !decay_w64 && !scatter_w64 && !event_w;
+    if (fast && paired && !inj && !hist) {
+        const int rc = launch_chain_rows<Prod>(what, a, stage, standard, noevents, none, rate, scratch, st);
+        if (rc >= 0) return rc;
+    }
 #define ALPK_CHAIN_LAUNCH(I, S, F, H, P, O, SH) chain_kernel<Prod, I, S, F, H, P, O, SH><<<grid, kThreads, smem, st>>>(a)
 #define ALPK_CHAIN_PAIRED(S, O) { if (S >= 1 && a.prop.short_lived) ALPK_CHAIN_LAUNCH(false, S, true, false, true, O, true); \
                                   else ALPK_CHAIN_LAUNCH(false, S, true, false, true, O, false); }
@@ -349,3 +358,5 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
 }
 
 }  // namespace alpk
+
+#include "chain_rows.cuh"

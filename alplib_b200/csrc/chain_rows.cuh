@@ -1,0 +1,197 @@
+// Row-aligned variant of the per-sample chain kernel for the production configuration: fast arithmetic, free-running
+// Philox, even n_samples, rows of at least kRowsMinSamples samples, no fused histogram.
+//
+//   Work unit = (row, chunk of the row's sample pairs), owned by ONE WARP: a unit never straddles two rows, so
+//     * the row record is loaded once per unit into registers (warp-uniform __ldg, no shared-memory staging) -- the
+//       tile loop of chain_kernel needs two __syncthreads per tile and a per-pair row select;
+//     * the Philox counter of a pair is its pair index within the row and the row id is a per-unit constant;
+//     * there is no CTA-level synchronisation in the loop at all: warps drift apart, which spreads their integer
+//       (Philox) and FP64 phases over the sub-partition's issue slots.
+//   Units are handed out dynamically (one atomicAdd per unit, fetched one unit ahead so its latency is hidden), which
+//   removes the tail of a static tile->CTA assignment; the counter is reset by the finalize kernel of the same launch.
+//
+// The per-sample arithmetic is the same inline code as chain_kernel's fast path (Prod::sample_fast, propagate_try_fast,
+// decay_event_weight_coupled), and sample s of a row uses the same Philox counter / words, so both kernels produce the
+// same bits for every per-sample output; only the order of the rate sum differs.
+#pragma once
+#include "chain_kernel.cuh"
+#include <stdlib.h>
+
+namespace alpk {
+
+#ifndef ALPK_ROWS_MIN_BLOCKS
+#define ALPK_ROWS_MIN_BLOCKS 3
+#endif
+#ifndef ALPK_ROWS_THREADS
+#define ALPK_ROWS_THREADS 256
+#endif
+#ifndef ALPK_ROWS_UNROLL
+#define ALPK_ROWS_UNROLL 1
+#endif
+#ifndef ALPK_ROWS_CHUNK_PAIRS
+#define ALPK_ROWS_CHUNK_PAIRS 512          // target pairs per unit (16 warp iterations)
+#endif
+constexpr int kRowsThreads = ALPK_ROWS_THREADS;
+constexpr int kRowsUnroll = ALPK_ROWS_UNROLL;
+constexpr uint32_t kRowsMinSamples = 256;   // shorter rows stay with the tile kernel (units would be mostly lane padding)
+
+struct RowsGeom {
+    uint32_t chunks_per_row;     // units per row
+    uint32_t pairs_per_chunk;    // pairs per unit (the last unit of a row may hold fewer)
+    uint32_t pairs_per_row;      // n_samples / 2
+    uint32_t n_units_lo, n_units_hi;   // n_rows * chunks_per_row as two words
+    unsigned long long* counter; // dynamic unit counter (zero on entry; the finalize kernel re-zeroes it)
+};
+
+template <class Prod, int STAGE, int OUT, bool SHORT>
+__global__ void __launch_bounds__(kRowsThreads, ALPK_ROWS_MIN_BLOCKS)
+chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
+    using namespace alp;
+    constexpr int NP = Prod::NP;
+    __shared__ double s_tab[alp::kExpTabSize];
+    __shared__ double red[32];
+    for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = kExpTabDev[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_units = ((uint64_t)geo.n_units_hi << 32) | geo.n_units_lo;
+    const uint64_t n_warps = (uint64_t)gridDim.x * (kRowsThreads / 32);
+    double acc = 0.0;
+
+    uint64_t unit = (uint64_t)blockIdx.x * (kRowsThreads / 32) + (threadIdx.x >> 5);
+    // the first n_warps units are assigned statically; with a counter the further ones are handed out dynamically,
+    // fetched one unit ahead so that the atomic's latency is hidden behind the current unit
+    const bool dynamic = geo.counter != nullptr;
+    uint64_t next = unit + n_warps;
+    if (dynamic) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(geo.counter, 1ull);
+        next = n_warps + __shfl_sync(0xffffffffu, t, 0);
+    }
+    const bool small = geo.n_units_hi == 0u;
+    while (unit < n_units) {
+        unsigned long long fetched = 0;
+        if (dynamic && lane == 0 && next < n_units) fetched = atomicAdd(geo.counter, 1ull);
+        uint64_t r;
+        uint32_t c;
+        if (small) { const uint32_t r32 = (uint32_t)unit / geo.chunks_per_row; r = r32; c = (uint32_t)unit - r32 * geo.chunks_per_row; }
+        else { r = unit / geo.chunks_per_row; c = (uint32_t)(unit - r * geo.chunks_per_row); }
+        const uint32_t p_begin = c * geo.pairs_per_chunk;
+        const uint32_t p_stop = min(p_begin + geo.pairs_per_chunk, geo.pairs_per_row);
+        double row[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) row[k] = __ldg(a.table + r * NP + k);
+        const uint32_t rid = a.row_ids ? __ldg(a.row_ids + r) : (uint32_t)r;
+        const uint64_t base = r * (uint64_t)a.n_samples;
+
+#pragma unroll kRowsUnroll
+        for (uint32_t p = p_begin + lane; p < p_stop; p += 32u) {
+            const Philox4 q = philox4x32_10_rk(p, 0u, rid, Prod::kTag, a.rk);     // sample s: counter s>>1, words 2(s&1)..
+            double u[2], e[2], f[2], d64v[2], s64v[2], evv[2];
+            float d32v[2], s32v[2];
+            u[0] = u53(q.x, q.y);
+            u[1] = u53(q.z, q.w);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) e[j] = Prod::sample_fast(u[j], row, a.g, f[j], s_tab);
+            if (STAGE >= 1) {
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) ok &= propagate_try_fast<SHORT>(e[j], f[j], a.prop, d64v[j], s64v[j], s_tab);
+                if (!ok) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    d32v[j] = prop_cast_fast(d64v[j], a.prop);
+                    s32v[j] = prop_cast_fast(s64v[j], a.prop);
+                }
+            }
+            if (STAGE >= 2) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    evv[j] = decay_event_weight_coupled(e[j], d32v[j], a.ev);
+                    acc += evv[j];
+                }
+            }
+            if (OUT != kOutNone) {
+                constexpr bool kAll = OUT == kOutStandard || OUT == kOutNoEvents;
+                constexpr bool kEvw = OUT == kOutStandard;
+                const uint64_t i0 = base + 2ull * p;
+                if (kAll || a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
+                if (kAll || a.out_f) *reinterpret_cast<double2*>(a.out_f + i0) = make_double2(f[0], f[1]);
+                if (STAGE >= 1) {
+                    if (kAll || a.d32) *reinterpret_cast<float2*>(a.d32 + i0) = make_float2(d32v[0], d32v[1]);
+                    if (kAll || a.s32) *reinterpret_cast<float2*>(a.s32 + i0) = make_float2(s32v[0], s32v[1]);
+                    if (!kAll && a.d64) *reinterpret_cast<double2*>(a.d64 + i0) = make_double2(d64v[0], d64v[1]);
+                    if (!kAll && a.s64) *reinterpret_cast<double2*>(a.s64 + i0) = make_double2(s64v[0], s64v[1]);
+                }
+                if (STAGE >= 2 && (kEvw || (OUT == kOutGeneric && a.event_w)))
+                    *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
+            }
+        }
+        unit = next;
+        // (a warp that did not fetch -- next was already past the end -- ends with unit >= n_units)
+        next = dynamic ? (next < n_units ? n_warps + __shfl_sync(0xffffffffu, fetched, 0) : next) : next + n_warps;
+    }
+    if (STAGE >= 2) {
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) a.partials[blockIdx.x] = acc;
+    }
+}
+
+// Geometry of the units for a given row length.
+inline RowsGeom rows_geometry(uint64_t n_rows, uint32_t n_samples, unsigned long long* counter) {
+    RowsGeom g;
+    g.pairs_per_row = n_samples / 2u;
+    g.chunks_per_row = (g.pairs_per_row + ALPK_ROWS_CHUNK_PAIRS - 1) / ALPK_ROWS_CHUNK_PAIRS;
+    // equal-sized units, rounded up to whole warp iterations
+    uint32_t ppc = (g.pairs_per_row + g.chunks_per_row - 1) / g.chunks_per_row;
+    ppc = (ppc + 31u) & ~31u;
+    g.pairs_per_chunk = ppc;
+    g.chunks_per_row = (g.pairs_per_row + ppc - 1) / ppc;
+    const uint64_t n_units = n_rows * (uint64_t)g.chunks_per_row;
+    g.n_units_lo = (uint32_t)n_units; g.n_units_hi = (uint32_t)(n_units >> 32);
+    g.counter = counter;
+    return g;
+}
+
+inline int chain_rows_mode() {
+    // ALPK_CHAIN_ROWS=0 keeps every launch on the tile kernel, 2 = row kernel with static unit assignment (A/B timing and
+    // the kernel-vs-kernel bit-identity test); default 1.  Read per launch so a test can flip it.
+    const char* e = getenv("ALPK_CHAIN_ROWS");
+    return e ? atoi(e) : 1;
+}
+
+template <class Prod>
+int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool standard, bool noevents, bool none,
+                      double* rate, double* scratch, cudaStream_t st) {
+    const int mode = chain_rows_mode();
+    if (!mode || a.n_samples < kRowsMinSamples) return -1;
+    unsigned long long* counter = nullptr;
+    if (mode != 2 && scratch) {                 // (mode 2: static unit assignment, for A/B timing)
+        counter = reinterpret_cast<unsigned long long*>(scratch + 2 * kMaxPartials);
+        cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    }
+    const RowsGeom geo = rows_geometry(a.n_rows, a.n_samples, counter);
+    const uint64_t n_units = ((uint64_t)geo.n_units_hi << 32) | geo.n_units_lo;
+    uint64_t blocks = (n_units + (kRowsThreads / 32) - 1) / (kRowsThreads / 32);
+    const uint64_t cap = (uint64_t)sm_count() * ALPK_ROWS_MIN_BLOCKS;
+    if (blocks > cap) blocks = cap;
+    const int grid = (int)blocks;
+    const bool sh = stage >= 1 && a.prop.short_lived;
+#define ALPK_ROWS_LAUNCH(S, O) { if (sh) chain_rows_kernel<Prod, S, O, true><<<grid, kRowsThreads, 0, st>>>(a, geo); \
+                                 else chain_rows_kernel<Prod, S, O, false><<<grid, kRowsThreads, 0, st>>>(a, geo); }
+#define ALPK_ROWS_CASE(S)                                                  \
+    if (standard) ALPK_ROWS_LAUNCH(S, kOutStandard)                        \
+    else if (S == 2 && noevents) ALPK_ROWS_LAUNCH(S, kOutNoEvents)         \
+    else if (none) ALPK_ROWS_LAUNCH(S, kOutNone)                           \
+    else ALPK_ROWS_LAUNCH(S, kOutGeneric)
+    if (stage == 0) { ALPK_ROWS_CASE(0) } else if (stage == 1) { ALPK_ROWS_CASE(1) } else { ALPK_ROWS_CASE(2) }
+#undef ALPK_ROWS_LAUNCH
+#undef ALPK_ROWS_CASE
+    if (check_launch(what)) return 1;
+    if (stage == 2) return finalize_sum(scratch, grid, rate, st);
+    return 0;
+}
+
+}  // namespace alpk

@@ -370,6 +370,54 @@ int alpk_meson_mixing(const double* p4, uint64_t n, double ma, double det_sa, do
 int alpk_meson3_m2(double m122, const double* m232, uint64_t n, double lepton_mass, const alpk_meson3_t* h_par, double* out,
                    void* stream);
 
+/* ---- generic 2 -> 2 scattering MC: cross_section_mc.py:148-275 (Scatter2to2MC.scatter_sim, dsigma_dt,
+ * get_cosine_lab_weights, get_e3_lab_weights, get_e4_lab_weights) with the squared matrix elements of
+ * matrix_element.py:629-734 (M2Compton, M2InverseCompton, M2InversePrimakoff, M2Primakoff, M2AssociatedProduction) and the
+ * atomic elastic form factor form_factors.py:54-64; usage README.md:144-158. ------------------------------------------ */
+enum { ALPK_M2_INVERSE_PRIMAKOFF = 0, ALPK_M2_PRIMAKOFF = 1, ALPK_M2_INVERSE_COMPTON = 2, ALPK_M2_COMPTON = 3,
+       ALPK_M2_ASSOCIATED_PRODUCTION = 4 };
+
+typedef struct {
+    int    model;            /* ALPK_M2_* */
+    double ma2, ma4;         /* ma**2, ma**4 */
+    double mN2, mN4;         /* mN**2, mN**4 (Primakoff-type) */
+    double z;                /* atomic number */
+    double ff_a2;            /* a**2 of AtomicElasticFF (form_factors.py:63) */
+    double pref;             /* prefactor incl. coupling_product**2: z*4*pi*ALPHA*cp^2 | 2*cp^2 | cp^2 | pi*ALPHA*cp^2 */
+    double me2, me4;         /* M_E**2, M_E**4 */
+    double tmax;             /* associated production: soft-photon cut (matrix_element.py:729-731) */
+} alpk_m2_t;
+
+/* out[i] = M2(s[i*s_stride], t[i]) (den == 0) or M2/den (dsigma_dt, cross_section_mc.py:184-185 with
+ * den = 16*pi*(s-(m1+m2)^2)*(s-(m1-m2)^2)); s_stride 0 broadcasts one s. */
+int alpk_m2_eval(const alpk_m2_t* h_m2, const double* s, uint64_t s_stride, const double* t, uint64_t n, double den,
+                 double* out, void* stream);
+
+/* AtomicElasticFF.__call__ (form_factors.py:61-64): out[i] = (z*(q^2 a2)/(1 + q^2 a2))^2 */
+int alpk_atomic_ff2(const double* q, uint64_t n, double z, double a2, double* out, void* stream);
+
+typedef struct {
+    alpk_m2_t m2;
+    double s;                /* (lv_p1 + lv_p2).mass2() */
+    double msum;             /* m1**2 + m3**2 */
+    double pp, ee;           /* p1_cm*p3_cm, e1_cm*e3_cm */
+    double p3_cm, e3_cm;
+    double vol;              /* 4*p1_cm*p3_cm/n_samples (linear sampling) */
+    double p1_cm, n_samples; /* log sampling: exp(logu)*2*p1_cm*p3_cm/n_samples */
+    double den;              /* 16*pi*(s-(m1+m2)^2)*(s-(m1-m2)^2) */
+    double mat[16];          /* lorentz_boost matrix for -v_in, row-major (identity if beta == 0) */
+    double p12[4];           /* lv_p1 + lv_p2 */
+    int    log_sampling;
+} alpk_scatter2_t;
+
+/* One scatter_sim(): n_samples draws (phi, theta).  uniforms (parity mode): [2][n] -- the phi block then the theta (or
+ * logu) block, the reference's draw order; NULL: Philox keyed (seed, tag 8, stream_id, sample).  Outputs (each may be
+ * NULL): t[n], weights[n] = dsigma_dcos_cm_wgts, component planes p3_cm[4][n], p3_lab[4][n], p4_lab[4][n],
+ * cosine_lab[n] = p3_lab.cosine(), 3-velocity planes v3_cm[3][n], v3_lab[3][n], v4_lab[3][n]. */
+int alpk_scatter2to2(const alpk_scatter2_t* h_par, uint64_t n_samples, const double* uniforms, uint64_t seed,
+                     uint32_t stream_id, double* t_out, double* weights, double* p3_cm, double* p3_lab, double* p4_lab,
+                     double* cosine_lab, double* v3_cm, double* v3_lab, double* v4_lab, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -641,6 +641,131 @@ def pairann_simulate(positron_flux, ma, g, target, n_samples, usrc):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# Generic 2 -> 2 scattering MC: cross_section_mc.py:148-275 (Scatter2to2MC) with the matrix elements of
+# matrix_element.py:629-734 and the atomic form factor form_factors.py:54-64
+# ---------------------------------------------------------------------------------------------------------
+def atomic_elastic_ff2(q, z):                                                        # form_factors.py:61-64
+    t = q ** 2
+    a = 184.15 * np.power(2.718, -1 / 2) * np.power(z, -1 / 3) / M_E
+    return np.power(z * (t * a ** 2) / (1 + t * a ** 2), 2)
+
+
+def _m2_compton_like(s, t, ma, z, coupling_product):                                 # matrix_element.py:638-645 / 659-666
+    u = 2 * M_E ** 2 + ma ** 2 - s - t
+    prefactor = z * 4 * pi * ALPHA * coupling_product ** 2
+    Ms2 = prefactor * (M_E ** 4 + M_E ** 2 * (3 * ma ** 2 - 2 * s - t) + s * (s + t - ma ** 2)) / np.power(M_E ** 2 - s, 2)
+    Mu2 = prefactor * (M_E ** 4 + M_E ** 2 * (3 * ma ** 2 - 2 * s - t) + s * (s + t - ma ** 2)) / np.power(M_E ** 2 - u, 2)
+    MuMt = prefactor * (M_E ** 4 + M_E ** 2 * (3 * ma ** 2 - 2 * s - t) - (ma ** 2 - s) * (s + t)) / ((M_E ** 2 - s) * (M_E ** 2 - u))
+    return Ms2 + Mu2 + 2 * MuMt
+
+
+def m2_compton(s, t, ma, z, coupling_product=1.0):                                   # matrix_element.py:629-645
+    return _m2_compton_like(s, t, ma, z, coupling_product)
+
+
+def m2_inverse_compton(s, t, ma, z, coupling_product=1.0):                           # matrix_element.py:650-666
+    return 2 * _m2_compton_like(s, t, ma, z, coupling_product)
+
+
+def _m2_primakoff_like(s, t, ma, mN, z, prefactor):                                  # matrix_element.py:681-686 / 700-705
+    propagator = np.power(t, 2)
+    numerator = -t * (2 * mN ** 2 * (ma ** 2 - 2 * s - t) + 2 * mN ** 4 - 2 * ma ** 2 * (s + t) + ma ** 4 + 2 * s ** 2
+                      + 2 * s * t + t ** 2)
+    return atomic_elastic_ff2(np.sqrt(abs(t)), z) * prefactor * numerator / propagator
+
+
+def m2_inverse_primakoff(s, t, ma, mN, z, coupling_product=1.0):                     # matrix_element.py:671-686
+    return _m2_primakoff_like(s, t, ma, mN, z, 2 * coupling_product ** 2)
+
+
+def m2_primakoff(s, t, ma, mN, z, coupling_product=1.0):                             # matrix_element.py:690-705
+    return _m2_primakoff_like(s, t, ma, mN, z, coupling_product ** 2)
+
+
+# (name, masses (m1, m2, m3, m4), callable(s, t)) of the matrix elements Scatter2to2MC is used with on this path
+def matrix_element(model, ma, mN=0.0, z=1):
+    if model == "inverse_primakoff":
+        return (ma, mN, 0, mN), lambda s, t: m2_inverse_primakoff(s, t, ma, mN, z)
+    if model == "primakoff":
+        return (0, mN, ma, mN), lambda s, t: m2_primakoff(s, t, ma, mN, z)
+    if model == "inverse_compton":
+        return (ma, M_E, 0, M_E), lambda s, t: m2_inverse_compton(s, t, ma, z)
+    if model == "compton":
+        return (0, M_E, ma, M_E), lambda s, t: m2_compton(s, t, ma, z)
+    if model == "associated_production":
+        return (M_E, M_E, ma, 0.0), lambda s, t: m2_associated(s, t, ma)
+    raise ValueError(model)
+
+
+def boost_matrix(v):
+    """The 4x4 matrix of lorentz_boost (cross_section_mc.py:676-685) for frame velocity v = (vx, vy, vz); None if
+    beta == 0 (the reference returns the momentum unchanged)."""
+    v = np.asarray(v, dtype=np.float64)
+    beta = np.sqrt(np.dot(v, v))                                                     # Vector3.mag :59-60
+    if beta == 0.0:
+        return None
+    n = v / beta if not beta < 1e-40 else np.zeros(3)                                # unit_vec :49-53
+    g = 1 / np.sqrt(1 - beta ** 2)
+    return np.array([[g, -g * beta * n[0], -g * beta * n[1], -g * beta * n[2]],
+                     [-g * beta * n[0], 1 + (g - 1) * n[0] * n[0], (g - 1) * n[0] * n[1], (g - 1) * n[0] * n[2]],
+                     [-g * beta * n[1], (g - 1) * n[1] * n[0], 1 + (g - 1) * n[1] * n[1], (g - 1) * n[1] * n[2]],
+                     [-g * beta * n[2], (g - 1) * n[2] * n[0], (g - 1) * n[2] * n[1], 1 + (g - 1) * n[2] * n[2]]])
+
+
+def scatter2to2_sim(masses, m2, p1, p2, n_samples, usrc, log_sampling=False):
+    """Scatter2to2MC.scatter_sim (cross_section_mc.py:193-240) for incoming 4-vectors p1, p2 = (E, px, py, pz).
+    Draw order: n phi, then n theta variates (or n logu with log_sampling) -- drawn before the s-threshold return.
+
+    Returns None below threshold (the reference leaves its lists empty), else a dict with
+      t[n], weights[n] (dsigma_dcos_cm_wgts), p3_cm[n,4], p3_lab[n,4], p4_lab[n,4],
+      cosines[n] (get_cosine_lab_weights), e3_lab[n], e4_lab[n], and the 3-velocity arrays."""
+    m1, m2_, m3, m4 = masses
+    p1 = np.asarray(p1, dtype=np.float64)
+    p2 = np.asarray(p2, dtype=np.float64)
+    n = int(n_samples)
+    with np.errstate(all="ignore"):
+        if log_sampling:
+            phi = 2 * pi * usrc.take(n)                                              # :199
+            logu = usrc.uniform(-12, 0, n)                                           # :200
+            theta = np.arccos(1 - 2 * np.exp(logu))                                  # :201
+        else:
+            phi = 2 * pi * usrc.take(n)                                              # :203
+            theta = np.arccos(1 - 2 * usrc.take(n))                                  # :204
+        cm = p1 + p2                                                                 # :207 (component-wise LorentzVector add)
+        e_in = cm[0]
+        v_in = np.array([cm[1] / e_in, cm[2] / e_in, cm[3] / e_in])                  # :210
+        s = float(np.dot(cm ** 2, np.array([1, -1, -1, -1])))                        # mass2 :110-111
+        if s < (m3 + m4) ** 2:                                                       # :212-213
+            return None
+        p1_cm = np.sqrt((np.power(s - m1 ** 2 - m2_ ** 2, 2) - np.power(2 * m1 * m2_, 2)) / (4 * s))   # :187-188
+        p3_cm = np.sqrt((np.power(s - m3 ** 2 - m4 ** 2, 2) - np.power(2 * m3 * m4, 2)) / (4 * s))     # :190-191
+        e1_cm = np.sqrt(p1_cm ** 2 + m1 ** 2)
+        e3_cm = np.sqrt(p3_cm ** 2 + m3 ** 2)
+        t_rnd = m1 ** 2 + m3 ** 2 + 2 * (p1_cm * p3_cm * np.cos(theta) - e1_cm * e3_cm)                # :220
+        if log_sampling:
+            mc_volume = np.exp(logu) * 2 * p1_cm * p3_cm / n                         # :224
+        else:
+            mc_volume = 4 * p1_cm * p3_cm / n                                        # :226
+        dsdt = m2(s, t_rnd) / (16 * np.pi * (s - (m1 + m2_) ** 2) * (s - (m1 - m2_) ** 2))             # :184-185
+        wts = mc_volume * dsdt                                                       # :227
+        p3cm = np.stack([e3_cm * np.ones(n), p3_cm * np.cos(phi) * np.sin(theta), p3_cm * np.sin(phi) * np.sin(theta),
+                         p3_cm * np.cos(theta)], axis=1)                             # :230-233
+        mat = boost_matrix(-v_in)                                                    # :234  lorentz_boost(p3, -v_in)
+        if mat is None:
+            p3lab = p3cm.copy()
+        else:
+            p3lab = np.stack([((mat[r, 0] * p3cm[:, 0] + mat[r, 1] * p3cm[:, 1]) + mat[r, 2] * p3cm[:, 2]) + mat[r, 3] * p3cm[:, 3]
+                              for r in range(4)], axis=1)
+        p4lab = (p1 + p2)[None, :] - p3lab                                           # :238
+        mom3 = np.sqrt((p3lab[:, 1] * p3lab[:, 1] + p3lab[:, 2] * p3lab[:, 2]) + p3lab[:, 3] * p3lab[:, 3])   # Vector3.mag
+        return {"s": s, "t": t_rnd, "weights": wts, "p3_cm": p3cm, "p3_lab": p3lab, "p4_lab": p4lab,
+                "cosines": p3lab[:, 3] / mom3,                                       # :257 LorentzVector.cosine :119-120
+                "e3_lab": p3lab[:, 0], "e4_lab": p4lab[:, 0],                        # :268, :272
+                "v3_cm": p3cm[:, 1:] / p3cm[:, :1], "v3_lab": p3lab[:, 1:] / p3lab[:, :1],   # get_3velocity :142-143
+                "v4_lab": p4lab[:, 1:] / p4lab[:, :1]}
+
+
+# ---------------------------------------------------------------------------------------------------------
 # generators.py:41-46, 80-92  event weights
 # ---------------------------------------------------------------------------------------------------------
 def decays(axion_energy, decay_axion_weight, days_exposure, threshold):              # generators.py:88-92

@@ -9,6 +9,7 @@ import numpy as np
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 TAG_COMPTON_EA, TAG_BREM_ROW, TAG_BREM_EA, TAG_RESONANCE, TAG_PAIRANN, TAG_DECAY2 = 1, 2, 3, 4, 5, 6
+TAG_SCATTER2 = 8          # alpk_scatter2to2 (alpk_scatter2.cu)
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

@@ -45,7 +45,8 @@ def hostcheck():
     deps = [os.path.join(d, "hostcheck.cpp"), os.path.join(d, "hostcheck2.inc"),
             os.path.join(ROOT, "alplib_b200", "csrc", "alp_math.cuh"),
             os.path.join(ROOT, "alplib_b200", "csrc", "alp_math2.cuh"),
-            os.path.join(ROOT, "alplib_b200", "csrc", "alp_math3.cuh"), os.path.join(ROOT, "include", "alpk.h")]
+            os.path.join(ROOT, "alplib_b200", "csrc", "alp_math3.cuh"),
+            os.path.join(ROOT, "alplib_b200", "csrc", "alp_math4.cuh"), os.path.join(ROOT, "include", "alpk.h")]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so,
                                os.path.join(d, "hostcheck.cpp")])

@@ -615,6 +615,171 @@ def case_meson_mixing():
     save("meson_mixing", n_cases=k, **out)
 
 
+def case_scatter2to2():
+    """Scatter2to2MC (cross_section_mc.py:148-275) with M2InversePrimakoff (README.md:144-158), M2InverseCompton,
+    M2Primakoff, M2Compton and M2AssociatedProduction; linear and log sampling; target at rest and a moving second
+    particle (boost along a general direction)."""
+    print("Scatter2to2MC (README snippet + 2->2 matrix elements)")
+    import alplib.cross_section_mc as X
+    import alplib.matrix_element as ME
+    Ar = F.Material("Ar")
+    mN, z = float(Ar.m[0]), Ar.z[0]
+    cases = [
+        # tag, model, ma, p1 (E, p along z unless given), p2, n, log_sampling, seed
+        ("readme_iprim", "inverse_primakoff", 0.1, 100.0, None, 1000, False, 31),
+        ("iprim_log", "inverse_primakoff", 0.1, 100.0, None, 64, True, 32),
+        ("iprim_heavy", "inverse_primakoff", 25.0, 40.0, None, 64, False, 33),
+        ("icompton", "inverse_compton", 0.1, 30.0, None, 64, False, 34),
+        ("icompton_log", "inverse_compton", 1.5, 8.0, None, 64, True, 35),
+        ("primakoff", "primakoff", 0.5, 50.0, None, 64, False, 36),
+        ("compton", "compton", 1.5, 20.0, None, 64, False, 37),
+        ("assoc", "associated_production", 10.0, 300.0, None, 64, False, 38),
+        ("icompton_moving", "inverse_compton", 0.3, 12.0, (0.8, 0.15, -0.22, 0.31), 64, False, 39),
+        ("icompton_below", "inverse_compton", 0.1, 30.0, "below", 8, False, 40),
+    ]
+    out, kk = {}, 0
+    for tag, model, ma, e1, p2spec, n, logs, seed in cases:
+        if model == "inverse_primakoff":
+            m2r = ME.M2InversePrimakoff(ma=ma, mN=mN, z=z); m_in, m_tgt = ma, mN
+        elif model == "primakoff":
+            m2r = ME.M2Primakoff(ma=ma, mN=mN, z=z); m_in, m_tgt = 0.0, mN
+        elif model == "inverse_compton":
+            m2r = ME.M2InverseCompton(ma=ma, z=z); m_in, m_tgt = ma, F.M_E
+        elif model == "compton":
+            m2r = ME.M2Compton(ma=ma, z=z); m_in, m_tgt = 0.0, F.M_E
+        else:
+            m2r = ME.M2AssociatedProduction(ma); m_in, m_tgt = F.M_E, F.M_E
+        p1 = (e1, 0.0, 0.0, float(np.sqrt(e1 ** 2 - m_in ** 2)))
+        if p2spec is None:
+            p2 = (m_tgt, 0.0, 0.0, 0.0)
+        elif p2spec == "below":                       # s below (m3+m4)^2 is impossible for these elastic-type processes with a
+            p2 = (m_tgt, 0.0, 0.0, 0.0)               # physical p1; force it with an off-shell, backward-moving p1 instead
+            p1 = (0.2, 0.0, 0.0, -0.19)
+            m2r = ME.M2Compton(ma=5.0, z=z); model, ma = "compton", 5.0
+        else:
+            pe = p2spec
+            p2 = (float(np.sqrt(m_tgt ** 2 + pe[1] ** 2 + pe[2] ** 2 + pe[3] ** 2)), pe[1], pe[2], pe[3])
+        np.random.seed(seed)
+        mc = X.Scatter2to2MC(mtrx2=m2r, p1=X.LorentzVector(*p1), p2=X.LorentzVector(*p2), n_samples=n)
+        mc.scatter_sim(log_sampling=logs)
+        us = O.UniformSource(np.random.RandomState(seed))
+        masses, m2o = O.matrix_element(model, ma, mN=mN, z=z)
+        r = O.scatter2to2_sim(masses, m2o, p1, p2, n, us, log_sampling=logs)
+        pre = f"c{kk}_"
+        out[pre + "model"] = model; out[pre + "ma"] = ma; out[pre + "mN"] = mN; out[pre + "z"] = z
+        out[pre + "p1"] = np.array(p1); out[pre + "p2"] = np.array(p2); out[pre + "n"] = n; out[pre + "log"] = logs
+        out[pre + "uniforms"] = np.concatenate(us.log)
+        if r is None:
+            assert len(mc.p3_lab_4vectors) == 0 and mc.dsigma_dcos_cm_wgts.shape[0] == 0, tag
+            out[pre + "empty"] = True
+            print(f"  [OK ] {tag:48s} below threshold: no samples")
+        else:
+            cos_r, w_r = mc.get_cosine_lab_weights()
+            e3_r, _ = mc.get_e3_lab_weights()
+            e4_r, _ = mc.get_e4_lab_weights()
+            p3cm = np.array([v.pmu for v in mc.p3_cm_4vectors]); p3lab = np.array([v.pmu for v in mc.p3_lab_4vectors])
+            p4lab = np.array([v.pmu for v in mc.p4_lab_4vectors])
+            v3lab = np.array([v.vec for v in mc.p3_lab_3vectors]); v4lab = np.array([v.vec for v in mc.p4_lab_3vectors])
+            v3cm = np.array([v.vec for v in mc.p3_cm_3vectors])
+            scale = abs(p1[0]) + abs(p2[0])
+            check(tag + " weights", r["weights"], w_r, 1e-12)
+            check(tag + " cosines", r["cosines"], cos_r, 1e-12)
+            check(tag + " e3_lab", r["e3_lab"], e3_r, 1e-13)
+            check(tag + " p3_lab/scale", r["p3_lab"] / scale + 1, p3lab / scale + 1, 1e-14)
+            check(tag + " p4_lab/scale", r["p4_lab"] / scale + 1, p4lab / scale + 1, 1e-14)
+            check(tag + " p3_cm/scale", r["p3_cm"] / scale + 1, p3cm / scale + 1, 1e-15)
+            check(tag + " v3_lab", r["v3_lab"] + 2, v3lab + 2, 1e-14)
+            check(tag + " v4_lab", r["v4_lab"] + 2, v4lab + 2, 1e-12)
+            out[pre + "empty"] = False
+            out.update({pre + "weights": w_r, pre + "cosines": cos_r, pre + "e3_lab": e3_r, pre + "e4_lab": e4_r,
+                        pre + "p3_cm": p3cm, pre + "p3_lab": p3lab, pre + "p4_lab": p4lab, pre + "v3_lab": v3lab,
+                        pre + "v4_lab": v4lab, pre + "v3_cm": v3cm,
+                        pre + "dsigma_dt_probe": np.array([mc.dsigma_dt(r["s"], t) for t in r["t"][:4]]),
+                        pre + "t_probe": r["t"][:4], pre + "s": r["s"],
+                        pre + "total_xs": mc.get_total_xs(r["s"]) if model != "associated_production" else np.nan})
+        out[pre + "tag"] = tag
+        kk += 1
+    # matrix elements evaluated directly (the classes are callable: mtrx2(s, t[, coupling_product]))
+    sg = np.array([2.0, 50.0, 4.0e3]); tg = -np.array([1e-6, 0.3, 7.0])
+    out["m2_s"], out["m2_t"] = sg, tg
+    out["m2_inverse_compton"] = np.array([ME.M2InverseCompton(0.4, 18)(s_, tg, 1e-3) for s_ in sg])
+    out["m2_compton"] = np.array([ME.M2Compton(0.4, 18)(s_, tg, 1e-3) for s_ in sg])
+    out["m2_inverse_primakoff"] = np.array([ME.M2InversePrimakoff(0.4, mN, 18)(s_ + mN ** 2, tg, 1e-3) for s_ in sg])
+    out["m2_primakoff"] = np.array([ME.M2Primakoff(0.4, mN, 18)(s_ + mN ** 2, tg, 1e-3) for s_ in sg])
+    out["m2_associated"] = np.array([ME.M2AssociatedProduction(0.4)(s_ + 1.5, tg, 1e-3) for s_ in sg])
+    out["atomic_ff_q"] = np.array([1e-4, 0.02, 3.0]); out["atomic_ff"] = ME.AtomicElasticFF(18)(out["atomic_ff_q"])
+    check("m2_inverse_compton", np.array([O.m2_inverse_compton(s_, tg, 0.4, 18, 1e-3) for s_ in sg]), out["m2_inverse_compton"], 1e-15)
+    check("m2_inverse_primakoff", np.array([O.m2_inverse_primakoff(s_ + mN ** 2, tg, 0.4, mN, 18, 1e-3) for s_ in sg]), out["m2_inverse_primakoff"], 1e-15)
+    check("atomic_ff", O.atomic_elastic_ff2(out["atomic_ff_q"], 18), out["atomic_ff"], 1e-15)
+    save("scatter2to2", n_cases=kk, **out)
+
+
+def _fit_cases():
+    """Fixed inputs of the limit-helper fixture; shared with tests/test_fit_cpu.py through fit.json (inputs are stored too)."""
+    grid = np.logspace(-8, -3, 700)
+
+    def events(g):            # toy signal: rises as g^4, then dies off when the ALP decays before the detector
+        return np.array([1e24 * g ** 4 * np.exp(-(g / 3e-5) ** 2), 3e23 * g ** 4 * np.exp(-(g / 1e-5) ** 2)])
+    bkg = np.array([40.0, 12.0])
+    obs = np.array([44.0, 9.0])
+    return grid, events, bkg, obs
+
+
+def case_fit():
+    """Limit helpers (fit.py:12-121): TwoSidedGridSearch, binary_search, cleanLimitData run in the reference."""
+    print("fit.py limit helpers")
+    import alplib.fit as RF
+    from alplib_b200 import fit as MF
+    grid, events, bkg, obs = _fit_cases()
+    out = {"grid": grid.tolist(), "background": bkg.tolist(), "observations": obs.tolist()}
+
+    def pair(x):
+        return [None if v is None else float(v) for v in x]
+    tsgs = {
+        "signal_only": dict(observations=np.zeros(2)),
+        "signal_only_cl": dict(observations=np.zeros(2), delta_chi2=False),
+        "with_background": dict(observations=obs, background=bkg),
+        "with_background_cl": dict(observations=obs, background=bkg, delta_chi2=False, target_cl=0.95),
+    }
+    out["TwoSidedGridSearch"] = {}
+    for k, kw in tsgs.items():
+        r = RF.TwoSidedGridSearch(events, param_grid=grid, **kw)
+        m = MF.TwoSidedGridSearch(events, param_grid=grid, **kw)
+        assert pair(r) == pair(m), (k, r, m)
+        out["TwoSidedGridSearch"][k] = pair(r)
+        print(f"  [OK ] TwoSidedGridSearch {k:24s} {pair(r)}")
+    r = RF.TwoSidedGridSearch(lambda g: np.zeros(2), np.zeros(2), grid)
+    assert r == (None, None) == MF.TwoSidedGridSearch(lambda g: np.zeros(2), np.zeros(2), grid)
+    out["TwoSidedGridSearch"]["no_signal"] = pair(r)
+    bs = {
+        "increasing": (lambda t: t ** 2, 9.0, 0.0, 10.0, dict(tolerance=1e-6)),
+        "decreasing": (lambda t: 100 - t, 40.0, 0.0, 100.0, dict(tolerance=1e-6, is_increasing=False)),
+        "coarse": (lambda t: np.exp(t), 5.0, -3.0, 4.0, dict(tolerance=0.1)),
+        "edge": (lambda t: t, 1e300, 1.0, 1.0 + 4e-16, dict(tolerance=1e-3)),
+    }
+    out["binary_search"] = {}
+    for k, (fn, stop, lo, hi, kw) in bs.items():
+        r = RF.binary_search(fn, stop, lo, hi, **kw)
+        m = MF.binary_search(fn, stop, lo, hi, **kw)
+        assert float(r) == float(m), (k, r, m)
+        out["binary_search"][k] = float(r)
+        print(f"  [OK ] binary_search {k:29s} {float(r)!r}")
+    masses = np.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0])
+    lower = np.array([1e-6, 2e-6, 5e-5, 4e-6, 6e-6, 9e-6])
+    upper = np.array([1e-4, 1e-4, 1e-5, 8e-5, 5e-5, 2e-5])
+    out["cleanLimitData"] = {"masses": masses.tolist(), "lower": lower.tolist(), "upper": upper.tolist()}
+    for smooth in (False, True):
+        rm, rl = RF.cleanLimitData(masses, lower, upper, apply_smoothing=smooth)
+        mm, ml = MF.cleanLimitData(masses, lower, upper, apply_smoothing=smooth)
+        assert np.array_equal(rm, mm) and np.array_equal(rl, ml), smooth
+        out["cleanLimitData"]["smooth" if smooth else "plain"] = {"masses": rm.tolist(), "limits": rl.tolist()}
+        print(f"  [OK ] cleanLimitData smoothing={smooth}")
+    path = os.path.join(HERE, "fit.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print(f"  wrote {os.path.relpath(path, ROOT)}")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:                      # regenerate selected cases only: python make_golden.py case_meson3body
         for name in sys.argv[1:]:
@@ -634,4 +799,6 @@ if __name__ == "__main__":
     case_general_decay()
     case_meson3body()
     case_meson_mixing()
+    case_scatter2to2()
+    case_fit()
     print("all golden fixtures written; oracle pinned against the reference")

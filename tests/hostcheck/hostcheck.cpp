@@ -8,6 +8,7 @@
 #include "../../alplib_b200/csrc/alp_math.cuh"
 #include "../../alplib_b200/csrc/alp_math2.cuh"
 #include "../../alplib_b200/csrc/alp_math3.cuh"
+#include "../../alplib_b200/csrc/alp_math4.cuh"
 #include "../../include/alpk.h"
 
 using namespace alp;
@@ -119,5 +120,31 @@ void hc_decay2body(const double* e, const float* w32, uint64_t n_parents, double
 }
 
 #include "hostcheck2.inc"
+
+// Scatter2to2MC sample arithmetic (alp_math4.cuh); u = [2][n]: phi block then theta block
+void hc_scatter2(const alpk_scatter2_t* h, uint64_t n, const double* u, double* t, double* w, double* p3cm, double* p3lab,
+                 double* p4lab, double* cosine) {
+    Scatter2Const c;
+    c.m2.model = h->m2.model; c.m2.ma2 = h->m2.ma2; c.m2.ma4 = h->m2.ma4; c.m2.mN2 = h->m2.mN2; c.m2.mN4 = h->m2.mN4;
+    c.m2.z = h->m2.z; c.m2.ff_a2 = h->m2.ff_a2; c.m2.pref = h->m2.pref; c.m2.me2 = h->m2.me2; c.m2.me4 = h->m2.me4;
+    c.m2.tmax = h->m2.tmax;
+    c.s = h->s; c.msum = h->msum; c.pp = h->pp; c.ee = h->ee; c.p3_cm = h->p3_cm; c.e3_cm = h->e3_cm; c.vol = h->vol;
+    c.p1_cm = h->p1_cm; c.n_samples = h->n_samples; c.den = h->den; c.log_sampling = h->log_sampling;
+    for (int k = 0; k < 16; ++k) c.mat[k] = h->mat[k];
+    for (int k = 0; k < 4; ++k) c.p12[k] = h->p12[k];
+    for (uint64_t i = 0; i < n; ++i) {
+        Scatter2Out o;
+        scatter2_sample(u[i], u[n + i], c, o);
+        t[i] = o.t; w[i] = o.w; cosine[i] = o.cosine;
+        for (int k = 0; k < 4; ++k) { p3cm[k * n + i] = o.p3cm[k]; p3lab[k * n + i] = o.p3lab[k]; p4lab[k * n + i] = o.p4lab[k]; }
+    }
+}
+
+void hc_m2_eval(const alpk_m2_t* h, const double* s, const double* t, uint64_t n, double* out) {
+    M2Const c;
+    c.model = h->model; c.ma2 = h->ma2; c.ma4 = h->ma4; c.mN2 = h->mN2; c.mN4 = h->mN4; c.z = h->z; c.ff_a2 = h->ff_a2;
+    c.pref = h->pref; c.me2 = h->me2; c.me4 = h->me4; c.tmax = h->tmax;
+    for (uint64_t i = 0; i < n; ++i) out[i] = m2_eval(c, s[i], t[i]);
+}
 
 }  // extern "C"
