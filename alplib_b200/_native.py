@@ -43,20 +43,21 @@ class EventT(C.Structure):
 
 class ComptonT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("aa", C.c_double), ("z", C.c_double),
-                ("n_samples", C.c_double), ("fast", C.c_int)]
+                ("n_samples", C.c_double), ("fast", C.c_int), ("rng_rounds", C.c_int)]
 
 
 class BremT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("log10_ma", C.c_double), ("ep_min", C.c_double),
                 ("nt", C.c_double), ("pref_num", C.c_double), ("zl", C.c_double), ("zz", C.c_double),
                 ("pref_vec", C.c_double), ("ln10", C.c_double), ("n_samples", C.c_double), ("t_arg", C.c_double),
-                ("vector", C.c_int), ("use_track_length", C.c_int), ("fast", C.c_int)]
+                ("vector", C.c_int), ("use_track_length", C.c_int), ("fast", C.c_int), ("rng_rounds", C.c_int)]
 
 
 class PairAnnT(C.Structure):
     _fields_ = [("ma", C.c_double), ("ma2", C.c_double), ("me2", C.c_double), ("me4", C.c_double),
                 ("pref", C.c_double), ("wconst", C.c_double), ("z", C.c_double), ("ge2", C.c_double),
-                ("ntad", C.c_double), ("hbarc2", C.c_double), ("n_samples", C.c_double), ("fast", C.c_int)]
+                ("ntad", C.c_double), ("hbarc2", C.c_double), ("n_samples", C.c_double), ("fast", C.c_int),
+                ("rng_rounds", C.c_int)]
 
 
 class PairGammaT(C.Structure):
@@ -171,8 +172,8 @@ _SIGNATURES = {
     "alpk_decay2body_f32": ([_P, _U64, _U32, _P, _U64, _P, _P, _P, _P], _I),
     "alpk_decay2body_general": ([_P, _P, _U64, _D, _D, _U32, _P, _P, _U64, _P, _P, _P, _P, _P, _P], _I),
     "alpk_scan_tiles": ([_U32, _U32], _U32),
-    "alpk_scan": ([_I, _P, _P, _U32, _U32, _P, _P, _I, _P, _P, _I, _P, _P, _I, _D, _D, _D, _U32, _U64,
-                   C.POINTER(PropT), C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_scan": ([_I, _P, _P, _U32, _U32, _P, _P, _I, _P, _P, _I, _P, _P, _I, _D, _D, _D, _U32, _U64, _I,
+                   C.POINTER(PropT), C.POINTER(EventT), _P, _P, _U32, _P, _P], _I),
     "alpk_vol_int_chunks": ([_U64, _U32], _U32),
     "alpk_vol_int": ([_P, _P, _U64, C.POINTER(PropT), _P, _P, _P, _U32, _D, _D, _P, _P, _P, _P, _P, _P], _I),
     "alpk_nuclear": ([_P, _U64, _D, _D, _D, _D, _D, _P, _P, _P], _I),
@@ -187,6 +188,7 @@ _SIGNATURES = {
     "alpk_m2_eval": ([C.POINTER(M2T), _P, _U64, _P, _U64, _D, _P, _P], _I),
     "alpk_atomic_ff2": ([_P, _U64, _D, _D, _P, _P], _I),
     "alpk_scatter2to2": ([C.POINTER(Scatter2T), _U64, _P, _U64, _U32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "alpk_planes_to_rows": ([_P, _U64, _I, _P, _P], _I),
     "alpk_scale": ([_P, _U64, _D, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),

@@ -15,3 +15,19 @@ PRECISION = _os.environ.get("ALPK_PRECISION", "fast")          # (env override: 
 #   True              deferred and reduce-only: decays() returns the rate without materialising per-sample arrays
 #                     (they are regenerated bit-identically if read later).
 FUSED = "auto"
+
+# Strict compatibility with the reference's host containers (off by default: NumPy arrays are what vectorised user code
+# wants).  True: `axion_energy` / `axion_flux` are Python lists of np.float64 (fluxes.py:222-224) and
+# `simulate_decay_4vectors` returns three Python lists -- two of `LorentzVector` objects and one of weights
+# (generators.py:124-128) -- so scripts that `.append`, concatenate with `+` or mutate the elements behave as with the
+# reference.  Per object: the `strict=` keyword of the flux classes / `simulate_decay_4vectors(strict=...)`.
+STRICT = _os.environ.get("ALPK_STRICT", "0") not in ("0", "", "false", "False")
+
+# Rounds of the counter-based generator for the per-sample PRODUCTION streams (Compton / bremsstrahlung / associated-
+# production E_a and angle draws, and the scan kernel that regenerates them).  10 = Philox4x32-10, the Random123 / cuRAND
+# default; 7 = Philox4x32-7, the fewest rounds Salmon et al. (SC'11) found Crush-resistant.  The generator is a fifth of the
+# chain kernel's issue slots, so the fast arithmetic mode defaults to 7 (6 % faster chain kernel); "faithful" keeps 10.  A
+# variate stays a pure function of (seed, rounds, stream tag, row, sample); `oracle/philox.py` restates both.  Every other
+# stream (decay angles, per-row draws, meson channels, 2 -> 2 scattering) is Philox4x32-10.
+PHILOX_ROUNDS = {"fast": int(_os.environ.get("ALPK_PHILOX_ROUNDS", "7")), "fp32": int(_os.environ.get("ALPK_PHILOX_ROUNDS", "7")),
+                 "faithful": 10}

@@ -21,7 +21,7 @@ from numpy import pi
 from . import _native as N
 from .matrix_element import MatrixElement2
 from .runtime import Runtime
-from .vectors import LorentzVector, LorentzVectorArray, Vector3
+from .vectors import LorentzVector, LorentzVectorArray, Vector3, planes_to_host_rows
 
 __all__ = ["Scatter2to2MC", "LorentzVector", "Vector3", "lorentz_boost"]
 
@@ -59,7 +59,7 @@ class _Vec3Array:
     @property
     def vec(self):
         if self._host is None:
-            self._host = np.ascontiguousarray(self.device.cpu().numpy().T)
+            self._host = planes_to_host_rows(self.device)
         return self._host
 
     def __len__(self):

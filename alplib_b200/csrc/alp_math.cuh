@@ -73,13 +73,14 @@ ALP_HD PhiloxKeys philox_keys(uint64_t seed) {
     return rk;
 }
 
-#ifndef ALPK_PHILOX_ROUNDS
-#define ALPK_PHILOX_ROUNDS 10          // (kernel-variant experiments only: the stream definition is Philox4x32-10)
-#endif
-ALP_HD Philox4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& rk) {
+// R rounds with the precomputed key schedule.  R = 10 is Philox4x32-10 (the Random123 / cuRAND default); R = 7 is
+// Philox4x32-7, the fewest rounds Salmon et al. (SC'11, table 2) found Crush-resistant -- the fast-mode choice for the
+// per-sample production streams, where the generator is 1/5 of the chain kernel's issue slots.
+template <int R>
+ALP_HD Philox4 philox4x32_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& rk) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-    for (int r = 0; r < ALPK_PHILOX_ROUNDS; ++r) {
+    for (int r = 0; r < R; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo32(M0, c0, hi0, lo0);
         mulhilo32(M1, c2, hi1, lo1);
@@ -139,9 +140,12 @@ enum StreamTag : uint32_t {
 };
 
 // One uniform per sample: sample s uses Philox counter s>>1 and word pair s&1.
-ALP_HD double uniform_1(uint64_t seed, uint32_t tag, uint32_t row, uint64_t s) {
+// rounds: 10 (default) or 7 (see philox4x32_rk).
+ALP_HD double uniform_1(uint64_t seed, uint32_t tag, uint32_t row, uint64_t s, int rounds = 10) {
     const uint64_t c = s >> 1;
-    const Philox4 r = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), row, tag, (uint32_t)seed, (uint32_t)(seed >> 32));
+    Philox4 r;
+    if (rounds == 7) r = philox4x32_rk<7>((uint32_t)c, (uint32_t)(c >> 32), row, tag, philox_keys(seed));
+    else r = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), row, tag, (uint32_t)seed, (uint32_t)(seed >> 32));
     return (s & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
 }
 

@@ -534,7 +534,7 @@ ALPK_EXPORT int alpk_compton_samples(const double* row_table, uint64_t n_rows, u
                                      const double* hist_edges, int n_edges, double* hist, void* stream) {
     if (!h_par) { set_error("alpk_compton_samples: null argument"); return 2; }
     return launch_chain<ComptonProd>("alpk_compton_samples", row_table, n_rows, n_samples, row_ids, to_compton(h_par),
-                                     h_par->fast, uniforms, seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64,
+                                     h_par->fast, h_par->rng_rounds, uniforms, seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64,
                                      scatter_w64, h_ev, event_w, rate, scratch, hist_edges, n_edges, hist, stream);
 }
 

@@ -121,7 +121,7 @@ ALPK_EXPORT int alpk_brem_samples(const double* row_table, uint64_t n_rows, uint
     if (!h_par) { set_error("alpk_brem_samples: null argument"); return 2; }
     if (h_prop && (h_prop->fast != 0) != (h_par->fast != 0)) { set_error("alpk_brem_samples: production and propagate precision modes differ"); return 2; }
     return launch_chain<BremProd>("alpk_brem_samples", row_table, n_rows, n_samples, row_ids, to_brem(h_par),
-                                  h_par->fast ? 1 : 0, uniforms,
+                                  h_par->fast ? 1 : 0, h_par->rng_rounds, uniforms,
                                   seed, out_energy, out_flux, h_prop, decay_w32, scatter_w32, decay_w64, scatter_w64,
                                   h_ev, event_w, rate, scratch, hist_edges, n_edges, hist, stream);
 }

@@ -125,6 +125,37 @@ ALPK_EXPORT int alpk_meson_mixing(const double* p4, uint64_t n, double ma, doubl
     return check_launch("alpk_meson_mixing");
 }
 
+// planes[ncomp][n] (what the decay / scatter kernels write: coalesced per component) -> rows[n][ncomp] (the layout of the
+// reference's per-event `pmu` arrays), so a host copy of all events is ONE contiguous transfer instead of a strided gather.
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+planes_to_rows_kernel(const double* __restrict__ planes, uint64_t n, double* __restrict__ rows) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[c] = __ldg(planes + (uint64_t)c * n + i);
+        if (NC == 4) {
+            reinterpret_cast<double2*>(rows + 4 * i)[0] = make_double2(v[0], v[1]);
+            reinterpret_cast<double2*>(rows + 4 * i)[1] = make_double2(v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) rows[(uint64_t)NC * i + c] = v[c];
+        }
+    }
+}
+
+ALPK_EXPORT int alpk_planes_to_rows(const double* planes, uint64_t n, int ncomp, double* rows, void* stream) {
+    if (n == 0) return 0;
+    if (!planes || !rows) { set_error("alpk_planes_to_rows: null argument"); return 2; }
+    if (ncomp != 3 && ncomp != 4) { set_error("alpk_planes_to_rows: ncomp must be 3 or 4"); return 2; }
+    if (ncomp == 4 && ((uintptr_t)rows & 15)) { set_error("alpk_planes_to_rows: rows must be 16-byte aligned"); return 2; }
+    const int grid = grid_for(n, kThreads, 8);
+    if (ncomp == 4) planes_to_rows_kernel<4><<<grid, kThreads, 0, (cudaStream_t)stream>>>(planes, n, rows);
+    else planes_to_rows_kernel<3><<<grid, kThreads, 0, (cudaStream_t)stream>>>(planes, n, rows);
+    return check_launch("alpk_planes_to_rows");
+}
+
 ALPK_EXPORT int alpk_scale(const double* x, uint64_t n, double factor, double* out, void* stream) {
     if (n == 0) return 0;
     if (!x || !out) { set_error("alpk_scale: null argument"); return 2; }

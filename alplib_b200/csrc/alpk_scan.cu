@@ -88,10 +88,11 @@ struct ScanArgs {
     const double* ma_grid; const double* ma2_grid;
     const double* width;         // [n_ma][n_g]
     const double* rescale;       // [n_g]
-    double aa, z; uint64_t seed; uint32_t row_offset;
+    double aa, z; uint64_t seed; uint32_t row_offset; int rounds;
     ScanGeom geo;
-    double* partials;            // [n_ma][n_tiles][n_g]
+    double* partials;            // [n_ma][n_tiles][n_g]  (n_tiles = tiles of this launch: the tile axis is walked in chunks)
     uint32_t n_tiles;
+    uint32_t tile0;              // first tile of this launch
 };
 
 template <bool COMPTON, bool FAST>
@@ -104,7 +105,7 @@ scan_kernel(const ScanArgs a) {
     __shared__ double s_wh[kScanTile];      // fast path: weight with the (exact 0/1/NaN) threshold flag folded in
     constexpr int NP = COMPTON ? (int)CB_NP : 2;
     const int im = blockIdx.y;
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = a.tile0 + blockIdx.x;
     const double ma = __ldg(a.ma_grid + im), ma2 = __ldg(a.ma2_grid + im);
     const uint64_t n = (uint64_t)a.n_rows * a.n_samples;
     const uint64_t base = (uint64_t)tile * kScanTile;
@@ -143,7 +144,7 @@ scan_kernel(const ScanArgs a) {
                 double row[CB_NP];
 #pragma unroll
                 for (int c = 0; c < CB_NP; ++c) row[c] = __ldg(b + c);
-                const double u = uniform_1(a.seed, kTagComptonEa, a.row_offset + r, s);
+                const double u = uniform_1(a.seed, kTagComptonEa, a.row_offset + r, s, a.rounds);
                 ea = FAST ? compton_sample_fast(u, row, cg, w) : compton_sample(u, row, cg, w);
             } else {
                 ea = __ldg(b); w = __ldg(b + 1);
@@ -265,16 +266,18 @@ scan_kernel(const ScanArgs a) {
             }
         }
         acc = warp_sum(acc);
-        if (lane == 0) a.partials[((size_t)im * a.n_tiles + tile) * a.n_g + j] = acc;
+        if (lane == 0) a.partials[((size_t)im * a.n_tiles + blockIdx.x) * a.n_g + j] = acc;
     }
 }
 
+// Fixed-order sum over the tiles of one chunk; later chunks continue the running sum of the earlier ones (the order of the
+// additions is the tile order whatever the chunking, so the map does not depend on the size of the partials buffer).
 __global__ void scan_finalize_kernel(const double* __restrict__ partials, int n_ma, uint32_t n_tiles, int n_g,
-                                     double* __restrict__ out) {
+                                     int accumulate, double* __restrict__ out) {
     const uint64_t total = (uint64_t)n_ma * n_g;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t im = (uint32_t)(i / n_g), j = (uint32_t)(i - (uint64_t)im * n_g);
-        double acc = 0.0;
+        double acc = accumulate ? out[i] : 0.0;
         for (uint32_t t = 0; t < n_tiles; ++t) acc += partials[((size_t)im * n_tiles + t) * n_g + j];
         out[i] = acc;
     }
@@ -293,9 +296,9 @@ ALPK_EXPORT int alpk_scan(int process, const double* e_gamma, const double* phi_
                           const double* log10_e, const double* log10_xs, int n_table,
                           const double* ma_grid, const double* ma2_grid, int n_ma,
                           const double* width, const double* rescale, int n_g,
-                          double c0, double c1, double z, uint32_t n_samples, uint64_t seed,
+                          double c0, double c1, double z, uint32_t n_samples, uint64_t seed, int rng_rounds,
                           const alpk_prop_t* h_geom, const alpk_event_t* h_ev,
-                          double* tables, double* partials, double* out_rates, void* stream) {
+                          double* tables, double* partials, uint32_t partial_tiles, double* out_rates, void* stream) {
     if (process != 0 && process != 1) { set_error("alpk_scan: process must be 0 (Compton) or 1 (Primakoff)"); return 2; }
     if (!h_geom || !h_ev || !tables || !partials || !out_rates || !ma_grid || !ma2_grid || !width || !rescale) {
         set_error("alpk_scan: null argument"); return 2;
@@ -323,25 +326,33 @@ ALPK_EXPORT int alpk_scan(int process, const double* e_gamma, const double* phi_
     memset(&a, 0, sizeof(a));
     a.tables = tables; a.n_rows = n_rows; a.n_samples = n_samples; a.n_ma = n_ma; a.n_g = n_g;
     a.ma_grid = ma_grid; a.ma2_grid = ma2_grid; a.width = width; a.rescale = rescale;
-    a.aa = c0; a.z = z; a.seed = seed; a.row_offset = row_offset;
+    a.aa = c0; a.z = z; a.seed = seed; a.row_offset = row_offset; a.rounds = rng_rounds == 7 ? 7 : 10;
     a.geo.neg_dist_mbm = h_geom->neg_dist_mbm; a.geo.neg_len_mbm = h_geom->neg_len_mbm; a.geo.geom = h_geom->geom;
     a.geo.geom32 = h_geom->geom32; a.geo.apply_geom = h_geom->apply_geom; a.geo.geom_f64 = h_geom->geom_f64;
     a.geo.fast = h_geom->fast;
     a.geo.ev.days_sec = h_ev->days_sec; a.geo.ev.days_sec32 = h_ev->days_sec32; a.geo.ev.days_f64 = h_ev->days_f64;
     a.geo.ev.threshold = h_ev->threshold;
     a.partials = partials;
-    a.n_tiles = alpk_scan_tiles(n_rows, n_samples);
-    dim3 grid(a.n_tiles, (unsigned)n_ma);
+    const uint32_t all_tiles = alpk_scan_tiles(n_rows, n_samples);
+    if (partial_tiles == 0) { set_error("alpk_scan: partials buffer holds no tile"); return 2; }
     if (n_ma > 65535) { set_error("alpk_scan: at most 65535 masses per call"); return 2; }
     const bool fast = h_geom->fast != 0;
-    if (process == 0) {
-        if (fast) scan_kernel<true, true><<<grid, kScanThreads, 0, st>>>(a);
-        else scan_kernel<true, false><<<grid, kScanThreads, 0, st>>>(a);
-    } else {
-        if (fast) scan_kernel<false, true><<<grid, kScanThreads, 0, st>>>(a);
-        else scan_kernel<false, false><<<grid, kScanThreads, 0, st>>>(a);
+    // the tile axis in chunks of what the caller's partials buffer holds (scratch stays bounded for any sample count)
+    for (uint32_t t0 = 0; t0 < all_tiles; t0 += partial_tiles) {
+        a.tile0 = t0;
+        a.n_tiles = all_tiles - t0 < partial_tiles ? all_tiles - t0 : partial_tiles;
+        dim3 grid(a.n_tiles, (unsigned)n_ma);
+        if (process == 0) {
+            if (fast) scan_kernel<true, true><<<grid, kScanThreads, 0, st>>>(a);
+            else scan_kernel<true, false><<<grid, kScanThreads, 0, st>>>(a);
+        } else {
+            if (fast) scan_kernel<false, true><<<grid, kScanThreads, 0, st>>>(a);
+            else scan_kernel<false, false><<<grid, kScanThreads, 0, st>>>(a);
+        }
+        if (check_launch("alpk_scan")) return 1;
+        scan_finalize_kernel<<<grid_for((uint64_t)n_ma * n_g, 256, 4), 256, 0, st>>>(partials, n_ma, a.n_tiles, n_g, t0 != 0,
+                                                                                     out_rates);
+        if (check_launch("alpk_scan(finalize)")) return 1;
     }
-    if (check_launch("alpk_scan")) return 1;
-    scan_finalize_kernel<<<grid_for((uint64_t)n_ma * n_g, 256, 4), 256, 0, st>>>(partials, n_ma, a.n_tiles, n_g, out_rates);
-    return check_launch("alpk_scan(finalize)");
+    return 0;
 }

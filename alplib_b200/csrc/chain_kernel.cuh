@@ -34,6 +34,7 @@ struct ChainArgs {
     const double* table; uint64_t n_rows; uint32_t n_samples; const uint32_t* row_ids;
     typename Prod::Globals g; const double* uniforms; uint64_t seed;
     alp::PhiloxKeys rk;                                       // key schedule of `seed`
+    int rounds;                                               // Philox rounds of the sample stream: 10 or 7
     double* out_e; double* out_f;
     alp::PropConst prop; float* d32; float* s32; double* d64; double* s64;
     alp::EventConst ev; double* event_w; double* partials;
@@ -100,7 +101,8 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
         // sample s uses Philox counter s>>1, word pair s&1: adjacent samples of one row share a call
         const uint64_t ra = r0 + rr[0];
         const uint32_t rid0 = LONG ? rid_long : (a.row_ids ? __ldg(a.row_ids + ra) : (uint32_t)ra);
-        const Philox4 q = philox4x32_10_rk(ss[0] >> 1, 0u, rid0, Prod::kTag, a.rk);
+        const Philox4 q = a.rounds == 7 ? philox4x32_rk<7>(ss[0] >> 1, 0u, rid0, Prod::kTag, a.rk)
+                                        : philox4x32_rk<10>(ss[0] >> 1, 0u, rid0, Prod::kTag, a.rk);
         if (PAIRED) {                        // ss[0] is even
             u[0] = u53(q.x, q.y);
             u[1] = u53(q.z, q.w);
@@ -111,7 +113,7 @@ __device__ __forceinline__ void chain_pair(const ChainArgs<Prod>& a, const doubl
             } else {
                 const uint64_t rb = r0 + rr[1];
                 const uint32_t rid1 = a.row_ids ? __ldg(a.row_ids + rb) : (uint32_t)rb;
-                u[1] = uniform_1(a.seed, Prod::kTag, rid1, ss[1]);
+                u[1] = uniform_1(a.seed, Prod::kTag, rid1, ss[1], a.rounds);
             }
         }
     }
@@ -284,7 +286,7 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
 // Host-side launcher shared by every production channel.
 template <class Prod>
 int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uint32_t n_samples, const uint32_t* row_ids,
-                 const typename Prod::Globals& g, int fast_mode, const double* uniforms, uint64_t seed, double* out_energy,
+                 const typename Prod::Globals& g, int fast_mode, int rng_rounds, const double* uniforms, uint64_t seed, double* out_energy,
                  double* out_flux, const alpk_prop_t* h_prop, float* decay_w32, float* scatter_w32, double* decay_w64,
                  double* scatter_w64, const alpk_event_t* h_ev, double* event_w, double* rate, double* scratch,
                  const double* hist_edges, int n_edges, double* hist, void* stream) {
@@ -301,6 +303,8 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     memset(&a, 0, sizeof(a));
     a.table = row_table; a.n_rows = n_rows; a.n_samples = n_samples; a.row_ids = row_ids;
     a.g = g; a.uniforms = uniforms; a.seed = seed; a.rk = alp::philox_keys(seed);
+    if (rng_rounds != 0 && rng_rounds != 7 && rng_rounds != 10) { set_error("%s: rng_rounds must be 10 (or 0) or 7", what); return 2; }
+    a.rounds = rng_rounds == 7 ? 7 : 10;
     a.out_e = out_energy; a.out_f = out_flux;
     const int stage = h_ev ? 2 : (h_prop ? 1 : 0);
     if (h_prop) { a.prop = to_prop(h_prop); a.d32 = decay_w32; a.s32 = scatter_w32; a.d64 = decay_w64; a.s64 = scatter_w64; }

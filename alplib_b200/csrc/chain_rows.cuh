@@ -20,7 +20,7 @@
 namespace alpk {
 
 #ifndef ALPK_ROWS_MIN_BLOCKS
-#define ALPK_ROWS_MIN_BLOCKS 3
+#define ALPK_ROWS_MIN_BLOCKS 2
 #endif
 #ifndef ALPK_ROWS_THREADS
 #define ALPK_ROWS_THREADS 256
@@ -85,7 +85,9 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
 
 #pragma unroll kRowsUnroll
         for (uint32_t p = p_begin + lane; p < p_stop; p += 32u) {
-            const Philox4 q = philox4x32_10_rk(p, 0u, rid, Prod::kTag, a.rk);     // sample s: counter s>>1, words 2(s&1)..
+            // sample s: counter s>>1 = pair index, words (x,y) / (z,w)
+            const Philox4 q = a.rounds == 7 ? philox4x32_rk<7>(p, 0u, rid, Prod::kTag, a.rk)
+                                            : philox4x32_rk<10>(p, 0u, rid, Prod::kTag, a.rk);
             double u[2], e[2], f[2], d64v[2], s64v[2], evv[2];
             float d32v[2], s32v[2];
             u[0] = u53(q.x, q.y);

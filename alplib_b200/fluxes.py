@@ -76,7 +76,7 @@ class AxionFlux:
 
     def __init__(self, axion_mass, target: Material, det_dist, det_length, det_area, n_samples=1000,
                  off_axis_angle=0.0, timing_window_ns=np.inf, seed=None, device=None, fused=None, keep_f64=False,
-                 precision=None):
+                 precision=None, strict=None):
         self.ma = axion_mass
         self.target_z = target.z[0]
         self.target_a = target.z[0] + target.n[0]
@@ -92,9 +92,13 @@ class AxionFlux:
         self.seed = seed
         self.fused = config.FUSED if fused is None else fused      # False | True | "auto" (see config.py)
         self.keep_f64 = keep_f64          # also keep the float64 weights before the float32 cast (parity / fp64 mode)
+        # strict compatibility (config.STRICT): axion_energy / axion_flux are materialised as Python lists of np.float64
+        # (what the reference's simulate() leaves behind, fluxes.py:222-224), so `.append`, `+ [..]` etc. behave as there
+        self.strict = config.STRICT if strict is None else bool(strict)
         self.precision = precision if precision is not None else config.PRECISION
         if self.precision not in ("fast", "faithful", "fp32"):
             raise ValueError("precision must be 'fast', 'faithful' or 'fp32'")
+        self.rng_rounds = config.PHILOX_ROUNDS[self.precision]     # Philox rounds of the production sample stream (config.py)
         self._device = device
         self._rt_cached = None
         self._reset_samples()
@@ -106,7 +110,10 @@ class AxionFlux:
             self._rt_cached = Runtime.get(self._device)
         return self._rt_cached
 
+    _epoch = 0                              # bumped by every simulate() / propagate(): lets event generators detect stale state
+
     def _reset_samples(self):
+        self._epoch += 1
         self._E = self._F = None            # device float64: axion_energy / axion_flux
         self._D32 = self._S32 = None        # device float32: decay / scatter weights
         self._D64 = self._S64 = None        # device float64 pre-cast weights (keep_f64)
@@ -138,7 +145,12 @@ class AxionFlux:
             return empty
         h = self._host.get(key)
         if h is None:
-            h = self._host[key] = tensor.cpu().numpy()
+            # pinned, chunked, double-buffered device -> host copy (Runtime.to_host)
+            h = self._rt.to_host(tensor)
+            if self.strict and key in ("E", "F"):
+                # the reference's simulate() leaves Python lists of np.float64 (fluxes.py:222-224: list.extend / append)
+                h = list(h)
+            self._host[key] = h
         return h
 
     # ---- the reference's public attributes ---------------------------------------------------------------------------
@@ -239,6 +251,7 @@ class AxionFlux:
             self._host.pop(k, None)
 
     def _propagate(self, decay_width, rescale_factor=1.0, geom_accept=None, time_of_flight_cut=None):
+        self._epoch += 1
         prop = self._prop_params(decay_width, rescale_factor, geom_accept, time_of_flight_cut)
         self._D32 = self._S32 = self._D64 = self._S64 = None
         for k in ("D32", "S32", "D64", "S64"):
@@ -335,6 +348,12 @@ class FluxPrimakoffIsotropic(AxionFlux):
         self.gagamma = axion_coupling
         self.n_samples = n_samples
         self.target_photon_xs = AbsCrossSection(target)
+
+    _TABLE_ATTR = "photon_flux"
+
+    def _row_keep(self, table):
+        """Rows that produce a sample: fluxes.py:136 returns for E_gamma < m_a."""
+        return ~(table[:, 0] < self.ma)
 
     def decay_width(self, gagamma, ma):
         return W_gg(gagamma, ma)
@@ -538,6 +557,11 @@ class FluxComptonIsotropic(_ChainFlux):
         self.row_offset = 0      # global index of photon_flux row 0 when the table is one shard of a larger one
 
     _SAMPLES_FN = "alpk_compton_samples"
+    _TABLE_ATTR = "photon_flux"
+
+    def _row_keep(self, table):
+        """Rows that produce samples: fluxes.py:214-216 returns for s < (m_e + m_a)^2."""
+        return ~(2 * M_E * table[:, 0] + M_E ** 2 < (M_E + self.ma)**2)
 
     def _stage_inputs(self, uniforms=None):
         """Host-side row filter (fluxes.py:214-216) + upload of the surviving rows, their global row ids (Philox
@@ -568,7 +592,7 @@ class FluxComptonIsotropic(_ChainFlux):
     def _launch_rows(self):
         """Per-row constants (threshold window, prefactors, sigma_abs lookup) -> row table, on the device."""
         d_eg, d_ph, n_rows, ns, d_ids, d_u, seed = self._inputs
-        par = P.compton_params(self.ma, self.ge, self.target_z, ns, fast=self.precision != "faithful")
+        par = P.compton_params(self.ma, self.ge, self.target_z, ns, fast=self.precision != "faithful", rng_rounds=self.rng_rounds)
         rt = self._rt
         with rt.activate():
             if n_rows:
@@ -585,7 +609,7 @@ class FluxComptonIsotropic(_ChainFlux):
         self._finish_simulate()
 
 
-_DEVICE_KW = ("seed", "device", "fused", "keep_f64", "precision")
+_DEVICE_KW = ("seed", "device", "fused", "keep_f64", "precision", "strict")
 
 
 def _split_kwargs(kwargs):
@@ -648,7 +672,7 @@ class FluxBremIsotropic(_ChainFlux):
         ef = _as_flux_table(self.electron_flux, "electron_flux")
         ns = int(self.n_samples)
         par = P.brem_params(self.ma, self.ge, self.target_z, self._rad_length, ns, self.boson_type, self.max_t,
-                            use_track_length, fast=self.precision != "faithful")
+                            use_track_length, fast=self.precision != "faithful", rng_rounds=self.rng_rounds)
         if use_track_length:
             ep_min = max(self.ma, M_E)                                           # fluxes.py:346
             keep = ~(ef[:, 0] < ep_min)
@@ -838,7 +862,8 @@ class FluxPairAnnihilationIsotropic(_ChainFlux):
         n_rows, ns = int(rows.shape[0]), int(self.n_samples)
         seed = self.seed if self.seed is not None else (_draw_seed() if uniforms is None else 0)
         self._seed_used = seed
-        par = P.pairann_params(self.ma, self.ge, self.target_z, self._rad_length, ns, fast=self.precision != "faithful")
+        par = P.pairann_params(self.ma, self.ge, self.target_z, self._rad_length, ns, fast=self.precision != "faithful",
+                               rng_rounds=self.rng_rounds)
         rt = self._rt
         with rt.activate():
             d_u = None

@@ -30,6 +30,7 @@ class _EventGenerator:
         self._dev = {}            # name -> device tensor of per-sample event weights
         self._hostcache = {}
         self.materialize_weights = True   # keep per-sample event weights (device) so the attributes can be read
+        self._last_decay = None           # (event params, flux epoch) of the last decays(): lazily computed decay_weights
 
     # reference attributes (host views, lazily copied)
     @property
@@ -42,11 +43,28 @@ class _EventGenerator:
             return np.zeros_like(like)
         h = self._hostcache.get(name)
         if h is None:
-            h = self._hostcache[name] = t.cpu().numpy()
+            h = self._hostcache[name] = self.flux._rt.to_host(t)
         return h
 
     @property
     def decay_weights(self):
+        """days*S_PER_DAY*decay_axion_weight*heaviside(E - threshold, 1) of the last decays() call (generators.py:88-90).
+        In the reduce-only schedule (flux.fused=True, or decays_device()) the kernel returns only the rate; the per-sample
+        weights are then computed here, on demand, by one alpk_decays launch on the (re)materialised flux arrays."""
+        if self._dev.get("decay") is None and self._last_decay is not None:
+            ev, epoch = self._last_decay
+            fl = self.flux
+            if epoch != fl._epoch:
+                raise RuntimeError("decay_weights: the flux was re-simulated / re-propagated after decays(); call decays() again")
+            fl._ensure_production()
+            fl._ensure_propagated()
+            rt = fl._rt
+            n = 0 if fl._E is None else int(fl._E.shape[0])
+            with rt.activate():
+                rate, evw = rt.empty(1), rt.empty(n)
+                N.call("alpk_decays", N.ptr(fl._E), N.ptr(fl._D32), n, C.byref(ev), N.ptr(evw), N.ptr(rate),
+                       N.ptr(rt.scratch), rt.stream())
+            self._store("decay", evw)
         return self._weights("decay", self.flux.decay_axion_weight)
 
     @property
@@ -73,12 +91,15 @@ class _EventGenerator:
         self._need_f32(self.flux._D32, "decay_axion_weight")       # (None while a fused chain is still pending)
         rate, evw = self.flux._decay_rate(ev, self.materialize_weights and self.flux.fused is not True)
         self._store("decay", evw)
+        self._last_decay = (ev, self.flux._epoch)
         return np.float64(rate.item())
 
     def decays_device(self, days_exposure, threshold):
         """Same as decays() but returns the rate as a 1-element CUDA tensor without synchronising."""
         ev = P.event_params(days_exposure, threshold)
         rate, evw = self.flux._decay_rate(ev, False)
+        self._store("decay", None)                 # (no stale weights of an earlier call; computed on demand if read)
+        self._last_decay = (ev, self.flux._epoch)
         return rate
 
     def _scatter(self, kind, xs, ntargets, days_exposure, threshold):
@@ -155,7 +176,7 @@ class PhotonEventGenerator(_EventGenerator):
         return self._scatter(1, P.iprimakoff_consts(ma, gagamma, self.det_z), ntargets, days_exposure, threshold)
 
     def simulate_decay_4vectors(self, days_exposure, n_samples=1, uniforms=None, seed=None, parent_phis=None,
-                                dtype=np.float64):
+                                dtype=np.float64, strict=None):
         """2-body decay a -> gamma gamma of every flux sample, `n_samples` decays each (generators.py:94-128).
 
         Returns (photon-1 4-vectors, photon-2 4-vectors, weights): two LorentzVectorArray (sequence of
@@ -164,7 +185,10 @@ class PhotonEventGenerator(_EventGenerator):
         (theta_i, phi_i) with phi_i drawn like the reference draws it (or given as `parent_phis`).
         `uniforms` (parity mode): array [n_flux, 2, n_samples] -- per parent the phi draws then the theta draws.
         `dtype=np.float32`: optional single-precision mode (forward parents, free-running RNG): float 4-vectors and
-        weights, 36 B/event instead of 72, relative accuracy ~1e-7 of the parent energy (north star bound 1e-5)."""
+        weights, 36 B/event instead of 72, relative accuracy ~1e-7 of the parent energy (north star bound 1e-5).
+        `strict=True` (default `flux.strict` / config.STRICT): return the reference's containers -- two Python lists of
+        `LorentzVector` objects and a list of weights (generators.py:124-128); meant for small n (one Python object per
+        event)."""
         fl = self.flux
         fl._ensure_production()
         fl._ensure_propagated()
@@ -219,7 +243,10 @@ class PhotonEventGenerator(_EventGenerator):
                 table = rt.empty(n_flux * N.PARENT_GENERAL_NP)
                 N.call("alpk_decay2body_general", N.ptr(d_p4), N.ptr(d_w), n_flux, 0.0, 0.0, ns, None, N.ptr(d_u),
                        C.c_uint64(seed), N.ptr(table), N.ptr(p1), N.ptr(p2), N.ptr(w), None, rt.stream())
-        return LorentzVectorArray(p1), LorentzVectorArray(p2), _DeviceWeights(w)
+        lv1, lv2, wts = LorentzVectorArray(p1), LorentzVectorArray(p2), _DeviceWeights(w)
+        if fl.strict if strict is None else strict:
+            return list(lv1), list(lv2), list(wts)
+        return lv1, lv2, wts
 
 
 class _DeviceWeights:
@@ -231,7 +258,8 @@ class _DeviceWeights:
 
     def _host(self):
         if self._h is None:
-            self._h = self.device.cpu().numpy()
+            from .runtime import Runtime
+            self._h = Runtime.get(self.device.device).to_host(self.device)
         return self._h
 
     def __len__(self):

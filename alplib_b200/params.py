@@ -63,7 +63,7 @@ def event_params(days_exposure, threshold):
     return e
 
 
-def compton_params(ma, g, z, n_samples, fast=False):
+def compton_params(ma, g, z, n_samples, fast=False, rng_rounds=10):
     c = N.ComptonT()
     c.ma = float(ma)
     c.ma2 = float(ma ** 2)
@@ -71,6 +71,7 @@ def compton_params(ma, g, z, n_samples, fast=False):
     c.z = float(z)
     c.n_samples = float(n_samples)
     c.fast = 1 if fast else 0
+    c.rng_rounds = int(rng_rounds)
     return c
 
 
@@ -99,7 +100,8 @@ def gauss_legendre():
     return np.ascontiguousarray(x), np.ascontiguousarray(w)
 
 
-def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_t=5.0, use_track_length=True, fast=False):
+def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_t=5.0, use_track_length=True, fast=False,
+                rng_rounds=10):
     """fluxes.py:276-337 + prod_xs.py:209-221, 313-323 scalars (z is the np.int64 of Material.z[0])."""
     from numpy import log, power
     b = N.BremT()
@@ -126,10 +128,11 @@ def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_
     b.vector = 1 if boson_type == "vector" else 0
     b.use_track_length = 1 if use_track_length else 0
     b.fast = 1 if fast else 0
+    b.rng_rounds = int(rng_rounds)
     return b
 
 
-def pairann_params(ma, ge, z, rad_length, n_samples, fast=False):
+def pairann_params(ma, ge, z, rad_length, n_samples, fast=False, rng_rounds=10):
     """fluxes.py:484,518 + matrix_element.py:717-734 scalars."""
     p = N.PairAnnT()
     p.ma = float(ma)
@@ -144,4 +147,5 @@ def pairann_params(ma, ge, z, rad_length, n_samples, fast=False):
     p.hbarc2 = float(HBARC ** 2)
     p.n_samples = float(n_samples)
     p.fast = 1 if fast else 0
+    p.rng_rounds = int(rng_rounds)
     return p

@@ -6,6 +6,7 @@ event-rate map in a single kernel launch (grid = mass x sample tile, threads = c
 The samples are the ones the per-point API would generate with the same seed, so each map entry equals the per-point
 result up to the order of the final sum.
 """
+import collections
 import ctypes as C
 
 import numpy as np
@@ -17,7 +18,7 @@ from . import config
 from . import params as P
 from .constants import ALPHA, M_E, pi
 from .decay import W_ee, W_gg, W_gg_loop, b1
-from .dist import merge_row_blocks, shard_range, world as _world
+from .dist import gather_row_blocks, world as _world
 from .fluxes import _as_flux_table, _draw_seed
 from .materials import Material
 from .photon_xs import AbsCrossSection
@@ -25,6 +26,53 @@ from .runtime import Runtime
 
 COMPTON, PRIMAKOFF = 0, 1
 _PROC = {"compton": COMPTON, "primakoff": PRIMAKOFF}
+
+
+_PARTIALS_BYTES = 256 << 20          # cap of the per-call partial-sum scratch (the tile axis is walked in chunks beyond it)
+_grid_cache = collections.OrderedDict()     # (device, process, grids, g0, loop_decay) -> device tables of the grid
+_flux_cache = collections.OrderedDict()     # (device, table bytes) -> device columns of the flux table
+_CACHE_SLOTS = 8
+
+
+def _cached(cache, key, build):
+    hit = cache.get(key)
+    if hit is not None:
+        cache.move_to_end(key)
+        return hit
+    val = cache[key] = build()
+    while len(cache) > _CACHE_SLOTS:
+        cache.popitem(last=False)
+    return val
+
+
+def _grid_tables(rt, proc, ma, g, g0, loop_decay):
+    """Device tables that depend only on the grid: ma, ma**2, width[n_ma][n_g], rescale[n_g] -- kept resident across calls
+    (a scan is usually repeated on the same grid for several fluxes / exposures / detectors)."""
+    def build():
+        # decay widths of every grid point, with the operation order of decay.py:10-13, 26-29, 48-52 (vectorised: 4e4 scalar
+        # calls would cost more than the scan kernel itself); per-axis powers as Python-float pow (what the scalar width
+        # functions evaluate), products broadcast in their order
+        g2 = np.array([float(x) ** 2 for x in g])
+        ma3 = np.array([float(m) ** 3 for m in ma])
+        with np.errstate(all="ignore"):
+            if proc == COMPTON:
+                open_ = 1 - 4 * (M_E / ma) ** 2 > 0
+                root = np.sqrt(np.where(open_, 1 - (2 * M_E / ma) ** 2, 0.0))
+                width = np.where(open_[:, None], (g2[None, :] * ma[:, None]) * root[:, None] / (8 * pi), 0.0)
+                if loop_decay:      # rare option: keep the scalar functions (exact same widths as the per-point API)
+                    width = np.array([[W_ee(gj, m) + W_gg_loop(gj, m, M_E) for gj in g] for m in ma])
+            else:
+                width = g2[None, :] * ma3[:, None] / (64 * pi)
+        rescale = power(g / g0, 2)
+        # ONE pinned H2D copy for the four tables
+        return tuple(rt.upload_packed([(ma, np.float64), (ma ** 2, np.float64), (np.ascontiguousarray(width).ravel(), np.float64),
+                                       (rescale, np.float64)]))
+    return _cached(_grid_cache, (rt.index, proc, ma.tobytes(), g.tobytes(), float(g0), bool(loop_decay)), build)
+
+
+def _flux_columns(rt, pf):
+    return _cached(_flux_cache, (rt.index, pf.shape, pf.tobytes()),
+                   lambda: tuple(rt.upload_packed([(pf[:, 0], np.float64), (pf[:, 1], np.float64)])))
 
 
 def scan_rates(process, photon_flux, target, ma_grid, g_grid, n_samples=100, det_dist=4.0, det_length=0.2,
@@ -46,22 +94,6 @@ def scan_rates(process, photon_flux, target, ma_grid, g_grid, n_samples=100, det
     precision = precision if precision is not None else config.PRECISION
     seed = seed if seed is not None else _draw_seed()
     z = target.z[0]
-    # decay widths of every grid point, with the operation order of decay.py:10-13, 26-29, 48-52 (vectorised: 4e4 scalar
-    # calls would cost more than the scan kernel itself)
-    # per-axis powers as Python-float pow (what the scalar width functions evaluate), products broadcast in their order
-    g2 = np.array([float(x) ** 2 for x in g])
-    ma3 = np.array([float(m) ** 3 for m in ma])
-    with np.errstate(all="ignore"):
-        if proc == COMPTON:
-            open_ = 1 - 4 * (M_E / ma) ** 2 > 0
-            root = np.sqrt(np.where(open_, 1 - (2 * M_E / ma) ** 2, 0.0))
-            width = np.where(open_[:, None], (g2[None, :] * ma[:, None]) * root[:, None] / (8 * pi), 0.0)
-            if loop_decay:      # rare option: keep the scalar functions (exact same widths as the per-point API)
-                width = np.array([[W_ee(gj, m) + W_gg_loop(gj, m, M_E) for gj in g] for m in ma])
-        else:
-            width = g2[None, :] * ma3[:, None] / (64 * pi)
-    width = np.ascontiguousarray(width)
-    rescale = power(g / g0, 2)
     if proc == COMPTON:
         c0, c1 = float(g0 ** 2 / 4 / pi), 0.0
         np_row = N.COMPTON_NP
@@ -77,31 +109,50 @@ def scan_rates(process, photon_flux, target, ma_grid, g_grid, n_samples=100, det
     xs = AbsCrossSection(target)
     n_rows = int(pf.shape[0])
     with rt.activate():
-        le, lx, nt = xs.device_table(rt)
-        d_e, d_p = rt.upload(pf[:, 0]), rt.upload(pf[:, 1])
-        d_ma, d_ma2 = rt.upload(ma), rt.upload(ma ** 2)
-        d_w, d_r = rt.upload(width), rt.upload(rescale)
-        n_tiles = int(N.lib().alpk_scan_tiles(n_rows, int(n_samples)))
-        tables = rt.empty(max(1, n_ma * n_rows * np_row))
-        partials = rt.empty(max(1, n_ma * n_tiles * n_g))
         out = rt.empty(n_ma * n_g)
-        N.call("alpk_scan", proc, N.ptr(d_e), N.ptr(d_p), n_rows, int(row_offset), N.ptr(le), N.ptr(lx), nt,
-               N.ptr(d_ma), N.ptr(d_ma2), n_ma, N.ptr(d_w), N.ptr(d_r), n_g, c0, c1, float(z), int(n_samples),
-               C.c_uint64(seed), C.byref(prop), C.byref(ev), N.ptr(tables), N.ptr(partials), N.ptr(out), rt.stream())
+        if n_ma and n_g:
+            le, lx, nt = xs.device_table(rt)
+            d_e, d_p = _flux_columns(rt, pf)
+            d_ma, d_ma2, d_w, d_r = _grid_tables(rt, proc, ma, g, g0, loop_decay)
+            n_tiles = max(1, int(N.lib().alpk_scan_tiles(n_rows, int(n_samples))))
+            # partial sums [n_ma][tiles of one chunk][n_g]: bounded, the launcher walks the tile axis in chunks
+            chunk_tiles = max(1, min(n_tiles, _PARTIALS_BYTES // (8 * n_ma * n_g)))
+            tables = rt.empty(max(1, n_ma * n_rows * np_row))
+            partials = rt.empty(n_ma * chunk_tiles * n_g)
+            N.call("alpk_scan", proc, N.ptr(d_e), N.ptr(d_p), n_rows, int(row_offset), N.ptr(le), N.ptr(lx), nt,
+                   N.ptr(d_ma), N.ptr(d_ma2), n_ma, N.ptr(d_w), N.ptr(d_r), n_g, c0, c1, float(z), int(n_samples),
+                   C.c_uint64(seed), int(config.PHILOX_ROUNDS[precision]), C.byref(prop), C.byref(ev), N.ptr(tables),
+                   N.ptr(partials), chunk_tiles, N.ptr(out),
+                   rt.stream())
     out = out.view(n_ma, n_g)
-    return out if return_device else out.cpu().numpy()
+    return out if return_device else rt.to_host(out)
 
 
 def scan_rates_distributed(process, photon_flux, target, ma_grid, g_grid, group=None, **kw):
     """`scan_rates` with the mass axis sharded over the ranks of a torch.distributed process group (one process per
-    GPU).  Every rank returns the full map; the only communication is one all-reduce of the (n_ma x n_g) map
-    (NCCL over NVLink on the GPU box)."""
+    GPU).  Masses are dealt round-robin (rank r takes ma[r::world]): the cost of a mass row is very uneven -- stable
+    ALPs (m_a < 2 m_e for the electron coupling) are skipped by the kernel, heavy ones have few rows above threshold --
+    and contiguous blocks would leave some ranks idle.  Every rank returns the full map; the only communication is one
+    all-gather of the ranks' disjoint row blocks (NCCL over NVLink on the GPU box)."""
     rank, nranks = _world(group)
     ma = np.ascontiguousarray(ma_grid, dtype=np.float64).ravel()
     g = np.ascontiguousarray(g_grid, dtype=np.float64).ravel()
-    lo, hi = shard_range(ma.shape[0], rank, nranks)
     kw = dict(kw)
     kw.setdefault("g0", float(g[0]))
+    if kw.get("seed") is None and nranks > 1:
+        # one Philox key for the whole map: drawn on rank 0, broadcast (each rank drawing its own would make the map depend
+        # on the number of ranks)
+        import torch.distributed as dist
+        box = [_draw_seed() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        kw["seed"] = int(box[0])
+    if nranks == 1:
+        return scan_rates(process, photon_flux, target, ma, g, **kw)
     kw["return_device"] = True
-    local = scan_rates(process, photon_flux, target, ma[lo:hi], g, **kw)
-    return merge_row_blocks(local, lo, ma.shape[0], group).cpu().numpy()
+    local = scan_rates(process, photon_flux, target, ma[rank::nranks], g, **kw)
+    counts = [len(range(r, ma.shape[0], nranks)) for r in range(nranks)]
+    blocks = gather_row_blocks(local, counts, group)
+    full = torch.empty((ma.shape[0], g.shape[0]), dtype=local.dtype, device=local.device)
+    for r, b in enumerate(blocks):
+        full[r::nranks] = b
+    return Runtime.get(local.device).to_host(full)

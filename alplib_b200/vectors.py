@@ -106,6 +106,22 @@ class LorentzVector:
         return Vector3(self.p1/self.p0, self.p2/self.p0, self.p3/self.p0)
 
 
+def planes_to_host_rows(planes):
+    """(C, N) CUDA planes -> (N, C) host array: transposed on the device (alpk_planes_to_rows), then one pinned, chunked,
+    double-buffered device -> host copy (Runtime.to_host) -- not a strided pageable gather."""
+    import torch
+    from . import _native as N
+    from .runtime import Runtime
+    c, n = int(planes.shape[0]), int(planes.shape[1])
+    if planes.dtype != torch.float64 or c not in (3, 4):
+        return np.ascontiguousarray(Runtime.get(planes.device).to_host(planes).T)       # (float32 mode: small)
+    rt = Runtime.get(planes.device)
+    with rt.activate():
+        rows = torch.empty((n, c), dtype=torch.float64, device=planes.device)
+        N.call("alpk_planes_to_rows", N.ptr(planes), n, c, N.ptr(rows), rt.stream())
+        return rt.to_host(rows)
+
+
 class LorentzVectorArray:
     """N four-vectors stored as planes (E, px, py, pz) -- what `simulate_decay_4vectors` returns.
 
@@ -121,7 +137,7 @@ class LorentzVectorArray:
     @property
     def pmu(self):
         if self._host is None:
-            self._host = np.ascontiguousarray(self.device.cpu().numpy().T)
+            self._host = planes_to_host_rows(self.device)
         return self._host
 
     def __len__(self):

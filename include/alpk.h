@@ -135,6 +135,7 @@ typedef struct {
     double z;                /* target Z */
     double n_samples;        /* n_samples as a double */
     int    fast;             /* 1 = fast mode: shared reciprocal, per-row factors pre-folded (<= 1e-9 relative) */
+    int    rng_rounds;       /* Philox rounds of the free-running sample stream: 10 (or 0) = Philox4x32-10, 7 = Philox4x32-7 */
 } alpk_compton_t;
 
 /* per-row table [n_rows][ALPK_COMPTON_NP]; rows already filtered by the host (s >= (M_E+ma)^2, fluxes.py:214-216) */
@@ -199,6 +200,7 @@ typedef struct {
     int use_track_length;    /* simulate(use_track_length=...) */
     int fast;                /* 1: fast arithmetic mode of the per-sample production (<= 1e-9 relative); must equal the mode of a
                                 fused alpk_prop_t so that every schedule produces the same bits */
+    int rng_rounds;          /* as in alpk_compton_t (the per-sample E_a stream; the per-row draw stays Philox4x32-10) */
 } alpk_brem_t;
 
 /* Row prelude: one thread per electron row (rows already filtered by the host: E0 >= ep_min in track-length mode).
@@ -238,6 +240,7 @@ typedef struct {
     double z, ge2, ntad, hbarc2;   /* applied left to right after the positron weight, fluxes.py:518 */
     double n_samples;
     int fast;                /* as in alpk_brem_t */
+    int rng_rounds;          /* as in alpk_compton_t */
 } alpk_pairann_t;
 
 /* rows already filtered by the host (E+ >= max((ma^2-me^2)/(2 me), me), fluxes.py:507) */
@@ -294,6 +297,10 @@ int alpk_pairgamma(const double* centers, const double* widths, uint64_t n_bins,
                    const alpk_pairgamma_t* h_par, const double* u_bins, const double* u_alp, uint64_t seed,
                    double* out_energy, double* out_flux, void* stream);
 
+/* planes[ncomp][n] -> rows[n][ncomp] (ncomp 3 or 4): the per-event layout of LorentzVector.pmu / Vector3.vec
+ * (cross_section_mc.py:14-143) for a single contiguous device -> host copy of all events.  rows 16-byte aligned. */
+int alpk_planes_to_rows(const double* planes, uint64_t n, int ncomp, double* rows, void* stream);
+
 /* out[i] = factor * x[i]  (float64 weights of FluxPi0Isotropic.propagate, fluxes.py:985-991) */
 int alpk_scale(const double* x, uint64_t n, double factor, double* out, void* stream);
 
@@ -309,16 +316,19 @@ int alpk_hist(const double* x, const double* w64_or_null, const float* w32_or_nu
  * row_offset: global index of row 0 (Philox key) when the table is a shard.
  * ma_grid/ma2_grid[n_ma] (ma, ma**2); width[n_ma][n_g] decay widths; rescale[n_g] = (g/g0)**2.
  * h_geom: detector geometry / acceptance / fast flag of alpk_prop_t (ma, width, rescale fields ignored).
- * tables: scratch [n_ma][n_rows][ALPK_COMPTON_NP or 2]; partials: scratch [n_ma][alpk_scan_tiles()][n_g];
+ * rng_rounds: Philox rounds of the Compton sample stream (as alpk_compton_t: must match the per-point API's to reproduce it).
+ * tables: scratch [n_ma][n_rows][ALPK_COMPTON_NP or 2]; partials: scratch [n_ma][partial_tiles][n_g] with
+ * 1 <= partial_tiles <= alpk_scan_tiles(): the tile axis (1024 samples per tile) is walked in chunks of partial_tiles, so
+ * the scratch stays bounded for any sample count; the sums run in tile order whatever the chunking.
  * out_rates[n_ma][n_g] = decays(days, threshold) of every grid point. */
 uint32_t alpk_scan_tiles(uint32_t n_rows, uint32_t n_samples);
 int alpk_scan(int process, const double* e_gamma, const double* phi_gamma, uint32_t n_rows, uint32_t row_offset,
               const double* log10_e, const double* log10_xs, int n_table,
               const double* ma_grid, const double* ma2_grid, int n_ma,
               const double* width, const double* rescale, int n_g,
-              double c0, double c1, double z, uint32_t n_samples, uint64_t seed,
+              double c0, double c1, double z, uint32_t n_samples, uint64_t seed, int rng_rounds,
               const alpk_prop_t* h_geom, const alpk_event_t* h_ev,
-              double* tables, double* partials, double* out_rates, void* stream);
+              double* tables, double* partials, uint32_t partial_tiles, double* out_rates, void* stream);
 
 /* FP64 issue-rate microbenchmark: `blocks` CTAs x 256 threads x 8 independent DFMA chains x iters (bench.py uses it
  * to measure the FP64 roofline denominator on the box).  out: >= blocks*256 doubles (never written in practice). */

@@ -11,12 +11,24 @@ W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 TAG_COMPTON_EA, TAG_BREM_ROW, TAG_BREM_EA, TAG_RESONANCE, TAG_PAIRANN, TAG_DECAY2 = 1, 2, 3, 4, 5, 6
 TAG_SCATTER2 = 8          # alpk_scatter2to2 (alpk_scatter2.cu)
 
+# Rounds of the per-sample PRODUCTION streams (tags 1, 3, 5): 10 in the faithful arithmetic mode, 7 (Philox4x32-7) in the fast
+# modes -- alplib_b200/config.py:PHILOX_ROUNDS.  Tests set this to the mode under test; every other stream is 10 rounds.
+PRODUCTION_ROUNDS = 10
+_PRODUCTION_TAGS = (TAG_COMPTON_EA, TAG_BREM_EA, TAG_PAIRANN)
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
+
+def rounds_of(tag, rounds=None):
+    if rounds is not None:
+        return int(rounds)
+    return PRODUCTION_ROUNDS if tag in _PRODUCTION_TAGS else 10
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1, rounds=10):
+    """Philox4x32-R block function (R = 10 unless `rounds` says otherwise)."""
     c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint32) for c in np.broadcast_arrays(c0, c1, c2, c3))
     k0 = np.uint32(k0); k1 = np.uint32(k1)
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        for _ in range(int(rounds)):
             p0 = M0 * c0.astype(np.uint64)
             p1 = M1 * c2.astype(np.uint64)
             hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
@@ -30,12 +42,13 @@ def u53(a, b):
     return ((a >> np.uint32(5)).astype(np.float64) * 67108864.0 + (b >> np.uint32(6)).astype(np.float64)) / 9007199254740992.0
 
 
-def uniform_1(seed, tag, row, n):
+def uniform_1(seed, tag, row, n, rounds=None):
     """n uniforms of stream (seed, tag, row): sample s = counter s>>1, word pair s&1."""
     s = np.arange(n, dtype=np.uint64)
     c = s >> np.uint64(1)
     x, y, z, w = philox4x32_10((c & np.uint64(0xFFFFFFFF)).astype(np.uint32), (c >> np.uint64(32)).astype(np.uint32),
-                               np.uint32(row), np.uint32(tag), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+                               np.uint32(row), np.uint32(tag), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF,
+                               rounds=rounds_of(tag, rounds))
     return np.where((s & np.uint64(1)) == 1, u53(z, w), u53(x, y))
 
 

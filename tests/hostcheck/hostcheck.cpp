@@ -39,6 +39,10 @@ void hc_philox(uint64_t seed, uint32_t tag, uint32_t row, uint64_t n, int two, d
     }
 }
 
+void hc_philox_rounds(uint64_t seed, uint32_t tag, uint32_t row, uint64_t n, int rounds, double* out) {
+    for (uint64_t s = 0; s < n; ++s) out[s] = uniform_1(seed, tag, row, s, rounds);
+}
+
 void hc_exp_fast(const double* x, uint64_t n, double* out) {
     for (uint64_t i = 0; i < n; ++i) out[i] = exp_fast(x[i]);
 }

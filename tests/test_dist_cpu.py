@@ -27,6 +27,34 @@ def test_shard_range_partitions():
     assert off == 4 and rows.tolist() == t[4:7].tolist()
 
 
+def test_shard_kept_rows_balances_the_kept_rows():
+    e = np.logspace(np.log10(0.5), 3, 50)
+    t = np.stack([e, np.ones(50)], axis=1)
+    keep = e >= 4.0
+    for w in (1, 2, 3, 8):
+        blocks = [D.shard_kept_rows(t, keep, r, w) for r in range(w)]
+        kept = [b[b[:, 0] >= 4.0] for b, _ in blocks]
+        sizes = [k.shape[0] for k in kept]
+        assert sum(sizes) == int(keep.sum()) and max(sizes) - min(sizes) <= 1
+        assert np.array_equal(np.concatenate(kept), t[keep])
+        for b, off in blocks:
+            if b.shape[0]:
+                assert np.array_equal(b, t[off:off + b.shape[0]]) and keep[off] and keep[off + b.shape[0] - 1]
+    none, off = D.shard_kept_rows(t, np.zeros(50, bool), 1, 4)
+    assert none.shape[0] == 0 and off == 0
+
+    class Fl:                                  # shard_flux only touches the table attribute and row_offset
+        _TABLE_ATTR = "photon_flux"
+        photon_flux = t.tolist()
+        row_offset = 3
+
+        def _row_keep(self, table):
+            return table[:, 0] >= 4.0
+    f = D.shard_flux(Fl(), rank=1, nranks=2)
+    b, off = D.shard_kept_rows(t, keep, 1, 2)
+    assert np.array_equal(f.photon_flux, b) and f.row_offset == 3 + off
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -62,8 +90,13 @@ def _worker(rank, world, port, q):
         lo, hi = D.shard_range(7, rank, world)
         local = torch.arange(lo * 3, hi * 3, dtype=torch.float64).view(hi - lo, 3)
         full = D.merge_row_blocks(local, lo, 7)
+        # the same blocks through the all-gather path (ragged: 4 + 3 rows) and the packed [rates || hist] merge
+        counts = [b - a for a, b in (D.shard_range(7, r, world) for r in range(world))]
+        gathered = torch.cat(D.gather_row_blocks(local, counts))
+        rr, hh = D.merged_rates_and_hists([torch.tensor([1.0 + rank], dtype=torch.float64), torch.tensor([10.0 * rank], dtype=torch.float64)],
+                                          [torch.arange(5, dtype=torch.float64) * (rank + 1)])
         if rank == 0:
-            q.put((t.tolist(), full.tolist(), D.world()))
+            q.put((t.tolist(), full.tolist(), D.world(), gathered.tolist(), rr.tolist(), hh[0].tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -76,7 +109,7 @@ def test_two_rank_sharding_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    (rate2, n2), full, (rk, ws) = q.get(timeout=100)
+    (rate2, n2), full, (rk, ws), gathered, rr, hh = q.get(timeout=100)
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
@@ -86,4 +119,5 @@ def test_two_rank_sharding_matches_single_process():
     assert (rk, ws) == (0, 2)
     assert n2 == E1.shape[0]
     assert rate2 == pytest.approx(rate1, rel=1e-13)
-    assert full == np.arange(21, dtype=float).reshape(7, 3).tolist()
+    assert full == np.arange(21, dtype=float).reshape(7, 3).tolist() and gathered == full
+    assert rr == [3.0, 10.0] and hh == [0.0, 3.0, 6.0, 9.0, 12.0]

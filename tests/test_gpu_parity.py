@@ -21,10 +21,11 @@ GA = O.geom_acceptance(0.04, 4.0)
 def precision(request):
     """Every GPU parity test runs in both arithmetic modes (alplib_b200.config.PRECISION)."""
     from alplib_b200 import config
-    old = config.PRECISION
+    old, old_rounds = config.PRECISION, PX.PRODUCTION_ROUNDS
     config.PRECISION = request.param
+    PX.PRODUCTION_ROUNDS = config.PHILOX_ROUNDS[request.param]      # the oracle's Philox replays the stream of the mode under test
     yield request.param
-    config.PRECISION = old
+    config.PRECISION, PX.PRODUCTION_ROUNDS = old, old_rounds
 
 
 @pytest.fixture(scope="module")

@@ -31,6 +31,27 @@ def test_philox_known_answers():
     assert [int(v) for v in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
+def test_philox_7_rounds_device_code_matches_numpy(hostcheck):
+    """Philox4x32-7 (fast-mode production streams, config.PHILOX_ROUNDS): the kernels' C++ and the NumPy restatement are
+    independent implementations of the same round function (pinned at 10 rounds by the Random123 vectors above)."""
+    n = 4097
+    out = np.empty(n)
+    for tag, row in ((PX.TAG_COMPTON_EA, 0), (PX.TAG_BREM_EA, 123456), (PX.TAG_PAIRANN, 2 ** 32 - 1)):
+        for rounds in (7, 10):
+            hostcheck.hc_philox_rounds(C.c_uint64(0xA1B2C3D4E5F60718), C.c_uint32(tag), C.c_uint32(row), C.c_uint64(n), rounds, dptr(out))
+            assert np.array_equal(out, PX.uniform_1(0xA1B2C3D4E5F60718, tag, row, n, rounds=rounds))
+    a = PX.uniform_1(5, PX.TAG_COMPTON_EA, 0, 1000, rounds=7)
+    b = PX.uniform_1(5, PX.TAG_COMPTON_EA, 0, 1000, rounds=10)
+    assert not np.array_equal(a, b) and abs(a.mean() - 0.5) < 0.03 and abs(a.var() - 1 / 12) < 0.01
+    old = PX.PRODUCTION_ROUNDS
+    try:
+        PX.PRODUCTION_ROUNDS = 7                      # default rounds: production tags follow the module setting, others stay 10
+        assert np.array_equal(PX.uniform_1(5, PX.TAG_COMPTON_EA, 0, 1000), a)
+        assert np.array_equal(PX.uniform_1(5, PX.TAG_BREM_ROW, 0, 8), PX.uniform_1(5, PX.TAG_BREM_ROW, 0, 8, rounds=10))
+    finally:
+        PX.PRODUCTION_ROUNDS = old
+
+
 def test_philox_device_code_matches_numpy(hostcheck):
     seed = 0xA1B2C3D4_0000_0007
     out = np.empty(1001)
