@@ -15,7 +15,7 @@ SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_pairann.cu", "a
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
-SCRATCH_DOUBLES = 16384
+SCRATCH_DOUBLES = 1 << 20
 COMPTON_NP = 12
 PARENT_NP = 6
 PARENT_GENERAL_NP = 20
@@ -155,6 +155,7 @@ _SIGNATURES = {
     "alpk_decays": ([_P, _P, _U64, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_scatter_events": ([_I, _P, _P, _U64, C.POINTER(_D), _D, _D, C.POINTER(EventT), _P, _P, _P, _P], _I),
     "alpk_pair_events": ([_P, _P, _U64, _P, _P, _I, _D, _D, C.POINTER(EventT), _P, _P, _P, _P], _I),
+    "alpk_table_sigma": ([_I, _P, _P, _I, _P, _U64, _P, _P], _I),
     "alpk_abs_sigma_mev": ([_P, _P, _I, _P, _U64, _P, _P], _I),
     "alpk_primakoff": ([_P, _P, _U64, _P, _P, _I, _D, _D, _D, _P, _P, _P], _I),
     "alpk_compton_rows": ([_P, _P, _U64, _P, _P, _I, C.POINTER(ComptonT), _P, _P], _I),

@@ -31,3 +31,10 @@ STRICT = _os.environ.get("ALPK_STRICT", "0") not in ("0", "", "false", "False")
 # stream (decay angles, per-row draws, meson channels, 2 -> 2 scattering) is Philox4x32-10.
 PHILOX_ROUNDS = {"fast": int(_os.environ.get("ALPK_PHILOX_ROUNDS", "7")), "fp32": int(_os.environ.get("ALPK_PHILOX_ROUNDS", "7")),
                  "faithful": 10}
+
+# Device -> host copies of large per-sample arrays (flux.axion_energy ..., LorentzVectorArray.pmu): True returns NumPy arrays
+# that are views of PINNED host memory from torch's caching host allocator, filled by one cudaMemcpyAsync at the PCIe rate
+# (measured 52 GB/s on the B200 boxes); False copies through two 64 MiB pinned staging buffers into an ordinary (pageable)
+# NumPy array, double-buffered -- bounded pinned memory, but limited by the host-side copy and the page faults of the fresh
+# array (~5 GB/s measured).
+PINNED_RESULTS = _os.environ.get("ALPK_PINNED_RESULTS", "1") not in ("0", "", "false", "False")

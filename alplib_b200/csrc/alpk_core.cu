@@ -227,6 +227,23 @@ __device__ __forceinline__ void stage_table(double* s_e, double* s_xs, const dou
     __syncthreads();
 }
 
+// Generic log-log table lookup of the tabulated cross-section classes (photon_xs.py:45-52, 117-128):
+//   kind 0: 10**interp(log10 E; left = 0, right = 0)                                  AbsCrossSection.sigma_cm2 / sigma_mev
+//   kind 1: heaviside(E - 2 me, 0) * 10**interp(log10 E; left = -inf, right = fp[-1])   (ALP)PairProdutionCrossSection
+// The unit (cm2 or MeV^-2) is whatever the caller folded into log10_xs, exactly as the reference folds it.
+__global__ void __launch_bounds__(kThreads)
+table_sigma_kernel(int kind, const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
+                   const double* __restrict__ energy, uint64_t n, double* __restrict__ out) {
+    __shared__ double s_e[kMaxTable], s_xs[kMaxTable];
+    stage_table(s_e, s_xs, log10_e, log10_xs, n_table);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = __ldg(energy + i);
+        if (kind == 0) out[i] = pow(10.0, interp(log10(e), s_e, s_xs, n_table, 0.0, 0.0));
+        else out[i] = heaviside(e - 2 * kME, 0.0) * pow(10.0, interp(log10(e), s_e, s_xs, n_table, -INFINITY, s_xs[n_table - 1]));
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 abs_sigma_kernel(const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
                  const double* __restrict__ energy, uint64_t n, double* __restrict__ out) {
@@ -490,6 +507,16 @@ ALPK_EXPORT int alpk_sum(const double* x, uint64_t n, double* out, double* scrat
     sum_kernel<<<grid, kThreads, 0, st>>>(x, n, scratch);
     if (check_launch("alpk_sum")) return 1;
     return finalize_sum(scratch, grid, out, st);
+}
+
+ALPK_EXPORT int alpk_table_sigma(int kind, const double* log10_e, const double* log10_xs, int n_table, const double* energy,
+                                 uint64_t n, double* sigma, void* stream) {
+    if (kind != 0 && kind != 1) { set_error("alpk_table_sigma: kind must be 0 or 1"); return 2; }
+    if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_table_sigma: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
+    if (n == 0) return 0;
+    if (!log10_e || !log10_xs || !energy || !sigma) { set_error("alpk_table_sigma: null argument"); return 2; }
+    table_sigma_kernel<<<grid_for(n, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(kind, log10_e, log10_xs, n_table, energy, n, sigma);
+    return check_launch("alpk_table_sigma");
 }
 
 ALPK_EXPORT int alpk_abs_sigma_mev(const double* log10_e, const double* log10_xs, int n_table, const double* energy,

@@ -304,6 +304,8 @@ ALPK_EXPORT int alpk_decay2body(const double* row_table, uint64_t n_parents, uin
     if (n_samples == 0 || n_samples > 0x7fffffffu - kDTile) { set_error("alpk_decay2body: n_samples out of range"); return 2; }
     const uint64_t n = n_parents * (uint64_t)n_samples;
     if (n == 0) return 0;
+    // the kernel stores pairs of events as 16-byte vectors into every plane (odd n is handled in the kernel: scalar stores)
+    if (((uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)w) & 15u) { set_error("alpk_decay2body: p1, p2, w must be 16-byte aligned"); return 2; }
     DecayArgs a;
     a.table = row_table; a.n_parents = n_parents; a.n_samples = n_samples; a.row_ids = row_ids;
     a.uniforms = uniforms; a.seed = seed; a.p1 = p1; a.p2 = p2; a.w = w;
@@ -320,6 +322,7 @@ ALPK_EXPORT int alpk_decay2body_f32(const double* row_table, uint64_t n_parents,
     if (n_samples == 0) { set_error("alpk_decay2body_f32: n_samples out of range"); return 2; }
     const uint64_t n = n_parents * (uint64_t)n_samples;
     if (n == 0) return 0;
+    if (((uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)w) & 15u) { set_error("alpk_decay2body_f32: p1, p2, w must be 16-byte aligned"); return 2; }
     DecayArgs a;
     a.table = row_table; a.n_parents = n_parents; a.n_samples = n_samples; a.row_ids = row_ids;
     a.uniforms = nullptr; a.seed = seed; a.p1 = nullptr; a.p2 = nullptr; a.w = nullptr;

@@ -299,6 +299,13 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
         return 0;
     }
     if (!row_table) { set_error("%s: null row table", what); return 2; }
+    // pairs of samples are stored as 16-byte (f64) / 8-byte (f32) vectors: reject misaligned outputs here rather than fault
+    // asynchronously in the kernel
+    if ((((uintptr_t)out_energy | (uintptr_t)out_flux | (uintptr_t)decay_w64 | (uintptr_t)scatter_w64 | (uintptr_t)event_w) & 15u) ||
+        (((uintptr_t)decay_w32 | (uintptr_t)scatter_w32) & 7u)) {
+        set_error("%s: per-sample output arrays must be 16-byte aligned (float32 arrays: 8-byte)", what);
+        return 2;
+    }
     ChainArgs<Prod> a;
     memset(&a, 0, sizeof(a));
     a.table = row_table; a.n_rows = n_rows; a.n_samples = n_samples; a.row_ids = row_ids;

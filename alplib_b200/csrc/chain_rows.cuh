@@ -1,5 +1,5 @@
 // Row-aligned variant of the per-sample chain kernel for the production configuration: fast arithmetic, free-running
-// Philox, even n_samples, rows of at least kRowsMinSamples samples, no fused histogram.
+// Philox, even n_samples, rows of at least kRowsMinSamples samples.
 //
 //   Work unit = (row, chunk of the row's sample pairs), owned by ONE WARP: a unit never straddles two rows, so
 //     * the row record is loaded once per unit into registers (warp-uniform __ldg, no shared-memory staging) -- the
@@ -8,19 +8,26 @@
 //     * there is no CTA-level synchronisation in the loop at all: warps drift apart, which spreads their integer
 //       (Philox) and FP64 phases over the sub-partition's issue slots.
 //   Units are handed out dynamically (one atomicAdd per unit, fetched one unit ahead so its latency is hidden), which
-//   removes the tail of a static tile->CTA assignment; the counter is reset by the finalize kernel of the same launch.
+//   removes the tail of a static assignment (measured: 0.508 ms static vs 0.472 ms dynamic on the C2 chain).
+//   The event rate stays deterministic all the same: every unit's sum is formed in a fixed order (lane-local adds in
+//   iteration order, then a fixed shuffle tree) and stored per UNIT; the finalize kernel adds the unit sums in unit order.
+//   Which warp happened to run a unit does not enter the result, nor does the grid size.
 //
 // The per-sample arithmetic is the same inline code as chain_kernel's fast path (Prod::sample_fast, propagate_try_fast,
 // decay_event_weight_coupled), and sample s of a row uses the same Philox counter / words, so both kernels produce the
 // same bits for every per-sample output; only the order of the rate sum differs.
+//
+// The fused-histogram launches stay with chain_kernel: its per-warp bin copies need many resident warps to hide the
+// shuffle latency of the aggregated adds, and this kernel's 16 warps / SM measured slower there (1.24 vs 1.0 ms, 50 bins).
 #pragma once
-#include "chain_kernel.cuh"
 #include <stdlib.h>
+
+#include "chain_kernel.cuh"
 
 namespace alpk {
 
 #ifndef ALPK_ROWS_MIN_BLOCKS
-#define ALPK_ROWS_MIN_BLOCKS 2
+#define ALPK_ROWS_MIN_BLOCKS 2             // 2 x 256 threads / SM: 128 registers per thread (3 blocks / 80 registers: 2 % slower)
 #endif
 #ifndef ALPK_ROWS_THREADS
 #define ALPK_ROWS_THREADS 256
@@ -29,65 +36,66 @@ namespace alpk {
 #define ALPK_ROWS_UNROLL 1
 #endif
 #ifndef ALPK_ROWS_CHUNK_PAIRS
-#define ALPK_ROWS_CHUNK_PAIRS 512          // target pairs per unit (16 warp iterations)
+#define ALPK_ROWS_CHUNK_PAIRS 512          // target pairs per unit (16 warp iterations); 256 / 1024 measured 1-2 % slower
 #endif
 constexpr int kRowsThreads = ALPK_ROWS_THREADS;
 constexpr int kRowsUnroll = ALPK_ROWS_UNROLL;
 constexpr uint32_t kRowsMinSamples = 256;   // shorter rows stay with the tile kernel (units would be mostly lane padding)
+// layout of the caller's scratch (>= ALPK_SCRATCH_DOUBLES doubles): [0, 2 kMaxPartials) block partials of the other kernels,
+// then the dynamic-unit counter, then the per-unit rate sums of this kernel
+constexpr uint64_t kRowsCounterOffset = 2 * kMaxPartials;      // [+0] unit counter (u64), [+1] arrival counter of the finalize kernel
+constexpr uint64_t kRowsUnitSumOffset = 2 * kMaxPartials + 16;
+constexpr uint64_t kRowsMaxUnits = ALPK_SCRATCH_DOUBLES - kRowsUnitSumOffset;
 
 struct RowsGeom {
     uint32_t chunks_per_row;     // units per row
     uint32_t pairs_per_chunk;    // pairs per unit (the last unit of a row may hold fewer)
     uint32_t pairs_per_row;      // n_samples / 2
-    uint32_t n_units_lo, n_units_hi;   // n_rows * chunks_per_row as two words
-    unsigned long long* counter; // dynamic unit counter (zero on entry; the finalize kernel re-zeroes it)
+    uint32_t n_units;            // n_rows * chunks_per_row (<= kRowsMaxUnits)
+    unsigned long long* counter; // dynamic unit counter (zeroed by the launcher), or NULL: static assignment
+    double* unit_sums;           // [n_units] rate sum of every unit (STAGE 2)
 };
 
-template <class Prod, int STAGE, int OUT, bool SHORT>
+template <class Prod, int STAGE, int OUT, bool SHORT, int ROUNDS>
 __global__ void __launch_bounds__(kRowsThreads, ALPK_ROWS_MIN_BLOCKS)
 chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
     using namespace alp;
     constexpr int NP = Prod::NP;
     __shared__ double s_tab[alp::kExpTabSize];
-    __shared__ double red[32];
     for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = kExpTabDev[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t n_units = ((uint64_t)geo.n_units_hi << 32) | geo.n_units_lo;
-    const uint64_t n_warps = (uint64_t)gridDim.x * (kRowsThreads / 32);
-    double acc = 0.0;
+    const uint32_t n_units = geo.n_units;
+    const uint32_t n_warps = gridDim.x * (kRowsThreads / 32);
 
-    uint64_t unit = (uint64_t)blockIdx.x * (kRowsThreads / 32) + (threadIdx.x >> 5);
+    uint32_t unit = blockIdx.x * (kRowsThreads / 32) + (threadIdx.x >> 5);
     // the first n_warps units are assigned statically; with a counter the further ones are handed out dynamically,
     // fetched one unit ahead so that the atomic's latency is hidden behind the current unit
     const bool dynamic = geo.counter != nullptr;
-    uint64_t next = unit + n_warps;
+    uint64_t next = (uint64_t)unit + n_warps;
     if (dynamic) {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(geo.counter, 1ull);
         next = n_warps + __shfl_sync(0xffffffffu, t, 0);
     }
-    const bool small = geo.n_units_hi == 0u;
     while (unit < n_units) {
         unsigned long long fetched = 0;
         if (dynamic && lane == 0 && next < n_units) fetched = atomicAdd(geo.counter, 1ull);
-        uint64_t r;
-        uint32_t c;
-        if (small) { const uint32_t r32 = (uint32_t)unit / geo.chunks_per_row; r = r32; c = (uint32_t)unit - r32 * geo.chunks_per_row; }
-        else { r = unit / geo.chunks_per_row; c = (uint32_t)(unit - r * geo.chunks_per_row); }
+        const uint32_t r = unit / geo.chunks_per_row;
+        const uint32_t c = unit - r * geo.chunks_per_row;
         const uint32_t p_begin = c * geo.pairs_per_chunk;
         const uint32_t p_stop = min(p_begin + geo.pairs_per_chunk, geo.pairs_per_row);
         double row[NP];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) row[k] = __ldg(a.table + r * NP + k);
-        const uint32_t rid = a.row_ids ? __ldg(a.row_ids + r) : (uint32_t)r;
-        const uint64_t base = r * (uint64_t)a.n_samples;
+        for (int k = 0; k < NP; ++k) row[k] = __ldg(a.table + (uint64_t)r * NP + k);
+        const uint32_t rid = a.row_ids ? __ldg(a.row_ids + r) : r;
+        const uint64_t base = (uint64_t)r * a.n_samples;
+        double acc = 0.0;
 
 #pragma unroll kRowsUnroll
         for (uint32_t p = p_begin + lane; p < p_stop; p += 32u) {
             // sample s: counter s>>1 = pair index, words (x,y) / (z,w)
-            const Philox4 q = a.rounds == 7 ? philox4x32_rk<7>(p, 0u, rid, Prod::kTag, a.rk)
-                                            : philox4x32_rk<10>(p, 0u, rid, Prod::kTag, a.rk);
+            const Philox4 q = philox4x32_rk<ROUNDS>(p, 0u, rid, Prod::kTag, a.rk);
             double u[2], e[2], f[2], d64v[2], s64v[2], evv[2];
             float d32v[2], s32v[2];
             u[0] = u53(q.x, q.y);
@@ -131,29 +139,61 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
                     *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
             }
         }
-        unit = next;
+        if (STAGE >= 2) {                            // the unit's rate sum: fixed order whichever warp ran the unit
+            acc = warp_sum(acc);
+            if (lane == 0) geo.unit_sums[unit] = acc;
+        }
+        const uint64_t cur_next = next;
         // (a warp that did not fetch -- next was already past the end -- ends with unit >= n_units)
-        next = dynamic ? (next < n_units ? n_warps + __shfl_sync(0xffffffffu, fetched, 0) : next) : next + n_warps;
-    }
-    if (STAGE >= 2) {
-        acc = block_sum(acc, red);
-        if (threadIdx.x == 0) a.partials[blockIdx.x] = acc;
+        next = dynamic ? (cur_next < n_units ? n_warps + __shfl_sync(0xffffffffu, fetched, 0) : cur_next) : cur_next + n_warps;
+        unit = cur_next < n_units ? (uint32_t)cur_next : n_units;
     }
 }
 
-// Geometry of the units for a given row length.
-inline RowsGeom rows_geometry(uint64_t n_rows, uint32_t n_samples, unsigned long long* counter) {
+// Fixed-order sum of the unit sums: CTA b adds its contiguous block of units (thread-strided, then the block tree), the last
+// CTA to finish adds the block sums in block order.  One launch; the result depends only on (n, grid, block size).
+static __global__ void __launch_bounds__(256)
+finalize_units_kernel(const double* __restrict__ sums, uint32_t n, double* __restrict__ partials, unsigned int* done,
+                      double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ bool s_last;
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per, hi = min(lo + per, n);
+    double v = 0.0;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) v += sums[i];
+    v = block_sum(v, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = v;
+        __threadfence();
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double t = 0.0;
+        for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += reinterpret_cast<const volatile double*>(partials)[i];
+        t = block_sum(t, red);
+        if (threadIdx.x == 0) { *out = t; *done = 0u; }
+    }
+}
+
+// Geometry of the units for a given row length: equal-sized units of whole warp iterations, at most kRowsMaxUnits of them.
+inline RowsGeom rows_geometry(uint64_t n_rows, uint32_t n_samples, double* scratch, bool dynamic) {
     RowsGeom g;
     g.pairs_per_row = n_samples / 2u;
-    g.chunks_per_row = (g.pairs_per_row + ALPK_ROWS_CHUNK_PAIRS - 1) / ALPK_ROWS_CHUNK_PAIRS;
-    // equal-sized units, rounded up to whole warp iterations
-    uint32_t ppc = (g.pairs_per_row + g.chunks_per_row - 1) / g.chunks_per_row;
-    ppc = (ppc + 31u) & ~31u;
-    g.pairs_per_chunk = ppc;
-    g.chunks_per_row = (g.pairs_per_row + ppc - 1) / ppc;
-    const uint64_t n_units = n_rows * (uint64_t)g.chunks_per_row;
-    g.n_units_lo = (uint32_t)n_units; g.n_units_hi = (uint32_t)(n_units >> 32);
-    g.counter = counter;
+    uint64_t target = ALPK_ROWS_CHUNK_PAIRS;
+    for (;;) {
+        g.chunks_per_row = (uint32_t)((g.pairs_per_row + target - 1) / target);
+        uint32_t ppc = (g.pairs_per_row + g.chunks_per_row - 1) / g.chunks_per_row;
+        ppc = (ppc + 31u) & ~31u;
+        g.pairs_per_chunk = ppc;
+        g.chunks_per_row = (g.pairs_per_row + ppc - 1) / ppc;
+        if (n_rows * (uint64_t)g.chunks_per_row <= kRowsMaxUnits || g.chunks_per_row == 1) break;
+        target *= 2;                                 // very many rows: larger units so the unit sums fit the scratch
+    }
+    g.n_units = (uint32_t)(n_rows * (uint64_t)g.chunks_per_row);
+    g.counter = (dynamic && scratch) ? reinterpret_cast<unsigned long long*>(scratch + kRowsCounterOffset) : nullptr;
+    g.unit_sums = scratch ? scratch + kRowsUnitSumOffset : nullptr;
     return g;
 }
 
@@ -169,20 +209,18 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
                       double* rate, double* scratch, cudaStream_t st) {
     const int mode = chain_rows_mode();
     if (!mode || a.n_samples < kRowsMinSamples) return -1;
-    unsigned long long* counter = nullptr;
-    if (mode != 2 && scratch) {                 // (mode 2: static unit assignment, for A/B timing)
-        counter = reinterpret_cast<unsigned long long*>(scratch + 2 * kMaxPartials);
-        cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
-    }
-    const RowsGeom geo = rows_geometry(a.n_rows, a.n_samples, counter);
-    const uint64_t n_units = ((uint64_t)geo.n_units_hi << 32) | geo.n_units_lo;
-    uint64_t blocks = (n_units + (kRowsThreads / 32) - 1) / (kRowsThreads / 32);
+    const RowsGeom geo = rows_geometry(a.n_rows, a.n_samples, scratch, mode != 2);
+    if ((uint64_t)a.n_rows * geo.chunks_per_row > kRowsMaxUnits) return -1;          // (more rows than unit slots: tile kernel)
+    // (the unit counter and the finalize kernel's arrival counter sit next to each other: one 16-byte memset)
+    if (scratch) cudaMemsetAsync(scratch + kRowsCounterOffset, 0, 16, st);
+    uint64_t blocks = ((uint64_t)geo.n_units + (kRowsThreads / 32) - 1) / (kRowsThreads / 32);
     const uint64_t cap = (uint64_t)sm_count() * ALPK_ROWS_MIN_BLOCKS;
     if (blocks > cap) blocks = cap;
     const int grid = (int)blocks;
     const bool sh = stage >= 1 && a.prop.short_lived;
-#define ALPK_ROWS_LAUNCH(S, O) { if (sh) chain_rows_kernel<Prod, S, O, true><<<grid, kRowsThreads, 0, st>>>(a, geo); \
-                                 else chain_rows_kernel<Prod, S, O, false><<<grid, kRowsThreads, 0, st>>>(a, geo); }
+#define ALPK_ROWS_LAUNCH_R(S, O, R) { if (sh) chain_rows_kernel<Prod, S, O, true, R><<<grid, kRowsThreads, 0, st>>>(a, geo); \
+                                      else chain_rows_kernel<Prod, S, O, false, R><<<grid, kRowsThreads, 0, st>>>(a, geo); }
+#define ALPK_ROWS_LAUNCH(S, O) { if (a.rounds == 7) ALPK_ROWS_LAUNCH_R(S, O, 7) else ALPK_ROWS_LAUNCH_R(S, O, 10) }
 #define ALPK_ROWS_CASE(S)                                                  \
     if (standard) ALPK_ROWS_LAUNCH(S, kOutStandard)                        \
     else if (S == 2 && noevents) ALPK_ROWS_LAUNCH(S, kOutNoEvents)         \
@@ -190,9 +228,16 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
     else ALPK_ROWS_LAUNCH(S, kOutGeneric)
     if (stage == 0) { ALPK_ROWS_CASE(0) } else if (stage == 1) { ALPK_ROWS_CASE(1) } else { ALPK_ROWS_CASE(2) }
 #undef ALPK_ROWS_LAUNCH
+#undef ALPK_ROWS_LAUNCH_R
 #undef ALPK_ROWS_CASE
     if (check_launch(what)) return 1;
-    if (stage == 2) return finalize_sum(scratch, grid, rate, st);
+    if (stage == 2) {
+        if (geo.n_units <= (uint32_t)kMaxPartials) return finalize_sum(geo.unit_sums, (int)geo.n_units, rate, st);
+        const int fgrid = (int)min((uint64_t)sm_count(), ((uint64_t)geo.n_units + 511) / 512);
+        finalize_units_kernel<<<fgrid, 256, 0, st>>>(geo.unit_sums, geo.n_units, scratch,
+                                                     reinterpret_cast<unsigned int*>(scratch + kRowsCounterOffset + 1), rate);
+        return check_launch("finalize_units");
+    }
     return 0;
 }
 

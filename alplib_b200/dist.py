@@ -61,11 +61,23 @@ def world(group=None):
     return 0, 1
 
 
+def _host_staged(t, group):
+    """gloo moves host memory: with that backend (CPU tests, or more ranks than GPUs) CUDA tensors are staged through the
+    host; NCCL takes the device tensor as it is."""
+    import torch.distributed as dist
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
 def all_reduce_sum(t, group=None):
     """In-place sum over ranks (no-op in a single process)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, group=group)
+        if _host_staged(t, group):
+            h = t.cpu()
+            dist.all_reduce(h, group=group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, group=group)
     return t
 
 
@@ -91,6 +103,8 @@ def gather_row_blocks(local, counts, group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return [local]
+    if _host_staged(local, group):
+        return [b.to(local.device) for b in gather_row_blocks(local.cpu(), counts, group)]
     tail = tuple(local.shape[1:])
     outs = [torch.empty((int(c),) + tail, dtype=local.dtype, device=local.device) for c in counts]
     if len(set(int(c) for c in counts)) == 1:

@@ -71,10 +71,24 @@ class AbsCrossSection:
         return r if np.ndim(E) else np.float64(r[0])
 
     def sigma_cm2(self, E):
-        return self.sigma_mev(E) * MEV2_CM2
+        """10**interp(log10 E, log10 E_i, log10(xs_dim*sigma_i), 0, 0) (photon_xs.py:45-46) -- its own lookup, not
+        sigma_mev*MEV2_CM2 (a divide and a multiply would move the last bit)."""
+        rt = Runtime.get()
+        le, lx, nt = self.device_table(rt)
+        return _table_sigma(rt, 0, le, lx, nt, E)
 
     def mu(self, E, n):
         return self.sigma_cm2(E) * n
+
+
+def _table_sigma(rt, kind, le, lx, nt, E):
+    e = np.atleast_1d(np.asarray(E, dtype=np.float64))
+    with rt.activate():
+        d_e = rt.upload(e.ravel())
+        out = rt.empty(e.size)
+        N.call("alpk_table_sigma", kind, N.ptr(le), N.ptr(lx), nt, N.ptr(d_e), e.size, N.ptr(out), rt.stream())
+    r = rt.to_host(out).reshape(e.shape)
+    return r if np.ndim(E) else np.float64(r[0])
 
 
 class ALPPairProdutionCrossSection:
@@ -93,10 +107,29 @@ class ALPPairProdutionCrossSection:
         self.xs_data = _load_table(data_path("alp_pair_production", "pair_production_xs_table_" + mass_extension[idx_closest] + ".txt"), 0)
         self.log10_e = np.log10(self.xs_data[:, 0])
         self.log10_xs_mev = np.log10(self.argon_rescale * self.xs_dim * self.xs_data[:, 1] / MEV2_CM2)
+        self.log10_xs_cm2 = np.log10(self.argon_rescale * self.xs_dim * self.xs_data[:, 1])
         self._dev = {}
+        self._dev_cm2 = {}
 
     def device_table(self, rt: Runtime):
         t = self._dev.get(rt.index)
         if t is None:
             t = self._dev[rt.index] = (rt.upload(self.log10_e), rt.upload(self.log10_xs_mev), int(self.log10_e.shape[0]))
         return t
+
+    def sigma_cm2(self, E):
+        """heaviside(E-2me,0)*10**interp(log10 E; log10(argon_rescale*xs_dim*sigma_i), left=-inf) (photon_xs.py:117-120)."""
+        rt = Runtime.get()
+        t = self._dev_cm2.get(rt.index)
+        if t is None:
+            t = self._dev_cm2[rt.index] = (rt.upload(self.log10_e), rt.upload(self.log10_xs_cm2), int(self.log10_e.shape[0]))
+        return _table_sigma(rt, 1, t[0], t[1], t[2], E)
+
+    def sigma_mev(self, E):
+        """The same in MeV^-2 (photon_xs.py:122-125): the lookup pair_production() evaluates per sample."""
+        rt = Runtime.get()
+        le, lx, nt = self.device_table(rt)
+        return _table_sigma(rt, 1, le, lx, nt, E)
+
+    def mu(self, E, n):  # atomic number density in cm^-3
+        return self.sigma_cm2(E) * n

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import config
 
 
 _NULL_CTX = contextlib.nullcontext()
@@ -18,6 +19,42 @@ _TORCH_DTYPE = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch
 
 _NP_DTYPE = {torch.float64: np.float64, torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64,
              torch.uint8: np.uint8}
+
+
+_COPY_THREADS = 4
+_copy_pool = None
+
+
+def _parallel_copy(dst, src):
+    """dst[:] = src for large byte arrays on a few host threads (NumPy releases the GIL in the copy loop): one thread cannot
+    keep up with a PCIe 5 x16 device -> host stream."""
+    global _copy_pool, _COPY_THREADS
+    n = dst.shape[0]
+    if n < (8 << 20) or _COPY_THREADS == 1:
+        dst[:] = src
+        return
+    if _copy_pool is None:
+        # calibrate once on this chunk: some hosts (small VMs) copy faster on one thread
+        import time
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(_COPY_THREADS)
+        dst[:] = src                                            # (touches the destination pages)
+        t0 = time.perf_counter(); dst[:] = src; t1 = time.perf_counter() - t0
+        st = (n + _COPY_THREADS - 1) // _COPY_THREADS
+        t0 = time.perf_counter()
+        for f in [pool.submit(np.copyto, dst[i:i + st], src[i:i + st]) for i in range(0, n, st)]:
+            f.result()
+        tn = time.perf_counter() - t0
+        if tn > 0.9 * t1:
+            _COPY_THREADS = 1
+            pool.shutdown()
+            return
+        _copy_pool = pool
+        return
+    step = (n + _COPY_THREADS - 1) // _COPY_THREADS
+    futs = [_copy_pool.submit(np.copyto, dst[i:i + step], src[i:i + step]) for i in range(0, n, step)]
+    for f in futs:
+        f.result()
 
 
 class Runtime:
@@ -36,7 +73,7 @@ class Runtime:
         self.cc = (maj.value, mnr.value)
         if maj.value != 10:
             raise N.AlpkError(f"libalpk.so is built for sm_100a only; device {index} ({self.name}) is sm_{maj.value}{mnr.value}")
-        self.scratch = torch.empty(N.SCRATCH_DOUBLES, dtype=torch.float64, device=self.device)
+        self._scratch = {}          # CUDA stream handle -> reduction scratch (launches sharing a scratch must be stream-ordered)
 
     @classmethod
     def get(cls, device=None):
@@ -55,6 +92,16 @@ class Runtime:
         return rt
 
     # ---- plumbing ---------------------------------------------------------------------------------------------
+    @property
+    def scratch(self):
+        """Reduction scratch (ALPK_SCRATCH_DOUBLES doubles) of the CURRENT stream: the two-stage reductions write partial
+        sums there, so flux objects driven from different streams must not share one."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        s = self._scratch.get(key)
+        if s is None:
+            s = self._scratch[key] = torch.empty(N.SCRATCH_DOUBLES, dtype=torch.float64, device=self.device)
+        return s
+
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -122,6 +169,9 @@ class Runtime:
     def to_host(self, tensor, out=None):
         """Device tensor -> NumPy array through pinned memory.
 
+        Large arrays (> 4 MiB) are by default returned AS pinned memory (config.PINNED_RESULTS, see below); with that off, or
+        when an `out` array is given:
+
         Small results (rates, maps, histograms) take one cudaMemcpyAsync into a pinned slot.  Large per-sample arrays are
         copied in chunks of D2H_CHUNK through TWO pinned buffers: while chunk k is copied from the pinned buffer into the
         destination array by the host, chunk k+1 is already in flight on the copy stream -- a pageable `tensor.cpu()`
@@ -142,6 +192,21 @@ class Runtime:
             ev.synchronize()
             flat_host[:] = hnp[:nbytes]
             return res
+        if out is None and config.PINNED_RESULTS:
+            # large result: the NumPy array IS pinned memory (a view of a pinned torch tensor served by torch's caching host
+            # allocator), filled by ONE cudaMemcpyAsync at the full PCIe rate -- no second, host-side copy and no page faults
+            # on a fresh pageable array.  The first request of a size pays cudaHostAlloc; when the array is garbage-collected
+            # its block goes back to the allocator's cache, so loops that re-read arrays of the same size run at DMA speed.
+            try:
+                dst = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+            except RuntimeError:
+                dst = None                                   # (not enough lockable memory: chunked path below)
+            if dst is not None:
+                dst.copy_(t, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                ev.synchronize()
+                return dst.numpy()
         bufs = self._d2h_buffers()
         copy_stream = self.__dict__.setdefault("_d2h_stream", torch.cuda.Stream(self.device))
         copy_stream.wait_stream(cur)                         # the producer kernels have been queued on the current stream
@@ -156,7 +221,7 @@ class Runtime:
                 hb, ev, hnp = bufs[k & 1]
                 lo, hi = k * chunk, min((k + 1) * chunk, nbytes)
                 ev.synchronize()
-                flat_host[lo:hi] = hnp[:hi - lo]
+                _parallel_copy(flat_host[lo:hi], hnp[:hi - lo])
                 nk = k + 2
                 if nk < n_chunks:                               # refill this buffer with chunk k+2 while k+1 is consumed
                     lo2, hi2 = nk * chunk, min((nk + 1) * chunk, nbytes)

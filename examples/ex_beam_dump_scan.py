@@ -20,22 +20,33 @@ photons = np.stack([e, 1e16 * e ** -1.5 * np.exp(-e / 150)], axis=1)          # 
 ma_grid, g_grid = np.logspace(-2, 2, 200), np.logspace(-9, -3, 200)
 kw = dict(det_dist=4.0, det_length=0.2, det_area=0.04, days_exposure=100, threshold=5.0, seed=1)
 
-if __name__ == "__main__":
-    import os
-    if "RANK" in os.environ:
+def main():
+    """Returns (compton map, primakoff map, {name: (masses, limits)}); under torchrun every rank gets the full maps."""
+    distributed = "RANK" in os.environ
+    if distributed:
         import torch
-        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-        dist.init_process_group("nccl")
+        world, local = int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+        n_dev = torch.cuda.device_count()
+        torch.cuda.set_device(local % n_dev)
+        # one GPU per rank -> NCCL over NVLink; fewer GPUs than ranks (a 1-GPU test box) -> the ranks share devices and the
+        # small merge goes through gloo
+        dist.init_process_group("nccl" if n_dev >= world else "gloo")
         run = scan_rates_distributed
     else:
         run = scan_rates
     compton = run("compton", photons, Material("W"), ma_grid, g_grid, n_samples=100, **kw)
     primakoff = run("primakoff", photons, Material("W"), ma_grid, g_grid, **kw)
-    if not dist.is_initialized() or dist.get_rank() == 0:
-        for name, rates in (("electron coupling (Compton)", compton), ("photon coupling (Primakoff)", primakoff)):
-            lo, hi = limits_from_rate_map(g_grid, rates, stop_value=2.71)
-            ok = ~np.isnan(lo)
-            m, lim = cleanLimitData(ma_grid[ok], lo[ok], hi[ok])
+    limits = {}
+    for name, rates in (("electron coupling (Compton)", compton), ("photon coupling (Primakoff)", primakoff)):
+        lo, hi = limits_from_rate_map(g_grid, rates, stop_value=2.71)
+        ok = ~np.isnan(lo)
+        limits[name] = cleanLimitData(ma_grid[ok], lo[ok], hi[ok])
+        if not distributed or dist.get_rank() == 0:
             print(f"{name}: {ok.sum()} masses excluded; at ma = {ma_grid[ok][0]:.3g} MeV: {lo[ok][0]:.3g} < g < {hi[ok][0]:.3g}")
-    if dist.is_initialized():
+    if distributed:
         dist.destroy_process_group()
+    return compton, primakoff, limits
+
+
+if __name__ == "__main__":
+    main()

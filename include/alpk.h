@@ -11,7 +11,10 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it; nothing synchronises;
  *   - return value 0 = OK, non-zero = error, text from alpk_last_error() (thread local);
  *   - nothing is allocated or freed across the boundary; `scratch` arguments are caller-owned device buffers of
- *     at least ALPK_SCRATCH_DOUBLES doubles used for the deterministic two-stage reductions;
+ *     at least ALPK_SCRATCH_DOUBLES doubles (8 MiB) used for the deterministic two-stage reductions (block / unit partial
+ *     sums, then a fixed-order finalize) -- one scratch per stream: launches that share a scratch must be stream-ordered;
+ *   - per-sample output arrays must be 16-byte aligned (8-byte for the float32 arrays): the kernels store pairs of samples
+ *     as vectors; a misaligned pointer is rejected with rc 2 (alpk_propagate alone falls back to scalar stores);
  *   - all arithmetic is IEEE FP64 in the reference's operation order (library built with -fmad=false), weights
  *     are rounded to float32 exactly where the reference rounds them;
  *   - `uniforms` arguments: NULL = free-running Philox4x32-10 keyed by (seed, stream tag, row id, sample);
@@ -27,7 +30,7 @@ extern "C" {
 #endif
 
 #define ALPK_VERSION 1
-#define ALPK_SCRATCH_DOUBLES 16384
+#define ALPK_SCRATCH_DOUBLES 1048576
 
 /* number of doubles per row of the per-row parameter tables */
 #define ALPK_COMPTON_NP 12
@@ -117,6 +120,12 @@ int alpk_scatter_events(int kind, const double* energy, const float* scatter_w32
 int alpk_pair_events(const double* energy, const float* scatter_w32, uint64_t n, const double* log10_e,
                      const double* log10_xs, int n_table, double lead, double mbm2, const alpk_event_t* h_ev,
                      double* event_w_or_null, double* rate, double* scratch, void* stream);
+
+/* ---- tabulated cross sections as functions of E (photon_xs.py:45-52 AbsCrossSection.sigma_cm2 / mu; :117-128
+ * ALPPairProdutionCrossSection.sigma_cm2 / sigma_mev / mu): log-log interpolation of a table whose unit factor the caller
+ * folded into log10_xs.  kind 0: 10**interp(left = 0, right = 0); kind 1: heaviside(E-2me,0)*10**interp(left = -inf). */
+int alpk_table_sigma(int kind, const double* log10_e, const double* log10_xs, int n_table, const double* energy, uint64_t n,
+                     double* sigma, void* stream);
 
 /* ---- photon absorption table: photon_xs.py:48-49 (AbsCrossSection.sigma_mev) --------------------------------- */
 int alpk_abs_sigma_mev(const double* log10_e, const double* log10_xs, int n_table, const double* energy, uint64_t n,

@@ -714,6 +714,22 @@ def case_scatter2to2():
     save("scatter2to2", n_cases=kk, **out)
 
 
+def case_xs_methods():
+    """Public methods of the tabulated cross-section classes (photon_xs.py:45-52, 117-128)."""
+    print("cross-section class methods")
+    import alplib.photon_xs as PXS
+    e = np.array([0.0009, 0.0015, 0.9, 1.021, 1.03, 5.0, 100.0, 9.9e4, 2e5])
+    out = {"energy": e}
+    for mat in ("W", "Ar", "NaI"):
+        a = PXS.AbsCrossSection(F.Material(mat))
+        out[f"abs_{mat}_cm2"] = a.sigma_cm2(e); out[f"abs_{mat}_mev"] = a.sigma_mev(e); out[f"abs_{mat}_mu"] = a.mu(e, 6.3e22)
+    for tag, mat, ma in (("ar01", "Ar", 0.1), ("ar095", "Ar", 0.95), ("ge2", "Ge", 2.0)):
+        with np.errstate(all="ignore"):
+            x = PXS.ALPPairProdutionCrossSection(F.Material(mat), ma=ma)
+            out[f"pair_{tag}_cm2"] = x.sigma_cm2(e); out[f"pair_{tag}_mev"] = x.sigma_mev(e); out[f"pair_{tag}_mu"] = x.mu(e, 2.1e22)
+    save("xs_methods", **out)
+
+
 def _fit_cases():
     """Fixed inputs of the limit-helper fixture; shared with tests/test_fit_cpu.py through fit.json (inputs are stored too)."""
     grid = np.logspace(-8, -3, 700)
@@ -800,5 +816,6 @@ if __name__ == "__main__":
     case_meson3body()
     case_meson_mixing()
     case_scatter2to2()
+    case_xs_methods()
     case_fit()
     print("all golden fixtures written; oracle pinned against the reference")

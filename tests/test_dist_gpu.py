@@ -53,10 +53,7 @@ def _run_rank(rank, world, port, backend, outdir):
         prim.simulate(); prim.propagate()
         rate_p = A.PhotonEventGenerator(prim, Ar).decays_device(100, 5.0)
         hist = comp.last_hist
-        if backend == "gloo":
-            rates, hists = D.merged_rates_and_hists([rate_c.cpu(), rate_p.cpu()], [hist.cpu()])
-        else:
-            rates, hists = D.merged_rates_and_hists([rate_c, rate_p], [hist])
+        rates, hists = D.merged_rates_and_hists([rate_c, rate_p], [hist])     # (gloo: staged through the host by dist.py)
         np.savez(os.path.join(outdir, f"rank{rank}.npz"), E=comp.axion_energy, F=comp.axion_flux, D=comp.decay_axion_weight,
                  S=comp.scatter_axion_weight, evw=evw.cpu().numpy(), rates=rates.cpu().numpy(), hist=hists[0].cpu().numpy(),
                  pE=prim.axion_energy, pD=prim.decay_axion_weight, n_rows=comp._rows[1], row_offset=comp.row_offset)
@@ -103,3 +100,39 @@ def test_sharded_single_job_equals_one_rank(tmp_path):
         assert np.allclose(p["hist"], hist1, rtol=1e-12, atol=0.0)
     assert np.array_equal(parts[0]["rates"], parts[1]["rates"]) and np.array_equal(parts[0]["hist"], parts[1]["hist"])
     assert hist1.sum() == pytest.approx(float(rate1.item()), rel=1e-9)          # edges span every E_a above threshold
+
+
+def _run_example_rank(rank, world, port, outdir):
+    import runpy
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ns = runpy.run_path(os.path.join(root, "examples", "ex_beam_dump_scan.py"), run_name="scan_example")
+    compton, primakoff, limits = ns["main"]()
+    np.savez(os.path.join(outdir, f"scan{rank}.npz"), compton=compton, primakoff=primakoff)
+
+
+@pytest.mark.timeout(300)
+def test_scan_example_distributed_equals_single_process(tmp_path):
+    """examples/ex_beam_dump_scan.py: its torchrun branch under 2 ranks (masses dealt round-robin, one all-gather per map) gives
+    the maps of the single-process run bit for bit, and the limit helpers run on them."""
+    import runpy
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_run_example_rank, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=280)
+        assert p.exitcode == 0
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        os.environ.pop(k, None)
+    ns = runpy.run_path(os.path.join(root, "examples", "ex_beam_dump_scan.py"), run_name="scan_example")
+    compton, primakoff, limits = ns["main"]()
+    assert compton.shape == (200, 200) and np.count_nonzero(compton) > 1000 and np.count_nonzero(primakoff) > 1000
+    for r in range(2):
+        z = np.load(os.path.join(str(tmp_path), f"scan{r}.npz"))
+        assert np.array_equal(z["compton"], compton) and np.array_equal(z["primakoff"], primakoff)
+    m, lim = limits["photon coupling (Primakoff)"]
+    assert m.shape == lim.shape and m.shape[0] > 10 and m[0] == 0.0

@@ -46,6 +46,22 @@ def test_abs_sigma(A, mat):
     assert float(xs.sigma_mev(2e5)) == pytest.approx(2.5680599121454694e+21, rel=1e-12)   # out-of-range quirk kept
 
 
+def test_cross_section_class_methods(A):
+    """sigma_cm2 / sigma_mev / mu of AbsCrossSection and ALPPairProdutionCrossSection against the reference (photon_xs.py)."""
+    g = load_golden("xs_methods")
+    e = g["energy"]
+    for mat in ("W", "Ar", "NaI"):
+        a = A.AbsCrossSection(A.Material(mat))
+        assert max_rel(a.sigma_cm2(e), g[f"abs_{mat}_cm2"]) < 1e-12 and max_rel(a.sigma_mev(e), g[f"abs_{mat}_mev"]) < 1e-12
+        assert max_rel(a.mu(e, 6.3e22), g[f"abs_{mat}_mu"]) < 1e-12
+        assert float(a.sigma_cm2(5.0)) == pytest.approx(float(g[f"abs_{mat}_cm2"][5]), rel=1e-12)
+    for tag, mat, ma in (("ar01", "Ar", 0.1), ("ar095", "Ar", 0.95), ("ge2", "Ge", 2.0)):
+        x = A.ALPPairProdutionCrossSection(A.Material(mat), ma=ma)
+        assert max_rel(x.sigma_cm2(e), g[f"pair_{tag}_cm2"]) < 1e-12 and max_rel(x.sigma_mev(e), g[f"pair_{tag}_mev"]) < 1e-12
+        assert max_rel(x.mu(e, 2.1e22), g[f"pair_{tag}_mu"]) < 1e-12
+        assert x.sigma_mev(0.9) == 0.0                        # below 2 m_e
+
+
 def test_c1_readme_example(A):
     """BASELINE config 1: README Primakoff example end to end."""
     g = load_golden("c1_primakoff")
@@ -205,9 +221,11 @@ def test_compton_fused_equals_unfused(A):
 @pytest.mark.parametrize("ns,n_bins", [(256, 40), (1000, 300), (10000, 37), (4098, 11)])
 def test_row_kernel_equals_tile_kernel(A, ns, n_bins, monkeypatch):
     """The row-aligned warp-unit kernel (chain_rows.cuh, dynamic and static unit assignment) and the tile kernel
-    (chain_kernel.cuh) give the same bits for every per-sample output and the same rate to summation order."""
+    (chain_kernel.cuh) give the same bits for every per-sample output, the same rate to summation order, and -- unit sums
+    being added in unit order -- the row kernel's rate does not depend on how the units were scheduled."""
     pf = _c2_flux(n_bins)
     kw = dict(axion_mass=1.5, axion_coupling=1e-7, n_samples=ns, seed=4242, **GEOM)
+    edges = np.logspace(np.log10(1.5), 3, 33)
     res = {}
     for mode in ("0", "1", "2"):
         monkeypatch.setenv("ALPK_CHAIN_ROWS", mode)
@@ -216,18 +234,24 @@ def test_row_kernel_equals_tile_kernel(A, ns, n_bins, monkeypatch):
         fl.simulate()
         rate, evw = fl.chain(100, 5.0, new_coupling=3e-7, materialize=True)
         rate_ro, _ = fl.chain(100, 5.0, new_coupling=3e-7, materialize=False)
+        rate_h, _ = fl.chain(100, 5.0, new_coupling=3e-7, materialize=False, hist_edges=edges)
+        hist = fl.last_hist.cpu().numpy()
         prod = A.FluxComptonIsotropic(pf, A.Material("W"), fused=False, **kw)      # production-only and production+propagate launches
         prod.row_offset = 17
         prod.simulate()
         res[mode] = (fl.axion_energy.copy(), fl.axion_flux.copy(), fl.decay_axion_weight.copy(), fl.scatter_axion_weight.copy(),
-                     evw.cpu().numpy(), float(rate.item()), float(rate_ro.item()), prod.axion_flux.copy())
+                     evw.cpu().numpy(), float(rate.item()), float(rate_ro.item()), prod.axion_flux.copy(), float(rate_h.item()), hist)
     ref = res["0"]
     assert ref[0].shape[0] > 0
     for mode in ("1", "2"):
         for k in (0, 1, 2, 3, 4, 7):
             assert np.array_equal(res[mode][k], ref[k]), (mode, k)
-        assert res[mode][5] == pytest.approx(ref[5], rel=1e-12) and res[mode][6] == pytest.approx(ref[5], rel=1e-12)
-    assert res["1"][5] == res["1"][6]            # materialising and reduce-only launches sum in the same order
+        assert res[mode][5] == pytest.approx(ref[5], rel=1e-12)
+        assert np.allclose(res[mode][9], ref[9], rtol=1e-11, atol=0.0) and res[mode][9].sum() == pytest.approx(ref[5], rel=1e-9)
+        # materialising and reduce-only launches sum the same unit sums in the same order (the histogram launch runs on the
+        # tile kernel: same rate to summation order)
+        assert res[mode][5] == res[mode][6] and res[mode][8] == pytest.approx(ref[5], rel=1e-12)
+    assert res["1"][5] == res["2"][5]            # dynamic vs static unit assignment: identical rate, bit for bit
 
 
 def test_compton_rates_statistical(A):

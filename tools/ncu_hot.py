@@ -47,6 +47,42 @@ def main():
     print("ops: " + ", ".join(f"{k} {v:.1f}" for k, v in ops.most_common(40)))
     ts = sum(st.values())
     print("stall samples on the hot path: " + ", ".join(f"{k[6:]} {100.0 * v / ts:.1f}%" for k, v in st.most_common(12)))
+    if "--json" in sys.argv:
+        # the per-kernel evidence file bench.py reads (profiles/chain_metrics_r2.json)
+        import json
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rr = list(csv.reader(io.StringIO(raw)))
+        hd, row = rr[0], rr[2 + idx]
+        g = lambda k: row[hd.index(k)] if k in hd else None          # noqa: E731
+        fl = lambda k: float(g(k)) if g(k) not in (None, "", "n/a") else None   # noqa: E731
+        unit = lambda k: rr[1][hd.index(k)] if k in hd else ""       # noqa: E731
+
+        def to_bytes(k):
+            v = fl(k)
+            if v is None:
+                return None
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit(k), 1.0)
+        stl = sorted(((float(row[i]), k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")])
+                      for i, k in enumerate(hd) if k.startswith("smsp__average_warps_issue_stalled_")
+                      and k.endswith("_per_issue_active.ratio") and row[i] not in ("", "n/a")), reverse=True)
+        dur = fl("gpu__time_duration.sum")
+        out = {"report": rep, "kernel": g("Kernel Name"), "instr_per_pair": round(n, 2), "fp64_instr_per_pair": round(fp64, 2),
+               "imad_wide_per_pair": round(ops.get("IMAD.WIDE", 0), 2), "mufu_per_pair": round(ops.get("MUFU", 0), 2),
+               "issue_cost_cycles_per_pair": round(cost, 1), "ops_per_pair": {k: round(v, 2) for k, v in ops.most_common()},
+               "executed_warp_instructions": tot,
+               "fp64_pipe_pct": fl("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+               "alu_pipe_pct": fl("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+               "fma_pipe_pct": fl("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+               "xu_pipe_pct": fl("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+               "issue_active_pct": fl("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "warps_active_pct": fl("sm__warps_active.avg.pct_of_peak_sustained_active"),
+               "registers_per_thread": fl("launch__registers_per_thread"),
+               "dram_bytes_per_launch": (to_bytes("dram__bytes_read.sum") or 0) + (to_bytes("dram__bytes_write.sum") or 0),
+               "duration_ms_under_ncu": dur / 1e3 if dur and unit("gpu__time_duration.sum") in ("us", "usecond") else dur,
+               "local_memory_sectors": (fl("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum") or 0) + (fl("l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum") or 0),
+               "top_stalls": {k: round(v, 2) for v, k in stl[:8]}}
+        print(json.dumps(out, indent=1))
+        return
     if "--list" in sys.argv:
         for r in hot:
             print(f"{int(r[iE]) / mx:5.2f} {r[iN]:>5s} {r[iS][:100]}")

@@ -16,7 +16,11 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
-        "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "lts__t_sectors_op_write.sum"]
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "lts__t_sectors_op_write.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+        "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "smsp__issue_active.avg.per_cycle_active"]
+STALL_PREFIX, STALL_SUFFIX = "smsp__average_warps_issue_stalled_", "_per_issue_active.ratio"
 
 
 def raw(path):
@@ -38,9 +42,14 @@ def mix(path, idx):
     hdr = rows[hi]
     iS, iE = hdr.index("Source"), hdr.index("Instructions Executed")
     ops = collections.Counter()
+    iA = hdr.index("Address")
+    seen = set()
     for r in rows[hi + 1:]:
         if len(r) <= iE:
             continue
+        if r[iA] in seen:          # the CSV lists every instruction once per source view: count each address once
+            continue
+        seen.add(r[iA])
         m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[iS].strip())
         if not m:
             continue
@@ -64,6 +73,11 @@ def main():
         for k in KEYS:
             if k in d:
                 print(f"    {k:75s} {d[k][0]:>18s} {d[k][1]}")
+        st = sorted(((float(v[0]), k[len(STALL_PREFIX):-len(STALL_SUFFIX)]) for k, v in d.items()
+                     if k.startswith(STALL_PREFIX) and k.endswith(STALL_SUFFIX) and v[0] not in ("", "n/a")), reverse=True)
+        if st:
+            print("    warp stall reasons per issued instruction (smsp__average_warps_issue_stalled_*_per_issue_active):")
+            print("        " + ", ".join(f"{k} {v:.2f}" for v, k in st if v >= 0.005))
         try:
             ops = mix(path, idx)
             tot = sum(ops.values())
