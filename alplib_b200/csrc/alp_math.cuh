@@ -157,114 +157,49 @@ ALP_HD void uniform_2(uint64_t seed, uint32_t tag, uint32_t row, uint64_t s, dou
 }
 
 // Reduction / polynomial constants of exp_fast live in constant memory on the device so that each step is a single
-// DFMA with a constant-bank operand (64-bit immediates would cost two extra moves per step).
-//   [0] 256/ln2   [1],[2] -ln2/256 split high (32 trailing zero bits) / low   [3..5] c2..c4 of exp(r)-1-r ~ r^2 (c2+c3 r+c4 r^2)
-#define ALP_EXP_COEFS {369.3299304675746, -0.002707604318857193, -1.855205093371747e-09, 0.5, \
-    0.16666667813301728, 0.04166666857772509, 0.0, 0.0}
-constexpr int kExpTabBits = 8;                  // 2^8 = 256 table entries (2 KB)
+// DFMA with a constant operand (64-bit immediates would cost two extra moves per step).  Table and constants are generated
+// by tools/gen_exp_table.py (80-digit arithmetic): 2^11 = 2048 entries (16 KB; the sample kernels keep a copy in shared
+// memory), which makes |r| <= ln2/4096 = 1.7e-4 small enough for a degree-3 polynomial (truncation r^4/24 = 3.4e-17).
+#include "alp_exp_table.inc"
+constexpr int kExpTabBits = ALP_EXP_TAB_BITS;
 constexpr int kExpTabSize = 1 << kExpTabBits;
-// Entry j holds the bit pattern of 2^(j/256) (rounded to nearest) minus (j << 44), so that adding (256 n + j) << 44 to it
-// yields 2^n 2^(j/256) with a single integer add (the construction of glibc's exp table).
-#define ALP_EXP_TABLE { \
-    0x1.0000000000000p+0, 0x1.ffb1afa5abcbfp-1, 0x1.ff63da9fb3335p-1, 0x1.ff168143b0281p-1, \
-    0x1.fec9a3e778061p-1, 0x1.fe7d42e11bbccp-1, 0x1.fe315e86e7f85p-1, 0x1.fde5f72f654b1p-1, \
-    0x1.fd9b0d3158574p-1, 0x1.fd50a0e3c1f89p-1, 0x1.fd06b29ddf6dep-1, 0x1.fcbd42b72a836p-1, \
-    0x1.fc74518759bc8p-1, 0x1.fc2bdf66607e0p-1, 0x1.fbe3ecac6f383p-1, 0x1.fb9c79b1f3919p-1, \
-    0x1.fb5586cf9890fp-1, 0x1.fb0f145e46c85p-1, 0x1.fac922b7247f7p-1, 0x1.fa83b23395decp-1, \
-    0x1.fa3ec32d3d1a2p-1, 0x1.f9fa55fdfa9c5p-1, 0x1.f9b66affed31bp-1, 0x1.f973028d7233ep-1, \
-    0x1.f9301d0125b51p-1, 0x1.f8edbab5e2ab6p-1, 0x1.f8abdc06c31ccp-1, 0x1.f86a814f204abp-1, \
-    0x1.f829aaea92de0p-1, 0x1.f7e95934f312ep-1, 0x1.f7a98c8a58e51p-1, 0x1.f76a45471c3c2p-1, \
-    0x1.f72b83c7d517bp-1, 0x1.f6ed48695bbc0p-1, 0x1.f6af9388c8deap-1, 0x1.f672658375d2fp-1, \
-    0x1.f635beb6fcb75p-1, 0x1.f5f99f8138a1cp-1, 0x1.f5be084045cd4p-1, 0x1.f582f95281c6bp-1, \
-    0x1.f54873168b9aap-1, 0x1.f50e75eb44027p-1, 0x1.f4d5022fcd91dp-1, 0x1.f49c18438ce4dp-1, \
-    0x1.f463b88628cd6p-1, 0x1.f42be3578a819p-1, 0x1.f3f49917ddc96p-1, 0x1.f3bdda27912d1p-1, \
-    0x1.f387a6e756238p-1, 0x1.f351ffb82140ap-1, 0x1.f31ce4fb2a63fp-1, 0x1.f2e85711ece75p-1, \
-    0x1.f2b4565e27cddp-1, 0x1.f280e341ddf29p-1, 0x1.f24dfe1f56381p-1, 0x1.f21ba7591bb70p-1, \
-    0x1.f1e9df51fdee1p-1, 0x1.f1b8a66d10f13p-1, 0x1.f187fd0dad990p-1, 0x1.f157e39771b2fp-1, \
-    0x1.f1285a6e4030bp-1, 0x1.f0f961f641589p-1, 0x1.f0cafa93e2f56p-1, 0x1.f09d24abd886bp-1, \
-    0x1.f06fe0a31b715p-1, 0x1.f0432edeeb2fdp-1, 0x1.f0170fc4cd831p-1, 0x1.efeb83ba8ea32p-1, \
-    0x1.efc08b26416ffp-1, 0x1.ef96266e3fa2dp-1, 0x1.ef6c55f929ff1p-1, 0x1.ef431a2de883bp-1, \
-    0x1.ef1a7373aa9cbp-1, 0x1.eef26231e754ap-1, 0x1.eecae6d05d866p-1, 0x1.eea401b7140efp-1, \
-    0x1.ee7db34e59ff7p-1, 0x1.ee57fbfec6cf4p-1, 0x1.ee32dc313a8e5p-1, 0x1.ee0e544ede173p-1, \
-    0x1.edea64c123422p-1, 0x1.edc70df1c5175p-1, 0x1.eda4504ac801cp-1, 0x1.ed822c367a024p-1, \
-    0x1.ed60a21f72e2ap-1, 0x1.ed3fb2709468ap-1, 0x1.ed1f5d950a897p-1, 0x1.ecffa3f84b9d4p-1, \
-    0x1.ece086061892dp-1, 0x1.ecc2042a7d232p-1, 0x1.eca41ed1d0057p-1, 0x1.ec86d668b3237p-1, \
-    0x1.ec6a2b5c13cd0p-1, 0x1.ec4e1e192aed2p-1, 0x1.ec32af0d7d3dep-1, 0x1.ec17dea6db7d7p-1, \
-    0x1.ebfdad5362a27p-1, 0x1.ebe41b817c114p-1, 0x1.ebcb299fddd0dp-1, 0x1.ebb2d81d8abffp-1, \
-    0x1.eb9b2769d2ca7p-1, 0x1.eb8417f4531eep-1, 0x1.eb6daa2cf6642p-1, 0x1.eb57de83f4eefp-1, \
-    0x1.eb42b569d4f82p-1, 0x1.eb2e2f4f6ad27p-1, 0x1.eb1a4ca5d920fp-1, 0x1.eb070dde910d2p-1, \
-    0x1.eaf4736b527dap-1, 0x1.eae27dbe2c4cfp-1, 0x1.ead12d497c7fdp-1, 0x1.eac0827ff07ccp-1, \
-    0x1.eab07dd485429p-1, 0x1.eaa11fba87a03p-1, 0x1.ea9268a5946b7p-1, 0x1.ea84590998b93p-1, \
-    0x1.ea76f15ad2148p-1, 0x1.ea6a320dceb71p-1, 0x1.ea5e1b976dc09p-1, 0x1.ea52ae6cdf6f4p-1, \
-    0x1.ea47eb03a5585p-1, 0x1.ea3dd1d1929fdp-1, 0x1.ea34634ccc320p-1, 0x1.ea2b9febc8fb7p-1, \
-    0x1.ea23882552225p-1, 0x1.ea1c1c70833f6p-1, 0x1.ea155d44ca973p-1, 0x1.ea0f4b19e9538p-1, \
-    0x1.ea09e667f3bcdp-1, 0x1.ea052fa75173ep-1, 0x1.ea012750bdabfp-1, 0x1.e9fdcddd47645p-1, \
-    0x1.e9fb23c651a2fp-1, 0x1.e9f9298593ae5p-1, 0x1.e9f7df9519484p-1, 0x1.e9f7466f42e87p-1, \
-    0x1.e9f75e8ec5f74p-1, 0x1.e9f8286ead08ap-1, 0x1.e9f9a48a58174p-1, 0x1.e9fbd35d7cbfdp-1, \
-    0x1.e9feb564267c9p-1, 0x1.ea024b1ab6e09p-1, 0x1.ea0694fde5d3fp-1, 0x1.ea0b938ac1cf6p-1, \
-    0x1.ea11473eb0187p-1, 0x1.ea17b0976cfdbp-1, 0x1.ea1ed0130c132p-1, 0x1.ea26a62ff86f0p-1, \
-    0x1.ea2f336cf4e62p-1, 0x1.ea3878491c491p-1, 0x1.ea427543e1a12p-1, 0x1.ea4d2add106d9p-1, \
-    0x1.ea589994cce13p-1, 0x1.ea64c1eb941f7p-1, 0x1.ea71a4623c7adp-1, 0x1.ea7f4179f5b21p-1, \
-    0x1.ea8d99b4492edp-1, 0x1.ea9cad931a436p-1, 0x1.eaac7d98a6699p-1, 0x1.eabd0a478580fp-1, \
-    0x1.eace5422aa0dbp-1, 0x1.eae05bad61778p-1, 0x1.eaf3216b5448cp-1, 0x1.eb06a5e0866d9p-1, \
-    0x1.eb1ae99157736p-1, 0x1.eb2fed0282c8ap-1, 0x1.eb45b0b91ffc6p-1, 0x1.eb5c353aa2fe2p-1, \
-    0x1.eb737b0cdc5e5p-1, 0x1.eb8b82b5f98e5p-1, 0x1.eba44cbc8520fp-1, 0x1.ebbdd9a7670b3p-1, \
-    0x1.ebd829fde4e50p-1, 0x1.ebf33e47a22a2p-1, 0x1.ec0f170ca07bap-1, 0x1.ec2bb4d53fe0dp-1, \
-    0x1.ec49182a3f090p-1, 0x1.ec674194bb8d5p-1, 0x1.ec86319e32323p-1, 0x1.eca5e8d07f29ep-1, \
-    0x1.ecc667b5de565p-1, 0x1.ece7aed8eb8bbp-1, 0x1.ed09bec4a2d33p-1, 0x1.ed2c980460ad8p-1, \
-    0x1.ed503b23e255dp-1, 0x1.ed74a8af46052p-1, 0x1.ed99e1330b358p-1, 0x1.edbfe53c12e59p-1, \
-    0x1.ede6b5579fdbfp-1, 0x1.ee0e521356ebap-1, 0x1.ee36bbfd3f37ap-1, 0x1.ee5ff3a3c2774p-1, \
-    0x1.ee89f995ad3adp-1, 0x1.eeb4ce622f2ffp-1, 0x1.eee07298db666p-1, 0x1.ef0ce6c9a8952p-1, \
-    0x1.ef3a2b84f15fbp-1, 0x1.ef68415b749b1p-1, 0x1.ef9728de5593ap-1, 0x1.efc6e29f1c52ap-1, \
-    0x1.eff76f2fb5e47p-1, 0x1.f028cf22749e4p-1, 0x1.f05b030a1064ap-1, 0x1.f08e0b79a6f1fp-1, \
-    0x1.f0c1e904bc1d2p-1, 0x1.f0f69c3f3a207p-1, 0x1.f12c25bd71e09p-1, 0x1.f16286141b33dp-1, \
-    0x1.f199bdd85529cp-1, 0x1.f1d1cd9fa652cp-1, 0x1.f20ab5fffd07ap-1, 0x1.f244778fafb22p-1, \
-    0x1.f27f12e57d14bp-1, 0x1.f2ba88988c933p-1, 0x1.f2f6d9406e7b5p-1, 0x1.f33405751c4dbp-1, \
-    0x1.f3720dcef9069p-1, 0x1.f3b0f2e6d1675p-1, 0x1.f3f0b555dc3fap-1, 0x1.f43155b5bab74p-1, \
-    0x1.f472d4a07897cp-1, 0x1.f4b532b08c968p-1, 0x1.f4f87080d89f2p-1, 0x1.f53c8eacaa1d6p-1, \
-    0x1.f5818dcfba487p-1, 0x1.f5c76e862e6d3p-1, 0x1.f60e316c98398p-1, 0x1.f655d71ff6075p-1, \
-    0x1.f69e603db3285p-1, 0x1.f6e7cd63a8315p-1, 0x1.f7321f301b460p-1, 0x1.f77d5641c0658p-1, \
-    0x1.f7c97337b9b5fp-1, 0x1.f81676b197d17p-1, 0x1.f864614f5a129p-1, 0x1.f8b333b16ee12p-1, \
-    0x1.f902ee78b3ff6p-1, 0x1.f953924676d76p-1, 0x1.f9a51fbc74c83p-1, 0x1.f9f7977cdb740p-1, \
-    0x1.fa4afa2a490dap-1, 0x1.fa9f4867cca6ep-1, 0x1.faf482d8e67f1p-1, 0x1.fb4aaa2188510p-1, \
-    0x1.fba1bee615a27p-1, 0x1.fbf9c1cb6412ap-1, 0x1.fc52b376bba97p-1, 0x1.fcac948dd7274p-1, \
-    0x1.fd0765b6e4540p-1, 0x1.fd632798844f8p-1, 0x1.fdbfdad9cbe14p-1, 0x1.fe1d802243c89p-1, \
-    0x1.fe7c1819e90d8p-1, 0x1.fedba3692d514p-1, 0x1.ff3c22b8f71f1p-1, 0x1.ff9d96b2a23d9p-1 }
 #if defined(__CUDACC__)
 static __constant__ double kExpCoefDev[8] = ALP_EXP_COEFS;
+static __constant__ double kExp10CoefDev[4] = ALP_EXP10_COEFS;
 static __device__ const double kExpTabDev[kExpTabSize] = ALP_EXP_TABLE;
 #endif
 static const double kExpCoefHost[8] = ALP_EXP_COEFS;
+static const double kExp10CoefHost[4] = ALP_EXP10_COEFS;
 static const double kExpTabHost[kExpTabSize] = ALP_EXP_TABLE;
 #if defined(__CUDA_ARCH__)
 #define ALP_EXPC(i) kExpCoefDev[i]
+#define ALP_EXP10C(i) kExp10CoefDev[i]
 #else
 #define ALP_EXPC(i) kExpCoefHost[i]
+#define ALP_EXP10C(i) kExp10CoefHost[i]
 #endif
 
 // ---- exp for the fast mode ---------------------------------------------------------------------------------------
-// Table-driven: x = (256 n + j) ln2/256 + r with |r| <= ln2/512 (Cody-Waite, two-part ln2/256), exp(x) = 2^n 2^(j/256) exp(r);
-// 2^(j/256) from a 256-entry table (2 KB; the kernels keep a copy in shared memory), exp(r)-1 from a degree-4 polynomial
-// (Chebyshev-node interpolant computed with 60-digit arithmetic, 0.09 ulp), 2^n applied to the exponent field.
-// 9 FP64 instructions, dependency depth 8.  Within 1 ulp of glibc on [-708, 708] (tests/test_hostmath.py measures it);
+// Table-driven: x = (N n + j) ln2/N + r with N = 2048, |r| <= ln2/4096 (Cody-Waite, two-part ln2/N), exp(x) = 2^n 2^(j/N) exp(r);
+// 2^(j/N) from the table, exp(r)-1 = r + r^2 (1/2 + r/6) (truncation 3.4e-17 relative), 2^n applied to the exponent field.
+// 8 FP64 instructions, dependency depth 7.  Within 1 ulp of glibc on [-708, 708] (tests/test_hostmath.py measures it);
 // anything outside (including NaN) takes the library exp.  Branch-free, so several calls interleave.
 ALP_HD double exp_table_finish(double kd, double r, const double* tab) {
     const double r2 = r * r;
-    double q = fma(ALP_EXPC(5), r, ALP_EXPC(4));
-    q = fma(q, r, ALP_EXPC(3));
+    const double q = fma(ALP_EXPC(4), r, ALP_EXPC(3));
     const double t = fma(q, r2, r);                                 // exp(r) - 1
 #if defined(__CUDA_ARCH__)
-    const int ki = __double2loint(kd);                              // 256 n + j, two's complement
+    const int ki = __double2loint(kd);                              // N n + j, two's complement
     double tv;
     if (tab) {
-        // shared-memory copy: address = base + 8 (ki & 255) as one LOP3 + one IMAD (the compiler's own sequence is three)
+        // shared-memory copy: address = base + 8 (ki & (N-1)) as one LOP3 + one IMAD (the compiler's own sequence is three)
         unsigned addr;
         asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(ki & (kExpTabSize - 1)), "r"((unsigned)__cvta_generic_to_shared(tab)));
         asm("ld.shared.f64 %0, [%1];" : "=d"(tv) : "r"(addr));
     } else {
         tv = __ldg(&kExpTabDev[ki & (kExpTabSize - 1)]);
     }
-    const double S = __hiloint2double(__double2hiint(tv) + (ki << (20 - kExpTabBits)), __double2loint(tv));   // 2^n 2^(j/256)
+    const double S = __hiloint2double(__double2hiint(tv) + (ki << (20 - kExpTabBits)), __double2loint(tv));   // 2^n 2^(j/N)
     return fma(S, t, S);
 #else
     int64_t bits, tb;
@@ -282,22 +217,22 @@ ALP_HD double exp_table_finish(double kd, double r, const double* tab) {
 // `tab`: a copy of the table in shared memory (the chain / scan / volume-integral kernels); default: the global copy through L1
 ALP_HD double exp_fast_core(double x, const double* tab = nullptr) {          // requires |x| <= 708
     const double kShift = 6755399441055744.0;                       // 1.5 * 2^52: rounds to nearest integer
-    const double kd = fma(x, ALP_EXPC(0), kShift);                  // 256 x / ln2
+    const double kd = fma(x, ALP_EXPC(0), kShift);                  // N x / ln2
     const double fn = kd - kShift;
     double r = fma(fn, ALP_EXPC(1), x);
     r = fma(fn, ALP_EXPC(2), r);
     return exp_table_finish(kd, r, tab);
 }
 
-// 10^x with the same table and polynomial: x = (256 n + j) log10(2)/256 + t, 10^x = 2^n 2^(j/256) exp(t ln10).
+// 10^x with the same table and polynomial: x = (N n + j) log10(2)/N + t, 10^x = 2^n 2^(j/N) exp(t ln10).
 // Requires |x| <= 300.  ~1 ulp; used for the log-uniform energy draw of the bremsstrahlung channel (fluxes.py:326-327).
 ALP_HD double exp10_fast_core(double x, const double* tab = nullptr) {
     const double kShift = 6755399441055744.0;
-    const double kd = fma(x, 850.4135922911647, kShift);           // 256 x log2(10)
+    const double kd = fma(x, ALP_EXP10C(0), kShift);                // N x log2(10)
     const double fn = kd - kShift;
-    double t = fma(fn, -0.001175898127257824, x);                   // log10(2)/256, high part (32 trailing zero bits)
-    t = fma(fn, -2.9330460259971186e-10, t);                        // low part
-    return exp_table_finish(kd, t * 2.302585092994046, tab);        // |r| <= ln2/512
+    double t = fma(fn, ALP_EXP10C(1), x);                           // log10(2)/N, high part (32 trailing zero bits)
+    t = fma(fn, ALP_EXP10C(2), t);                                  // low part
+    return exp_table_finish(kd, t * ALP_EXP10C(3), tab);            // |r| <= ln2/(2N)
 }
 
 ALP_HD double exp_fast(double x) {

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreads)
 propagate_pairs_kernel(const double* __restrict__ energy, const double* __restrict__ weight, uint64_t n, PropConst c,
                        float* __restrict__ d32, float* __restrict__ s32, double* __restrict__ d64o, double* __restrict__ s64o) {
     __shared__ double s_tab[alp::kExpTabSize];
-    if (threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = kExpTabDev[i];
     __syncthreads();
     const uint64_t n_pairs = n >> 1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -585,7 +585,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256)
 exp_peak_kernel(uint64_t iters, double* __restrict__ out) {
     __shared__ double s_tab[alp::kExpTabSize];
-    if (threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = alp::kExpTabDev[threadIdx.x];
+    for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = alp::kExpTabDev[i];
     __syncthreads();
     double x0 = -1e-3 * threadIdx.x - 0.5, x1 = x0 - 1.0, x2 = x0 - 2.0, x3 = x0 - 3.0, acc = 0.0;
     for (uint64_t i = 0; i < iters; ++i) {

@@ -377,7 +377,7 @@ vol_int_kernel(const double* __restrict__ energy, uint64_t n, const double* __re
     __shared__ double s_x[kVolTile], s_b[kVolTile], s_j[kVolTile];
     __shared__ double s_tab[alp::kExpTabSize];                     // exp_fast table
     __shared__ unsigned long long s_xmax_bits;       // fast mode: largest |x| of the staged tile (ordered bits)
-    if (FAST && threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    if (FAST) for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = kExpTabDev[i];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t k0 = blockIdx.y * chunk;
     const uint32_t k1 = (k0 + chunk < n_points) ? k0 + chunk : n_points;
@@ -457,7 +457,7 @@ vol_int_finish_kernel(const double* __restrict__ energy, const double* __restric
 ALPK_EXPORT uint32_t alpk_vol_int_chunks(uint64_t n, uint32_t n_points) {
     // enough (sample block, point chunk) CTAs to fill the GPU even for a handful of samples
     const uint64_t blocks = (n + kThreads - 1) / kThreads;
-    uint32_t want = (uint32_t)((2ull * 148 + blocks - 1) / (blocks ? blocks : 1));
+    uint32_t want = (uint32_t)((2ull * (uint64_t)sm_count() + blocks - 1) / (blocks ? blocks : 1));
     uint32_t maxc = (n_points + kVolTile - 1) / kVolTile;
     if (want < 1) want = 1;
     return want < maxc ? want : (maxc ? maxc : 1);

@@ -71,7 +71,7 @@ resonance_kernel(const double* __restrict__ pos_e, const double* __restrict__ po
     __shared__ double s_tab[alp::kExpTabSize];
     double inv_dx = 0.0;
     if (FAST) {
-        if (threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+        for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = kExpTabDev[i];
         // uniformly spaced positron table (the usual linspace): index from the spacing instead of a binary search
         const BinGuess g = detect_spacing(pos_e, n_pos);      // (contains the CTA-wide barriers that also publish s_tab)
         inv_dx = g.mode == 1 ? g.scale : 0.0;

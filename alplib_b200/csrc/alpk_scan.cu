@@ -118,9 +118,10 @@ scan_kernel(const ScanArgs a) {
     //      sums are bit-identical to walking the whole tile (the skipped terms are exact zeros) ------------------------
     __shared__ int s_warp[kScanThreads / 32];
     __shared__ int s_live;
-    __shared__ double s_tab[alp::kExpTabSize];                 // exp_fast table
+    // exp_fast table: read through L1 from its global copy (16 KB; the five sample arrays already take 40 KB of the 48 KB
+    // of static shared memory a CTA may declare)
+    const double* const s_tab = nullptr;
     __shared__ unsigned long long s_tmax_bits;   // max over live samples of 1/p_a (non-finite / NaN -> +inf), as ordered bits
-    if (threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
     __shared__ unsigned long long s_tmin_bits;   // min over live samples of 1/p_a; 0 if any live sample has a NaN 1/p_a or a non-finite weight
     __shared__ unsigned long long s_wmax_bits;   // max |weight| over live samples
     if (threadIdx.x == 0) { s_tmax_bits = 0ull; s_tmin_bits = 0x7ff0000000000000ull; s_wmax_bits = 0ull; }

@@ -213,7 +213,7 @@ chain_kernel(const ChainArgs<Prod> a) {
         guess = detect_spacing(s_edges, a.n_edges);
         if (a.hist_copies > 1) s_bins = s_bins_all + (threadIdx.x >> 5) * (a.n_edges - 1);
     }
-    if (FAST && threadIdx.x < alp::kExpTabSize) s_tab[threadIdx.x] = kExpTabDev[threadIdx.x];
+    if (FAST) for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = kExpTabDev[i];
     // (all made visible by the __syncthreads of the first tile)
     const uint64_t n = a.n_rows * (uint64_t)a.n_samples;
     const uint32_t tile_elems = a.tile_elems;        // kTile, or fewer when rows are so short that a full tile would
@@ -342,7 +342,12 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
         const int rc = launch_chain_rows<Prod>(what, a, stage, standard, noevents, none, rate, scratch, st);
         if (rc >= 0) return rc;
     }
-#define ALPK_CHAIN_LAUNCH(I, S, F, H, P, O, SH) chain_kernel<Prod, I, S, F, H, P, O, SH><<<grid, kThreads, smem, st>>>(a)
+    // (histogram launches: static shared memory -- row stage + 16 KB exp table -- plus the bins can exceed the 48 KB a kernel
+    // gets without opting in)
+#define ALPK_CHAIN_LAUNCH(I, S, F, H, P, O, SH) do {                                                                   \
+        auto kfn = chain_kernel<Prod, I, S, F, H, P, O, SH>;                                                          \
+        if (smem > 16 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kfn<<<grid, kThreads, smem, st>>>(a); } while (0)
 #define ALPK_CHAIN_PAIRED(S, O) { if (S >= 1 && a.prop.short_lived) ALPK_CHAIN_LAUNCH(false, S, true, false, true, O, true); \
                                   else ALPK_CHAIN_LAUNCH(false, S, true, false, true, O, false); }
 #define ALPK_CHAIN_CASE(S)                                                                                   \
