@@ -213,8 +213,21 @@ class Scatter2to2MC:
         return self._dev
 
     def get_total_xs(self, s):
-        raise NotImplementedError("get_total_xs integrates dsigma_dt with scipy.integrate.quad in the reference "
-                                  "(cross_section_mc.py:242-258); it is outside the Monte-Carlo hot path and not offered")
+        """Integral of dsigma/dt over the kinematic t range (cross_section_mc.py:242-258).  As in the reference the adaptive
+        quadrature driver is scipy.integrate.quad on the host; every integrand evaluation is the device evaluator of the
+        matrix element (dsigma_dt -> alpk_m2_eval), one small launch per abscissa -- a utility, not a hot-path call."""
+        from numpy import power
+        from scipy.integrate import quad
+        p1_cm = self.p1_cm(s)
+        p3_cm = self.p3_cm(s)
+
+        t0 = power(self.m1**2 - self.m3**2 - self.m2**2 + self.m4**2, 2)/(4*s) - power(p1_cm - p3_cm, 2)
+        t1 = power(self.m1**2 - self.m3**2 - self.m2**2 + self.m4**2, 2)/(4*s) - power(p1_cm + p3_cm, 2)
+
+        def integrand(t):
+            return float(self.dsigma_dt(s, t))
+
+        return quad(integrand, t1, t0)[0]
 
     def get_cosine_lab_weights(self):
         """(cosines of p3 in the lab frame, weights) -- cross_section_mc.py:260-268"""

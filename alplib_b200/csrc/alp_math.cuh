@@ -413,8 +413,11 @@ ALP_HD double compton_sample_fast(double u, const double* b, const ComptonGlobal
     const double t = rcp_fast(x * omx);
     const double r_omx = x * t, r_x = omx * t;                    // 1/(1-x), 1/x
     const double inner = fma(b[CB_K], fma(-g.ma2, r_x, fma(-me2, r_omx, b[CB_S])), x);
-    const double v = b[CB_Q] * ((x * r_omx) * inner);
-    flux = in ? v : 0.0 * v;                                      // outside the window: 0 (NaN/inf propagate like 0*v)
+    // outside the window the reference's prefactor is an exact 0 (its heavisides) that multiplies the bracket: select the
+    // per-row factor (Q or 0*Q, both row constants -- hoisted out of the sample loop where the row is fixed) instead of
+    // multiplying the result by 0; NaN/inf brackets still propagate as 0*inf = NaN
+    const double qrow = in ? b[CB_Q] : 0.0 * b[CB_Q];
+    flux = qrow * ((x * r_omx) * inner);
     return ea;
 }
 
@@ -475,11 +478,11 @@ ALP_HD void propagate_sample(double ea, double wgt, const PropConst& c, double& 
 // below -708.  Each exponential is then handled on its own: below -746 it is exactly 0 (survival 0 / decay probability 1),
 // so only the narrow band (-746, -708) of denormal results still goes to the library path.  The launchers pick the
 // variant from the host-known exponent scale (PropConst::short_lived); the long-lived regime pays nothing for it.
-template <bool SHORT_LIVED = false>
+template <bool SHORT_LIVED = false, bool PLAIN = false>      // PLAIN: the launcher guarantees c.fast == 1 (no FP32 mode)
 ALP_HD bool propagate_try_fast(double ea, double wgt, const PropConst& c, double& d64, double& s64,
                                const double* exp_tab = nullptr) {
     const double d = ea * ea - c.ma2;
-    if (c.fast == 2) {
+    if (!PLAIN && c.fast == 2) {
         // optional FP32 mode (north star: 1e-5 relative): only the transcendental part is single precision -- rsqrt and
         // the two exponentials (~1e-7 relative each); the decay probability uses expm1f, which unlike the reference's
         // 1 - exp(-x) does not cancel for long-lived ALPs.  Products stay FP64 so the dynamic range is unchanged.
@@ -552,8 +555,21 @@ ALP_HD double decay_event_weight(double ea, float w32, const EventConst& c) {
 // the NaN branch of heaviside is covered by the product) and E_a - threshold >= 0 <=> E_a >= threshold (IEEE subtraction
 // is zero only for equal operands).
 ALP_HD double decay_event_weight_coupled(double ea, float w32, const EventConst& c) {
-    const double base = c.days_f64 ? c.days_sec * (double)w32 : (double)(c.days_sec32 * w32);
-    return ea >= c.threshold ? base : base * 0.0;
+    if (c.days_f64) {
+        const double base = c.days_sec * (double)w32;
+        return ea >= c.threshold ? base : base * 0.0;
+    }
+    // Python-scalar exposure: the product and the threshold factor live in float32 (NEP 50); the widening is exact, so the
+    // select can be done before it -- one FMUL instead of a DMUL for the 0 * base that keeps NaN / inf weights NaN
+    const float b32 = c.days_sec32 * w32;
+    return (double)(ea >= c.threshold ? b32 : b32 * 0.0f);
+}
+
+// PLAIN variants for kernels whose launcher has excluded the rare modes (np.float64 exposure, FP32 transcendentals): the mode
+// tests disappear from the sample loop.
+ALP_HD double decay_event_weight_plain(double ea, float w32, const EventConst& c) {
+    const float b32 = c.days_sec32 * w32;
+    return (double)(ea >= c.threshold ? b32 : b32 * 0.0f);
 }
 
 // ---- 2-body decay a -> gamma gamma of a forward parent (generators.py:116-126, cross_section_mc.py:510-544,669-685) ----------

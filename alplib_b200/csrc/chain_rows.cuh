@@ -38,6 +38,14 @@ namespace alpk {
 #ifndef ALPK_ROWS_CHUNK_PAIRS
 #define ALPK_ROWS_CHUNK_PAIRS 512          // target pairs per unit (16 warp iterations); 256 / 1024 measured 1-2 % slower
 #endif
+#ifndef ALPK_ROWS_STCS
+#define ALPK_ROWS_STCS 1
+#endif
+#if ALPK_ROWS_STCS
+#define ALPK_ROWS_ST(ptr, val) __stcs(ptr, val)
+#else
+#define ALPK_ROWS_ST(ptr, val) (*(ptr) = (val))
+#endif
 constexpr int kRowsThreads = ALPK_ROWS_THREADS;
 constexpr int kRowsUnroll = ALPK_ROWS_UNROLL;
 constexpr uint32_t kRowsMinSamples = 256;   // shorter rows stay with the tile kernel (units would be mostly lane padding)
@@ -89,7 +97,18 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
 #pragma unroll
         for (int k = 0; k < NP; ++k) row[k] = __ldg(a.table + (uint64_t)r * NP + k);
         const uint32_t rid = a.row_ids ? __ldg(a.row_ids + r) : r;
-        const uint64_t base = (uint64_t)r * a.n_samples;
+        // per-lane output cursors of the unit, advanced by one warp trip (32 pairs) per iteration: two adds per array instead
+        // of rebuilding every address from the sample index
+        const uint64_t i_first = (uint64_t)r * a.n_samples + 2ull * (p_begin + lane);
+        constexpr bool kAll = OUT == kOutStandard || OUT == kOutNoEvents;   // pointers known non-null (d64 / s64 known null)
+        constexpr bool kEvw = OUT == kOutStandard;                            // event_w known non-null
+        double2* pe = (kAll || a.out_e) ? reinterpret_cast<double2*>(a.out_e + i_first) : nullptr;
+        double2* pf = (kAll || a.out_f) ? reinterpret_cast<double2*>(a.out_f + i_first) : nullptr;
+        float2* pd32 = (STAGE >= 1 && (kAll || a.d32)) ? reinterpret_cast<float2*>(a.d32 + i_first) : nullptr;
+        float2* ps32 = (STAGE >= 1 && (kAll || a.s32)) ? reinterpret_cast<float2*>(a.s32 + i_first) : nullptr;
+        double2* pd64 = (STAGE >= 1 && !kAll && a.d64) ? reinterpret_cast<double2*>(a.d64 + i_first) : nullptr;
+        double2* ps64 = (STAGE >= 1 && !kAll && a.s64) ? reinterpret_cast<double2*>(a.s64 + i_first) : nullptr;
+        double2* pev = (STAGE >= 2 && (kEvw || (OUT == kOutGeneric && a.event_w))) ? reinterpret_cast<double2*>(a.event_w + i_first) : nullptr;
         double acc = 0.0;
 
 #pragma unroll kRowsUnroll
@@ -105,7 +124,7 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
             if (STAGE >= 1) {
                 bool ok = true;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) ok &= propagate_try_fast<SHORT>(e[j], f[j], a.prop, d64v[j], s64v[j], s_tab);
+                for (int j = 0; j < 2; ++j) ok &= propagate_try_fast<SHORT, true>(e[j], f[j], a.prop, d64v[j], s64v[j], s_tab);
                 if (!ok) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) propagate_sample_fast(e[j], f[j], a.prop, d64v[j], s64v[j]);
@@ -119,24 +138,21 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
             if (STAGE >= 2) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    evv[j] = decay_event_weight_coupled(e[j], d32v[j], a.ev);
+                    evv[j] = decay_event_weight_plain(e[j], d32v[j], a.ev);
                     acc += evv[j];
                 }
             }
             if (OUT != kOutNone) {
-                constexpr bool kAll = OUT == kOutStandard || OUT == kOutNoEvents;
-                constexpr bool kEvw = OUT == kOutStandard;
-                const uint64_t i0 = base + 2ull * p;
-                if (kAll || a.out_e) *reinterpret_cast<double2*>(a.out_e + i0) = make_double2(e[0], e[1]);
-                if (kAll || a.out_f) *reinterpret_cast<double2*>(a.out_f + i0) = make_double2(f[0], f[1]);
+                // write-once outputs: streaming stores (evict-first in L2)
+                if (kAll || pe) { ALPK_ROWS_ST(pe, make_double2(e[0], e[1])); pe += 32; }
+                if (kAll || pf) { ALPK_ROWS_ST(pf, make_double2(f[0], f[1])); pf += 32; }
                 if (STAGE >= 1) {
-                    if (kAll || a.d32) *reinterpret_cast<float2*>(a.d32 + i0) = make_float2(d32v[0], d32v[1]);
-                    if (kAll || a.s32) *reinterpret_cast<float2*>(a.s32 + i0) = make_float2(s32v[0], s32v[1]);
-                    if (!kAll && a.d64) *reinterpret_cast<double2*>(a.d64 + i0) = make_double2(d64v[0], d64v[1]);
-                    if (!kAll && a.s64) *reinterpret_cast<double2*>(a.s64 + i0) = make_double2(s64v[0], s64v[1]);
+                    if (kAll || pd32) { ALPK_ROWS_ST(pd32, make_float2(d32v[0], d32v[1])); pd32 += 32; }
+                    if (kAll || ps32) { ALPK_ROWS_ST(ps32, make_float2(s32v[0], s32v[1])); ps32 += 32; }
+                    if (!kAll && pd64) { ALPK_ROWS_ST(pd64, make_double2(d64v[0], d64v[1])); pd64 += 32; }
+                    if (!kAll && ps64) { ALPK_ROWS_ST(ps64, make_double2(s64v[0], s64v[1])); ps64 += 32; }
                 }
-                if (STAGE >= 2 && (kEvw || (OUT == kOutGeneric && a.event_w)))
-                    *reinterpret_cast<double2*>(a.event_w + i0) = make_double2(evv[0], evv[1]);
+                if (STAGE >= 2 && (kEvw || (OUT == kOutGeneric && pev))) { ALPK_ROWS_ST(pev, make_double2(evv[0], evv[1])); pev += 32; }
             }
         }
         if (STAGE >= 2) {                            // the unit's rate sum: fixed order whichever warp ran the unit
@@ -209,6 +225,9 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
                       double* rate, double* scratch, cudaStream_t st) {
     const int mode = chain_rows_mode();
     if (!mode || a.n_samples < kRowsMinSamples) return -1;
+    // the sample loop is compiled without the rare-mode tests: FP32 transcendentals and an np.float64 exposure stay with the
+    // tile kernel
+    if ((stage >= 1 && a.prop.fast != 1) || (stage >= 2 && a.ev.days_f64)) return -1;
     const RowsGeom geo = rows_geometry(a.n_rows, a.n_samples, scratch, mode != 2);
     if ((uint64_t)a.n_rows * geo.chunks_per_row > kRowsMaxUnits) return -1;          // (more rows than unit slots: tile kernel)
     // (the unit counter and the finalize kernel's arrival counter sit next to each other: one 16-byte memset)

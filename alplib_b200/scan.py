@@ -18,7 +18,7 @@ from . import config
 from . import params as P
 from .constants import ALPHA, M_E, pi
 from .decay import W_ee, W_gg, W_gg_loop, b1
-from .dist import gather_row_blocks, world as _world
+from .dist import world as _world
 from .fluxes import _as_flux_table, _draw_seed
 from .materials import Material
 from .photon_xs import AbsCrossSection
@@ -148,11 +148,24 @@ def scan_rates_distributed(process, photon_flux, target, ma_grid, g_grid, group=
         kw["seed"] = int(box[0])
     if nranks == 1:
         return scan_rates(process, photon_flux, target, ma, g, **kw)
+    import torch.distributed as dist
     kw["return_device"] = True
+    n_ma, n_g = int(ma.shape[0]), int(g.shape[0])
     local = scan_rates(process, photon_flux, target, ma[rank::nranks], g, **kw)
-    counts = [len(range(r, ma.shape[0], nranks)) for r in range(nranks)]
-    blocks = gather_row_blocks(local, counts, group)
-    full = torch.empty((ma.shape[0], g.shape[0]), dtype=local.dtype, device=local.device)
-    for r, b in enumerate(blocks):
-        full[r::nranks] = b
-    return Runtime.get(local.device).to_host(full)
+    rt = Runtime.get(local.device)
+    # every rank's block padded to the same number of rows -> ONE all_gather_into_tensor (a single NCCL call, no per-rank
+    # output list), one pinned D2H of the gathered blocks; the round-robin interleave is undone on the host (a reshape)
+    n_loc = (n_ma + nranks - 1) // nranks
+    if local.shape[0] < n_loc:
+        pad = torch.zeros((n_loc, n_g), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        local = pad
+    flat = torch.empty((nranks * n_loc, n_g), dtype=local.dtype, device=local.device)      # rank-major concatenation
+    if dist.get_backend(group) == "gloo":                       # (CPU tests / more ranks than GPUs: host-staged)
+        h = flat.cpu()
+        dist.all_gather_into_tensor(h, local.cpu().contiguous(), group=group)
+        blocks = h.numpy()
+    else:
+        dist.all_gather_into_tensor(flat, local.contiguous(), group=group)
+        blocks = rt.to_host(flat)
+    return np.ascontiguousarray(blocks.reshape(nranks, n_loc, n_g).transpose(1, 0, 2).reshape(nranks * n_loc, n_g)[:n_ma])

@@ -254,6 +254,48 @@ def test_row_kernel_equals_tile_kernel(A, ns, n_bins, monkeypatch):
     assert res["1"][5] == res["2"][5]            # dynamic vs static unit assignment: identical rate, bit for bit
 
 
+def test_strict_compat_containers_and_lazy_decay_weights(A):
+    """strict=True materialises the reference's host containers -- Python lists of np.float64 after simulate() (fluxes.py:222-224)
+    and three Python lists from simulate_decay_4vectors (generators.py:124-128) -- and in the reduce-only schedule
+    decay_weights is computed on demand (it is what the reference's decays() leaves behind, generators.py:88-90)."""
+    pf = _c2_flux(60)
+    kw = dict(axion_mass=1.5, axion_coupling=1e-7, n_samples=64, seed=9, **GEOM)
+    ref = A.FluxComptonIsotropic(pf, A.Material("W"), fused=False, **kw)
+    ref.simulate(); ref.propagate()
+    gen_ref = A.ElectronEventGenerator(ref, A.Material("Ar"))
+    rate_ref = gen_ref.decays(100, 5.0)
+    fl = A.FluxComptonIsotropic(pf, A.Material("W"), strict=True, **kw)
+    fl.simulate()
+    assert isinstance(fl.axion_energy, list) and isinstance(fl.axion_flux, list) and isinstance(fl.axion_energy[0], np.float64)
+    assert fl.axion_energy == list(ref.axion_energy) and fl.axion_flux == list(ref.axion_flux)
+    assert (fl.axion_energy + [1.0])[-1] == 1.0                     # list semantics: concatenation, not broadcasting
+    fl.propagate()
+    assert isinstance(fl.decay_axion_weight, np.ndarray) and fl.decay_axion_weight.dtype == np.float32   # as after the reference's propagate()
+    # reduce-only schedule: decays() launches one kernel and keeps nothing; reading decay_weights afterwards computes them
+    fr = A.FluxComptonIsotropic(pf, A.Material("W"), fused=True, **kw)
+    fr.simulate(); fr.propagate()
+    gen = A.ElectronEventGenerator(fr, A.Material("Ar"))
+    assert gen.decays(100, 5.0) == pytest.approx(rate_ref, rel=1e-12) and fr._E is None
+    assert np.array_equal(gen.decay_weights, gen_ref.decay_weights) and np.count_nonzero(gen.decay_weights) > 0
+    r_dev = gen.decays_device(50, 5.0)                                # a later call must not leave the earlier weights behind
+    assert np.allclose(gen.decay_weights, 0.5 * gen_ref.decay_weights, rtol=1e-6) and float(r_dev.item()) == pytest.approx(0.5 * rate_ref, rel=1e-6)
+    fr.propagate(new_coupling=2e-7)
+    assert np.allclose(gen.decay_weights, 0.5 * gen_ref.decay_weights, rtol=1e-6)     # already materialised: what that decays() left behind
+    gen.decays_device(25, 5.0)
+    fr.propagate(new_coupling=3e-7)
+    with pytest.raises(RuntimeError):
+        gen.decay_weights                                              # not materialised and the flux changed after decays()
+    # decay MC: three Python lists in strict mode
+    prim = A.FluxPrimakoffIsotropic(np.array([[100.0, 1e12], [40.0, 1e11]]), A.Material("W"), axion_mass=0.1, axion_coupling=1e-5,
+                                    strict=True, **GEOM)
+    prim.simulate(); prim.propagate()
+    l1, l2, w = A.PhotonEventGenerator(prim, A.Material("Ar")).simulate_decay_4vectors(100, n_samples=3, seed=7)
+    assert isinstance(l1, list) and isinstance(l2, list) and isinstance(w, list) and len(l1) == len(l2) == len(w) == 6
+    assert isinstance(l1[0], A.LorentzVector) and (l1[0] + l2[0]).energy() == pytest.approx(100.0, rel=1e-12)
+    a1, a2, aw = A.PhotonEventGenerator(prim, A.Material("Ar")).simulate_decay_4vectors(100, n_samples=3, seed=7, strict=False)
+    assert np.array_equal(a1.pmu, np.array([v.pmu for v in l1])) and np.array_equal(np.asarray(aw), np.array(w))
+
+
 def test_compton_rates_statistical(A):
     """Free-running RNG, different seeds: total rate agrees with an independent oracle run within MC error."""
     pf = _c2_flux(200)

@@ -145,8 +145,10 @@ def test_scatter_sim_injected_uniforms_match_reference(A):
         assert isinstance(v, A.LorentzVector) and v.energy() == pytest.approx(c["e3_lab"][3], rel=TOL)
         assert mc.p3_lab_4vectors[3].cosine() == pytest.approx(c["cosines"][3], abs=TOL)
         assert isinstance(mc.p4_lab_3vectors[0], A.Vector3)
-        # dsigma_dt through the device evaluator
+        # dsigma_dt through the device evaluator, and its integral (scipy quad driver, device integrand)
         assert max_rel(mc.dsigma_dt(float(c["s"]), c["t_probe"]), c["dsigma_dt_probe"]) < TOL
+        if np.isfinite(c["total_xs"]) and str(c["tag"]) in ("icompton", "compton", "readme_iprim"):
+            assert mc.get_total_xs(float(c["s"])) == pytest.approx(float(c["total_xs"]), rel=1e-8)
     # matrix elements are callable like the reference's
     sg, tg, mN = g["m2_s"], g["m2_t"], float(cases[0]["mN"])
     for i, s in enumerate(sg):

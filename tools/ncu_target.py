@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launches each hot kernel exactly twice at BASELINE size (warm-up + capture) -- the ncu target:
-   ncu --set full -k regex:"chain_kernel|decay2body_kernel|scan_kernel" --launch-skip 4 --launch-count 4 python tools/ncu_target.py
+   ncu --set full -k regex:"chain_rows_kernel|decay2body_kernel|scan_kernel" --launch-skip 4 --launch-count 4 python tools/ncu_target.py
 order: chain materialise, chain reduce-only, decay2body, compton scan."""
 import os, sys
 import numpy as np

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Measured parity of the CUDA path against the reference's golden fixtures, both arithmetic modes, written to
-profiles/parity_r1.json (run on the GPU box)."""
+profiles/parity_r2.json (run on the GPU box)."""
 import json
 import os
 import sys
@@ -124,13 +124,34 @@ def report():
             wm["angle"] = max(wm["angle"], max_rel(fl.axion_angle, g[f"c{k}_T"])); wm["flux"] = max(wm["flux"], max_rel(fl.axion_flux, g[f"c{k}_F"]))
             wm["scatter_w64"] = max(wm["scatter_w64"], max_rel(fl.scatter_axion_weight_f64, g[f"c{k}_s64"]))
         r["meson_mixing (4 cases)"] = wm
+        # generic 2 -> 2 scatter MC (one arithmetic mode: the reference's operation order)
+        g = load_golden("scatter2to2")
+        ws = {"weights": 0.0, "cosines_abs": 0.0, "e3_lab": 0.0, "p3_lab_over_E": 0.0, "p4_lab_over_E": 0.0}
+        for k in range(int(g["n_cases"])):
+            pre = f"c{k}_"
+            if bool(g[pre + "empty"]):
+                continue
+            model, ma, mN, z = str(g[pre + "model"]), float(g[pre + "ma"]), float(g[pre + "mN"]), int(g[pre + "z"])
+            me = {"inverse_primakoff": lambda: A.M2InversePrimakoff(ma=ma, mN=mN, z=z), "primakoff": lambda: A.M2Primakoff(ma=ma, mN=mN, z=z),
+                  "inverse_compton": lambda: A.M2InverseCompton(ma=ma, z=z), "compton": lambda: A.M2Compton(ma=ma, z=z),
+                  "associated_production": lambda: A.M2AssociatedProduction(ma)}[model]()
+            mc = A.Scatter2to2MC(me, p1=A.LorentzVector(*g[pre + "p1"]), p2=A.LorentzVector(*g[pre + "p2"]), n_samples=int(g[pre + "n"]))
+            mc.scatter_sim(log_sampling=bool(g[pre + "log"]), uniforms=g[pre + "uniforms"])
+            cos, w = mc.get_cosine_lab_weights()
+            scale = abs(g[pre + "p1"][0]) + abs(g[pre + "p2"][0])
+            ws["weights"] = max(ws["weights"], max_rel(w, g[pre + "weights"]))
+            ws["cosines_abs"] = max(ws["cosines_abs"], float(np.max(np.abs(cos - g[pre + "cosines"]))))
+            ws["e3_lab"] = max(ws["e3_lab"], max_rel(mc.get_e3_lab_weights()[0], g[pre + "e3_lab"]))
+            ws["p3_lab_over_E"] = max(ws["p3_lab_over_E"], float(np.max(np.abs(mc.p3_lab_4vectors.pmu - g[pre + "p3_lab"])) / scale))
+            ws["p4_lab_over_E"] = max(ws["p4_lab_over_E"], float(np.max(np.abs(mc.p4_lab_4vectors.pmu - g[pre + "p4_lab"])) / scale))
+        r["scatter2to2 (9 cases: README snippet, 5 matrix elements, log sampling, moving target)"] = ws
         out[mode] = r
     out["tolerance"] = {"fp64_relative": 1e-9, "float32_attributes": 1.2e-7,
                         "decay_weights": "1e-9 + 4*2^-53/decay_prob (reported in units of that bound; <= 1 passes)"}
     worst = {m: max(v for c in out[m].values() for k, v in c.items() if isinstance(v, float) and "fraction" not in k and "units" not in k and "w32" not in k) for m in ("faithful", "fast")}
     out["worst_fp64_relative_error"] = worst
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "parity_r1.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "parity_r2.json"), "w"), indent=1)
     print(json.dumps(out["worst_fp64_relative_error"]))
     for m in ("faithful", "fast"):
         for c, v in out[m].items():
