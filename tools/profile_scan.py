@@ -57,8 +57,30 @@ for key, n_bins, ns in (("c5", 1000, 100), ("large", 10_000, 1000)):
         for _ in range(reps):
             rt.to_host(full)
         t_d2h = (time.perf_counter() - t0) / reps
-        res[proc] = {"call_ms": t_call * 1e3, "host_queue_ms": t_queue * 1e3, "device_ms": t_dev * 1e3, "d2h_map_ms": t_d2h * 1e3,
-                     "gather_and_rest_ms": (t_call - max(t_queue, t_dev) - t_d2h) * 1e3}
+        entry = {"call_ms": t_call * 1e3, "host_queue_ms": t_queue * 1e3, "device_ms": t_dev * 1e3, "d2h_map_ms": t_d2h * 1e3}
+        if world > 1:
+            # (4) the collective alone, ranks aligned by a barrier first: NCCL + torch launch latency without rank skew
+            n_loc = (200 + world - 1) // world
+            loc = torch.zeros((n_loc, 200), dtype=torch.float64, device=d.device)
+            flat = torch.empty((world * n_loc, 200), dtype=torch.float64, device=d.device)
+            for _ in range(3):
+                dist.all_gather_into_tensor(flat, loc)
+            t_coll = 0.0
+            for _ in range(reps):
+                dist.barrier(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dist.all_gather_into_tensor(flat, loc)
+                torch.cuda.synchronize()
+                t_coll += time.perf_counter() - t0
+            entry["all_gather_ms"] = t_coll / reps * 1e3
+            # (5) device time of every rank's share: the slowest rank sets the pace of the collective
+            tt = torch.tensor([t_dev * 1e3], dtype=torch.float64, device=d.device)
+            allt = torch.empty(world, dtype=torch.float64, device=d.device)
+            dist.all_gather_into_tensor(allt, tt)
+            entry["device_ms_per_rank"] = [round(float(x), 4) for x in allt.cpu()]
+        entry["unaccounted_ms"] = (t_call - max(t_queue, max(entry.get("device_ms_per_rank", [t_dev * 1e3])) * 1e-3) - t_d2h
+                                   - entry.get("all_gather_ms", 0.0) * 1e-3) * 1e3
+        res[proc] = entry
     out[key] = res
 if rank == 0:
     print(json.dumps(out))
