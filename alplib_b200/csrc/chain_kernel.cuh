@@ -331,14 +331,14 @@ int launch_chain(const char* what, const double* row_table, uint64_t n_rows, uin
     const int grid = grid_for(n, (int)a.tile_elems, ALPK_GRID_PER_SM);
     const bool inj = uniforms != nullptr;
     const bool fast = fast_mode != 0;
-    // the PAIRED / output-set specialisations exist for the production configuration (fast arithmetic, free-running RNG,
-    // no histogram)
+    // the PAIRED / output-set specialisations exist for the production configuration (fast arithmetic, free-running RNG);
+    // the row kernel takes it, with or without the fused histogram, whenever its geometry applies
     const bool paired = (n_samples % 2u) == 0u;
     const bool none = !out_energy && !out_flux && !decay_w32 && !scatter_w32 && !decay_w64 && !scatter_w64 && !event_w;
     const bool standard = out_energy && out_flux && !decay_w64 && !scatter_w64 && (stage < 1 || (decay_w32 && scatter_w32)) &&
                           (stage < 2 || event_w);
     const bool noevents = stage == 2 && out_energy && out_flux && decay_w32 && scatter_w32 && !decay_w64 && !scatter_w64 && !event_w;
-    if (fast && paired && !inj && !hist) {
+    if (fast && paired && !inj) {
         const int rc = launch_chain_rows<Prod>(what, a, stage, standard, noevents, none, rate, scratch, st);
         if (rc >= 0) return rc;
     }

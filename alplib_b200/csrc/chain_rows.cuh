@@ -17,9 +17,18 @@
 // decay_event_weight_coupled), and sample s of a row uses the same Philox counter / words, so both kernels produce the
 // same bits for every per-sample output; only the order of the rate sum differs.
 //
-// The fused-histogram launches stay with chain_kernel: its per-warp bin copies need many resident warps to hide the
-// shuffle latency of the aggregated adds, and this kernel's 16 warps / SM measured slower there (1.24 vs 1.0 ms, 50 bins).
+// Fused weighted histogram of E_a (HIST): np.histogram(E_a, edges, weights = weight of the last fused stage).  Each warp
+// owns `hist_cols` private COLUMNS of the bins in shared memory (cell = bins[warp][bin][col]); K = 32 / hist_cols lanes share
+// a column and take turns in K warp-synchronous phases, each lane doing plain read-modify-writes on its column: no atomics,
+// no shuffles, no branches (lanes whose turn it is not, and samples outside the edges, add into a per-lane trash cell).
+// The bin comes from a float spacing guess confirmed against the bin's edge pair (one 16-byte shared load, common.cuh
+// find_bin_pairs).  hist_cols is the largest power of two whose bins fit the CTA's shared-memory budget (50 bins: 16 columns,
+// K = 2).  Histograms with too many bins for four columns per warp keep ONE copy of the bins per CTA and use shared-memory
+// atomics (collisions are rare there).  The CTA's bins are merged into the output with one global atomic per non-empty bin,
+// so a spectrum is reproducible to rounding only (the rate sum stays bit-reproducible).  The match.any-aggregated adds of
+// chain_kernel measured 1.24 ms in this kernel (50 bins), the first, branchy version of the columns 0.67 ms.
 #pragma once
+#include <math_constants.h>
 #include <stdlib.h>
 
 #include "chain_kernel.cuh"
@@ -48,6 +57,7 @@ namespace alpk {
 #endif
 constexpr int kRowsThreads = ALPK_ROWS_THREADS;
 constexpr int kRowsUnroll = ALPK_ROWS_UNROLL;
+constexpr int kRowsHistSmem = 88 * 1024;    // dynamic shared memory of a HIST launch: 2 CTAs x (16 KB exp table + this) per SM
 constexpr uint32_t kRowsMinSamples = 256;   // shorter rows stay with the tile kernel (units would be mostly lane padding)
 // layout of the caller's scratch (>= ALPK_SCRATCH_DOUBLES doubles): [0, 2 kMaxPartials) block partials of the other kernels,
 // then the dynamic-unit counter, then the per-unit rate sums of this kernel
@@ -62,17 +72,44 @@ struct RowsGeom {
     uint32_t n_units;            // n_rows * chunks_per_row (<= kRowsMaxUnits)
     unsigned long long* counter; // dynamic unit counter (zeroed by the launcher), or NULL: static assignment
     double* unit_sums;           // [n_units] rate sum of every unit (STAGE 2)
+    uint32_t hist_cols;          // HIST: bin columns per warp (32 .. 2), or 0: one copy of the bins per CTA, shared atomics
 };
 
-template <class Prod, int STAGE, int OUT, bool SHORT, int ROUNDS>
+template <class Prod, int STAGE, int OUT, bool SHORT, int ROUNDS, bool HIST = false>
 __global__ void __launch_bounds__(kRowsThreads, ALPK_ROWS_MIN_BLOCKS)
 chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
     using namespace alp;
     constexpr int NP = Prod::NP;
     __shared__ double s_tab[alp::kExpTabSize];
+    extern __shared__ double2 s_rows_dyn[];          // HIST: edge pairs [nb], edges [n_edges], then the bins (hist_rows_doubles)
     for (int i = threadIdx.x; i < alp::kExpTabSize; i += blockDim.x) s_tab[i] = kExpTabDev[i];
-    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
+    const int n_hbins = HIST ? a.n_edges - 1 : 0;
+    const double2* const s_pairs = s_rows_dyn;
+    double* const s_edges = reinterpret_cast<double*>(s_rows_dyn) + 2 * n_hbins;
+    double* const s_bins = s_edges + (HIST ? ((a.n_edges + 1) & ~1) : 0);
+    const uint32_t hcols = HIST ? geo.hist_cols : 0u;             // columns per warp
+    const uint32_t hphases = hcols ? 32u / hcols : 0u;            // lanes per column = warp-synchronous phases
+    const uint32_t hwarp = HIST ? (uint32_t)n_hbins * hcols + 32u : 0u;   // cells per warp: bins x columns + one trash cell per lane
+    const int n_hcells = HIST ? (hcols ? (int)hwarp * (kRowsThreads / 32) : n_hbins) : 0;
+    double* my_col = s_bins;
+    double* my_trash = s_bins;
+    BinGuessF guess{0, 0.f, 0.f, 0.0, 0.0};
+    if (HIST) {
+        for (int i = threadIdx.x; i < a.n_edges; i += blockDim.x) s_edges[i] = __ldg(a.hist_edges + i);
+        for (int i = threadIdx.x; i < n_hbins; i += blockDim.x) {
+            const double hi = __ldg(a.hist_edges + i + 1);
+            s_rows_dyn[i] = make_double2(__ldg(a.hist_edges + i), i == n_hbins - 1 ? nextafter(hi, CUDART_INF) : hi);
+        }
+        for (int i = threadIdx.x; i < n_hcells; i += blockDim.x) s_bins[i] = 0.0;
+        __syncthreads();
+        guess = to_float_guess(detect_spacing(s_edges, a.n_edges), s_edges, a.n_edges);
+        if (hcols) {
+            my_col = s_bins + (size_t)(threadIdx.x >> 5) * hwarp + lane / hphases;
+            my_trash = s_bins + (size_t)(threadIdx.x >> 5) * hwarp + (uint32_t)n_hbins * hcols + lane;
+        }
+    }
+    __syncthreads();
     const uint32_t n_units = geo.n_units;
     const uint32_t n_warps = gridDim.x * (kRowsThreads / 32);
 
@@ -112,7 +149,9 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
         double acc = 0.0;
 
 #pragma unroll kRowsUnroll
-        for (uint32_t p = p_begin + lane; p < p_stop; p += 32u) {
+        // (HIST: warp-uniform trip count -- the column phases synchronise the warp --, lanes past the end are masked by `in`)
+        for (uint32_t p = p_begin + lane; HIST ? (p - lane < p_stop) : (p < p_stop); p += 32u) {
+            const bool in = !HIST || p < p_stop;
             // sample s: counter s>>1 = pair index, words (x,y) / (z,w)
             const Philox4 q = philox4x32_rk<ROUNDS>(p, 0u, rid, Prod::kTag, a.rk);
             double u[2], e[2], f[2], d64v[2], s64v[2], evv[2];
@@ -139,10 +178,44 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     evv[j] = decay_event_weight_plain(e[j], d32v[j], a.ev);
-                    acc += evv[j];
+                    if (HIST) acc += in ? evv[j] : 0.0; else acc += evv[j];
                 }
             }
-            if (OUT != kOutNone) {
+            if (HIST) {
+                // np.histogram(E_a, bins=edges, weights=<weight of the last fused stage>)
+                int hb[2];
+                double hw[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    hw[j] = STAGE >= 2 ? evv[j] : (STAGE == 1 ? (double)d32v[j] : f[j]);
+                    hb[j] = find_bin_pairs(e[j], s_pairs, n_hbins, guess);
+                }
+                if (__any_sync(0xffffffffu, (hb[0] == -2) | (hb[1] == -2))) {        // rare: the spacing guess missed
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) if (hb[j] == -2) hb[j] = find_bin(e[j], s_edges, a.n_edges);
+                }
+                if (!in) hb[0] = hb[1] = -1;
+                if (hcols) {
+                    // both samples in one bin: a single add, so that the two read-modify-writes below never alias
+                    const bool same = hb[1] == hb[0];
+                    hw[0] += same ? hw[1] : 0.0;
+                    double* const c0 = hb[0] >= 0 ? my_col + (uint32_t)hb[0] * hcols : my_trash;
+                    double* const c1 = (hb[1] >= 0 && !same) ? my_col + (uint32_t)hb[1] * hcols : my_trash;
+                    for (uint32_t ph = 0; ph < hphases; ++ph) {
+                        const bool act = (lane & (hphases - 1u)) == ph;
+                        double* const q0 = act ? c0 : my_trash;
+                        double* const q1 = act ? c1 : my_trash;
+                        const double v0 = *q0, v1 = *q1;
+                        *q0 = v0 + hw[0];
+                        *q1 = v1 + hw[1];
+                        __syncwarp();
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) if (hb[j] >= 0) atomicAdd(s_bins + hb[j], hw[j]);
+                }
+            }
+            if (OUT != kOutNone && in) {
                 // write-once outputs: streaming stores (evict-first in L2)
                 if (kAll || pe) { ALPK_ROWS_ST(pe, make_double2(e[0], e[1])); pe += 32; }
                 if (kAll || pf) { ALPK_ROWS_ST(pf, make_double2(f[0], f[1])); pf += 32; }
@@ -163,6 +236,17 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
         // (a warp that did not fetch -- next was already past the end -- ends with unit >= n_units)
         next = dynamic ? (cur_next < n_units ? n_warps + __shfl_sync(0xffffffffu, fetched, 0) : cur_next) : cur_next + n_warps;
         unit = cur_next < n_units ? (uint32_t)cur_next : n_units;
+    }
+    if (HIST) {
+        // the CTA's bins: warp copies and columns added in a fixed order, one global atomic per non-empty bin
+        __syncthreads();
+        const uint32_t per_bin = hcols ? hcols : 1u, copies = hcols ? kRowsThreads / 32 : 1;
+        for (int i = threadIdx.x; i < n_hbins; i += blockDim.x) {
+            double v = 0.0;
+            for (uint32_t w = 0; w < copies; ++w)
+                for (uint32_t c = 0; c < per_bin; ++c) v += s_bins[(size_t)w * hwarp + (size_t)i * per_bin + c];
+            if (v != 0.0) atomicAdd(a.hist + i, v);
+        }
     }
 }
 
@@ -220,6 +304,19 @@ inline int chain_rows_mode() {
     return e ? atoi(e) : 1;
 }
 
+// Dynamic shared memory of a HIST launch, in doubles: edge pairs [nb][2], edges [n_edges] (padded to even), then per warp
+// nb x cols bin cells + 32 trash cells -- or, cols == 0, one copy of the nb bins for the CTA.
+inline size_t hist_rows_doubles(int n_edges, uint32_t cols) {
+    const size_t nb = (size_t)n_edges - 1;
+    return 2 * nb + (((size_t)n_edges + 1) & ~(size_t)1) + (cols ? (nb * cols + 32) * (kRowsThreads / 32) : nb);
+}
+
+inline int hist_rows_mode() {
+    // ALPK_HIST_ROWS=0 keeps the fused-histogram launches on the tile kernel (A/B timing, kernel-vs-kernel test); default 1
+    const char* e = getenv("ALPK_HIST_ROWS");
+    return e ? atoi(e) : 1;
+}
+
 template <class Prod>
 int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool standard, bool noevents, bool none,
                       double* rate, double* scratch, cudaStream_t st) {
@@ -228,8 +325,18 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
     // the sample loop is compiled without the rare-mode tests: FP32 transcendentals and an np.float64 exposure stay with the
     // tile kernel
     if ((stage >= 1 && a.prop.fast != 1) || (stage >= 2 && a.ev.days_f64)) return -1;
-    const RowsGeom geo = rows_geometry(a.n_rows, a.n_samples, scratch, mode != 2);
+    RowsGeom geo = rows_geometry(a.n_rows, a.n_samples, scratch, mode != 2);
     if ((uint64_t)a.n_rows * geo.chunks_per_row > kRowsMaxUnits) return -1;          // (more rows than unit slots: tile kernel)
+    size_t smem = 0;
+    geo.hist_cols = 0;
+    if (a.hist) {
+        if (!hist_rows_mode()) return -1;
+        uint32_t cols = 32;
+        while (cols >= 4 && hist_rows_doubles(a.n_edges, cols) * sizeof(double) > (size_t)kRowsHistSmem) cols >>= 1;
+        geo.hist_cols = cols >= 4 ? cols : 0;
+        smem = hist_rows_doubles(a.n_edges, geo.hist_cols) * sizeof(double);
+        if (smem > (size_t)kRowsHistSmem) return -1;                                  // (too many bins: tile kernel / alpk_hist)
+    }
     // (the unit counter and the finalize kernel's arrival counter sit next to each other: one 16-byte memset)
     if (scratch) cudaMemsetAsync(scratch + kRowsCounterOffset, 0, 16, st);
     uint64_t blocks = ((uint64_t)geo.n_units + (kRowsThreads / 32) - 1) / (kRowsThreads / 32);
@@ -237,17 +344,23 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
     if (blocks > cap) blocks = cap;
     const int grid = (int)blocks;
     const bool sh = stage >= 1 && a.prop.short_lived;
-#define ALPK_ROWS_LAUNCH_R(S, O, R) { if (sh) chain_rows_kernel<Prod, S, O, true, R><<<grid, kRowsThreads, 0, st>>>(a, geo); \
-                                      else chain_rows_kernel<Prod, S, O, false, R><<<grid, kRowsThreads, 0, st>>>(a, geo); }
-#define ALPK_ROWS_LAUNCH(S, O) { if (a.rounds == 7) ALPK_ROWS_LAUNCH_R(S, O, 7) else ALPK_ROWS_LAUNCH_R(S, O, 10) }
-#define ALPK_ROWS_CASE(S)                                                  \
-    if (standard) ALPK_ROWS_LAUNCH(S, kOutStandard)                        \
-    else if (S == 2 && noevents) ALPK_ROWS_LAUNCH(S, kOutNoEvents)         \
-    else if (none) ALPK_ROWS_LAUNCH(S, kOutNone)                           \
-    else ALPK_ROWS_LAUNCH(S, kOutGeneric)
+#define ALPK_ROWS_LAUNCH_K(S, O, SH, R, H) {                                                                              \
+        auto kfn = chain_rows_kernel<Prod, S, O, SH, R, H>;                                                                \
+        if (H) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowsHistSmem);                      \
+        kfn<<<grid, kRowsThreads, smem, st>>>(a, geo); }
+#define ALPK_ROWS_LAUNCH_R(S, O, R, H) { if (sh) ALPK_ROWS_LAUNCH_K(S, O, true, R, H) else ALPK_ROWS_LAUNCH_K(S, O, false, R, H) }
+#define ALPK_ROWS_LAUNCH(S, O, H) { if (a.rounds == 7) ALPK_ROWS_LAUNCH_R(S, O, 7, H) else ALPK_ROWS_LAUNCH_R(S, O, 10, H) }
+#define ALPK_ROWS_CASE(S)                                                         \
+    if (a.hist) { if (none) ALPK_ROWS_LAUNCH(S, kOutNone, true)                   \
+                  else ALPK_ROWS_LAUNCH(S, kOutGeneric, true) }                   \
+    else if (standard) ALPK_ROWS_LAUNCH(S, kOutStandard, false)                   \
+    else if (S == 2 && noevents) ALPK_ROWS_LAUNCH(S, kOutNoEvents, false)         \
+    else if (none) ALPK_ROWS_LAUNCH(S, kOutNone, false)                           \
+    else ALPK_ROWS_LAUNCH(S, kOutGeneric, false)
     if (stage == 0) { ALPK_ROWS_CASE(0) } else if (stage == 1) { ALPK_ROWS_CASE(1) } else { ALPK_ROWS_CASE(2) }
 #undef ALPK_ROWS_LAUNCH
 #undef ALPK_ROWS_LAUNCH_R
+#undef ALPK_ROWS_LAUNCH_K
 #undef ALPK_ROWS_CASE
     if (check_launch(what)) return 1;
     if (stage == 2) {

@@ -101,6 +101,34 @@ __device__ __forceinline__ int find_bin_guess(double x, const double* edges, int
     return find_bin(x, edges, n_edges);
 }
 
+// Branch-free bin lookup for the fused histogram of the row kernel.  The spacing guess is evaluated in float (one FFMA on x
+// or on log2 x, floor), the bin's edge pair {edges[b], edges[b+1]} comes with ONE 16-byte shared load from `pairs`
+// (pairs[nb-1].y = nextafter(edges[nb], +inf): np.histogram's closed last bin), and two compares confirm the bin.  Returns
+// the bin, -1 when x lies outside [edges[0], edges[nb]] (or is NaN), or -2 when x is in range but the guess missed (float
+// rounding next to an edge, irregular edges): the caller redoes those rare lanes with find_bin().
+struct BinGuessF { int mode; float off, scale; double lo, hi; };
+
+__device__ __forceinline__ BinGuessF to_float_guess(const BinGuess& g, const double* s_edges, int n_edges) {
+    BinGuessF f;
+    f.mode = g.mode;
+    f.scale = (float)g.scale;
+    f.off = (float)(-g.x0 * g.scale);
+    f.lo = s_edges[0];
+    f.hi = s_edges[n_edges - 1];
+    return f;
+}
+
+__device__ __forceinline__ int find_bin_pairs(double x, const double2* pairs, int nb, const BinGuessF& g) {
+    const float xf = (float)x;
+    const float v = g.mode == 2 ? __log2f(xf) : xf;
+    int b = __float2int_rd(fmaf(v, g.scale, g.off));
+    b = max(0, min(b, nb - 1));
+    const double2 e = pairs[b];
+    const bool hit = (x >= e.x) & (x < e.y);
+    const bool inside = (x >= g.lo) & (x <= g.hi);
+    return hit ? b : (inside ? -2 : -1);
+}
+
 // Add w to bins[b] for the valid lanes of a fully converged warp, without atomics: `bins` is private to this warp.  Lanes
 // that hit the same bin are combined first (match.any); the leader of each group does a plain read-modify-write.  Two
 // schedules: few distinct bins -> one masked butterfly sum per bin; many distinct bins -> the leaders walk their peers.

@@ -638,17 +638,19 @@ def test_propagate_iso_vol_int_large(A):
     assert np.max(np.abs(vol[sel] / plain[sel] - 1)) < 0.03
 
 
+@pytest.mark.parametrize("hist_rows", ["1", "0"])         # fused histogram in the row kernel / in the tile kernel
 @pytest.mark.parametrize("ns", [999, 1000, 20000])      # odd: generic kernel; even: paired kernel, short and long rows
-def test_chain_fused_histogram(A, ns):
+def test_chain_fused_histogram(A, ns, hist_rows, monkeypatch):
     """Event-weighted E_a spectrum accumulated inside the chain kernel == np.histogram of the materialised arrays: linear,
-    logarithmic and irregular edges (spacing guess on / off), few bins (one copy per warp, aggregated adds) and many
-    (one copy per CTA)."""
+    logarithmic and irregular edges (spacing guess on / off), few bins (row kernel: private bin columns per warp, 32 / 16
+    columns; tile kernel: one copy per warp, aggregated adds) and many (one copy per CTA, shared atomics)."""
     from alplib_b200.reduce import histogram
+    monkeypatch.setenv("ALPK_HIST_ROWS", hist_rows)
     pf = _c2_flux(150 if ns < 20000 else 40)
     fl = A.FluxComptonIsotropic(pf, A.Material("W"), axion_mass=1.5, axion_coupling=3e-6, n_samples=ns, seed=8, **GEOM)
     fl.simulate()
     irregular = np.array([0.0, 1.5, 1.6, 2.0, 7.0, 7.5, 40.0, 300.0, 301.0, 1000.0])
-    for edges in (np.linspace(0.0, 1000.0, 51), np.logspace(0, 3, 33), irregular, np.logspace(0, 3, 2001)):
+    for edges in (np.linspace(0.0, 1000.0, 51), np.logspace(0, 3, 33), irregular, np.logspace(0, 3, 201), np.logspace(0, 3, 2001)):
         rate, evw = fl.chain(100, 5.0, materialize=True, hist_edges=edges)
         h = fl.last_hist.cpu().numpy()
         ref = O.histogram(np.asarray(fl.axion_energy), evw.cpu().numpy(), edges)
