@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ALPK_LIB_PATH") or os.path.join(_HERE, "libalpk.so")   # override: kernel-variant experiments
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["alpk_core.cu", "alpk_decay.cu", "alpk_epm.cu", "alpk_pairann.cu", "alpk_scan.cu", "alpk_misc.cu", "alpk_meson.cu",
-           "alpk_scatter2.cu"]
+           "alpk_scatter2.cu", "alpk_peer.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
 
@@ -86,6 +86,13 @@ class Scatter2T(C.Structure):
 
 
 MESON3_NP = 13
+PEER_MAX_RANKS = 16
+PEER_MAX_PARTS = 8
+PEER_HANDLE_BYTES = 64
+
+
+class PeerT(C.Structure):      # alpk_peer_t
+    _fields_ = [("windows", C.c_void_p * PEER_MAX_RANKS), ("rank", C.c_int), ("n_ranks", C.c_int), ("capacity", C.c_uint64)]
 
 
 def sources():
@@ -193,6 +200,14 @@ _SIGNATURES = {
     "alpk_scale": ([_P, _U64, _D, _P, _P], _I),
     "alpk_hist": ([_P, _P, _P, _U64, _P, _I, _P, _P], _I),
     "alpk_sum": ([_P, _U64, _P, _P, _P], _I),
+    "alpk_peer_window_bytes": ([_U64], _U64),
+    "alpk_peer_window_create": ([_U64, C.POINTER(C.c_void_p), C.c_char_p], _I),
+    "alpk_peer_window_open": ([C.c_char_p, C.POINTER(C.c_void_p)], _I),
+    "alpk_peer_window_close": ([_P], _I),
+    "alpk_peer_window_destroy": ([_P], _I),
+    "alpk_peer_status": ([C.POINTER(PeerT), C.POINTER(_U64), C.POINTER(_I), _P], _I),
+    "alpk_peer_all_reduce_sum": ([C.POINTER(PeerT), C.POINTER(C.c_void_p), C.POINTER(_U32), _I, _P, _U64, _P], _I),
+    "alpk_peer_all_gather_rows": ([C.POINTER(PeerT), _P, _U32, _U32, _U32, _U32, _U32, _P, _U64, _P], _I),
     "alpk_fp64_peak": ([_U64, _I, _P, _P], _I),
     "alpk_exp_peak": ([_I, _U64, _I, _P, _P], _I),
 }

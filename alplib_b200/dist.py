@@ -1,5 +1,7 @@
 """Multi-GPU plumbing: one process per GPU (torchrun), work sharded by flux-row range or by scan-grid row, one small
-all-reduce of the merged rates / histograms / rate maps (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+merge of the rates / histograms / rate maps: a single libalpk kernel per rank over NVLink peer memory (peer.py,
+csrc/alpk_peer.cu) when the ranks share a node, torch.distributed's all-reduce / all-gather otherwise (NCCL; gloo in the
+CPU tests).
 
 No per-sample data crosses the interconnect: every flux row, sample and grid point is independent, and
 the Philox variates are keyed by the GLOBAL row index, so results do not depend on the number of ranks.
@@ -83,12 +85,19 @@ def all_reduce_sum(t, group=None):
 
 def merged_rates_and_hists(rates, hists=(), group=None):
     """The path's one exchange step: total rates and binned spectra of all ranks merged with ONE all-reduce
-    over the packed buffer [rate_0, rate_1, ... || hist_0 || hist_1 ...] (NCCL over NVLink on the GPU box).
+    over the packed buffer [rate_0, rate_1, ... || hist_0 || hist_1 ...].  On one node this is a single kernel per rank
+    over NVLink peer memory (peer.PeerGroup.all_reduce_sum: the segments are packed, pushed, and summed in rank order by the
+    kernel itself -- every rank gets the same bits); otherwise one NCCL all-reduce of the concatenated buffer.
     rates: 1-element float64 tensors; hists: float64 tensors.  Returns (rates tensor [n_rates], list of merged hists) --
     views of the packed buffer, on the tensors' device."""
+    from .peer import peer_group
     parts = [r.reshape(-1) for r in rates] + [h.reshape(-1) for h in hists]
-    buf = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
-    all_reduce_sum(buf, group)
+    pg = peer_group(group, parts[0])
+    if pg is not None and pg.fits_reduce(sum(int(p.numel()) for p in parts)):
+        buf = pg.all_reduce_sum([p.contiguous() for p in parts])
+    else:
+        buf = torch.cat(parts) if len(parts) > 1 else parts[0].clone()
+        all_reduce_sum(buf, group)
     n_r = len(rates)
     out_h, pos = [], n_r
     for h in hists:

@@ -256,6 +256,26 @@ class Runtime:
         return (dev[0:k * 8].view(torch.float64), dev[ow:ow + k * 8].view(torch.float64),
                 dev[oi:oi + k * 4].view(torch.int32), k)
 
+    def capture(self, fn, warmup=2):
+        """Capture the launch sequence of `fn()` in a CUDA graph: (graph, fn's return value).  `graph.replay()` re-runs every
+        kernel of the sequence with one host call -- for launch-bound loops (a small job repeated many times, a sharded job
+        whose per-rank kernels last microseconds).  fn must be free of host synchronisation (no .item(), no host arrays out)
+        and of first-use uploads: it is run `warmup` times on a side stream first, which also fills the table caches.  The
+        tensors fn returns live in the graph's memory pool and are rewritten by every replay.  Peer-window merges
+        (peer.PeerGroup) may be part of fn; every rank then has to capture and replay in step."""
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn()
+        return graph, out
+
     def activate(self):
         """Context manager making this runtime's device current (a no-op object when it already is)."""
         if torch.cuda.current_device() == self.index:

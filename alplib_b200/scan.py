@@ -133,7 +133,8 @@ def scan_rates_distributed(process, photon_flux, target, ma_grid, g_grid, group=
     GPU).  Masses are dealt round-robin (rank r takes ma[r::world]): the cost of a mass row is very uneven -- stable
     ALPs (m_a < 2 m_e for the electron coupling) are skipped by the kernel, heavy ones have few rows above threshold --
     and contiguous blocks would leave some ranks idle.  Every rank returns the full map; the only communication is one
-    all-gather of the ranks' disjoint row blocks (NCCL over NVLink on the GPU box)."""
+    all-gather of the ranks' disjoint rows: on one node a single kernel per rank that pushes its rows into every rank's peer
+    window over NVLink, already interleaved (peer.PeerGroup.all_gather_rows); otherwise one NCCL all_gather_into_tensor."""
     rank, nranks = _world(group)
     ma = np.ascontiguousarray(ma_grid, dtype=np.float64).ravel()
     g = np.ascontiguousarray(g_grid, dtype=np.float64).ravel()
@@ -153,6 +154,12 @@ def scan_rates_distributed(process, photon_flux, target, ma_grid, g_grid, group=
     n_ma, n_g = int(ma.shape[0]), int(g.shape[0])
     local = scan_rates(process, photon_flux, target, ma[rank::nranks], g, **kw)
     rt = Runtime.get(local.device)
+    from .peer import peer_group
+    pg = peer_group(group, local)
+    if pg is not None and pg.fits_gather(n_ma * n_g):
+        with rt.activate():
+            full = pg.all_gather_rows(local, rank, nranks, n_ma)
+        return rt.to_host(full)
     # every rank's block padded to the same number of rows -> ONE all_gather_into_tensor (a single NCCL call, no per-rank
     # output list), one pinned D2H of the gathered blocks; the round-robin interleave is undone on the host (a reshape)
     n_loc = (n_ma + nranks - 1) // nranks

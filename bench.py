@@ -404,7 +404,7 @@ def run_gpu(args):
 
     # ---- (m_a, g) scans: BASELINE config 5 and a 100x larger one, masses dealt round-robin over the ranks ----------------
     if want("scan"):
-        for key, n_bins, ns, reps in (("scan", 1000, 100, 3), ("scan_large", 10_000, 1000, 1)):
+        for key, n_bins, ns, reps in (("scan", 1000, 100, 20), ("scan_large", 10_000, 1000, 2)):
             try:
                 extras[key] = scan_leg(A, W, n_bins, ns, reps, barrier, max_over_ranks)
             except Exception as exc:          # noqa: BLE001
@@ -436,6 +436,8 @@ def run_gpu(args):
         out["bench_wall_s"] = time.perf_counter() - t_start
         print(json.dumps(out))
     if world > 1:
+        from alplib_b200 import peer
+        peer.reset()
         dist.destroy_process_group()
 
 
@@ -596,7 +598,10 @@ def strong_leg(A, D, rt, W, Ar, rank, world, barrier, max_over_ranks):
     C2 job and an 8x larger one (8e4 bins); on N > 1 rank 0 afterwards runs the whole job alone, which gives the strong-scaling
     speed-up inside one run."""
     import torch
-    out = {"collective": "one all_reduce(sum, f64) of [2 rates || 50 histogram bins] per job (dist.merged_rates_and_hists)",
+    from alplib_b200.peer import peer_group
+    merge_kind = ("one libalpk kernel per rank over NVLink peer memory (alpk_peer_all_reduce_sum: push, signal, wait, fixed-order sum)"
+                  if peer_group(None, rt.empty(1)) is not None else "one NCCL all_reduce")
+    out = {"collective": "merge of [2 rates || 50 histogram bins] per job (dist.merged_rates_and_hists): " + merge_kind,
            "sharding": "contiguous blocks of KEPT rows per rank (dist.shard_flux), Philox keys = global row ids"}
     d_edges = rt.upload(HIST_EDGES)
 
@@ -632,10 +637,30 @@ def strong_leg(A, D, rt, W, Ar, rank, world, barrier, max_over_ranks):
         sync()
         return e0.elapsed_time(e1) / reps, rates, hists
 
+    def timed_graph(c, p, gp, merge, reps, sync):
+        # the same job as ONE CUDA graph per rank (Runtime.capture): a single host call replays the ~10 launches, merge included
+        graph, (rates, hists) = rt.capture(lambda: job(c, p, gp, merge))
+        for _ in range(3):
+            graph.replay()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+        sync()
+        return e0.elapsed_time(e1) / reps, rates, hists
+
     for key, n_bins, reps in (("c2", N_BINS, 50), ("c2x8", 8 * N_BINS, 10)):
         c, p, gp = make(n_bins, rank, world)
         ms, rates, hists = timed(c, p, gp, world > 1, reps, barrier)
         ms = max_over_ranks(ms)
+        try:
+            ms_g, rates_g, _ = timed_graph(c, p, gp, world > 1, reps, barrier)
+            ms_g = max_over_ranks(ms_g)
+            graph_rate_ok = abs(float(rates_g[0].item()) / float(rates[0].item()) - 1.0) < 1e-12
+        except Exception as exc:      # noqa: BLE001
+            ms_g, graph_rate_ok = None, repr(exc)[:200]
         n_job = 0
         # samples of the whole job = kept Compton rows x n_samples + kept Primakoff rows (identical on every rank)
         pf = c2_spectrum(n_bins)
@@ -643,7 +668,9 @@ def strong_leg(A, D, rt, W, Ar, rank, world, barrier, max_over_ranks):
             + int(np.count_nonzero(pf[:, 0] >= MA_P))
         entry = {"n_bins": n_bins, "samples_per_job": n_job, "ms_per_job": ms, "value": n_job / (ms * 1e-3), "unit": UNIT,
                  "rows_this_rank": int(c._inputs[2]), "rates": [float(x) for x in rates.cpu()],
-                 "hist_sum_over_rate": float(hists[0].sum().item() / max(float(rates[0].item()), 1e-300))}
+                 "hist_sum_over_rate": float(hists[0].sum().item() / max(float(rates[0].item()), 1e-300)),
+                 "ms_per_job_graph": ms_g, "value_graph": (n_job / (ms_g * 1e-3)) if ms_g else None,
+                 "graph_rate_equals_eager": graph_rate_ok}
         del c, p, gp
         if world > 1:
             barrier()
@@ -653,6 +680,14 @@ def strong_leg(A, D, rt, W, Ar, rank, world, barrier, max_over_ranks):
                 entry["ms_per_job_one_rank"] = ms1
                 entry["speedup_vs_one_rank"] = ms1 / ms
                 entry["efficiency"] = ms1 / ms / world
+                if ms_g:
+                    try:
+                        ms1g, _, _ = timed_graph(c1, p1, g1, False, max(3, reps // 3), torch.cuda.synchronize)
+                        entry["ms_per_job_one_rank_graph"] = ms1g
+                        entry["speedup_vs_one_rank_graph"] = ms1g / ms_g
+                        entry["efficiency_graph"] = ms1g / ms_g / world
+                    except Exception as exc:      # noqa: BLE001
+                        entry["ms_per_job_one_rank_graph"] = repr(exc)[:200]
                 entry["rate_vs_one_rank_rel_diff"] = abs(float(rates[0].item()) / float(rates1[0].item()) - 1.0)
                 del c1, p1, g1
             barrier()
@@ -684,7 +719,7 @@ def scan_leg(A, W, n_bins, n_samples, reps, barrier, max_over_ranks):
             "seconds_per_map_pair": dt / reps,
             "config": f"ma=logspace(-2,2,200), g=logspace(-9,-3,200), {n_bins} bins x ({n_samples} Compton + 1 Primakoff) samples, "
                       "decays(100 d, 5 MeV); host grids in, host maps out (end to end); masses dealt round-robin over the ranks, "
-                      "one all-gather per map; grid tables and flux columns cached on the device across calls",
+                      "one all-gather per map (a libalpk kernel over NVLink peer memory when the ranks share a node); grid tables and flux columns cached on the device across calls",
             "nonzero_points": [int(np.count_nonzero(mc)), int(np.count_nonzero(mp_))]}
 
 

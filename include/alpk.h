@@ -345,6 +345,44 @@ int alpk_fp64_peak(uint64_t iters, int blocks, double* out, void* stream);
 /* FP64 exp throughput: `blocks` CTAs x 256 threads x 4*iters evaluations; kind 0 = library exp, 1 = the fast-mode table exp */
 int alpk_exp_peak(int kind, uint64_t iters, int blocks, double* out, void* stream);
 
+/* ---- peer windows: the path's one exchange step over NVLink peer memory ------------------------------------------------
+ * The reference is single-process; its only cross-sample steps are np.sum / np.histogram of the per-sample weights
+ * (generators.py:27-30, 48-52) and the user's loop over a (m_a, g) grid (README.md:199-226).  When those are sharded over
+ * GPUs (one process per GPU), the ranks' partial [rates || histogram bins] or their rows of a rate map are merged by ONE
+ * single-CTA kernel per rank that pushes its values into every rank's window with NVLink stores, signals, waits for the
+ * other ranks' signals and combines the slots in rank order (alpk_peer.cu) -- no library collective, no host round trip,
+ * replayable from a captured CUDA graph.  Every rank gets the same bits, independent of arrival order.
+ *
+ * A window is created by its owner (cudaMalloc + cudaIpcGetMemHandle), the 64-byte handle is sent to the other processes
+ * of the node by any means (alplib_b200.peer uses torch.distributed's object all-gather), and they map it with
+ * alpk_peer_window_open (cudaIpcOpenMemHandle; peer access is enabled on demand).  All ranks must issue the same sequence
+ * of merges on a window, each rank on ONE stream.  capacity = doubles per payload half: an all-reduce needs
+ * n_ranks * n_total <= capacity, an all-gather n_total_rows * row_len <= capacity.  timeout_ns = 0 -> 10 s; a merge that
+ * times out (a rank died or never launched) writes NaN to `out` and sets the status word -- it does not hang the GPU. */
+#define ALPK_PEER_MAX_RANKS 16
+#define ALPK_PEER_MAX_PARTS 8
+#define ALPK_PEER_HANDLE_BYTES 64
+typedef struct {
+    void* windows[ALPK_PEER_MAX_RANKS];   /* device pointers of every rank's window as mapped in THIS process (own included) */
+    int rank, n_ranks;
+    uint64_t capacity;                    /* doubles per payload half (the same on every rank) */
+} alpk_peer_t;
+uint64_t alpk_peer_window_bytes(uint64_t capacity_doubles);
+int alpk_peer_window_create(uint64_t capacity_doubles, void** h_window, unsigned char* h_handle);
+int alpk_peer_window_open(const unsigned char* h_handle, void** h_window);
+int alpk_peer_window_close(void* d_window);        /* a window mapped with _open */
+int alpk_peer_window_destroy(void* d_window);      /* a window made with _create */
+/* number of merges completed on this rank's window and its status (0 ok, 1 a merge timed out); synchronises `stream` */
+int alpk_peer_status(const alpk_peer_t* h_peer, uint64_t* h_epoch, int* h_status, void* stream);
+/* out[n_total] = sum over ranks of the concatenation of the n_parts segments (h_parts[i]: device pointer, h_part_len[i]
+ * doubles), added in rank order */
+int alpk_peer_all_reduce_sum(const alpk_peer_t* h_peer, const double* const* h_parts, const uint32_t* h_part_len, int n_parts,
+                             double* out, uint64_t timeout_ns, void* stream);
+/* out[n_total_rows][row_len]: local row i of local[n_local_rows][row_len] is global row row_start + i * row_stride */
+int alpk_peer_all_gather_rows(const alpk_peer_t* h_peer, const double* local, uint32_t n_local_rows, uint32_t row_len,
+                              uint32_t row_start, uint32_t row_stride, uint32_t n_total_rows, double* out,
+                              uint64_t timeout_ns, void* stream);
+
 /* sum of a f64 array (deterministic two-stage) */
 int alpk_sum(const double* x, uint64_t n, double* out, double* scratch, void* stream);
 

@@ -41,6 +41,8 @@ def main():
     n = sum(ops.values())
     fp64 = sum(v for k, v in ops.items() if k in ("DFMA", "DMUL", "DADD", "DSETP"))
     cost = n + fp64 + 3 * ops.get("IMAD.WIDE", 0) + 7 * ops.get("MUFU", 0)
+    if "--json" in sys.argv:                        # (--json: stdout is the JSON document alone, the summary goes to stderr)
+        sys.stdout, real_stdout = sys.stderr, sys.stdout
     print(f"executed warp-instructions (whole kernel): {tot}; most executed instruction: {mx}")
     print(f"hot path (>= {frac} of max): {n:.1f} instructions per trip, FP64 {fp64:.1f}, other {n - fp64:.1f}; "
           f"issue-cost model {cost:.0f} cycles per trip")
@@ -81,7 +83,7 @@ def main():
                "duration_ms_under_ncu": dur / 1e3 if dur and unit("gpu__time_duration.sum") in ("us", "usecond") else dur,
                "local_memory_sectors": (fl("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum") or 0) + (fl("l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum") or 0),
                "top_stalls": {k: round(v, 2) for v, k in stl[:8]}}
-        print(json.dumps(out, indent=1))
+        real_stdout.write(json.dumps(out, indent=1) + "\n")
         return
     if "--list" in sys.argv:
         for r in hot:
