@@ -157,7 +157,7 @@ scan_kernel(const ScanArgs a) {
         double t, bo = 0.0;
         if (FAST) {
             // E_a <= m_a: the reference gives surv = exp(-inf) = 0 (v = 0) or NaN (E_a < m_a); 1/p_a = inf / NaN
-            t = d > 1e-300 ? rsqrt_fast(d) : (d > 0.0 ? rsqrt(d) : ((d == 0.0) ? INFINITY : NAN));   // as propagate_sample_fast
+            t = d > 1e-300 ? rsqrt_fast1(d) : (d > 0.0 ? rsqrt(d) : ((d == 0.0) ? INFINITY : NAN));   // as propagate_sample_fast
         } else {
             const double pa = sqrt(d);
             t = pa / ea;                 // v_a
@@ -232,8 +232,8 @@ scan_kernel(const ScanArgs a) {
 #pragma unroll 2
             for (int k = lane; k < n_live; k += 32) {
                 const double t = s_t[k];
-                const double surv = exp_fast_core(k1 * t, s_tab);
-                const double dec = 1 - exp_fast_core(k2 * t, s_tab);
+                const double surv = exp_surv(k1 * t, s_tab);
+                const double dec = 1 - exp_dec(k2 * t, s_tab);
                 const double s64 = (resc * s_wh[k]) * surv;
                 const double d64 = s64 * dec;                                         // fluxes.py:64
                 const float d32 = (float)d64 * G.geom32;                              // prop_cast_fast (:159-162)
@@ -249,7 +249,7 @@ scan_kernel(const ScanArgs a) {
                     dec = (double)(-expm1f((float)k2 * tf32));
                 } else if (FAST) {
                     const double t = s_t[k];
-                    if (t <= tf) { surv = exp_fast_core(k1 * t, s_tab); dec = 1 - exp_fast_core(k2 * t, s_tab); }
+                    if (t <= tf) { surv = exp_surv(k1 * t, s_tab); dec = 1 - exp_dec(k2 * t, s_tab); }
                     else { surv = exp(k1 * t); dec = 1 - exp(k2 * t); }
                 } else {
                     const double va = s_t[k];
