@@ -257,11 +257,16 @@ def lib():
     return L
 
 
+_fns = {}
+
+
 def call(name, *args):
-    L = lib()
-    rc = getattr(L, name)(*args)
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = getattr(lib(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise AlpkError(f"{name} failed ({rc}): {L.alpk_last_error().decode(errors='replace')}")
+        raise AlpkError(f"{name} failed ({rc}): {lib().alpk_last_error().decode(errors='replace')}")
 
 
 def launch_count():

@@ -102,6 +102,15 @@ class _EventGenerator:
         self._last_decay = (ev, self.flux._epoch)
         return rate
 
+    def decays_async(self, days_exposure, threshold):
+        """decays() without the wait: queues the kernels and the device -> host copy of the rate and returns a
+        runtime.PendingValue; `.result()` (or float()) gives what decays() returns.  A loop over many jobs that reads each
+        rate one job late keeps the GPU busy while the host prepares the next job."""
+        from .runtime import PendingValue
+        rate = self.decays_device(days_exposure, threshold)
+        with self.flux._rt.activate():
+            return PendingValue(rate)
+
     def _scatter(self, kind, xs, ntargets, days_exposure, threshold):
         fl = self.flux
         fl._ensure_production()

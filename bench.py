@@ -261,6 +261,13 @@ def run_gpu(args):
     rate_bufs = [torch.zeros(2, dtype=torch.float64, device=rt.device) for _ in range(2)]   # double-buffered for the async merge
     pending = []
     pass_no = [0]
+    pg = None
+    if world > 1:
+        from alplib_b200.peer import peer_group
+        pg = peer_group(None, rates)
+        merge_stream = torch.cuda.Stream()
+        ev_ready = [torch.cuda.Event() for _ in range(2)]
+        ev_merged = [torch.cuda.Event() for _ in range(2)]
     n_kev = min(max(args.steps, 1), 16)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_kev)]
 
@@ -274,23 +281,37 @@ def run_gpu(args):
             rates[0:1].copy_(r1)
             rates[1:2].copy_(r2)
             return
-        # the path's only exchange: the merged rates of every pass (NCCL over NVLink).  The all-reduce is issued
-        # asynchronously on NCCL's stream and joined one pass later, so its latency overlaps the next pass's kernels
-        buf = rate_bufs[pass_no[0] & 1]
+        # the path's only exchange: the merged rates of every pass.  Ranks on one node: ONE libalpk kernel per rank over NVLink
+        # peer memory (alpk_peer_all_reduce_sum), issued on a side stream right behind the chain kernel and joined one pass
+        # later, so its NVLink round trip overlaps the next pass's kernels; otherwise an asynchronous NCCL all-reduce
+        k = pass_no[0] & 1
         pass_no[0] += 1
-        buf[0:1].copy_(r1)
-        buf[1:2].copy_(r2)
-        pending.append((dist.all_reduce(buf, async_op=True), buf))
+        if pg is not None:
+            cur = torch.cuda.current_stream()
+            ev_ready[k].record(cur)
+            merge_stream.wait_event(ev_ready[k])
+            with torch.cuda.stream(merge_stream):
+                pg.all_reduce_sum([r1, r2], out=rate_bufs[k])
+                ev_merged[k].record(merge_stream)
+            pending.append((ev_merged[k], rate_bufs[k], (r1, r2)))        # (the inputs stay referenced until the join)
+        else:
+            buf = rate_bufs[k]
+            buf[0:1].copy_(r1)
+            buf[1:2].copy_(r2)
+            pending.append((dist.all_reduce(buf, async_op=True), buf, None))
         if len(pending) > 1:
-            w, b = pending.pop(0)
-            w.wait()                           # stream-side join: the compute stream waits, the host does not
-            rates.copy_(b)
+            join(*pending.pop(0))
+
+    def join(w, b, _keep):
+        if pg is not None:
+            torch.cuda.current_stream().wait_event(w)      # stream-side join: the compute stream waits, the host does not
+        else:
+            w.wait()
+        rates.copy_(b)
 
     def drain():
         while pending:
-            w, b = pending.pop(0)
-            w.wait()
-            rates.copy_(b)
+            join(*pending.pop(0))
 
     def step(kpair=None):
         for p in range(PASSES_PER_STEP):
@@ -373,6 +394,43 @@ def run_gpu(args):
         del p, c
     extras = {}
 
+    # ---- the same passes with every rate read ONE PASS LATE (EventGenerator.decays_async): host set-up of pass k+1 overlaps the
+    # kernels of pass k; every pass still uploads its host tables and brings its two rates back to the host
+    if want("e2e_variants"):
+        def pipelined_pass(prev):
+            c = A.FluxComptonIsotropic(pf, W, axion_mass=MA_C, axion_coupling=G_C, n_samples=N_SAMPLES, seed=SEED, **GEOM)
+            c.row_offset = rank * N_BINS
+            c.simulate(); c.propagate()
+            pc = A.ElectronEventGenerator(c, Ar).decays_async(DAYS, THR)
+            p = A.FluxPrimakoffIsotropic(pf, W, axion_mass=MA_P, axion_coupling=G_P, **GEOM)
+            p.simulate(); p.propagate()
+            pp = A.PhotonEventGenerator(p, Ar).decays_async(DAYS, THR)
+            got = (prev[0].result(), prev[1].result()) if prev is not None else None
+            return (pp, pc), got
+        try:
+            prev = None
+            for _ in range(E2E_PASSES_PER_STEP):
+                prev, got = pipelined_pass(prev)
+            prev[0].result(); prev[1].result()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                prev = None
+                for _p in range(E2E_PASSES_PER_STEP):
+                    prev, got = pipelined_pass(prev)
+                got = (prev[0].result(), prev[1].result())          # the step ends with its last rates on the host
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            extras["e2e_pipelined"] = {"value": world * n_pass * E2E_PASSES_PER_STEP * e2e_steps / dt, "unit": UNIT,
+                                       "h2d_bytes_per_step": e2e["e2e"]["h2d_bytes_per_step"],
+                                       "d2h_bytes_per_step": 16 * E2E_PASSES_PER_STEP, "steps": e2e_steps,
+                                       "passes_per_step": E2E_PASSES_PER_STEP, "timed_region_s": dt,
+                                       "api": "as `e2e`, but the rates come back through EventGenerator.decays_async() and are read "
+                                              "one pass late (pinned D2H + event per rate)",
+                                       "rates": [float(got[0]), float(got[1])]}
+        except Exception as exc:      # noqa: BLE001
+            extras["e2e_pipelined"] = {"error": repr(exc)[:300]}
+
     # ---- per-sample arrays all the way to NumPy (what a script that reads flux.axion_energy etc. pays) ----------------
     if want("host_arrays") and rank == 0:
         try:
@@ -428,6 +486,10 @@ def run_gpu(args):
                "gpu_launches": int(launches), "passes_per_step": PASSES_PER_STEP, "ms_per_pass": ms_total / (args.steps * PASSES_PER_STEP),
                "samples_per_step": world * n_pass * PASSES_PER_STEP, "timed_region_s": ms_total * 1e-3, "rates": final_rates,
                "rng": f"Philox4x32-{comp.rng_rounds} production stream (alplib_b200.config.PHILOX_ROUNDS), precision={comp.precision}",
+               "merge_step": ("none (one rank)" if world == 1 else
+                              "merged rates of every pass: " + ("one libalpk kernel per rank over NVLink peer memory (alpk_peer_all_reduce_sum) "
+                                                                "on a side stream, joined one pass later" if pg is not None else
+                                                                "asynchronous NCCL all-reduce, joined one pass later")),
                "roofline": roofline, "cpu_baseline": cpu_baseline}
         for k in ("e2e_eager", "e2e_fused"):
             if k in e2e:

@@ -80,6 +80,9 @@ def test_c1_readme_example(A):
     assert isinstance(rate, np.float64)
     assert rate == pytest.approx(284.1535949707031, rel=2 * F32)
     assert max_rel(gen.decay_weights, g["decay_weights"]) <= 2 * F32
+    pending = gen.decays_async(100, 5.0)                    # the same rate, read late (pinned copy + event)
+    later = A.PhotonEventGenerator(fl, A.Material("Ar")).decays(50, 5.0)          # other work queued in between
+    assert pending.result() == rate and float(pending) == float(rate) and pending.done() and later < rate
     ipr = gen.inverse_primakoff(1e-5, 0.1, 1e27, 100, 5.0)
     assert ipr == pytest.approx(float(g["iprimakoff_1e27_100_5"]), rel=2 * F32)
     # 1-D photon table fails like the reference (README.md:90 quirk)
