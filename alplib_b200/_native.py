@@ -165,6 +165,8 @@ _SIGNATURES = {
     "alpk_table_sigma": ([_I, _P, _P, _I, _P, _U64, _P, _P], _I),
     "alpk_abs_sigma_mev": ([_P, _P, _I, _P, _U64, _P, _P], _I),
     "alpk_primakoff": ([_P, _P, _U64, _P, _P, _I, _D, _D, _D, _P, _P, _P], _I),
+    "alpk_primakoff_chain": ([_P, _P, _U64, _P, _P, _I, _D, _D, _D, C.POINTER(PropT), C.POINTER(EventT), _P, _P, _P, _P, _P, _P,
+                              _P, _P, _P, _P], _I),
     "alpk_compton_rows": ([_P, _P, _U64, _P, _P, _I, C.POINTER(ComptonT), _P, _P], _I),
     "alpk_compton_samples": ([_P, _U64, _U32, _P, C.POINTER(ComptonT), _P, _U64, _P, _P,
                               C.POINTER(PropT), _P, _P, _P, _P, C.POINTER(EventT), _P, _P, _P, _P, _I, _P, _P], _I),

@@ -270,6 +270,45 @@ primakoff_kernel(const double* __restrict__ eg, const double* __restrict__ phi, 
     }
 }
 
+// Primakoff production -> propagate -> decay event weights in one pass over the rows (one ALP sample per photon row): the
+// arithmetic is the separate kernels' (primakoff_kernel, propagate_sample[_fast] + prop_cast, decay_event_weight), the grid
+// and the accumulation order are decays_kernel's, so every array and the rate have the bits of the call-by-call schedule.
+template <bool FAST>
+__global__ void __launch_bounds__(kThreads)
+primakoff_chain_kernel(const double* __restrict__ eg, const double* __restrict__ phi, uint64_t n,
+                       const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
+                       double ma, double pref, double r02, PropConst pc, EventConst ec,
+                       double* __restrict__ out_e, double* __restrict__ out_f, float* __restrict__ d32o, float* __restrict__ s32o,
+                       double* __restrict__ d64o, double* __restrict__ s64o, double* __restrict__ event_w,
+                       double* __restrict__ partials) {
+    __shared__ double s_e[kMaxTable], s_xs[kMaxTable];
+    __shared__ double red[32];
+    stage_table(s_e, s_xs, log10_e, log10_xs, n_table);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = __ldg(eg + i);
+        const double xs = primakoff_sigma(e, ma, pref, r02);               // fluxes.py:139
+        const double br = xs / abs_sigma_mev(e, s_e, s_xs, n_table);       // :140
+        const double f = __ldg(phi + i) * br;                              // :142
+        double d64, s64;
+        if (FAST) propagate_sample_fast(e, f, pc, d64, s64); else propagate_sample(e, f, pc, d64, s64);
+        const float d32 = FAST ? prop_cast_fast(d64, pc) : prop_cast(d64, pc);
+        const float s32 = FAST ? prop_cast_fast(s64, pc) : prop_cast(s64, pc);
+        const double ev = decay_event_weight(e, d32, ec);
+        acc += ev;
+        if (out_e) out_e[i] = e;
+        if (out_f) out_f[i] = f;
+        if (d32o) d32o[i] = d32;
+        if (s32o) s32o[i] = s32;
+        if (d64o) d64o[i] = d64;
+        if (s64o) s64o[i] = s64;
+        if (event_w) event_w[i] = ev;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
 __global__ void __launch_bounds__(kThreads)
 compton_rows_kernel(const double* __restrict__ eg, const double* __restrict__ phi, uint64_t n,
                     const double* __restrict__ log10_e, const double* __restrict__ log10_xs, int n_table,
@@ -537,6 +576,30 @@ ALPK_EXPORT int alpk_primakoff(const double* e_gamma, const double* phi_gamma, u
     primakoff_kernel<<<grid_for(n_rows, kThreads, 4), kThreads, 0, (cudaStream_t)stream>>>(
         e_gamma, phi_gamma, n_rows, log10_e, log10_xs, n_table, ma, pref, r02, out_energy, out_flux);
     return check_launch("alpk_primakoff");
+}
+
+ALPK_EXPORT int alpk_primakoff_chain(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,
+                                     const double* log10_e, const double* log10_xs, int n_table,
+                                     double ma, double pref, double r02, const alpk_prop_t* h_prop, const alpk_event_t* h_ev,
+                                     double* out_energy, double* out_flux, float* decay_w32, float* scatter_w32,
+                                     double* decay_w64, double* scatter_w64, double* event_w, double* rate, double* scratch,
+                                     void* stream) {
+    if (n_table < 1 || n_table > kMaxTable) { set_error("alpk_primakoff_chain: table size %d not in [1,%d]", n_table, kMaxTable); return 2; }
+    if (!h_prop || !h_ev || !rate || !scratch) { set_error("alpk_primakoff_chain: null argument"); return 2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0) { cudaMemsetAsync(rate, 0, sizeof(double), st); return check_launch("alpk_primakoff_chain(memset)"); }
+    if (!e_gamma || !phi_gamma || !log10_e || !log10_xs) { set_error("alpk_primakoff_chain: null input"); return 2; }
+    const int grid = grid_for(n_rows, kThreads * 4, 8);                    // decays_kernel's grid: the same rate bits
+    if (h_prop->fast)
+        primakoff_chain_kernel<true><<<grid, kThreads, 0, st>>>(e_gamma, phi_gamma, n_rows, log10_e, log10_xs, n_table, ma, pref, r02,
+                                                               to_prop(h_prop), to_event(h_ev), out_energy, out_flux, decay_w32,
+                                                               scatter_w32, decay_w64, scatter_w64, event_w, scratch);
+    else
+        primakoff_chain_kernel<false><<<grid, kThreads, 0, st>>>(e_gamma, phi_gamma, n_rows, log10_e, log10_xs, n_table, ma, pref, r02,
+                                                                to_prop(h_prop), to_event(h_ev), out_energy, out_flux, decay_w32,
+                                                                scatter_w32, decay_w64, scatter_w64, event_w, scratch);
+    if (check_launch("alpk_primakoff_chain")) return 1;
+    return finalize_sum(scratch, grid, rate, st);
 }
 
 ALPK_EXPORT int alpk_compton_rows(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,

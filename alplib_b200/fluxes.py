@@ -399,6 +399,59 @@ class FluxPrimakoffIsotropic(AxionFlux):
         else:
             self._produce()
 
+    # ---- one-kernel schedule: production -> propagate -> decay weights + rate (alpk_primakoff_chain) ----------------------------
+    def _launch_chain(self, prop, ev, materialize, want_event_w):
+        d_eg, d_ph, n = self._inputs
+        rt = self._rt
+        with rt.activate():
+            rate = rt.empty(1)
+            E = F = d32 = s32 = d64 = s64 = evw = None
+            if materialize:
+                E, F = rt.empty(n), rt.empty(n)
+                d32, s32 = rt.empty(n, torch.float32), rt.empty(n, torch.float32)
+                if self.keep_f64:
+                    d64, s64 = rt.empty(n), rt.empty(n)
+            if want_event_w:
+                evw = rt.empty(n)
+            le, lx, nt = self.target_photon_xs.device_table(rt)
+            pref, r02 = P.primakoff_consts(self.gagamma, self.target_z)
+            N.call("alpk_primakoff_chain", N.ptr(d_eg), N.ptr(d_ph), n, N.ptr(le), N.ptr(lx), nt, float(self.ma), pref, r02,
+                   C.byref(prop), C.byref(ev), N.ptr(E), N.ptr(F), N.ptr(d32), N.ptr(s32), N.ptr(d64), N.ptr(s64), N.ptr(evw),
+                   N.ptr(rate), N.ptr(rt.scratch), rt.stream())
+        if materialize:
+            self._pending_production = None
+            self._pending_prop = None
+            self._set_production(E, F)
+            self._D32, self._S32, self._D64, self._S64 = d32, s32, d64, s64
+        return rate, evw
+
+    def _chain_pending(self):
+        return (getattr(self, "_inputs", None) is not None and self._pending_production is not None
+                and self._pending_prop is not None and self._E is None)
+
+    def _fused_decay_rate(self, ev):
+        """fused=True: the rate alone, nothing materialised."""
+        if not self._chain_pending():
+            return None
+        return self._launch_chain(self._pending_prop, ev, False, False)[0]
+
+    def _fused_decay_materialize(self, ev, want_event_w):
+        """"auto" schedule: one kernel that also writes every per-sample array."""
+        if not self._chain_pending():
+            return None
+        return self._launch_chain(self._pending_prop, ev, True, want_event_w)
+
+    def chain(self, days_exposure, threshold, new_coupling=None, materialize=True):
+        """One-kernel production -> propagate -> decays on the staged photon rows (simulate() first): returns (rate tensor,
+        event-weight tensor or None); with materialize=True also fills axion_energy / axion_flux / decay_axion_weight /
+        scatter_axion_weight on the device."""
+        if getattr(self, "_inputs", None) is None:
+            raise RuntimeError("simulate() must be called first")
+        g = self.gagamma if new_coupling is None else new_coupling
+        rescale = 1.0 if new_coupling is None else power(new_coupling/self.gagamma, 2)
+        prop = self._prop_params(W_gg(g, self.ma), rescale, self._geom_accept(), None)
+        return self._launch_chain(prop, P.event_params(days_exposure, threshold), materialize, materialize)
+
     def propagate(self, new_coupling=None, is_isotropic=True):
         geom = self._geom_accept() if is_isotropic else None
         if new_coupling is not None:

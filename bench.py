@@ -272,9 +272,7 @@ def run_gpu(args):
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_kev)]
 
     def one_pass(kpair=None):
-        prim._produce()
-        prim.propagate()
-        r1 = genP.decays_device(DAYS, THR)
+        r1, _ = prim.chain(DAYS, THR, materialize=True)    # Primakoff: production -> propagate -> decays in one kernel
         comp._launch_rows()
         r2, _ = comp.chain(DAYS, THR, materialize=True, events=kpair)   # events recorded right around the kernel launch
         if world == 1:
@@ -678,8 +676,7 @@ def strong_leg(A, D, rt, W, Ar, rank, world, barrier, max_over_ranks):
         return c, p, A.PhotonEventGenerator(p, Ar)
 
     def job(c, p, gp, merge):
-        p._produce(); p.propagate()
-        r1 = gp.decays_device(DAYS, THR)
+        r1, _ = p.chain(DAYS, THR, materialize=False)
         c._launch_rows()
         hist = rt.zeros(HIST_EDGES.shape[0] - 1)
         r2, _ = c.chain(DAYS, THR, materialize=False, hist_edges=d_edges, hist=hist)

@@ -136,6 +136,16 @@ int alpk_abs_sigma_mev(const double* log10_e, const double* log10_xs, int n_tabl
 int alpk_primakoff(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,
                    const double* log10_e, const double* log10_xs, int n_table,
                    double ma, double pref, double r02, double* out_energy, double* out_flux, void* stream);
+/* The same production fused with propagate (fluxes.py:43-65, 159-162) and the decay event weights + rate
+ * (generators.py:88-92) in ONE pass over the rows (the deferred schedule of FluxPrimakoffIsotropic + PhotonEventGenerator.decays):
+ * every output array is optional (NULL = not written); arrays and rate have the bits of alpk_primakoff + alpk_propagate +
+ * alpk_decays. */
+int alpk_primakoff_chain(const double* e_gamma, const double* phi_gamma, uint64_t n_rows,
+                         const double* log10_e, const double* log10_xs, int n_table,
+                         double ma, double pref, double r02, const alpk_prop_t* h_prop, const alpk_event_t* h_ev,
+                         double* out_energy, double* out_flux, float* decay_w32, float* scatter_w32,
+                         double* decay_w64, double* scatter_w64, double* event_w, double* rate, double* scratch,
+                         void* stream);
 
 /* ---- Compton production: fluxes.py:210-224, prod_xs.py:155-169 ------------------------------------------------------ */
 typedef struct {

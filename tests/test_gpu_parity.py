@@ -178,6 +178,40 @@ def test_compton_free_running_matches_oracle_sample_by_sample(A, ns):
     assert rate == pytest.approx(orate, rel=1e-6)
 
 
+def test_primakoff_fused_equals_unfused(A):
+    """The one-kernel Primakoff schedule (alpk_primakoff_chain: production -> propagate -> decay weights + rate) leaves the
+    arrays and the rate of the call-by-call schedule, bit for bit, in every arithmetic mode; fused=True materialises nothing
+    until an attribute is read."""
+    pf = _c2_flux(3000)
+    for precision in ("fast", "faithful", "fp32"):
+        res = {}
+        for fused in (False, "auto", True):
+            fl = A.FluxPrimakoffIsotropic(pf, A.Material("W"), axion_mass=0.1, axion_coupling=1e-5, fused=fused, keep_f64=(fused != True),
+                                          precision=precision, **GEOM)
+            fl.simulate(); fl.propagate(new_coupling=3e-5)
+            gen = A.PhotonEventGenerator(fl, A.Material("Ar"))
+            rate = gen.decays(100, 5.0)
+            if fused is True:
+                assert fl._E is None and fl._D32 is None            # reduce-only: nothing materialised yet
+            res[fused] = (rate, np.asarray(fl.axion_energy), np.asarray(fl.axion_flux), np.asarray(fl.decay_axion_weight),
+                          np.asarray(fl.scatter_axion_weight), np.asarray(gen.decay_weights))
+            if fused == "auto":
+                assert np.array_equal(fl.decay_axion_weight_f64, ref_f64)
+            if fused is False:
+                ref_f64 = np.asarray(fl.decay_axion_weight_f64)
+        for fused in ("auto", True):
+            assert res[fused][0] == res[False][0], (precision, fused)
+            for a, b in zip(res[fused][1:], res[False][1:]):
+                assert a.shape == b.shape and np.array_equal(a, b), (precision, fused)
+        # explicit one-kernel call
+        fl = A.FluxPrimakoffIsotropic(pf, A.Material("W"), axion_mass=0.1, axion_coupling=1e-5, precision=precision, **GEOM)
+        fl.simulate()
+        r, evw = fl.chain(100, 5.0, new_coupling=3e-5)
+        assert float(r.item()) == res[False][0] and np.array_equal(evw.cpu().numpy(), res[False][5])
+        r2, none = fl.chain(100, 5.0, new_coupling=3e-5, materialize=False)
+        assert none is None and float(r2.item()) == res[False][0]
+
+
 def test_compton_fused_equals_unfused(A):
     """One-kernel chain (materialising and reduce-only) vs the three separate launches: identical samples."""
     pf = _c2_flux(300)
