@@ -201,14 +201,26 @@ chain_rows_kernel(const ChainArgs<Prod> a, const RowsGeom geo) {
                     hw[0] += same ? hw[1] : 0.0;
                     double* const c0 = hb[0] >= 0 ? my_col + (uint32_t)hb[0] * hcols : my_trash;
                     double* const c1 = (hb[1] >= 0 && !same) ? my_col + (uint32_t)hb[1] * hcols : my_trash;
-                    for (uint32_t ph = 0; ph < hphases; ++ph) {
-                        const bool act = (lane & (hphases - 1u)) == ph;
+                    // read-modify-write of the lane's column cells; lanes whose turn it is not add into their trash cell
+                    auto phase = [&](bool act) {
                         double* const q0 = act ? c0 : my_trash;
                         double* const q1 = act ? c1 : my_trash;
                         const double v0 = *q0, v1 = *q1;
                         *q0 = v0 + hw[0];
                         *q1 = v1 + hw[1];
+                    };
+                    if (hphases == 1) {                              // a private column per lane: no turns (warp-uniform branches)
+                        phase(true);
+                    } else if (hphases == 2) {
+                        phase((lane & 1u) == 0u);
                         __syncwarp();
+                        phase((lane & 1u) == 1u);
+                        __syncwarp();
+                    } else {
+                        for (uint32_t ph = 0; ph < hphases; ++ph) {
+                            phase((lane & (hphases - 1u)) == ph);
+                            __syncwarp();
+                        }
                     }
                 } else {
 #pragma unroll

@@ -119,8 +119,13 @@ __device__ __forceinline__ BinGuessF to_float_guess(const BinGuess& g, const dou
 }
 
 __device__ __forceinline__ int find_bin_pairs(double x, const double2* pairs, int nb, const BinGuessF& g) {
-    const float xf = (float)x;
-    const float v = g.mode == 2 ? __log2f(xf) : xf;
+    float v = (float)x;
+    if (g.mode == 2) {                    // (a real, warp-uniform branch: linear edges do not pay for the logarithm)
+#if defined(__CUDA_ARCH__)
+        asm volatile("");
+#endif
+        v = __log2f(v);
+    }
     int b = __float2int_rd(fmaf(v, g.scale, g.off));
     b = max(0, min(b, nb - 1));
     const double2 e = pairs[b];
