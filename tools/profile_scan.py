@@ -59,20 +59,31 @@ for key, n_bins, ns in (("c5", 1000, 100), ("large", 10_000, 1000)):
         t_d2h = (time.perf_counter() - t0) / reps
         entry = {"call_ms": t_call * 1e3, "host_queue_ms": t_queue * 1e3, "device_ms": t_dev * 1e3, "d2h_map_ms": t_d2h * 1e3}
         if world > 1:
-            # (4) the collective alone, ranks aligned by a barrier first: NCCL + torch launch latency without rank skew
+            # (4) the gather alone, ranks aligned by a barrier first (launch latency without rank skew): the peer-window kernel
+            # the scan uses on one node, and NCCL's all_gather_into_tensor beside it
+            from alplib_b200.peer import peer_group
+            pg = peer_group(None, d)
             n_loc = (200 + world - 1) // world
             loc = torch.zeros((n_loc, 200), dtype=torch.float64, device=d.device)
             flat = torch.empty((world * n_loc, 200), dtype=torch.float64, device=d.device)
-            for _ in range(3):
-                dist.all_gather_into_tensor(flat, loc)
-            t_coll = 0.0
-            for _ in range(reps):
-                dist.barrier(); torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                dist.all_gather_into_tensor(flat, loc)
-                torch.cuda.synchronize()
-                t_coll += time.perf_counter() - t0
-            entry["all_gather_ms"] = t_coll / reps * 1e3
+            mine = torch.zeros((len(range(rank, 200, world)), 200), dtype=torch.float64, device=d.device)
+
+            def coll(fn):
+                for _ in range(3):
+                    fn()
+                t_coll = 0.0
+                for _ in range(reps):
+                    dist.barrier(); torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    fn()
+                    torch.cuda.synchronize()
+                    t_coll += time.perf_counter() - t0
+                return t_coll / reps * 1e3
+            entry["nccl_all_gather_ms"] = coll(lambda: dist.all_gather_into_tensor(flat, loc))
+            entry["all_gather_ms"] = entry["nccl_all_gather_ms"]
+            if pg is not None:
+                entry["peer_all_gather_ms"] = coll(lambda: pg.all_gather_rows(mine, rank, world, 200))
+                entry["all_gather_ms"] = entry["peer_all_gather_ms"]
             # (5) device time of every rank's share: the slowest rank sets the pace of the collective
             tt = torch.tensor([t_dev * 1e3], dtype=torch.float64, device=d.device)
             allt = torch.empty(world, dtype=torch.float64, device=d.device)
@@ -85,4 +96,6 @@ for key, n_bins, ns in (("c5", 1000, 100), ("large", 10_000, 1000)):
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
+    from alplib_b200 import peer
+    peer.reset()
     dist.destroy_process_group()
