@@ -189,7 +189,9 @@ class Runtime:
         k = self.__dict__["_pin_next"] = (self.__dict__.get("_pin_next", -1) + 1) % len(ring)
         slot = ring[k]
         if slot is None or slot[0].shape[0] < nbytes:
-            buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, pin_memory=True)
+            # (at least 1 MiB: a ring slot that had only served small uploads would otherwise be re-allocated -- cudaHostAlloc,
+            # ~0.3 ms -- the first time a 320 KB rate map or flux table comes its way)
+            buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, pin_memory=True)
             slot = ring[k] = (buf, torch.cuda.Event(), buf.numpy())
         else:
             slot[1].synchronize()                       # previous copy out of this slot has completed

@@ -765,7 +765,8 @@ def scan_leg(A, W, n_bins, n_samples, reps, barrier, max_over_ranks):
         mp_ = scan_rates_distributed("primakoff", pf_scan, W, ma_grid, g_grid, **kw)
         return mc, mp_
 
-    scan_once()
+    for _ in range(3):
+        scan_once()
     barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
