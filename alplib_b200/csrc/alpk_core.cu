@@ -437,15 +437,21 @@ ALPK_EXPORT int alpk_stage_flux_rows(const double* h_table, uint64_t n_rows, uin
     double* w = (double*)((char*)h_pinned + cap);
     uint32_t* ids = (uint32_t*)((char*)h_pinned + 2 * cap);
     const double me = alp::kME, me2 = alp::kME * alp::kME;
+    // branch-free compaction: every row is written at the cursor, the cursor advances only for kept rows (the staging
+    // block has room for all n_rows)
     uint64_t k = 0;
-    for (uint64_t r = 0; r < n_rows; ++r) {
-        const double en = h_table[r * row_stride];
-        bool drop;
-        if (rule == 0) drop = en < cut;                                   // fluxes.py:136   if photon[0] < self.ma: return
-        else drop = ((2 * me) * en + me2) < cut;                          // :214-215  s < (M_E + ma)**2
-        if (drop) continue;
-        e[k] = en; w[k] = h_table[r * row_stride + 1]; ids[k] = (uint32_t)r + row_offset;
-        ++k;
+    if (rule == 0) {
+        for (uint64_t r = 0; r < n_rows; ++r) {
+            const double en = h_table[r * row_stride];
+            e[k] = en; w[k] = h_table[r * row_stride + 1]; ids[k] = (uint32_t)r + row_offset;
+            k += !(en < cut);                                             // fluxes.py:136   if photon[0] < self.ma: return
+        }
+    } else {
+        for (uint64_t r = 0; r < n_rows; ++r) {
+            const double en = h_table[r * row_stride];
+            e[k] = en; w[k] = h_table[r * row_stride + 1]; ids[k] = (uint32_t)r + row_offset;
+            k += !(((2 * me) * en + me2) < cut);                          // :214-215  s < (M_E + ma)**2
+        }
     }
     *h_n_kept = k;
     if (k == 0) return 0;

@@ -48,6 +48,31 @@ def test_struct_layouts_match_header():
     assert N.EventT.threshold.offset == 16
 
 
+def test_peer_window_abi(libpath):
+    """alpk_peer_t mirrors the header; the window size helper needs no device."""
+    hdr = open(os.path.join(ROOT, "include", "alpk.h")).read()
+    assert int(re.search(r"#define ALPK_PEER_MAX_RANKS (\d+)", hdr).group(1)) == N.PEER_MAX_RANKS
+    assert int(re.search(r"#define ALPK_PEER_MAX_PARTS (\d+)", hdr).group(1)) == N.PEER_MAX_PARTS
+    assert int(re.search(r"#define ALPK_PEER_HANDLE_BYTES (\d+)", hdr).group(1)) == N.PEER_HANDLE_BYTES
+    assert ctypes.sizeof(N.PeerT) == N.PEER_MAX_RANKS * 8 + 4 + 4 + 8 and N.PeerT.capacity.offset == N.PEER_MAX_RANKS * 8 + 8
+    L = N.lib()
+    assert L.alpk_peer_window_bytes(1000) == 512 + 2 * 1000 * 8
+    # a merge without mapped windows is refused on the host, before any launch
+    peer = N.PeerT(rank=0, n_ranks=2, capacity=1000)
+    ptrs = (ctypes.c_void_p * 1)(0)
+    lens = (ctypes.c_uint32 * 1)(4)
+    assert L.alpk_peer_all_reduce_sum(ctypes.byref(peer), ptrs, lens, 1, None, 0, None) == 2
+    assert b"not mapped" in L.alpk_last_error()
+
+
+def test_peer_group_not_used_without_nccl():
+    """Single process / no process group: merges stay local, peer_group() is None (the gloo tiers use torch.distributed)."""
+    import torch
+    from alplib_b200 import peer
+    assert peer.peer_group(None) is None
+    assert peer.peer_group(None, torch.zeros(1)) is None
+
+
 def test_library_contains_sm100a_code_only(libpath):
     out = os.popen(f"cuobjdump -lelf {libpath} 2>/dev/null").read()
     if out:
