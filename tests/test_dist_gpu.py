@@ -73,9 +73,14 @@ def test_sharded_single_job_equals_one_rank(tmp_path):
     procs = [ctx.Process(target=_run_rank, args=(r, world, port, backend, str(tmp_path))) for r in range(world)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout=280)
-        assert p.exitcode == 0
+    try:
+        for p in procs:
+            p.join(timeout=280)
+            assert p.exitcode == 0
+    finally:                                    # never leave a rank behind (it would keep the GPU busy and block interpreter exit)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     import alplib_b200 as A
     W, Ar = A.Material("W"), A.Material("Ar")
     one = A.FluxComptonIsotropic(_pf(), W, **KW, **GEOM)
@@ -122,9 +127,14 @@ def test_scan_example_distributed_equals_single_process(tmp_path):
     procs = [ctx.Process(target=_run_example_rank, args=(r, 2, port, str(tmp_path))) for r in range(2)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout=280)
-        assert p.exitcode == 0
+    try:
+        for p in procs:
+            p.join(timeout=280)
+            assert p.exitcode == 0
+    finally:                                    # never leave a rank behind (it would keep the GPU busy and block interpreter exit)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         os.environ.pop(k, None)

@@ -103,9 +103,14 @@ def test_peer_window_merges(tmp_path):
     procs = [ctx.Process(target=_run_rank, args=(r, world, port, backend, str(tmp_path))) for r in range(world)]
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout=280)
-        assert p.exitcode == 0
+    try:
+        for p in procs:
+            p.join(timeout=280)
+            assert p.exitcode == 0
+    finally:                                    # never leave a rank behind (it would keep the GPU busy and block interpreter exit)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     z = [np.load(os.path.join(str(tmp_path), f"peer{r}.npz")) for r in range(world)]
     # fixed-order sum: rank 0's values first -- exactly the left-to-right NumPy sum, identical on both ranks
     cat = [np.concatenate([_rank_data(r, 1), _rank_data(r + 10, 1), _rank_data(r + 20, 50)]) for r in range(world)]
