@@ -184,14 +184,21 @@ class Runtime:
                 for (a, dt), o in zip(arrays, offs)]
 
     def _pin_slot(self, nbytes):
-        """Next pinned staging slot of the ring (>= nbytes), safe to overwrite: (tensor, event, numpy view)."""
-        ring = self.__dict__.setdefault("_pin_ring", [None] * 8)
+        """Next pinned staging slot of the ring (>= nbytes), safe to overwrite: (tensor, event, numpy view).  The ring's 8
+        slots of 1 MiB are carved out of ONE pinned allocation at first use (eight separate cudaHostAlloc calls cost ~0.5 ms
+        each and used to land in the first timed calls of a short run); a slot is re-allocated only for a larger request."""
+        ring = self.__dict__.get("_pin_ring")
+        if ring is None:
+            base = torch.empty(8 << 20, dtype=torch.uint8, pin_memory=True)
+            ring = self.__dict__["_pin_ring"] = []
+            for k in range(8):
+                buf = base[k << 20:(k + 1) << 20]
+                ring.append((buf, torch.cuda.Event(), buf.numpy()))
         k = self.__dict__["_pin_next"] = (self.__dict__.get("_pin_next", -1) + 1) % len(ring)
         slot = ring[k]
-        if slot is None or slot[0].shape[0] < nbytes:
-            # (at least 1 MiB: a ring slot that had only served small uploads would otherwise be re-allocated -- cudaHostAlloc,
-            # ~0.3 ms -- the first time a 320 KB rate map or flux table comes its way)
-            buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        if slot[0].shape[0] < nbytes:
+            slot[1].synchronize()
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True)
             slot = ring[k] = (buf, torch.cuda.Event(), buf.numpy())
         else:
             slot[1].synchronize()                       # previous copy out of this slot has completed

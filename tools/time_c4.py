@@ -14,7 +14,7 @@ pos = np.stack([E, 0.3 * 1e14 * np.exp(-E / 2e4)], axis=1)
 DUNE = dict(det_dist=574.0, det_length=5.0, det_area=21.0)
 
 
-def timeit(fn, n=5, warm=2):
+def timeit(fn, n=20, warm=8):
     for _ in range(warm):
         r = fn()
     torch.cuda.synchronize()
