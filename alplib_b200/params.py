@@ -94,10 +94,19 @@ def iprimakoff_consts(ma, g, z, r0=R0_SCREEN):
     return (N.C.c_double * 6)(float(ma), float(ma ** 2), pref, r02, 0.0, 0.0)
 
 
+_GL = None
+
+
 def gauss_legendre():
-    """Nodes/weights of the 32-point Gauss-Legendre rule used for the track-length integral (fmath.py:33-36)."""
-    x, w = np.polynomial.legendre.leggauss(N.GL_POINTS)
-    return np.ascontiguousarray(x), np.ascontiguousarray(w)
+    """Nodes/weights of the 32-point Gauss-Legendre rule used for the track-length integral (fmath.py:33-36).  Computed
+    once: numpy's leggauss (companion-matrix eigenvalues + Newton step) costs 0.4 ms, more than the kernels it feeds."""
+    global _GL
+    if _GL is None:
+        x, w = np.polynomial.legendre.leggauss(N.GL_POINTS)
+        x, w = np.ascontiguousarray(x), np.ascontiguousarray(w)
+        x.setflags(write=False); w.setflags(write=False)
+        _GL = (x, w)
+    return _GL
 
 
 def brem_params(ma, g, z, rad_length, n_samples, boson_type="pseudoscalar", max_t=5.0, use_track_length=True, fast=False,
