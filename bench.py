@@ -660,7 +660,7 @@ def strong_leg(A, D, rt, W, Ar, rank, world, barrier, max_over_ranks):
     import torch
     from alplib_b200.peer import peer_group
     merge_kind = ("one libalpk kernel per rank over NVLink peer memory (alpk_peer_all_reduce_sum: push, signal, wait, fixed-order sum)"
-                  if peer_group(None, rt.empty(1)) is not None else "one NCCL all_reduce")
+                  if peer_group(None, rt.empty(1)) is not None else ("none (one rank)" if world == 1 else "one NCCL all_reduce"))
     out = {"collective": "merge of [2 rates || 50 histogram bins] per job (dist.merged_rates_and_hists): " + merge_kind,
            "sharding": "contiguous blocks of KEPT rows per rank (dist.shard_flux), Philox keys = global row ids"}
     d_edges = rt.upload(HIST_EDGES)
