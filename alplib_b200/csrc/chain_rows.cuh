@@ -342,7 +342,9 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
     size_t smem = 0;
     geo.hist_cols = 0;
     if (a.hist) {
-        if (!hist_rows_mode()) return -1;
+        // the fused spectrum of this kernel is the event-weighted one (stage 2: what flux.chain() asks for); histograms of the
+        // production flux or of the decay weights alone stay with the tile kernel
+        if (!hist_rows_mode() || stage != 2) return -1;
         uint32_t cols = 32;
         while (cols >= 4 && hist_rows_doubles(a.n_edges, cols) * sizeof(double) > (size_t)kRowsHistSmem) cols >>= 1;
         geo.hist_cols = cols >= 4 ? cols : 0;
@@ -363,13 +365,13 @@ int launch_chain_rows(const char* what, ChainArgs<Prod>& a, int stage, bool stan
 #define ALPK_ROWS_LAUNCH_R(S, O, R, H) { if (sh) ALPK_ROWS_LAUNCH_K(S, O, true, R, H) else ALPK_ROWS_LAUNCH_K(S, O, false, R, H) }
 #define ALPK_ROWS_LAUNCH(S, O, H) { if (a.rounds == 7) ALPK_ROWS_LAUNCH_R(S, O, 7, H) else ALPK_ROWS_LAUNCH_R(S, O, 10, H) }
 #define ALPK_ROWS_CASE(S)                                                         \
-    if (a.hist) { if (none) ALPK_ROWS_LAUNCH(S, kOutNone, true)                   \
-                  else ALPK_ROWS_LAUNCH(S, kOutGeneric, true) }                   \
-    else if (standard) ALPK_ROWS_LAUNCH(S, kOutStandard, false)                   \
+    if (standard) ALPK_ROWS_LAUNCH(S, kOutStandard, false)                        \
     else if (S == 2 && noevents) ALPK_ROWS_LAUNCH(S, kOutNoEvents, false)         \
     else if (none) ALPK_ROWS_LAUNCH(S, kOutNone, false)                           \
     else ALPK_ROWS_LAUNCH(S, kOutGeneric, false)
-    if (stage == 0) { ALPK_ROWS_CASE(0) } else if (stage == 1) { ALPK_ROWS_CASE(1) } else { ALPK_ROWS_CASE(2) }
+    if (a.hist) {                                  // (stage 2 only: checked above)
+        if (none) ALPK_ROWS_LAUNCH(2, kOutNone, true) else ALPK_ROWS_LAUNCH(2, kOutGeneric, true)
+    } else if (stage == 0) { ALPK_ROWS_CASE(0) } else if (stage == 1) { ALPK_ROWS_CASE(1) } else { ALPK_ROWS_CASE(2) }
 #undef ALPK_ROWS_LAUNCH
 #undef ALPK_ROWS_LAUNCH_R
 #undef ALPK_ROWS_LAUNCH_K
