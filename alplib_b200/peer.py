@@ -158,7 +158,16 @@ def peer_group(group=None, tensor=None):
         return None
     if tensor is not None and not tensor.is_cuda:
         return None
-    key = id(group) if group is not None else 0
+    if group is None:
+        # the default group is a new object after destroy_process_group() + init_process_group(): windows of a group that no
+        # longer exists are released here
+        key = ("world", id(dist.distributed_c10d._get_default_group()))
+        for k in [k for k in _groups if isinstance(k, tuple) and k[0] == "world" and k != key]:
+            stale = _groups.pop(k)
+            if stale is not None:
+                stale.close()
+    else:
+        key = id(group)
     if key not in _groups:
         try:
             _groups[key] = PeerGroup(group)

@@ -146,3 +146,44 @@ def test_scan_example_distributed_equals_single_process(tmp_path):
         assert np.array_equal(z["compton"], compton) and np.array_equal(z["primakoff"], primakoff)
     m, lim = limits["photon coupling (Primakoff)"]
     assert m.shape == lim.shape and m.shape[0] > 10 and m[0] == 0.0
+
+
+def _run_sharded_example_rank(rank, world, port, outdir):
+    import runpy
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ns = runpy.run_path(os.path.join(root, "examples", "ex_sharded_beam_dump.py"), run_name="sharded_example")
+    rc, rp, spec = ns["main"]()
+    np.savez(os.path.join(outdir, f"sharded{rank}.npz"), rc=rc, rp=rp, spec=spec)
+
+
+@pytest.mark.timeout(300)
+def test_sharded_example_equals_single_process(tmp_path):
+    """examples/ex_sharded_beam_dump.py under 2 ranks == the single-process run (rates to 1e-12, spectrum to 1e-10), and both
+    ranks hold the same merged bits."""
+    import runpy
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_run_sharded_example_rank, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        for p in procs:
+            p.join(timeout=280)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        os.environ.pop(k, None)
+    ns = runpy.run_path(os.path.join(root, "examples", "ex_sharded_beam_dump.py"), run_name="sharded_example")
+    rc, rp, spec = ns["main"]()
+    z = [np.load(os.path.join(str(tmp_path), f"sharded{r}.npz")) for r in range(2)]
+    assert rc > 0 and rp > 0 and spec.sum() == pytest.approx(rc, rel=1e-9)
+    for r in range(2):
+        assert float(z[r]["rc"]) == pytest.approx(rc, rel=1e-12) and float(z[r]["rp"]) == pytest.approx(rp, rel=1e-12)
+        assert np.allclose(z[r]["spec"], spec, rtol=1e-10, atol=0.0)
+    assert np.array_equal(z[0]["spec"], z[1]["spec"]) and float(z[0]["rc"]) == float(z[1]["rc"])
