@@ -108,10 +108,30 @@ ALP_HD double u53(uint32_t a, uint32_t b) {
 // ---- branch-free reciprocal / reciprocal square root for the fast mode --------------------------------------------
 // Hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-22 relative) + one cubically convergent correction: ~1 ulp for normal,
 // finite, non-zero arguments; no special-case branch (callers guard the argument range), so several of them interleave.
+#if !defined(__CUDA_ARCH__) && defined(ALP_EMULATE_APPROX_SEED)
+// tests/hostcheck only: the hardware seeds (MUFU.RCP64H / RSQ64H, ~2^-22 relative) emulated by the exact result cut to 21
+// mantissa bits, so that the CPU test tier runs the DEVICE correction steps on a seed at least as bad as the hardware's.
+static inline double alp_seed21(double v) {
+    uint64_t b;
+    __builtin_memcpy(&b, &v, 8);
+    b &= ~((1ull << 31) - 1ull);
+    __builtin_memcpy(&v, &b, 8);
+    return v;
+}
+#define ALP_HOST_SEEDS 1
+#else
+#define ALP_HOST_SEEDS 0
+#endif
+
 ALP_HD double rcp_fast(double a) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    e = fma(e, e, e);
+    return fma(y, e, y);
+#elif ALP_HOST_SEEDS
+    const double y = alp_seed21(1.0 / a);
     double e = fma(-a, y, 1.0);
     e = fma(e, e, e);
     return fma(y, e, y);
@@ -127,6 +147,11 @@ ALP_HD double rsqrt_fast(double d) {
     const double h = fma(-d, y * y, 1.0);
     const double p = fma(h, 0.375, 0.5);
     return fma(p, y * h, y);
+#elif ALP_HOST_SEEDS
+    const double y = alp_seed21(1.0 / sqrt(d));
+    const double h = fma(-d, y * y, 1.0);
+    const double p = fma(h, 0.375, 0.5);
+    return fma(p, y * h, y);
 #else
     return 1.0 / sqrt(d);
 #endif
@@ -139,6 +164,9 @@ ALP_HD double rcp_fast1(double a) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     return fma(y, fma(-a, y, 1.0), y);
+#elif ALP_HOST_SEEDS
+    const double y = alp_seed21(1.0 / a);
+    return fma(y, fma(-a, y, 1.0), y);
 #else
     return 1.0 / a;
 #endif
@@ -148,6 +176,10 @@ ALP_HD double rsqrt_fast1(double d) {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double h = fma(-d, y * y, 1.0);
+    return fma(y * 0.5, h, y);
+#elif ALP_HOST_SEEDS
+    const double y = alp_seed21(1.0 / sqrt(d));
     const double h = fma(-d, y * y, 1.0);
     return fma(y * 0.5, h, y);
 #else

@@ -37,20 +37,26 @@ def max_rel(a, b, floor=0.0):
     return float(np.max(d / s))
 
 
-@pytest.fixture(scope="session")
-def hostcheck():
-    """Host build (g++, -ffp-contract=off) of the kernels' per-sample arithmetic -- test infrastructure only."""
+@pytest.fixture(scope="session", params=["libm", "seed21"])
+def hostcheck(request):
+    """Host build (g++, -ffp-contract=off) of the kernels' per-sample arithmetic -- test infrastructure only.  Two flavours:
+    "libm" evaluates the fast mode's reciprocal / reciprocal square root exactly (1/a, 1/sqrt(d)); "seed21" runs the DEVICE
+    algorithm -- the Newton correction steps of rcp_fast / rsqrt_fast -- on a seed cut to 21 mantissa bits, a little worse
+    than the hardware's MUFU.RCP64H / RSQ64H, so the 1e-9 bar of the fast mode is checked on the CPU for the code the GPU runs."""
     d = os.path.join(ROOT, "tests", "hostcheck")
-    so = os.path.join(d, "libhostcheck.so")
+    seed = request.param == "seed21"
+    so = os.path.join(d, "libhostcheck_seed21.so" if seed else "libhostcheck.so")
     deps = [os.path.join(d, "hostcheck.cpp"), os.path.join(d, "hostcheck2.inc"),
             os.path.join(ROOT, "alplib_b200", "csrc", "alp_math.cuh"),
             os.path.join(ROOT, "alplib_b200", "csrc", "alp_math2.cuh"),
             os.path.join(ROOT, "alplib_b200", "csrc", "alp_math3.cuh"),
             os.path.join(ROOT, "alplib_b200", "csrc", "alp_math4.cuh"), os.path.join(ROOT, "include", "alpk.h")]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so,
-                               os.path.join(d, "hostcheck.cpp")])
-    return ctypes.CDLL(so)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared"]
+                              + (["-DALP_EMULATE_APPROX_SEED"] if seed else []) + ["-o", so, os.path.join(d, "hostcheck.cpp")])
+    lib = ctypes.CDLL(so)
+    lib.flavour = request.param
+    return lib
 
 
 def dptr(a):

@@ -558,3 +558,27 @@ def test_propagate_fast_regimes(hostcheck, regime):
         assert np.all(s64 == 0) and np.all(p["scatter_w64"] == 0)
     if regime == "short_lived":
         assert 0 < np.count_nonzero(s64 == 0) < e.shape[0]          # both the exact-zero and the regular branch are exercised
+
+
+def test_seed21_flavour_runs_the_device_corrections():
+    """The two host builds differ only in how the fast mode's reciprocal / reciprocal square root are formed: "seed21" must
+    really go through the Newton steps on a truncated seed (results differ from the exact ones) and stay far inside 1e-9."""
+    import ctypes
+    import os
+    import subprocess
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostcheck")
+    libs = {}
+    for name, flags in (("libhostcheck.so", []), ("libhostcheck_seed21.so", ["-DALP_EMULATE_APPROX_SEED"])):
+        so = os.path.join(d, name)
+        if not os.path.exists(so):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared"] + flags
+                                  + ["-o", so, os.path.join(d, "hostcheck.cpp")])
+        libs[name] = ctypes.CDLL(so)
+    rng = np.random.default_rng(5)
+    e = 1.5 * (1 + 10 ** rng.uniform(-6, 3, 4000))
+    w = 10 ** rng.uniform(-5, 8, e.shape[0])
+    prop = P.prop_params(1.5, 1e-18, 1.0, 4.0, 0.2, geom_accept=GA, fast=True)
+    out = {k: run_propagate(lib, e, w, prop) for k, lib in libs.items()}
+    a, b = out["libhostcheck.so"][3], out["libhostcheck_seed21.so"][3]          # float64 scatter weights
+    rel = np.abs(a - b) / np.abs(a)
+    assert 1e-17 < rel.max() < 1e-11, rel.max()
