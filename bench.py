@@ -14,14 +14,16 @@ A "pass" is one run of that chain over the whole spectrum; a "sample" is one wei
 + propagate + decay weighting.  One pass of the fused kernel takes ~0.45 ms, so a "step" is PASSES_PER_STEP = 128
 back-to-back passes: `--steps 20` times 2560 passes, a sustained region of > 1 s (clocks, power and throttle reasons are
 sampled over it).  With N GPUs every rank runs the full spectrum as an independent replica with its own Philox row keys
-(weak scaling: N x the Monte-Carlo statistics of the same job) and the per-pass rates are merged with one NCCL all-reduce.
+(weak scaling: N x the Monte-Carlo statistics of the same job) and the per-pass rates are merged by one peer-window kernel per
+rank over NVLink (alplib_b200.peer; an NCCL all-reduce when the ranks do not share a node), joined one pass later.
 
 `value`: samples/s with the flux tables resident in HBM, every per-sample output (E, flux, decay_w, scatter_w, event
 weight: 32 B/sample) written to HBM by the fused kernel.  `e2e`: the same chain through the public drop-in classes from
 HOST arrays (H2D of the flux tables and D2H of the rates inside the timed region, every pass).  Extra keys: `e2e_eager`,
-`e2e_fused` (other schedules), `e2e_host_arrays` (per-sample arrays copied to NumPy), `c3` (BASELINE config 3: 1e8 decay
+`e2e_fused` (other schedules), `e2e_pipelined` (rates read one pass late through decays_async()), `e2e_host_arrays` (per-sample arrays copied to NumPy), `c3` (BASELINE config 3: 1e8 decay
 events), `c4` (config 4: e+- channels on graphite), `scan` / `scan_large` (config 5 and a 100x larger scan), `strong`
-(one row-sharded job with the merged [rates || histogram] all-reduce), `roofline`, `cpu_baseline`.
+(one row-sharded job with the merged [rates || histogram] all-reduce, host-driven and as a CUDA graph), `roofline`,
+`cpu_baseline`.
 """
 import argparse
 import json
